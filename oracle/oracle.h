@@ -1,0 +1,67 @@
+/* ORACLE / TEST INFRASTRUCTURE ONLY.
+ * C ABI of the CPU oracle (liboracle.so) and of the compiled reference
+ * (oracle/_ref/libref_rrtconnect.so exports ref_rrtc_solve with the signature of
+ * orc_rrtc_solve).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load these libraries.
+ * Parity unpinned upstream: the reference ships no tests, fixtures or golden
+ * vectors; the oracle is pinned instead against the
+ * reference's own RRTConnect.cpp compiled here (oracle/_ref) and against
+ * hand-computed known answers (tests/test_oracle_*.py). */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- nearest neighbours (NearestNeighborsLinear / findKnnNodes semantics) ---- */
+/* pts: n x dim row-major; queries: nq x dim.  Candidates of query i are the
+ * points with index >= lo[i] (lo == NULL: all).  Results ordered by
+ * (sqrt-distance, index); idx padded with 0xFFFFFFFF, dist with +inf. */
+int orc_knn(const double *pts, uint64_t n, int dim, const double *queries, uint64_t nq, int k,
+            const uint32_t *lo, uint32_t *idx_out, double *dist_out, int nthreads);
+double orc_distance(const double *a, const double *b, int dim);
+void orc_interpolate(const double *from, const double *to, double t, int dim, double *out);
+
+/* ---- synthetic world ---- */
+void *orc_world_create(int dof, const double *dh /* dof x 5: a,d,cos(alpha),sin(alpha),theta0 */,
+                       int n_link_spheres, const int32_t *sphere_link, const double *sphere_xyzr,
+                       int n_obs_spheres, const double *obs_spheres /* x4 */, int n_obs_boxes,
+                       const double *obs_boxes /* x6 */);
+void orc_world_destroy(void *world);
+double orc_clearance(const void *world, const double *q);
+void orc_fk(const void *world, const double *q, double *pose12, double *sphere_centres);
+
+/* ---- edge validation ---- */
+enum { ORC_MODE_OMPL_DISCRETE = 0, ORC_MODE_NNF_ALPHA = 1 };
+/* mode 0: DiscreteMotionValidator::checkMotion(from,to) with longest valid segment
+ *         `resolution` (check_first != 0: isValid(from) && checkMotion(from,to)).
+ * mode 1: NNFrechet::evaluateEdge with check resolution `resolution`; valid = !inCollision.
+ * min_clearance (nullable): minimum clearance over ALL tested states (no early exit).
+ * n_tested (nullable): number of states in the tested set. */
+int orc_check_motion_batch(const void *world, const double *from, const double *to, uint64_t n,
+                           double resolution, int mode, int check_first, uint8_t *valid,
+                           double *min_clearance, uint32_t *n_tested, int nthreads);
+int orc_is_valid_batch(const void *world, const double *q, uint64_t n, uint8_t *valid,
+                       double *clearance, int nthreads);
+
+/* ---- sample stream ---- */
+double orc_sample_uniform(uint64_t seed, uint64_t query, uint64_t it, uint64_t dim, double lo, double hi);
+
+/* ---- RRTConnect (port in liboracle.so; ref_rrtc_solve in oracle/_ref has the same signature) ---- */
+typedef struct {
+  int32_t status;        /* ompl::base::PlannerStatus::StatusType */
+  uint32_t iterations;   /* uniform samples drawn */
+  uint32_t n_start, n_goal;
+  uint32_t path_len;
+  uint32_t overflow;     /* 1 if an output buffer was too small */
+} orc_rrtc_result;
+int orc_rrtc_solve(const void *world, int dim, const double *lo, const double *hi, const double *start,
+                   const double *goal, double range, int ext_first, int ext_second,
+                   double resolution_fraction, uint64_t seed, uint64_t query_id, uint32_t max_iters,
+                   uint32_t max_nodes, uint32_t max_path, orc_rrtc_result *res, double *start_states,
+                   int32_t *start_parent, double *goal_states, int32_t *goal_parent, double *path);
+#ifdef __cplusplus
+}
+#endif
+#endif

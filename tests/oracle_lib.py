@@ -1,0 +1,171 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so) and the compiled reference
+(oracle/_ref/libref_rrtconnect.so).  TEST INFRASTRUCTURE: imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+c_dp = C.POINTER(C.c_double)
+c_u32p = C.POINTER(C.c_uint32)
+c_i32p = C.POINTER(C.c_int32)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class RrtcResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_uint32), ("n_start", C.c_uint32),
+                ("n_goal", C.c_uint32), ("path_len", C.c_uint32), ("overflow", C.c_uint32)]
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+_RRTC_ARGS = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int, C.c_int, C.c_double,
+              C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RrtcResult), c_dp,
+              c_i32p, c_dp, c_i32p, c_dp]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_knn.argtypes = [c_dp, C.c_uint64, C.c_int, c_dp, C.c_uint64, C.c_int, c_u32p, c_u32p, c_dp,
+                              C.c_int]
+        L.orc_distance.argtypes = [c_dp, c_dp, C.c_int]
+        L.orc_distance.restype = C.c_double
+        L.orc_interpolate.argtypes = [c_dp, c_dp, C.c_double, C.c_int, c_dp]
+        L.orc_world_create.argtypes = [C.c_int, c_dp, C.c_int, c_i32p, c_dp, C.c_int, c_dp, C.c_int, c_dp]
+        L.orc_world_create.restype = C.c_void_p
+        L.orc_world_destroy.argtypes = [C.c_void_p]
+        L.orc_clearance.argtypes = [C.c_void_p, c_dp]
+        L.orc_clearance.restype = C.c_double
+        L.orc_fk.argtypes = [C.c_void_p, c_dp, c_dp, c_dp]
+        L.orc_check_motion_batch.argtypes = [C.c_void_p, c_dp, c_dp, C.c_uint64, C.c_double, C.c_int,
+                                             C.c_int, c_u8p, c_dp, c_u32p, C.c_int]
+        L.orc_is_valid_batch.argtypes = [C.c_void_p, c_dp, C.c_uint64, c_u8p, c_dp, C.c_int]
+        L.orc_sample_uniform.argtypes = [C.c_uint64] * 4 + [C.c_double] * 2
+        L.orc_sample_uniform.restype = C.c_double
+        L.orc_rrtc_solve.argtypes = _RRTC_ARGS
+        _lib = L
+    return _lib
+
+
+def ref():
+    """The reference's own RRTConnect.cpp compiled over ompl_min, or None if never built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_rrtconnect.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_rrtc_solve.argtypes = _RRTC_ARGS
+        _ref = L
+    return _ref
+
+
+def knn(pts, queries, k, lo=None, nthreads=1):
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    queries = np.ascontiguousarray(queries, dtype=np.float64)
+    n, dim = pts.shape
+    nq = queries.shape[0]
+    idx = np.empty((nq, k), dtype=np.uint32)
+    dist = np.empty((nq, k), dtype=np.float64)
+    lo_p = None
+    if lo is not None:
+        lo = np.ascontiguousarray(lo, dtype=np.uint32)
+        lo_p = lo.ctypes.data_as(c_u32p)
+    rc = lib().orc_knn(_dp(pts), n, dim, _dp(queries), nq, k, lo_p, idx.ctypes.data_as(c_u32p), _dp(dist),
+                       nthreads)
+    assert rc == 0
+    return idx, dist
+
+
+class World:
+    def __init__(self, dh, sphere_link, sphere_xyzr, obs_spheres, obs_boxes):
+        self.dh = np.ascontiguousarray(dh, dtype=np.float64)
+        self.link = np.ascontiguousarray(sphere_link, dtype=np.int32)
+        self.xyzr = np.ascontiguousarray(sphere_xyzr, dtype=np.float64)
+        self.os = np.ascontiguousarray(obs_spheres, dtype=np.float64).reshape(-1, 4)
+        self.ob = np.ascontiguousarray(obs_boxes, dtype=np.float64).reshape(-1, 6)
+        self.dof = self.dh.shape[0]
+        self.h = lib().orc_world_create(self.dof, _dp(self.dh), len(self.link),
+                                        self.link.ctypes.data_as(c_i32p), _dp(self.xyzr), len(self.os),
+                                        _dp(self.os), len(self.ob), _dp(self.ob))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_world_destroy(self.h)
+            self.h = None
+
+    def clearance(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        return lib().orc_clearance(self.h, _dp(q))
+
+    def fk(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        pose = np.empty(12)
+        cen = np.empty((len(self.link), 3))
+        lib().orc_fk(self.h, _dp(q), _dp(pose), _dp(cen))
+        return pose.reshape(3, 4), cen
+
+    def is_valid_batch(self, q, nthreads=1):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        n = q.shape[0]
+        valid = np.empty(n, dtype=np.uint8)
+        clear = np.empty(n, dtype=np.float64)
+        lib().orc_is_valid_batch(self.h, _dp(q), n, valid.ctypes.data_as(c_u8p), _dp(clear), nthreads)
+        return valid, clear
+
+    def check_motion_batch(self, a, b, resolution, mode=0, check_first=False, want_clearance=True,
+                           nthreads=1):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        n = a.shape[0]
+        valid = np.empty(n, dtype=np.uint8)
+        clear = np.empty(n, dtype=np.float64) if want_clearance else None
+        ntest = np.empty(n, dtype=np.uint32) if want_clearance else None
+        rc = lib().orc_check_motion_batch(self.h, _dp(a), _dp(b), n, resolution, mode, int(check_first),
+                                          valid.ctypes.data_as(c_u8p), _dp(clear),
+                                          ntest.ctypes.data_as(c_u32p) if ntest is not None else None,
+                                          nthreads)
+        assert rc == 0
+        return valid, clear, ntest
+
+    def rrtc_solve(self, start, goal, lo, hi, rng=0.0, ext=(0, 1), resolution_fraction=0.01, seed=0,
+                   query=0, max_iters=1000, max_nodes=20000, max_path=4096, impl="port"):
+        """impl: "port" (oracle/rrtconnect_port.cpp) or "ref" (the reference's RRTConnect.cpp)."""
+        dim = self.dof
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        goal = np.ascontiguousarray(goal, dtype=np.float64)
+        lo = np.ascontiguousarray(np.broadcast_to(lo, (dim,)), dtype=np.float64)
+        hi = np.ascontiguousarray(np.broadcast_to(hi, (dim,)), dtype=np.float64)
+        res = RrtcResult()
+        ss = np.zeros((max_nodes, dim))
+        sp = np.zeros(max_nodes, dtype=np.int32)
+        gs = np.zeros((max_nodes, dim))
+        gp = np.zeros(max_nodes, dtype=np.int32)
+        path = np.zeros((max_path, dim))
+        fn = lib().orc_rrtc_solve if impl == "port" else ref().ref_rrtc_solve
+        rc = fn(self.h, dim, _dp(lo), _dp(hi), _dp(start), _dp(goal), float(rng), int(ext[0]), int(ext[1]),
+                float(resolution_fraction), int(seed), int(query), int(max_iters), int(max_nodes),
+                int(max_path), C.byref(res), _dp(ss), sp.ctypes.data_as(c_i32p), _dp(gs),
+                gp.ctypes.data_as(c_i32p), _dp(path))
+        assert rc == 0 and res.overflow == 0, (rc, res.overflow)
+        return dict(status=res.status, iterations=res.iterations, start_states=ss[:res.n_start].copy(),
+                    start_parent=sp[:res.n_start].copy(), goal_states=gs[:res.n_goal].copy(),
+                    goal_parent=gp[:res.n_goal].copy(), path=path[:res.path_len].copy())
