@@ -1,0 +1,124 @@
+/* prgpu.h -- C ABI of the B200-native hot path behind pr-ompl's planners.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its
+ * hot path sits behind three OMPL C++ plugin interfaces.  Each entry point below names the
+ * reference call site it replaces; the C++ host mirror (pr-ompl_b200/plugin/) subclasses
+ * those OMPL interfaces and calls only this header.
+ *
+ *   ompl::NearestNeighbors<Motion*>  (pr_ompl/include/pr_ompl/RRTConnect.h:154; add/nearest/
+ *       size/list/clear used at pr_ompl/src/RRTConnect.cpp:181,209,235,278,172-174)
+ *       and findKnnNodes (frechet/src/util.cpp:34-58)                 -> prgpu_knn_*
+ *   ompl::base::StateValidityChecker / MotionValidator (si_->checkMotion, isValid at
+ *       pr_ompl/src/RRTConnect.cpp:198; evaluateEdge frechet/src/NNFrechet.cpp:655-683)
+ *                                                                     -> prgpu_world_*, prgpu_check_motion_*
+ *   pr_ompl::RRTConnect::solve / growTree (pr_ompl/src/RRTConnect.cpp:178-376), many
+ *       independent queries                                           -> prgpu_rrtc_batch_*
+ *   NNFrechet::setup / solve (frechet/src/NNFrechet.cpp:95-221, LPAStar.cpp:125-159)
+ *                                                                     -> prgpu_nnf_*
+ *
+ * Conventions: opaque handles; every function returns 0 on success and a negative
+ * PRGPU_E* code on failure (text via prgpu_last_error(), thread-local); no C++ exceptions
+ * or STL types cross the boundary; the caller owns every host buffer; a handle owns its
+ * device buffers and a CUDA stream; calls are synchronous unless they take a stream
+ * argument (`*_device` variants: device pointers in/out, enqueued on `stream`, a
+ * cudaStream_t passed as void*); one handle is used from one thread at a time.  There is
+ * NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ * PRGPU_ENODEV.
+ */
+#ifndef PRGPU_H
+#define PRGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRGPU_OK 0
+#define PRGPU_EINVAL (-1)   /* bad argument */
+#define PRGPU_ENODEV (-2)   /* no CUDA device / wrong architecture */
+#define PRGPU_ECUDA (-3)    /* CUDA runtime error (see prgpu_last_error) */
+#define PRGPU_ENOMEM (-4)
+#define PRGPU_ELIMIT (-5)   /* size beyond a documented limit */
+
+#define PRGPU_INVALID_INDEX 0xFFFFFFFFu
+#define PRGPU_MAX_DIM 8
+#define PRGPU_MAX_K 64
+
+const char *prgpu_last_error(void);
+int prgpu_version(void);
+int prgpu_device_count(void); /* number of CUDA devices, 0 if none; never fails */
+
+/* ------------------------------------------------------------------------------------
+ * K1: nearest neighbours over a configuration buffer (a planner's tree).
+ * Points are appended in order; the insertion index is the point's identity and the
+ * tie-break: results are ordered by (sqrt-distance, index), exactly the order of OMPL's
+ * linear scan (first strict minimum wins) and of findKnnNodes' sort of (distance, vertex).
+ * Distances are RealVectorStateSpace::distance bit for bit (sequential sum of squared
+ * differences in double, no FMA, IEEE sqrt).
+ * ---------------------------------------------------------------------------------- */
+typedef struct prgpu_knn prgpu_knn_t;
+int prgpu_knn_create(int device, int dim, uint64_t capacity_hint, prgpu_knn_t **out);
+int prgpu_knn_destroy(prgpu_knn_t *h);
+int prgpu_knn_clear(prgpu_knn_t *h);                                   /* NearestNeighbors::clear */
+int prgpu_knn_add(prgpu_knn_t *h, const double *pts, uint64_t n);      /* ::add ; pts n x dim row-major, host */
+int prgpu_knn_add_device(prgpu_knn_t *h, const double *pts_dev, uint64_t n, void *stream);
+int prgpu_knn_size(const prgpu_knn_t *h, uint64_t *n);                 /* ::size */
+/* global index reported for local point i is index_base + i (node-sharded trees) */
+int prgpu_knn_set_index_base(prgpu_knn_t *h, uint32_t index_base);
+/* copies points [first, first+n) back in insertion order (NearestNeighbors::list) */
+int prgpu_knn_get_points(prgpu_knn_t *h, uint64_t first, uint64_t n, double *pts);
+/* ::nearest (k=1) / ::nearestK ; findKnnNodes when lo != NULL: candidates of query i are
+ * the points with local index >= lo[i].  idx: nq x k (PRGPU_INVALID_INDEX padded),
+ * dist: nq x k (+inf padded) or NULL. */
+int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int k, const uint32_t *lo,
+                        uint32_t *idx, double *dist);
+int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64_t nq, int k,
+                               const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, void *stream);
+/* merge `nparts` per-shard candidate tables (each nq x k, ordered, same padding) into the
+ * global top-k under the same (distance, index) order: the step after the NCCL all-gather
+ * of per-shard candidates.  Layout: part p of query q at ((p * nq) + q) * k. */
+int prgpu_topk_merge_device(int device, const uint32_t *idx_parts_dev, const double *dist_parts_dev,
+                            int nparts, uint64_t nq, int k, uint32_t *idx_dev, double *dist_dev,
+                            void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2: synthetic world (sphere-approximated FK of a DH arm vs sphere/box obstacles) and
+ * batched discretised edge validation.
+ * ---------------------------------------------------------------------------------- */
+typedef struct prgpu_world prgpu_world_t;
+#define PRGPU_MAX_LINK_SPHERES 32
+#define PRGPU_MAX_OBSTACLES 4096
+/* dh: dof x 5 (a, d, cos(alpha), sin(alpha), theta0); sphere_link[s] in [0,dof];
+ * sphere_xyzr: S x 4; obs_spheres: x4 (x,y,z,R); obs_boxes: x6 (cx,cy,cz,hx,hy,hz). */
+int prgpu_world_create(int device, int dof, const double *dh, int n_link_spheres,
+                       const int32_t *sphere_link, const double *sphere_xyzr, int n_obs_spheres,
+                       const double *obs_spheres, int n_obs_boxes, const double *obs_boxes,
+                       prgpu_world_t **out);
+int prgpu_world_destroy(prgpu_world_t *w);
+int prgpu_world_dof(const prgpu_world_t *w);
+
+#define PRGPU_MODE_OMPL_DISCRETE 0 /* DiscreteMotionValidator::checkMotion: {to} U {j/nd, 0<j<nd} */
+#define PRGPU_MODE_NNF_ALPHA 1     /* NNFrechet::evaluateEdge: alpha = 0, +1/numQ, ... while <= 1 */
+/* valid[i] = 1 iff every state of edge i's tested set is collision free.
+ * mode 0: resolution = the space's longest valid segment length; check_first != 0 also
+ *         tests `from` (the goal-tree form isValid(from) && checkMotion(from,to),
+ *         pr_ompl/src/RRTConnect.cpp:198).
+ * mode 1: resolution = NNF's check resolution (0.05, frechet/include/NNFrechet.hpp:277);
+ *         valid = !evaluateEdge(...). */
+int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double *to, uint64_t n,
+                             double resolution, int mode, int check_first, uint8_t *valid);
+int prgpu_check_motion_batch_device(prgpu_world_t *w, const double *from_dev, const double *to_dev,
+                                    uint64_t n, double resolution, int mode, int check_first,
+                                    uint8_t *valid_dev, void *stream);
+/* StateValidityChecker::isValid for n states (n x dof) */
+int prgpu_is_valid_batch(prgpu_world_t *w, const double *q, uint64_t n, uint8_t *valid);
+int prgpu_is_valid_batch_device(prgpu_world_t *w, const double *q_dev, uint64_t n, uint8_t *valid_dev,
+                                void *stream);
+/* end-effector pose (3x4 row-major [R|p]) of n states: the FK callback of NNF */
+int prgpu_fk_batch(prgpu_world_t *w, const double *q, uint64_t n, double *pose12);
+int prgpu_fk_batch_device(prgpu_world_t *w, const double *q_dev, uint64_t n, double *pose12_dev,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRGPU_H */

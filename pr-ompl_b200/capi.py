@@ -1,0 +1,209 @@
+"""ctypes binding of include/prgpu.h (libprgpu.so).  No CPU fallback: if the library is missing
+or no sm_100 device is present, calls raise PrgpuError."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INVALID_INDEX = 0xFFFFFFFF
+MODE_OMPL_DISCRETE = 0
+MODE_NNF_ALPHA = 1
+
+c_dp = C.POINTER(C.c_double)
+c_u32p = C.POINTER(C.c_uint32)
+c_i32p = C.POINTER(C.c_int32)
+c_u8p = C.POINTER(C.c_uint8)
+c_vp = C.c_void_p
+
+
+class PrgpuError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libprgpu.so")
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libprgpu.so (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-j8", "-C", os.path.join(_HERE, "csrc")], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    return lib_path()
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/prgpu.h declares
+SIGNATURES = {
+    "prgpu_last_error": (C.c_char_p, []),
+    "prgpu_version": (C.c_int, []),
+    "prgpu_device_count": (C.c_int, []),
+    "prgpu_knn_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.POINTER(c_vp)]),
+    "prgpu_knn_destroy": (C.c_int, [c_vp]),
+    "prgpu_knn_clear": (C.c_int, [c_vp]),
+    "prgpu_knn_add": (C.c_int, [c_vp, c_vp, C.c_uint64]),
+    "prgpu_knn_add_device": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp]),
+    "prgpu_knn_size": (C.c_int, [c_vp, C.POINTER(C.c_uint64)]),
+    "prgpu_knn_set_index_base": (C.c_int, [c_vp, C.c_uint32]),
+    "prgpu_knn_get_points": (C.c_int, [c_vp, C.c_uint64, C.c_uint64, c_vp]),
+    "prgpu_knn_nearest_k": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
+    "prgpu_knn_nearest_k_device": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "prgpu_topk_merge_device": (C.c_int, [C.c_int, c_vp, c_vp, C.c_int, C.c_uint64, C.c_int, c_vp, c_vp,
+                                          c_vp]),
+    "prgpu_world_create": (C.c_int, [C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.c_int, c_vp, C.c_int,
+                                     c_vp, C.POINTER(c_vp)]),
+    "prgpu_world_destroy": (C.c_int, [c_vp]),
+    "prgpu_world_dof": (C.c_int, [c_vp]),
+    "prgpu_check_motion_batch": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_double, C.c_int, C.c_int,
+                                           c_vp]),
+    "prgpu_check_motion_batch_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_double, C.c_int,
+                                                  C.c_int, c_vp, c_vp]),
+    "prgpu_is_valid_batch": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp]),
+    "prgpu_is_valid_batch_device": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp, c_vp]),
+    "prgpu_fk_batch": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp]),
+    "prgpu_fk_batch_device": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp, c_vp]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise PrgpuError("libprgpu.so is not built (run __graft_entry__.build()); there is no CPU "
+                             "fallback for the prgpu hot path")
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PrgpuError("prgpu error %d: %s" % (rc, lib().prgpu_last_error().decode()))
+
+
+def _ptr(a):
+    """host numpy array, torch tensor (device or host) or raw int address -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())
+
+
+class KnnIndex:
+    """Tree configuration buffer + nearest / nearestK (ompl::NearestNeighbors semantics)."""
+
+    def __init__(self, dim, device=0, capacity=0):
+        self.dim = dim
+        self.device = device
+        h = c_vp()
+        _check(lib().prgpu_knn_create(device, dim, capacity, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.prgpu_knn_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def clear(self):
+        _check(lib().prgpu_knn_clear(self.h))
+
+    def size(self):
+        n = C.c_uint64()
+        _check(lib().prgpu_knn_size(self.h, C.byref(n)))
+        return n.value
+
+    def set_index_base(self, base):
+        _check(lib().prgpu_knn_set_index_base(self.h, base))
+
+    def add(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, self.dim)
+        _check(lib().prgpu_knn_add(self.h, _ptr(pts), pts.shape[0]))
+
+    def add_device(self, pts_dev, n, stream=0):
+        _check(lib().prgpu_knn_add_device(self.h, _ptr(pts_dev), n, C.c_void_p(stream)))
+
+    def points(self, first=0, n=None):
+        n = self.size() - first if n is None else n
+        out = np.empty((n, self.dim), dtype=np.float64)
+        _check(lib().prgpu_knn_get_points(self.h, first, n, _ptr(out)))
+        return out
+
+    def nearest_k(self, queries, k, lo=None, want_dist=True):
+        queries = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)
+        nq = queries.shape[0]
+        idx = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float64) if want_dist else None
+        if lo is not None:
+            lo = np.ascontiguousarray(lo, dtype=np.uint32)
+        _check(lib().prgpu_knn_nearest_k(self.h, _ptr(queries), nq, k, _ptr(lo), _ptr(idx), _ptr(dist)))
+        return (idx, dist) if want_dist else idx
+
+    def nearest_k_device(self, q_dev, nq, k, idx_dev, dist_dev=None, lo_dev=None, stream=0):
+        _check(lib().prgpu_knn_nearest_k_device(self.h, _ptr(q_dev), nq, k, _ptr(lo_dev), _ptr(idx_dev),
+                                                _ptr(dist_dev), C.c_void_p(stream)))
+
+
+def topk_merge_device(device, idx_parts, dist_parts, nparts, nq, k, idx_out, dist_out, stream=0):
+    _check(lib().prgpu_topk_merge_device(device, _ptr(idx_parts), _ptr(dist_parts), nparts, nq, k,
+                                         _ptr(idx_out), _ptr(dist_out), C.c_void_p(stream)))
+
+
+class World:
+    """Synthetic world (DH arm with link spheres vs sphere/box obstacles) on the device."""
+
+    def __init__(self, dh, sphere_link, sphere_xyzr, obs_spheres, obs_boxes, device=0):
+        dh = np.ascontiguousarray(dh, dtype=np.float64)
+        link = np.ascontiguousarray(sphere_link, dtype=np.int32)
+        xyzr = np.ascontiguousarray(sphere_xyzr, dtype=np.float64)
+        os_ = np.ascontiguousarray(obs_spheres, dtype=np.float64).reshape(-1, 4)
+        ob_ = np.ascontiguousarray(obs_boxes, dtype=np.float64).reshape(-1, 6)
+        self.dof = dh.shape[0]
+        self.device = device
+        h = c_vp()
+        _check(lib().prgpu_world_create(device, self.dof, _ptr(dh), len(link), _ptr(link), _ptr(xyzr),
+                                        len(os_), _ptr(os_), len(ob_), _ptr(ob_), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.prgpu_world_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def check_motion_batch(self, a, b, resolution, mode=MODE_OMPL_DISCRETE, check_first=False):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, self.dof)
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1, self.dof)
+        valid = np.empty(a.shape[0], dtype=np.uint8)
+        _check(lib().prgpu_check_motion_batch(self.h, _ptr(a), _ptr(b), a.shape[0], resolution, mode,
+                                              int(check_first), _ptr(valid)))
+        return valid
+
+    def check_motion_batch_device(self, a_dev, b_dev, n, resolution, valid_dev, mode=MODE_OMPL_DISCRETE,
+                                  check_first=False, stream=0):
+        _check(lib().prgpu_check_motion_batch_device(self.h, _ptr(a_dev), _ptr(b_dev), n, resolution, mode,
+                                                     int(check_first), _ptr(valid_dev), C.c_void_p(stream)))
+
+    def is_valid_batch(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
+        valid = np.empty(q.shape[0], dtype=np.uint8)
+        _check(lib().prgpu_is_valid_batch(self.h, _ptr(q), q.shape[0], _ptr(valid)))
+        return valid
+
+    def fk_batch(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
+        pose = np.empty((q.shape[0], 3, 4), dtype=np.float64)
+        _check(lib().prgpu_fk_batch(self.h, _ptr(q), q.shape[0], _ptr(pose)))
+        return pose

@@ -1,0 +1,551 @@
+// C ABI (include/prgpu.h) over the kernels: handle bookkeeping, staging of host buffers,
+// stream ownership.  No compute happens on the host; every entry point fails loudly when
+// no sm_100 device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "check_motion.cuh"
+#include "knn.cuh"
+
+namespace prgpu {
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+static int select_device(int device, int *sm_count) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(PRGPU_ENODEV, "no CUDA device available (prgpu has no CPU fallback)");
+  }
+  if (device < 0 || device >= count)
+    return fail(PRGPU_EINVAL, "device ordinal out of range");
+  cudaDeviceProp prop;
+  PRGPU_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(PRGPU_ENODEV, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                  "; prgpu kernels are built for sm_100a only");
+  PRGPU_CUDA_TRY(cudaSetDevice(device));
+  if (sm_count)
+    *sm_count = prop.multiProcessorCount;
+  return PRGPU_OK;
+}
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes)
+      return PRGPU_OK;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    PRGPU_CUDA_TRY(cudaMalloc(&p, need));
+    bytes = need;
+    return PRGPU_OK;
+  }
+  void release() {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T> T *as() { return static_cast<T *>(p); }
+};
+} // namespace prgpu
+
+using namespace prgpu;
+
+struct prgpu_knn {
+  int device = 0, dim = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  double *pts = nullptr; // SoA, dim x stride
+  uint64_t stride = 0, n = 0;
+  uint32_t index_base = 0;
+  KnnScratch scratch;
+  DevBuf stage, d_q, d_lo, d_idx, d_dist;
+};
+
+struct prgpu_world {
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  DeviceWorld host; // copy of the device struct (device pointers inside)
+  DeviceWorld *dev = nullptr;
+  DevBuf os_f, ob_f, os_d, ob_d;
+  DevBuf d_a, d_b, d_valid, d_pose;
+};
+
+extern "C" {
+
+const char *prgpu_last_error(void) { return g_last_error.c_str(); }
+int prgpu_version(void) { return 100; }
+int prgpu_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+/* ---------------------------------------------- K1 ---------------------------------------------- */
+
+static int knn_reserve(prgpu_knn *h, uint64_t need) {
+  if (need <= h->stride)
+    return PRGPU_OK;
+  uint64_t cap = std::max<uint64_t>(need, std::max<uint64_t>(2 * h->stride, 4096));
+  cap = round_up(cap, KNN_TILE);
+  double *np = nullptr;
+  PRGPU_CUDA_TRY(cudaMalloc(&np, (size_t)h->dim * cap * sizeof(double)));
+  if (h->pts) {
+    for (int d = 0; d < h->dim; ++d)
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(np + (size_t)d * cap, h->pts + (size_t)d * h->stride,
+                                     h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->pts);
+  }
+  h->pts = np;
+  h->stride = cap;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_create(int device, int dim, uint64_t capacity_hint, prgpu_knn_t **out) {
+  if (!out)
+    return fail(PRGPU_EINVAL, "knn_create: out is NULL");
+  *out = nullptr;
+  if (dim < 1 || dim > PRGPU_MAX_DIM)
+    return fail(PRGPU_ELIMIT, "knn_create: dim must be in [1,PRGPU_MAX_DIM]");
+  int sm = 0;
+  int rc = select_device(device, &sm);
+  if (rc != PRGPU_OK)
+    return rc;
+  prgpu_knn *h = new prgpu_knn();
+  h->device = device;
+  h->dim = dim;
+  h->sm_count = sm;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(PRGPU_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  if (capacity_hint) {
+    rc = knn_reserve(h, capacity_hint);
+    if (rc != PRGPU_OK) {
+      prgpu_knn_destroy(h);
+      return rc;
+    }
+  }
+  *out = h;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_destroy(prgpu_knn_t *h) {
+  if (!h)
+    return PRGPU_OK;
+  cudaSetDevice(h->device);
+  if (h->stream)
+    cudaStreamSynchronize(h->stream);
+  if (h->pts)
+    cudaFree(h->pts);
+  if (h->scratch.part_dist)
+    cudaFree(h->scratch.part_dist);
+  if (h->scratch.part_idx)
+    cudaFree(h->scratch.part_idx);
+  h->stage.release();
+  h->d_q.release();
+  h->d_lo.release();
+  h->d_idx.release();
+  h->d_dist.release();
+  if (h->stream)
+    cudaStreamDestroy(h->stream);
+  delete h;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_clear(prgpu_knn_t *h) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "knn_clear: NULL handle");
+  h->n = 0;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_size(const prgpu_knn_t *h, uint64_t *n) {
+  if (!h || !n)
+    return fail(PRGPU_EINVAL, "knn_size: NULL argument");
+  *n = h->n;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_set_index_base(prgpu_knn_t *h, uint32_t index_base) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "knn_set_index_base: NULL handle");
+  h->index_base = index_base;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_add_device(prgpu_knn_t *h, const double *pts_dev, uint64_t n, void *stream) {
+  if (!h || (!pts_dev && n))
+    return fail(PRGPU_EINVAL, "knn_add: NULL argument");
+  if (h->n + n >= 0xFFFFFFFFull)
+    return fail(PRGPU_ELIMIT, "knn_add: more than 2^32-2 points");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  int rc = knn_reserve(h, h->n + n);
+  if (rc != PRGPU_OK)
+    return rc;
+  rc = knn_transpose_append(h->dim, pts_dev, n, h->pts, h->stride, h->n, (cudaStream_t)stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  h->n += n;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_add(prgpu_knn_t *h, const double *pts, uint64_t n) {
+  if (!h || (!pts && n))
+    return fail(PRGPU_EINVAL, "knn_add: NULL argument");
+  if (n == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)n * h->dim * sizeof(double);
+  int rc = h->stage.reserve(bytes);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(h->stage.p, pts, bytes, cudaMemcpyHostToDevice, h->stream));
+  rc = prgpu_knn_add_device(h, h->stage.as<double>(), n, h->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PRGPU_OK;
+}
+
+int prgpu_knn_get_points(prgpu_knn_t *h, uint64_t first, uint64_t n, double *pts) {
+  if (!h || (!pts && n))
+    return fail(PRGPU_EINVAL, "knn_get_points: NULL argument");
+  if (first + n > h->n)
+    return fail(PRGPU_EINVAL, "knn_get_points: range beyond size");
+  if (n == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)n * h->dim * sizeof(double);
+  int rc = h->stage.reserve(bytes);
+  if (rc != PRGPU_OK)
+    return rc;
+  rc = knn_gather_points(h->dim, h->pts, h->stride, first, n, h->stage.as<double>(), h->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(pts, h->stage.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PRGPU_OK;
+}
+
+int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64_t nq, int k,
+                               const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, void *stream) {
+  if (!h || (nq && (!queries_dev || !idx_dev)))
+    return fail(PRGPU_EINVAL, "knn_nearest_k: NULL argument");
+  if (k < 1 || k > PRGPU_MAX_K)
+    return fail(PRGPU_ELIMIT, "knn_nearest_k: k must be in [1,PRGPU_MAX_K]");
+  if (nq > 0x7FFFFFFFull)
+    return fail(PRGPU_ELIMIT, "knn_nearest_k: too many queries in one call");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  double *dd = dist_dev;
+  if (!dd) {
+    int rc = h->d_dist.reserve((size_t)nq * k * sizeof(double));
+    if (rc != PRGPU_OK)
+      return rc;
+    dd = h->d_dist.as<double>();
+  }
+  return knn_search(h->dim, h->pts, h->stride, (uint32_t)h->n, h->index_base, queries_dev, (uint32_t)nq, k,
+                    lo_dev, idx_dev, dd, h->scratch, h->sm_count, (cudaStream_t)stream);
+}
+
+int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int k, const uint32_t *lo,
+                        uint32_t *idx, double *dist) {
+  if (!h || (nq && (!queries || !idx)))
+    return fail(PRGPU_EINVAL, "knn_nearest_k: NULL argument");
+  if (k < 1 || k > PRGPU_MAX_K)
+    return fail(PRGPU_ELIMIT, "knn_nearest_k: k must be in [1,PRGPU_MAX_K]");
+  if (nq == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = h->d_q.reserve((size_t)nq * h->dim * sizeof(double))) != PRGPU_OK)
+    return rc;
+  if ((rc = h->d_idx.reserve((size_t)nq * k * sizeof(uint32_t))) != PRGPU_OK)
+    return rc;
+  if ((rc = h->d_dist.reserve((size_t)nq * k * sizeof(double))) != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(h->d_q.p, queries, (size_t)nq * h->dim * sizeof(double),
+                                 cudaMemcpyHostToDevice, h->stream));
+  const uint32_t *lo_dev = nullptr;
+  if (lo) {
+    if ((rc = h->d_lo.reserve((size_t)nq * sizeof(uint32_t))) != PRGPU_OK)
+      return rc;
+    PRGPU_CUDA_TRY(
+        cudaMemcpyAsync(h->d_lo.p, lo, (size_t)nq * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    lo_dev = h->d_lo.as<uint32_t>();
+  }
+  rc = knn_search(h->dim, h->pts, h->stride, (uint32_t)h->n, h->index_base, h->d_q.as<double>(),
+                  (uint32_t)nq, k, lo_dev, h->d_idx.as<uint32_t>(), h->d_dist.as<double>(), h->scratch,
+                  h->sm_count, h->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(idx, h->d_idx.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                 h->stream));
+  if (dist)
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(dist, h->d_dist.p, (size_t)nq * k * sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->stream));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PRGPU_OK;
+}
+
+int prgpu_topk_merge_device(int device, const uint32_t *idx_parts_dev, const double *dist_parts_dev,
+                            int nparts, uint64_t nq, int k, uint32_t *idx_dev, double *dist_dev,
+                            void *stream) {
+  if (!idx_parts_dev || !dist_parts_dev || !idx_dev || !dist_dev)
+    return fail(PRGPU_EINVAL, "topk_merge: NULL argument");
+  int rc = select_device(device, nullptr);
+  if (rc != PRGPU_OK)
+    return rc;
+  return topk_merge(idx_parts_dev, dist_parts_dev, nparts, (uint32_t)nq, k, idx_dev, dist_dev,
+                    (cudaStream_t)stream);
+}
+
+/* ---------------------------------------------- K2 ---------------------------------------------- */
+
+int prgpu_world_create(int device, int dof, const double *dh, int ns, const int32_t *sphere_link,
+                       const double *sphere_xyzr, int nos, const double *obs_spheres, int nob,
+                       const double *obs_boxes, prgpu_world_t **out) {
+  if (!out)
+    return fail(PRGPU_EINVAL, "world_create: out is NULL");
+  *out = nullptr;
+  if (dof < 1 || dof > WORLD_MAX_DOF)
+    return fail(PRGPU_ELIMIT, "world_create: dof must be in [1,PRGPU_MAX_DIM]");
+  if (ns < 0 || ns > WORLD_MAX_S)
+    return fail(PRGPU_ELIMIT, "world_create: at most PRGPU_MAX_LINK_SPHERES link spheres");
+  if (nos < 0 || nob < 0 || nos + nob > PRGPU_MAX_OBSTACLES)
+    return fail(PRGPU_ELIMIT, "world_create: at most PRGPU_MAX_OBSTACLES obstacles");
+  if (!dh || (ns && (!sphere_link || !sphere_xyzr)) || (nos && !obs_spheres) || (nob && !obs_boxes))
+    return fail(PRGPU_EINVAL, "world_create: NULL array");
+  for (int s = 0; s < ns; ++s)
+    if (sphere_link[s] < 0 || sphere_link[s] > dof)
+      return fail(PRGPU_EINVAL, "world_create: sphere_link out of [0,dof]");
+  int sm = 0;
+  int rc = select_device(device, &sm);
+  if (rc != PRGPU_OK)
+    return rc;
+
+  prgpu_world *w = new prgpu_world();
+  w->device = device;
+  w->sm_count = sm;
+  DeviceWorld &H = w->host;
+  std::memset(&H, 0, sizeof(H));
+  H.dof = dof;
+  H.S = ns;
+  H.n_os = nos;
+  H.n_ob = nob;
+  double reach = 0.0, rmax = 0.0, maxabs = 0.0;
+  for (int i = 0; i < dof; ++i) {
+    for (int c = 0; c < 5; ++c)
+      H.dh[i][c] = dh[5 * i + c];
+    reach += std::fabs(dh[5 * i + 0]) + std::fabs(dh[5 * i + 1]);
+  }
+  double maxlocal = 0.0;
+  for (int s = 0; s < ns; ++s) {
+    H.sphere_link[s] = sphere_link[s];
+    for (int c = 0; c < 4; ++c)
+      H.sphere_local[s][c] = sphere_xyzr[4 * s + c];
+    maxlocal = std::max(maxlocal, std::fabs(sphere_xyzr[4 * s]) + std::fabs(sphere_xyzr[4 * s + 1]) +
+                                      std::fabs(sphere_xyzr[4 * s + 2]));
+    rmax = std::max(rmax, sphere_xyzr[4 * s + 3]);
+  }
+  for (int o = 0; o < nos; ++o)
+    for (int c = 0; c < 3; ++c)
+      maxabs = std::max(maxabs, std::fabs(obs_spheres[4 * o + c]));
+  for (int o = 0; o < nob; ++o)
+    for (int c = 0; c < 3; ++c)
+      maxabs = std::max(maxabs, std::fabs(obs_boxes[6 * o + c]) + std::fabs(obs_boxes[6 * o + 3 + c]));
+  // fp32 filter margin: rounding of both centres to fp32 plus the fp32 arithmetic, with 16x headroom
+  const double scale = std::max(1.0, maxabs + reach + maxlocal);
+  const double delta = 16.0 * 5.9604644775390625e-08 * scale * 4.0;
+  H.delta = (float)delta;
+  for (int s = 0; s < WORLD_MAX_S; ++s) {
+    if (s < ns) {
+      H.sphere_r[s] = (float)(H.sphere_local[s][3] + delta);
+    } else { // padding sphere: attached to the base, far away, never hits
+      H.sphere_link[s] = 0;
+      H.sphere_local[s][0] = 1.0e18;
+      H.sphere_local[s][1] = 0.0;
+      H.sphere_local[s][2] = 0.0;
+      H.sphere_local[s][3] = 0.0;
+      H.sphere_r[s] = 0.0f;
+    }
+  }
+  const double bt = rmax + delta;
+  H.box_thr2 = (float)(bt * bt * (1.0 + 1e-6));
+
+  std::vector<float4> osf(nos), obf(2 * (size_t)nob);
+  for (int o = 0; o < nos; ++o) {
+    const double t = obs_spheres[4 * o + 3] + rmax + delta;
+    osf[o] = make_float4((float)obs_spheres[4 * o], (float)obs_spheres[4 * o + 1],
+                         (float)obs_spheres[4 * o + 2], (float)(t * t * (1.0 + 1e-6)));
+  }
+  for (int o = 0; o < nob; ++o) {
+    obf[2 * o] = make_float4((float)obs_boxes[6 * o], (float)obs_boxes[6 * o + 1],
+                             (float)obs_boxes[6 * o + 2], 0.f);
+    obf[2 * o + 1] = make_float4((float)obs_boxes[6 * o + 3], (float)obs_boxes[6 * o + 4],
+                                 (float)obs_boxes[6 * o + 5], 0.f);
+  }
+  auto upload = [&](DevBuf &b, const void *src, size_t bytes) -> int {
+    int r = b.reserve(std::max<size_t>(bytes, 16));
+    if (r != PRGPU_OK)
+      return r;
+    if (bytes)
+      PRGPU_CUDA_TRY(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return PRGPU_OK;
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete w;
+    return fail(PRGPU_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  if ((rc = upload(w->os_f, osf.data(), osf.size() * sizeof(float4))) != PRGPU_OK ||
+      (rc = upload(w->ob_f, obf.data(), obf.size() * sizeof(float4))) != PRGPU_OK ||
+      (rc = upload(w->os_d, obs_spheres, (size_t)nos * 4 * sizeof(double))) != PRGPU_OK ||
+      (rc = upload(w->ob_d, obs_boxes, (size_t)nob * 6 * sizeof(double))) != PRGPU_OK) {
+    prgpu_world_destroy(w);
+    return rc;
+  }
+  H.os_f = w->os_f.as<float4>();
+  H.ob_f = w->ob_f.as<float4>();
+  H.os_d = w->os_d.as<double>();
+  H.ob_d = w->ob_d.as<double>();
+  e = cudaMalloc(&w->dev, sizeof(DeviceWorld));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(w->dev, &H, sizeof(DeviceWorld), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    prgpu_world_destroy(w);
+    return fail(PRGPU_ECUDA, std::string("world upload: ") + cudaGetErrorString(e));
+  }
+  *out = w;
+  return PRGPU_OK;
+}
+
+int prgpu_world_destroy(prgpu_world_t *w) {
+  if (!w)
+    return PRGPU_OK;
+  cudaSetDevice(w->device);
+  if (w->stream)
+    cudaStreamSynchronize(w->stream);
+  w->os_f.release();
+  w->ob_f.release();
+  w->os_d.release();
+  w->ob_d.release();
+  w->d_a.release();
+  w->d_b.release();
+  w->d_valid.release();
+  w->d_pose.release();
+  if (w->dev)
+    cudaFree(w->dev);
+  if (w->stream)
+    cudaStreamDestroy(w->stream);
+  delete w;
+  return PRGPU_OK;
+}
+
+int prgpu_world_dof(const prgpu_world_t *w) { return w ? w->host.dof : PRGPU_EINVAL; }
+
+int prgpu_check_motion_batch_device(prgpu_world_t *w, const double *from_dev, const double *to_dev,
+                                    uint64_t n, double resolution, int mode, int check_first,
+                                    uint8_t *valid_dev, void *stream) {
+  if (!w || (n && (!from_dev || !to_dev || !valid_dev)))
+    return fail(PRGPU_EINVAL, "check_motion_batch: NULL argument");
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  return check_motion_launch(w->host, w->dev, from_dev, to_dev, n, resolution, mode, check_first, valid_dev,
+                             w->sm_count, (cudaStream_t)stream);
+}
+
+int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double *to, uint64_t n,
+                             double resolution, int mode, int check_first, uint8_t *valid) {
+  if (!w || (n && (!from || !to || !valid)))
+    return fail(PRGPU_EINVAL, "check_motion_batch: NULL argument");
+  if (n == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  const size_t bytes = (size_t)n * w->host.dof * sizeof(double);
+  int rc;
+  if ((rc = w->d_a.reserve(bytes)) != PRGPU_OK || (rc = w->d_b.reserve(bytes)) != PRGPU_OK ||
+      (rc = w->d_valid.reserve(n)) != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, from, bytes, cudaMemcpyHostToDevice, w->stream));
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_b.p, to, bytes, cudaMemcpyHostToDevice, w->stream));
+  rc = check_motion_launch(w->host, w->dev, w->d_a.as<double>(), w->d_b.as<double>(), n, resolution, mode,
+                           check_first, w->d_valid.as<uint8_t>(), w->sm_count, w->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(valid, w->d_valid.p, n, cudaMemcpyDeviceToHost, w->stream));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return PRGPU_OK;
+}
+
+int prgpu_is_valid_batch_device(prgpu_world_t *w, const double *q_dev, uint64_t n, uint8_t *valid_dev,
+                                void *stream) {
+  if (!w || (n && (!q_dev || !valid_dev)))
+    return fail(PRGPU_EINVAL, "is_valid_batch: NULL argument");
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  return is_valid_launch(w->host, w->dev, q_dev, n, valid_dev, (cudaStream_t)stream);
+}
+
+int prgpu_is_valid_batch(prgpu_world_t *w, const double *q, uint64_t n, uint8_t *valid) {
+  if (!w || (n && (!q || !valid)))
+    return fail(PRGPU_EINVAL, "is_valid_batch: NULL argument");
+  if (n == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  const size_t bytes = (size_t)n * w->host.dof * sizeof(double);
+  int rc;
+  if ((rc = w->d_a.reserve(bytes)) != PRGPU_OK || (rc = w->d_valid.reserve(n)) != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, q, bytes, cudaMemcpyHostToDevice, w->stream));
+  rc = is_valid_launch(w->host, w->dev, w->d_a.as<double>(), n, w->d_valid.as<uint8_t>(), w->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(valid, w->d_valid.p, n, cudaMemcpyDeviceToHost, w->stream));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return PRGPU_OK;
+}
+
+int prgpu_fk_batch_device(prgpu_world_t *w, const double *q_dev, uint64_t n, double *pose12_dev,
+                          void *stream) {
+  if (!w || (n && (!q_dev || !pose12_dev)))
+    return fail(PRGPU_EINVAL, "fk_batch: NULL argument");
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  return fk_launch(w->host, w->dev, q_dev, n, pose12_dev, (cudaStream_t)stream);
+}
+
+int prgpu_fk_batch(prgpu_world_t *w, const double *q, uint64_t n, double *pose12) {
+  if (!w || (n && (!q || !pose12)))
+    return fail(PRGPU_EINVAL, "fk_batch: NULL argument");
+  if (n == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  const size_t bytes = (size_t)n * w->host.dof * sizeof(double);
+  int rc;
+  if ((rc = w->d_a.reserve(bytes)) != PRGPU_OK || (rc = w->d_pose.reserve((size_t)n * 12 * sizeof(double))) != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, q, bytes, cudaMemcpyHostToDevice, w->stream));
+  rc = fk_launch(w->host, w->dev, w->d_a.as<double>(), n, w->d_pose.as<double>(), w->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(pose12, w->d_pose.p, (size_t)n * 12 * sizeof(double),
+                                 cudaMemcpyDeviceToHost, w->stream));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return PRGPU_OK;
+}
+
+} // extern "C"

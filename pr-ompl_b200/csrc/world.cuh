@@ -1,0 +1,178 @@
+// K2 device-side world model: sphere-approximated FK of a DH arm vs sphere/box obstacles.
+// Specification: the double-precision CPU definition the tests check against
+// (clearance(q) = min over (link sphere, obstacle) pairs, valid iff > 0).  This file restates it
+// for the device, with an fp32 conservative filter in front of the fp64 decision:
+//   level 1  per obstacle: min over link spheres of squared centre distance vs (R + r_max + delta)^2
+//   level 2  per (sphere, obstacle): fp32 test with the sphere's own radius (+delta)
+//   level 3  fp64 clearance with the specification's formula -> the only place a verdict is made
+// delta bounds the fp32 rounding of centres and arithmetic, so levels 1-2 never reject a colliding
+// pair; every "collision" verdict comes from level 3.
+#pragma once
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace prgpu {
+
+constexpr int WORLD_MAX_DOF = PRGPU_MAX_DIM;
+constexpr int WORLD_MAX_S = PRGPU_MAX_LINK_SPHERES;
+
+struct DeviceWorld {
+  int dof, S, n_os, n_ob;
+  double dh[WORLD_MAX_DOF][5];       // a, d, cos(alpha), sin(alpha), theta0
+  int sphere_link[WORLD_MAX_S];
+  double sphere_local[WORLD_MAX_S][4]; // x,y,z,r  (padding spheres: far away, r = 0)
+  float sphere_r[WORLD_MAX_S];       // fp32 radius + delta
+  float box_thr2;                    // (r_max + delta)^2
+  float delta;
+  const float4 *os_f;                // n_os x (x,y,z,(R + r_max + delta)^2)
+  const float4 *ob_f;                // n_ob x 2: (cx,cy,cz,_) (hx,hy,hz,_)
+  const double *os_d;                // n_os x 4
+  const double *ob_d;                // n_ob x 6
+};
+
+// frames F[(i)*12 ..]: 3x4 row-major [R|p] of frame i = 0..dof
+__device__ __forceinline__ void fk_frames(const DeviceWorld &w, const double *q, double *F) {
+  F[0] = 1; F[1] = 0; F[2] = 0; F[3] = 0;
+  F[4] = 0; F[5] = 1; F[6] = 0; F[7] = 0;
+  F[8] = 0; F[9] = 0; F[10] = 1; F[11] = 0;
+  for (int i = 0; i < w.dof; ++i) {
+    double st, ct;
+    sincos(q[i] + w.dh[i][4], &st, &ct);
+    const double a = w.dh[i][0], d = w.dh[i][1], cA = w.dh[i][2], sA = w.dh[i][3];
+    const double L0[4] = {ct, -st * cA, st * sA, a * ct};
+    const double L1[4] = {st, ct * cA, -ct * sA, a * st};
+    const double L2[4] = {0.0, sA, cA, d};
+    const double *P = F + 12 * i;
+    double *N = F + 12 * (i + 1);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double p0 = P[4 * r + 0], p1 = P[4 * r + 1], p2 = P[4 * r + 2], p3 = P[4 * r + 3];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double v = p0 * L0[c] + p1 * L1[c] + p2 * L2[c];
+        if (c == 3)
+          v += p3;
+        N[4 * r + c] = v;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void sphere_centre(const DeviceWorld &w, const double *F, int s, double c[3]) {
+  const double *T = F + 12 * w.sphere_link[s];
+  const double lx = w.sphere_local[s][0], ly = w.sphere_local[s][1], lz = w.sphere_local[s][2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    c[r] = T[4 * r + 0] * lx + T[4 * r + 1] * ly + T[4 * r + 2] * lz + T[4 * r + 3];
+}
+
+// level 3: specification formula in double; true = this pair collides (clearance <= 0)
+static __device__ __noinline__ bool exact_sphere_hit(const DeviceWorld &w, const double *F, int s, int o) {
+  double c[3];
+  sphere_centre(w, F, s, c);
+  const double *ob = w.os_d + 4 * o;
+  const double dx = c[0] - ob[0], dy = c[1] - ob[1], dz = c[2] - ob[2];
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  const double cl = __dsub_rn(__dsqrt_rn(d2), __dadd_rn(w.sphere_local[s][3], ob[3]));
+  return !(cl > 0.0);
+}
+static __device__ __noinline__ bool exact_box_hit(const DeviceWorld &w, const double *F, int s, int o) {
+  double c[3];
+  sphere_centre(w, F, s, c);
+  const double *ob = w.ob_d + 6 * o;
+  double ex = fabs(c[0] - ob[0]) - ob[3];
+  double ey = fabs(c[1] - ob[1]) - ob[4];
+  double ez = fabs(c[2] - ob[2]) - ob[5];
+  ex = ex > 0.0 ? ex : 0.0;
+  ey = ey > 0.0 ? ey : 0.0;
+  ez = ez > 0.0 ? ez : 0.0;
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+  const double cl = __dsub_rn(__dsqrt_rn(d2), w.sphere_local[s][3]);
+  return !(cl > 0.0);
+}
+
+// StateValidityChecker::isValid for one configuration.  s_os / s_ob: fp32 obstacle tables in
+// shared memory.  SP = number of link spheres padded to a multiple of 8 (compile time).
+template <int SP>
+__device__ __forceinline__ bool state_valid(const DeviceWorld &w, const float4 *__restrict__ s_os,
+                                            const float4 *__restrict__ s_ob, const double *q) {
+  double F[12 * (WORLD_MAX_DOF + 1)];
+  fk_frames(w, q, F);
+  float cx[SP], cy[SP], cz[SP];
+#pragma unroll
+  for (int s = 0; s < SP; ++s) {
+    double c[3];
+    sphere_centre(w, F, s, c);
+    cx[s] = (float)c[0];
+    cy[s] = (float)c[1];
+    cz[s] = (float)c[2];
+  }
+  // sphere obstacles
+  for (int o = 0; o < w.n_os; ++o) {
+    const float4 ob = s_os[o];
+    float t = CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      const float dx = cx[s] - ob.x, dy = cy[s] - ob.y, dz = cz[s] - ob.z;
+      t = fminf(t, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
+    if (t < ob.w) {
+      const float R = (float)w.os_d[4 * o + 3];
+      unsigned hits = 0;
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        const float dx = cx[s] - ob.x, dy = cy[s] - ob.y, dz = cz[s] - ob.z;
+        const float thr = w.sphere_r[s] + R;
+        if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < thr * thr)
+          hits |= 1u << s;
+      }
+      while (hits) {
+        const int s = __ffs(hits) - 1;
+        hits &= hits - 1;
+        if (s < w.S && exact_sphere_hit(w, F, s, o))
+          return false;
+      }
+    }
+  }
+  // box obstacles
+  for (int o = 0; o < w.n_ob; ++o) {
+    const float4 bc = s_ob[2 * o], bh = s_ob[2 * o + 1];
+    float t = CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      const float ex = fmaxf(fabsf(cx[s] - bc.x) - bh.x, 0.0f);
+      const float ey = fmaxf(fabsf(cy[s] - bc.y) - bh.y, 0.0f);
+      const float ez = fmaxf(fabsf(cz[s] - bc.z) - bh.z, 0.0f);
+      t = fminf(t, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+    }
+    if (t < w.box_thr2) {
+      unsigned hits = 0;
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        const float ex = fmaxf(fabsf(cx[s] - bc.x) - bh.x, 0.0f);
+        const float ey = fmaxf(fabsf(cy[s] - bc.y) - bh.y, 0.0f);
+        const float ez = fmaxf(fabsf(cz[s] - bc.z) - bh.z, 0.0f);
+        const float thr = w.sphere_r[s];
+        if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < thr * thr)
+          hits |= 1u << s;
+      }
+      while (hits) {
+        const int s = __ffs(hits) - 1;
+        hits &= hits - 1;
+        if (s < w.S && exact_box_hit(w, F, s, o))
+          return false;
+      }
+    }
+  }
+  return true;
+}
+
+// cooperative copy of the fp32 obstacle tables into shared memory
+__device__ __forceinline__ void load_obstacles(const DeviceWorld &w, float4 *s_os, float4 *s_ob) {
+  for (int i = threadIdx.x; i < w.n_os; i += blockDim.x)
+    s_os[i] = w.os_f[i];
+  for (int i = threadIdx.x; i < 2 * w.n_ob; i += blockDim.x)
+    s_ob[i] = w.ob_f[i];
+}
+
+} // namespace prgpu

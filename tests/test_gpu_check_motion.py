@@ -1,0 +1,68 @@
+"""K2 parity: CUDA batched checkMotion / isValid / FK through the C ABI vs the CPU oracle.
+Validity booleans must be identical except where the oracle's minimum |clearance| over the
+tested set is below the 1e-6 contact band stated by BASELINE.json's north_star."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+BAND = 1e-6
+
+
+def _compare(gv, ov, clear):
+    diff = gv != ov
+    assert not np.any(diff & (np.abs(clear) >= BAND)), np.argwhere(diff)[:10]
+    return int(diff.sum())
+
+
+def test_fk_matches(P, O, synth, gpu_world, oracle_world):
+    q = synth.cloud(11, 500)
+    g = gpu_world.fk_batch(q)
+    for i in range(0, 500, 7):
+        pose, _ = oracle_world.fk(q[i])
+        assert np.allclose(g[i], pose, atol=1e-13)
+
+
+def test_is_valid(P, O, synth, gpu_world, oracle_world):
+    q = synth.cloud(12, 20000)
+    gv = gpu_world.is_valid_batch(q)
+    ov, oc = oracle_world.is_valid_batch(q, nthreads=8)
+    assert _compare(gv, ov, oc) == 0
+    assert 0.3 < gv.mean() < 0.9
+
+
+@pytest.mark.parametrize("check_first", [False, True])
+def test_check_motion_discrete(P, O, synth, gpu_world, oracle_world, check_first):
+    a, b = synth.edges(2, 6000)
+    gv = gpu_world.check_motion_batch(a, b, 0.01, check_first=check_first)
+    ov, oc, nt = oracle_world.check_motion_batch(a, b, 0.01, check_first=check_first, nthreads=8)
+    _compare(gv, ov, oc)
+    assert 0.2 < gv.mean() < 0.8
+
+
+def test_check_motion_edge_cases(P, O, synth, gpu_world, oracle_world):
+    a, b = synth.edges(21, 512, max_len=0.02)       # nd in {0,1,2}: only endpoint(s) tested
+    a[:64] = b[:64]                                  # zero-length edges
+    a2, b2 = synth.edges(22, 256, max_len=6.0)      # long edges, many rounds per warp
+    A, B = np.vstack([a, a2]), np.vstack([b, b2])
+    for res in (0.01, 0.05, 0.5):
+        gv = gpu_world.check_motion_batch(A, B, res)
+        ov, oc, nt = oracle_world.check_motion_batch(A, B, res, nthreads=8)
+        _compare(gv, ov, oc)
+    assert gpu_world.check_motion_batch(A[:0], B[:0], 0.01).shape == (0,)
+
+
+def test_check_motion_nnf_alpha(P, O, synth, gpu_world, oracle_world):
+    # evaluateEdge's accumulated alpha: numQ values that skip alpha=1 (9, 11, 18, ...) are covered
+    # by lengths spread over (0, 1.2]
+    a, b = synth.edges(23, 4000, max_len=1.2)
+    a[:16] = b[:16]
+    gv = gpu_world.check_motion_batch(a, b, 0.05, mode=P.MODE_NNF_ALPHA)
+    ov, oc, nt = oracle_world.check_motion_batch(a, b, 0.05, mode=1, nthreads=8)
+    _compare(gv, ov, oc)
+
+
+def test_free_world_all_valid(P, synth, world_arrays):
+    dh, link, xyzr, _, _ = world_arrays
+    w = P.World(dh, link, xyzr, np.zeros((0, 4)), np.zeros((0, 6)))
+    a, b = synth.edges(5, 300)
+    assert np.all(w.check_motion_batch(a, b, 0.01) == 1)

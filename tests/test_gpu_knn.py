@@ -1,0 +1,114 @@
+"""K1 parity: CUDA nearest / nearestK through the C ABI vs the CPU oracle (bit-exact indices
+under the (sqrt-distance, insertion index) order, bit-exact distances)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(P, O, synth, n, nq, k, dim=7, dup=0.0, lo=None, seed=0):
+    pts = synth.cloud(seed, n, dim, dup_fraction=dup)
+    q = synth.cloud(seed + 1, nq, dim)
+    if dup > 0 and n > 0:
+        q[: nq // 2] = pts[np.random.default_rng(5).integers(0, n, nq // 2)]  # zero-distance hits
+    t = P.KnnIndex(dim)
+    t.add(pts)
+    assert t.size() == n
+    gi, gd = t.nearest_k(q, k, lo=lo)
+    oi, od = O.knn(pts, q, k, lo=lo, nthreads=8)
+    assert np.array_equal(gi, oi), (n, nq, k, np.argwhere(gi != oi)[:5])
+    assert np.array_equal(gd, od)
+    t.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 256, 257, 1000, 10000])
+@pytest.mark.parametrize("k", [1, 16])
+def test_small_trees(P, O, synth, n, k):
+    for nq in (1, 5, 130):
+        _check(P, O, synth, n, nq, k)
+
+
+@pytest.mark.parametrize("k", [1, 5, 16, 33, 64])
+def test_k_sweep(P, O, synth, k):
+    _check(P, O, synth, 20000, 300, k)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3, 6, 8])
+def test_dims(P, O, synth, dim):
+    _check(P, O, synth, 5000, 200, 4, dim=dim)
+
+
+def test_duplicates_tie_break(P, O, synth):
+    # exact duplicates: ties must resolve to the lower insertion index
+    _check(P, O, synth, 30000, 512, 1, dup=0.3)
+    _check(P, O, synth, 30000, 512, 16, dup=0.3)
+    pts = np.zeros((700, 7))
+    t = P.KnnIndex(7)
+    t.add(pts)
+    idx, dist = t.nearest_k(np.zeros((3, 7)), 5)
+    assert np.array_equal(idx, np.tile(np.arange(5, dtype=np.uint32), (3, 1)))
+    assert np.all(dist == 0.0)
+
+
+def test_suffix_mask(P, O, synth):
+    # findKnnNodes: candidates = nodes of strictly deeper layers = index >= lo[q]
+    n, nq = 6000, 400
+    lo = np.sort(np.random.default_rng(9).integers(0, n + 50, nq)).astype(np.uint32)
+    _check(P, O, synth, n, nq, 5, lo=lo)
+    _check(P, O, synth, n, nq, 1, lo=lo)
+
+
+def test_batched_sweep_shape(P, O, synth):
+    # BASELINE config "batched kNN sweep" at its smallest size: N=1e5 here, Q=4096, k=1/16
+    n, nq = 100000, 4096
+    pts = synth.cloud(0, n)
+    q = synth.cloud(1, nq)
+    t = P.KnnIndex(7)
+    t.add(pts[: n // 2])
+    t.add(pts[n // 2:])  # incremental add keeps insertion order
+    sub = np.arange(0, nq, 16)
+    for k in (1, 16):
+        gi, gd = t.nearest_k(q, k)
+        oi, od = O.knn(pts, q[sub], k, nthreads=8)
+        assert np.array_equal(gi[sub], oi)
+        assert np.array_equal(gd[sub], od)
+        # size-independent properties on the full result
+        assert np.all(np.diff(gd, axis=1) >= 0)
+        d0 = np.sqrt(((pts[gi[:, 0]] - q) ** 2).sum(1))
+        assert np.allclose(d0, gd[:, 0], rtol=1e-12)
+    assert np.array_equal(t.points(), pts)
+
+
+def test_empty_and_k_gt_n(P, O, synth):
+    t = P.KnnIndex(7)
+    idx, dist = t.nearest_k(synth.cloud(1, 4), 3)
+    assert np.all(idx == P.INVALID_INDEX) and np.all(np.isinf(dist))
+    t.add(synth.cloud(0, 2))
+    _check(P, O, synth, 2, 9, 16)
+    t.clear()
+    assert t.size() == 0
+
+
+def test_topk_merge_matches_single_pass(P, O, synth):
+    import torch
+    n, nq, k, shards = 50000, 512, 16, 4
+    pts = synth.cloud(0, n)
+    q = synth.cloud(1, nq)
+    parts_i, parts_d = [], []
+    bounds = np.linspace(0, n, shards + 1).astype(int)
+    for s in range(shards):
+        t = P.KnnIndex(7)
+        t.add(pts[bounds[s]:bounds[s + 1]])
+        t.set_index_base(int(bounds[s]))
+        i, d = t.nearest_k(q, k)
+        parts_i.append(i)
+        parts_d.append(d)
+    pi = torch.from_numpy(np.stack(parts_i).view(np.int32)).cuda()
+    pd = torch.from_numpy(np.stack(parts_d)).cuda()
+    oi = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    od = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+    P.topk_merge_device(0, pi, pd, shards, nq, k, oi, od, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ri, rd = O.knn(pts, q, k, nthreads=8)
+    assert np.array_equal(oi.cpu().numpy().view(np.uint32), ri)
+    assert np.array_equal(od.cpu().numpy(), rd)
