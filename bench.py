@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native pr-ompl hot path.
+
+Default workload (BASELINE.json configs[1], "batched kNN sweep"): one tree of 10^7 7-DOF
+nodes, 4096 queries, k=16.  A step is one pass of the hot path over that batch:
+  ours       : prgpu_knn_nearest_k_device (search kernel + partial-list merge kernel); with
+               --gpus N the tree is node-sharded over the ranks and a step also contains the NCCL
+               all-gather of the per-shard top-k candidates and the merge kernel (strong scaling).
+  reference  : (--impl reference) the CPU linear-scan NearestNeighbors the reference would use
+               (oracle port: the reference's own NN code lives in un-vendored OMPL), all host
+               threads, on a bounded sample of the same queries against the same tree.
+Other BASELINE configs are reachable with --workload check_motion (10^6 edges, 0.01 rad, 256
+obstacles).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="knn", choices=["knn", "check_motion"])
+    ap.add_argument("--nodes", type=int, default=10_000_000)
+    ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--k", type=int, default=16)
+    ap.add_argument("--edges", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full summary, else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the CPU implementation the reference would run, on the box's host cores
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle_lib as O
+    import prgpu_loader
+    synth = prgpu_loader.load().synth
+    O.build()
+    cores = host_cores()
+    if args.workload == "knn":
+        pts = synth.cloud(0, args.nodes)
+        q = synth.cloud(1, args.queries)
+        per_step = min(args.queries, 8 * cores)
+        def step(i):
+            lo = (i * per_step) % max(1, args.queries - per_step + 1)
+            O.knn(pts, q[lo:lo + per_step], args.k, nthreads=cores)
+        units, unit, metric = per_step, "queries/s", "kNN queries/s"
+        sample = (f"{per_step} of the {args.queries} queries per step against the full {args.nodes}-node "
+                  f"tree, k={args.k}, linear scan (NearestNeighborsLinear semantics), {cores} threads")
+        config = {"workload": f"batched kNN sweep: N={args.nodes} nodes, 7-DOF, Q={args.queries}, k={args.k}"}
+    else:
+        dh, link, xyzr = synth.default_arm()
+        sph, box = synth.obstacles(3)
+        W = O.World(dh, link, xyzr, sph, box)
+        a, b = synth.edges(2, args.edges)
+        per_step = min(args.edges, 1500 * cores)
+        def step(i):
+            lo = (i * per_step) % max(1, args.edges - per_step + 1)
+            W.check_motion_batch(a[lo:lo + per_step], b[lo:lo + per_step], 0.01, want_clearance=False,
+                                 nthreads=cores)
+        units, unit, metric = per_step, "edges/s", "validated edges/s"
+        sample = (f"{per_step} of the {args.edges} edges per step, DiscreteMotionValidator bisection with "
+                  f"early exit over the double-precision synthetic checker, {cores} threads")
+        config = {"workload": f"batched checkMotion: {args.edges} edges, 0.01 rad, 7-DOF sphere-FK arm vs "
+                              f"256 obstacles"}
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = units * args.steps / dt
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import prgpu_loader
+    P = prgpu_loader.load()
+    synth = P.synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the prgpu hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    hbm_peak, peak_src = peaks()
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    extra = {}
+    if args.workload == "knn":
+        N, Q, k = args.nodes, args.queries, args.k
+        pts_all = synth.cloud(0, N)
+        q_host = torch.from_numpy(synth.cloud(1, Q)).pin_memory()
+        b0, b1 = rank * N // world, (rank + 1) * N // world
+        pts_host = torch.from_numpy(pts_all[b0:b1]).pin_memory()
+        del pts_all
+        n_local = b1 - b0
+        tree = P.KnnIndex(7, device=local_rank, capacity=n_local)
+        tree.set_index_base(b0)
+        pts_dev = pts_host.to(dev, non_blocking=True)
+        q_dev = q_host.to(dev, non_blocking=True)
+        tree.add_device(pts_dev, n_local, stream)
+        idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+        dd = torch.empty((Q, k), dtype=torch.float64, device=dev)
+        if world > 1:
+            gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
+            gd = torch.empty((world, Q, k), dtype=torch.float64, device=dev)
+            fi = torch.empty((Q, k), dtype=torch.int32, device=dev)
+            fd = torch.empty((Q, k), dtype=torch.float64, device=dev)
+        tree.set_profiling(True)
+        kernel_ms = []
+
+        def step(record=False):
+            tree.nearest_k_device(q_dev, Q, k, idx, dd, stream=stream)
+            if world > 1:
+                dist.all_gather_into_tensor(gi, idx)
+                dist.all_gather_into_tensor(gd, dd)
+                P.topk_merge_device(local_rank, gi, gd, world, Q, k, fi, fd, stream)
+            if record:
+                kernel_ms.append(tree.last_kernel_ms())
+
+        launches_per_step = 2 + (1 if world > 1 else 0)
+        units_per_step = Q
+        metric, unit = "kNN queries/s", "queries/s"
+        algo_bytes = n_local * 56 + Q * 56 + Q * k * 12
+        kernel_name = "knn_tile_kernel"
+        config = {
+            "workload": f"batched kNN sweep: N={N} nodes, 7-DOF, Q={Q}, k={k} (BASELINE.json configs[1])",
+            "parallelism": "single GPU" if world == 1 else f"tree nodes sharded over {world} GPUs + NCCL "
+                           f"all-gather of per-shard top-{k} + merge kernel",
+            "l2": f"inputs larger than L2 ({n_local * 56 / 1e6:.0f} MB tree shard per GPU, fp64 SoA)",
+            "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks",
+        }
+
+        def e2e_step():
+            # the NearestNeighbors handle is (re)filled from HOST memory and queried with HOST buffers
+            tree.clear()
+            P.capi._check(P.lib().prgpu_knn_add(tree.h, P.capi._ptr(pts_host), n_local))
+            if world == 1:
+                P.capi._check(P.lib().prgpu_knn_nearest_k(tree.h, P.capi._ptr(q_host), Q, k, None,
+                                                          P.capi._ptr(e2e_idx), P.capi._ptr(e2e_dist)))
+            else:
+                q_dev.copy_(q_host, non_blocking=True)
+                tree.nearest_k_device(q_dev, Q, k, idx, dd, stream=stream)
+                dist.all_gather_into_tensor(gi, idx)
+                dist.all_gather_into_tensor(gd, dd)
+                P.topk_merge_device(local_rank, gi, gd, world, Q, k, fi, fd, stream)
+                e2e_idx.copy_(fi, non_blocking=True)
+                e2e_dist.copy_(fd, non_blocking=True)
+                torch.cuda.synchronize()
+
+        e2e_idx = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+        e2e_dist = torch.empty((Q, k), dtype=torch.float64).pin_memory()
+        h2d = n_local * 56 + Q * 56
+        d2h = Q * k * 12
+    else:
+        E = args.edges
+        dh, link, xyzr = synth.default_arm()
+        sph, box = synth.obstacles(3)
+        world_h = P.World(dh, link, xyzr, sph, box, device=local_rank)
+        a_all, b_all = synth.edges(2, E)
+        e0_, e1_ = rank * E // world, (rank + 1) * E // world
+        a_host = torch.from_numpy(a_all[e0_:e1_]).pin_memory()
+        b_host = torch.from_numpy(b_all[e0_:e1_]).pin_memory()
+        n_local = e1_ - e0_
+        a_dev, b_dev = a_host.to(dev), b_host.to(dev)
+        valid = torch.empty(n_local, dtype=torch.uint8, device=dev)
+        world_h.set_profiling(True)
+        kernel_ms = []
+
+        def step(record=False):
+            world_h.check_motion_batch_device(a_dev, b_dev, n_local, 0.01, valid, stream=stream)
+            if record:
+                kernel_ms.append(world_h.last_kernel_ms())
+
+        launches_per_step = 1
+        units_per_step = E  # all ranks together
+        metric, unit = "validated edges/s", "edges/s"
+        algo_bytes = n_local * (2 * 56 + 1)
+        kernel_name = "check_motion_kernel"
+        config = {
+            "workload": f"batched checkMotion: {E} edges at 0.01 rad, 7-DOF sphere-FK arm (16 link spheres) "
+                        f"vs 256 obstacles (BASELINE.json configs[2]); edge length ~U(0,1] rad",
+            "parallelism": "single GPU" if world == 1 else f"edges split over {world} GPUs, no collective",
+            "l2": "L2 flushed by a 256 MB write between timed iterations",
+            "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks",
+        }
+        e2e_valid = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+
+        def e2e_step():
+            P.capi._check(P.lib().prgpu_check_motion_batch(world_h.h, P.capi._ptr(a_host), P.capi._ptr(b_host),
+                                                           n_local, 0.01, 0, 0, P.capi._ptr(e2e_valid)))
+        h2d = n_local * 112
+        d2h = n_local
+
+    flush = None
+    if args.workload != "knn":
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(Wm):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if flush is None:
+        e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_beg.record()
+        for _ in range(K):
+            step(record=True)
+        e_end.record()
+        torch.cuda.synchronize()
+        total_ms = e_beg.elapsed_time(e_end)
+    else:
+        total_ms = 0.0
+        for _ in range(K):
+            flush.fill_(1)
+            e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_beg.record()
+            step(record=True)
+            e_end.record()
+            torch.cuda.synchronize()
+            total_ms += e_beg.elapsed_time(e_end)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / K
+    value = units_per_step * K / (total_ms * 1e-3)
+    kms = max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+
+    # ---- end to end through the C ABI with host buffers ----
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = units_per_step * K / e2e_s
+
+    # ---- extras (rank 0, single GPU): the other shapes of the sweep ----
+    if world == 1 and not args.no_extra and args.workload == "knn":
+        def time_knn(nq, kk, reps=5):
+            qd = torch.from_numpy(synth.cloud(7, nq)).to(dev)
+            i_ = torch.empty((nq, kk), dtype=torch.int32, device=dev)
+            d_ = torch.empty((nq, kk), dtype=torch.float64, device=dev)
+            for _ in range(2):
+                tree.nearest_k_device(qd, nq, kk, i_, d_, stream=stream)
+            b, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b.record()
+            for _ in range(reps):
+                tree.nearest_k_device(qd, nq, kk, i_, d_, stream=stream)
+            e.record()
+            torch.cuda.synchronize()
+            return b.elapsed_time(e) / reps
+        tree.clear()
+        tree.add_device(pts_dev, n_local, stream)
+        m1 = time_knn(args.queries, 1)
+        extra["knn_k1_queries_per_s"] = args.queries / (m1 * 1e-3)
+        ms1 = time_knn(1, 1, reps=20)
+        extra["single_query_scan"] = {"ms": ms1, "hbm_gbs": n_local * 56 / (ms1 * 1e-3) / 1e9,
+                                      "frac_of_hbm_peak": n_local * 56 / (ms1 * 1e-3) / 1e9 / hbm_peak}
+
+    if rank != 0:
+        return
+    fp64_peak_pairs = None
+    roof = {"bound": "hbm", "achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": algo_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic(kernel_name),
+            "kernel": kernel_name, "kernel_ms": kms, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algo_bytes}
+    if args.workload == "knn":
+        # what actually binds this kernel: the FP64 pipe; 21 DP instr / pair,
+        # 64 FP64 lanes per SM per clock, 148 SMs
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp64_peak_pairs = 148 * 64 * sm_mhz * 1e6 / 21.0
+        pairs = n_local * args.queries / (kms * 1e-3)
+        roof["issue"] = {"bound": "fp64 pipe", "achieved_pairs_per_s": pairs,
+                         "peak_pairs_per_s": fp64_peak_pairs, "frac": pairs / fp64_peak_pairs,
+                         "note": "21 DADD/DMUL/DSETP per pair at the sampled SM clock; bit-exact "
+                                 "RealVectorStateSpace::distance forbids FMA"}
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config, "roofline": roof,
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches_per_step * K, "clocks": clocks, "extra": extra,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, synth)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, synth):
+    """Oracle port timed on this box's host cores on a bounded sample of the same workload."""
+    import oracle_lib as O
+    O.build()
+    cores = host_cores()
+    if args.workload == "knn":
+        pts = synth.cloud(0, args.nodes)
+        q = synth.cloud(1, args.queries)
+        ns = min(args.queries, 32 * cores)
+        O.knn(pts, q[:cores], args.k, nthreads=cores)
+        t0 = time.perf_counter()
+        O.knn(pts, q[:ns], args.k, nthreads=cores)
+        dt = time.perf_counter() - t0
+        return {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                "sample": f"first {ns} of the {args.queries} queries against the full {args.nodes}-node tree, "
+                          f"k={args.k}, linear scan with (distance, index) order, {cores} threads"}
+    dh, link, xyzr = synth.default_arm()
+    sph, box = synth.obstacles(3)
+    W = O.World(dh, link, xyzr, sph, box)
+    a, b = synth.edges(2, args.edges)
+    ns = min(args.edges, 6000 * cores)
+    t0 = time.perf_counter()
+    W.check_motion_batch(a[:ns], b[:ns], 0.01, want_clearance=False, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": ns / dt, "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": f"first {ns} of the {args.edges} edges, DiscreteMotionValidator bisection with early "
+                      f"exit over the double-precision synthetic checker, {cores} threads"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

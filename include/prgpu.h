@@ -73,6 +73,10 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
                         uint32_t *idx, double *dist);
 int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64_t nq, int k,
                                const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, void *stream);
+/* measurement aid: when on, CUDA events bracket the search kernel of every nearest_k call on
+ * the stream it is launched on; last_kernel_ms waits for and returns the latest duration. */
+int prgpu_knn_set_profiling(prgpu_knn_t *h, int on);
+int prgpu_knn_last_kernel_ms(prgpu_knn_t *h, float *ms);
 /* merge `nparts` per-shard candidate tables (each nq x k, ordered, same padding) into the
  * global top-k under the same (distance, index) order: the step after the NCCL all-gather
  * of per-shard candidates.  Layout: part p of query q at ((p * nq) + q) * k. */
@@ -95,6 +99,8 @@ int prgpu_world_create(int device, int dof, const double *dh, int n_link_spheres
                        prgpu_world_t **out);
 int prgpu_world_destroy(prgpu_world_t *w);
 int prgpu_world_dof(const prgpu_world_t *w);
+int prgpu_world_set_profiling(prgpu_world_t *w, int on);      /* brackets the check_motion kernel */
+int prgpu_world_last_kernel_ms(prgpu_world_t *w, float *ms);
 
 #define PRGPU_MODE_OMPL_DISCRETE 0 /* DiscreteMotionValidator::checkMotion: {to} U {j/nd, 0<j<nd} */
 #define PRGPU_MODE_NNF_ALPHA 1     /* NNFrechet::evaluateEdge: alpha = 0, +1/numQ, ... while <= 1 */

@@ -50,6 +50,10 @@ SIGNATURES = {
     "prgpu_knn_get_points": (C.c_int, [c_vp, C.c_uint64, C.c_uint64, c_vp]),
     "prgpu_knn_nearest_k": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
     "prgpu_knn_nearest_k_device": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "prgpu_knn_set_profiling": (C.c_int, [c_vp, C.c_int]),
+    "prgpu_knn_last_kernel_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
+    "prgpu_world_set_profiling": (C.c_int, [c_vp, C.c_int]),
+    "prgpu_world_last_kernel_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
     "prgpu_topk_merge_device": (C.c_int, [C.c_int, c_vp, c_vp, C.c_int, C.c_uint64, C.c_int, c_vp, c_vp,
                                           c_vp]),
     "prgpu_world_create": (C.c_int, [C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.c_int, c_vp, C.c_int,
@@ -124,6 +128,14 @@ class KnnIndex:
         _check(lib().prgpu_knn_size(self.h, C.byref(n)))
         return n.value
 
+    def set_profiling(self, on=True):
+        _check(lib().prgpu_knn_set_profiling(self.h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _check(lib().prgpu_knn_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def set_index_base(self, base):
         _check(lib().prgpu_knn_set_index_base(self.h, base))
 
@@ -182,6 +194,14 @@ class World:
         self.h = None
 
     __del__ = close
+
+    def set_profiling(self, on=True):
+        _check(lib().prgpu_world_set_profiling(self.h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _check(lib().prgpu_world_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def check_motion_batch(self, a, b, resolution, mode=MODE_OMPL_DISCRETE, check_first=False):
         a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, self.dof)

@@ -70,6 +70,7 @@ struct prgpu_knn {
   uint64_t stride = 0, n = 0;
   uint32_t index_base = 0;
   KnnScratch scratch;
+  KernelTimer timer;
   DevBuf stage, d_q, d_lo, d_idx, d_dist;
 };
 
@@ -80,6 +81,7 @@ struct prgpu_world {
   DeviceWorld *dev = nullptr;
   DevBuf os_f, ob_f, os_d, ob_d;
   DevBuf d_a, d_b, d_valid, d_pose;
+  KernelTimer timer;
 };
 
 extern "C" {
@@ -158,11 +160,16 @@ int prgpu_knn_destroy(prgpu_knn_t *h) {
     cudaFree(h->scratch.part_dist);
   if (h->scratch.part_idx)
     cudaFree(h->scratch.part_idx);
+  if (h->scratch.part2_dist)
+    cudaFree(h->scratch.part2_dist);
+  if (h->scratch.part2_idx)
+    cudaFree(h->scratch.part2_idx);
   h->stage.release();
   h->d_q.release();
   h->d_lo.release();
   h->d_idx.release();
   h->d_dist.release();
+  h->timer.destroy();
   if (h->stream)
     cudaStreamDestroy(h->stream);
   delete h;
@@ -261,7 +268,7 @@ int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64
     dd = h->d_dist.as<double>();
   }
   return knn_search(h->dim, h->pts, h->stride, (uint32_t)h->n, h->index_base, queries_dev, (uint32_t)nq, k,
-                    lo_dev, idx_dev, dd, h->scratch, h->sm_count, (cudaStream_t)stream);
+                    lo_dev, idx_dev, dd, h->scratch, h->sm_count, (cudaStream_t)stream, &h->timer);
 }
 
 int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int k, const uint32_t *lo,
@@ -292,7 +299,7 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
   }
   rc = knn_search(h->dim, h->pts, h->stride, (uint32_t)h->n, h->index_base, h->d_q.as<double>(),
                   (uint32_t)nq, k, lo_dev, h->d_idx.as<uint32_t>(), h->d_dist.as<double>(), h->scratch,
-                  h->sm_count, h->stream);
+                  h->sm_count, h->stream, &h->timer);
   if (rc != PRGPU_OK)
     return rc;
   PRGPU_CUDA_TRY(cudaMemcpyAsync(idx, h->d_idx.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -302,6 +309,18 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
                                    cudaMemcpyDeviceToHost, h->stream));
   PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PRGPU_OK;
+}
+
+int prgpu_knn_set_profiling(prgpu_knn_t *h, int on) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "knn_set_profiling: NULL handle");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  return h->timer.enable(on != 0);
+}
+int prgpu_knn_last_kernel_ms(prgpu_knn_t *h, float *ms) {
+  if (!h || !ms)
+    return fail(PRGPU_EINVAL, "knn_last_kernel_ms: NULL argument");
+  return h->timer.read(ms);
 }
 
 int prgpu_topk_merge_device(int device, const uint32_t *idx_parts_dev, const double *dist_parts_dev,
@@ -450,12 +469,25 @@ int prgpu_world_destroy(prgpu_world_t *w) {
   w->d_b.release();
   w->d_valid.release();
   w->d_pose.release();
+  w->timer.destroy();
   if (w->dev)
     cudaFree(w->dev);
   if (w->stream)
     cudaStreamDestroy(w->stream);
   delete w;
   return PRGPU_OK;
+}
+
+int prgpu_world_set_profiling(prgpu_world_t *w, int on) {
+  if (!w)
+    return fail(PRGPU_EINVAL, "world_set_profiling: NULL handle");
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  return w->timer.enable(on != 0);
+}
+int prgpu_world_last_kernel_ms(prgpu_world_t *w, float *ms) {
+  if (!w || !ms)
+    return fail(PRGPU_EINVAL, "world_last_kernel_ms: NULL argument");
+  return w->timer.read(ms);
 }
 
 int prgpu_world_dof(const prgpu_world_t *w) { return w ? w->host.dof : PRGPU_EINVAL; }
@@ -467,7 +499,7 @@ int prgpu_check_motion_batch_device(prgpu_world_t *w, const double *from_dev, co
     return fail(PRGPU_EINVAL, "check_motion_batch: NULL argument");
   PRGPU_CUDA_TRY(cudaSetDevice(w->device));
   return check_motion_launch(w->host, w->dev, from_dev, to_dev, n, resolution, mode, check_first, valid_dev,
-                             w->sm_count, (cudaStream_t)stream);
+                             w->sm_count, (cudaStream_t)stream, &w->timer);
 }
 
 int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double *to, uint64_t n,
@@ -485,7 +517,7 @@ int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double 
   PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, from, bytes, cudaMemcpyHostToDevice, w->stream));
   PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_b.p, to, bytes, cudaMemcpyHostToDevice, w->stream));
   rc = check_motion_launch(w->host, w->dev, w->d_a.as<double>(), w->d_b.as<double>(), n, resolution, mode,
-                           check_first, w->d_valid.as<uint8_t>(), w->sm_count, w->stream);
+                           check_first, w->d_valid.as<uint8_t>(), w->sm_count, w->stream, &w->timer);
   if (rc != PRGPU_OK)
     return rc;
   PRGPU_CUDA_TRY(cudaMemcpyAsync(valid, w->d_valid.p, n, cudaMemcpyDeviceToHost, w->stream));

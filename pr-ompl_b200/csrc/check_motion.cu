@@ -158,7 +158,7 @@ size_t obstacle_smem(const DeviceWorld &w) { return ((size_t)w.n_os + 2 * (size_
 
 int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *from_dev, const double *to_dev, uint64_t n,
                         double resolution, int mode, int check_first, uint8_t *valid_dev, int sm_count,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, KernelTimer *timer) {
   if (n == 0)
     return PRGPU_OK;
   if (!(resolution > 0.0))
@@ -171,12 +171,16 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
   const uint64_t cap = (uint64_t)sm_count * 8;
   if (blocks > cap)
     blocks = cap;
+  if (timer)
+    timer->begin(stream);
   PRGPU_SP_DISPATCH(w.S, {
     auto kern = check_motion_kernel<SP>;
     PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, CM_THREADS, smem, stream>>>(w_dev, from_dev, to_dev, n, resolution, mode,
                                                          check_first, valid_dev);
   });
+  if (timer)
+    timer->end(stream);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

@@ -4,7 +4,7 @@
 namespace prgpu {
 int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *from_dev, const double *to_dev, uint64_t n,
                         double resolution, int mode, int check_first, uint8_t *valid_dev, int sm_count,
-                        cudaStream_t stream);
+                        cudaStream_t stream, KernelTimer *timer = nullptr);
 int is_valid_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *q_dev, uint64_t n, uint8_t *valid_dev,
                     cudaStream_t stream);
 int fk_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *q_dev, uint64_t n, double *pose12_dev, cudaStream_t stream);

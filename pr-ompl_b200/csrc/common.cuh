@@ -20,6 +20,45 @@ int fail(int code, const std::string &msg);
                            std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
   } while (0)
 
+// optional CUDA-event bracket around a handle's dominant kernel (bench.py's live roofline timing)
+struct KernelTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool on = false, armed = false;
+  int enable(bool want) {
+    if (want && !e0) {
+      PRGPU_CUDA_TRY(cudaEventCreate(&e0));
+      PRGPU_CUDA_TRY(cudaEventCreate(&e1));
+    }
+    on = want;
+    armed = false;
+    return PRGPU_OK;
+  }
+  void begin(cudaStream_t s) {
+    if (on)
+      cudaEventRecord(e0, s);
+  }
+  void end(cudaStream_t s) {
+    if (on) {
+      cudaEventRecord(e1, s);
+      armed = true;
+    }
+  }
+  int read(float *ms) {
+    if (!on || !armed)
+      return ::prgpu::fail(PRGPU_EINVAL, "profiling not enabled or no kernel launched yet");
+    PRGPU_CUDA_TRY(cudaEventSynchronize(e1));
+    PRGPU_CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+    return PRGPU_OK;
+  }
+  void destroy() {
+    if (e0)
+      cudaEventDestroy(e0);
+    if (e1)
+      cudaEventDestroy(e1);
+    e0 = e1 = nullptr;
+  }
+};
+
 inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 // ---- bit-exact double arithmetic (no FMA contraction), matching the x86-64 reference ----

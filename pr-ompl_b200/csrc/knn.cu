@@ -185,29 +185,46 @@ knn_tile_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, uin
       const uint32_t base = t * KNN_TILE;
       const uint32_t jmax = min((uint32_t)KNN_TILE, n - base);
       if (BCAST) {
-        // every thread visits every node: 2 nodes per 16-byte broadcast load
-        uint32_t j = (my_lo > base) ? ((my_lo - base) & ~1u) : 0u;
-#pragma unroll 2
-        for (; j + 1 < jmax; j += 2) {
-          double s0, s1;
+        // every thread visits every node: 4 nodes (two 16-byte broadcast loads per dimension)
+        // per step, i.e. 4 independent accumulation chains in flight
+        uint32_t j = (my_lo > base) ? ((my_lo - base) & ~3u) : 0u;
+        for (; j + 3 < jmax; j += 4) {
+          double s0, s1, s2, s3;
           {
             const double2 x = *reinterpret_cast<const double2 *>(T + j);
+            const double2 y = *reinterpret_cast<const double2 *>(T + j + 2);
             const double a = __dsub_rn(qx[0], x.x), b = __dsub_rn(qx[0], x.y);
+            const double c = __dsub_rn(qx[0], y.x), e = __dsub_rn(qx[0], y.y);
             s0 = __dmul_rn(a, a);
             s1 = __dmul_rn(b, b);
+            s2 = __dmul_rn(c, c);
+            s3 = __dmul_rn(e, e);
           }
 #pragma unroll
           for (int d = 1; d < DIM; ++d) {
             const double2 x = *reinterpret_cast<const double2 *>(T + d * KNN_TILE + j);
+            const double2 y = *reinterpret_cast<const double2 *>(T + d * KNN_TILE + j + 2);
             const double a = __dsub_rn(qx[d], x.x), b = __dsub_rn(qx[d], x.y);
+            const double c = __dsub_rn(qx[d], y.x), e = __dsub_rn(qx[d], y.y);
             s0 = __dadd_rn(s0, __dmul_rn(a, a));
             s1 = __dadd_rn(s1, __dmul_rn(b, b));
+            s2 = __dadd_rn(s2, __dmul_rn(c, c));
+            s3 = __dadd_rn(s3, __dmul_rn(e, e));
           }
-          if (base + j >= my_lo)
-            offer(s0, base + j);
-          offer(s1, base + j + 1);
+          const double smin = fmin(fmin(s0, s1), fmin(s2, s3));
+          if (smin < U) { // rare: at least one of the four may enter the list
+            if (base + j >= my_lo)
+              offer(s0, base + j);
+            if (base + j + 1 >= my_lo)
+              offer(s1, base + j + 1);
+            if (base + j + 2 >= my_lo)
+              offer(s2, base + j + 2);
+            offer(s3, base + j + 3);
+          }
         }
-        if (j < jmax && base + j >= my_lo) {
+        for (; j < jmax; ++j) {
+          if (base + j < my_lo)
+            continue;
           double a = __dsub_rn(qx[0], T[j]);
           double s0 = __dmul_rn(a, a);
 #pragma unroll
@@ -261,18 +278,23 @@ knn_tile_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, uin
   }
 }
 
+// lists [g*group, min((g+1)*group, nparts)) of every query are merged into list g of the output
 __global__ void __launch_bounds__(128)
 topk_merge_kernel(const uint32_t *__restrict__ idx_parts, const double *__restrict__ dist_parts, int nparts,
-                  uint32_t nq, int k, uint32_t *__restrict__ idx_out, double *__restrict__ dist_out) {
+                  int group, uint32_t nq, int k, uint32_t *__restrict__ idx_out,
+                  double *__restrict__ dist_out) {
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq)
     return;
+  const int g = blockIdx.y;
+  const int first = g * group;
+  const int P = min(group, nparts - first);
   auto get = [&](int l, int e, double &d, uint32_t &i) {
-    const size_t at = ((size_t)l * nq + q) * k + e;
+    const size_t at = ((size_t)(first + l) * nq + q) * k + e;
     d = dist_parts[at];
     i = idx_parts[at];
   };
-  warp_merge(get, nparts, k, dist_out + (size_t)q * k, idx_out + (size_t)q * k);
+  warp_merge(get, P, k, dist_out + ((size_t)g * nq + q) * k, idx_out + ((size_t)g * nq + q) * k);
 }
 
 // row-major (n x dim) -> SoA at `offset`
@@ -291,6 +313,36 @@ __global__ void gather_points_kernel(const double *__restrict__ soa, uint64_t st
     return;
   for (int d = 0; d < dim; ++d)
     aos[i * dim + d] = soa[(uint64_t)d * stride + first + i];
+}
+
+template <int DIM, bool KONE, bool BCAST> size_t tile_smem(int k) {
+  return (size_t)2 * DIM * KNN_TILE * sizeof(double) + 2 * sizeof(uint64_t) +
+         (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(uint32_t));
+}
+
+// resident blocks per SM of the kernel variant that (dim, k, nsplit) selects
+template <int DIM> int tile_blocks_per_sm(int k, bool bcast) {
+  const size_t smem = tile_smem<DIM, false, false>(k);
+  int nb = 0;
+#define PRGPU_KNN_OCC(KONE, BCAST)                                                                 \
+  do {                                                                                             \
+    auto kern = knn_tile_kernel<DIM, KONE, BCAST>;                                                 \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, KNN_THREADS, smem);                   \
+  } while (0)
+  if (k == 1) {
+    if (bcast)
+      PRGPU_KNN_OCC(true, true);
+    else
+      PRGPU_KNN_OCC(true, false);
+  } else {
+    if (bcast)
+      PRGPU_KNN_OCC(false, true);
+    else
+      PRGPU_KNN_OCC(false, false);
+  }
+#undef PRGPU_KNN_OCC
+  return nb > 0 ? nb : 1;
 }
 
 template <int DIM>
@@ -327,23 +379,67 @@ int launch_tile(const double *pts, uint64_t stride, uint32_t n, uint32_t index_b
 
 } // namespace
 
+static int scratch_reserve(double *&d, uint32_t *&i, size_t &cap, size_t need) {
+  if (cap >= need)
+    return PRGPU_OK;
+  if (d)
+    cudaFree(d);
+  if (i)
+    cudaFree(i);
+  d = nullptr;
+  i = nullptr;
+  cap = 0;
+  PRGPU_CUDA_TRY(cudaMalloc(&d, need * sizeof(double)));
+  PRGPU_CUDA_TRY(cudaMalloc(&i, need * sizeof(uint32_t)));
+  cap = need;
+  return PRGPU_OK;
+}
+
+constexpr int MERGE_GROUP = 32 * MERGE_LISTS_PER_LANE;
+
 int topk_merge(const uint32_t *idx_parts, const double *dist_parts, int nparts, uint32_t nq, int k,
                uint32_t *idx_out, double *dist_out, cudaStream_t stream) {
-  if (nparts < 1 || nparts > 32 * MERGE_LISTS_PER_LANE)
+  if (nparts < 1 || nparts > MERGE_GROUP)
     return fail(PRGPU_ELIMIT, "topk_merge: nparts must be in [1,128]");
   if (k < 1 || k > PRGPU_MAX_K)
     return fail(PRGPU_ELIMIT, "topk_merge: k must be in [1,PRGPU_MAX_K]");
   if (nq == 0)
     return PRGPU_OK;
-  topk_merge_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(idx_parts, dist_parts, nparts, nq, k, idx_out,
-                                                     dist_out);
+  topk_merge_kernel<<<dim3((nq + 3) / 4, 1), 128, 0, stream>>>(idx_parts, dist_parts, nparts, MERGE_GROUP, nq,
+                                                              k, idx_out, dist_out);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
 
+// any number of partial lists: passes of 128-way merges (parts -> parts2 -> ... -> out)
+static int merge_passes(KnnScratch &sc, int nparts, uint32_t nq, int k, uint32_t *idx_out, double *dist_out,
+                        cudaStream_t stream) {
+  const uint32_t *si = sc.part_idx;
+  const double *sd = sc.part_dist;
+  bool into2 = true;
+  while (nparts > MERGE_GROUP) {
+    const int groups = (nparts + MERGE_GROUP - 1) / MERGE_GROUP;
+    int rc = into2 ? scratch_reserve(sc.part2_dist, sc.part2_idx, sc.part2_capacity, (size_t)groups * nq * k)
+                   : PRGPU_OK; // the first buffer is always large enough for a later pass
+    if (rc != PRGPU_OK)
+      return rc;
+    uint32_t *di = into2 ? sc.part2_idx : sc.part_idx;
+    double *dd = into2 ? sc.part2_dist : sc.part_dist;
+    topk_merge_kernel<<<dim3((nq + 3) / 4, groups), 128, 0, stream>>>(si, sd, nparts, MERGE_GROUP, nq, k, di,
+                                                                   dd);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    si = di;
+    sd = dd;
+    nparts = groups;
+    into2 = !into2;
+  }
+  return topk_merge(si, sd, nparts, nq, k, idx_out, dist_out, stream);
+}
+
 int knn_search(int dim, const double *pts_soa, uint64_t stride, uint32_t n, uint32_t index_base,
                const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev, uint32_t *idx_dev,
-               double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream) {
+               double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
+               KernelTimer *timer) {
   if (k < 1 || k > PRGPU_MAX_K)
     return fail(PRGPU_ELIMIT, "knn: k must be in [1,PRGPU_MAX_K]");
   if (nq == 0)
@@ -354,11 +450,31 @@ int knn_search(int dim, const double *pts_soa, uint64_t stride, uint32_t n, uint
     ++nsplit_log2;
   const uint32_t qblocks = (uint32_t)((((uint64_t)nq << nsplit_log2) + KNN_THREADS - 1) / KNN_THREADS);
   const uint32_t ntiles = (n + KNN_TILE - 1) / KNN_TILE;
-  const uint32_t target_blocks = 4u * (uint32_t)sm_count;
-  uint32_t chunks = (target_blocks + qblocks - 1) / qblocks;
+  // one wave: as many node chunks as fit in the resident block slots next to the query blocks
+  // (a second, partial wave would double the run time of this compute-bound kernel)
+  int per_sm = 4;
+  switch (dim) {
+#define PRGPU_DIM_CASE(D)                                                                          \
+  case D:                                                                                          \
+    per_sm = tile_blocks_per_sm<D>(k, nsplit_log2 == 0);                                           \
+    break;
+    PRGPU_DIM_CASE(1)
+    PRGPU_DIM_CASE(2)
+    PRGPU_DIM_CASE(3)
+    PRGPU_DIM_CASE(4)
+    PRGPU_DIM_CASE(5)
+    PRGPU_DIM_CASE(6)
+    PRGPU_DIM_CASE(7)
+    PRGPU_DIM_CASE(8)
+#undef PRGPU_DIM_CASE
+  default:
+    return fail(PRGPU_ELIMIT, "knn: dim must be in [1,PRGPU_MAX_DIM]");
+  }
+  const uint32_t slots = (uint32_t)per_sm * (uint32_t)sm_count;
+  uint32_t chunks = slots / qblocks;
   chunks = chunks < 1 ? 1 : chunks;
-  if (chunks > 128)
-    chunks = 128;
+  if (chunks > 4096)
+    chunks = 4096;
   if (chunks > ntiles)
     chunks = ntiles ? ntiles : 1;
   uint32_t tiles_per_chunk = ntiles ? (ntiles + chunks - 1) / chunks : 1;
@@ -367,23 +483,16 @@ int knn_search(int dim, const double *pts_soa, uint64_t stride, uint32_t n, uint
   double *od = dist_dev;
   uint32_t *oi = idx_dev;
   if (chunks > 1) {
-    const size_t need = (size_t)chunks * nq * k;
-    if (scratch.part_capacity < need) {
-      if (scratch.part_dist)
-        cudaFree(scratch.part_dist);
-      if (scratch.part_idx)
-        cudaFree(scratch.part_idx);
-      scratch.part_dist = nullptr;
-      scratch.part_idx = nullptr;
-      scratch.part_capacity = 0;
-      PRGPU_CUDA_TRY(cudaMalloc(&scratch.part_dist, need * sizeof(double)));
-      PRGPU_CUDA_TRY(cudaMalloc(&scratch.part_idx, need * sizeof(uint32_t)));
-      scratch.part_capacity = need;
-    }
+    int rcs = scratch_reserve(scratch.part_dist, scratch.part_idx, scratch.part_capacity,
+                              (size_t)chunks * nq * k);
+    if (rcs != PRGPU_OK)
+      return rcs;
     od = scratch.part_dist;
     oi = scratch.part_idx;
   }
   int rc;
+  if (timer)
+    timer->begin(stream);
   switch (dim) {
 #define PRGPU_DIM_CASE(D)                                                                          \
   case D:                                                                                          \
@@ -402,10 +511,12 @@ int knn_search(int dim, const double *pts_soa, uint64_t stride, uint32_t n, uint
   default:
     return fail(PRGPU_ELIMIT, "knn: dim must be in [1,PRGPU_MAX_DIM]");
   }
+  if (timer)
+    timer->end(stream);
   if (rc != PRGPU_OK)
     return rc;
   if (chunks > 1)
-    return topk_merge(oi, od, (int)chunks, nq, k, idx_dev, dist_dev, stream);
+    return merge_passes(scratch, (int)chunks, nq, k, idx_dev, dist_dev, stream);
   return PRGPU_OK;
 }
 
