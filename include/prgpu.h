@@ -124,6 +124,50 @@ int prgpu_fk_batch(prgpu_world_t *w, const double *q, uint64_t n, double *pose12
 int prgpu_fk_batch_device(prgpu_world_t *w, const double *q_dev, uint64_t n, double *pose12_dev,
                           void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * T1: many independent RRTConnect queries (pr_ompl::RRTConnect::solve, one planner per query,
+ * pr_ompl/src/RRTConnect.cpp:219-376) against one world, one thread block per query.
+ * Start/goal are single configurations (ProblemDefinition::setStartAndGoalStates); samples come
+ * from the counter-based stream u(seed, query_id_base + i, iteration, dim) over [lo, hi];
+ * termination = max_iters uniform samples (the ptc) or a full tree.
+ * ---------------------------------------------------------------------------------- */
+typedef struct prgpu_rrtc_batch prgpu_rrtc_batch_t;
+#define PRGPU_EXT_EXTEND 0  /* RRTConnect::EXTTYPE_EXTEND  */
+#define PRGPU_EXT_CONNECT 1 /* RRTConnect::EXTTYPE_CONNECT */
+/* ompl::base::PlannerStatus::StatusType values reported per query */
+#define PRGPU_STATUS_INVALID_START 1
+#define PRGPU_STATUS_INVALID_GOAL 2
+#define PRGPU_STATUS_TIMEOUT 4
+#define PRGPU_STATUS_EXACT_SOLUTION 6
+typedef struct {
+  int32_t dim;
+  double lo[PRGPU_MAX_DIM], hi[PRGPU_MAX_DIM]; /* RealVectorBounds */
+  double range;               /* "range" param; < eps -> 0.2 * maximum extent (configurePlannerRange) */
+  double resolution_fraction; /* si->setStateValidityCheckingResolution (OMPL default 0.01) */
+  int32_t ext_first, ext_second; /* "extension_type": con-con / con-ext / ext-con (default) / ext-ext */
+  uint64_t seed, query_id_base;
+  uint32_t max_iters; /* uniform samples per query */
+  uint32_t max_nodes; /* capacity of each tree */
+} prgpu_rrtc_params;
+int prgpu_rrtc_batch_create(prgpu_world_t *w, const prgpu_rrtc_params *params, uint32_t n_queries,
+                            prgpu_rrtc_batch_t **out);
+int prgpu_rrtc_batch_destroy(prgpu_rrtc_batch_t *h);
+/* starts/goals: n_queries x dim (host).  Synchronous: upload, plan all queries, keep trees on
+ * the device. */
+int prgpu_rrtc_batch_run(prgpu_rrtc_batch_t *h, const double *starts, const double *goals);
+int prgpu_rrtc_batch_run_device(prgpu_rrtc_batch_t *h, const double *starts_dev, const double *goals_dev,
+                                void *stream);
+/* per-query results (any pointer may be NULL): status, samples drawn, tree sizes */
+int prgpu_rrtc_batch_summary(prgpu_rrtc_batch_t *h, int32_t *status, uint32_t *iterations,
+                             uint32_t *n_start, uint32_t *n_goal);
+/* one query's trees in insertion order (NearestNeighbors::list / getPlannerData,
+ * pr_ompl/src/RRTConnect.cpp:378-415) and its solution path (start ... goal).  Buffers hold
+ * max_nodes x dim / max_nodes / max_path x dim entries; path_len receives the path length
+ * (0 if unsolved). */
+int prgpu_rrtc_batch_fetch(prgpu_rrtc_batch_t *h, uint32_t query, double *start_states,
+                           int32_t *start_parent, double *goal_states, int32_t *goal_parent,
+                           uint32_t *path_len, double *path, uint32_t max_path);
+
 #ifdef __cplusplus
 }
 #endif

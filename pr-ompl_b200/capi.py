@@ -68,7 +68,21 @@ SIGNATURES = {
     "prgpu_is_valid_batch_device": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp, c_vp]),
     "prgpu_fk_batch": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp]),
     "prgpu_fk_batch_device": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp, c_vp]),
+    "prgpu_rrtc_batch_create": (C.c_int, [c_vp, c_vp, C.c_uint32, C.POINTER(c_vp)]),
+    "prgpu_rrtc_batch_destroy": (C.c_int, [c_vp]),
+    "prgpu_rrtc_batch_run": (C.c_int, [c_vp, c_vp, c_vp]),
+    "prgpu_rrtc_batch_run_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "prgpu_rrtc_batch_summary": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "prgpu_rrtc_batch_fetch": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, c_vp, c_vp, C.POINTER(C.c_uint32),
+                                         c_vp, C.c_uint32]),
 }
+
+
+class RrtcParams(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("lo", C.c_double * 8), ("hi", C.c_double * 8), ("range", C.c_double),
+                ("resolution_fraction", C.c_double), ("ext_first", C.c_int32), ("ext_second", C.c_int32),
+                ("seed", C.c_uint64), ("query_id_base", C.c_uint64), ("max_iters", C.c_uint32),
+                ("max_nodes", C.c_uint32)]
 
 
 def lib():
@@ -227,3 +241,69 @@ class World:
         pose = np.empty((q.shape[0], 3, 4), dtype=np.float64)
         _check(lib().prgpu_fk_batch(self.h, _ptr(q), q.shape[0], _ptr(pose)))
         return pose
+
+
+EXT_TYPES = {"ext-ext": (0, 0), "ext-con": (0, 1), "con-ext": (1, 0), "con-con": (1, 1)}
+
+
+class RrtcBatch:
+    """Many independent pr_ompl::RRTConnect queries against one world (one thread block each)."""
+
+    def __init__(self, world, n_queries, lo, hi, rng=0.0, extension_type="ext-con", resolution_fraction=0.01,
+                 seed=0, query_id_base=0, max_iters=1000, max_nodes=2048):
+        if extension_type not in EXT_TYPES:
+            raise ValueError("Invalid extension type string.")  # RRTConnect::setExtensionTypesString
+        self.world = world
+        self.n = n_queries
+        self.dim = world.dof
+        self.max_nodes = max_nodes
+        p = RrtcParams()
+        p.dim = self.dim
+        lo = np.broadcast_to(np.asarray(lo, dtype=np.float64), (self.dim,))
+        hi = np.broadcast_to(np.asarray(hi, dtype=np.float64), (self.dim,))
+        for i in range(self.dim):
+            p.lo[i] = lo[i]
+            p.hi[i] = hi[i]
+        p.range = rng
+        p.resolution_fraction = resolution_fraction
+        p.ext_first, p.ext_second = EXT_TYPES[extension_type]
+        p.seed, p.query_id_base = seed, query_id_base
+        p.max_iters, p.max_nodes = max_iters, max_nodes
+        h = c_vp()
+        _check(lib().prgpu_rrtc_batch_create(world.h, C.byref(p), n_queries, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.prgpu_rrtc_batch_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def run(self, starts, goals):
+        starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(self.n, self.dim)
+        goals = np.ascontiguousarray(goals, dtype=np.float64).reshape(self.n, self.dim)
+        _check(lib().prgpu_rrtc_batch_run(self.h, _ptr(starts), _ptr(goals)))
+
+    def run_device(self, starts_dev, goals_dev, stream=0):
+        _check(lib().prgpu_rrtc_batch_run_device(self.h, _ptr(starts_dev), _ptr(goals_dev), C.c_void_p(stream)))
+
+    def summary(self):
+        st = np.empty(self.n, dtype=np.int32)
+        it = np.empty(self.n, dtype=np.uint32)
+        ns = np.empty(self.n, dtype=np.uint32)
+        ng = np.empty(self.n, dtype=np.uint32)
+        _check(lib().prgpu_rrtc_batch_summary(self.h, _ptr(st), _ptr(it), _ptr(ns), _ptr(ng)))
+        return dict(status=st, iterations=it, n_start=ns, n_goal=ng)
+
+    def fetch(self, query, ns, ng, max_path=8192):
+        ss = np.zeros((max(ns, 1), self.dim))
+        sp = np.zeros(max(ns, 1), dtype=np.int32)
+        gs = np.zeros((max(ng, 1), self.dim))
+        gp = np.zeros(max(ng, 1), dtype=np.int32)
+        path = np.zeros((max_path, self.dim))
+        plen = C.c_uint32()
+        _check(lib().prgpu_rrtc_batch_fetch(self.h, query, _ptr(ss), _ptr(sp), _ptr(gs), _ptr(gp),
+                                            C.byref(plen), _ptr(path), max_path))
+        return dict(start_states=ss[:ns], start_parent=sp[:ns], goal_states=gs[:ng], goal_parent=gp[:ng],
+                    path=path[:plen.value].copy())

@@ -7,6 +7,7 @@
 #include <vector>
 #include "check_motion.cuh"
 #include "knn.cuh"
+#include "rrtc_batch.cuh"
 
 namespace prgpu {
 static thread_local std::string g_last_error;
@@ -577,6 +578,210 @@ int prgpu_fk_batch(prgpu_world_t *w, const double *q, uint64_t n, double *pose12
   PRGPU_CUDA_TRY(cudaMemcpyAsync(pose12, w->d_pose.p, (size_t)n * 12 * sizeof(double),
                                  cudaMemcpyDeviceToHost, w->stream));
   PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return PRGPU_OK;
+}
+
+/* ---------------------------------------------- T1 ---------------------------------------------- */
+} // extern "C"
+
+struct prgpu_rrtc_batch {
+  prgpu_world *world = nullptr;
+  prgpu_rrtc_params params;
+  RrtcDeviceParams dp;
+  uint32_t n = 0;
+  DevBuf starts, goals, ss, gs, sp, gp, status, iters, ns, ng, cs, cg, ovf;
+  bool ran = false;
+};
+
+extern "C" {
+
+int prgpu_rrtc_batch_create(prgpu_world_t *w, const prgpu_rrtc_params *params, uint32_t n_queries,
+                            prgpu_rrtc_batch_t **out) {
+  if (!out)
+    return fail(PRGPU_EINVAL, "rrtc_batch_create: out is NULL");
+  *out = nullptr;
+  if (!w || !params)
+    return fail(PRGPU_EINVAL, "rrtc_batch_create: NULL argument");
+  if (params->dim != w->host.dof)
+    return fail(PRGPU_EINVAL, "rrtc_batch_create: dim must equal the world's dof");
+  if (params->max_nodes < 2 || params->max_iters < 1)
+    return fail(PRGPU_EINVAL, "rrtc_batch_create: max_nodes >= 2 and max_iters >= 1 required");
+  if (!(params->resolution_fraction > 0.0 && params->resolution_fraction < 1.0))
+    return fail(PRGPU_EINVAL, "rrtc_batch_create: resolution_fraction must be in (0,1)");
+  for (int e : {params->ext_first, params->ext_second})
+    if (e != PRGPU_EXT_EXTEND && e != PRGPU_EXT_CONNECT)
+      return fail(PRGPU_EINVAL, "rrtc_batch_create: Invalid extension type");
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  prgpu_rrtc_batch *h = new prgpu_rrtc_batch();
+  h->world = w;
+  h->params = *params;
+  h->n = n_queries;
+  RrtcDeviceParams &d = h->dp;
+  std::memset(&d, 0, sizeof(d));
+  d.dim = params->dim;
+  double ext = 0.0; // RealVectorStateSpace::getMaximumExtent
+  for (int i = 0; i < d.dim; ++i) {
+    if (!(params->hi[i] >= params->lo[i])) {
+      delete h;
+      return fail(PRGPU_EINVAL, "rrtc_batch_create: bounds must satisfy lo <= hi");
+    }
+    d.lo[i] = params->lo[i];
+    d.hi[i] = params->hi[i];
+    const double e = params->hi[i] - params->lo[i];
+    ext += e * e;
+  }
+  ext = std::sqrt(ext);
+  d.range = params->range;
+  if (d.range < 2.220446049250313e-16) // SelfConfig::configurePlannerRange
+    d.range = ext * 0.2;
+  d.lvs = ext * params->resolution_fraction;
+  d.ext_first = params->ext_first;
+  d.ext_second = params->ext_second;
+  d.seed = params->seed;
+  d.query_id_base = params->query_id_base;
+  d.max_iters = params->max_iters;
+  d.max_nodes = params->max_nodes;
+  const size_t B = n_queries ? n_queries : 1, M = params->max_nodes, D = d.dim;
+  int rc;
+  if ((rc = h->starts.reserve(B * D * 8)) || (rc = h->goals.reserve(B * D * 8)) ||
+      (rc = h->ss.reserve(B * M * D * 8)) || (rc = h->gs.reserve(B * M * D * 8)) ||
+      (rc = h->sp.reserve(B * M * 4)) || (rc = h->gp.reserve(B * M * 4)) || (rc = h->status.reserve(B * 4)) ||
+      (rc = h->iters.reserve(B * 4)) || (rc = h->ns.reserve(B * 4)) || (rc = h->ng.reserve(B * 4)) ||
+      (rc = h->cs.reserve(B * 4)) || (rc = h->cg.reserve(B * 4)) || (rc = h->ovf.reserve(B * 4))) {
+    prgpu_rrtc_batch_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return PRGPU_OK;
+}
+
+int prgpu_rrtc_batch_destroy(prgpu_rrtc_batch_t *h) {
+  if (!h)
+    return PRGPU_OK;
+  cudaSetDevice(h->world->device);
+  cudaStreamSynchronize(h->world->stream);
+  for (DevBuf *b : {&h->starts, &h->goals, &h->ss, &h->gs, &h->sp, &h->gp, &h->status, &h->iters, &h->ns,
+                    &h->ng, &h->cs, &h->cg, &h->ovf})
+    b->release();
+  delete h;
+  return PRGPU_OK;
+}
+
+int prgpu_rrtc_batch_run_device(prgpu_rrtc_batch_t *h, const double *starts_dev, const double *goals_dev,
+                                void *stream) {
+  if (!h || (h->n && (!starts_dev || !goals_dev)))
+    return fail(PRGPU_EINVAL, "rrtc_batch_run: NULL argument");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->world->device));
+  RrtcDeviceBuffers b;
+  b.starts = starts_dev;
+  b.goals = goals_dev;
+  b.start_states = h->ss.as<double>();
+  b.goal_states = h->gs.as<double>();
+  b.start_parent = h->sp.as<int32_t>();
+  b.goal_parent = h->gp.as<int32_t>();
+  b.status = h->status.as<int32_t>();
+  b.iters = h->iters.as<uint32_t>();
+  b.n_start = h->ns.as<uint32_t>();
+  b.n_goal = h->ng.as<uint32_t>();
+  b.conn_start = h->cs.as<int32_t>();
+  b.conn_goal = h->cg.as<int32_t>();
+  b.overflow = h->ovf.as<uint32_t>();
+  int rc = rrtc_batch_launch(h->world->host, h->world->dev, h->dp, b, h->n, (cudaStream_t)stream);
+  if (rc == PRGPU_OK)
+    h->ran = true;
+  return rc;
+}
+
+int prgpu_rrtc_batch_run(prgpu_rrtc_batch_t *h, const double *starts, const double *goals) {
+  if (!h || (h->n && (!starts || !goals)))
+    return fail(PRGPU_EINVAL, "rrtc_batch_run: NULL argument");
+  if (h->n == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(h->world->device));
+  cudaStream_t s = h->world->stream;
+  const size_t bytes = (size_t)h->n * h->dp.dim * sizeof(double);
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(h->starts.p, starts, bytes, cudaMemcpyHostToDevice, s));
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(h->goals.p, goals, bytes, cudaMemcpyHostToDevice, s));
+  int rc = prgpu_rrtc_batch_run_device(h, h->starts.as<double>(), h->goals.as<double>(), s);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+  return PRGPU_OK;
+}
+
+int prgpu_rrtc_batch_summary(prgpu_rrtc_batch_t *h, int32_t *status, uint32_t *iterations,
+                             uint32_t *n_start, uint32_t *n_goal) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "rrtc_batch_summary: NULL handle");
+  if (!h->ran)
+    return fail(PRGPU_EINVAL, "rrtc_batch_summary: run() has not been called");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->world->device));
+  const size_t b4 = (size_t)h->n * 4;
+  if (status)
+    PRGPU_CUDA_TRY(cudaMemcpy(status, h->status.p, b4, cudaMemcpyDeviceToHost));
+  if (iterations)
+    PRGPU_CUDA_TRY(cudaMemcpy(iterations, h->iters.p, b4, cudaMemcpyDeviceToHost));
+  if (n_start)
+    PRGPU_CUDA_TRY(cudaMemcpy(n_start, h->ns.p, b4, cudaMemcpyDeviceToHost));
+  if (n_goal)
+    PRGPU_CUDA_TRY(cudaMemcpy(n_goal, h->ng.p, b4, cudaMemcpyDeviceToHost));
+  return PRGPU_OK;
+}
+
+int prgpu_rrtc_batch_fetch(prgpu_rrtc_batch_t *h, uint32_t query, double *start_states,
+                           int32_t *start_parent, double *goal_states, int32_t *goal_parent,
+                           uint32_t *path_len, double *path, uint32_t max_path) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "rrtc_batch_fetch: NULL handle");
+  if (!h->ran || query >= h->n)
+    return fail(PRGPU_EINVAL, "rrtc_batch_fetch: no such query (or run() not called)");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->world->device));
+  const size_t M = h->dp.max_nodes, D = h->dp.dim;
+  uint32_t ns = 0, ng = 0;
+  int32_t cs = -1, cg = -1;
+  PRGPU_CUDA_TRY(cudaMemcpy(&ns, h->ns.as<uint32_t>() + query, 4, cudaMemcpyDeviceToHost));
+  PRGPU_CUDA_TRY(cudaMemcpy(&ng, h->ng.as<uint32_t>() + query, 4, cudaMemcpyDeviceToHost));
+  PRGPU_CUDA_TRY(cudaMemcpy(&cs, h->cs.as<int32_t>() + query, 4, cudaMemcpyDeviceToHost));
+  PRGPU_CUDA_TRY(cudaMemcpy(&cg, h->cg.as<int32_t>() + query, 4, cudaMemcpyDeviceToHost));
+  std::vector<double> S(ns * D), G(ng * D);
+  std::vector<int32_t> PS(ns), PG(ng);
+  if (ns) {
+    PRGPU_CUDA_TRY(cudaMemcpy(S.data(), h->ss.as<double>() + query * M * D, ns * D * 8, cudaMemcpyDeviceToHost));
+    PRGPU_CUDA_TRY(cudaMemcpy(PS.data(), h->sp.as<int32_t>() + query * M, ns * 4, cudaMemcpyDeviceToHost));
+  }
+  if (ng) {
+    PRGPU_CUDA_TRY(cudaMemcpy(G.data(), h->gs.as<double>() + query * M * D, ng * D * 8, cudaMemcpyDeviceToHost));
+    PRGPU_CUDA_TRY(cudaMemcpy(PG.data(), h->gp.as<int32_t>() + query * M, ng * 4, cudaMemcpyDeviceToHost));
+  }
+  if (start_states && ns)
+    std::memcpy(start_states, S.data(), ns * D * 8);
+  if (start_parent && ns)
+    std::memcpy(start_parent, PS.data(), ns * 4);
+  if (goal_states && ng)
+    std::memcpy(goal_states, G.data(), ng * D * 8);
+  if (goal_parent && ng)
+    std::memcpy(goal_parent, PG.data(), ng * 4);
+  // solution path: start chain reversed, then goal chain (pr_ompl/src/RRTConnect.cpp:338-363)
+  uint32_t len = 0;
+  if (cs >= 0 && cg >= 0) {
+    std::vector<int32_t> c1, c2;
+    for (int32_t s = cs; s >= 0; s = PS[s])
+      c1.push_back(s);
+    for (int32_t s = cg; s >= 0; s = PG[s])
+      c2.push_back(s);
+    len = (uint32_t)(c1.size() + c2.size());
+    if (path) {
+      if (len > max_path)
+        return fail(PRGPU_ELIMIT, "rrtc_batch_fetch: path buffer too small");
+      uint32_t o = 0;
+      for (int i = (int)c1.size() - 1; i >= 0; --i)
+        std::memcpy(path + (size_t)(o++) * D, S.data() + (size_t)c1[i] * D, D * 8);
+      for (size_t i = 0; i < c2.size(); ++i)
+        std::memcpy(path + (size_t)(o++) * D, G.data() + (size_t)c2[i] * D, D * 8);
+    }
+  }
+  if (path_len)
+    *path_len = len;
   return PRGPU_OK;
 }
 

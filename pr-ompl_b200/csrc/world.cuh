@@ -167,6 +167,14 @@ __device__ __forceinline__ bool state_valid(const DeviceWorld &w, const float4 *
   return true;
 }
 
+// out-of-line variant for kernels that test states from several places (keeps their register
+// footprint at the checker's own)
+template <int SP>
+__device__ __noinline__ bool state_valid_call(const DeviceWorld *wp, const float4 *s_os, const float4 *s_ob,
+                                              const double *q) {
+  return state_valid<SP>(*wp, s_os, s_ob, q);
+}
+
 // cooperative copy of the fp32 obstacle tables into shared memory
 __device__ __forceinline__ void load_obstacles(const DeviceWorld &w, float4 *s_os, float4 *s_ob) {
   for (int i = threadIdx.x; i < w.n_os; i += blockDim.x)
