@@ -1,0 +1,30 @@
+/* C entry points of libprgpu_plugin.so used by the parity tests: they drive the C++ OMPL-plugin
+ * mirror (pr_gpu::RRTConnect over GpuNearestNeighbors / GpuMotionValidator / CounterSampler)
+ * exactly the way an OMPL application would, and return the planner's trees. */
+#ifndef PLUGIN_TEST_API_H
+#define PLUGIN_TEST_API_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct {
+  int32_t status;
+  uint32_t iterations, n_start, n_goal, path_len, overflow;
+} plg_rrtc_result;
+void *plg_world_create(int device, int dof, const double *dh, int ns, const int32_t *link, const double *xyzr,
+                       int nos, const double *os, int nob, const double *ob);
+void plg_world_destroy(void *world);
+const char *plg_last_error(void);
+/* nn_kind: 0 = GpuNearestNeighbors (default of the planner). */
+int plg_rrtc_solve(void *world, int dim, const double *lo, const double *hi, const double *start,
+                   const double *goal, double range, const char *extension_type, double resolution_fraction,
+                   uint64_t seed, uint64_t query_id, uint32_t max_iters, uint32_t max_nodes, uint32_t max_path,
+                   plg_rrtc_result *res, double *start_states, int32_t *start_parent, double *goal_states,
+                   int32_t *goal_parent, double *path, uint32_t *planner_data_counts /* 4: vertices, edges, starts, goals */);
+/* exercises the OMPL-facing classes directly: returns 0 if every check passes */
+int plg_selftest_interfaces(void *world, const double *states, uint32_t n, uint8_t *is_valid_out,
+                            uint8_t *motion_out /* n-1 consecutive edges */, uint32_t *nearest_out /* n */);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,88 @@
+"""ctypes loader of libprgpu_plugin.so (the C++ OMPL-plugin mirror and its C test driver)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+c_vp = C.c_void_p
+
+
+class PlgResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_uint32), ("n_start", C.c_uint32),
+                ("n_goal", C.c_uint32), ("path_len", C.c_uint32), ("overflow", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(os.path.join(ROOT, "pr-ompl_b200", "libprgpu_plugin.so"))
+        L.plg_world_create.restype = c_vp
+        L.plg_world_create.argtypes = [C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.c_int, c_vp, C.c_int, c_vp]
+        L.plg_world_destroy.argtypes = [c_vp]
+        L.plg_last_error.restype = C.c_char_p
+        L.plg_rrtc_solve.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_char_p, C.c_double,
+                                     C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.POINTER(PlgResult), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.plg_selftest_interfaces.argtypes = [c_vp, c_vp, C.c_uint32, c_vp, c_vp, c_vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class PluginWorld:
+    def __init__(self, dh, link, xyzr, sph, box, device=0):
+        self.keep = [np.ascontiguousarray(dh, dtype=np.float64), np.ascontiguousarray(link, dtype=np.int32),
+                     np.ascontiguousarray(xyzr, dtype=np.float64), np.ascontiguousarray(sph, dtype=np.float64),
+                     np.ascontiguousarray(box, dtype=np.float64)]
+        dh, link, xyzr, sph, box = self.keep
+        self.dof = dh.shape[0]
+        self.h = lib().plg_world_create(device, self.dof, _p(dh), len(link), _p(link), _p(xyzr), len(sph), _p(sph),
+                                        len(box), _p(box))
+        if not self.h:
+            raise RuntimeError(lib().plg_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.plg_world_destroy(self.h)
+            self.h = None
+
+    def rrtc_solve(self, start, goal, lo, hi, rng=0.0, extension_type="ext-con", resolution_fraction=0.01, seed=0,
+                   query=0, max_iters=1000, max_nodes=20000, max_path=4096):
+        dim = self.dof
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        goal = np.ascontiguousarray(goal, dtype=np.float64)
+        lo = np.ascontiguousarray(np.broadcast_to(lo, (dim,)), dtype=np.float64)
+        hi = np.ascontiguousarray(np.broadcast_to(hi, (dim,)), dtype=np.float64)
+        res = PlgResult()
+        ss, gs = np.zeros((max_nodes, dim)), np.zeros((max_nodes, dim))
+        sp, gp = np.zeros(max_nodes, dtype=np.int32), np.zeros(max_nodes, dtype=np.int32)
+        path = np.zeros((max_path, dim))
+        pd = np.zeros(4, dtype=np.uint32)
+        rc = lib().plg_rrtc_solve(self.h, dim, _p(lo), _p(hi), _p(start), _p(goal), float(rng),
+                                  extension_type.encode(), float(resolution_fraction), int(seed), int(query),
+                                  int(max_iters), int(max_nodes), int(max_path), C.byref(res), _p(ss), _p(sp),
+                                  _p(gs), _p(gp), _p(path), _p(pd))
+        if rc != 0:
+            raise RuntimeError(lib().plg_last_error().decode())
+        assert res.overflow == 0
+        return dict(status=res.status, iterations=res.iterations, start_states=ss[:res.n_start].copy(),
+                    start_parent=sp[:res.n_start].copy(), goal_states=gs[:res.n_goal].copy(),
+                    goal_parent=gp[:res.n_goal].copy(), path=path[:res.path_len].copy()), pd
+
+    def selftest(self, states):
+        states = np.ascontiguousarray(states, dtype=np.float64)
+        n = states.shape[0]
+        v = np.zeros(n, dtype=np.uint8)
+        m = np.zeros(max(n - 1, 1), dtype=np.uint8)
+        nn = np.zeros(n, dtype=np.uint32)
+        rc = lib().plg_selftest_interfaces(self.h, _p(states), n, _p(v), _p(m), _p(nn))
+        if rc != 0:
+            raise RuntimeError(lib().plg_last_error().decode())
+        return v, m[:n - 1], nn

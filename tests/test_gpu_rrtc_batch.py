@@ -76,7 +76,7 @@ def test_batch_invalid_endpoints_and_caps(P, synth, gpu_world, oracle_world):
     assert s["status"][2] == 6                               # start == goal
     assert s["iterations"][3] <= 50
     for qi in (2, 3):  # and the oracle agrees on these too
-        ref = oracle_world.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, max_iters=50, max_nodes=64)
+        ref = oracle_world.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, seed=0, query=qi, max_iters=50)
         assert s["status"][qi] == ref["status"] and s["iterations"][qi] == ref["iterations"]
     with pytest.raises(ValueError):
         P.RrtcBatch(gpu_world, 1, -1, 1, extension_type="con-bad")
