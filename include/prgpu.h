@@ -168,6 +168,52 @@ int prgpu_rrtc_batch_fetch(prgpu_rrtc_batch_t *h, uint32_t query, double *start_
                            int32_t *start_parent, double *goal_states, int32_t *goal_parent,
                            uint32_t *path_len, double *path, uint32_t max_path);
 
+/* ------------------------------------------------------------------------------------
+ * K3: NNF (Nearest-Neighbor Frechet) end-effector path following
+ * (NNFrechet::setup / solve, frechet/src/NNFrechet.cpp:184-221, :95-178).
+ * The host planner supplies what the reference obtains through its callbacks: the
+ * sub-sampled reference poses (subsampleRefPath :235-252) and the IK solutions of every
+ * layer (sampleIKNodes :282-308; poses are recomputed with the world's FK as at :295).
+ * create() = buildNNGraph + buildTensorProductGraph: suffix-masked kNN (findKnnNodes), the D
+ * sub-sampled vertices of every edge with their FK, and the tensor-product DAG in flat
+ * arrays.  solve() = the LazySP loop: wavefront min-bottleneck search, path extraction,
+ * evaluateEdge on the path's NN edges (accumulated-alpha discretisation at
+ * check_resolution), knock-out of the first colliding edge, repeat.
+ * Task-space metric: Euclidean distance between pose translations.
+ * ---------------------------------------------------------------------------------- */
+typedef struct prgpu_nnf prgpu_nnf_t;
+typedef struct {
+  int32_t num_nn;          /* mNumNN (default 5, frechet/include/NNFrechet.hpp:269) */
+  int32_t discretization;  /* mDiscretization D >= 1 (default 3, :274) */
+  double check_resolution; /* mCheckResolution (0.05, :277) */
+} prgpu_nnf_params;
+typedef struct {
+  uint32_t n_vertices, n_edges, n_ik;
+  uint32_t lazy_iters;  /* TPG searches executed */
+  int32_t solved;       /* 1: collision-free path found */
+  double final_error;   /* mFinalError: max node weight over non-dummy path nodes (:615-645) */
+  double goal_cost;     /* bottleneck cost of the goal in the last search */
+  uint32_t path_len;
+  uint32_t n_evaluated, n_collisions;
+  uint32_t overflow;
+} prgpu_nnf_result;
+/* ref_pose12: R x 12; layer_counts: R (IK solutions per reference index); ik_states: sum(counts) x dof
+ * in NN-graph vertex order: layer 0, layer R-1, then layers 1..R-2 (the order of buildNNGraph). */
+int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, const double *ref_pose12,
+                     const uint32_t *layer_counts, const double *ik_states, prgpu_nnf_t **out);
+int prgpu_nnf_destroy(prgpu_nnf_t *h);
+int prgpu_nnf_graph_info(prgpu_nnf_t *h, uint32_t *n_vertices, uint32_t *n_edges, uint32_t *n_ik);
+/* neighbours chosen for every IK node (n_ik x num_nn NN-graph vertex ids, PRGPU_INVALID_INDEX padded) */
+int prgpu_nnf_get_knn(prgpu_nnf_t *h, uint32_t *knn);
+/* all NN-graph vertices: configuration (n_vertices x dof; zeros for the two dummies) and pose */
+int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12);
+/* path_vertices: NN-graph vertex ids of the solution (cap_path entries); goal_cost_trace: goal
+ * cost of every search (max_lazy_iters entries) or NULL.  May be called again to continue. */
+int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *res, uint32_t *path_vertices,
+                    uint32_t cap_path, double *goal_cost_trace);
+/* duration of the latest wavefront search kernel (measurement aid, always on) */
+int prgpu_nnf_last_dp_ms(prgpu_nnf_t *h, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,31 @@ int orc_rrtc_solve(const void *world, int dim, const double *lo, const double *h
                    double resolution_fraction, uint64_t seed, uint64_t query_id, uint32_t max_iters,
                    uint32_t max_nodes, uint32_t max_path, orc_rrtc_result *res, double *start_states,
                    int32_t *start_parent, double *goal_states, int32_t *goal_parent, double *path);
+/* ---- NNF (flat-array port of frechet/src/{NNFrechet,LPAStar,util}.cpp; the literal reference
+ * needs Boost.Graph + Eigen, absent here, so there is no compiled-reference counterpart) ---- */
+/* util.cpp:3-21 linDoubleSpace/linIntSpace: (int)(min + i*delta), delta = (max-min)/(N-1) */
+void orc_lin_int_space(double mn, double mx, uint64_t n, int32_t *out);
+/* NNFrechet.cpp:398-448: IK budget per super-sampled reference index: counts[0] = counts[R-1] = M,
+ * interior = multinomial of W*M - 2M draws of std::uniform_int_distribution<int>(1, R-2) on a
+ * std::default_random_engine seeded with `seed` (a fresh distribution object per draw, :324). */
+void orc_nnf_layer_counts(int seed, int R, int W, int M, uint32_t *counts);
+typedef struct {
+  uint32_t n_vertices, n_edges, n_ik;
+  uint32_t lazy_iters;      /* LazySP iterations executed (TPG searches) */
+  int32_t solved;           /* 1: collision-free path found; 0: no path left / iteration cap */
+  double final_error;       /* mFinalError of the last extracted path (NNFrechet.cpp:615-645) */
+  double goal_cost;         /* bottleneck cost g[goal] of the last search */
+  uint32_t path_len;        /* NN-graph vertices on the final path */
+  uint32_t n_evaluated, n_collisions;
+  uint32_t overflow;
+} orc_nnf_result;
+/* ref_pose12: R x 12 (sub-sampled reference path); layer_counts: R; ik_states: n_ik x dof in vertex
+ * order (layer 0, layer R-1, then layers 1..R-2).  Task metric = Euclidean distance of the pose
+ * translations.  knn_out: n_ik x k neighbour vertex ids (0xFFFFFFFF padded). */
+int orc_nnf_run(const void *world, int R, const double *ref_pose12, int k, int D, double check_res,
+                const uint32_t *layer_counts, const double *ik_states, uint32_t max_lazy_iters, int nthreads,
+                orc_nnf_result *res, uint32_t *knn_out, double *vertex_states, double *vertex_pose12,
+                uint32_t cap_vertices, uint32_t *path_vertices, uint32_t cap_path, double *goal_cost_trace);
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,25 @@ SIGNATURES = {
     "prgpu_rrtc_batch_summary": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "prgpu_rrtc_batch_fetch": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, c_vp, c_vp, C.POINTER(C.c_uint32),
                                          c_vp, C.c_uint32]),
+    "prgpu_nnf_create": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
+    "prgpu_nnf_destroy": (C.c_int, [c_vp]),
+    "prgpu_nnf_graph_info": (C.c_int, [c_vp, c_u32p, c_u32p, c_u32p]),
+    "prgpu_nnf_get_knn": (C.c_int, [c_vp, c_vp]),
+    "prgpu_nnf_get_vertices": (C.c_int, [c_vp, c_vp, c_vp]),
+    "prgpu_nnf_solve": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, C.c_uint32, c_vp]),
+    "prgpu_nnf_last_dp_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
 }
+
+
+class NnfParams(C.Structure):
+    _fields_ = [("num_nn", C.c_int32), ("discretization", C.c_int32), ("check_resolution", C.c_double)]
+
+
+class NnfResult(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint32), ("n_edges", C.c_uint32), ("n_ik", C.c_uint32),
+                ("lazy_iters", C.c_uint32), ("solved", C.c_int32), ("final_error", C.c_double),
+                ("goal_cost", C.c_double), ("path_len", C.c_uint32), ("n_evaluated", C.c_uint32),
+                ("n_collisions", C.c_uint32), ("overflow", C.c_uint32)]
 
 
 class RrtcParams(C.Structure):
@@ -307,3 +325,57 @@ class RrtcBatch:
                                             C.byref(plen), _ptr(path), max_path))
         return dict(start_states=ss[:ns], start_parent=sp[:ns], goal_states=gs[:ng], goal_parent=gp[:ng],
                     path=path[:plen.value].copy())
+
+
+class Nnf:
+    """NNF planner state on the device: NN graph + tensor-product DAG (setup) and LazySP (solve)."""
+
+    def __init__(self, world, ref_pose12, layer_counts, ik_states, num_nn=5, discretization=3,
+                 check_resolution=0.05):
+        self.world = world
+        self.k = num_nn
+        ref = np.ascontiguousarray(ref_pose12, dtype=np.float64).reshape(-1, 12)
+        counts = np.ascontiguousarray(layer_counts, dtype=np.uint32)
+        ik = np.ascontiguousarray(ik_states, dtype=np.float64).reshape(-1, world.dof)
+        assert len(counts) == len(ref) and counts.sum() == len(ik)
+        p = NnfParams(num_nn, discretization, check_resolution)
+        h = c_vp()
+        _check(lib().prgpu_nnf_create(world.h, C.byref(p), len(ref), _ptr(ref), _ptr(counts), _ptr(ik),
+                                      C.byref(h)))
+        self.h = h
+        nv, ne, ni = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().prgpu_nnf_graph_info(self.h, C.byref(nv), C.byref(ne), C.byref(ni)))
+        self.n_vertices, self.n_edges, self.n_ik = nv.value, ne.value, ni.value
+
+    def close(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.prgpu_nnf_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def knn(self):
+        out = np.empty((self.n_ik, self.k), dtype=np.uint32)
+        _check(lib().prgpu_nnf_get_knn(self.h, _ptr(out)))
+        return out
+
+    def vertices(self):
+        st = np.empty((self.n_vertices, self.world.dof))
+        po = np.empty((self.n_vertices, 12))
+        _check(lib().prgpu_nnf_get_vertices(self.h, _ptr(st), _ptr(po)))
+        return st, po
+
+    def solve(self, max_lazy_iters=1000, cap_path=65536):
+        res = NnfResult()
+        path = np.zeros(cap_path, dtype=np.uint32)
+        trace = np.zeros(max_lazy_iters, dtype=np.float64)
+        _check(lib().prgpu_nnf_solve(self.h, max_lazy_iters, C.byref(res), _ptr(path), cap_path, _ptr(trace)))
+        out = {f[0]: getattr(res, f[0]) for f in NnfResult._fields_}
+        out["path"] = path[:res.path_len].copy()
+        out["goal_cost_trace"] = trace[:res.lazy_iters].copy()
+        return out
+
+    def last_dp_ms(self):
+        ms = C.c_float()
+        _check(lib().prgpu_nnf_last_dp_ms(self.h, C.byref(ms)))
+        return ms.value

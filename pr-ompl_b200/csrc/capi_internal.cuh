@@ -1,0 +1,52 @@
+// Handle structs shared by the C-ABI translation units (capi.cu, capi_nnf.cu).
+#pragma once
+#include "check_motion.cuh"
+#include "knn.cuh"
+
+namespace prgpu {
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes)
+      return PRGPU_OK;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    PRGPU_CUDA_TRY(cudaMalloc(&p, need));
+    bytes = need;
+    return PRGPU_OK;
+  }
+  void release() {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T> T *as() { return static_cast<T *>(p); }
+};
+} // namespace prgpu
+
+struct prgpu_knn {
+  int device = 0, dim = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  double *pts = nullptr; // SoA, dim x stride
+  uint64_t stride = 0, n = 0;
+  uint32_t index_base = 0;
+  prgpu::KnnScratch scratch;
+  prgpu::KernelTimer timer;
+  prgpu::DevBuf stage, d_q, d_lo, d_idx, d_dist;
+};
+
+struct prgpu_world {
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  prgpu::DeviceWorld host; // copy of the device struct (device pointers inside)
+  prgpu::DeviceWorld *dev = nullptr;
+  prgpu::DevBuf os_f, ob_f, os_d, ob_d;
+  prgpu::DevBuf d_a, d_b, d_valid, d_pose;
+  prgpu::KernelTimer timer;
+};
+

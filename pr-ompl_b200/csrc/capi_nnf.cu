@@ -1,0 +1,555 @@
+// C ABI of the NNF path (include/prgpu.h, prgpu_nnf_*): host-side graph bookkeeping in flat
+// arrays around the K1 / K2 / K3 kernels.  What the reference keeps in three Boost graphs with
+// string-keyed hash maps (frechet/src/NNFrechet.cpp:467-599) is here: vertex ids in creation
+// order, an edge list in creation order, a CSR of predecessors and a level-sorted vertex order.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include "capi_internal.cuh"
+#include "nnf.cuh"
+
+using namespace prgpu;
+
+struct prgpu_nnf {
+  prgpu_world *world = nullptr;
+  prgpu_nnf_params params;
+  int R = 0, dof = 0;
+  uint32_t V = 0, E = 0, nIk = 0, Lv = 0;
+  // host graph
+  std::vector<double> ref_pose;                      // R x 12
+  std::vector<uint32_t> knn;                         // nIk x k (vertex ids)
+  std::vector<std::pair<uint32_t, uint32_t>> edges;  // creation order
+  std::vector<uint32_t> pred_off_v;                  // V+1, by vertex id
+  std::vector<std::pair<uint32_t, uint32_t>> pred_v; // (pred vertex, edge id), creation order
+  std::vector<uint32_t> pos_of_vertex, vertex_of_pos;
+  std::vector<double> states, pose;                  // V x dof, V x 12 (downloaded)
+  std::vector<uint8_t> evaluated, blocked;           // per edge (reference semantics)
+  std::vector<int8_t> known;                         // per edge: -1 unknown, 0 collides, 1 free
+  // device
+  DevBuf d_states, d_pose, d_lvl_start, d_level, d_pred_off, d_pred_pos, d_pred_eid, d_blocked, d_pnn, d_pref, d_B,
+      d_path, d_pn, d_cost;
+  NnfGraphDev g;
+  KernelTimer timer;
+  uint32_t total_iters = 0, n_evaluated = 0, n_collisions = 0;
+};
+
+namespace {
+template <class T> int upload(DevBuf &b, const std::vector<T> &v, cudaStream_t s) {
+  int rc = b.reserve(std::max<size_t>(v.size() * sizeof(T), 16));
+  if (rc != PRGPU_OK)
+    return rc;
+  if (!v.empty())
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return PRGPU_OK;
+}
+double host_task_distance(const double *a12, const double *b12) {
+  volatile double dx = a12[3] - b12[3], dy = a12[7] - b12[7], dz = a12[11] - b12[11];
+  volatile double xx = dx * dx, yy = dy * dy, zz = dz * dz;
+  volatile double s = xx + yy;
+  s = s + zz;
+  return std::sqrt(s);
+}
+} // namespace
+
+extern "C" {
+
+int prgpu_nnf_destroy(prgpu_nnf_t *h) {
+  if (!h)
+    return PRGPU_OK;
+  cudaSetDevice(h->world->device);
+  cudaStreamSynchronize(h->world->stream);
+  for (DevBuf *b : {&h->d_states, &h->d_pose, &h->d_lvl_start, &h->d_level, &h->d_pred_off, &h->d_pred_pos,
+                    &h->d_pred_eid, &h->d_blocked, &h->d_pnn, &h->d_pref, &h->d_B, &h->d_path, &h->d_pn, &h->d_cost})
+    b->release();
+  h->timer.destroy();
+  delete h;
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, const double *ref_pose12,
+                     const uint32_t *layer_counts, const double *ik_states, prgpu_nnf_t **out) {
+  if (!out)
+    return fail(PRGPU_EINVAL, "nnf_create: out is NULL");
+  *out = nullptr;
+  if (!w || !params || !ref_pose12 || !layer_counts)
+    return fail(PRGPU_EINVAL, "nnf_create: NULL argument");
+  if (R < 2)
+    return fail(PRGPU_EINVAL, "nnf_create: referencePath is empty!"); // setRefPath, NNFrechet.cpp:24-25
+  if (params->num_nn <= 0 || params->num_nn > PRGPU_MAX_K)
+    return fail(PRGPU_EINVAL, "nnf_create: numNN must be positive! (and <= PRGPU_MAX_K)");
+  if (params->discretization <= 0)
+    return fail(PRGPU_EINVAL, "nnf_create: discretization must be positive!");
+  if (!(params->check_resolution > 0.0))
+    return fail(PRGPU_EINVAL, "nnf_create: check_resolution must be positive");
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  cudaStream_t s = w->stream;
+  const int dof = w->host.dof, k = params->num_nn, D = params->discretization;
+
+  prgpu_nnf *h = new prgpu_nnf();
+  h->world = w;
+  h->params = *params;
+  h->R = R;
+  h->dof = dof;
+  h->ref_pose.assign(ref_pose12, ref_pose12 + (size_t)R * 12);
+  uint64_t N = 0;
+  for (int r = 0; r < R; ++r)
+    N += layer_counts[r];
+  if (N && !ik_states) {
+    delete h;
+    return fail(PRGPU_EINVAL, "nnf_create: ik_states is NULL");
+  }
+  h->nIk = (uint32_t)N;
+  const uint32_t M0 = layer_counts[0], ML = layer_counts[R - 1];
+  const uint32_t nInterior = (uint32_t)N - M0 - ML;
+#define NNF_TRY(expr)                                                                              \
+  do {                                                                                             \
+    int _rc = (expr);                                                                              \
+    if (_rc != PRGPU_OK) {                                                                         \
+      prgpu_nnf_destroy(h);                                                                        \
+      return _rc;                                                                                  \
+    }                                                                                              \
+  } while (0)
+#define NNF_CUDA(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      prgpu_nnf_destroy(h);                                                                        \
+      return fail(PRGPU_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    }                                                                                              \
+  } while (0)
+
+  // ---- findKnnNodes for every node of layers 0..R-2 (NNFrechet.cpp:452-459) --------------------
+  // candidates = strictly deeper layers = [suffix of the interior nodes] U [the last layer];
+  // two device indices whose reported index is the NN-graph vertex id, merged per query under
+  // (distance, vertex id) -- the order of util.cpp:49.
+  const uint32_t nq = (uint32_t)N - ML; // queries: layer 0 then interior layers
+  h->knn.assign((size_t)N * k, PRGPU_INVALID_INDEX);
+  if (nq > 0) {
+    DevBuf d_ik, d_q, d_lo, d_pi, d_pd, d_oi, d_od;
+    auto cleanup = [&]() {
+      for (DevBuf *b : {&d_ik, &d_q, &d_lo, &d_pi, &d_pd, &d_oi, &d_od})
+        b->release();
+    };
+    prgpu_knn_t *A = nullptr, *B = nullptr;
+    int rc = PRGPU_OK;
+    do {
+      if ((rc = d_ik.reserve(std::max<size_t>(N * dof * 8, 16))) != PRGPU_OK)
+        break;
+      cudaMemcpyAsync(d_ik.p, ik_states, N * dof * 8, cudaMemcpyHostToDevice, s);
+      if ((rc = prgpu_knn_create(w->device, dof, std::max<uint32_t>(ML, 1), &A)) != PRGPU_OK)
+        break;
+      if ((rc = prgpu_knn_create(w->device, dof, std::max<uint32_t>(nInterior, 1), &B)) != PRGPU_OK)
+        break;
+      prgpu_knn_set_index_base(A, 2 + M0);
+      prgpu_knn_set_index_base(B, 2 + M0 + ML);
+      if ((rc = prgpu_knn_add_device(A, d_ik.as<double>() + (size_t)M0 * dof, ML, s)) != PRGPU_OK)
+        break;
+      if ((rc = prgpu_knn_add_device(B, d_ik.as<double>() + (size_t)(M0 + ML) * dof, nInterior, s)) != PRGPU_OK)
+        break;
+      // queries and their suffix bounds into the interior index
+      std::vector<double> q((size_t)nq * dof);
+      std::memcpy(q.data(), ik_states, (size_t)M0 * dof * 8);
+      std::memcpy(q.data() + (size_t)M0 * dof, ik_states + (size_t)(M0 + ML) * dof, (size_t)nInterior * dof * 8);
+      std::vector<uint32_t> lo(nq, 0);
+      uint32_t cum = 0, qi = M0;
+      for (int r = 1; r <= R - 2; ++r) {
+        cum += layer_counts[r]; // first interior index of layer r+1
+        for (uint32_t i = 0; i < layer_counts[r]; ++i)
+          lo[qi++] = cum;
+      }
+      if ((rc = upload(d_q, q, s)) != PRGPU_OK || (rc = upload(d_lo, lo, s)) != PRGPU_OK)
+        break;
+      const size_t part = (size_t)nq * k;
+      if ((rc = d_pi.reserve(2 * part * 4)) != PRGPU_OK || (rc = d_pd.reserve(2 * part * 8)) != PRGPU_OK ||
+          (rc = d_oi.reserve(part * 4)) != PRGPU_OK || (rc = d_od.reserve(part * 8)) != PRGPU_OK)
+        break;
+      if ((rc = prgpu_knn_nearest_k_device(A, d_q.as<double>(), nq, k, nullptr, d_pi.as<uint32_t>(),
+                                           d_pd.as<double>(), s)) != PRGPU_OK)
+        break;
+      if ((rc = prgpu_knn_nearest_k_device(B, d_q.as<double>(), nq, k, d_lo.as<uint32_t>(),
+                                           d_pi.as<uint32_t>() + part, d_pd.as<double>() + part, s)) != PRGPU_OK)
+        break;
+      if ((rc = topk_merge(d_pi.as<uint32_t>(), d_pd.as<double>(), 2, nq, k, d_oi.as<uint32_t>(), d_od.as<double>(),
+                           s)) != PRGPU_OK)
+        break;
+      std::vector<uint32_t> res(part);
+      if (cudaMemcpyAsync(res.data(), d_oi.p, part * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess) {
+        rc = fail(PRGPU_ECUDA, "nnf_create: kNN download failed");
+        break;
+      }
+      // rows back into IK order (layer 0 | last layer (none) | interior)
+      std::memcpy(h->knn.data(), res.data(), (size_t)M0 * k * 4);
+      std::memcpy(h->knn.data() + (size_t)(M0 + ML) * k, res.data() + (size_t)M0 * k, (size_t)nInterior * k * 4);
+    } while (0);
+    cudaStreamSynchronize(s);
+    prgpu_knn_destroy(A);
+    prgpu_knn_destroy(B);
+    cleanup();
+    NNF_TRY(rc);
+  }
+
+  // ---- NN graph in creation order (:407-464) -----------------------------------------------------
+  const uint32_t c0 = 0, c1 = 1;
+  auto ikVertex = [](uint32_t i) { return 2 + i; };
+  for (uint32_t i = 0; i < M0; ++i)
+    h->edges.emplace_back(c0, ikVertex(i)); // :423
+  for (uint32_t i = 0; i < ML; ++i)
+    h->edges.emplace_back(ikVertex(M0 + i), c1); // :435
+  std::vector<uint32_t> sub_src, sub_dst, sub_step, sub_layer;
+  std::vector<uint32_t> layer_of_ik(N);
+  {
+    uint32_t i = 0;
+    for (; i < M0; ++i)
+      layer_of_ik[i] = 0;
+    for (uint32_t j = 0; j < ML; ++j)
+      layer_of_ik[i++] = (uint32_t)(R - 1);
+    for (int r = 1; r <= R - 2; ++r)
+      for (uint32_t j = 0; j < layer_counts[r]; ++j)
+        layer_of_ik[i++] = (uint32_t)r;
+  }
+  uint32_t nextVertex = 2 + (uint32_t)N;
+  auto expand = [&](uint32_t ik) { // addSubsampledEdge for every neighbour of one node (:461-462)
+    for (int j = 0; j < k; ++j) {
+      const uint32_t nbr = h->knn[(size_t)ik * k + j];
+      if (nbr == PRGPU_INVALID_INDEX)
+        break;
+      uint32_t prev = ikVertex(ik);
+      for (int i = 0; i < D; ++i) {
+        const uint32_t a = nextVertex++;
+        sub_src.push_back(ikVertex(ik));
+        sub_dst.push_back(nbr);
+        sub_step.push_back((uint32_t)i);
+        sub_layer.push_back(layer_of_ik[ik]);
+        h->edges.emplace_back(prev, a); // :388
+        if (i == D - 1)
+          h->edges.emplace_back(a, nbr); // :391
+        prev = a;
+      }
+    }
+  };
+  for (uint32_t i = 0; i < M0; ++i) // refIndex 0
+    expand(i);
+  for (uint32_t i = M0 + ML; i < N; ++i) // refIndex 1..R-2 (vertex order == layer order)
+    expand(i);
+  const uint32_t V = nextVertex, E = (uint32_t)h->edges.size();
+  h->V = V;
+  h->E = E;
+
+  // ---- vertex data on the device: states, FK poses ----------------------------------------------
+  NNF_TRY(h->d_states.reserve((size_t)V * dof * 8));
+  NNF_TRY(h->d_pose.reserve((size_t)V * 12 * 8));
+  NNF_CUDA(cudaMemsetAsync(h->d_states.p, 0, 2 * (size_t)dof * 8, s));
+  if (N)
+    NNF_CUDA(cudaMemcpyAsync(h->d_states.as<double>() + 2 * (size_t)dof, ik_states, N * dof * 8,
+                             cudaMemcpyHostToDevice, s));
+  NNF_CUDA(cudaMemcpyAsync(h->d_pose.p, ref_pose12, 12 * 8, cudaMemcpyHostToDevice, s)); // c0 pose (:409)
+  NNF_CUDA(cudaMemcpyAsync(h->d_pose.as<double>() + 12, ref_pose12 + 12 * (size_t)(R - 1), 12 * 8,
+                           cudaMemcpyHostToDevice, s)); // c1 pose (:414)
+  NNF_TRY(fk_launch(w->host, w->dev, h->d_states.as<double>() + 2 * (size_t)dof, N,
+                    h->d_pose.as<double>() + 2 * 12, s)); // sampleIKNodes :295
+  {
+    DevBuf d_src, d_dst, d_step;
+    int rc = upload(d_src, sub_src, s);
+    if (rc == PRGPU_OK)
+      rc = upload(d_dst, sub_dst, s);
+    if (rc == PRGPU_OK)
+      rc = upload(d_step, sub_step, s);
+    if (rc == PRGPU_OK)
+      rc = nnf_subsample_launch(w->dev, dof, (uint32_t)sub_src.size(), 2 + (uint32_t)N, d_src.as<uint32_t>(),
+                                d_dst.as<uint32_t>(), d_step.as<uint32_t>(), D, h->d_states.as<double>(),
+                                h->d_pose.as<double>(), s);
+    cudaStreamSynchronize(s);
+    d_src.release();
+    d_dst.release();
+    d_step.release();
+    NNF_TRY(rc);
+  }
+  h->states.resize((size_t)V * dof);
+  h->pose.resize((size_t)V * 12);
+  NNF_CUDA(cudaMemcpyAsync(h->states.data(), h->d_states.p, (size_t)V * dof * 8, cudaMemcpyDeviceToHost, s));
+  NNF_CUDA(cudaMemcpyAsync(h->pose.data(), h->d_pose.p, (size_t)V * 12 * 8, cudaMemcpyDeviceToHost, s));
+
+  // ---- predecessors (by vertex, creation order), topological levels, level-sorted order ---------
+  h->pred_off_v.assign(V + 1, 0);
+  for (auto &e : h->edges)
+    h->pred_off_v[e.second + 1]++;
+  for (uint32_t v = 0; v < V; ++v)
+    h->pred_off_v[v + 1] += h->pred_off_v[v];
+  h->pred_v.resize(E);
+  {
+    std::vector<uint32_t> cur(h->pred_off_v.begin(), h->pred_off_v.end() - 1);
+    for (uint32_t e = 0; e < E; ++e)
+      h->pred_v[cur[h->edges[e].second]++] = std::make_pair(h->edges[e].first, e);
+  }
+  // level: c0 = 0; IK node of layer r = 1 + r(D+1); i-th sub-sampled vertex of an edge leaving
+  // layer r = 1 + r(D+1) + 1 + i; c1 = 2 + (R-1)(D+1)
+  const uint32_t Lv = 3 + (uint32_t)(R - 1) * (uint32_t)(D + 1);
+  h->Lv = Lv;
+  std::vector<uint32_t> level(V);
+  level[c0] = 0;
+  level[c1] = Lv - 1;
+  for (uint32_t i = 0; i < N; ++i)
+    level[ikVertex(i)] = 1 + layer_of_ik[i] * (uint32_t)(D + 1);
+  for (size_t i = 0; i < sub_src.size(); ++i)
+    level[2 + N + i] = 1 + sub_layer[i] * (uint32_t)(D + 1) + 1 + sub_step[i];
+  std::vector<uint32_t> lvl_start(Lv + 1, 0);
+  for (uint32_t v = 0; v < V; ++v)
+    lvl_start[level[v] + 1]++;
+  for (uint32_t l = 0; l < Lv; ++l)
+    lvl_start[l + 1] += lvl_start[l];
+  h->pos_of_vertex.resize(V);
+  h->vertex_of_pos.resize(V);
+  {
+    std::vector<uint32_t> cur(lvl_start.begin(), lvl_start.end() - 1);
+    for (uint32_t v = 0; v < V; ++v) { // stable: vertex id order inside a level
+      const uint32_t p = cur[level[v]]++;
+      h->pos_of_vertex[v] = p;
+      h->vertex_of_pos[p] = v;
+    }
+  }
+  std::vector<uint32_t> level_s(V), pred_off_s(V + 1, 0), pred_pos(E), pred_eid(E);
+  for (uint32_t p = 0; p < V; ++p) {
+    const uint32_t v = h->vertex_of_pos[p];
+    level_s[p] = level[v];
+    pred_off_s[p + 1] = pred_off_s[p] + (h->pred_off_v[v + 1] - h->pred_off_v[v]);
+  }
+  for (uint32_t p = 0; p < V; ++p) {
+    const uint32_t v = h->vertex_of_pos[p];
+    uint32_t o = pred_off_s[p];
+    for (uint32_t e = h->pred_off_v[v]; e < h->pred_off_v[v + 1]; ++e, ++o) {
+      pred_pos[o] = h->pos_of_vertex[h->pred_v[e].first];
+      pred_eid[o] = h->pred_v[e].second;
+    }
+  }
+  NNF_TRY(upload(h->d_lvl_start, lvl_start, s));
+  NNF_TRY(upload(h->d_level, level_s, s));
+  NNF_TRY(upload(h->d_pred_off, pred_off_s, s));
+  NNF_TRY(upload(h->d_pred_pos, pred_pos, s));
+  NNF_TRY(upload(h->d_pred_eid, pred_eid, s));
+  h->evaluated.assign(E, 0);
+  h->blocked.assign(E, 0);
+  h->known.assign(E, -1);
+  NNF_TRY(upload(h->d_blocked, h->blocked, s));
+  {
+    DevBuf d_vop;
+    int rc = upload(d_vop, h->vertex_of_pos, s);
+    if (rc == PRGPU_OK)
+      rc = h->d_pnn.reserve((size_t)V * 3 * 8);
+    if (rc == PRGPU_OK)
+      rc = nnf_translations_launch(h->d_pose.as<double>(), d_vop.as<uint32_t>(), V, h->d_pnn.as<double>(), s);
+    cudaStreamSynchronize(s);
+    d_vop.release();
+    NNF_TRY(rc);
+  }
+  {
+    std::vector<double> pref((size_t)R * 3);
+    for (int r = 0; r < R; ++r) {
+      pref[3 * r + 0] = ref_pose12[12 * (size_t)r + 3];
+      pref[3 * r + 1] = ref_pose12[12 * (size_t)r + 7];
+      pref[3 * r + 2] = ref_pose12[12 * (size_t)r + 11];
+    }
+    NNF_TRY(upload(h->d_pref, pref, s));
+  }
+  NNF_TRY(h->d_B.reserve((size_t)R * V * 8));
+  NNF_TRY(h->d_path.reserve(((size_t)R + Lv + 8) * 2 * 4));
+  NNF_TRY(h->d_pn.reserve(16));
+  NNF_TRY(h->d_cost.reserve(16));
+  NNF_TRY(h->timer.enable(true));
+  NNF_CUDA(cudaStreamSynchronize(s));
+
+  NnfGraphDev &g = h->g;
+  g.R = R;
+  g.V = V;
+  g.Lv = Lv;
+  g.lvl_start = h->d_lvl_start.as<uint32_t>();
+  g.level = h->d_level.as<uint32_t>();
+  g.pred_off = h->d_pred_off.as<uint32_t>();
+  g.pred_pos = h->d_pred_pos.as<uint32_t>();
+  g.pred_eid = h->d_pred_eid.as<uint32_t>();
+  g.blocked = h->d_blocked.as<uint8_t>();
+  g.pnn = h->d_pnn.as<double>();
+  g.pref = h->d_pref.as<double>();
+  g.B = h->d_B.as<double>();
+  g.start_pos = h->pos_of_vertex[c0];
+  g.goal_pos = h->pos_of_vertex[c1];
+  *out = h;
+  return PRGPU_OK;
+#undef NNF_TRY
+#undef NNF_CUDA
+}
+
+int prgpu_nnf_graph_info(prgpu_nnf_t *h, uint32_t *n_vertices, uint32_t *n_edges, uint32_t *n_ik) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "nnf_graph_info: NULL handle");
+  if (n_vertices)
+    *n_vertices = h->V;
+  if (n_edges)
+    *n_edges = h->E;
+  if (n_ik)
+    *n_ik = h->nIk;
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_get_knn(prgpu_nnf_t *h, uint32_t *knn) {
+  if (!h || !knn)
+    return fail(PRGPU_EINVAL, "nnf_get_knn: NULL argument");
+  std::memcpy(knn, h->knn.data(), h->knn.size() * 4);
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "nnf_get_vertices: NULL handle");
+  if (states)
+    std::memcpy(states, h->states.data(), h->states.size() * 8);
+  if (pose12)
+    std::memcpy(pose12, h->pose.data(), h->pose.size() * 8);
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_last_dp_ms(prgpu_nnf_t *h, float *ms) {
+  if (!h || !ms)
+    return fail(PRGPU_EINVAL, "nnf_last_dp_ms: NULL argument");
+  return h->timer.read(ms);
+}
+
+int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *res, uint32_t *path_vertices,
+                    uint32_t cap_path, double *goal_cost_trace) {
+  if (!h || !res)
+    return fail(PRGPU_EINVAL, "nnf_solve: NULL argument");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->world->device));
+  cudaStream_t s = h->world->stream;
+  const int R = h->R, dof = h->dof;
+  const uint32_t V = h->V, c0 = 0, c1 = 1;
+  std::memset(res, 0, sizeof(*res));
+  res->n_vertices = V;
+  res->n_edges = h->E;
+  res->n_ik = h->nIk;
+  const uint32_t cap_pairs = (uint32_t)R + h->Lv + 8;
+  std::vector<uint32_t> tp(2 * (size_t)cap_pairs);
+  std::vector<uint32_t> finalPath;
+  bool solutionFound = false;
+  uint32_t iters = 0;
+  while (iters < max_lazy_iters) { // NNFrechet.cpp:106
+    int rc = nnf_dp_launch(h->g, h->world->sm_count, s, &h->timer); // computeShortestPath :109-110
+    if (rc != PRGPU_OK)
+      return rc;
+    rc = nnf_backtrack_launch(h->g, h->d_path.as<uint32_t>(), cap_pairs, h->d_pn.as<uint32_t>(),
+                              h->d_cost.as<double>(), s);
+    if (rc != PRGPU_OK)
+      return rc;
+    uint32_t np = 0;
+    double goalCost = 0.0;
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(&np, h->d_pn.p, 4, cudaMemcpyDeviceToHost, s));
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(&goalCost, h->d_cost.p, 8, cudaMemcpyDeviceToHost, s));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+    if (goal_cost_trace)
+      goal_cost_trace[iters] = goalCost;
+    ++iters;
+    ++h->total_iters;
+    res->goal_cost = goalCost;
+    if (np == 0) // search found no path (:112-113)
+      break;
+    if (np == 0xFFFFFFFFu || np > cap_pairs)
+      return fail(PRGPU_ECUDA, "nnf_solve: inconsistent bottleneck table while backtracking");
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(tp.data(), h->d_path.p, (size_t)np * 8, cudaMemcpyDeviceToHost, s));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+
+    // extractNNPath (:615-645); the device path runs goal -> start
+    std::vector<uint32_t> nnPath;
+    double bottleneck = 0;
+    for (uint32_t i = np; i-- > 0;) {
+      const uint32_t r = tp[2 * i], v = h->vertex_of_pos[tp[2 * i + 1]];
+      if (v == c0 || v == c1)
+        continue;
+      if (nnPath.empty() || nnPath.back() != v)
+        nnPath.push_back(v);
+      const double c = host_task_distance(h->ref_pose.data() + 12 * (size_t)r, h->pose.data() + 12 * (size_t)v);
+      if (c > bottleneck)
+        bottleneck = c;
+    }
+    res->final_error = bottleneck;
+
+    // edges of the path; evaluate the not-yet-known ones in one batch (evaluateEdge is a pure
+    // function of the edge, so knowing a verdict early is invisible to the LazySP bookkeeping)
+    std::vector<uint32_t> eids;
+    for (size_t i = 0; i + 1 < nnPath.size(); ++i) {
+      const uint32_t u = nnPath[i], v = nnPath[i + 1];
+      uint32_t eid = PRGPU_INVALID_INDEX;
+      for (uint32_t e = h->pred_off_v[v]; e < h->pred_off_v[v + 1]; ++e)
+        if (h->pred_v[e].first == u)
+          eid = h->pred_v[e].second;
+      if (eid == PRGPU_INVALID_INDEX)
+        return fail(PRGPU_ECUDA, "nnf_solve: path uses a non-existent NN edge");
+      eids.push_back(eid);
+    }
+    std::vector<uint32_t> todo;
+    for (uint32_t eid : eids)
+      if (h->known[eid] < 0 && std::find(todo.begin(), todo.end(), eid) == todo.end())
+        todo.push_back(eid);
+    if (!todo.empty()) {
+      std::vector<double> from(todo.size() * dof), to(todo.size() * dof);
+      for (size_t i = 0; i < todo.size(); ++i) {
+        std::memcpy(from.data() + i * dof, h->states.data() + (size_t)h->edges[todo[i]].first * dof, dof * 8);
+        std::memcpy(to.data() + i * dof, h->states.data() + (size_t)h->edges[todo[i]].second * dof, dof * 8);
+      }
+      std::vector<uint8_t> ok(todo.size());
+      rc = prgpu_check_motion_batch(h->world, from.data(), to.data(), todo.size(), h->params.check_resolution,
+                                    PRGPU_MODE_NNF_ALPHA, 0, ok.data());
+      if (rc != PRGPU_OK)
+        return rc;
+      for (size_t i = 0; i < todo.size(); ++i)
+        h->known[todo[i]] = ok[i] ? 1 : 0;
+    }
+    bool collisionFree = true;
+    finalPath.clear();
+    for (size_t i = 0; i < eids.size(); ++i) { // :120-145
+      const uint32_t eid = eids[i];
+      if (!h->evaluated[eid]) {
+        h->evaluated[eid] = 1;
+        ++h->n_evaluated;
+        if (h->known[eid] == 0) { // in collision: markEdgeInCollision (:131-136, :685-702)
+          h->blocked[eid] = 1;
+          ++h->n_collisions;
+          const uint8_t one = 1;
+          PRGPU_CUDA_TRY(cudaMemcpyAsync(h->d_blocked.as<uint8_t>() + eid, &one, 1, cudaMemcpyHostToDevice, s));
+          PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+          collisionFree = false;
+          break;
+        }
+      }
+      if (finalPath.empty()) {
+        finalPath.push_back(nnPath[i]);
+        finalPath.push_back(nnPath[i + 1]);
+      } else
+        finalPath.push_back(nnPath[i + 1]);
+    }
+    if (collisionFree) { // :148-151
+      solutionFound = true;
+      if (finalPath.empty() && nnPath.size() == 1)
+        finalPath = nnPath;
+      break;
+    }
+  }
+  res->lazy_iters = iters;
+  res->solved = solutionFound ? 1 : 0;
+  res->n_evaluated = h->n_evaluated;
+  res->n_collisions = h->n_collisions;
+  if (solutionFound) {
+    res->path_len = (uint32_t)finalPath.size();
+    for (size_t i = 0; i < finalPath.size(); ++i) {
+      if (i >= cap_path || !path_vertices) {
+        res->overflow = 1;
+        break;
+      }
+      path_vertices[i] = finalPath[i];
+    }
+  }
+  return PRGPU_OK;
+}
+
+} // extern "C"

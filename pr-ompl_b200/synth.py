@@ -104,3 +104,50 @@ def edges(seed, n, dim=DOF, low=-PI, high=PI, max_len=1.0):
     L = max_len * (1.0 - rng.uniform(0.0, 1.0, size=(n, 1)))
     b = a + L * u
     return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
+def fk_pose(dh, q):
+    """End-effector pose (3x4) of the DH arm at configuration q (numpy; input generation only)."""
+    T = np.eye(4)
+    for i in range(dh.shape[0]):
+        a, d, ca, sa, th0 = dh[i]
+        ct, st = np.cos(q[i] + th0), np.sin(q[i] + th0)
+        L = np.array([[ct, -st * ca, st * sa, a * ct], [st, ct * ca, -ct * sa, a * st], [0.0, sa, ca, d],
+                      [0.0, 0.0, 0.0, 1.0]])
+        T = T @ L
+    return T[:3, :]
+
+
+def lin_int_space(mn, mx, n):
+    """frechet/src/util.cpp:3-21 -- (int)(min + i*delta); may stop short of max."""
+    delta = (mx - mn) / float(n - 1)
+    return np.array([int(mn + i * delta) for i in range(n)], dtype=np.int64)
+
+
+def nnf_reference(seed, n_poses, dh, dof=DOF, amplitude=0.6):
+    """A smooth joint trajectory (n_poses x dof) and the end-effector poses (n_poses x 12) it traces:
+    the reference path handed to NNFrechet::setRefPath."""
+    rng = np.random.default_rng(seed)
+    q0 = rng.uniform(-1.0, 1.0, size=dof)
+    amp = rng.uniform(0.3, 1.0, size=dof) * amplitude
+    freq = rng.uniform(0.5, 1.5, size=dof)
+    phase = rng.uniform(0, 2 * PI, size=dof)
+    t = np.linspace(0.0, 1.0, n_poses)[:, None]
+    q = q0 + amp * np.sin(2 * PI * freq * t + phase)
+    poses = np.stack([fk_pose(dh, qi).reshape(12) for qi in q])
+    return q, poses
+
+
+def nnf_ik_states(seed, ref_configs, layer_counts, sigma=0.15):
+    """Synthetic IK: the trajectory configuration of the waypoint plus N(0, sigma^2) joint noise, in
+    NN-graph vertex order (layer 0, layer R-1, layers 1..R-2).  Legal because the planner
+    recomputes every pose with FK (frechet/src/NNFrechet.cpp:295)."""
+    rng = np.random.default_rng(seed)
+    R = len(layer_counts)
+    order = [0, R - 1] + list(range(1, R - 1)) if R > 1 else [0]
+    rows = []
+    for r in order:
+        c = int(layer_counts[r])
+        if c:
+            rows.append(ref_configs[r] + sigma * rng.normal(size=(c, ref_configs.shape[1])))
+    return np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((0, ref_configs.shape[1]))

@@ -16,6 +16,13 @@ c_i32p = C.POINTER(C.c_int32)
 c_u8p = C.POINTER(C.c_uint8)
 
 
+class NnfResult(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint32), ("n_edges", C.c_uint32), ("n_ik", C.c_uint32),
+                ("lazy_iters", C.c_uint32), ("solved", C.c_int32), ("final_error", C.c_double),
+                ("goal_cost", C.c_double), ("path_len", C.c_uint32), ("n_evaluated", C.c_uint32),
+                ("n_collisions", C.c_uint32), ("overflow", C.c_uint32)]
+
+
 class RrtcResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("iterations", C.c_uint32), ("n_start", C.c_uint32),
                 ("n_goal", C.c_uint32), ("path_len", C.c_uint32), ("overflow", C.c_uint32)]
@@ -61,6 +68,11 @@ def lib():
         L.orc_sample_uniform.argtypes = [C.c_uint64] * 4 + [C.c_double] * 2
         L.orc_sample_uniform.restype = C.c_double
         L.orc_rrtc_solve.argtypes = _RRTC_ARGS
+        L.orc_lin_int_space.argtypes = [C.c_double, C.c_double, C.c_uint64, c_i32p]
+        L.orc_nnf_layer_counts.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_u32p]
+        L.orc_nnf_run.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_int, C.c_double, c_u32p, c_dp,
+                                  C.c_uint32, C.c_int, C.POINTER(NnfResult), c_u32p, c_dp, c_dp, C.c_uint32,
+                                  c_u32p, C.c_uint32, c_dp]
         _lib = L
     return _lib
 
@@ -169,3 +181,39 @@ class World:
         return dict(status=res.status, iterations=res.iterations, start_states=ss[:res.n_start].copy(),
                     start_parent=sp[:res.n_start].copy(), goal_states=gs[:res.n_goal].copy(),
                     goal_parent=gp[:res.n_goal].copy(), path=path[:res.path_len].copy())
+
+
+def lin_int_space(mn, mx, n):
+    out = np.empty(n, dtype=np.int32)
+    lib().orc_lin_int_space(float(mn), float(mx), n, out.ctypes.data_as(c_i32p))
+    return out
+
+
+def nnf_layer_counts(seed, R, W, M):
+    out = np.empty(R, dtype=np.uint32)
+    lib().orc_nnf_layer_counts(seed, R, W, M, out.ctypes.data_as(c_u32p))
+    return out
+
+
+def nnf_run(world, ref_pose12, layer_counts, ik_states, k=5, D=3, check_res=0.05, max_lazy_iters=1000,
+            nthreads=1, cap_vertices=None, cap_path=65536):
+    ref = np.ascontiguousarray(ref_pose12, dtype=np.float64).reshape(-1, 12)
+    counts = np.ascontiguousarray(layer_counts, dtype=np.uint32)
+    ik = np.ascontiguousarray(ik_states, dtype=np.float64).reshape(-1, world.dof)
+    n_ik = len(ik)
+    if cap_vertices is None:
+        cap_vertices = 2 + n_ik + n_ik * k * D
+    res = NnfResult()
+    knn_out = np.empty((n_ik, k), dtype=np.uint32)
+    vs = np.zeros((cap_vertices, world.dof))
+    vp = np.zeros((cap_vertices, 12))
+    path = np.zeros(cap_path, dtype=np.uint32)
+    trace = np.zeros(max_lazy_iters)
+    rc = lib().orc_nnf_run(world.h, len(ref), _dp(ref), k, D, check_res, counts.ctypes.data_as(c_u32p), _dp(ik),
+                           max_lazy_iters, nthreads, C.byref(res), knn_out.ctypes.data_as(c_u32p), _dp(vs), _dp(vp),
+                           cap_vertices, path.ctypes.data_as(c_u32p), cap_path, _dp(trace))
+    assert rc == 0 and res.overflow == 0, (rc, res.overflow)
+    out = {f[0]: getattr(res, f[0]) for f in NnfResult._fields_}
+    out.update(knn=knn_out, states=vs[:res.n_vertices], pose=vp[:res.n_vertices], path=path[:res.path_len].copy(),
+               goal_cost_trace=trace[:res.lazy_iters].copy())
+    return out
