@@ -4,6 +4,6 @@ The product is the C-ABI shared library `libprgpu.so` (include/prgpu.h, sources 
 the C++ OMPL-plugin mirror in plugin/.  This Python package is a thin ctypes binding used by
 tests and bench.py; it computes nothing itself and raises if the CUDA library is missing.
 """
-from . import synth  # noqa: F401
+from . import synth, sharded  # noqa: F401
 from .capi import (KnnIndex, World, PrgpuError, build, lib, lib_path, topk_merge_device,  # noqa: F401
                    INVALID_INDEX, MODE_OMPL_DISCRETE, MODE_NNF_ALPHA, RrtcBatch, RrtcParams, Nnf)
