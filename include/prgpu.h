@@ -211,7 +211,12 @@ int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12);
  * cost of every search (max_lazy_iters entries) or NULL.  May be called again to continue. */
 int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *res, uint32_t *path_vertices,
                     uint32_t cap_path, double *goal_cost_trace);
-/* duration of the latest wavefront search kernel (measurement aid, always on) */
+/* search kernel: 0 (default) = banded column-wise DP (only cells that can lie on a path of cost
+ * <= tau are stored; tau is widened until the optimum is provably inside), 1 = full R x V table
+ * swept by anti-diagonals.  Both return identical costs and paths. */
+int prgpu_nnf_set_mode(prgpu_nnf_t *h, int mode);
+int prgpu_nnf_band_info(prgpu_nnf_t *h, double *tau, uint64_t *cells, uint32_t *rebuilds);
+/* duration of the latest search kernel (measurement aid, always on) */
 int prgpu_nnf_last_dp_ms(prgpu_nnf_t *h, float *ms);
 
 #ifdef __cplusplus

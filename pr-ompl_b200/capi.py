@@ -81,6 +81,8 @@ SIGNATURES = {
     "prgpu_nnf_get_knn": (C.c_int, [c_vp, c_vp]),
     "prgpu_nnf_get_vertices": (C.c_int, [c_vp, c_vp, c_vp]),
     "prgpu_nnf_solve": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, C.c_uint32, c_vp]),
+    "prgpu_nnf_set_mode": (C.c_int, [c_vp, C.c_int]),
+    "prgpu_nnf_band_info": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), c_u32p]),
     "prgpu_nnf_last_dp_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
 }
 
@@ -374,6 +376,15 @@ class Nnf:
         out["path"] = path[:res.path_len].copy()
         out["goal_cost_trace"] = trace[:res.lazy_iters].copy()
         return out
+
+    def set_mode(self, mode):
+        """0 = banded column-wise DP (default), 1 = full-table anti-diagonal wavefront."""
+        _check(lib().prgpu_nnf_set_mode(self.h, mode))
+
+    def band_info(self):
+        tau, cells, reb = C.c_double(), C.c_uint64(), C.c_uint32()
+        _check(lib().prgpu_nnf_band_info(self.h, C.byref(tau), C.byref(cells), C.byref(reb)))
+        return dict(tau=tau.value, cells=cells.value, rebuilds=reb.value)
 
     def last_dp_ms(self):
         ms = C.c_float()

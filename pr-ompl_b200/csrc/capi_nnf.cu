@@ -33,6 +33,16 @@ struct prgpu_nnf {
       d_path, d_pn, d_cost;
   NnfGraphDev g;
   KernelTimer timer;
+  // banded form
+  int mode = 0;                 // 0 banded column-wise DP (default), 1 full-table wavefront
+  std::vector<uint32_t> level_of_vertex, slot_of_eid;
+  DevBuf d_band_lo, d_band_w, d_col_off, d_meta, d_edge, d_Bc, d_scan_tmp, d_rowmin;
+  NnfBandDev bg;
+  double tau_ub = 0.0;
+  bool band_valid = false, band_full = false;
+  uint32_t dirty_level = 0;
+  uint64_t band_cells = 0;
+  uint32_t band_rebuilds = 0;
   uint32_t total_iters = 0, n_evaluated = 0, n_collisions = 0;
 };
 
@@ -52,9 +62,88 @@ double host_task_distance(const double *a12, const double *b12) {
   s = s + zz;
   return std::sqrt(s);
 }
+__global__ void nnf_block_edge_kernel(NnfEdgeRec *edge, uint32_t slot, uint8_t *blocked, uint32_t eid) {
+  edge[slot].band_w_blocked |= 0x80000000u;
+  blocked[eid] = 1;
+}
+
+// (re)build the band for the current tau_ub: per-vertex row interval, column offsets, packed records
+int nnf_build_band(prgpu_nnf *h, cudaStream_t s) {
+  const int R = h->R;
+  const uint32_t V = h->V;
+  int rc = nnf_band_launch(R, V, h->g.pnn, h->g.pref, h->tau_ub, h->d_band_lo.as<uint32_t>(),
+                           h->d_band_w.as<unsigned long long>(), s);
+  if (rc != PRGPU_OK)
+    return rc;
+  size_t tmp = 0;
+  rc = nnf_exclusive_scan_u64(h->d_band_w.as<unsigned long long>(), h->d_col_off.as<unsigned long long>(), V, nullptr,
+                              tmp, s);
+  if (rc != PRGPU_OK)
+    return rc;
+  if ((rc = h->d_scan_tmp.reserve(std::max<size_t>(tmp, 16))) != PRGPU_OK)
+    return rc;
+  rc = nnf_exclusive_scan_u64(h->d_band_w.as<unsigned long long>(), h->d_col_off.as<unsigned long long>(), V,
+                              h->d_scan_tmp.p, tmp, s);
+  if (rc != PRGPU_OK)
+    return rc;
+  unsigned long long last_off = 0, last_w = 0;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(&last_off, h->d_col_off.as<unsigned long long>() + (V - 1), 8,
+                                 cudaMemcpyDeviceToHost, s));
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(&last_w, h->d_band_w.as<unsigned long long>() + (V - 1), 8, cudaMemcpyDeviceToHost, s));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+  h->band_cells = last_off + last_w;
+  h->band_full = h->band_cells == (uint64_t)R * V;
+  if ((rc = h->d_Bc.reserve(std::max<size_t>((size_t)h->band_cells * 8, 16))) != PRGPU_OK)
+    return rc;
+  h->bg.Bc = h->d_Bc.as<double>();
+  rc = nnf_band_pack_launch(V, h->E, h->d_band_lo.as<uint32_t>(), h->d_band_w.as<unsigned long long>(),
+                            h->d_col_off.as<unsigned long long>(), h->g.pred_off, h->g.pred_pos, h->g.pred_eid,
+                            h->g.blocked, h->d_meta.as<NnfVertexMeta>(), h->d_edge.as<NnfEdgeRec>(), s);
+  if (rc != PRGPU_OK)
+    return rc;
+  h->band_valid = true;
+  h->dirty_level = 0;
+  ++h->band_rebuilds;
+  return PRGPU_OK;
+}
+
+// lower bound on the optimum: every start-goal path visits every reference row
+int nnf_initial_tau(prgpu_nnf *h, cudaStream_t s) {
+  int rc = nnf_rowmin_launch(h->R, h->V, h->g.pnn, h->g.pref, h->d_rowmin.as<unsigned long long>(), s);
+  if (rc != PRGPU_OK)
+    return rc;
+  std::vector<double> rowmin(h->R);
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(rowmin.data(), h->d_rowmin.p, (size_t)h->R * 8, cudaMemcpyDeviceToHost, s));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+  double lb = 0.0;
+  for (double x : rowmin)
+    lb = std::max(lb, x);
+  h->tau_ub = std::max(lb * 1.5, 1e-6);
+  return PRGPU_OK;
+}
 } // namespace
 
 extern "C" {
+
+int prgpu_nnf_set_mode(prgpu_nnf_t *h, int mode) {
+  if (!h || (mode != 0 && mode != 1))
+    return fail(PRGPU_EINVAL, "nnf_set_mode: mode must be 0 (banded) or 1 (full table)");
+  h->mode = mode;
+  h->dirty_level = 0; // the other mode's table may be stale
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_band_info(prgpu_nnf_t *h, double *tau, uint64_t *cells, uint32_t *rebuilds) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "nnf_band_info: NULL handle");
+  if (tau)
+    *tau = h->tau_ub;
+  if (cells)
+    *cells = h->band_cells;
+  if (rebuilds)
+    *rebuilds = h->band_rebuilds;
+  return PRGPU_OK;
+}
 
 int prgpu_nnf_destroy(prgpu_nnf_t *h) {
   if (!h)
@@ -62,7 +151,9 @@ int prgpu_nnf_destroy(prgpu_nnf_t *h) {
   cudaSetDevice(h->world->device);
   cudaStreamSynchronize(h->world->stream);
   for (DevBuf *b : {&h->d_states, &h->d_pose, &h->d_lvl_start, &h->d_level, &h->d_pred_off, &h->d_pred_pos,
-                    &h->d_pred_eid, &h->d_blocked, &h->d_pnn, &h->d_pref, &h->d_B, &h->d_path, &h->d_pn, &h->d_cost})
+                    &h->d_pred_eid, &h->d_blocked, &h->d_pnn, &h->d_pref, &h->d_B, &h->d_path, &h->d_pn, &h->d_cost,
+                    &h->d_band_lo, &h->d_band_w, &h->d_col_off, &h->d_meta, &h->d_edge, &h->d_Bc, &h->d_scan_tmp,
+                    &h->d_rowmin})
     b->release();
   h->timer.destroy();
   delete h;
@@ -325,6 +416,10 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
       pred_eid[o] = h->pred_v[e].second;
     }
   }
+  h->level_of_vertex = level;
+  h->slot_of_eid.assign(E, 0);
+  for (uint32_t o = 0; o < E; ++o)
+    h->slot_of_eid[pred_eid[o]] = o;
   NNF_TRY(upload(h->d_lvl_start, lvl_start, s));
   NNF_TRY(upload(h->d_level, level_s, s));
   NNF_TRY(upload(h->d_pred_off, pred_off_s, s));
@@ -354,7 +449,12 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
     }
     NNF_TRY(upload(h->d_pref, pref, s));
   }
-  NNF_TRY(h->d_B.reserve((size_t)R * V * 8));
+  NNF_TRY(h->d_band_lo.reserve((size_t)V * 4));
+  NNF_TRY(h->d_band_w.reserve((size_t)V * 8));
+  NNF_TRY(h->d_col_off.reserve((size_t)V * 8));
+  NNF_TRY(h->d_meta.reserve((size_t)V * sizeof(NnfVertexMeta)));
+  NNF_TRY(h->d_edge.reserve(std::max<size_t>((size_t)E * sizeof(NnfEdgeRec), 16)));
+  NNF_TRY(h->d_rowmin.reserve((size_t)R * 8));
   NNF_TRY(h->d_path.reserve(((size_t)R + Lv + 8) * 2 * 4));
   NNF_TRY(h->d_pn.reserve(16));
   NNF_TRY(h->d_cost.reserve(16));
@@ -373,9 +473,22 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
   g.blocked = h->d_blocked.as<uint8_t>();
   g.pnn = h->d_pnn.as<double>();
   g.pref = h->d_pref.as<double>();
-  g.B = h->d_B.as<double>();
+  g.B = nullptr; // allocated on first use of the full-table mode
   g.start_pos = h->pos_of_vertex[c0];
   g.goal_pos = h->pos_of_vertex[c1];
+  NnfBandDev &bg = h->bg;
+  bg.R = R;
+  bg.V = V;
+  bg.Lv = Lv;
+  bg.lvl_start = g.lvl_start;
+  bg.meta = h->d_meta.as<NnfVertexMeta>();
+  bg.edge = h->d_edge.as<NnfEdgeRec>();
+  bg.pred_pos = g.pred_pos;
+  bg.pnn = g.pnn;
+  bg.pref = g.pref;
+  bg.Bc = nullptr;
+  bg.start_pos = g.start_pos;
+  bg.goal_pos = g.goal_pos;
   *out = h;
   return PRGPU_OK;
 #undef NNF_TRY
@@ -435,18 +548,52 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
   bool solutionFound = false;
   uint32_t iters = 0;
   while (iters < max_lazy_iters) { // NNFrechet.cpp:106
-    int rc = nnf_dp_launch(h->g, h->world->sm_count, s, &h->timer); // computeShortestPath :109-110
-    if (rc != PRGPU_OK)
-      return rc;
-    rc = nnf_backtrack_launch(h->g, h->d_path.as<uint32_t>(), cap_pairs, h->d_pn.as<uint32_t>(),
-                              h->d_cost.as<double>(), s);
-    if (rc != PRGPU_OK)
-      return rc;
+    int rc;
     uint32_t np = 0;
     double goalCost = 0.0;
-    PRGPU_CUDA_TRY(cudaMemcpyAsync(&np, h->d_pn.p, 4, cudaMemcpyDeviceToHost, s));
-    PRGPU_CUDA_TRY(cudaMemcpyAsync(&goalCost, h->d_cost.p, 8, cudaMemcpyDeviceToHost, s));
-    PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+    if (h->mode == 1) { // full-table wavefront
+      if (!h->g.B) {
+        if ((rc = h->d_B.reserve((size_t)R * V * 8)) != PRGPU_OK)
+          return rc;
+        h->g.B = h->d_B.as<double>();
+      }
+      rc = nnf_dp_launch(h->g, h->world->sm_count, s, &h->timer); // computeShortestPath :109-110
+      if (rc != PRGPU_OK)
+        return rc;
+      rc = nnf_backtrack_launch(h->g, h->d_path.as<uint32_t>(), cap_pairs, h->d_pn.as<uint32_t>(),
+                                h->d_cost.as<double>(), s);
+      if (rc != PRGPU_OK)
+        return rc;
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(&np, h->d_pn.p, 4, cudaMemcpyDeviceToHost, s));
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(&goalCost, h->d_cost.p, 8, cudaMemcpyDeviceToHost, s));
+      PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+    } else { // banded column-wise DP; widen the band until it provably contains the optimum
+      if (!h->band_valid) {
+        if (h->tau_ub == 0.0 && (rc = nnf_initial_tau(h, s)) != PRGPU_OK)
+          return rc;
+        if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
+          return rc;
+      }
+      while (true) {
+        rc = nnf_band_dp_launch(h->bg, h->dirty_level, s, &h->timer);
+        if (rc != PRGPU_OK)
+          return rc;
+        h->dirty_level = h->Lv; // table consistent
+        rc = nnf_band_backtrack_launch(h->bg, h->d_path.as<uint32_t>(), cap_pairs, h->d_pn.as<uint32_t>(),
+                                       h->d_cost.as<double>(), s);
+        if (rc != PRGPU_OK)
+          return rc;
+        PRGPU_CUDA_TRY(cudaMemcpyAsync(&np, h->d_pn.p, 4, cudaMemcpyDeviceToHost, s));
+        PRGPU_CUDA_TRY(cudaMemcpyAsync(&goalCost, h->d_cost.p, 8, cudaMemcpyDeviceToHost, s));
+        PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+        if (goalCost <= h->tau_ub || h->band_full)
+          break; // exact: the optimum lies inside the band (or the band is the whole table)
+        // a finite cost found inside the band is an upper bound of the optimum: use it directly
+        h->tau_ub = goalCost < 1e300 ? goalCost * (1.0 + 1e-9) : h->tau_ub * 2.0;
+        if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
+          return rc;
+      }
+    }
     if (goal_cost_trace)
       goal_cost_trace[iters] = goalCost;
     ++iters;
@@ -515,9 +662,10 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
         if (h->known[eid] == 0) { // in collision: markEdgeInCollision (:131-136, :685-702)
           h->blocked[eid] = 1;
           ++h->n_collisions;
-          const uint8_t one = 1;
-          PRGPU_CUDA_TRY(cudaMemcpyAsync(h->d_blocked.as<uint8_t>() + eid, &one, 1, cudaMemcpyHostToDevice, s));
-          PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+          nnf_block_edge_kernel<<<1, 1, 0, s>>>(h->d_edge.as<NnfEdgeRec>(), h->slot_of_eid[eid],
+                                                h->d_blocked.as<uint8_t>(), eid);
+          PRGPU_CUDA_TRY(cudaGetLastError());
+          h->dirty_level = std::min(h->dirty_level, h->level_of_vertex[h->edges[eid].second]);
           collisionFree = false;
           break;
         }

@@ -17,6 +17,7 @@
 //    cell, the first predecessor that attains the cell's cost.
 #include <cfloat>
 #include <cooperative_groups.h>
+#include <cub/device/device_scan.cuh>
 #include "nnf.cuh"
 
 namespace cg = cooperative_groups;
@@ -170,6 +171,222 @@ __global__ void nnf_backtrack_kernel(const NnfGraphDev g, uint32_t *__restrict__
   *out_n = n;
 }
 
+// ------------------------------ banded column-wise dynamic program ------------------------------
+
+// lower bound on any path's bottleneck: every path visits every row, so cost >= max_r min_n f[r,n]
+__global__ void nnf_rowmin_kernel(int R, uint32_t V, const double *__restrict__ pnn, const double *__restrict__ pref,
+                                  unsigned long long *__restrict__ rowmin_bits) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t r = blockIdx.y;
+  double f = NNF_INF;
+  if (s < V)
+    f = task_distance(pref + 3 * (size_t)r, pnn + 3 * (size_t)s);
+  // non-negative doubles order like their bit patterns
+  unsigned long long b = (unsigned long long)__double_as_longlong(f);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
+    b = o < b ? o : b;
+  }
+  if ((threadIdx.x & 31) == 0)
+    atomicMin(rowmin_bits + r, b);
+}
+
+__global__ void nnf_band_kernel(int R, uint32_t V, const double *__restrict__ pnn, const double *__restrict__ pref,
+                                double tau, uint32_t *__restrict__ band_lo, unsigned long long *__restrict__ band_w64) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= V)
+    return;
+  const double x = pnn[3 * (size_t)s], y = pnn[3 * (size_t)s + 1], z = pnn[3 * (size_t)s + 2];
+  int first = -1, last = -1;
+  for (int r = 0; r < R; ++r) {
+    const double dx = __dsub_rn(pref[3 * r], x), dy = __dsub_rn(pref[3 * r + 1], y), dz = __dsub_rn(pref[3 * r + 2], z);
+    const double f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    if (f <= tau) {
+      if (first < 0)
+        first = r;
+      last = r;
+    }
+  }
+  band_lo[s] = first < 0 ? 0u : (uint32_t)first;
+  band_w64[s] = first < 0 ? 0ull : (unsigned long long)(last - first + 1);
+}
+
+__global__ void nnf_band_pack_kernel(uint32_t V, const uint32_t *__restrict__ band_lo,
+                                     const unsigned long long *__restrict__ band_w64,
+                                     const unsigned long long *__restrict__ col_off,
+                                     const uint32_t *__restrict__ pred_off, const uint32_t *__restrict__ pred_pos,
+                                     const uint32_t *__restrict__ pred_eid, const uint8_t *__restrict__ blocked,
+                                     NnfVertexMeta *__restrict__ meta, NnfEdgeRec *__restrict__ edge) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= V)
+    return;
+  NnfVertexMeta m;
+  m.col_off = col_off[s];
+  m.band_lo = band_lo[s];
+  m.band_w = (uint32_t)band_w64[s];
+  m.pred_begin = pred_off[s];
+  m.pred_end = pred_off[s + 1];
+  m.pad0 = m.pad1 = 0;
+  meta[s] = m;
+  for (uint32_t e = m.pred_begin; e < m.pred_end; ++e) {
+    const uint32_t p = pred_pos[e];
+    NnfEdgeRec rec;
+    rec.col_off = col_off[p];
+    rec.band_lo = band_lo[p];
+    rec.band_w_blocked = (uint32_t)band_w64[p] | (blocked[pred_eid[e]] ? 0x80000000u : 0u);
+    edge[e] = rec;
+  }
+}
+
+// clamp function g(x) = max(a, min(x, b)), a <= b; (g2 o g1) is again a clamp
+struct Clamp {
+  double a, b;
+};
+__device__ __forceinline__ Clamp compose(const Clamp &g2, const Clamp &g1) { // g2 after g1
+  Clamp c;
+  c.a = fmax(g2.a, fmin(g1.a, g2.b));
+  c.b = fmax(g2.a, fmin(g1.b, g2.b));
+  return c;
+}
+
+constexpr int BAND_THREADS = 1024;
+
+// One thread-block cluster sweeps the NN-graph levels; a warp owns a vertex, its lanes the rows of
+// the vertex's band.  Row recurrence x_r = max(f_r, min(x_{r-1}, m_r)) is a composition of clamps,
+// evaluated with a warp-shuffle scan, so a level costs one round of gathers plus one barrier.
+__global__ void __launch_bounds__(BAND_THREADS) nnf_band_dp_kernel(const NnfBandDev g, uint32_t first_level) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = cluster.block_rank() * (BAND_THREADS / 32) + (threadIdx.x >> 5);
+  const uint32_t nwarps = cluster.num_blocks() * (BAND_THREADS / 32);
+  for (uint32_t level = first_level; level < g.Lv; ++level) {
+    const uint32_t ls = g.lvl_start[level], le = g.lvl_start[level + 1];
+    for (uint32_t s = ls + warp; s < le; s += nwarps) {
+      const NnfVertexMeta m = g.meta[s];
+      if (m.band_w == 0)
+        continue;
+      const double px = g.pnn[3 * (size_t)s], py = g.pnn[3 * (size_t)s + 1], pz = g.pnn[3 * (size_t)s + 2];
+      double carry = NNF_INF; // x just below the band
+      for (uint32_t c0 = 0; c0 < m.band_w; c0 += 32) {
+        const bool active = c0 + lane < m.band_w;
+        const uint32_t r = m.band_lo + c0 + lane;
+        Clamp gfn;
+        gfn.a = -NNF_INF; // identity for inactive lanes
+        gfn.b = NNF_INF;
+        if (active) {
+          double mm = NNF_INF;
+          for (uint32_t e = m.pred_begin; e < m.pred_end; ++e) {
+            const NnfEdgeRec rec = g.edge[e];
+            if (rec.band_w_blocked & 0x80000000u)
+              continue;
+            const uint32_t pw = rec.band_w_blocked;
+            const uint32_t i0 = r - rec.band_lo; // row r of the predecessor (unsigned wrap = outside)
+            if (i0 < pw)
+              mm = fmin(mm, __ldcg(g.Bc + rec.col_off + i0));
+            const uint32_t i1 = i0 - 1u; // row r-1
+            if (r > 0 && i1 < pw)
+              mm = fmin(mm, __ldcg(g.Bc + rec.col_off + i1));
+          }
+          const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
+                       dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
+          const double f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+          gfn.a = f;
+          gfn.b = fmax(f, mm);
+          if (s == g.start_pos && r == 0)
+            gfn.a = gfn.b = 0.0; // rhs(start) = 0
+        }
+        // inclusive scan of compositions: lane i ends with g_i o ... o g_0
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          Clamp lower;
+          lower.a = __shfl_up_sync(0xffffffffu, gfn.a, off);
+          lower.b = __shfl_up_sync(0xffffffffu, gfn.b, off);
+          if ((int)lane >= off)
+            gfn = compose(gfn, lower);
+        }
+        const double x = fmax(gfn.a, fmin(carry, gfn.b));
+        if (active)
+          __stcg(g.Bc + m.col_off + c0 + lane, x);
+        const uint32_t last = min(31u, m.band_w - c0 - 1u);
+        carry = __shfl_sync(0xffffffffu, x, last);
+      }
+    }
+    cluster.sync();
+  }
+}
+
+__device__ __forceinline__ double band_get(const NnfBandDev &g, uint32_t r, uint32_t s) {
+  const NnfVertexMeta m = g.meta[s];
+  const uint32_t i = r - m.band_lo;
+  return i < m.band_w ? g.Bc[m.col_off + i] : NNF_INF;
+}
+
+__global__ void nnf_band_backtrack_kernel(const NnfBandDev g, uint32_t *__restrict__ out_path, uint32_t cap_pairs,
+                                          uint32_t *__restrict__ out_n, double *__restrict__ out_cost) {
+  if (blockIdx.x != 0 || threadIdx.x != 0)
+    return;
+  uint32_t r = (uint32_t)g.R - 1, s = g.goal_pos, n = 0;
+  const double goal = band_get(g, r, s);
+  *out_cost = goal;
+  if (goal == NNF_INF) {
+    *out_n = 0;
+    return;
+  }
+  while (true) {
+    if (n < cap_pairs) {
+      out_path[2 * n] = r;
+      out_path[2 * n + 1] = s;
+    }
+    ++n;
+    if (r == 0 && s == g.start_pos)
+      break;
+    const double target = band_get(g, r, s);
+    const double fv = task_distance(g.pref + 3 * (size_t)r, g.pnn + 3 * (size_t)s);
+    bool found = false;
+    uint32_t br = 0, bs = 0;
+    // same fixed order as the full-table walk: (r-1,s), then per predecessor (r,p), (r-1,p)
+    if (r > 0) {
+      const double bu = band_get(g, r - 1, s);
+      if (bu != NNF_INF && fmax(bu, fv) == target) {
+        found = true;
+        br = r - 1;
+        bs = s;
+      }
+    }
+    const NnfVertexMeta m = g.meta[s];
+    for (uint32_t e = m.pred_begin; !found && e < m.pred_end; ++e) {
+      const NnfEdgeRec rec = g.edge[e];
+      if (rec.band_w_blocked & 0x80000000u)
+        continue;
+      const uint32_t pw = rec.band_w_blocked;
+      const uint32_t i0 = r - rec.band_lo;
+      const double b0 = i0 < pw ? g.Bc[rec.col_off + i0] : NNF_INF;
+      if (b0 != NNF_INF && fmax(b0, fv) == target) {
+        found = true;
+        br = r;
+        bs = g.pred_pos[e];
+        break;
+      }
+      const uint32_t i1 = i0 - 1u;
+      const double b1 = (r > 0 && i1 < pw) ? g.Bc[rec.col_off + i1] : NNF_INF;
+      if (b1 != NNF_INF && fmax(b1, fv) == target) {
+        found = true;
+        br = r - 1;
+        bs = g.pred_pos[e];
+        break;
+      }
+    }
+    if (!found) { // cannot happen on a consistent table
+      n = 0xFFFFFFFFu;
+      break;
+    }
+    r = br;
+    s = bs;
+  }
+  *out_n = n;
+}
+
 } // namespace
 
 int nnf_subsample_launch(const DeviceWorld *w_dev, int dof, uint32_t n_new, uint32_t first_vertex,
@@ -205,6 +422,87 @@ int nnf_dp_launch(const NnfGraphDev &g, int sm_count, cudaStream_t stream, Kerne
   PRGPU_CUDA_TRY(cudaLaunchCooperativeKernel((void *)nnf_dp_kernel, grid, block, args, 0, stream));
   if (timer)
     timer->end(stream);
+  return PRGPU_OK;
+}
+
+int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, unsigned long long *rowmin_bits,
+                      cudaStream_t stream) {
+  PRGPU_CUDA_TRY(cudaMemsetAsync(rowmin_bits, 0xFF, (size_t)R * sizeof(unsigned long long), stream));
+  nnf_rowmin_kernel<<<dim3((V + 255) / 256, R), 256, 0, stream>>>(R, V, pnn, pref, rowmin_bits);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
+int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, double tau, uint32_t *band_lo,
+                    unsigned long long *band_w64, cudaStream_t stream) {
+  nnf_band_kernel<<<(V + 127) / 128, 128, 0, stream>>>(R, V, pnn, pref, tau, band_lo, band_w64);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
+int nnf_band_pack_launch(uint32_t V, uint32_t E, const uint32_t *band_lo, const unsigned long long *band_w64,
+                         const unsigned long long *col_off, const uint32_t *pred_off, const uint32_t *pred_pos,
+                         const uint32_t *pred_eid, const uint8_t *blocked, NnfVertexMeta *meta, NnfEdgeRec *edge,
+                         cudaStream_t stream) {
+  (void)E;
+  nnf_band_pack_kernel<<<(V + 127) / 128, 128, 0, stream>>>(V, band_lo, band_w64, col_off, pred_off, pred_pos,
+                                                            pred_eid, blocked, meta, edge);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
+int nnf_exclusive_scan_u64(const unsigned long long *in, unsigned long long *out, uint32_t n, void *temp,
+                           size_t &temp_bytes, cudaStream_t stream) {
+  PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, stream));
+  return PRGPU_OK;
+}
+
+int nnf_band_dp_launch(const NnfBandDev &g, uint32_t first_level, cudaStream_t stream, KernelTimer *timer) {
+  static int cluster_size = 0;
+  if (cluster_size == 0) {
+    // 16 CTAs per cluster where the device allows it (non-portable size), else the portable 8
+    cluster_size = 8;
+    if (cudaFuncSetAttribute(nnf_band_dp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t probe = {};
+      probe.gridDim = dim3(16);
+      probe.blockDim = dim3(BAND_THREADS);
+      cudaLaunchAttribute pa[1];
+      pa[0].id = cudaLaunchAttributeClusterDimension;
+      pa[0].val.clusterDim.x = 16;
+      pa[0].val.clusterDim.y = 1;
+      pa[0].val.clusterDim.z = 1;
+      probe.attrs = pa;
+      probe.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, nnf_band_dp_kernel, &probe) == cudaSuccess && nclusters >= 1)
+        cluster_size = 16;
+    }
+    cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster_size);
+  cfg.blockDim = dim3(BAND_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (timer)
+    timer->begin(stream);
+  PRGPU_CUDA_TRY(cudaLaunchKernelEx(&cfg, nnf_band_dp_kernel, g, first_level));
+  if (timer)
+    timer->end(stream);
+  return PRGPU_OK;
+}
+
+int nnf_band_backtrack_launch(const NnfBandDev &g, uint32_t *out_path, uint32_t cap_pairs, uint32_t *out_n,
+                              double *out_cost, cudaStream_t stream) {
+  nnf_band_backtrack_kernel<<<1, 32, 0, stream>>>(g, out_path, cap_pairs, out_n, out_cost);
+  PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
 

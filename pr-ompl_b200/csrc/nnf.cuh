@@ -18,6 +18,47 @@ struct NnfGraphDev {
   double *B;                 // R x V: bottleneck cost table
   uint32_t start_pos, goal_pos; // sorted positions of c0 / c1
 };
+// ---- banded (column-wise) form of the same dynamic program -----------------------------------
+// Only cells whose node weight can matter for a path of cost <= tau are stored: vertex s keeps
+// rows [band_lo, band_lo + band_w) (a superset interval of {r : f[r,s] <= tau}); everything outside
+// is +inf by construction.  Every cell whose true cost is <= tau is computed exactly, so the goal
+// cost and the backtracked path equal the full table's whenever the goal cost is <= tau.
+struct NnfVertexMeta {   // one 32-byte record per sorted vertex
+  uint64_t col_off;      // first cell of the vertex's column in Bc
+  uint32_t band_lo, band_w;
+  uint32_t pred_begin, pred_end; // range into the packed edge records
+  uint32_t pad0, pad1;
+};
+struct NnfEdgeRec {      // one 16-byte record per (vertex, predecessor) pair, creation order
+  uint64_t col_off;      // predecessor's column
+  uint32_t band_lo;
+  uint32_t band_w_blocked; // bit 31 = edge knocked out; low bits = predecessor's band width
+};
+struct NnfBandDev {
+  int R;
+  uint32_t V, Lv;
+  const uint32_t *lvl_start; // Lv+1
+  const NnfVertexMeta *meta; // V
+  const NnfEdgeRec *edge;    // E (CSR order)
+  const uint32_t *pred_pos;  // E (CSR order): sorted position of the predecessor
+  const double *pnn, *pref;
+  double *Bc;
+  uint32_t start_pos, goal_pos;
+};
+int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, unsigned long long *rowmin_bits,
+                      cudaStream_t stream);
+int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, double tau, uint32_t *band_lo,
+                    unsigned long long *band_w64, cudaStream_t stream);
+int nnf_band_pack_launch(uint32_t V, uint32_t E, const uint32_t *band_lo, const unsigned long long *band_w64,
+                         const unsigned long long *col_off, const uint32_t *pred_off, const uint32_t *pred_pos,
+                         const uint32_t *pred_eid, const uint8_t *blocked, NnfVertexMeta *meta, NnfEdgeRec *edge,
+                         cudaStream_t stream);
+int nnf_band_dp_launch(const NnfBandDev &g, uint32_t first_level, cudaStream_t stream, KernelTimer *timer);
+int nnf_band_backtrack_launch(const NnfBandDev &g, uint32_t *out_path, uint32_t cap_pairs, uint32_t *out_n,
+                              double *out_cost, cudaStream_t stream);
+int nnf_exclusive_scan_u64(const unsigned long long *in, unsigned long long *out, uint32_t n, void *temp,
+                           size_t &temp_bytes, cudaStream_t stream);
+
 int nnf_subsample_launch(const DeviceWorld *w_dev, int dof, uint32_t n_new, uint32_t first_vertex,
                          const uint32_t *src, const uint32_t *dst, const uint32_t *step, int D,
                          double *states, double *pose12, cudaStream_t stream);

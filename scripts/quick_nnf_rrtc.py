@@ -20,8 +20,9 @@ if what == "nnf":
     ik = synth.nnf_ik_states(2, q[ids], counts)
     t = time.time(); g = P.Nnf(gw, poses[ids], counts, ik, num_nn=k, discretization=D); torch.cuda.synchronize(); t1 = time.time() - t
     print(f"nnf W={W} M={M} D={D}: R={R} V={g.n_vertices} E={g.n_edges} TPG nodes={R*g.n_vertices:.3e} setup {t1:.3f}s", flush=True)
+    if len(sys.argv) > 6: g.set_mode(int(sys.argv[6]))
     t = time.time(); r = g.solve(max_lazy_iters=iters); t2 = time.time() - t
-    print(f"solve: iters={r['lazy_iters']} solved={r['solved']} err={r['final_error']:.4f} goal={r['goal_cost']:.4g} eval={r['n_evaluated']} coll={r['n_collisions']} {t2:.3f}s  last dp {g.last_dp_ms():.3f} ms", flush=True)
+    print(f"solve: iters={r['lazy_iters']} solved={r['solved']} err={r['final_error']:.4f} goal={r['goal_cost']:.4g} eval={r['n_evaluated']} coll={r['n_collisions']} {t2:.3f}s  last dp {g.last_dp_ms():.3f} ms band={g.band_info()}", flush=True)
 else:
     B = int(sys.argv[2]); iters = int(sys.argv[3])
     sph, box = synth.obstacles(3)

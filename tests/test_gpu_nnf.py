@@ -25,13 +25,15 @@ def _problem(O, synth, dh, seed, W, M, D):
     return poses[ids], counts, ik
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("seed,W,M,k,D", [(4, 5, 5, 5, 3), (3, 12, 20, 5, 1), (4, 20, 30, 4, 2), (1, 12, 20, 5, 1),
                                           (2, 8, 6, 3, 1), (4, 30, 40, 5, 1)])
-def test_nnf_matches_oracle(P, O, synth, nnf_worlds, seed, W, M, k, D):
+def test_nnf_matches_oracle(P, O, synth, nnf_worlds, seed, W, M, k, D, mode):
     dh, gw, ow = nnf_worlds
     ref, counts, ik = _problem(O, synth, dh, seed, W, M, D)
     o = O.nnf_run(ow, ref, counts, ik, k=k, D=D, max_lazy_iters=3000, nthreads=8)
     g = P.Nnf(gw, ref, counts, ik, num_nn=k, discretization=D)
+    g.set_mode(mode)  # 0: banded column-wise DP, 1: full-table wavefront
     assert (g.n_vertices, g.n_edges, g.n_ik) == (o["n_vertices"], o["n_edges"], o["n_ik"])
     assert np.array_equal(g.knn(), o["knn"])                      # findKnnNodes: bit-exact choices
     st, po = g.vertices()
@@ -67,6 +69,26 @@ def test_nnf_free_world_first_path_is_solution(P, O, synth):
     # re-solving is idempotent
     r2 = g.solve()
     assert r2["lazy_iters"] == 1 and np.array_equal(r2["path"], r["path"])
+
+
+def test_nnf_banded_equals_full_at_scale(P, O, synth, nnf_worlds):
+    """Mid-size problem (too slow for the CPU oracle's LazySP): both device searches must agree on
+    every LazySP iteration's goal cost, the evaluated/colliding edge counts and the final path."""
+    dh, gw, _ = nnf_worlds
+    ref, counts, ik = _problem(O, synth, dh, 4, 40, 128, 1)
+    out = []
+    for mode in (0, 1):
+        g = P.Nnf(gw, ref, counts, ik, num_nn=5, discretization=1)
+        g.set_mode(mode)
+        out.append(g.solve(max_lazy_iters=60))
+        if mode == 0:
+            info = g.band_info()
+            assert 0 < info["cells"] < len(ref) * g.n_vertices   # the band is a strict subset
+    a, b = out
+    assert np.array_equal(a["goal_cost_trace"], b["goal_cost_trace"])
+    assert (a["lazy_iters"], a["n_evaluated"], a["n_collisions"], a["solved"]) == \
+           (b["lazy_iters"], b["n_evaluated"], b["n_collisions"], b["solved"])
+    assert np.array_equal(a["path"], b["path"]) and a["final_error"] == b["final_error"]
 
 
 def test_nnf_bad_params(P, synth, nnf_worlds):
