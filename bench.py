@@ -10,7 +10,9 @@ nodes, 4096 queries, k=16.  A step is one pass of the hot path over that batch:
                (oracle port: the reference's own NN code lives in un-vendored OMPL), all host
                threads, on a bounded sample of the same queries against the same tree.
 Other BASELINE configs are reachable with --workload check_motion (10^6 edges, 0.01 rad, 256
-obstacles).  Prints ONE JSON line (rank 0).
+obstacles) and --workload rrtc (4096 independent RRTConnect queries, split over the GPUs); a
+short pass of both is also reported under "extra" of the default run.  Prints ONE JSON line
+(rank 0).
 """
 import argparse
 import json
@@ -32,11 +34,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="knn", choices=["knn", "check_motion"])
+    ap.add_argument("--workload", default="knn", choices=["knn", "check_motion", "rrtc"])
     ap.add_argument("--nodes", type=int, default=10_000_000)
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--edges", type=int, default=1_000_000)
+    ap.add_argument("--plans", type=int, default=4096)
+    ap.add_argument("--plan-iters", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     return ap.parse_args()
@@ -140,6 +144,28 @@ def run_reference(args, rank):
         sample = (f"{per_step} of the {args.queries} queries per step against the full {args.nodes}-node "
                   f"tree, k={args.k}, linear scan (NearestNeighborsLinear semantics), {cores} threads")
         config = {"workload": f"batched kNN sweep: N={args.nodes} nodes, 7-DOF, Q={args.queries}, k={args.k}"}
+    elif args.workload == "rrtc":
+        from concurrent.futures import ThreadPoolExecutor
+        dh, link, xyzr = synth.default_arm()
+        sph, box = synth.obstacles(3)
+        W = O.World(dh, link, xyzr, sph, box)
+        starts, goals = plan_problems(synth, W, args.plans)
+        impl = "ref" if O.ref() is not None else "port"
+        per_step = min(args.plans, 16 * cores)
+        pool = ThreadPoolExecutor(cores)
+        def one(qi):
+            return W.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=(0, 1), seed=4, query=qi,
+                                max_iters=args.plan_iters, max_nodes=4096, impl=impl)["status"]
+        def step(i):
+            lo = (i * per_step) % max(1, args.plans - per_step + 1)
+            list(pool.map(one, range(lo, lo + per_step)))
+        units, unit, metric = per_step, "plans/s", "RRTConnect plans/s"
+        sample = (f"{per_step} of the {args.plans} queries per step, one query per thread, "
+                  + ("the reference's own pr_ompl/src/RRTConnect.cpp over the OMPL-API stand-in (oracle/_ref)"
+                     if impl == "ref" else "oracle port of RRTConnect.cpp") + f", {cores} threads")
+        config = {"workload": f"{args.plans} independent RRTConnect queries (ext-con), 7-DOF, 256 obstacles, "
+                              f"<= {args.plan_iters} samples each"}
+        kind = "reference" if impl == "ref" else "port"
     else:
         dh, link, xyzr = synth.default_arm()
         sph, box = synth.obstacles(3)
@@ -167,11 +193,23 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config,
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores,
+                         "kind": kind if args.workload == "rrtc" else "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def plan_problems(synth, world, n, seed=4):
+    """n valid (start, goal) pairs: BASELINE 'independent RRTConnect queries', seed 4.  `world` is any
+    object with is_valid_batch (the device world in our arm, the oracle world in the reference arm)."""
+    import numpy as np
+    q = synth.cloud(seed, 8 * n)
+    v = world.is_valid_batch(q)
+    v = v[0] if isinstance(v, tuple) else v
+    qv = q[v == 1]
+    return np.ascontiguousarray(qv[0:2 * n:2]), np.ascontiguousarray(qv[1:2 * n:2])
 
 
 # --------------------------------------------------------------------------------------------
@@ -232,12 +270,18 @@ def run_ours(args, rank, local_rank, world):
         tree.set_profiling(True)
         kernel_ms = []
 
+        bufs = dict(idx=idx, dist=dd)
+        if world > 1:
+            bufs.update(gidx=gi, gdist=gd, fidx=fi, fdist=fd)
+
+        def local_search(qd, nq_, k_, io, do):
+            tree.nearest_k_device(qd, nq_, k_, io, do, stream=stream)
+
+        def merge(gi_, gd_, nparts, nq_, k_, fi_, fd_):
+            P.topk_merge_device(local_rank, gi_, gd_, nparts, nq_, k_, fi_, fd_, stream)
+
         def step(record=False):
-            tree.nearest_k_device(q_dev, Q, k, idx, dd, stream=stream)
-            if world > 1:
-                dist.all_gather_into_tensor(gi, idx)
-                dist.all_gather_into_tensor(gd, dd)
-                P.topk_merge_device(local_rank, gi, gd, world, Q, k, fi, fd, stream)
+            P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
             if record:
                 kernel_ms.append(tree.last_kernel_ms())
 
@@ -263,10 +307,7 @@ def run_ours(args, rank, local_rank, world):
                                                           P.capi._ptr(e2e_idx), P.capi._ptr(e2e_dist)))
             else:
                 q_dev.copy_(q_host, non_blocking=True)
-                tree.nearest_k_device(q_dev, Q, k, idx, dd, stream=stream)
-                dist.all_gather_into_tensor(gi, idx)
-                dist.all_gather_into_tensor(gd, dd)
-                P.topk_merge_device(local_rank, gi, gd, world, Q, k, fi, fd, stream)
+                P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
                 e2e_idx.copy_(fi, non_blocking=True)
                 e2e_dist.copy_(fd, non_blocking=True)
                 torch.cuda.synchronize()
@@ -275,6 +316,56 @@ def run_ours(args, rank, local_rank, world):
         e2e_dist = torch.empty((Q, k), dtype=torch.float64).pin_memory()
         h2d = n_local * 56 + Q * 56
         d2h = Q * k * 12
+    elif args.workload == "rrtc":
+        Bq = args.plans
+        dh, link, xyzr = synth.default_arm()
+        sph, box = synth.obstacles(3)
+        world_h = P.World(dh, link, xyzr, sph, box, device=local_rank)
+        starts_all, goals_all = plan_problems(synth, world_h, Bq)
+        p0, p1 = P.sharded.shard_bounds(Bq, world)[rank]
+        n_local = p1 - p0
+        s_host = torch.from_numpy(starts_all[p0:p1].copy()).pin_memory()
+        g_host = torch.from_numpy(goals_all[p0:p1].copy()).pin_memory()
+        s_dev, g_dev = s_host.to(dev), g_host.to(dev)
+        rb = P.RrtcBatch(world_h, n_local, -np.pi, np.pi, extension_type="ext-con", seed=4, query_id_base=p0,
+                         max_iters=args.plan_iters, max_nodes=2048)
+        kernel_ms = []
+
+        def step(record=False):
+            if record:
+                b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b_.record()
+            rb.run_device(s_dev, g_dev, stream)
+            if record:
+                e_.record()
+                e_.synchronize()
+                kernel_ms.append(b_.elapsed_time(e_))
+
+        launches_per_step = 1
+        units_per_step = Bq
+        metric, unit = "RRTConnect plans/s", "plans/s"
+        kernel_name = "rrtc_batch_kernel"
+        config = {
+            "workload": f"{Bq} independent RRTConnect queries (ext-con, default range, 0.01 resolution), 7-DOF "
+                        f"sphere-FK arm vs 256 obstacles, <= {args.plan_iters} samples each (BASELINE.json "
+                        f"configs[4], query-sharded)",
+            "parallelism": "single GPU" if world == 1 else f"queries split over {world} GPUs, no collective",
+            "l2": "L2 flushed by a 256 MB write between timed iterations",
+            "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks",
+        }
+
+        def e2e_step():
+            P.capi._check(P.lib().prgpu_rrtc_batch_run(rb.h, P.capi._ptr(s_host), P.capi._ptr(g_host)))
+            rb.summary()
+        h2d = n_local * 112
+        d2h = n_local * 16
+        rb.run_device(s_dev, g_dev, stream)
+        torch.cuda.synchronize()
+        summ = rb.summary()
+        nodes = int(summ["n_start"].sum() + summ["n_goal"].sum())
+        algo_bytes = n_local * 112 + nodes * 60 + n_local * 16
+        config["solved_fraction"] = float((summ["status"] == 6).mean())
+        config["mean_samples_per_plan"] = float(summ["iterations"].mean())
     else:
         E = args.edges
         dh, link, xyzr = synth.default_arm()
@@ -385,6 +476,34 @@ def run_ours(args, rank, local_rank, world):
         ms1 = time_knn(1, 1, reps=20)
         extra["single_query_scan"] = {"ms": ms1, "hbm_gbs": n_local * 56 / (ms1 * 1e-3) / 1e9,
                                       "frac_of_hbm_peak": n_local * 56 / (ms1 * 1e-3) / 1e9 / hbm_peak}
+
+    if world == 1 and not args.no_extra and args.workload == "knn":
+        del pts_dev
+        tree.close()
+        torch.cuda.empty_cache()
+        dh, link, xyzr = synth.default_arm()
+        sph, box = synth.obstacles(3)
+        wx = P.World(dh, link, xyzr, sph, box, device=local_rank)
+        ea, eb = synth.edges(2, 1_000_000)
+        ea_d, eb_d = torch.from_numpy(ea).to(dev), torch.from_numpy(eb).to(dev)
+        ev = torch.empty(len(ea), dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            wx.check_motion_batch_device(ea_d, eb_d, len(ea), 0.01, ev, stream=stream)
+        b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b_.record()
+        for _ in range(3):
+            wx.check_motion_batch_device(ea_d, eb_d, len(ea), 0.01, ev, stream=stream)
+        e_.record()
+        torch.cuda.synchronize()
+        extra["check_motion_1e6_edges_per_s"] = len(ea) / (b_.elapsed_time(e_) / 3 * 1e-3)
+        extra["check_motion_valid_fraction"] = float(ev.float().mean().item())
+        ps, pg = plan_problems(synth, wx, 4096)
+        rbx = P.RrtcBatch(wx, 4096, -np.pi, np.pi, extension_type="ext-con", seed=4, max_iters=1000, max_nodes=2048)
+        rbx.run(ps, pg)
+        t0 = time.perf_counter()
+        rbx.run(ps, pg)
+        extra["rrtc_4096_plans_per_s_e2e"] = 4096 / (time.perf_counter() - t0)
+        extra["rrtc_solved_fraction"] = float((rbx.summary()["status"] == 6).mean())
 
     if rank != 0:
         return
