@@ -553,6 +553,25 @@ def cpu_baseline(args, synth):
     dh, link, xyzr = synth.default_arm()
     sph, box = synth.obstacles(3)
     W = O.World(dh, link, xyzr, sph, box)
+    if args.workload == "rrtc":
+        import numpy as np
+        from concurrent.futures import ThreadPoolExecutor
+        starts, goals = plan_problems(synth, W, args.plans)
+        impl = "ref" if O.ref() is not None else "port"
+        ns = min(args.plans, 128 * cores)
+
+        def one(qi):
+            return W.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=(0, 1), seed=4, query=qi,
+                                max_iters=args.plan_iters, max_nodes=4096, impl=impl)["status"]
+        with ThreadPoolExecutor(cores) as pool:
+            list(pool.map(one, range(cores)))
+            t0 = time.perf_counter()
+            list(pool.map(one, range(ns)))
+            dt = time.perf_counter() - t0
+        return {"value": ns / dt, "unit": "plans/s", "cores": cores, "kind": "reference" if impl == "ref" else "port",
+                "sample": f"first {ns} of the {args.plans} queries, one query per thread, "
+                          + ("the reference's own RRTConnect.cpp over the OMPL-API stand-in (oracle/_ref)"
+                             if impl == "ref" else "oracle port of RRTConnect.cpp") + f", {cores} threads"}
     a, b = synth.edges(2, args.edges)
     ns = min(args.edges, 6000 * cores)
     t0 = time.perf_counter()
@@ -572,6 +591,10 @@ def main():
         run_reference(args, rank)
         return
     run_ours(args, rank, local_rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
