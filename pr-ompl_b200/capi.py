@@ -50,6 +50,8 @@ SIGNATURES = {
     "prgpu_knn_get_points": (C.c_int, [c_vp, C.c_uint64, C.c_uint64, c_vp]),
     "prgpu_knn_nearest_k": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
     "prgpu_knn_nearest_k_device": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "prgpu_knn_set_search_mode": (C.c_int, [c_vp, C.c_int]),
+    "prgpu_knn_search_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "prgpu_knn_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "prgpu_knn_last_kernel_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
     "prgpu_world_set_profiling": (C.c_int, [c_vp, C.c_int]),
@@ -161,6 +163,15 @@ class KnnIndex:
         n = C.c_uint64()
         _check(lib().prgpu_knn_size(self.h, C.byref(n)))
         return n.value
+
+    def set_search_mode(self, force_exact):
+        """force_exact=True disables the fp32 filter path (results are identical either way)."""
+        _check(lib().prgpu_knn_set_search_mode(self.h, int(force_exact)))
+
+    def search_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(lib().prgpu_knn_search_stats(self.h, C.byref(a), C.byref(b)))
+        return dict(filter_calls=a.value, fallback_queries=b.value)
 
     def set_profiling(self, on=True):
         _check(lib().prgpu_knn_set_profiling(self.h, int(on)))

@@ -61,15 +61,27 @@ static int knn_reserve(prgpu_knn *h, uint64_t need) {
   uint64_t cap = std::max<uint64_t>(need, std::max<uint64_t>(2 * h->stride, 4096));
   cap = round_up(cap, KNN_TILE);
   double *np = nullptr;
+  float *nf = nullptr;
   PRGPU_CUDA_TRY(cudaMalloc(&np, (size_t)h->dim * cap * sizeof(double)));
+  if (h->dim <= 7)
+    PRGPU_CUDA_TRY(cudaMalloc(&nf, (size_t)cap * 8 * sizeof(float)));
+  if (!h->xmax2) {
+    PRGPU_CUDA_TRY(cudaMalloc(&h->xmax2, sizeof(double)));
+    PRGPU_CUDA_TRY(cudaMemsetAsync(h->xmax2, 0, sizeof(double), h->stream));
+  }
   if (h->pts) {
     for (int d = 0; d < h->dim; ++d)
       PRGPU_CUDA_TRY(cudaMemcpyAsync(np + (size_t)d * cap, h->pts + (size_t)d * h->stride,
                                      h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (nf && h->ptsf)
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(nf, h->ptsf, h->n * 8 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
     cudaFree(h->pts);
+    if (h->ptsf)
+      cudaFree(h->ptsf);
   }
   h->pts = np;
+  h->ptsf = nf;
   h->stride = cap;
   return PRGPU_OK;
 }
@@ -112,6 +124,15 @@ int prgpu_knn_destroy(prgpu_knn_t *h) {
     cudaStreamSynchronize(h->stream);
   if (h->pts)
     cudaFree(h->pts);
+  if (h->ptsf)
+    cudaFree(h->ptsf);
+  if (h->xmax2)
+    cudaFree(h->xmax2);
+  for (void *p : {(void *)h->scratch.cand_dist, (void *)h->scratch.cand_idx, (void *)h->scratch.flags,
+                  (void *)h->scratch.fb_q, (void *)h->scratch.fb_dist, (void *)h->scratch.fb_idx,
+                  (void *)h->scratch.fb_lo})
+    if (p)
+      cudaFree(p);
   if (h->scratch.part_dist)
     cudaFree(h->scratch.part_dist);
   if (h->scratch.part_idx)
@@ -136,6 +157,28 @@ int prgpu_knn_clear(prgpu_knn_t *h) {
   if (!h)
     return fail(PRGPU_EINVAL, "knn_clear: NULL handle");
   h->n = 0;
+  if (h->xmax2) {
+    PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+    PRGPU_CUDA_TRY(cudaMemsetAsync(h->xmax2, 0, sizeof(double), h->stream));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return PRGPU_OK;
+}
+
+int prgpu_knn_set_search_mode(prgpu_knn_t *h, int force_exact) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "knn_set_search_mode: NULL handle");
+  h->force_exact = force_exact ? 1 : 0;
+  return PRGPU_OK;
+}
+
+int prgpu_knn_search_stats(prgpu_knn_t *h, uint64_t *filter_calls, uint64_t *fallback_queries) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "knn_search_stats: NULL handle");
+  if (filter_calls)
+    *filter_calls = h->scratch.filter_calls;
+  if (fallback_queries)
+    *fallback_queries = h->scratch.fallback_queries;
   return PRGPU_OK;
 }
 
@@ -162,7 +205,7 @@ int prgpu_knn_add_device(prgpu_knn_t *h, const double *pts_dev, uint64_t n, void
   int rc = knn_reserve(h, h->n + n);
   if (rc != PRGPU_OK)
     return rc;
-  rc = knn_transpose_append(h->dim, pts_dev, n, h->pts, h->stride, h->n, (cudaStream_t)stream);
+  rc = knn_transpose_append(h->dim, pts_dev, n, h->pts, h->ptsf, h->xmax2, h->stride, h->n, (cudaStream_t)stream);
   if (rc != PRGPU_OK)
     return rc;
   h->n += n;
@@ -223,8 +266,8 @@ int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64
       return rc;
     dd = h->d_dist.as<double>();
   }
-  return knn_search(h->dim, h->pts, h->stride, (uint32_t)h->n, h->index_base, queries_dev, (uint32_t)nq, k,
-                    lo_dev, idx_dev, dd, h->scratch, h->sm_count, (cudaStream_t)stream, &h->timer);
+  return knn_search(h->dim, h->view(), queries_dev, (uint32_t)nq, k, lo_dev, idx_dev, dd, h->scratch, h->sm_count,
+                    (cudaStream_t)stream, &h->timer, h->force_exact);
 }
 
 int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int k, const uint32_t *lo,
@@ -253,9 +296,8 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
         cudaMemcpyAsync(h->d_lo.p, lo, (size_t)nq * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     lo_dev = h->d_lo.as<uint32_t>();
   }
-  rc = knn_search(h->dim, h->pts, h->stride, (uint32_t)h->n, h->index_base, h->d_q.as<double>(),
-                  (uint32_t)nq, k, lo_dev, h->d_idx.as<uint32_t>(), h->d_dist.as<double>(), h->scratch,
-                  h->sm_count, h->stream, &h->timer);
+  rc = knn_search(h->dim, h->view(), h->d_q.as<double>(), (uint32_t)nq, k, lo_dev, h->d_idx.as<uint32_t>(),
+                  h->d_dist.as<double>(), h->scratch, h->sm_count, h->stream, &h->timer, h->force_exact);
   if (rc != PRGPU_OK)
     return rc;
   PRGPU_CUDA_TRY(cudaMemcpyAsync(idx, h->d_idx.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost,

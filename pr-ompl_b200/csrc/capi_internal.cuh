@@ -33,6 +33,19 @@ struct prgpu_knn {
   int device = 0, dim = 0, sm_count = 0;
   cudaStream_t stream = nullptr;
   double *pts = nullptr; // SoA, dim x stride
+  float *ptsf = nullptr; // fp32 mirror, stride x 8 (dim <= 7 only)
+  double *xmax2 = nullptr; // device scalar: max |x|^2
+  int force_exact = 0;
+  prgpu::KnnTreeView view() const {
+    prgpu::KnnTreeView v;
+    v.pts = pts;
+    v.ptsf = ptsf;
+    v.xmax2 = xmax2;
+    v.stride = stride;
+    v.n = (uint32_t)n;
+    v.index_base = index_base;
+    return v;
+  }
   uint64_t stride = 0, n = 0;
   uint32_t index_base = 0;
   prgpu::KnnScratch scratch;

@@ -297,14 +297,34 @@ topk_merge_kernel(const uint32_t *__restrict__ idx_parts, const double *__restri
   warp_merge(get, P, k, dist_out + ((size_t)g * nq + q) * k, idx_out + ((size_t)g * nq + q) * k);
 }
 
-// row-major (n x dim) -> SoA at `offset`
+// row-major (n x dim) -> fp64 SoA at `offset`, plus the fp32 mirror (8 floats per node, |x|^2 in slot 7)
+// and the running maximum of |x|^2
 __global__ void transpose_append_kernel(const double *__restrict__ aos, uint64_t n, int dim,
-                                        double *__restrict__ soa, uint64_t stride, uint64_t offset) {
+                                        double *__restrict__ soa, float *__restrict__ ptsf,
+                                        double *__restrict__ xmax2, uint64_t stride, uint64_t offset) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  for (int d = 0; d < dim; ++d)
-    soa[(uint64_t)d * stride + offset + i] = aos[i * dim + d];
+  double n2 = 0.0;
+  if (i < n) {
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int d = 0; d < dim; ++d) {
+      const double v = aos[i * dim + d];
+      soa[(uint64_t)d * stride + offset + i] = v;
+      n2 += v * v;
+      if (d < 7)
+        f[d] = (float)v;
+    }
+    if (ptsf) {
+      f[7] = (float)n2;
+      float4 *o = reinterpret_cast<float4 *>(ptsf + (offset + i) * 8);
+      o[0] = make_float4(f[0], f[1], f[2], f[3]);
+      o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    n2 = fmax(n2, __shfl_xor_sync(0xffffffffu, n2, off));
+  if ((threadIdx.x & 31) == 0 && n2 > 0.0) // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long *>(xmax2), (unsigned long long)__double_as_longlong(n2));
 }
 __global__ void gather_points_kernel(const double *__restrict__ soa, uint64_t stride, uint64_t first,
                                      uint64_t n, int dim, double *__restrict__ aos) {
@@ -379,7 +399,7 @@ int launch_tile(const double *pts, uint64_t stride, uint32_t n, uint32_t index_b
 
 } // namespace
 
-static int scratch_reserve(double *&d, uint32_t *&i, size_t &cap, size_t need) {
+int scratch_reserve(double *&d, uint32_t *&i, size_t &cap, size_t need) {
   if (cap >= need)
     return PRGPU_OK;
   if (d)
@@ -412,7 +432,7 @@ int topk_merge(const uint32_t *idx_parts, const double *dist_parts, int nparts, 
 }
 
 // any number of partial lists: passes of 128-way merges (parts -> parts2 -> ... -> out)
-static int merge_passes(KnnScratch &sc, int nparts, uint32_t nq, int k, uint32_t *idx_out, double *dist_out,
+int merge_passes(KnnScratch &sc, int nparts, uint32_t nq, int k, uint32_t *idx_out, double *dist_out,
                         cudaStream_t stream) {
   const uint32_t *si = sc.part_idx;
   const double *sd = sc.part_dist;
@@ -436,10 +456,12 @@ static int merge_passes(KnnScratch &sc, int nparts, uint32_t nq, int k, uint32_t
   return topk_merge(si, sd, nparts, nq, k, idx_out, dist_out, stream);
 }
 
-int knn_search(int dim, const double *pts_soa, uint64_t stride, uint32_t n, uint32_t index_base,
-               const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev, uint32_t *idx_dev,
-               double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
-               KernelTimer *timer) {
+int knn_search_exact(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k,
+                     const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count,
+                     cudaStream_t stream, KernelTimer *timer) {
+  const double *pts_soa = t.pts;
+  const uint64_t stride = t.stride;
+  const uint32_t n = t.n, index_base = t.index_base;
   if (k < 1 || k > PRGPU_MAX_K)
     return fail(PRGPU_ELIMIT, "knn: k must be in [1,PRGPU_MAX_K]");
   if (nq == 0)
@@ -520,12 +542,12 @@ int knn_search(int dim, const double *pts_soa, uint64_t stride, uint32_t n, uint
   return PRGPU_OK;
 }
 
-int knn_transpose_append(int dim, const double *aos_dev, uint64_t n_new, double *pts_soa, uint64_t stride,
-                         uint64_t offset, cudaStream_t stream) {
+int knn_transpose_append(int dim, const double *aos_dev, uint64_t n_new, double *pts_soa, float *ptsf,
+                         double *xmax2, uint64_t stride, uint64_t offset, cudaStream_t stream) {
   if (n_new == 0)
     return PRGPU_OK;
-  transpose_append_kernel<<<(unsigned)((n_new + 255) / 256), 256, 0, stream>>>(aos_dev, n_new, dim, pts_soa,
-                                                                            stride, offset);
+  transpose_append_kernel<<<(unsigned)((n_new + 255) / 256), 256, 0, stream>>>(aos_dev, n_new, dim, pts_soa, ptsf,
+                                                                            xmax2, stride, offset);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

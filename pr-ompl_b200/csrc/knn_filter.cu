@@ -1,0 +1,470 @@
+// K1 fast path: fp32 filter scan + fp64 re-rank with a proof of exactness.
+//
+// The exact kernel (knn.cu) spends 20 FP64 instructions per (query, node) pair because the
+// reference's distance forbids FMA and runs on the half-rate FP64 pipe.  For the batched shapes
+// (>= 128 queries per tree pass, k <= 24) almost all of that work only establishes that a node is
+// NOT among the k nearest.  This path does that part in fp32:
+//   1. knn_filter_kernel: key(q,x) = |x|^2 - 2 q.x  (= |q-x|^2 - |q|^2) from an fp32 mirror of the tree,
+//      7 FFMA + 1 compare per pair, keeping the k+8 smallest keys per query (same tiling, bulk-copy
+//      double buffering and chunk merge as the exact kernel).
+//   2. knn_rerank_kernel: one warp per query recomputes the reference's exact fp64 distance of the
+//      k+8 candidates, sorts them under (distance, index) and emits the first k -- and PROVES that no
+//      discarded node can precede them: every discarded node has key >= keymax, the fp32 key is
+//      within eps = 16 * 2^-24 * (max|x| + |q|)^2 of the real value (9.1 u (|x|+|q|)^2 by a standard
+//      running-error bound of the 8-term FMA chain, rounded inputs included), so its exact squared
+//      distance is >= keymax - eps + |q|^2.  If the k-th exact squared distance is not strictly below
+//      that bound (ties, heavy duplicates), the query is flagged.
+//   3. flagged queries are re-run through the exact kernel.  Results are therefore bit-identical to
+//      knn_search_exact for every input.
+#include <math_constants.h>
+#include <vector>
+#include "knn.cuh"
+
+namespace prgpu {
+namespace {
+
+constexpr int FT_TILE = 256;     // nodes per tile (32 bytes each)
+constexpr int FT_THREADS = 128;  // queries per block
+
+constexpr int FT_RQ = 2;         // queries per thread (register tile: halves the shared-memory reads per pair)
+constexpr int FT_BUF = 8;        // per-query register buffer of pending candidates
+
+// Keeps, per query, the kp smallest keys seen so far.  The hot loop only compares against a
+// register threshold and appends the rare qualifying candidate to a small register buffer; when a
+// lane's buffer is nearly full the WARP merges that lane's list (kp entries in shared memory) with
+// its buffer -- 32 items, one per lane, one bitonic sort -- and hands the tightened threshold back.
+// No divergent per-lane insertion loops remain.
+template <int DIM>
+__global__ void __launch_bounds__(FT_THREADS)
+knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
+                  int kp, const uint32_t *__restrict__ lo, uint32_t tiles_per_chunk, double *__restrict__ out_key,
+                  uint32_t *__restrict__ out_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
+  float *lkey = reinterpret_cast<float *>(bars + 2);                       // [RQ][THREADS][kp]
+  uint32_t *lidx = reinterpret_cast<uint32_t *>(lkey + (size_t)FT_RQ * kp * FT_THREADS);
+  __shared__ uint32_t s_lo_min;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t qid[FT_RQ];
+  bool act[FT_RQ];
+  float q2[FT_RQ][7];
+  uint32_t my_lo[FT_RQ];
+#pragma unroll
+  for (int u = 0; u < FT_RQ; ++u) {
+    qid[u] = (blockIdx.x * FT_RQ + u) * FT_THREADS + tid;
+    act[u] = qid[u] < nq;
+#pragma unroll
+    for (int d = 0; d < 7; ++d)
+      q2[u][d] = (act[u] && d < DIM) ? (float)(-2.0 * queries[(size_t)qid[u] * DIM + d]) : 0.f;
+    my_lo[u] = (act[u] && lo) ? lo[qid[u]] : 0u;
+  }
+  if (tid == 0) {
+    s_lo_min = 0xFFFFFFFFu;
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  for (int e = 0; e < FT_RQ * kp; ++e) {
+    const int u = e / kp, j = e - u * kp;
+    lkey[((size_t)u * FT_THREADS + tid) * kp + j] = CUDART_INF_F;
+    lidx[((size_t)u * FT_THREADS + tid) * kp + j] = PRGPU_INVALID_INDEX;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < FT_RQ; ++u)
+    if (act[u])
+      atomicMin(&s_lo_min, my_lo[u]);
+  __syncthreads();
+
+  const uint32_t ntiles = (n + FT_TILE - 1) / FT_TILE;
+  uint32_t t0 = blockIdx.y * tiles_per_chunk;
+  const uint32_t t1 = min(t0 + tiles_per_chunk, ntiles);
+  if (s_lo_min != 0xFFFFFFFFu)
+    t0 = max(t0, s_lo_min / FT_TILE);
+
+  auto issue = [&](uint32_t t, int buf) {
+    mbar_expect_tx(&bars[buf], FT_TILE * 32);
+    bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
+  };
+
+  float thr[FT_RQ];            // upper bound of the kp-th smallest key of each query
+  float bk[FT_RQ][FT_BUF];     // pending candidates
+  uint32_t bi[FT_RQ][FT_BUF];
+  int bc[FT_RQ];
+#pragma unroll
+  for (int u = 0; u < FT_RQ; ++u) {
+    thr[u] = act[u] ? CUDART_INF_F : -CUDART_INF_F; // inactive: nothing ever qualifies
+    bc[u] = 0;
+#pragma unroll
+    for (int c = 0; c < FT_BUF; ++c) {
+      bk[u][c] = CUDART_INF_F;
+      bi[u][c] = PRGPU_INVALID_INDEX;
+    }
+  }
+  auto offer = [&](int u, float key, uint32_t gi) {
+    if (key < thr[u] && gi >= my_lo[u]) {
+#pragma unroll
+      for (int c = 0; c < FT_BUF; ++c)
+        if (bc[u] == c) {
+          bk[u][c] = key;
+          bi[u][c] = gi;
+        }
+      ++bc[u];
+    }
+  };
+  // warp-cooperative merge of lane L's list and buffer (query slot u); all 32 lanes participate
+  auto compact = [&](int u, int L) {
+    const int cnt = __shfl_sync(0xffffffffu, bc[u], L);
+    if (cnt == 0)
+      return;
+    const int wt = (tid & ~31) + L; // thread whose list is merged
+    float *K = lkey + ((size_t)u * FT_THREADS + wt) * kp;
+    uint32_t *I = lidx + ((size_t)u * FT_THREADS + wt) * kp;
+    float key = CUDART_INF_F;
+    uint32_t idx = PRGPU_INVALID_INDEX;
+    if (lane < kp) {
+      key = K[lane];
+      idx = I[lane];
+    }
+#pragma unroll
+    for (int c = 0; c < FT_BUF; ++c) {
+      const float vk = __shfl_sync(0xffffffffu, bk[u][c], L);
+      const uint32_t vi = __shfl_sync(0xffffffffu, bi[u][c], L);
+      if (lane == kp + c && c < cnt) {
+        key = vk;
+        idx = vi;
+      }
+    }
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int strd = size >> 1; strd > 0; strd >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, key, strd);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, strd);
+        const bool keep_min = (((lane & size) == 0) == ((lane & strd) == 0));
+        const bool other_less = ok < key || (ok == key && oi < idx);
+        const bool other_more = key < ok || (ok == key && idx < oi);
+        if (keep_min ? other_less : other_more) {
+          key = ok;
+          idx = oi;
+        }
+      }
+    }
+    if (lane < kp) {
+      K[lane] = key;
+      I[lane] = idx;
+    }
+    const float nt = __shfl_sync(0xffffffffu, key, kp - 1);
+    if (lane == L) {
+      thr[u] = nt;
+      bc[u] = 0;
+    }
+  };
+  auto compact_if = [&](bool need) {
+    unsigned mask = __ballot_sync(0xffffffffu, need);
+    while (mask) {
+      const int L = __ffs(mask) - 1;
+      mask &= mask - 1;
+#pragma unroll
+      for (int u = 0; u < FT_RQ; ++u)
+        compact(u, L);
+    }
+    __syncwarp();
+  };
+  auto key_of = [&](int u, const float4 &a, const float4 &b) {
+    float acc = b.w; // |x|^2
+    acc = fmaf(q2[u][0], a.x, acc);
+    if (DIM > 1) acc = fmaf(q2[u][1], a.y, acc);
+    if (DIM > 2) acc = fmaf(q2[u][2], a.z, acc);
+    if (DIM > 3) acc = fmaf(q2[u][3], a.w, acc);
+    if (DIM > 4) acc = fmaf(q2[u][4], b.x, acc);
+    if (DIM > 5) acc = fmaf(q2[u][5], b.y, acc);
+    if (DIM > 6) acc = fmaf(q2[u][6], b.z, acc);
+    return acc;
+  };
+
+  if (tid == 0 && t0 < t1)
+    issue(t0, 0);
+  for (uint32_t t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    const uint32_t parity = ((t - t0) >> 1) & 1;
+    if (tid == 0 && t + 1 < t1)
+      issue(t + 1, buf ^ 1);
+    mbar_wait(&bars[buf], parity);
+    {
+      const float4 *T = tile + buf * FT_TILE * 2;
+      const uint32_t base = t * FT_TILE;
+      const uint32_t jmax = min((uint32_t)FT_TILE, n - base);
+      uint32_t j = 0;
+      for (; j + 3 < jmax; j += 4) {
+        const float4 a0 = T[2 * j], b0 = T[2 * j + 1], a1 = T[2 * j + 2], b1 = T[2 * j + 3];
+        const float4 a2 = T[2 * j + 4], b2 = T[2 * j + 5], a3 = T[2 * j + 6], b3 = T[2 * j + 7];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < FT_RQ; ++u) {
+          const float k0 = key_of(u, a0, b0), k1 = key_of(u, a1, b1), k2 = key_of(u, a2, b2), k3 = key_of(u, a3, b3);
+          if (fminf(fminf(k0, k1), fminf(k2, k3)) < thr[u]) {
+            offer(u, k0, base + j);
+            offer(u, k1, base + j + 1);
+            offer(u, k2, base + j + 2);
+            offer(u, k3, base + j + 3);
+            any = true;
+          }
+        }
+        if (__any_sync(0xffffffffu, any)) {
+          bool need = false;
+#pragma unroll
+          for (int u = 0; u < FT_RQ; ++u)
+            need = need || bc[u] > FT_BUF - 4; // the next group may add up to 4
+          compact_if(need);
+        }
+      }
+      for (; j < jmax; ++j) {
+        const float4 a0 = T[2 * j], b0 = T[2 * j + 1];
+#pragma unroll
+        for (int u = 0; u < FT_RQ; ++u)
+          offer(u, key_of(u, a0, b0), base + j);
+        bool need = false;
+#pragma unroll
+        for (int u = 0; u < FT_RQ; ++u)
+          need = need || bc[u] > FT_BUF - 4;
+        compact_if(need);
+      }
+    }
+    __syncthreads();
+  }
+  {
+    bool need = false;
+#pragma unroll
+    for (int u = 0; u < FT_RQ; ++u)
+      need = need || bc[u] > 0;
+    compact_if(need);
+  }
+#pragma unroll
+  for (int u = 0; u < FT_RQ; ++u)
+    if (act[u]) {
+      const float *K = lkey + ((size_t)u * FT_THREADS + tid) * kp;
+      const uint32_t *I = lidx + ((size_t)u * FT_THREADS + tid) * kp;
+      double *od = out_key + ((size_t)blockIdx.y * nq + qid[u]) * kp;
+      uint32_t *oi = out_idx + ((size_t)blockIdx.y * nq + qid[u]) * kp;
+      for (int e = 0; e < kp; ++e) {
+        const uint32_t i = I[e];
+        od[e] = i == PRGPU_INVALID_INDEX ? CUDART_INF : (double)K[e];
+        oi[e] = i;
+      }
+    }
+}
+
+// One warp per query: exact fp64 distances of the kp (<= 32) candidates, bitonic sort under
+// (distance, index), emit k, prove or flag.
+template <int DIM>
+__global__ void __launch_bounds__(128)
+knn_rerank_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t index_base, const double *__restrict__ xmax2,
+                  const double *__restrict__ queries, uint32_t nq, int k, int kp, const double *__restrict__ cand_key,
+                  const uint32_t *__restrict__ cand_idx, uint32_t *__restrict__ idx_out, double *__restrict__ dist_out,
+                  uint32_t *__restrict__ flags) {
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nq)
+    return;
+  const int lane = threadIdx.x & 31;
+  double qx[DIM];
+  double qn2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    qx[d] = queries[(size_t)q * DIM + d];
+    qn2 += qx[d] * qx[d];
+  }
+  uint32_t idx = PRGPU_INVALID_INDEX;
+  double key = CUDART_INF, dist = CUDART_INF;
+  if (lane < kp) {
+    idx = cand_idx[(size_t)q * kp + lane];
+    key = cand_key[(size_t)q * kp + lane];
+  }
+  if (idx != PRGPU_INVALID_INDEX) {
+    double x[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+      x[d] = pts[(size_t)d * stride + idx];
+    dist = __dsqrt_rn(sqdist_exact<DIM>(x, qx)); // RealVectorStateSpace::distance(node, query)
+  }
+  // the filter list is full iff its last entry is a real node; its key bounds every discarded node
+  const uint32_t last_idx = __shfl_sync(0xffffffffu, idx, kp - 1);
+  const double keymax = __shfl_sync(0xffffffffu, key, kp - 1);
+  // bitonic sort of 32 (dist, idx) pairs, ascending
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int strd = size >> 1; strd > 0; strd >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, dist, strd);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, strd);
+      const bool up = ((lane & size) == 0);     // ascending block
+      const bool lower = ((lane & strd) == 0);  // this lane keeps the smaller of the pair when ascending
+      const bool other_less = od < dist || (od == dist && oi < idx);
+      const bool take = (up == lower) ? other_less : !other_less && !(od == dist && oi == idx);
+      if (take) {
+        dist = od;
+        idx = oi;
+      }
+    }
+  }
+  if (lane < k) {
+    dist_out[(size_t)q * k + lane] = dist;
+    idx_out[(size_t)q * k + lane] = idx == PRGPU_INVALID_INDEX ? idx : idx + index_base;
+  }
+  const double dk = __shfl_sync(0xffffffffu, dist, k - 1);
+  if (lane == 0 && last_idx != PRGPU_INVALID_INDEX) { // nodes were discarded: prove they cannot matter
+    const double xn = sqrt(*xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
+    const double eps = 16.0 * 5.9604644775390625e-08 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
+    const double bound = keymax - eps + qn2; // lower bound of the exact squared distance of any discarded node
+    const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (qn2 + 1.0);
+    if (!(sk < bound)) {
+      const uint32_t slot = atomicAdd(flags, 1u);
+      flags[1 + slot] = q;
+    }
+  }
+}
+
+__global__ void gather_queries_kernel(const double *__restrict__ queries, const uint32_t *__restrict__ lo, int dim,
+                                      const uint32_t *__restrict__ ids, uint32_t n, double *__restrict__ out_q,
+                                      uint32_t *__restrict__ out_lo) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const uint32_t q = ids[i];
+  for (int d = 0; d < dim; ++d)
+    out_q[(size_t)i * dim + d] = queries[(size_t)q * dim + d];
+  if (out_lo)
+    out_lo[i] = lo ? lo[q] : 0u;
+}
+__global__ void scatter_rows_kernel(const uint32_t *__restrict__ ids, uint32_t n, int k, const uint32_t *__restrict__ si,
+                                    const double *__restrict__ sd, uint32_t *__restrict__ idx_out,
+                                    double *__restrict__ dist_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (uint32_t)k)
+    return;
+  const uint32_t row = i / k, e = i % k, q = ids[row];
+  idx_out[(size_t)q * k + e] = si[i];
+  dist_out[(size_t)q * k + e] = sd[i];
+}
+
+template <int DIM>
+int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k, const uint32_t *lo,
+                uint32_t *idx_out, double *dist_out, KnnScratch &sc, int sm_count, cudaStream_t stream,
+                KernelTimer *timer) {
+  const int kp = k + KNN_FILTER_MARGIN;
+  const size_t smem = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t) + (size_t)FT_RQ * kp * FT_THREADS * 8;
+  auto kern = knn_filter_kernel<DIM>;
+  PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FT_THREADS, smem));
+  per_sm = per_sm > 0 ? per_sm : 1;
+  const uint32_t qblocks = (nq + FT_RQ * FT_THREADS - 1) / (FT_RQ * FT_THREADS);
+  const uint32_t ntiles = (t.n + FT_TILE - 1) / FT_TILE;
+  uint32_t chunks = (uint32_t)(per_sm * sm_count) / qblocks;
+  chunks = chunks < 1 ? 1 : chunks;
+  if (chunks > 4096)
+    chunks = 4096;
+  if (chunks > ntiles)
+    chunks = ntiles;
+  const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
+  chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+
+  int rc = scratch_reserve(sc.cand_dist, sc.cand_idx, sc.cand_capacity, (size_t)nq * kp);
+  if (rc != PRGPU_OK)
+    return rc;
+  if (sc.flags_capacity < (size_t)nq + 1) {
+    if (sc.flags)
+      cudaFree(sc.flags);
+    sc.flags = nullptr;
+    sc.flags_capacity = 0;
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.flags, ((size_t)nq + 1) * sizeof(uint32_t)));
+    sc.flags_capacity = (size_t)nq + 1;
+  }
+  PRGPU_CUDA_TRY(cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t), stream));
+  double *pk = sc.cand_dist;
+  uint32_t *pi = sc.cand_idx;
+  if (chunks > 1) {
+    rc = scratch_reserve(sc.part_dist, sc.part_idx, sc.part_capacity, (size_t)chunks * nq * kp);
+    if (rc != PRGPU_OK)
+      return rc;
+    pk = sc.part_dist;
+    pi = sc.part_idx;
+  }
+  if (timer)
+    timer->begin(stream);
+  kern<<<dim3(qblocks, chunks), FT_THREADS, smem, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, tiles_per_chunk, pk, pi);
+  if (timer)
+    timer->end(stream);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  if (chunks > 1) {
+    rc = merge_passes(sc, (int)chunks, nq, kp, sc.cand_idx, sc.cand_dist, stream);
+    if (rc != PRGPU_OK)
+      return rc;
+  }
+  knn_rerank_kernel<DIM><<<(nq + 3) / 4, 128, 0, stream>>>(t.pts, t.stride, t.index_base, t.xmax2, queries, nq, k, kp,
+                                                         sc.cand_dist, sc.cand_idx, idx_out, dist_out, sc.flags);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  ++sc.filter_calls;
+
+  // unproven queries (ties at the cut, heavy duplicates) take the exact kernel
+  uint32_t nflag = 0;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(&nflag, sc.flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (nflag == 0)
+    return PRGPU_OK;
+  sc.fallback_queries += nflag;
+  if (sc.fb_capacity < nflag) {
+    for (void *p : {(void *)sc.fb_q, (void *)sc.fb_dist, (void *)sc.fb_idx, (void *)sc.fb_lo})
+      if (p)
+        cudaFree(p);
+    sc.fb_q = sc.fb_dist = nullptr;
+    sc.fb_idx = sc.fb_lo = nullptr;
+    sc.fb_capacity = 0;
+    const size_t cap = (size_t)nflag * 2;
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_q, cap * DIM * sizeof(double)));
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_dist, cap * KNN_FILTER_MAX_K * sizeof(double)));
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_idx, cap * KNN_FILTER_MAX_K * sizeof(uint32_t)));
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_lo, cap * sizeof(uint32_t)));
+    sc.fb_capacity = cap;
+  }
+  gather_queries_kernel<<<(nflag + 127) / 128, 128, 0, stream>>>(queries, lo, DIM, sc.flags + 1, nflag, sc.fb_q,
+                                                                sc.fb_lo);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  rc = knn_search_exact(DIM, t, sc.fb_q, nflag, k, lo ? sc.fb_lo : nullptr, sc.fb_idx, sc.fb_dist, sc, sm_count,
+                        stream, nullptr);
+  if (rc != PRGPU_OK)
+    return rc;
+  scatter_rows_kernel<<<(nflag * k + 127) / 128, 128, 0, stream>>>(sc.flags + 1, nflag, k, sc.fb_idx, sc.fb_dist,
+                                                                  idx_out, dist_out);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
+} // namespace
+
+int knn_search(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev,
+               uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
+               KernelTimer *timer, int force_exact) {
+  const bool eligible = !force_exact && t.ptsf != nullptr && dim <= 7 && k >= 1 &&
+                        k + KNN_FILTER_MARGIN <= 32 && nq >= (uint32_t)FT_THREADS && t.n >= 8192;
+  if (!eligible)
+    return knn_search_exact(dim, t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, timer);
+  switch (dim) {
+#define PRGPU_DIM_CASE(D)                                                                          \
+  case D:                                                                                          \
+    return filter_path<D>(t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, timer);
+    PRGPU_DIM_CASE(1)
+    PRGPU_DIM_CASE(2)
+    PRGPU_DIM_CASE(3)
+    PRGPU_DIM_CASE(4)
+    PRGPU_DIM_CASE(5)
+    PRGPU_DIM_CASE(6)
+    PRGPU_DIM_CASE(7)
+#undef PRGPU_DIM_CASE
+  }
+  return fail(PRGPU_ELIMIT, "knn: dim must be in [1,PRGPU_MAX_DIM]");
+}
+
+} // namespace prgpu

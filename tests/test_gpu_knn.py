@@ -112,3 +112,62 @@ def test_topk_merge_matches_single_pass(P, O, synth):
     ri, rd = O.knn(pts, q, k, nthreads=8)
     assert np.array_equal(oi.cpu().numpy().view(np.uint32), ri)
     assert np.array_equal(od.cpu().numpy(), rd)
+
+
+# ---- the fp32-filter fast path must be indistinguishable from the exact kernel -----------------
+
+def _both_modes(P, O, pts, q, k, lo=None, expect_filter=True):
+    t = P.KnnIndex(pts.shape[1])
+    t.add(pts)
+    gi, gd = t.nearest_k(q, k, lo=lo)
+    st = t.search_stats()
+    assert (st["filter_calls"] > 0) == expect_filter
+    t.set_search_mode(True)
+    ei, ed = t.nearest_k(q, k, lo=lo)
+    assert np.array_equal(gi, ei) and np.array_equal(gd, ed)
+    oi, od = O.knn(pts, q, k, lo=lo, nthreads=8)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    t.close()
+    return st
+
+
+@pytest.mark.parametrize("k", [1, 5, 16, 24])
+def test_filter_path_uniform(P, O, synth, k):
+    st = _both_modes(P, O, synth.cloud(0, 60000), synth.cloud(1, 700), k)
+    assert st["fallback_queries"] == 0          # well separated data: every query is proven
+
+
+def test_filter_path_not_taken_outside_its_shape(P, O, synth):
+    _both_modes(P, O, synth.cloud(0, 60000), synth.cloud(1, 700), 25, expect_filter=False)     # k + 8 > 32
+    _both_modes(P, O, synth.cloud(0, 60000), synth.cloud(1, 100), 4, expect_filter=False)      # < 128 queries
+    _both_modes(P, O, synth.cloud(0, 5000), synth.cloud(1, 300), 4, expect_filter=False)       # small tree
+    _both_modes(P, O, synth.cloud(0, 20000, dim=8), synth.cloud(1, 300, dim=8), 4, expect_filter=False)
+
+
+def test_filter_path_adversarial_ties(P, O, synth):
+    rng = np.random.default_rng(3)
+    # (a) every point identical: nothing can be proven, everything falls back
+    pts = np.tile(synth.cloud(5, 1), (20000, 1))
+    st = _both_modes(P, O, pts, synth.cloud(1, 256), 3)
+    assert st["fallback_queries"] == 256
+    # (b) heavy exact duplication (each point 12x) and queries sitting on points
+    base = synth.cloud(6, 2500)
+    pts = np.repeat(base, 12, axis=0)[rng.permutation(30000)]
+    q = np.vstack([base[:200], synth.cloud(7, 200)])
+    _both_modes(P, O, pts, q, 16)
+    # (c) clusters of near-duplicates separated by 1e-9 .. 1e-6 (below the fp32 resolution)
+    centres = synth.cloud(8, 1000)
+    pts = (centres[:, None, :] + rng.uniform(-1, 1, (1000, 20, 7)) * 10.0 ** rng.uniform(-9, -6, (1000, 20, 1))
+           ).reshape(-1, 7)
+    _both_modes(P, O, pts, np.vstack([centres[:300], synth.cloud(9, 100)]), 8)
+    # (d) far from the origin: the error bound grows with |x|^2, the proof gets harder, results stay exact
+    pts = synth.cloud(10, 40000) * 0.01 + 250.0
+    _both_modes(P, O, pts, synth.cloud(11, 300) * 0.01 + 250.0, 5)
+
+
+def test_filter_path_suffix_mask_and_dims(P, O, synth):
+    n, nq = 50000, 600
+    lo = np.sort(np.random.default_rng(9).integers(0, n + 50, nq)).astype(np.uint32)
+    _both_modes(P, O, synth.cloud(0, n), synth.cloud(1, nq), 5, lo=lo)
+    for dim in (2, 3, 6):
+        _both_modes(P, O, synth.cloud(0, 30000, dim=dim), synth.cloud(1, 300, dim=dim), 6)
