@@ -73,7 +73,7 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
                         uint32_t *idx, double *dist);
 int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64_t nq, int k,
                                const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, void *stream);
-/* Search strategy.  By default batched calls (>= 128 queries, k <= 24, dim <= 7, >= 8192 points) use an
+/* Search strategy.  By default batched calls (>= 128 queries, k <= 16, dim <= 7, >= 8192 points) use an
  * fp32 filter scan followed by an exact fp64 re-rank of k+8 candidates with a per-query proof that no
  * discarded point can precede them; unproven queries are re-run by the exact fp64 kernel, so the
  * results are bit-identical either way.  force_exact != 0 disables the filter. */

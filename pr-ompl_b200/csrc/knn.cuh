@@ -41,7 +41,7 @@ struct KnnTreeView {
 };
 
 constexpr int KNN_FILTER_MARGIN = 8;   // extra candidates kept by the fp32 filter pass
-constexpr int KNN_FILTER_MAX_K = 24;   // k + margin must fit one warp in the re-rank
+constexpr int KNN_FILTER_MAX_K = 16;   // k + margin + the 8-entry candidate buffer must fit one warp
 
 // exact search (always bit-identical to the reference); knn_search picks the filter path
 // (fp32 scan -> fp64 re-rank of k+8 candidates -> proof check -> exact fallback for unproven

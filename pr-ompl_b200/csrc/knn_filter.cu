@@ -4,17 +4,20 @@
 // reference's distance forbids FMA and runs on the half-rate FP64 pipe.  For the batched shapes
 // (>= 128 queries per tree pass, k <= 24) almost all of that work only establishes that a node is
 // NOT among the k nearest.  This path does that part in fp32:
-//   1. knn_filter_kernel: key(q,x) = |x|^2 - 2 q.x  (= |q-x|^2 - |q|^2) from an fp32 mirror of the tree,
-//      7 FFMA + 1 compare per pair, keeping the k+8 smallest keys per query (same tiling, bulk-copy
-//      double buffering and chunk merge as the exact kernel).
-//   2. knn_rerank_kernel: one warp per query recomputes the reference's exact fp64 distance of the
-//      k+8 candidates, sorts them under (distance, index) and emits the first k -- and PROVES that no
-//      discarded node can precede them: every discarded node has key >= keymax, the fp32 key is
-//      within eps = 16 * 2^-24 * (max|x| + |q|)^2 of the real value (9.1 u (|x|+|q|)^2 by a standard
-//      running-error bound of the 8-term FMA chain, rounded inputs included), so its exact squared
-//      distance is >= keymax - eps + |q|^2.  If the k-th exact squared distance is not strictly below
-//      that bound (ties, heavy duplicates), the query is flagged.
-//   3. flagged queries are re-run through the exact kernel.  Results are therefore bit-identical to
+//   key(q,x) = |x|^2 - 2 q.x  (= |q-x|^2 - |q|^2) from an fp32 mirror of the tree (8 floats per node).
+//   1. knn_filter_kernel on every 64th tile: T_q = (k+8)-th smallest key of the sample, an upper
+//      bound of the (k+8)-th smallest key of the whole tree.
+//   2. knn_collect_kernel: one pass over the tree, 7 FFMA + 1 compare per pair, each node tile
+//      broadcast from shared memory to 4 queries per thread; nodes with key <= T_q (~ (k+8)*64 per
+//      query) are appended to the query's candidate buffer.  No per-query state is updated in the loop.
+//   3. knn_select_kernel: one block per query recomputes the reference's exact fp64 distance of the
+//      candidates, selects the k first under (distance, index) -- and PROVES that no discarded node
+//      can precede them: a discarded node has key > T_q, the fp32 key is within
+//      eps = 16 * 2^-24 * (max|x| + |q|)^2 of the real value (9.1 u (|x|+|q|)^2 by the running-error
+//      bound of the 8-term FMA chain, rounded inputs included), so its exact squared distance is
+//      >= T_q - eps + |q|^2.  If the k-th exact squared distance is not strictly below that bound
+//      (ties at the cut, heavy duplication) or the buffer overflowed, the query is flagged.
+//   4. flagged queries are re-run through the exact kernel.  Results are therefore bit-identical to
 //      knn_search_exact for every input.
 #include <math_constants.h>
 #include <vector>
@@ -23,10 +26,10 @@
 namespace prgpu {
 namespace {
 
-constexpr int FT_TILE = 256;     // nodes per tile (32 bytes each)
+constexpr int FT_TILE = 128;     // nodes per tile (32 bytes each)
 constexpr int FT_THREADS = 128;  // queries per block
 
-constexpr int FT_RQ = 2;         // queries per thread (register tile: halves the shared-memory reads per pair)
+constexpr int FT_RQ = 4;         // queries per thread (register tile: halves the shared-memory reads per pair)
 constexpr int FT_BUF = 8;        // per-query register buffer of pending candidates
 
 // Keeps, per query, the kp smallest keys seen so far.  The hot loop only compares against a
@@ -34,26 +37,26 @@ constexpr int FT_BUF = 8;        // per-query register buffer of pending candida
 // lane's buffer is nearly full the WARP merges that lane's list (kp entries in shared memory) with
 // its buffer -- 32 items, one per lane, one bitonic sort -- and hands the tightened threshold back.
 // No divergent per-lane insertion loops remain.
-template <int DIM>
+template <int DIM, int RQ>
 __global__ void __launch_bounds__(FT_THREADS)
 knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
-                  int kp, const uint32_t *__restrict__ lo, uint32_t tiles_per_chunk, double *__restrict__ out_key,
-                  uint32_t *__restrict__ out_idx) {
+                  int kp, const uint32_t *__restrict__ lo, uint32_t tiles_per_chunk, uint32_t tile_stride,
+                  double *__restrict__ out_key, uint32_t *__restrict__ out_idx) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
   uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
   float *lkey = reinterpret_cast<float *>(bars + 2);                       // [RQ][THREADS][kp]
-  uint32_t *lidx = reinterpret_cast<uint32_t *>(lkey + (size_t)FT_RQ * kp * FT_THREADS);
+  uint32_t *lidx = reinterpret_cast<uint32_t *>(lkey + (size_t)RQ * kp * FT_THREADS);
   __shared__ uint32_t s_lo_min;
 
   const int tid = threadIdx.x, lane = tid & 31;
-  uint32_t qid[FT_RQ];
-  bool act[FT_RQ];
-  float q2[FT_RQ][7];
-  uint32_t my_lo[FT_RQ];
+  uint32_t qid[RQ];
+  bool act[RQ];
+  float q2[RQ][7];
+  uint32_t my_lo[RQ];
 #pragma unroll
-  for (int u = 0; u < FT_RQ; ++u) {
-    qid[u] = (blockIdx.x * FT_RQ + u) * FT_THREADS + tid;
+  for (int u = 0; u < RQ; ++u) {
+    qid[u] = (blockIdx.x * RQ + u) * FT_THREADS + tid;
     act[u] = qid[u] < nq;
 #pragma unroll
     for (int d = 0; d < 7; ++d)
@@ -66,35 +69,37 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
     mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
-  for (int e = 0; e < FT_RQ * kp; ++e) {
+  for (int e = 0; e < RQ * kp; ++e) {
     const int u = e / kp, j = e - u * kp;
     lkey[((size_t)u * FT_THREADS + tid) * kp + j] = CUDART_INF_F;
     lidx[((size_t)u * FT_THREADS + tid) * kp + j] = PRGPU_INVALID_INDEX;
   }
   __syncthreads();
 #pragma unroll
-  for (int u = 0; u < FT_RQ; ++u)
+  for (int u = 0; u < RQ; ++u)
     if (act[u])
       atomicMin(&s_lo_min, my_lo[u]);
   __syncthreads();
 
+  // this block visits the sampled tiles s*tile_stride, s in [t0, t1)
   const uint32_t ntiles = (n + FT_TILE - 1) / FT_TILE;
+  const uint32_t nsamp = (ntiles + tile_stride - 1) / tile_stride;
   uint32_t t0 = blockIdx.y * tiles_per_chunk;
-  const uint32_t t1 = min(t0 + tiles_per_chunk, ntiles);
+  const uint32_t t1 = min(t0 + tiles_per_chunk, nsamp);
   if (s_lo_min != 0xFFFFFFFFu)
-    t0 = max(t0, s_lo_min / FT_TILE);
+    t0 = max(t0, s_lo_min / FT_TILE / tile_stride);
 
   auto issue = [&](uint32_t t, int buf) {
     mbar_expect_tx(&bars[buf], FT_TILE * 32);
-    bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
+    bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * tile_stride * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
   };
 
-  float thr[FT_RQ];            // upper bound of the kp-th smallest key of each query
-  float bk[FT_RQ][FT_BUF];     // pending candidates
-  uint32_t bi[FT_RQ][FT_BUF];
-  int bc[FT_RQ];
+  float thr[RQ];            // upper bound of the kp-th smallest key of each query
+  float bk[RQ][FT_BUF];     // pending candidates
+  uint32_t bi[RQ][FT_BUF];
+  int bc[RQ];
 #pragma unroll
-  for (int u = 0; u < FT_RQ; ++u) {
+  for (int u = 0; u < RQ; ++u) {
     thr[u] = act[u] ? CUDART_INF_F : -CUDART_INF_F; // inactive: nothing ever qualifies
     bc[u] = 0;
 #pragma unroll
@@ -168,7 +173,7 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
       const int L = __ffs(mask) - 1;
       mask &= mask - 1;
 #pragma unroll
-      for (int u = 0; u < FT_RQ; ++u)
+      for (int u = 0; u < RQ; ++u)
         compact(u, L);
     }
     __syncwarp();
@@ -195,7 +200,7 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
     mbar_wait(&bars[buf], parity);
     {
       const float4 *T = tile + buf * FT_TILE * 2;
-      const uint32_t base = t * FT_TILE;
+      const uint32_t base = t * tile_stride * FT_TILE;
       const uint32_t jmax = min((uint32_t)FT_TILE, n - base);
       uint32_t j = 0;
       for (; j + 3 < jmax; j += 4) {
@@ -203,7 +208,7 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
         const float4 a2 = T[2 * j + 4], b2 = T[2 * j + 5], a3 = T[2 * j + 6], b3 = T[2 * j + 7];
         bool any = false;
 #pragma unroll
-        for (int u = 0; u < FT_RQ; ++u) {
+        for (int u = 0; u < RQ; ++u) {
           const float k0 = key_of(u, a0, b0), k1 = key_of(u, a1, b1), k2 = key_of(u, a2, b2), k3 = key_of(u, a3, b3);
           if (fminf(fminf(k0, k1), fminf(k2, k3)) < thr[u]) {
             offer(u, k0, base + j);
@@ -216,7 +221,7 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
         if (__any_sync(0xffffffffu, any)) {
           bool need = false;
 #pragma unroll
-          for (int u = 0; u < FT_RQ; ++u)
+          for (int u = 0; u < RQ; ++u)
             need = need || bc[u] > FT_BUF - 4; // the next group may add up to 4
           compact_if(need);
         }
@@ -224,11 +229,11 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
       for (; j < jmax; ++j) {
         const float4 a0 = T[2 * j], b0 = T[2 * j + 1];
 #pragma unroll
-        for (int u = 0; u < FT_RQ; ++u)
+        for (int u = 0; u < RQ; ++u)
           offer(u, key_of(u, a0, b0), base + j);
         bool need = false;
 #pragma unroll
-        for (int u = 0; u < FT_RQ; ++u)
+        for (int u = 0; u < RQ; ++u)
           need = need || bc[u] > FT_BUF - 4;
         compact_if(need);
       }
@@ -238,12 +243,12 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
   {
     bool need = false;
 #pragma unroll
-    for (int u = 0; u < FT_RQ; ++u)
+    for (int u = 0; u < RQ; ++u)
       need = need || bc[u] > 0;
     compact_if(need);
   }
 #pragma unroll
-  for (int u = 0; u < FT_RQ; ++u)
+  for (int u = 0; u < RQ; ++u)
     if (act[u]) {
       const float *K = lkey + ((size_t)u * FT_THREADS + tid) * kp;
       const uint32_t *I = lidx + ((size_t)u * FT_THREADS + tid) * kp;
@@ -257,18 +262,145 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
     }
 }
 
-// One warp per query: exact fp64 distances of the kp (<= 32) candidates, bitonic sort under
-// (distance, index), emit k, prove or flag.
+// Pass 2: full scan.  A node is a candidate of query q iff key(q, node) <= T_q (the threshold from
+// the sample pass) and node >= lo_q; candidates are appended to the query's global buffer.  The hot
+// loop is 7 FFMA + a compare per pair with the node tile broadcast from shared memory to RQ
+// queries per thread; nothing else is maintained.
 template <int DIM>
-__global__ void __launch_bounds__(128)
-knn_rerank_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t index_base, const double *__restrict__ xmax2,
-                  const double *__restrict__ queries, uint32_t nq, int k, int kp, const double *__restrict__ cand_key,
-                  const uint32_t *__restrict__ cand_idx, uint32_t *__restrict__ idx_out, double *__restrict__ dist_out,
-                  uint32_t *__restrict__ flags) {
-  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(FT_THREADS)
+knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
+                   const uint32_t *__restrict__ lo, const float *__restrict__ thresh, uint32_t tiles_per_chunk,
+                   uint32_t cap, uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
+  __shared__ uint32_t s_lo_min;
+  const int tid = threadIdx.x;
+  uint32_t qid[FT_RQ], my_lo[FT_RQ];
+  float q2[FT_RQ][7], thr[FT_RQ];
+#pragma unroll
+  for (int u = 0; u < FT_RQ; ++u) {
+    qid[u] = (blockIdx.x * FT_RQ + u) * FT_THREADS + tid;
+    const bool act = qid[u] < nq;
+#pragma unroll
+    for (int d = 0; d < 7; ++d)
+      q2[u][d] = (act && d < DIM) ? (float)(-2.0 * queries[(size_t)qid[u] * DIM + d]) : 0.f;
+    my_lo[u] = (act && lo) ? lo[qid[u]] : (act ? 0u : 0xFFFFFFFFu);
+    thr[u] = act ? thresh[qid[u]] : -CUDART_INF_F;
+  }
+  if (tid == 0) {
+    s_lo_min = 0xFFFFFFFFu;
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < FT_RQ; ++u)
+    atomicMin(&s_lo_min, my_lo[u]);
+  __syncthreads();
+  const uint32_t ntiles = (n + FT_TILE - 1) / FT_TILE;
+  uint32_t t0 = blockIdx.y * tiles_per_chunk;
+  const uint32_t t1 = min(t0 + tiles_per_chunk, ntiles);
+  if (s_lo_min != 0xFFFFFFFFu)
+    t0 = max(t0, s_lo_min / FT_TILE);
+  auto issue = [&](uint32_t t, int buf) {
+    mbar_expect_tx(&bars[buf], FT_TILE * 32);
+    bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
+  };
+  auto key_of = [&](int u, const float4 &a, const float4 &b) {
+    float acc = b.w; // |x|^2
+    acc = fmaf(q2[u][0], a.x, acc);
+    if (DIM > 1) acc = fmaf(q2[u][1], a.y, acc);
+    if (DIM > 2) acc = fmaf(q2[u][2], a.z, acc);
+    if (DIM > 3) acc = fmaf(q2[u][3], a.w, acc);
+    if (DIM > 4) acc = fmaf(q2[u][4], b.x, acc);
+    if (DIM > 5) acc = fmaf(q2[u][5], b.y, acc);
+    if (DIM > 6) acc = fmaf(q2[u][6], b.z, acc);
+    return acc;
+  };
+  auto emit = [&](int u, float key, uint32_t gi) {
+    if (key <= thr[u] && gi >= my_lo[u]) {
+      const uint32_t slot = atomicAdd(cand_count + qid[u], 1u);
+      if (slot < cap)
+        cand_idx[(size_t)qid[u] * cap + slot] = gi;
+    }
+  };
+  if (tid == 0 && t0 < t1)
+    issue(t0, 0);
+  for (uint32_t t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    const uint32_t parity = ((t - t0) >> 1) & 1;
+    if (tid == 0 && t + 1 < t1)
+      issue(t + 1, buf ^ 1);
+    mbar_wait(&bars[buf], parity);
+    const float4 *T = tile + buf * FT_TILE * 2;
+    const uint32_t base = t * FT_TILE;
+    const uint32_t jmax = min((uint32_t)FT_TILE, n - base);
+    uint32_t j = 0;
+    for (; j + 3 < jmax; j += 4) {
+      const float4 a0 = T[2 * j], b0 = T[2 * j + 1], a1 = T[2 * j + 2], b1 = T[2 * j + 3];
+      const float4 a2 = T[2 * j + 4], b2 = T[2 * j + 5], a3 = T[2 * j + 6], b3 = T[2 * j + 7];
+#pragma unroll
+      for (int u = 0; u < FT_RQ; ++u) {
+        const float k0 = key_of(u, a0, b0), k1 = key_of(u, a1, b1), k2 = key_of(u, a2, b2), k3 = key_of(u, a3, b3);
+        if (fminf(fminf(k0, k1), fminf(k2, k3)) <= thr[u]) {
+          emit(u, k0, base + j);
+          emit(u, k1, base + j + 1);
+          emit(u, k2, base + j + 2);
+          emit(u, k3, base + j + 3);
+        }
+      }
+    }
+    for (; j < jmax; ++j) {
+      const float4 a0 = T[2 * j], b0 = T[2 * j + 1];
+#pragma unroll
+      for (int u = 0; u < FT_RQ; ++u)
+        emit(u, key_of(u, a0, b0), base + j);
+    }
+    __syncthreads();
+  }
+}
+
+// threshold of every query = kp-th smallest key of the sample (last entry of its merged list)
+__global__ void knn_threshold_kernel(const double *__restrict__ cand_key, const uint32_t *__restrict__ cand_idx,
+                                     uint32_t nq, int kp, float *__restrict__ thresh, uint32_t *__restrict__ counts) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq)
     return;
-  const int lane = threadIdx.x & 31;
+  const bool full = cand_idx[(size_t)q * kp + kp - 1] != PRGPU_INVALID_INDEX;
+  thresh[q] = full ? (float)cand_key[(size_t)q * kp + kp - 1] : CUDART_INF_F; // fewer than kp sampled: keep all
+  counts[q] = 0;
+}
+
+// Pass 3: one block per query.  Exact fp64 distance (the reference's operation order) of every
+// candidate, k rounds of block-wide arg-min under (distance, index), then the proof: every discarded
+// node has key > T_q, its fp32 key is within eps of the real |x|^2 - 2 q.x, hence its exact squared
+// distance is >= T_q - eps + |q|^2; the query is final iff the k-th selected squared distance lies
+// strictly below that.  Unproven queries (and overflowed buffers) are flagged for the exact kernel.
+constexpr int SEL_THREADS = 128;
+template <int DIM>
+__global__ void __launch_bounds__(SEL_THREADS)
+knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t index_base, const double *__restrict__ xmax2,
+                  const double *__restrict__ queries, const float *__restrict__ thresh, uint32_t cap,
+                  const uint32_t *__restrict__ cand_count, const uint32_t *__restrict__ cand_idx, int k,
+                  uint32_t *__restrict__ idx_out, double *__restrict__ dist_out, uint32_t *__restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char sel_raw[];
+  double *sd = reinterpret_cast<double *>(sel_raw);             // [cap]
+  uint32_t *si = reinterpret_cast<uint32_t *>(sd + cap);        // [cap]
+  __shared__ double red_d[SEL_THREADS / 32];
+  __shared__ uint32_t red_i[SEL_THREADS / 32], red_p[SEL_THREADS / 32];
+  __shared__ uint32_t win_p;
+  const uint32_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t cnt = cand_count[q];
+  if (cnt > cap) { // buffer overflow: cannot be decided here
+    if (tid == 0) {
+      const uint32_t slot = atomicAdd(flags, 1u);
+      flags[1 + slot] = q;
+    }
+    return;
+  }
   double qx[DIM];
   double qn2 = 0.0;
 #pragma unroll
@@ -276,52 +408,75 @@ knn_rerank_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t inde
     qx[d] = queries[(size_t)q * DIM + d];
     qn2 += qx[d] * qx[d];
   }
-  uint32_t idx = PRGPU_INVALID_INDEX;
-  double key = CUDART_INF, dist = CUDART_INF;
-  if (lane < kp) {
-    idx = cand_idx[(size_t)q * kp + lane];
-    key = cand_key[(size_t)q * kp + lane];
-  }
-  if (idx != PRGPU_INVALID_INDEX) {
+  for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
+    const uint32_t i = cand_idx[(size_t)q * cap + c];
     double x[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
-      x[d] = pts[(size_t)d * stride + idx];
-    dist = __dsqrt_rn(sqdist_exact<DIM>(x, qx)); // RealVectorStateSpace::distance(node, query)
+      x[d] = pts[(size_t)d * stride + i];
+    sd[c] = __dsqrt_rn(sqdist_exact<DIM>(x, qx)); // RealVectorStateSpace::distance(node, query)
+    si[c] = i;
   }
-  // the filter list is full iff its last entry is a real node; its key bounds every discarded node
-  const uint32_t last_idx = __shfl_sync(0xffffffffu, idx, kp - 1);
-  const double keymax = __shfl_sync(0xffffffffu, key, kp - 1);
-  // bitonic sort of 32 (dist, idx) pairs, ascending
-#pragma unroll
-  for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-    for (int strd = size >> 1; strd > 0; strd >>= 1) {
-      const double od = __shfl_xor_sync(0xffffffffu, dist, strd);
-      const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, strd);
-      const bool up = ((lane & size) == 0);     // ascending block
-      const bool lower = ((lane & strd) == 0);  // this lane keeps the smaller of the pair when ascending
-      const bool other_less = od < dist || (od == dist && oi < idx);
-      const bool take = (up == lower) ? other_less : !other_less && !(od == dist && oi == idx);
-      if (take) {
-        dist = od;
-        idx = oi;
+  __syncthreads();
+  double dk = CUDART_INF;
+  for (int r = 0; r < k; ++r) {
+    double bd = CUDART_INF;
+    uint32_t bi = PRGPU_INVALID_INDEX, bp = 0xFFFFFFFFu;
+    for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
+      const double d = sd[c];
+      const uint32_t i = si[c];
+      if (d < bd || (d == bd && i < bi)) {
+        bd = d;
+        bi = i;
+        bp = c;
       }
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
+      if (od < bd || (od == bd && oi < bi)) {
+        bd = od;
+        bi = oi;
+        bp = op;
+      }
+    }
+    if (lane == 0) {
+      red_d[warp] = bd;
+      red_i[warp] = bi;
+      red_p[warp] = bp;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < SEL_THREADS / 32; ++w)
+        if (red_d[w] < bd || (red_d[w] == bd && red_i[w] < bi)) {
+          bd = red_d[w];
+          bi = red_i[w];
+          bp = red_p[w];
+        }
+      dist_out[(size_t)q * k + r] = bd;
+      idx_out[(size_t)q * k + r] = bi == PRGPU_INVALID_INDEX ? bi : bi + index_base;
+      win_p = bp;
+      if (bp != 0xFFFFFFFFu) { // remove the winner
+        sd[bp] = CUDART_INF;
+        si[bp] = PRGPU_INVALID_INDEX;
+      }
+      dk = bd;
+    }
+    __syncthreads();
   }
-  if (lane < k) {
-    dist_out[(size_t)q * k + lane] = dist;
-    idx_out[(size_t)q * k + lane] = idx == PRGPU_INVALID_INDEX ? idx : idx + index_base;
-  }
-  const double dk = __shfl_sync(0xffffffffu, dist, k - 1);
-  if (lane == 0 && last_idx != PRGPU_INVALID_INDEX) { // nodes were discarded: prove they cannot matter
-    const double xn = sqrt(*xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
-    const double eps = 16.0 * 5.9604644775390625e-08 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
-    const double bound = keymax - eps + qn2; // lower bound of the exact squared distance of any discarded node
-    const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (qn2 + 1.0);
-    if (!(sk < bound)) {
-      const uint32_t slot = atomicAdd(flags, 1u);
-      flags[1 + slot] = q;
+  if (tid == 0) {
+    const float T = thresh[q];
+    if (T < CUDART_INF_F) { // nodes were discarded: prove they cannot matter
+      const double xn = sqrt(*xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
+      const double eps = 16.0 * 5.9604644775390625e-08 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
+      const double bound = (double)T - eps + qn2; // lower bound of the exact squared distance of any discarded node
+      const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (qn2 + 1.0);
+      if (!(sk < bound)) {
+        const uint32_t slot = atomicAdd(flags, 1u);
+        flags[1 + slot] = q;
+      }
     }
   }
 }
@@ -349,62 +504,98 @@ __global__ void scatter_rows_kernel(const uint32_t *__restrict__ ids, uint32_t n
   dist_out[(size_t)q * k + e] = sd[i];
 }
 
+constexpr uint32_t FT_SAMPLE_STRIDE = 64; // the sample pass visits every 64th tile
+
 template <int DIM>
 int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k, const uint32_t *lo,
                 uint32_t *idx_out, double *dist_out, KnnScratch &sc, int sm_count, cudaStream_t stream,
                 KernelTimer *timer) {
   const int kp = k + KNN_FILTER_MARGIN;
-  const size_t smem = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t) + (size_t)FT_RQ * kp * FT_THREADS * 8;
-  auto kern = knn_filter_kernel<DIM>;
-  PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FT_THREADS, smem));
-  per_sm = per_sm > 0 ? per_sm : 1;
-  const uint32_t qblocks = (nq + FT_RQ * FT_THREADS - 1) / (FT_RQ * FT_THREADS);
   const uint32_t ntiles = (t.n + FT_TILE - 1) / FT_TILE;
-  uint32_t chunks = (uint32_t)(per_sm * sm_count) / qblocks;
-  chunks = chunks < 1 ? 1 : chunks;
-  if (chunks > 4096)
-    chunks = 4096;
-  if (chunks > ntiles)
-    chunks = ntiles;
-  const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
-  chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+  const uint32_t qblocks = (nq + FT_RQ * FT_THREADS - 1) / (FT_RQ * FT_THREADS);
+  // candidate buffer per query: the sample's kp-th smallest key admits ~kp*stride nodes of the full tree
+  uint32_t cap = 1;
+  while (cap < 3u * (uint32_t)kp * FT_SAMPLE_STRIDE)
+    cap <<= 1;
+  if (cap > 4096)
+    cap = 4096;
 
+  // ---- pass 1: thresholds from a 1/32 sample (list-maintaining kernel on few tiles) ----
+  // (one query per thread and few node chunks: every (query, chunk) list pays a warm-up transient)
+  const size_t smem1 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t) + (size_t)kp * FT_THREADS * 8;
+  auto samp = knn_filter_kernel<DIM, 1>;
+  PRGPU_CUDA_TRY(cudaFuncSetAttribute(samp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  const uint32_t nsamp = (ntiles + FT_SAMPLE_STRIDE - 1) / FT_SAMPLE_STRIDE;
+  const uint32_t qblocks1 = (nq + FT_THREADS - 1) / FT_THREADS;
+  uint32_t chunks1 = (uint32_t)(2 * sm_count) / qblocks1;
+  chunks1 = chunks1 < 1 ? 1 : chunks1;
+  if (chunks1 > nsamp)
+    chunks1 = nsamp;
+  const uint32_t tpc1 = (nsamp + chunks1 - 1) / chunks1;
+  chunks1 = (nsamp + tpc1 - 1) / tpc1;
   int rc = scratch_reserve(sc.cand_dist, sc.cand_idx, sc.cand_capacity, (size_t)nq * kp);
   if (rc != PRGPU_OK)
     return rc;
-  if (sc.flags_capacity < (size_t)nq + 1) {
-    if (sc.flags)
-      cudaFree(sc.flags);
-    sc.flags = nullptr;
-    sc.flags_capacity = 0;
-    PRGPU_CUDA_TRY(cudaMalloc(&sc.flags, ((size_t)nq + 1) * sizeof(uint32_t)));
-    sc.flags_capacity = (size_t)nq + 1;
-  }
-  PRGPU_CUDA_TRY(cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t), stream));
   double *pk = sc.cand_dist;
   uint32_t *pi = sc.cand_idx;
-  if (chunks > 1) {
-    rc = scratch_reserve(sc.part_dist, sc.part_idx, sc.part_capacity, (size_t)chunks * nq * kp);
+  if (chunks1 > 1) {
+    rc = scratch_reserve(sc.part_dist, sc.part_idx, sc.part_capacity, (size_t)chunks1 * nq * kp);
     if (rc != PRGPU_OK)
       return rc;
     pk = sc.part_dist;
     pi = sc.part_idx;
   }
-  if (timer)
-    timer->begin(stream);
-  kern<<<dim3(qblocks, chunks), FT_THREADS, smem, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, tiles_per_chunk, pk, pi);
-  if (timer)
-    timer->end(stream);
+  // flags | thresholds | counts | candidate indices
+  const size_t need_words = ((size_t)nq + 1) + (size_t)nq + (size_t)nq + (size_t)nq * cap;
+  if (sc.flags_capacity < need_words) {
+    if (sc.flags)
+      cudaFree(sc.flags);
+    sc.flags = nullptr;
+    sc.flags_capacity = 0;
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.flags, need_words * sizeof(uint32_t)));
+    sc.flags_capacity = need_words;
+  }
+  float *thresh = reinterpret_cast<float *>(sc.flags + (size_t)nq + 1);
+  uint32_t *counts = sc.flags + 2 * (size_t)nq + 1;
+  uint32_t *cidx = sc.flags + 3 * (size_t)nq + 1;
+  PRGPU_CUDA_TRY(cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t), stream));
+  samp<<<dim3(qblocks1, chunks1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, tpc1, FT_SAMPLE_STRIDE,
+                                                            pk, pi);
   PRGPU_CUDA_TRY(cudaGetLastError());
-  if (chunks > 1) {
-    rc = merge_passes(sc, (int)chunks, nq, kp, sc.cand_idx, sc.cand_dist, stream);
+  if (chunks1 > 1) {
+    rc = merge_passes(sc, (int)chunks1, nq, kp, sc.cand_idx, sc.cand_dist, stream);
     if (rc != PRGPU_OK)
       return rc;
   }
-  knn_rerank_kernel<DIM><<<(nq + 3) / 4, 128, 0, stream>>>(t.pts, t.stride, t.index_base, t.xmax2, queries, nq, k, kp,
-                                                         sc.cand_dist, sc.cand_idx, idx_out, dist_out, sc.flags);
+  knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, thresh, counts);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+
+  // ---- pass 2: full scan collecting every node at or below the threshold ----
+  const size_t smem2 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t);
+  auto coll = knn_collect_kernel<DIM>;
+  int per_sm = 0;
+  PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coll, FT_THREADS, smem2));
+  per_sm = per_sm > 0 ? per_sm : 1;
+  uint32_t chunks = (uint32_t)(per_sm * sm_count) / qblocks;
+  chunks = chunks < 1 ? 1 : chunks;
+  if (chunks > ntiles)
+    chunks = ntiles;
+  const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
+  chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+  if (timer)
+    timer->begin(stream);
+  coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf, t.n, queries, nq, lo, thresh, tiles_per_chunk, cap,
+                                                           counts, cidx);
+  if (timer)
+    timer->end(stream);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+
+  // ---- pass 3: exact re-rank of the candidates + proof ----
+  const size_t smem3 = (size_t)cap * 12;
+  auto sel = knn_select_kernel<DIM>;
+  PRGPU_CUDA_TRY(cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+  sel<<<nq, SEL_THREADS, smem3, stream>>>(t.pts, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts, cidx, k,
+                                         idx_out, dist_out, sc.flags);
   PRGPU_CUDA_TRY(cudaGetLastError());
   ++sc.filter_calls;
 
@@ -448,7 +639,7 @@ int knn_search(int dim, const KnnTreeView &t, const double *queries_dev, uint32_
                uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
                KernelTimer *timer, int force_exact) {
   const bool eligible = !force_exact && t.ptsf != nullptr && dim <= 7 && k >= 1 &&
-                        k + KNN_FILTER_MARGIN <= 32 && nq >= (uint32_t)FT_THREADS && t.n >= 8192;
+                        k <= KNN_FILTER_MAX_K && nq >= (uint32_t)FT_THREADS && t.n >= 8192;
   if (!eligible)
     return knn_search_exact(dim, t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, timer);
   switch (dim) {

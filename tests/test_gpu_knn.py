@@ -131,14 +131,14 @@ def _both_modes(P, O, pts, q, k, lo=None, expect_filter=True):
     return st
 
 
-@pytest.mark.parametrize("k", [1, 5, 16, 24])
+@pytest.mark.parametrize("k", [1, 5, 11, 16])
 def test_filter_path_uniform(P, O, synth, k):
     st = _both_modes(P, O, synth.cloud(0, 60000), synth.cloud(1, 700), k)
     assert st["fallback_queries"] == 0          # well separated data: every query is proven
 
 
 def test_filter_path_not_taken_outside_its_shape(P, O, synth):
-    _both_modes(P, O, synth.cloud(0, 60000), synth.cloud(1, 700), 25, expect_filter=False)     # k + 8 > 32
+    _both_modes(P, O, synth.cloud(0, 60000), synth.cloud(1, 700), 17, expect_filter=False)     # k > 16
     _both_modes(P, O, synth.cloud(0, 60000), synth.cloud(1, 100), 4, expect_filter=False)      # < 128 queries
     _both_modes(P, O, synth.cloud(0, 5000), synth.cloud(1, 300), 4, expect_filter=False)       # small tree
     _both_modes(P, O, synth.cloud(0, 20000, dim=8), synth.cloud(1, 300, dim=8), 4, expect_filter=False)
