@@ -387,9 +387,14 @@ int prgpu_world_create(int device, int dof, const double *dh, int ns, const int3
   for (int o = 0; o < nob; ++o)
     for (int c = 0; c < 3; ++c)
       maxabs = std::max(maxabs, std::fabs(obs_boxes[6 * o + c]) + std::fabs(obs_boxes[6 * o + 3 + c]));
-  // fp32 filter margin: rounding of both centres to fp32 plus the fp32 arithmetic, with 16x headroom
+  // fp32 filter margin.  (a) rounding of obstacle and sphere centres to fp32 plus the fp32 distance
+  // arithmetic: <= 4 u scale, taken with 16x headroom; (b) the fp32 forward-kinematics chain of the
+  // fast path: per joint ~4 u relative error on every frame entry and an angle error of ~4 u pi from
+  // sincosf and the rounded joint value, i.e. <= 8 u (dof+1) (reach + |local|) on a centre, taken with
+  // 8x headroom.  u = 2^-24.
+  const double u32 = 5.9604644775390625e-08;
   const double scale = std::max(1.0, maxabs + reach + maxlocal);
-  const double delta = 16.0 * 5.9604644775390625e-08 * scale * 4.0;
+  const double delta = 16.0 * u32 * scale * 4.0 + 64.0 * u32 * (dof + 1) * (reach + maxlocal);
   H.delta = (float)delta;
   for (int s = 0; s < WORLD_MAX_S; ++s) {
     if (s < ns) {
@@ -467,6 +472,9 @@ int prgpu_world_destroy(prgpu_world_t *w) {
   w->d_b.release();
   w->d_valid.release();
   w->d_pose.release();
+  for (void *p : {(void *)w->cm_scratch.owed, (void *)w->cm_scratch.off, w->cm_scratch.tmp})
+    if (p)
+      cudaFree(p);
   w->timer.destroy();
   if (w->dev)
     cudaFree(w->dev);
@@ -497,7 +505,7 @@ int prgpu_check_motion_batch_device(prgpu_world_t *w, const double *from_dev, co
     return fail(PRGPU_EINVAL, "check_motion_batch: NULL argument");
   PRGPU_CUDA_TRY(cudaSetDevice(w->device));
   return check_motion_launch(w->host, w->dev, from_dev, to_dev, n, resolution, mode, check_first, valid_dev,
-                             w->sm_count, (cudaStream_t)stream, &w->timer);
+                             w->sm_count, (cudaStream_t)stream, &w->timer, &w->cm_scratch);
 }
 
 int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double *to, uint64_t n,
@@ -515,7 +523,7 @@ int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double 
   PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, from, bytes, cudaMemcpyHostToDevice, w->stream));
   PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_b.p, to, bytes, cudaMemcpyHostToDevice, w->stream));
   rc = check_motion_launch(w->host, w->dev, w->d_a.as<double>(), w->d_b.as<double>(), n, resolution, mode,
-                           check_first, w->d_valid.as<uint8_t>(), w->sm_count, w->stream, &w->timer);
+                           check_first, w->d_valid.as<uint8_t>(), w->sm_count, w->stream, &w->timer, &w->cm_scratch);
   if (rc != PRGPU_OK)
     return rc;
   PRGPU_CUDA_TRY(cudaMemcpyAsync(valid, w->d_valid.p, n, cudaMemcpyDeviceToHost, w->stream));

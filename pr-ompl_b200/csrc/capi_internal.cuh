@@ -60,6 +60,7 @@ struct prgpu_world {
   prgpu::DeviceWorld *dev = nullptr;
   prgpu::DevBuf os_f, ob_f, os_d, ob_d;
   prgpu::DevBuf d_a, d_b, d_valid, d_pose;
+  prgpu::CmScratch cm_scratch;
   prgpu::KernelTimer timer;
 };
 

@@ -11,6 +11,8 @@
 // first round containing an invalid state (the result is the AND over the set, so evaluation
 // order is free).  Obstacles sit in shared memory as fp32 tables; see world.cuh for the
 // filter / exact split.
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
 #include "check_motion.cuh"
 
 namespace prgpu {
@@ -97,7 +99,7 @@ check_motion_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict
           for (int i = 0; i < WORLD_MAX_DOF; ++i)
             q[i] = lerp_exact(a[i], b[i], alpha);
         }
-        good = state_valid<SP>(w, s_os, s_ob, q);
+        good = state_valid_fast<SP>(w, s_os, s_ob, q);
       }
       if (__any_sync(0xffffffffu, !good)) {
         ok = false;
@@ -106,6 +108,167 @@ check_motion_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict
     }
     if (lane == 0)
       valid[e] = ok ? 1 : 0;
+  }
+}
+
+// ---- large batches: two flattened phases, one thread per tested state --------------------------
+// The warp-per-edge kernel above leaves lanes idle (an edge's state count is rarely a multiple of 32)
+// and can only stop an edge between rounds.  For large batches the tested sets are flattened instead:
+//   phase A: up to 8 states per edge, spread evenly over its tested set (stride m = ceil(np/8)), 8
+//            lanes per edge; an edge with an invalid sample is finished, and so is one with np <= 8;
+//   scan   : exclusive prefix sum of the states still owed by undecided edges;
+//   phase B: one thread per owed state, found by binary search in the prefix sums; a thread first
+//            looks at the edge's verdict and skips the state if the edge is already invalid.
+// Every lane of both phases carries a state, and the result is the same AND over the same set.
+
+struct EdgePlan {
+  uint32_t np, nd, extra, stride; // tested-set size, segment count, 1 if `from` is tested, sample stride
+  double step;                    // NNF mode: 1/numQ
+};
+
+__device__ __forceinline__ EdgePlan plan_edge(const double *a, const double *b, double resolution, int mode,
+                                              int check_first) {
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < WORLD_MAX_DOF; ++i) {
+    const double diff = __dsub_rn(a[i], b[i]);
+    sum = __dadd_rn(sum, __dmul_rn(diff, diff));
+  }
+  const double len = __dsqrt_rn(sum); // RealVectorStateSpace::distance, bit exact
+  EdgePlan p;
+  p.nd = 0;
+  p.extra = 0;
+  p.step = 0.0;
+  if (mode == PRGPU_MODE_OMPL_DISCRETE) {
+    p.nd = (uint32_t)ceil(len / resolution);
+    p.extra = check_first ? 1u : 0u;
+    p.np = 1u + (p.nd >= 2 ? p.nd - 1 : 0u) + p.extra;
+  } else {
+    const int numQ = (int)ceil(len / resolution);
+    p.step = 1.0 / (double)numQ;
+    p.np = 0;
+    for (double alpha = 0.0; alpha <= 1.0; alpha = __dadd_rn(alpha, p.step))
+      ++p.np;
+  }
+  p.stride = (p.np + 7) / 8;
+  if (p.stride < 1)
+    p.stride = 1;
+  return p;
+}
+
+__device__ __forceinline__ void edge_state(const EdgePlan &pl, const double *a, const double *b, int mode, uint32_t p,
+                                           double *q) {
+  if (mode == PRGPU_MODE_OMPL_DISCRETE) {
+    if (p == 0) {
+#pragma unroll
+      for (int i = 0; i < WORLD_MAX_DOF; ++i)
+        q[i] = b[i];
+    } else if (p <= pl.extra) {
+#pragma unroll
+      for (int i = 0; i < WORLD_MAX_DOF; ++i)
+        q[i] = a[i];
+    } else {
+      const double t = (double)(p - pl.extra) / (double)pl.nd;
+#pragma unroll
+      for (int i = 0; i < WORLD_MAX_DOF; ++i)
+        q[i] = lerp_exact(a[i], b[i], t);
+    }
+  } else {
+    double alpha = 0.0;
+    for (uint32_t i = 0; i < p; ++i)
+      alpha = __dadd_rn(alpha, pl.step);
+#pragma unroll
+    for (int i = 0; i < WORLD_MAX_DOF; ++i)
+      q[i] = lerp_exact(a[i], b[i], alpha);
+  }
+}
+
+template <int SP>
+__global__ void __launch_bounds__(CM_THREADS)
+cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
+                  uint32_t n, double resolution, int mode, int check_first, uint8_t *__restrict__ valid,
+                  uint32_t *__restrict__ owed) {
+  const DeviceWorld &w = *wp;
+  extern __shared__ float4 s_obs[];
+  float4 *s_os = s_obs;
+  float4 *s_ob = s_obs + w.n_os;
+  load_obstacles(w, s_os, s_ob);
+  __syncthreads();
+  const int dof = w.dof;
+  const uint32_t groups_total = gridDim.x * (CM_THREADS / 8);
+  for (uint32_t e0 = blockIdx.x * (CM_THREADS / 8); e0 < n; e0 += groups_total) {
+    const uint32_t e = e0 + (threadIdx.x >> 3);
+    const uint32_t slot = threadIdx.x & 7;
+    bool good = true;
+    EdgePlan pl;
+    pl.np = 0;
+    pl.stride = 1;
+    if (e < n) {
+      double a[WORLD_MAX_DOF], b[WORLD_MAX_DOF];
+#pragma unroll
+      for (int i = 0; i < WORLD_MAX_DOF; ++i) {
+        a[i] = i < dof ? from[(size_t)e * dof + i] : 0.0;
+        b[i] = i < dof ? to[(size_t)e * dof + i] : 0.0;
+      }
+      pl = plan_edge(a, b, resolution, mode, check_first);
+      const uint32_t p = slot * pl.stride;
+      if (p < pl.np) {
+        double q[WORLD_MAX_DOF];
+        edge_state(pl, a, b, mode, p, q);
+        good = state_valid_fast<SP>(w, s_os, s_ob, q);
+      }
+    }
+    const unsigned bad = __ballot_sync(0xffffffffu, !good);
+    if (e < n && slot == 0) {
+      const bool ok = ((bad >> ((threadIdx.x & 31) & ~7)) & 0xFFu) == 0;
+      const uint32_t sampled = (pl.np + pl.stride - 1) / pl.stride;
+      valid[e] = ok ? 1 : 0;
+      owed[e] = ok ? pl.np - sampled : 0u;
+    }
+  }
+}
+
+template <int SP>
+__global__ void __launch_bounds__(CM_THREADS)
+cm_phase_b_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
+                  uint32_t n, double resolution, int mode, int check_first, volatile uint8_t *valid,
+                  const uint32_t *__restrict__ owed, const uint32_t *__restrict__ off) {
+  const DeviceWorld &w = *wp;
+  extern __shared__ float4 s_obs[];
+  float4 *s_os = s_obs;
+  float4 *s_ob = s_obs + w.n_os;
+  load_obstacles(w, s_os, s_ob);
+  __syncthreads();
+  const int dof = w.dof;
+  const uint32_t total = off[n - 1] + owed[n - 1];
+  const uint32_t gsize = gridDim.x * CM_THREADS;
+  for (uint32_t g = blockIdx.x * CM_THREADS + threadIdx.x; g < total; g += gsize) {
+    // edge of work item g: last e with off[e] <= g
+    uint32_t lo_e = 0, hi_e = n - 1;
+    while (lo_e < hi_e) {
+      const uint32_t mid = (lo_e + hi_e + 1) >> 1;
+      if (off[mid] <= g)
+        lo_e = mid;
+      else
+        hi_e = mid - 1;
+    }
+    const uint32_t e = lo_e;
+    if (valid[e] == 0)
+      continue; // another state of this edge already failed
+    double a[WORLD_MAX_DOF], b[WORLD_MAX_DOF];
+#pragma unroll
+    for (int i = 0; i < WORLD_MAX_DOF; ++i) {
+      a[i] = i < dof ? from[(size_t)e * dof + i] : 0.0;
+      b[i] = i < dof ? to[(size_t)e * dof + i] : 0.0;
+    }
+    const EdgePlan pl = plan_edge(a, b, resolution, mode, check_first);
+    const uint32_t r = g - off[e];
+    const uint32_t m1 = pl.stride - 1; // >= 1 whenever states are owed
+    const uint32_t p = (r / m1) * pl.stride + (r % m1) + 1; // r-th state that is not a multiple of the stride
+    double q[WORLD_MAX_DOF];
+    edge_state(pl, a, b, mode, p, q);
+    if (!state_valid_fast<SP>(w, s_os, s_ob, q))
+      valid[e] = 0;
   }
 }
 
@@ -124,7 +287,7 @@ is_valid_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ q
 #pragma unroll
     for (int d = 0; d < WORLD_MAX_DOF; ++d)
       q[d] = d < w.dof ? qs[i * w.dof + d] : 0.0;
-    valid[i] = state_valid<SP>(w, s_os, s_ob, q) ? 1 : 0;
+    valid[i] = state_valid_fast<SP>(w, s_os, s_ob, q) ? 1 : 0;
   }
 }
 
@@ -158,9 +321,60 @@ size_t obstacle_smem(const DeviceWorld &w) { return ((size_t)w.n_os + 2 * (size_
 
 int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *from_dev, const double *to_dev, uint64_t n,
                         double resolution, int mode, int check_first, uint8_t *valid_dev, int sm_count,
-                        cudaStream_t stream, KernelTimer *timer) {
+                        cudaStream_t stream, KernelTimer *timer, CmScratch *scratch) {
   if (n == 0)
     return PRGPU_OK;
+  if (scratch && n >= 4096) {
+    if (!(resolution > 0.0))
+      return fail(PRGPU_EINVAL, "check_motion: resolution must be > 0");
+    if (mode != PRGPU_MODE_OMPL_DISCRETE && mode != PRGPU_MODE_NNF_ALPHA)
+      return fail(PRGPU_EINVAL, "check_motion: unknown mode");
+    const size_t smem = obstacle_smem(w);
+    const uint64_t PASS = 1ull << 21; // edges per pass: keeps the owed-state prefix sums in 32 bits
+    if (timer)
+      timer->begin(stream);
+    for (uint64_t b0 = 0; b0 < n; b0 += PASS) {
+      const uint32_t m = (uint32_t)std::min<uint64_t>(PASS, n - b0);
+      size_t tmp = 0;
+      PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)m, stream));
+      if (scratch->cap < m || scratch->tmp_bytes < tmp) {
+        if (scratch->owed)
+          cudaFree(scratch->owed);
+        if (scratch->off)
+          cudaFree(scratch->off);
+        if (scratch->tmp)
+          cudaFree(scratch->tmp);
+        scratch->owed = scratch->off = nullptr;
+        scratch->tmp = nullptr;
+        scratch->cap = 0;
+        const size_t cap = std::max<size_t>(m, std::min<uint64_t>(n, PASS));
+        PRGPU_CUDA_TRY(cudaMalloc(&scratch->owed, cap * sizeof(uint32_t)));
+        PRGPU_CUDA_TRY(cudaMalloc(&scratch->off, cap * sizeof(uint32_t)));
+        PRGPU_CUDA_TRY(cudaMalloc(&scratch->tmp, std::max<size_t>(tmp, 16) * 2));
+        scratch->cap = cap;
+        scratch->tmp_bytes = std::max<size_t>(tmp, 16) * 2;
+      }
+      const double *fa = from_dev + b0 * w.dof, *tb = to_dev + b0 * w.dof;
+      uint8_t *vd = valid_dev + b0;
+      const unsigned blocks_a = (unsigned)std::min<uint64_t>((m + CM_THREADS / 8 - 1) / (CM_THREADS / 8), (uint64_t)sm_count * 16);
+      const unsigned blocks_b = (unsigned)sm_count * 8;
+      PRGPU_SP_DISPATCH(w.S, {
+        auto ka = cm_phase_a_kernel<SP>;
+        auto kb = cm_phase_b_kernel<SP>;
+        PRGPU_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PRGPU_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ka<<<blocks_a, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed);
+        size_t tb2 = scratch->tmp_bytes;
+        PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scratch->tmp, tb2, scratch->owed, scratch->off, (int)m, stream));
+        kb<<<blocks_b, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed,
+                                                   scratch->off);
+      });
+      PRGPU_CUDA_TRY(cudaGetLastError());
+    }
+    if (timer)
+      timer->end(stream);
+    return PRGPU_OK;
+  }
   if (!(resolution > 0.0))
     return fail(PRGPU_EINVAL, "check_motion: resolution must be > 0");
   if (mode != PRGPU_MODE_OMPL_DISCRETE && mode != PRGPU_MODE_NNF_ALPHA)

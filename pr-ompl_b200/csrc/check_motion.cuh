@@ -2,9 +2,14 @@
 #pragma once
 #include "world.cuh"
 namespace prgpu {
+struct CmScratch { // owed-state counts, their prefix sums and the scan's temporary storage
+  uint32_t *owed = nullptr, *off = nullptr;
+  void *tmp = nullptr;
+  size_t cap = 0, tmp_bytes = 0;
+};
 int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *from_dev, const double *to_dev, uint64_t n,
                         double resolution, int mode, int check_first, uint8_t *valid_dev, int sm_count,
-                        cudaStream_t stream, KernelTimer *timer = nullptr);
+                        cudaStream_t stream, KernelTimer *timer = nullptr, CmScratch *scratch = nullptr);
 int is_valid_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *q_dev, uint64_t n, uint8_t *valid_dev,
                     cudaStream_t stream);
 int fk_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *q_dev, uint64_t n, double *pose12_dev, cudaStream_t stream);

@@ -167,12 +167,173 @@ __device__ __forceinline__ bool state_valid(const DeviceWorld &w, const float4 *
   return true;
 }
 
+// ---- fast path: fp32 FK in front of the same 3-level test ---------------------------------------
+// The link-sphere centres only feed the conservative fp32 filter (levels 1-2), so they can come from an
+// fp32 forward-kinematics chain; delta (world_create) bounds its error together with the fp32 rounding
+// of the obstacle tables.  A level-2 hit recomputes that sphere's centre with the fp64 chain and applies
+// the specification's fp64 formula, so every verdict is still made in double.
+__device__ __forceinline__ void fk_frames_f32(const DeviceWorld &w, const double *q, float *F) {
+  F[0] = 1.f; F[1] = 0.f; F[2] = 0.f; F[3] = 0.f;
+  F[4] = 0.f; F[5] = 1.f; F[6] = 0.f; F[7] = 0.f;
+  F[8] = 0.f; F[9] = 0.f; F[10] = 1.f; F[11] = 0.f;
+  for (int i = 0; i < w.dof; ++i) {
+    float st, ct;
+    sincosf((float)(q[i] + w.dh[i][4]), &st, &ct);
+    const float a = (float)w.dh[i][0], d = (float)w.dh[i][1], cA = (float)w.dh[i][2], sA = (float)w.dh[i][3];
+    const float L0[4] = {ct, -st * cA, st * sA, a * ct};
+    const float L1[4] = {st, ct * cA, -ct * sA, a * st};
+    const float L2[4] = {0.f, sA, cA, d};
+    const float *P = F + 12 * i;
+    float *N = F + 12 * (i + 1);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = P[4 * r + 0], p1 = P[4 * r + 1], p2 = P[4 * r + 2], p3 = P[4 * r + 3];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v = p0 * L0[c] + p1 * L1[c] + p2 * L2[c];
+        if (c == 3)
+          v += p3;
+        N[4 * r + c] = v;
+      }
+    }
+  }
+}
+
+// fp64 centre of one link sphere, chaining only up to its link (level 3 of the fast path)
+static __device__ __noinline__ void sphere_centre_exact(const DeviceWorld &w, const double *q, int s, double c[3]) {
+  double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  const int link = w.sphere_link[s];
+  for (int i = 0; i < link; ++i) {
+    double st, ct;
+    sincos(q[i] + w.dh[i][4], &st, &ct);
+    const double a = w.dh[i][0], d = w.dh[i][1], cA = w.dh[i][2], sA = w.dh[i][3];
+    const double L0[4] = {ct, -st * cA, st * sA, a * ct};
+    const double L1[4] = {st, ct * cA, -ct * sA, a * st};
+    const double L2[4] = {0.0, sA, cA, d};
+    double N[12];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2], p3 = T[4 * r + 3];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        double v = p0 * L0[cc] + p1 * L1[cc] + p2 * L2[cc];
+        if (cc == 3)
+          v += p3;
+        N[4 * r + cc] = v;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      T[k] = N[k];
+  }
+  const double lx = w.sphere_local[s][0], ly = w.sphere_local[s][1], lz = w.sphere_local[s][2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    c[r] = T[4 * r + 0] * lx + T[4 * r + 1] * ly + T[4 * r + 2] * lz + T[4 * r + 3];
+}
+static __device__ __noinline__ bool exact_pair_hit(const DeviceWorld &w, const double *q, int s, int o, bool box) {
+  double c[3];
+  sphere_centre_exact(w, q, s, c);
+  double d2;
+  double rr;
+  if (!box) {
+    const double *ob = w.os_d + 4 * o;
+    const double dx = c[0] - ob[0], dy = c[1] - ob[1], dz = c[2] - ob[2];
+    d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    rr = __dadd_rn(w.sphere_local[s][3], ob[3]);
+  } else {
+    const double *ob = w.ob_d + 6 * o;
+    double ex = fabs(c[0] - ob[0]) - ob[3];
+    double ey = fabs(c[1] - ob[1]) - ob[4];
+    double ez = fabs(c[2] - ob[2]) - ob[5];
+    ex = ex > 0.0 ? ex : 0.0;
+    ey = ey > 0.0 ? ey : 0.0;
+    ez = ez > 0.0 ? ez : 0.0;
+    d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+    rr = w.sphere_local[s][3];
+  }
+  const double cl = __dsub_rn(__dsqrt_rn(d2), rr);
+  return !(cl > 0.0);
+}
+
+template <int SP>
+__device__ __forceinline__ bool state_valid_fast(const DeviceWorld &w, const float4 *__restrict__ s_os,
+                                                 const float4 *__restrict__ s_ob, const double *q) {
+  float F[12 * (WORLD_MAX_DOF + 1)];
+  fk_frames_f32(w, q, F);
+  float cx[SP], cy[SP], cz[SP];
+#pragma unroll
+  for (int s = 0; s < SP; ++s) {
+    const float *T = F + 12 * w.sphere_link[s];
+    const float lx = (float)w.sphere_local[s][0], ly = (float)w.sphere_local[s][1], lz = (float)w.sphere_local[s][2];
+    cx[s] = T[0] * lx + T[1] * ly + T[2] * lz + T[3];
+    cy[s] = T[4] * lx + T[5] * ly + T[6] * lz + T[7];
+    cz[s] = T[8] * lx + T[9] * ly + T[10] * lz + T[11];
+  }
+  for (int o = 0; o < w.n_os; ++o) {
+    const float4 ob = s_os[o];
+    float t = CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      const float dx = cx[s] - ob.x, dy = cy[s] - ob.y, dz = cz[s] - ob.z;
+      t = fminf(t, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
+    if (t < ob.w) {
+      const float R = (float)w.os_d[4 * o + 3];
+      unsigned hits = 0;
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        const float dx = cx[s] - ob.x, dy = cy[s] - ob.y, dz = cz[s] - ob.z;
+        const float thr = w.sphere_r[s] + R;
+        if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < thr * thr)
+          hits |= 1u << s;
+      }
+      while (hits) {
+        const int s = __ffs(hits) - 1;
+        hits &= hits - 1;
+        if (s < w.S && exact_pair_hit(w, q, s, o, false))
+          return false;
+      }
+    }
+  }
+  for (int o = 0; o < w.n_ob; ++o) {
+    const float4 bc = s_ob[2 * o], bh = s_ob[2 * o + 1];
+    float t = CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      const float ex = fmaxf(fabsf(cx[s] - bc.x) - bh.x, 0.0f);
+      const float ey = fmaxf(fabsf(cy[s] - bc.y) - bh.y, 0.0f);
+      const float ez = fmaxf(fabsf(cz[s] - bc.z) - bh.z, 0.0f);
+      t = fminf(t, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+    }
+    if (t < w.box_thr2) {
+      unsigned hits = 0;
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        const float ex = fmaxf(fabsf(cx[s] - bc.x) - bh.x, 0.0f);
+        const float ey = fmaxf(fabsf(cy[s] - bc.y) - bh.y, 0.0f);
+        const float ez = fmaxf(fabsf(cz[s] - bc.z) - bh.z, 0.0f);
+        const float thr = w.sphere_r[s];
+        if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < thr * thr)
+          hits |= 1u << s;
+      }
+      while (hits) {
+        const int s = __ffs(hits) - 1;
+        hits &= hits - 1;
+        if (s < w.S && exact_pair_hit(w, q, s, o, true))
+          return false;
+      }
+    }
+  }
+  return true;
+}
+
 // out-of-line variant for kernels that test states from several places (keeps their register
 // footprint at the checker's own)
 template <int SP>
 __device__ __noinline__ bool state_valid_call(const DeviceWorld *wp, const float4 *s_os, const float4 *s_ob,
                                               const double *q) {
-  return state_valid<SP>(*wp, s_os, s_ob, q);
+  return state_valid_fast<SP>(*wp, s_os, s_ob, q);
 }
 
 // cooperative copy of the fp32 obstacle tables into shared memory
