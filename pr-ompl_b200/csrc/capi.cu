@@ -3,6 +3,7 @@
 // no sm_100 device is usable.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "capi_internal.cuh"
@@ -411,11 +412,85 @@ int prgpu_world_create(int device, int dof, const double *dh, int ns, const int3
   const double bt = rmax + delta;
   H.box_thr2 = (float)(bt * bt * (1.0 + 1e-6));
 
+  // ---- broad phase: uniform grid over the inflated obstacle boxes --------------------------------
+  std::vector<uint32_t> cell_start;
+  std::vector<uint16_t> cell_item;
+  H.grid_n[0] = H.grid_n[1] = H.grid_n[2] = 0;
+  H.grid_items = 0;
+  if (nos + nob > 0 && nos < 0x8000 && nob < 0x8000 && !getenv("PRGPU_NO_GRID")) {
+    const double infl = rmax + delta + 1e-4; // + slack for the fp32 cell index of a centre
+    double lo3[3] = {1e300, 1e300, 1e300}, hi3[3] = {-1e300, -1e300, -1e300};
+    auto box_of = [&](int id, bool isbox, double *bl, double *bh) {
+      for (int c = 0; c < 3; ++c) {
+        const double ctr = isbox ? obs_boxes[6 * id + c] : obs_spheres[4 * id + c];
+        const double ext = (isbox ? obs_boxes[6 * id + 3 + c] : obs_spheres[4 * id + 3]) + infl;
+        bl[c] = ctr - ext;
+        bh[c] = ctr + ext;
+      }
+    };
+    for (int pass = 0; pass < 2; ++pass)
+      for (int id = 0; id < (pass ? nob : nos); ++id) {
+        double bl[3], bh[3];
+        box_of(id, pass == 1, bl, bh);
+        for (int c = 0; c < 3; ++c) {
+          lo3[c] = std::min(lo3[c], bl[c]);
+          hi3[c] = std::max(hi3[c], bh[c]);
+        }
+      }
+    double cell = std::max(0.15, 2.5 * infl);
+    for (int attempt = 0; attempt < 12; ++attempt, cell *= 1.3) {
+      int nn[3];
+      uint64_t ncell = 1;
+      for (int c = 0; c < 3; ++c) {
+        nn[c] = std::max(1, (int)std::ceil((hi3[c] - lo3[c]) / cell));
+        ncell *= (uint64_t)nn[c];
+      }
+      if (ncell > 4096)
+        continue;
+      std::vector<std::vector<uint16_t>> lists(ncell);
+      uint64_t items = 0;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int id = 0; id < (pass ? nob : nos); ++id) {
+          double bl[3], bh[3];
+          box_of(id, pass == 1, bl, bh);
+          int c0[3], c1[3];
+          for (int c = 0; c < 3; ++c) {
+            c0[c] = std::min(nn[c] - 1, std::max(0, (int)std::floor((bl[c] - lo3[c]) / cell)));
+            c1[c] = std::min(nn[c] - 1, std::max(0, (int)std::floor((bh[c] - lo3[c]) / cell)));
+          }
+          for (int z = c0[2]; z <= c1[2]; ++z)
+            for (int y = c0[1]; y <= c1[1]; ++y)
+              for (int x = c0[0]; x <= c1[0]; ++x) {
+                lists[((size_t)z * nn[1] + y) * nn[0] + x].push_back((uint16_t)(id | (pass ? 0x8000 : 0)));
+                ++items;
+              }
+        }
+      if (items > 16384)
+        continue;
+      cell_start.assign(ncell + 1, 0);
+      cell_item.clear();
+      for (uint64_t i = 0; i < ncell; ++i) {
+        cell_start[i] = (uint32_t)cell_item.size();
+        cell_item.insert(cell_item.end(), lists[i].begin(), lists[i].end());
+      }
+      cell_start[ncell] = (uint32_t)cell_item.size();
+      for (int c = 0; c < 3; ++c) {
+        H.grid_n[c] = nn[c];
+        H.grid_org[c] = (float)lo3[c];
+      }
+      H.grid_inv = (float)(1.0 / cell);
+      H.grid_items = (uint32_t)cell_item.size();
+      break;
+    }
+  }
+  const bool use_grid = H.grid_n[0] > 0;
+
   std::vector<float4> osf(nos), obf(2 * (size_t)nob);
   for (int o = 0; o < nos; ++o) {
     const double t = obs_spheres[4 * o + 3] + rmax + delta;
-    osf[o] = make_float4((float)obs_spheres[4 * o], (float)obs_spheres[4 * o + 1],
-                         (float)obs_spheres[4 * o + 2], (float)(t * t * (1.0 + 1e-6)));
+    // .w: the grid path wants the obstacle radius, the brute-force filter its level-1 threshold
+    osf[o] = make_float4((float)obs_spheres[4 * o], (float)obs_spheres[4 * o + 1], (float)obs_spheres[4 * o + 2],
+                         use_grid ? (float)(obs_spheres[4 * o + 3] * (1.0 + 1e-6)) : (float)(t * t * (1.0 + 1e-6)));
   }
   for (int o = 0; o < nob; ++o) {
     obf[2 * o] = make_float4((float)obs_boxes[6 * o], (float)obs_boxes[6 * o + 1],
@@ -439,7 +514,9 @@ int prgpu_world_create(int device, int dof, const double *dh, int ns, const int3
   if ((rc = upload(w->os_f, osf.data(), osf.size() * sizeof(float4))) != PRGPU_OK ||
       (rc = upload(w->ob_f, obf.data(), obf.size() * sizeof(float4))) != PRGPU_OK ||
       (rc = upload(w->os_d, obs_spheres, (size_t)nos * 4 * sizeof(double))) != PRGPU_OK ||
-      (rc = upload(w->ob_d, obs_boxes, (size_t)nob * 6 * sizeof(double))) != PRGPU_OK) {
+      (rc = upload(w->ob_d, obs_boxes, (size_t)nob * 6 * sizeof(double))) != PRGPU_OK ||
+      (rc = upload(w->cell_start, cell_start.data(), cell_start.size() * sizeof(uint32_t))) != PRGPU_OK ||
+      (rc = upload(w->cell_item, cell_item.data(), cell_item.size() * sizeof(uint16_t))) != PRGPU_OK) {
     prgpu_world_destroy(w);
     return rc;
   }
@@ -447,6 +524,8 @@ int prgpu_world_create(int device, int dof, const double *dh, int ns, const int3
   H.ob_f = w->ob_f.as<float4>();
   H.os_d = w->os_d.as<double>();
   H.ob_d = w->ob_d.as<double>();
+  H.cell_start = w->cell_start.as<uint32_t>();
+  H.cell_item = w->cell_item.as<uint16_t>();
   e = cudaMalloc(&w->dev, sizeof(DeviceWorld));
   if (e == cudaSuccess)
     e = cudaMemcpy(w->dev, &H, sizeof(DeviceWorld), cudaMemcpyHostToDevice);
@@ -468,6 +547,8 @@ int prgpu_world_destroy(prgpu_world_t *w) {
   w->ob_f.release();
   w->os_d.release();
   w->ob_d.release();
+  w->cell_start.release();
+  w->cell_item.release();
   w->d_a.release();
   w->d_b.release();
   w->d_valid.release();

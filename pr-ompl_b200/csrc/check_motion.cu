@@ -27,9 +27,7 @@ check_motion_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict
                     uint8_t *__restrict__ valid) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
-  float4 *s_os = s_obs;
-  float4 *s_ob = s_obs + w.n_os;
-  load_obstacles(w, s_os, s_ob);
+  const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -99,7 +97,7 @@ check_motion_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict
           for (int i = 0; i < WORLD_MAX_DOF; ++i)
             q[i] = lerp_exact(a[i], b[i], alpha);
         }
-        good = state_valid_fast<SP>(w, s_os, s_ob, q);
+        good = state_valid_any<SP>(wp, &tabs, q);
       }
       if (__any_sync(0xffffffffu, !good)) {
         ok = false;
@@ -190,9 +188,7 @@ cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
                   uint32_t *__restrict__ owed) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
-  float4 *s_os = s_obs;
-  float4 *s_ob = s_obs + w.n_os;
-  load_obstacles(w, s_os, s_ob);
+  const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
   const int dof = w.dof;
   const uint32_t groups_total = gridDim.x * (CM_THREADS / 8);
@@ -215,7 +211,7 @@ cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
       if (p < pl.np) {
         double q[WORLD_MAX_DOF];
         edge_state(pl, a, b, mode, p, q);
-        good = state_valid_fast<SP>(w, s_os, s_ob, q);
+        good = state_valid_any<SP>(wp, &tabs, q);
       }
     }
     const unsigned bad = __ballot_sync(0xffffffffu, !good);
@@ -235,9 +231,7 @@ cm_phase_b_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
                   const uint32_t *__restrict__ owed, const uint32_t *__restrict__ off) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
-  float4 *s_os = s_obs;
-  float4 *s_ob = s_obs + w.n_os;
-  load_obstacles(w, s_os, s_ob);
+  const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
   const int dof = w.dof;
   const uint32_t total = off[n - 1] + owed[n - 1];
@@ -267,7 +261,7 @@ cm_phase_b_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
     const uint32_t p = (r / m1) * pl.stride + (r % m1) + 1; // r-th state that is not a multiple of the stride
     double q[WORLD_MAX_DOF];
     edge_state(pl, a, b, mode, p, q);
-    if (!state_valid_fast<SP>(w, s_os, s_ob, q))
+    if (!state_valid_any<SP>(wp, &tabs, q))
       valid[e] = 0;
   }
 }
@@ -277,9 +271,7 @@ __global__ void __launch_bounds__(CM_THREADS)
 is_valid_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ qs, uint64_t n, uint8_t *__restrict__ valid) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
-  float4 *s_os = s_obs;
-  float4 *s_ob = s_obs + w.n_os;
-  load_obstacles(w, s_os, s_ob);
+  const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
@@ -287,7 +279,7 @@ is_valid_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ q
 #pragma unroll
     for (int d = 0; d < WORLD_MAX_DOF; ++d)
       q[d] = d < w.dof ? qs[i * w.dof + d] : 0.0;
-    valid[i] = state_valid_fast<SP>(w, s_os, s_ob, q) ? 1 : 0;
+    valid[i] = state_valid_any<SP>(wp, &tabs, q) ? 1 : 0;
   }
 }
 
@@ -307,7 +299,7 @@ __global__ void fk_kernel(const DeviceWorld *__restrict__ wp, const double *__re
     pose12[i * 12 + k] = F[12 * w.dof + k];
 }
 
-size_t obstacle_smem(const DeviceWorld &w) { return ((size_t)w.n_os + 2 * (size_t)w.n_ob) * sizeof(float4); }
+size_t obstacle_smem(const DeviceWorld &w) { return obstacle_tables_bytes(w); }
 
 } // namespace
 

@@ -36,10 +36,8 @@ rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, 
                   uint32_t n_queries) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
-  float4 *s_os = s_obs;
-  float4 *s_ob = s_obs + w.n_os;
   __shared__ Shared sh;
-  load_obstacles(w, s_os, s_ob);
+  const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
 
   const uint32_t qid = blockIdx.x;
@@ -69,7 +67,7 @@ rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, 
 #pragma unroll
       for (int i = 0; i < WORLD_MAX_DOF; ++i)
         qq[i] = i < dim ? q[i] : 0.0;
-      sh.flag = (in_bounds(qq) && state_valid_call<SP>(wp, s_os, s_ob, qq)) ? 1 : 0;
+      sh.flag = (in_bounds(qq) && state_valid_call<SP>(wp, &tabs, qq)) ? 1 : 0;
     }
     __syncthreads();
     const int f = sh.flag;
@@ -186,7 +184,7 @@ rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, 
           for (int k = 0; k < WORLD_MAX_DOF; ++k)
             q[k] = lerp_exact(from[k], to[k], t);
         }
-        good = state_valid_call<SP>(wp, s_os, s_ob, q);
+        good = state_valid_call<SP>(wp, &tabs, q);
       }
       if (__syncthreads_or(!good)) {
         ok = false;
@@ -307,7 +305,7 @@ int rrtc_batch_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const Rrtc
                       const RrtcDeviceBuffers &b, uint32_t n_queries, cudaStream_t stream) {
   if (n_queries == 0)
     return PRGPU_OK;
-  const size_t smem = ((size_t)w.n_os + 2 * (size_t)w.n_ob) * sizeof(float4);
+  const size_t smem = obstacle_tables_bytes(w);
 #define PRGPU_RB_LAUNCH(SPV)                                                                       \
   do {                                                                                             \
     auto kern = rrtc_batch_kernel<SPV>;                                                            \

@@ -28,7 +28,17 @@ struct DeviceWorld {
   const float4 *ob_f;                // n_ob x 2: (cx,cy,cz,_) (hx,hy,hz,_)
   const double *os_d;                // n_os x 4
   const double *ob_d;                // n_ob x 6
+  // broad phase: uniform grid over the obstacles.  An obstacle is listed in every cell its bounding box
+  // inflated by (r_max + delta + GRID_SLACK) overlaps, so the cell that contains a link-sphere centre
+  // lists every obstacle that sphere could touch.  grid_n[0] == 0: no grid (brute-force filter).
+  int grid_n[3];
+  float grid_org[3], grid_inv;
+  uint32_t grid_items;               // total list length
+  const uint32_t *cell_start;        // ncell+1
+  const uint16_t *cell_item;         // obstacle index, bit 15 set for boxes
 };
+constexpr int WORLD_GRID_MAX_CELLS = 8192;
+constexpr int WORLD_GRID_MAX_ITEMS = 32768;
 
 // frames F[(i)*12 ..]: 3x4 row-major [R|p] of frame i = 0..dof
 __device__ __forceinline__ void fk_frames(const DeviceWorld &w, const double *q, double *F) {
@@ -328,20 +338,106 @@ __device__ __forceinline__ bool state_valid_fast(const DeviceWorld &w, const flo
   return true;
 }
 
-// out-of-line variant for kernels that test states from several places (keeps their register
-// footprint at the checker's own)
-template <int SP>
-__device__ __noinline__ bool state_valid_call(const DeviceWorld *wp, const float4 *s_os, const float4 *s_ob,
-                                              const double *q) {
-  return state_valid_fast<SP>(*wp, s_os, s_ob, q);
-}
-
 // cooperative copy of the fp32 obstacle tables into shared memory
 __device__ __forceinline__ void load_obstacles(const DeviceWorld &w, float4 *s_os, float4 *s_ob) {
   for (int i = threadIdx.x; i < w.n_os; i += blockDim.x)
     s_os[i] = w.os_f[i];
   for (int i = threadIdx.x; i < 2 * w.n_ob; i += blockDim.x)
     s_ob[i] = w.ob_f[i];
+}
+
+// ---- grid path: per link sphere, only the obstacles listed in the sphere centre's cell ------------
+struct ObstacleTables { // shared-memory views
+  const float4 *os, *ob;
+  const uint32_t *cell_start;
+  const uint16_t *cell_item;
+};
+__host__ __device__ __forceinline__ size_t obstacle_tables_bytes(const DeviceWorld &w) {
+  size_t b = ((size_t)w.n_os + 2 * (size_t)w.n_ob) * sizeof(float4);
+  if (w.grid_n[0] > 0)
+    b += ((size_t)w.grid_n[0] * w.grid_n[1] * w.grid_n[2] + 1) * sizeof(uint32_t) + (((size_t)w.grid_items + 7) & ~(size_t)7) * sizeof(uint16_t);
+  return b;
+}
+// cooperative load of all tables; returns the views (call from every thread, then __syncthreads)
+__device__ __forceinline__ ObstacleTables load_tables(const DeviceWorld &w, float4 *smem) {
+  ObstacleTables t;
+  float4 *s_os = smem, *s_ob = smem + w.n_os;
+  load_obstacles(w, s_os, s_ob);
+  t.os = s_os;
+  t.ob = s_ob;
+  t.cell_start = nullptr;
+  t.cell_item = nullptr;
+  if (w.grid_n[0] > 0) {
+    const uint32_t ncell = (uint32_t)(w.grid_n[0] * w.grid_n[1] * w.grid_n[2]);
+    uint32_t *cs = reinterpret_cast<uint32_t *>(smem + w.n_os + 2 * w.n_ob);
+    uint16_t *ci = reinterpret_cast<uint16_t *>(cs + ncell + 1);
+    for (uint32_t i = threadIdx.x; i <= ncell; i += blockDim.x)
+      cs[i] = w.cell_start[i];
+    for (uint32_t i = threadIdx.x; i < w.grid_items; i += blockDim.x)
+      ci[i] = w.cell_item[i];
+    t.cell_start = cs;
+    t.cell_item = ci;
+  }
+  return t;
+}
+
+static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q) {
+  const DeviceWorld &w = *wp;
+  const ObstacleTables &t = *tp;
+  float F[12 * (WORLD_MAX_DOF + 1)];
+  fk_frames_f32(w, q, F);
+  const int nx = w.grid_n[0], ny = w.grid_n[1], nz = w.grid_n[2];
+  for (int s = 0; s < w.S; ++s) {
+    const float *T = F + 12 * w.sphere_link[s];
+    const float lx = (float)w.sphere_local[s][0], ly = (float)w.sphere_local[s][1], lz = (float)w.sphere_local[s][2];
+    const float cx = T[0] * lx + T[1] * ly + T[2] * lz + T[3];
+    const float cy = T[4] * lx + T[5] * ly + T[6] * lz + T[7];
+    const float cz = T[8] * lx + T[9] * ly + T[10] * lz + T[11];
+    const float gx = (cx - w.grid_org[0]) * w.grid_inv, gy = (cy - w.grid_org[1]) * w.grid_inv,
+                gz = (cz - w.grid_org[2]) * w.grid_inv;
+    // outside the grid (or NaN): no inflated obstacle box contains the centre
+    if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float)nx && gy < (float)ny && gz < (float)nz))
+      continue;
+    const int cell = ((int)gz * ny + (int)gy) * nx + (int)gx;
+    const float rs = w.sphere_r[s];
+    for (uint32_t it = t.cell_start[cell]; it < t.cell_start[cell + 1]; ++it) {
+      const uint32_t id = t.cell_item[it];
+      bool hit;
+      if (id & 0x8000u) {
+        const uint32_t o = id & 0x7FFFu;
+        const float4 bc = t.ob[2 * o], bh = t.ob[2 * o + 1];
+        const float ex = fmaxf(fabsf(cx - bc.x) - bh.x, 0.0f);
+        const float ey = fmaxf(fabsf(cy - bc.y) - bh.y, 0.0f);
+        const float ez = fmaxf(fabsf(cz - bc.z) - bh.z, 0.0f);
+        hit = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < rs * rs;
+        if (hit && exact_pair_hit(w, q, s, (int)o, true))
+          return false;
+      } else {
+        const float4 ob = t.os[id];
+        const float dx = cx - ob.x, dy = cy - ob.y, dz = cz - ob.z;
+        const float thr = rs + ob.w; // grid tables keep the obstacle radius in .w
+        hit = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < thr * thr;
+        if (hit && exact_pair_hit(w, q, s, (int)id, false))
+          return false;
+      }
+    }
+  }
+  return true;
+}
+
+// validity of one state through whichever broad phase the world has
+template <int SP>
+__device__ __forceinline__ bool state_valid_any(const DeviceWorld *wp, const ObstacleTables *tp, const double *q) {
+  if (wp->grid_n[0] > 0)
+    return state_valid_grid(wp, tp, q);
+  return state_valid_fast<SP>(*wp, tp->os, tp->ob, q);
+}
+
+// out-of-line variant for kernels that test states from several places (keeps their register
+// footprint at the checker's own)
+template <int SP>
+__device__ __noinline__ bool state_valid_call(const DeviceWorld *wp, const ObstacleTables *tp, const double *q) {
+  return state_valid_any<SP>(wp, tp, q);
 }
 
 } // namespace prgpu
