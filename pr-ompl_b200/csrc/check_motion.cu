@@ -224,29 +224,30 @@ cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
   }
 }
 
+// item g of the owed states belongs to edge item_edge[g]
+__global__ void cm_expand_kernel(uint32_t n, const uint32_t *__restrict__ owed, const uint32_t *__restrict__ off,
+                                 uint32_t *__restrict__ item_edge) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n)
+    return;
+  const uint32_t c = owed[e], o = off[e];
+  for (uint32_t i = 0; i < c; ++i)
+    item_edge[o + i] = e;
+}
+
 template <int SP>
 __global__ void __launch_bounds__(CM_THREADS)
 cm_phase_b_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
-                  uint32_t n, double resolution, int mode, int check_first, volatile uint8_t *valid,
-                  const uint32_t *__restrict__ owed, const uint32_t *__restrict__ off) {
+                  uint32_t total, double resolution, int mode, int check_first, volatile uint8_t *valid,
+                  const uint32_t *__restrict__ off, const uint32_t *__restrict__ item_edge) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
   const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
   const int dof = w.dof;
-  const uint32_t total = off[n - 1] + owed[n - 1];
   const uint32_t gsize = gridDim.x * CM_THREADS;
   for (uint32_t g = blockIdx.x * CM_THREADS + threadIdx.x; g < total; g += gsize) {
-    // edge of work item g: last e with off[e] <= g
-    uint32_t lo_e = 0, hi_e = n - 1;
-    while (lo_e < hi_e) {
-      const uint32_t mid = (lo_e + hi_e + 1) >> 1;
-      if (off[mid] <= g)
-        lo_e = mid;
-      else
-        hi_e = mid - 1;
-    }
-    const uint32_t e = lo_e;
+    const uint32_t e = item_edge[g];
     if (valid[e] == 0)
       continue; // another state of this edge already failed
     double a[WORLD_MAX_DOF], b[WORLD_MAX_DOF];
@@ -322,7 +323,7 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
     if (mode != PRGPU_MODE_OMPL_DISCRETE && mode != PRGPU_MODE_NNF_ALPHA)
       return fail(PRGPU_EINVAL, "check_motion: unknown mode");
     const size_t smem = obstacle_smem(w);
-    const uint64_t PASS = 1ull << 21; // edges per pass: keeps the owed-state prefix sums in 32 bits
+    const uint64_t PASS = 1ull << 20; // edges per pass: keeps the owed-state prefix sums in 32 bits
     if (timer)
       timer->begin(stream);
     for (uint64_t b0 = 0; b0 < n; b0 += PASS) {
@@ -358,8 +359,26 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
         ka<<<blocks_a, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed);
         size_t tb2 = scratch->tmp_bytes;
         PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scratch->tmp, tb2, scratch->owed, scratch->off, (int)m, stream));
-        kb<<<blocks_b, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed,
-                                                   scratch->off);
+        // number of owed states (one small read-back per pass sizes the item table and the grid)
+        uint32_t last_off = 0, last_owed = 0;
+        PRGPU_CUDA_TRY(cudaMemcpyAsync(&last_off, scratch->off + (m - 1), 4, cudaMemcpyDeviceToHost, stream));
+        PRGPU_CUDA_TRY(cudaMemcpyAsync(&last_owed, scratch->owed + (m - 1), 4, cudaMemcpyDeviceToHost, stream));
+        PRGPU_CUDA_TRY(cudaStreamSynchronize(stream));
+        const uint32_t total = last_off + last_owed;
+        if (total > 0) {
+          if (scratch->item_cap < total) {
+            if (scratch->item_edge)
+              cudaFree(scratch->item_edge);
+            scratch->item_edge = nullptr;
+            scratch->item_cap = 0;
+            PRGPU_CUDA_TRY(cudaMalloc(&scratch->item_edge, (size_t)total * 5 / 4 * sizeof(uint32_t)));
+            scratch->item_cap = (size_t)total * 5 / 4;
+          }
+          cm_expand_kernel<<<(m + 255) / 256, 256, 0, stream>>>(m, scratch->owed, scratch->off, scratch->item_edge);
+          const unsigned nb = (unsigned)std::min<uint64_t>(((uint64_t)total + CM_THREADS - 1) / CM_THREADS, blocks_b);
+          kb<<<nb, CM_THREADS, smem, stream>>>(w_dev, fa, tb, total, resolution, mode, check_first, vd, scratch->off,
+                                               scratch->item_edge);
+        }
       });
       PRGPU_CUDA_TRY(cudaGetLastError());
     }

@@ -6,6 +6,8 @@ struct CmScratch { // owed-state counts, their prefix sums and the scan's tempor
   uint32_t *owed = nullptr, *off = nullptr;
   void *tmp = nullptr;
   size_t cap = 0, tmp_bytes = 0;
+  uint32_t *item_edge = nullptr; // owed state -> edge
+  size_t item_cap = 0;
 };
 int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *from_dev, const double *to_dev, uint64_t n,
                         double resolution, int mode, int check_first, uint8_t *valid_dev, int sm_count,

@@ -347,13 +347,20 @@ __device__ __forceinline__ void load_obstacles(const DeviceWorld &w, float4 *s_o
 }
 
 // ---- grid path: per link sphere, only the obstacles listed in the sphere centre's cell ------------
+struct ArmTableF32 { // fp32 copy of the arm for the filter path (shared memory)
+  float dh[WORLD_MAX_DOF][5];        // a, d, cos(alpha), sin(alpha), theta0
+  float4 sphere[WORLD_MAX_S];        // local x,y,z and radius + delta, ordered by link
+  uint8_t sphere_id[WORLD_MAX_S];    // original sphere index of slot j
+  uint8_t link_first[WORLD_MAX_DOF + 2]; // spheres of frame i are slots [link_first[i], link_first[i+1])
+};
 struct ObstacleTables { // shared-memory views
   const float4 *os, *ob;
   const uint32_t *cell_start;
   const uint16_t *cell_item;
+  const ArmTableF32 *arm;
 };
 __host__ __device__ __forceinline__ size_t obstacle_tables_bytes(const DeviceWorld &w) {
-  size_t b = ((size_t)w.n_os + 2 * (size_t)w.n_ob) * sizeof(float4);
+  size_t b = ((size_t)w.n_os + 2 * (size_t)w.n_ob) * sizeof(float4) + ((sizeof(ArmTableF32) + 15) & ~(size_t)15);
   if (w.grid_n[0] > 0)
     b += ((size_t)w.grid_n[0] * w.grid_n[1] * w.grid_n[2] + 1) * sizeof(uint32_t) + (((size_t)w.grid_items + 7) & ~(size_t)7) * sizeof(uint16_t);
   return b;
@@ -367,9 +374,29 @@ __device__ __forceinline__ ObstacleTables load_tables(const DeviceWorld &w, floa
   t.ob = s_ob;
   t.cell_start = nullptr;
   t.cell_item = nullptr;
+  ArmTableF32 *arm = reinterpret_cast<ArmTableF32 *>(smem + w.n_os + 2 * w.n_ob);
+  t.arm = arm;
+  if (threadIdx.x < WORLD_MAX_DOF)
+    for (int c = 0; c < 5; ++c)
+      arm->dh[threadIdx.x][c] = (float)w.dh[threadIdx.x][c];
+  if (threadIdx.x == 0) { // spheres grouped by the frame they ride on (counting sort, stable)
+    int n = 0;
+    for (int i = 0; i <= w.dof; ++i) {
+      arm->link_first[i] = (uint8_t)n;
+      for (int s = 0; s < w.S; ++s)
+        if (w.sphere_link[s] == i) {
+          arm->sphere[n] = make_float4((float)w.sphere_local[s][0], (float)w.sphere_local[s][1],
+                                       (float)w.sphere_local[s][2], w.sphere_r[s]);
+          arm->sphere_id[n] = (uint8_t)s;
+          ++n;
+        }
+    }
+    arm->link_first[w.dof + 1] = (uint8_t)n;
+  }
   if (w.grid_n[0] > 0) {
     const uint32_t ncell = (uint32_t)(w.grid_n[0] * w.grid_n[1] * w.grid_n[2]);
-    uint32_t *cs = reinterpret_cast<uint32_t *>(smem + w.n_os + 2 * w.n_ob);
+    uint32_t *cs = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(arm) +
+                                                ((sizeof(ArmTableF32) + 15) & ~(size_t)15));
     uint16_t *ci = reinterpret_cast<uint16_t *>(cs + ncell + 1);
     for (uint32_t i = threadIdx.x; i <= ncell; i += blockDim.x)
       cs[i] = w.cell_start[i];
@@ -384,41 +411,60 @@ __device__ __forceinline__ ObstacleTables load_tables(const DeviceWorld &w, floa
 static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q) {
   const DeviceWorld &w = *wp;
   const ObstacleTables &t = *tp;
-  float F[12 * (WORLD_MAX_DOF + 1)];
-  fk_frames_f32(w, q, F);
+  const ArmTableF32 &arm = *t.arm;
   const int nx = w.grid_n[0], ny = w.grid_n[1], nz = w.grid_n[2];
-  for (int s = 0; s < w.S; ++s) {
-    const float *T = F + 12 * w.sphere_link[s];
-    const float lx = (float)w.sphere_local[s][0], ly = (float)w.sphere_local[s][1], lz = (float)w.sphere_local[s][2];
-    const float cx = T[0] * lx + T[1] * ly + T[2] * lz + T[3];
-    const float cy = T[4] * lx + T[5] * ly + T[6] * lz + T[7];
-    const float cz = T[8] * lx + T[9] * ly + T[10] * lz + T[11];
-    const float gx = (cx - w.grid_org[0]) * w.grid_inv, gy = (cy - w.grid_org[1]) * w.grid_inv,
-                gz = (cz - w.grid_org[2]) * w.grid_inv;
-    // outside the grid (or NaN): no inflated obstacle box contains the centre
-    if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float)nx && gy < (float)ny && gz < (float)nz))
-      continue;
-    const int cell = ((int)gz * ny + (int)gy) * nx + (int)gx;
-    const float rs = w.sphere_r[s];
-    for (uint32_t it = t.cell_start[cell]; it < t.cell_start[cell + 1]; ++it) {
-      const uint32_t id = t.cell_item[it];
-      bool hit;
-      if (id & 0x8000u) {
-        const uint32_t o = id & 0x7FFFu;
-        const float4 bc = t.ob[2 * o], bh = t.ob[2 * o + 1];
-        const float ex = fmaxf(fabsf(cx - bc.x) - bh.x, 0.0f);
-        const float ey = fmaxf(fabsf(cy - bc.y) - bh.y, 0.0f);
-        const float ez = fmaxf(fabsf(cz - bc.z) - bh.z, 0.0f);
-        hit = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < rs * rs;
-        if (hit && exact_pair_hit(w, q, s, (int)o, true))
-          return false;
-      } else {
-        const float4 ob = t.os[id];
-        const float dx = cx - ob.x, dy = cy - ob.y, dz = cz - ob.z;
-        const float thr = rs + ob.w; // grid tables keep the obstacle radius in .w
-        hit = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < thr * thr;
-        if (hit && exact_pair_hit(w, q, s, (int)id, false))
-          return false;
+  const float ox = w.grid_org[0], oy = w.grid_org[1], oz = w.grid_org[2], ginv = w.grid_inv;
+  // current frame [R|p], fp32, in registers; the spheres of frame i are tested before moving on
+  float r00 = 1.f, r01 = 0.f, r02 = 0.f, p0 = 0.f;
+  float r10 = 0.f, r11 = 1.f, r12 = 0.f, p1 = 0.f;
+  float r20 = 0.f, r21 = 0.f, r22 = 1.f, p2 = 0.f;
+  for (int i = 0; i <= w.dof; ++i) {
+    if (i > 0) {
+      float st, ct;
+      sincosf((float)q[i - 1] + arm.dh[i - 1][4], &st, &ct);
+      const float a = arm.dh[i - 1][0], d = arm.dh[i - 1][1], cA = arm.dh[i - 1][2], sA = arm.dh[i - 1][3];
+      // T <- T * [Rz(theta) Tz(d) Tx(a) Rx(alpha)]
+      const float l01 = -st * cA, l02 = st * sA, l03 = a * ct;
+      const float l11 = ct * cA, l12 = -ct * sA, l13 = a * st;
+      float n0, n1, n2, n3;
+      n0 = r00 * ct + r01 * st; n1 = r00 * l01 + r01 * l11 + r02 * sA; n2 = r00 * l02 + r01 * l12 + r02 * cA;
+      n3 = r00 * l03 + r01 * l13 + r02 * d + p0;
+      r00 = n0; r01 = n1; r02 = n2; p0 = n3;
+      n0 = r10 * ct + r11 * st; n1 = r10 * l01 + r11 * l11 + r12 * sA; n2 = r10 * l02 + r11 * l12 + r12 * cA;
+      n3 = r10 * l03 + r11 * l13 + r12 * d + p1;
+      r10 = n0; r11 = n1; r12 = n2; p1 = n3;
+      n0 = r20 * ct + r21 * st; n1 = r20 * l01 + r21 * l11 + r22 * sA; n2 = r20 * l02 + r21 * l12 + r22 * cA;
+      n3 = r20 * l03 + r21 * l13 + r22 * d + p2;
+      r20 = n0; r21 = n1; r22 = n2; p2 = n3;
+    }
+    for (int j = arm.link_first[i]; j < arm.link_first[i + 1]; ++j) {
+      const float4 sp = arm.sphere[j];
+      const float cx = r00 * sp.x + r01 * sp.y + r02 * sp.z + p0;
+      const float cy = r10 * sp.x + r11 * sp.y + r12 * sp.z + p1;
+      const float cz = r20 * sp.x + r21 * sp.y + r22 * sp.z + p2;
+      const float gx = (cx - ox) * ginv, gy = (cy - oy) * ginv, gz = (cz - oz) * ginv;
+      // outside the grid (or NaN): no inflated obstacle box contains the centre
+      if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float)nx && gy < (float)ny && gz < (float)nz))
+        continue;
+      const int cell = ((int)gz * ny + (int)gy) * nx + (int)gx;
+      const float rs = sp.w;
+      for (uint32_t it = t.cell_start[cell]; it < t.cell_start[cell + 1]; ++it) {
+        const uint32_t id = t.cell_item[it];
+        if (id & 0x8000u) {
+          const uint32_t o = id & 0x7FFFu;
+          const float4 bc = t.ob[2 * o], bh = t.ob[2 * o + 1];
+          const float ex = fmaxf(fabsf(cx - bc.x) - bh.x, 0.0f);
+          const float ey = fmaxf(fabsf(cy - bc.y) - bh.y, 0.0f);
+          const float ez = fmaxf(fabsf(cz - bc.z) - bh.z, 0.0f);
+          if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < rs * rs && exact_pair_hit(w, q, arm.sphere_id[j], (int)o, true))
+            return false;
+        } else {
+          const float4 ob = t.os[id];
+          const float dx = cx - ob.x, dy = cy - ob.y, dz = cz - ob.z;
+          const float thr = rs + ob.w; // grid tables keep the obstacle radius in .w
+          if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < thr * thr && exact_pair_hit(w, q, arm.sphere_id[j], (int)id, false))
+            return false;
+        }
       }
     }
   }
