@@ -1,0 +1,223 @@
+// pr_gpu::NNFrechet: host side of the NNF planner over prgpu_nnf_* (see pr_gpu/NNFrechet.h).
+// Behaviour follows frechet/src/NNFrechet.cpp (setters :23-84, setup :184-221, solve :95-178,
+// subsampleRefPath :235-252 with util.cpp's linIntSpace :3-21, the IK budget :310-343 and :418-448).
+#include "pr_gpu/NNFrechet.h"
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <ompl/base/spaces/RealVectorStateSpace.h>
+
+namespace ob = ompl::base;
+namespace pr_gpu {
+
+NNFrechet::NNFrechet(const ob::SpaceInformationPtr &si) : ob::Planner(si, "NNFrechet"), space_(si->getStateSpace()) {
+  rng_.seed(1);
+}
+NNFrechet::NNFrechet(const ob::SpaceInformationPtr &si, int numWaypoints, int ikMultiplier, int numNN,
+                     int discretization, int seed)
+    : ob::Planner(si, "NNFrechet"), space_(si->getStateSpace()), numWaypoints_(numWaypoints),
+      ikMultiplier_(ikMultiplier), numNN_(numNN), discretization_(discretization) {
+  rng_.seed(seed);
+}
+NNFrechet::~NNFrechet() {
+  prgpu_nnf_destroy(handle_);
+  for (ob::State *s : ikStates_)
+    si_->freeState(s);
+}
+
+void NNFrechet::setRefPath(std::vector<Eigen::Isometry3d> &referencePath) {
+  if (referencePath.size() <= 1)
+    throw ompl::Exception("referencePath is empty!");
+  refPath_ = referencePath;
+}
+void NNFrechet::setFKFunc(std::function<Eigen::Isometry3d(ob::State *)> fkFunc) {
+  if (!fkFunc)
+    throw ompl::Exception("Passed FK function is NULL!");
+  fk_ = fkFunc;
+}
+void NNFrechet::setIKFunc(std::function<std::vector<ob::State *>(Eigen::Isometry3d &, int)> ikFunc) {
+  if (!ikFunc)
+    throw ompl::Exception("Passed IK function is NULL!");
+  ik_ = ikFunc;
+}
+void NNFrechet::setDistanceFunc(std::function<double(Eigen::Isometry3d &, Eigen::Isometry3d &)> distanceFunc) {
+  if (!distanceFunc)
+    throw ompl::Exception("Passed task-space distance function is NULL!");
+  dist_ = distanceFunc;
+}
+void NNFrechet::setNumWaypoints(int v) {
+  if (v <= 0)
+    throw ompl::Exception("numWaypoints must be positive!");
+  numWaypoints_ = v;
+}
+void NNFrechet::setIKMultiplier(int v) {
+  if (v <= 0)
+    throw ompl::Exception("ikMultiplier must be positive!");
+  ikMultiplier_ = v;
+}
+void NNFrechet::setNumNN(int v) {
+  if (v <= 0)
+    throw ompl::Exception("numNN must be positive!");
+  numNN_ = v;
+}
+void NNFrechet::setDiscretization(int v) {
+  if (v <= 0)
+    throw ompl::Exception("discretization must be positive!");
+  discretization_ = v;
+}
+void NNFrechet::setRandomSeed(int seed) { rng_.seed(seed); }
+
+void NNFrechet::setProblemDefinition(const ob::ProblemDefinitionPtr &pdef) {
+  ob::Planner::setProblemDefinition(pdef); // start/goal are not used by this planner
+}
+
+std::vector<Eigen::Isometry3d> NNFrechet::subsampleRefPath(const std::vector<Eigen::Isometry3d> &path) const {
+  const int numPts = ((numWaypoints_ - 1) * (discretization_ + 1)) + 1;
+  if (numPts > (int)path.size())
+    throw ompl::Exception("Can't subsample ref path!");
+  // linIntSpace(0, size-1, numPts): truncation of min + i*delta (may stop short of the last pose)
+  const double mn = 0.0, mx = (double)(path.size() - 1);
+  const double delta = (mx - mn) / double(numPts - 1);
+  std::vector<Eigen::Isometry3d> out;
+  for (int i = 0; i < numPts; i++)
+    out.push_back(path[(int)(mn + i * delta)]);
+  return out;
+}
+
+void NNFrechet::setup() {
+  if (refPath_.size() == 0)
+    throw ompl::Exception("Ref path not set!");
+  if (!fk_)
+    throw ompl::Exception("FK function not set!");
+  if (!ik_)
+    throw ompl::Exception("IK function not set!");
+  if (!dist_)
+    throw ompl::Exception("Task-space distance function not set!");
+  if (!world_)
+    throw ompl::Exception("NNFrechet", "device world not set (setWorld)");
+  const auto t0 = std::chrono::steady_clock::now();
+  const int dof = world_->dof();
+  if ((int)space_->getDimension() != dof)
+    throw ompl::Exception("NNFrechet", "state dimension differs from the world's dof");
+
+  refPath_ = subsampleRefPath(refPath_);
+  const int R = (int)refPath_.size();
+
+  // IK budget: both end waypoints get ikMultiplier solutions, the rest of numWaypoints*ikMultiplier
+  // is spread over the interior indices by uniform draws (a fresh distribution object per draw)
+  std::vector<int> want(R, 0);
+  want[0] = ikMultiplier_;
+  want[R - 1] = ikMultiplier_;
+  const int budget = numWaypoints_ * ikMultiplier_ - 2 * ikMultiplier_;
+  for (int i = 0; i < budget; i++) {
+    std::uniform_int_distribution<int> uniform(1, R - 2);
+    want[uniform(rng_)]++;
+  }
+  // IK callback in the reference's call order: first waypoint, last waypoint, then 1..R-2
+  layerCounts_.assign(R, 0);
+  std::vector<double> ik;
+  auto sample = [&](int r) {
+    std::vector<ob::State *> sols = ik_(refPath_[r], want[r]);
+    for (ob::State *s : sols) {
+      const double *v = space_->getValueAddressAtIndex(s, 0);
+      ik.insert(ik.end(), v, v + dof);
+      ikStates_.push_back(s);
+    }
+    layerCounts_[r] = (unsigned)sols.size();
+  };
+  sample(0);
+  sample(R - 1);
+  for (int r = 1; r <= R - 2; ++r)
+    sample(r);
+
+  std::vector<double> ref12((size_t)R * 12);
+  for (int r = 0; r < R; ++r)
+    std::memcpy(ref12.data() + (size_t)r * 12, refPath_[r].data(), 12 * sizeof(double));
+
+  prgpu_nnf_params p;
+  p.num_nn = numNN_;
+  p.discretization = discretization_;
+  p.check_resolution = checkResolution_;
+  prgpu_nnf_destroy(handle_);
+  handle_ = nullptr;
+  check(prgpu_nnf_create(world_->handle(), &p, R, ref12.data(), layerCounts_.data(), ik.data(), &handle_),
+        "NNFrechet::setup");
+  uint32_t nv = 0;
+  check(prgpu_nnf_graph_info(handle_, &nv, nullptr, nullptr), "NNFrechet::setup");
+  vertexStates_.resize((size_t)nv * dof);
+  std::vector<double> pose((size_t)nv * 12);
+  check(prgpu_nnf_get_vertices(handle_, vertexStates_.data(), pose.data()), "NNFrechet::setup");
+
+  // the device model must agree with the user's callbacks
+  if (!ikStates_.empty()) {
+    Eigen::Isometry3d userPose = fk_(ikStates_[0]);
+    double d2 = 0.0;
+    for (int r = 0; r < 3; ++r) {
+      const double diff = userPose(r, 3) - pose[2 * 12 + 4 * r + 3];
+      d2 += diff * diff;
+    }
+    if (std::sqrt(d2) > 1e-9)
+      throw ompl::Exception("NNFrechet", "FK callback and device world disagree on the end-effector position");
+    Eigen::Isometry3d a = refPath_[0], b = userPose;
+    double t2 = 0.0;
+    for (int r = 0; r < 3; ++r)
+      t2 += (a(r, 3) - b(r, 3)) * (a(r, 3) - b(r, 3));
+    if (std::fabs(dist_(a, b) - std::sqrt(t2)) > 1e-9 * (1.0 + std::sqrt(t2)))
+      throw ompl::Exception("NNFrechet", "only the translation-distance task metric is available on the device");
+  }
+  OMPL_INFORM("Tensor Product Graph has been built.");
+  buildTime_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  setup_ = true;
+}
+
+ob::PlannerStatus NNFrechet::solve(const ob::PlannerTerminationCondition &ptc) {
+  if (!handle_)
+    throw ompl::Exception("NNFrechet", "setup() has not been called");
+  const auto t0 = std::chrono::steady_clock::now();
+  bool solutionFound = false;
+  std::vector<uint32_t> path(1u << 16);
+  while (ptc == false) {
+    prgpu_nnf_result res;
+    check(prgpu_nnf_solve(handle_, 8, &res, path.data(), (uint32_t)path.size(), nullptr), "NNFrechet::solve");
+    lazyIters_ += res.lazy_iters;
+    nEvaluated_ = res.n_evaluated;
+    nCollisions_ = res.n_collisions;
+    goalCost_ = res.goal_cost;
+    if (res.lazy_iters)
+      finalError_ = res.final_error;
+    if (res.solved) {
+      solutionFound = true;
+      pathVertices_.assign(path.begin(), path.begin() + res.path_len);
+      break;
+    }
+    if (res.goal_cost >= DBL_MAX) // every path is in collision
+      break;
+  }
+  searchTime_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (solutionFound) {
+    const int dof = world_->dof();
+    auto *out = new ompl::geometric::PathGeometric(si_);
+    ob::State *tmp = si_->allocState();
+    for (unsigned v : pathVertices_) {
+      std::memcpy(space_->getValueAddressAtIndex(tmp, 0), vertexStates_.data() + (size_t)v * dof, dof * sizeof(double));
+      out->append(tmp);
+    }
+    si_->freeState(tmp);
+    pdef_->addSolutionPath(ob::PathPtr(out));
+    OMPL_INFORM("Solution Found!");
+    OMPL_INFORM("Final Frechet Error:    %f", finalError_);
+    OMPL_INFORM("Length of path:    %d", (int)pathVertices_.size());
+    OMPL_INFORM("Total time to init structures:    %f seconds", buildTime_);
+    OMPL_INFORM("Total time to search TPG:    %f seconds", searchTime_);
+    return ob::PlannerStatus::EXACT_SOLUTION;
+  }
+  OMPL_INFORM("Solution NOT Found");
+  return ob::PlannerStatus::TIMEOUT;
+}
+
+ob::PlannerStatus NNFrechet::solve(double solveTime) {
+  return solve(ob::timedPlannerTerminationCondition(solveTime));
+}
+
+} // namespace pr_gpu

@@ -1,10 +1,12 @@
 // Test driver for the OMPL-plugin mirror; see plugin_test_api.h.
 #include "plugin_test_api.h"
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <ompl/base/spaces/RealVectorStateSpace.h>
 #include <ompl/geometric/PathGeometric.h>
 #include <pr_ompl/RRTConnect.h>
+#include <NNFrechet.hpp>
 #include "pr_gpu/BatchedRRTConnect.h"
 #include "pr_gpu/CounterSampler.h"
 #include "pr_gpu/GpuWorld.h"
@@ -185,6 +187,75 @@ int plg_selftest_interfaces(void *worldp, const double *states, uint32_t n, uint
     if (!ok)
       g_err = "interface self-test failed";
     return ok ? 0 : 1;
+  } catch (std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+int plg_nnf_run(void *worldp, int W, int M, int k, int D, int seed, const double *ref_pose12, uint32_t P,
+                const double *ik_states, uint32_t n_ik_available, double solve_seconds, plg_nnf_result *res,
+                uint32_t *layer_counts, uint32_t *path_vertices, uint32_t cap_path, double *path_states) {
+  try {
+    const pr_gpu::GpuWorldPtr &world = *static_cast<pr_gpu::GpuWorldPtr *>(worldp);
+    const int dim = world->dof();
+    std::vector<double> lo(dim, -3.14159265358979323846), hi(dim, 3.14159265358979323846);
+    auto si = makeSpaceInformation(world, dim, lo.data(), hi.data(), 0.01, nullptr);
+    NNFrechet::NNFrechet planner(si, W, M, k, D, seed); // the drop-in name
+    std::vector<Eigen::Isometry3d> ref(P);
+    for (uint32_t i = 0; i < P; ++i)
+      std::memcpy(ref[i].data(), ref_pose12 + (std::size_t)i * 12, 12 * sizeof(double));
+    planner.setRefPath(ref);
+    planner.setWorld(world);
+    planner.setFKFunc([&](ob::State *s) {
+      Eigen::Isometry3d out;
+      double pose[12];
+      pr_gpu::check(prgpu_fk_batch(world->handle(), s->as<ob::RealVectorStateSpace::StateType>()->values, 1, pose),
+                    "fk callback");
+      std::memcpy(out.data(), pose, sizeof(pose));
+      return out;
+    });
+    uint32_t cursor = 0;
+    planner.setIKFunc([&](Eigen::Isometry3d &, int n) {
+      std::vector<ob::State *> out;
+      for (int i = 0; i < n && cursor < n_ik_available; ++i, ++cursor) {
+        ob::State *s = si->allocState();
+        std::memcpy(s->as<ob::RealVectorStateSpace::StateType>()->values, ik_states + (std::size_t)cursor * dim,
+                    sizeof(double) * dim);
+        out.push_back(s);
+      }
+      return out;
+    });
+    planner.setDistanceFunc([](Eigen::Isometry3d &a, Eigen::Isometry3d &b) {
+      double s = 0.0;
+      for (int r = 0; r < 3; ++r)
+        s += (a(r, 3) - b(r, 3)) * (a(r, 3) - b(r, 3));
+      return std::sqrt(s);
+    });
+    auto pdef = std::make_shared<ob::ProblemDefinition>(si);
+    planner.setProblemDefinition(pdef);
+    planner.setup();
+    ob::PlannerStatus st = planner.solve(solve_seconds);
+    std::memset(res, 0, sizeof(*res));
+    res->status = (int32_t)(ob::PlannerStatus::StatusType)st;
+    res->lazy_iters = planner.lazyIterations();
+    res->n_evaluated = planner.evaluatedEdges();
+    res->n_collisions = planner.collidingEdges();
+    res->final_error = planner.finalError();
+    res->goal_cost = planner.goalCost();
+    res->R = (uint32_t)planner.layerCounts().size();
+    for (std::size_t i = 0; i < planner.layerCounts().size(); ++i)
+      layer_counts[i] = planner.layerCounts()[i];
+    res->path_len = (uint32_t)planner.pathVertices().size();
+    for (uint32_t i = 0; i < res->path_len && i < cap_path; ++i)
+      path_vertices[i] = planner.pathVertices()[i];
+    if (pdef->hasSolution()) {
+      const og::PathGeometric *p = pdef->getSolutionPath()->as<og::PathGeometric>();
+      for (uint32_t i = 0; i < p->getStateCount() && i < cap_path; ++i)
+        std::memcpy(path_states + (std::size_t)i * dim,
+                    p->getState(i)->as<ob::RealVectorStateSpace::StateType>()->values, sizeof(double) * dim);
+    }
+    return 0;
   } catch (std::exception &e) {
     g_err = e.what();
     return -1;

@@ -24,6 +24,17 @@ int plg_rrtc_solve(void *world, int dim, const double *lo, const double *hi, con
 /* exercises the OMPL-facing classes directly: returns 0 if every check passes */
 int plg_selftest_interfaces(void *world, const double *states, uint32_t n, uint8_t *is_valid_out,
                             uint8_t *motion_out /* n-1 consecutive edges */, uint32_t *nearest_out /* n */);
+typedef struct {
+  int32_t status;            /* PlannerStatus */
+  uint32_t lazy_iters, n_evaluated, n_collisions, path_len, R;
+  double final_error, goal_cost;
+} plg_nnf_result;
+/* drives NNFrechet::NNFrechet (the drop-in name) through its public API: the reference path is
+ * ref_pose12 (P x 12), the IK callback pops pre-generated solutions (ik_states, in the planner's call
+ * order) -- returns the planner's layer counts, path (NN-graph vertex ids) and path states. */
+int plg_nnf_run(void *world, int W, int M, int k, int D, int seed, const double *ref_pose12, uint32_t P,
+                const double *ik_states, uint32_t n_ik_available, double solve_seconds, plg_nnf_result *res,
+                uint32_t *layer_counts /* R */, uint32_t *path_vertices, uint32_t cap_path, double *path_states);
 #ifdef __cplusplus
 }
 #endif

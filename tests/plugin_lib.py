@@ -13,6 +13,12 @@ class PlgResult(C.Structure):
                 ("n_goal", C.c_uint32), ("path_len", C.c_uint32), ("overflow", C.c_uint32)]
 
 
+class PlgNnfResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("lazy_iters", C.c_uint32), ("n_evaluated", C.c_uint32),
+                ("n_collisions", C.c_uint32), ("path_len", C.c_uint32), ("R", C.c_uint32),
+                ("final_error", C.c_double), ("goal_cost", C.c_double)]
+
+
 _lib = None
 
 
@@ -28,6 +34,8 @@ def lib():
                                      C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.POINTER(PlgResult), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.plg_selftest_interfaces.argtypes = [c_vp, c_vp, C.c_uint32, c_vp, c_vp, c_vp]
+        L.plg_nnf_run.argtypes = [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_uint32, c_vp,
+                                  C.c_uint32, C.c_double, C.POINTER(PlgNnfResult), c_vp, c_vp, C.c_uint32, c_vp]
         _lib = L
     return _lib
 
@@ -86,3 +94,19 @@ class PluginWorld:
         if rc != 0:
             raise RuntimeError(lib().plg_last_error().decode())
         return v, m[:n - 1], nn
+
+    def nnf_run(self, W, M, k, D, seed, ref_pose12, ik_states, solve_seconds=20.0, cap_path=65536):
+        ref = np.ascontiguousarray(ref_pose12, dtype=np.float64).reshape(-1, 12)
+        ik = np.ascontiguousarray(ik_states, dtype=np.float64).reshape(-1, self.dof)
+        R = (W - 1) * (D + 1) + 1
+        res = PlgNnfResult()
+        counts = np.zeros(R, dtype=np.uint32)
+        pv = np.zeros(cap_path, dtype=np.uint32)
+        ps = np.zeros((cap_path, self.dof))
+        rc = lib().plg_nnf_run(self.h, W, M, k, D, seed, _p(ref), len(ref), _p(ik), len(ik), float(solve_seconds),
+                               C.byref(res), _p(counts), _p(pv), cap_path, _p(ps))
+        if rc != 0:
+            raise RuntimeError(lib().plg_last_error().decode())
+        return dict(status=res.status, lazy_iters=res.lazy_iters, n_evaluated=res.n_evaluated,
+                    n_collisions=res.n_collisions, final_error=res.final_error, goal_cost=res.goal_cost,
+                    layer_counts=counts, path=pv[:res.path_len].copy(), path_states=ps[:res.path_len].copy())

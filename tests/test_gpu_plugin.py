@@ -68,3 +68,30 @@ def test_ompl_interfaces(plugin_world, oracle_world, O, synth):
     for i in range(1, 300, 13):
         idx, _ = O.knn(q[:i], q[i:i + 1], 1)
         assert nn[i] == idx[0, 0]
+
+
+def test_nnfrechet_planner_matches_oracle(O, synth, world_arrays):
+    """NNFrechet::NNFrechet (drop-in name) through its public API -- setRefPath / setFKFunc / setIKFunc /
+    setDistanceFunc / setup / solve -- vs the oracle NNF port: same IK budget per waypoint (the
+    std::default_random_engine draws), same path, same Frechet error."""
+    import plugin_lib
+    dh, link, xyzr, _, _ = world_arrays
+    sph, box = synth.obstacles(3, n_spheres=32, n_boxes=32)
+    pw = plugin_lib.PluginWorld(dh, link, xyzr, sph, box)
+    ow = O.World(dh, link, xyzr, sph, box)
+    for seed, W, M, k, D in [(4, 5, 5, 5, 3), (3, 12, 20, 5, 1), (4, 20, 30, 4, 2), (1, 12, 20, 5, 1)]:
+        R = (W - 1) * (D + 1) + 1
+        q, poses = synth.nnf_reference(seed, 2 * R + 5, dh)
+        ids = O.lin_int_space(0, len(q) - 1, R)                 # subsampleRefPath
+        counts = O.nnf_layer_counts(7, R, W, M)                 # planner seed 7
+        ik = synth.nnf_ik_states(2, q[ids], counts)
+        o = O.nnf_run(ow, poses[ids], counts, ik, k=k, D=D, max_lazy_iters=3000, nthreads=8)
+        g = pw.nnf_run(W, M, k, D, 7, poses, ik)                 # full reference path: the planner sub-samples
+        assert np.array_equal(g["layer_counts"], counts)
+        assert (g["status"] == 6) == bool(o["solved"])
+        assert g["lazy_iters"] == o["lazy_iters"]
+        assert (g["n_evaluated"], g["n_collisions"]) == (o["n_evaluated"], o["n_collisions"])
+        assert np.array_equal(g["path"], o["path"])
+        if o["solved"]:
+            assert abs(g["final_error"] - o["final_error"]) <= 1e-5 * o["final_error"]
+            assert np.array_equal(g["path_states"], o["states"][o["path"]])
