@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="knn", choices=["knn", "check_motion", "rrtc"])
+    ap.add_argument("--workload", default="knn", choices=["knn", "check_motion", "rrtc", "nnf"])
     ap.add_argument("--nodes", type=int, default=10_000_000)
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--k", type=int, default=16)
@@ -583,11 +583,100 @@ def cpu_baseline(args, synth):
                       f"exit over the double-precision synthetic checker, {cores} threads"}
 
 
+def nnf_problem(synth, dh, W, M, D, tseed=5):
+    """NNF config of BASELINE.json: W waypoints, M IK samples per layer (multinomial over the interior
+    layers), synthetic IK = trajectory configuration + N(0, 0.15^2) joint noise."""
+    import numpy as np
+    R = (W - 1) * (D + 1) + 1
+    q, poses = synth.nnf_reference(tseed, 2 * R + 5, dh)
+    ids = synth.lin_int_space(0, len(q) - 1, R)
+    rng = np.random.default_rng(1)
+    counts = np.zeros(R, dtype=np.uint32)
+    counts[0] = counts[-1] = M
+    counts[1:-1] += np.bincount(rng.integers(1, R - 1, W * M - 2 * M), minlength=R)[1:-1].astype(np.uint32)
+    ik = synth.nnf_ik_states(2, q[ids], counts)
+    return poses[ids], counts, ik
+
+
+def run_nnf(args, rank, local_rank, world):
+    """NNF Frechet following (BASELINE.json configs[3]): W=200 waypoints, 1024 IK samples per layer, k=5,
+    D=1, 16+16 obstacles.  Replicas only: every rank plans the same problem; rank 0 reports.
+    A step is one LazySP iteration (bottleneck search + path extraction + edge evaluation + knock-out)."""
+    import numpy as np
+    import torch
+    import prgpu_loader
+    P = prgpu_loader.load()
+    synth = P.synth
+    torch.cuda.set_device(local_rank)
+    dh, link, xyzr = synth.default_arm()
+    sph, box = synth.obstacles(3, n_spheres=16, n_boxes=16)
+    gw = P.World(dh, link, xyzr, sph, box, device=local_rank)
+    W, M, k, D = 200, 1024, 5, 1
+    ref, counts, ik = nnf_problem(synth, dh, W, M, D)
+    t0 = time.perf_counter()
+    g = P.Nnf(gw, ref, counts, ik, num_nn=k, discretization=D)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r = g.solve(max_lazy_iters=20000)
+    solve_s = time.perf_counter() - t0
+    if rank != 0:
+        return
+    hbm_peak, peak_src = peaks()
+    info = g.band_info()
+    dp_ms = g.last_dp_ms()
+    algo = info["cells"] * (8 + 8 * 4)  # band cells x (write + ~4 reads), DESIGN.md K3
+    line = {
+        "metric": "NNF LazySP searches/s", "value": r["lazy_iters"] / solve_s, "unit": "searches/s", "n_gpus": 1,
+        "steps": int(r["lazy_iters"]), "warmup": 0, "ms_per_step": solve_s / max(1, r["lazy_iters"]) * 1e3,
+        "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"NNF Frechet following: W={W} waypoints, {M} IK samples per layer, k={k}, D={D}, 7-DOF "
+                               f"arm, 32 obstacles (BASELINE.json configs[3]); R={len(ref)}, "
+                               f"{g.n_vertices} NN vertices, {len(ref) * g.n_vertices:.3g} TPG cells",
+                   "setup_s": setup_s, "solve_s": solve_s, "solved": int(r["solved"]),
+                   "final_frechet_error": r["final_error"], "edges_evaluated": int(r["n_evaluated"]),
+                   "edges_in_collision": int(r["n_collisions"]), "band": info},
+        "roofline": {"bound": "hbm", "achieved": algo / (dp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": algo / (dp_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic("nnf_band_dp_kernel"),
+                     "kernel": "nnf_band_dp_kernel", "kernel_ms": dp_ms, "peak_source": peak_src,
+                     "note": "latency-bound by the NN-graph level count (one cluster barrier per level), see DESIGN.md"},
+        "e2e": {"value": 1.0 / (setup_s + solve_s), "unit": "plans/s (setup + solve, host inputs)",
+                "h2d_bytes_per_step": int(ik.nbytes + ref.nbytes), "d2h_bytes_per_step": int(g.n_vertices * 19 * 8)},
+        "gpu_launches": int(3 * r["lazy_iters"]), "clocks": None,
+    }
+    if not args.no_cpu_baseline:
+        import oracle_lib as O
+        O.build()
+        ow = O.World(dh, link, xyzr, sph, box)
+        Ws, Ms = 50, 256
+        refs, cs, iks = nnf_problem(synth, dh, Ws, Ms, D)
+        cores = host_cores()
+        t0 = time.perf_counter()
+        o = O.nnf_run(ow, refs, cs, iks, k=k, D=D, max_lazy_iters=40, nthreads=cores)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": o["lazy_iters"] / dt, "unit": "searches/s (incl. setup)", "cores": cores,
+                                "kind": "port",
+                                "sample": f"REDUCED problem W={Ws}, M={Ms} ({len(refs) * o['n_vertices']:.3g} TPG cells, "
+                                          f"{len(ref) * g.n_vertices / (len(refs) * o['n_vertices']):.0f}x fewer than the GPU run), "
+                                          f"{o['lazy_iters']} LazySP iterations of the oracle port incl. its setup; the "
+                                          f"full-size CPU run does not finish in minutes"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "nnf":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "NNF reference arm: the literal frechet/ sources "
+                                  "need Boost.Graph and Eigen (absent); see cpu_baseline of --workload nnf"}))
+            return
+        run_nnf(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -9,10 +9,12 @@ what = sys.argv[1]
 if what == "nnf":
     W, M, k, D = int(sys.argv[2]), int(sys.argv[3]), 5, int(sys.argv[4])
     iters = int(sys.argv[5])
-    sph, box = synth.obstacles(3, n_spheres=32, n_boxes=32)
+    nobs = int(os.environ.get("NOBS", "32")); tseed = int(os.environ.get("TSEED", "4"))
+    sph, box = synth.obstacles(3, n_spheres=nobs, n_boxes=nobs)
     gw = P.World(dh, link, xyzr, sph, box)
     R = (W - 1) * (D + 1) + 1
-    q, poses = synth.nnf_reference(4, 2 * R + 5, dh)
+    q, poses = synth.nnf_reference(tseed, 2 * R + 5, dh)
+    print('traj valid frac', gw.is_valid_batch(q).mean())
     ids = synth.lin_int_space(0, len(q) - 1, R)
     rng = np.random.default_rng(1)
     counts = np.zeros(R, dtype=np.uint32); counts[0] = counts[-1] = M
