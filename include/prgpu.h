@@ -219,8 +219,9 @@ int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12);
 int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *res, uint32_t *path_vertices,
                     uint32_t cap_path, double *goal_cost_trace);
 /* search kernel: 0 (default) = banded column-wise DP (only cells that can lie on a path of cost
- * <= tau are stored; tau is widened until the optimum is provably inside), 1 = full R x V table
- * swept by anti-diagonals.  Both return identical costs and paths. */
+ * <= tau are stored; tau is widened until the optimum is provably inside) executed as a dataflow
+ * over per-vertex ready flags; 1 = full R x V table swept by anti-diagonals; 2 = the banded DP swept
+ * level by level by one thread-block cluster.  All return identical costs and paths. */
 int prgpu_nnf_set_mode(prgpu_nnf_t *h, int mode);
 int prgpu_nnf_band_info(prgpu_nnf_t *h, double *tau, uint64_t *cells, uint32_t *rebuilds);
 /* duration of the latest search kernel (measurement aid, always on) */

@@ -34,7 +34,10 @@ struct prgpu_nnf {
   NnfGraphDev g;
   KernelTimer timer;
   // banded form
-  int mode = 0;                 // 0 banded column-wise DP (default), 1 full-table wavefront
+  int mode = 0;                 // 0 banded dataflow DP (default), 1 full-table wavefront, 2 banded + cluster barriers
+  std::vector<uint32_t> lvl_start_host;
+  DevBuf d_done;
+  uint32_t epoch = 0;
   std::vector<uint32_t> level_of_vertex, slot_of_eid;
   DevBuf d_band_lo, d_band_w, d_col_off, d_meta, d_edge, d_Bc, d_scan_tmp, d_rowmin;
   NnfBandDev bg;
@@ -126,8 +129,8 @@ int nnf_initial_tau(prgpu_nnf *h, cudaStream_t s) {
 extern "C" {
 
 int prgpu_nnf_set_mode(prgpu_nnf_t *h, int mode) {
-  if (!h || (mode != 0 && mode != 1))
-    return fail(PRGPU_EINVAL, "nnf_set_mode: mode must be 0 (banded) or 1 (full table)");
+  if (!h || mode < 0 || mode > 2)
+    return fail(PRGPU_EINVAL, "nnf_set_mode: mode must be 0 (banded dataflow), 1 (full table) or 2 (banded, cluster barriers)");
   h->mode = mode;
   h->dirty_level = 0; // the other mode's table may be stale
   return PRGPU_OK;
@@ -153,7 +156,7 @@ int prgpu_nnf_destroy(prgpu_nnf_t *h) {
   for (DevBuf *b : {&h->d_states, &h->d_pose, &h->d_lvl_start, &h->d_level, &h->d_pred_off, &h->d_pred_pos,
                     &h->d_pred_eid, &h->d_blocked, &h->d_pnn, &h->d_pref, &h->d_B, &h->d_path, &h->d_pn, &h->d_cost,
                     &h->d_band_lo, &h->d_band_w, &h->d_col_off, &h->d_meta, &h->d_edge, &h->d_Bc, &h->d_scan_tmp,
-                    &h->d_rowmin})
+                    &h->d_rowmin, &h->d_done})
     b->release();
   h->timer.destroy();
   delete h;
@@ -417,6 +420,7 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
     }
   }
   h->level_of_vertex = level;
+  h->lvl_start_host = lvl_start;
   h->slot_of_eid.assign(E, 0);
   for (uint32_t o = 0; o < E; ++o)
     h->slot_of_eid[pred_eid[o]] = o;
@@ -455,6 +459,8 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
   NNF_TRY(h->d_meta.reserve((size_t)V * sizeof(NnfVertexMeta)));
   NNF_TRY(h->d_edge.reserve(std::max<size_t>((size_t)E * sizeof(NnfEdgeRec), 16)));
   NNF_TRY(h->d_rowmin.reserve((size_t)R * 8));
+  NNF_TRY(h->d_done.reserve((size_t)V * 4));
+  NNF_CUDA(cudaMemsetAsync(h->d_done.p, 0, (size_t)V * 4, s));
   NNF_TRY(h->d_path.reserve(((size_t)R + Lv + 8) * 2 * 4));
   NNF_TRY(h->d_pn.reserve(16));
   NNF_TRY(h->d_cost.reserve(16));
@@ -575,7 +581,11 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
           return rc;
       }
       while (true) {
-        rc = nnf_band_dp_launch(h->bg, h->dirty_level, s, &h->timer);
+        if (h->mode == 2)
+          rc = nnf_band_dp_launch(h->bg, h->dirty_level, s, &h->timer);
+        else
+          rc = nnf_flow_dp_launch(h->bg, h->dirty_level >= h->Lv ? h->V : h->lvl_start_host[h->dirty_level],
+                                  ++h->epoch, h->d_done.as<uint32_t>(), h->world->sm_count, s, &h->timer);
         if (rc != PRGPU_OK)
           return rc;
         h->dirty_level = h->Lv; // table consistent

@@ -316,6 +316,90 @@ __global__ void __launch_bounds__(BAND_THREADS) nnf_band_dp_kernel(const NnfBand
   }
 }
 
+// Dataflow form of the same banded sweep: no barriers at all.  Warps of one cooperative (co-resident)
+// grid take the vertices in level-sorted order; a warp waits only for the "done" flags of its own
+// vertex's predecessors (which sit earlier in that order, hence belong to warps that are running),
+// computes the column, publishes it and raises the vertex's flag.  The critical path is the chain of
+// dependent vertices (one flag + one gather round trip per NN-graph level) instead of one grid- or
+// cluster-wide barrier per level, and every SM takes part.
+constexpr int FLOW_THREADS = 256;
+__global__ void __launch_bounds__(FLOW_THREADS)
+nnf_flow_dp_kernel(const NnfBandDev g, uint32_t first_pos, uint32_t epoch, volatile uint32_t *done) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = blockIdx.x * (FLOW_THREADS / 32) + (threadIdx.x >> 5);
+  const uint32_t nwarps = gridDim.x * (FLOW_THREADS / 32);
+  for (uint32_t s = first_pos + warp; s < g.V; s += nwarps) {
+    const NnfVertexMeta m = g.meta[s];
+    if (m.band_w != 0) {
+      // wait until every (non-blocked) predecessor that is being recomputed has published its column
+      for (uint32_t e0 = m.pred_begin; e0 < m.pred_end; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        if (e < m.pred_end && !(g.edge[e].band_w_blocked & 0x80000000u)) {
+          const uint32_t p = g.pred_pos[e];
+          if (p >= first_pos) {
+            unsigned ns = 32;
+            while (done[p] != epoch) {
+              __nanosleep(ns);
+              if (ns < 256)
+                ns *= 2;
+            }
+          }
+        }
+      }
+      __threadfence(); // acquire: the columns behind the flags
+      __syncwarp();
+      const double px = g.pnn[3 * (size_t)s], py = g.pnn[3 * (size_t)s + 1], pz = g.pnn[3 * (size_t)s + 2];
+      double carry = NNF_INF;
+      for (uint32_t c0 = 0; c0 < m.band_w; c0 += 32) {
+        const bool active = c0 + lane < m.band_w;
+        const uint32_t r = m.band_lo + c0 + lane;
+        Clamp gfn;
+        gfn.a = -NNF_INF;
+        gfn.b = NNF_INF;
+        if (active) {
+          double mm = NNF_INF;
+          for (uint32_t e = m.pred_begin; e < m.pred_end; ++e) {
+            const NnfEdgeRec rec = g.edge[e];
+            if (rec.band_w_blocked & 0x80000000u)
+              continue;
+            const uint32_t pw = rec.band_w_blocked;
+            const uint32_t i0 = r - rec.band_lo;
+            if (i0 < pw)
+              mm = fmin(mm, __ldcg(g.Bc + rec.col_off + i0));
+            const uint32_t i1 = i0 - 1u;
+            if (r > 0 && i1 < pw)
+              mm = fmin(mm, __ldcg(g.Bc + rec.col_off + i1));
+          }
+          const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
+                       dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
+          const double f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+          gfn.a = f;
+          gfn.b = fmax(f, mm);
+          if (s == g.start_pos && r == 0)
+            gfn.a = gfn.b = 0.0;
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          Clamp lower;
+          lower.a = __shfl_up_sync(0xffffffffu, gfn.a, off);
+          lower.b = __shfl_up_sync(0xffffffffu, gfn.b, off);
+          if ((int)lane >= off)
+            gfn = compose(gfn, lower);
+        }
+        const double x = fmax(gfn.a, fmin(carry, gfn.b));
+        if (active)
+          __stcg(g.Bc + m.col_off + c0 + lane, x);
+        const uint32_t last = min(31u, m.band_w - c0 - 1u);
+        carry = __shfl_sync(0xffffffffu, x, last);
+      }
+      __threadfence(); // release: the column before the flag
+    }
+    __syncwarp();
+    if (lane == 0)
+      done[s] = epoch;
+  }
+}
+
 __device__ __forceinline__ double band_get(const NnfBandDev &g, uint32_t r, uint32_t s) {
   const NnfVertexMeta m = g.meta[s];
   const uint32_t i = r - m.band_lo;
@@ -494,6 +578,26 @@ int nnf_band_dp_launch(const NnfBandDev &g, uint32_t first_level, cudaStream_t s
   if (timer)
     timer->begin(stream);
   PRGPU_CUDA_TRY(cudaLaunchKernelEx(&cfg, nnf_band_dp_kernel, g, first_level));
+  if (timer)
+    timer->end(stream);
+  return PRGPU_OK;
+}
+
+int nnf_flow_dp_launch(const NnfBandDev &g, uint32_t first_pos, uint32_t epoch, uint32_t *done, int sm_count,
+                       cudaStream_t stream, KernelTimer *timer) {
+  int per_sm = 0;
+  PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nnf_flow_dp_kernel, FLOW_THREADS, 0));
+  if (per_sm < 1)
+    return fail(PRGPU_ECUDA, "nnf_flow_dp_kernel cannot be made resident");
+  if (per_sm > 4)
+    per_sm = 4;
+  dim3 grid((unsigned)(per_sm * sm_count)), block(FLOW_THREADS);
+  NnfBandDev arg = g;
+  void *args[] = {&arg, &first_pos, &epoch, &done};
+  if (timer)
+    timer->begin(stream);
+  // cooperative launch: guarantees that all blocks are co-resident (warps wait on one another's flags)
+  PRGPU_CUDA_TRY(cudaLaunchCooperativeKernel((void *)nnf_flow_dp_kernel, grid, block, args, 0, stream));
   if (timer)
     timer->end(stream);
   return PRGPU_OK;

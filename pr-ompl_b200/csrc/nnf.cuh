@@ -54,6 +54,8 @@ int nnf_band_pack_launch(uint32_t V, uint32_t E, const uint32_t *band_lo, const 
                          const uint32_t *pred_eid, const uint8_t *blocked, NnfVertexMeta *meta, NnfEdgeRec *edge,
                          cudaStream_t stream);
 int nnf_band_dp_launch(const NnfBandDev &g, uint32_t first_level, cudaStream_t stream, KernelTimer *timer);
+int nnf_flow_dp_launch(const NnfBandDev &g, uint32_t first_pos, uint32_t epoch, uint32_t *done, int sm_count,
+                       cudaStream_t stream, KernelTimer *timer);
 int nnf_band_backtrack_launch(const NnfBandDev &g, uint32_t *out_path, uint32_t cap_pairs, uint32_t *out_n,
                               double *out_cost, cudaStream_t stream);
 int nnf_exclusive_scan_u64(const unsigned long long *in, unsigned long long *out, uint32_t n, void *temp,

@@ -25,7 +25,7 @@ def _problem(O, synth, dh, seed, W, M, D):
     return poses[ids], counts, ik
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("seed,W,M,k,D", [(4, 5, 5, 5, 3), (3, 12, 20, 5, 1), (4, 20, 30, 4, 2), (1, 12, 20, 5, 1),
                                           (2, 8, 6, 3, 1), (4, 30, 40, 5, 1)])
 def test_nnf_matches_oracle(P, O, synth, nnf_worlds, seed, W, M, k, D, mode):
@@ -77,18 +77,19 @@ def test_nnf_banded_equals_full_at_scale(P, O, synth, nnf_worlds):
     dh, gw, _ = nnf_worlds
     ref, counts, ik = _problem(O, synth, dh, 4, 40, 128, 1)
     out = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         g = P.Nnf(gw, ref, counts, ik, num_nn=5, discretization=1)
         g.set_mode(mode)
         out.append(g.solve(max_lazy_iters=60))
-        if mode == 0:
+        if mode != 1:
             info = g.band_info()
             assert 0 < info["cells"] < len(ref) * g.n_vertices   # the band is a strict subset
-    a, b = out
-    assert np.array_equal(a["goal_cost_trace"], b["goal_cost_trace"])
-    assert (a["lazy_iters"], a["n_evaluated"], a["n_collisions"], a["solved"]) == \
-           (b["lazy_iters"], b["n_evaluated"], b["n_collisions"], b["solved"])
-    assert np.array_equal(a["path"], b["path"]) and a["final_error"] == b["final_error"]
+    a = out[0]
+    for b in out[1:]:
+        assert np.array_equal(a["goal_cost_trace"], b["goal_cost_trace"])
+        assert (a["lazy_iters"], a["n_evaluated"], a["n_collisions"], a["solved"]) == \
+               (b["lazy_iters"], b["n_evaluated"], b["n_collisions"], b["solved"])
+        assert np.array_equal(a["path"], b["path"]) and a["final_error"] == b["final_error"]
 
 
 def test_nnf_bad_params(P, synth, nnf_worlds):
