@@ -386,11 +386,11 @@ def run_ours(args, rank, local_rank, world):
             if record:
                 kernel_ms.append(world_h.last_kernel_ms())
 
-        launches_per_step = 1
+        launches_per_step = 5  # phase A, scan (2 kernels), expand, phase B
         units_per_step = E  # all ranks together
         metric, unit = "validated edges/s", "edges/s"
         algo_bytes = n_local * (2 * 56 + 1)
-        kernel_name = "check_motion_kernel"
+        kernel_name = "cm_phase_a_kernel+cm_phase_b_kernel"
         config = {
             "workload": f"batched checkMotion: {E} edges at 0.01 rad, 7-DOF sphere-FK arm (16 link spheres) "
                         f"vs 256 obstacles (BASELINE.json configs[2]); edge length ~U(0,1] rad",
@@ -638,9 +638,9 @@ def run_nnf(args, rank, local_rank, world):
                    "final_frechet_error": r["final_error"], "edges_evaluated": int(r["n_evaluated"]),
                    "edges_in_collision": int(r["n_collisions"]), "band": info},
         "roofline": {"bound": "hbm", "achieved": algo / (dp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": algo / (dp_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic("nnf_band_dp_kernel"),
-                     "kernel": "nnf_band_dp_kernel", "kernel_ms": dp_ms, "peak_source": peak_src,
-                     "note": "latency-bound by the NN-graph level count (one cluster barrier per level), see DESIGN.md"},
+                     "frac": algo / (dp_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic("nnf_flow_dp_kernel"),
+                     "kernel": "nnf_flow_dp_kernel", "kernel_ms": dp_ms, "peak_source": peak_src,
+                     "note": "last (incremental) search of the LazySP loop; latency-bound by the chain of dependent NN-graph levels, see DESIGN.md"},
         "e2e": {"value": 1.0 / (setup_s + solve_s), "unit": "plans/s (setup + solve, host inputs)",
                 "h2d_bytes_per_step": int(ik.nbytes + ref.nbytes), "d2h_bytes_per_step": int(g.n_vertices * 19 * 8)},
         "gpu_launches": int(3 * r["lazy_iters"]), "clocks": None,
