@@ -264,27 +264,35 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
 
 // Pass 2: full scan.  A node is a candidate of query q iff key(q, node) <= T_q (the threshold from
 // the sample pass) and node >= lo_q; candidates are appended to the query's global buffer.  The hot
-// loop is 7 FFMA + a compare per pair with the node tile broadcast from shared memory to RQ
-// queries per thread; nothing else is maintained.
+// loop holds no per-query state besides the threshold.  Each tile (one bulk copy of 32-byte node
+// records) is re-laid in shared memory as node PAIRS, coordinate-interleaved, so that one packed
+// fma.rn.f32x2 (FFMA2, sm_100) advances the keys of two nodes for one query: 3.5 issue slots per
+// (query, node) pair instead of 7, with the pair tile broadcast to 4 queries per thread.
+constexpr int CT_TILE = 256; // nodes per tile of the collect kernel
+
 template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS)
 knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
                    const uint32_t *__restrict__ lo, const float *__restrict__ thresh, uint32_t tiles_per_chunk,
                    uint32_t cap, uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
+  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][CT_TILE][2]   node records
+  float4 *pairs = tile + 2 * CT_TILE * 2;                                  // [CT_TILE/2][4]    pair records
+  uint64_t *bars = reinterpret_cast<uint64_t *>(pairs + (CT_TILE / 2) * 4); // [2]
   __shared__ uint32_t s_lo_min;
   const int tid = threadIdx.x;
   uint32_t qid[FT_RQ], my_lo[FT_RQ];
-  float q2[FT_RQ][7], thr[FT_RQ];
+  float2 q2[FT_RQ][7]; // (-2 q_d, -2 q_d)
+  float thr[FT_RQ];
 #pragma unroll
   for (int u = 0; u < FT_RQ; ++u) {
     qid[u] = (blockIdx.x * FT_RQ + u) * FT_THREADS + tid;
     const bool act = qid[u] < nq;
 #pragma unroll
-    for (int d = 0; d < 7; ++d)
-      q2[u][d] = (act && d < DIM) ? (float)(-2.0 * queries[(size_t)qid[u] * DIM + d]) : 0.f;
+    for (int d = 0; d < 7; ++d) {
+      const float v = (act && d < DIM) ? (float)(-2.0 * queries[(size_t)qid[u] * DIM + d]) : 0.f;
+      q2[u][d] = make_float2(v, v);
+    }
     my_lo[u] = (act && lo) ? lo[qid[u]] : (act ? 0u : 0xFFFFFFFFu);
     thr[u] = act ? thresh[qid[u]] : -CUDART_INF_F;
   }
@@ -299,32 +307,33 @@ knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__r
   for (int u = 0; u < FT_RQ; ++u)
     atomicMin(&s_lo_min, my_lo[u]);
   __syncthreads();
-  const uint32_t ntiles = (n + FT_TILE - 1) / FT_TILE;
+  const uint32_t ntiles = (n + CT_TILE - 1) / CT_TILE;
   uint32_t t0 = blockIdx.y * tiles_per_chunk;
   const uint32_t t1 = min(t0 + tiles_per_chunk, ntiles);
   if (s_lo_min != 0xFFFFFFFFu)
-    t0 = max(t0, s_lo_min / FT_TILE);
+    t0 = max(t0, s_lo_min / CT_TILE);
   auto issue = [&](uint32_t t, int buf) {
-    mbar_expect_tx(&bars[buf], FT_TILE * 32);
-    bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
-  };
-  auto key_of = [&](int u, const float4 &a, const float4 &b) {
-    float acc = b.w; // |x|^2
-    acc = fmaf(q2[u][0], a.x, acc);
-    if (DIM > 1) acc = fmaf(q2[u][1], a.y, acc);
-    if (DIM > 2) acc = fmaf(q2[u][2], a.z, acc);
-    if (DIM > 3) acc = fmaf(q2[u][3], a.w, acc);
-    if (DIM > 4) acc = fmaf(q2[u][4], b.x, acc);
-    if (DIM > 5) acc = fmaf(q2[u][5], b.y, acc);
-    if (DIM > 6) acc = fmaf(q2[u][6], b.z, acc);
-    return acc;
+    mbar_expect_tx(&bars[buf], CT_TILE * 32);
+    bulk_g2s(tile + buf * CT_TILE * 2, ptsf + (size_t)t * CT_TILE * 8, CT_TILE * 32, &bars[buf]);
   };
   auto emit = [&](int u, float key, uint32_t gi) {
-    if (key <= thr[u] && gi >= my_lo[u]) {
+    if (key <= thr[u] && gi >= my_lo[u] && gi < n) {
       const uint32_t slot = atomicAdd(cand_count + qid[u], 1u);
       if (slot < cap)
         cand_idx[(size_t)qid[u] * cap + slot] = gi;
     }
+  };
+  // keys of the node pair whose record is (v0..v3) for query slot u
+  auto keys_of = [&](int u, const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3) {
+    float2 acc = make_float2(v3.z, v3.w); // (|x_a|^2, |x_b|^2)
+    acc = __ffma2_rn(q2[u][0], make_float2(v0.x, v0.y), acc);
+    if (DIM > 1) acc = __ffma2_rn(q2[u][1], make_float2(v0.z, v0.w), acc);
+    if (DIM > 2) acc = __ffma2_rn(q2[u][2], make_float2(v1.x, v1.y), acc);
+    if (DIM > 3) acc = __ffma2_rn(q2[u][3], make_float2(v1.z, v1.w), acc);
+    if (DIM > 4) acc = __ffma2_rn(q2[u][4], make_float2(v2.x, v2.y), acc);
+    if (DIM > 5) acc = __ffma2_rn(q2[u][5], make_float2(v2.z, v2.w), acc);
+    if (DIM > 6) acc = __ffma2_rn(q2[u][6], make_float2(v3.x, v3.y), acc);
+    return acc;
   };
   if (tid == 0 && t0 < t1)
     issue(t0, 0);
@@ -334,29 +343,44 @@ knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__r
     if (tid == 0 && t + 1 < t1)
       issue(t + 1, buf ^ 1);
     mbar_wait(&bars[buf], parity);
-    const float4 *T = tile + buf * FT_TILE * 2;
-    const uint32_t base = t * FT_TILE;
-    const uint32_t jmax = min((uint32_t)FT_TILE, n - base);
-    uint32_t j = 0;
-    for (; j + 3 < jmax; j += 4) {
-      const float4 a0 = T[2 * j], b0 = T[2 * j + 1], a1 = T[2 * j + 2], b1 = T[2 * j + 3];
-      const float4 a2 = T[2 * j + 4], b2 = T[2 * j + 5], a3 = T[2 * j + 6], b3 = T[2 * j + 7];
+    // node records -> pair records: (x0a,x0b,x1a,x1b) (x2a,x2b,x3a,x3b) (x4a,x4b,x5a,x5b) (x6a,x6b,n2a,n2b)
+    {
+      const float4 *T = tile + buf * CT_TILE * 2;
+#pragma unroll
+      for (int it = 0; it < (CT_TILE / 2 * 2) / FT_THREADS; ++it) {
+        const int w = it * FT_THREADS + tid; // (pair, half)
+        const int p = w >> 1, h = w & 1;
+        const float4 a = T[2 * (2 * p) + h], b = T[2 * (2 * p + 1) + h];
+        pairs[4 * p + 2 * h] = make_float4(a.x, b.x, a.y, b.y);
+        pairs[4 * p + 2 * h + 1] = make_float4(a.z, b.z, a.w, b.w);
+      }
+    }
+    __syncthreads();
+    const uint32_t base = t * CT_TILE;
+    const uint32_t npair = (min((uint32_t)CT_TILE, n - base) + 1) / 2;
+    uint32_t p = 0;
+    for (; p + 1 < npair; p += 2) {
+      const float4 a0 = pairs[4 * p], a1 = pairs[4 * p + 1], a2 = pairs[4 * p + 2], a3 = pairs[4 * p + 3];
+      const float4 b0 = pairs[4 * p + 4], b1 = pairs[4 * p + 5], b2 = pairs[4 * p + 6], b3 = pairs[4 * p + 7];
 #pragma unroll
       for (int u = 0; u < FT_RQ; ++u) {
-        const float k0 = key_of(u, a0, b0), k1 = key_of(u, a1, b1), k2 = key_of(u, a2, b2), k3 = key_of(u, a3, b3);
-        if (fminf(fminf(k0, k1), fminf(k2, k3)) <= thr[u]) {
-          emit(u, k0, base + j);
-          emit(u, k1, base + j + 1);
-          emit(u, k2, base + j + 2);
-          emit(u, k3, base + j + 3);
+        const float2 ka = keys_of(u, a0, a1, a2, a3), kb = keys_of(u, b0, b1, b2, b3);
+        if (fminf(fminf(ka.x, ka.y), fminf(kb.x, kb.y)) <= thr[u]) {
+          emit(u, ka.x, base + 2 * p);
+          emit(u, ka.y, base + 2 * p + 1);
+          emit(u, kb.x, base + 2 * p + 2);
+          emit(u, kb.y, base + 2 * p + 3);
         }
       }
     }
-    for (; j < jmax; ++j) {
-      const float4 a0 = T[2 * j], b0 = T[2 * j + 1];
+    for (; p < npair; ++p) {
+      const float4 a0 = pairs[4 * p], a1 = pairs[4 * p + 1], a2 = pairs[4 * p + 2], a3 = pairs[4 * p + 3];
 #pragma unroll
-      for (int u = 0; u < FT_RQ; ++u)
-        emit(u, key_of(u, a0, b0), base + j);
+      for (int u = 0; u < FT_RQ; ++u) {
+        const float2 ka = keys_of(u, a0, a1, a2, a3);
+        emit(u, ka.x, base + 2 * p);
+        emit(u, ka.y, base + 2 * p + 1);
+      }
     }
     __syncthreads();
   }
@@ -571,17 +595,19 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   PRGPU_CUDA_TRY(cudaGetLastError());
 
   // ---- pass 2: full scan collecting every node at or below the threshold ----
-  const size_t smem2 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t);
+  const size_t smem2 = (size_t)2 * CT_TILE * 32 + (size_t)(CT_TILE / 2) * 64 + 2 * sizeof(uint64_t);
   auto coll = knn_collect_kernel<DIM>;
   int per_sm = 0;
+  PRGPU_CUDA_TRY(cudaFuncSetAttribute(coll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coll, FT_THREADS, smem2));
   per_sm = per_sm > 0 ? per_sm : 1;
+  const uint32_t ntiles2 = (t.n + CT_TILE - 1) / CT_TILE;
   uint32_t chunks = (uint32_t)(per_sm * sm_count) / qblocks;
   chunks = chunks < 1 ? 1 : chunks;
-  if (chunks > ntiles)
-    chunks = ntiles;
-  const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
-  chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+  if (chunks > ntiles2)
+    chunks = ntiles2;
+  const uint32_t tiles_per_chunk = (ntiles2 + chunks - 1) / chunks;
+  chunks = (ntiles2 + tiles_per_chunk - 1) / tiles_per_chunk;
   if (timer)
     timer->begin(stream);
   coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf, t.n, queries, nq, lo, thresh, tiles_per_chunk, cap,
