@@ -40,7 +40,7 @@ struct KnnTreeView {
   uint32_t index_base;
 };
 
-constexpr int KNN_FILTER_MARGIN = 8;   // extra candidates kept by the fp32 filter pass
+constexpr int KNN_FILTER_MARGIN = 2;   // the threshold is the (k+2)-th smallest key of the sample
 constexpr int KNN_FILTER_MAX_K = 16;   // k + margin + the 8-entry candidate buffer must fit one warp
 
 // exact search (always bit-identical to the reference); knn_search picks the filter path

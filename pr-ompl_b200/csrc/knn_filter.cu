@@ -5,10 +5,10 @@
 // (>= 128 queries per tree pass, k <= 24) almost all of that work only establishes that a node is
 // NOT among the k nearest.  This path does that part in fp32:
 //   key(q,x) = |x|^2 - 2 q.x  (= |q-x|^2 - |q|^2) from an fp32 mirror of the tree (8 floats per node).
-//   1. knn_filter_kernel on every 64th tile: T_q = (k+8)-th smallest key of the sample, an upper
-//      bound of the (k+8)-th smallest key of the whole tree.
+//   1. knn_filter_kernel on every 64th tile: T_q = (k+2)-th smallest key of the sample, an upper
+//      bound of the (k+2)-th smallest key of the whole tree.
 //   2. knn_collect_kernel: one pass over the tree, 7 FFMA + 1 compare per pair, each node tile
-//      broadcast from shared memory to 4 queries per thread; nodes with key <= T_q (~ (k+8)*64 per
+//      broadcast from shared memory to 4 queries per thread; nodes with key <= T_q (~ (k+2)*64 per
 //      query) are appended to the query's candidate buffer.  No per-query state is updated in the loop.
 //   3. knn_select_kernel: one block per query recomputes the reference's exact fp64 distance of the
 //      candidates, selects the k first under (distance, index) -- and PROVES that no discarded node
