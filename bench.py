@@ -280,7 +280,25 @@ def run_ours(args, rank, local_rank, world):
         def merge(gi_, gd_, nparts, nq_, k_, fi_, fd_):
             P.topk_merge_device(local_rank, gi_, gd_, nparts, nq_, k_, fi_, fd_, stream)
 
+        trace = os.environ.get("PRGPU_BENCH_TRACE") == "1"
+
         def step(record=False):
+            if trace and record:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+                local_search(q_dev, Q, k, idx, dd)
+                ev[1].record()
+                if world > 1:
+                    dist.all_gather_into_tensor(gi.view(world * Q, k), idx)
+                    dist.all_gather_into_tensor(gd.view(world * Q, k), dd)
+                    merge(gi, gd, world, Q, k, fi, fd)
+                ev[2].record()
+                torch.cuda.synchronize()
+                print(f"[rank {rank}] local search {ev[0].elapsed_time(ev[1]):.3f} ms, gather+merge "
+                      f"{ev[1].elapsed_time(ev[2]):.3f} ms, dominant kernel {tree.last_kernel_ms():.3f} ms",
+                      file=sys.stderr, flush=True)
+                kernel_ms.append(tree.last_kernel_ms())
+                return
             P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
             if record:
                 kernel_ms.append(tree.last_kernel_ms())

@@ -18,25 +18,37 @@ int fail(int code, const std::string &msg) {
 }
 
 static int select_device(int device, int *sm_count) {
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    cudaGetLastError();
-    return fail(PRGPU_ENODEV, "no CUDA device available (prgpu has no CPU fallback)");
+  // cudaGetDeviceProperties costs milliseconds: query each device once
+  static int cached_count = -1;
+  static int cached_major[64], cached_minor[64], cached_sms[64];
+  if (cached_count < 0) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      return fail(PRGPU_ENODEV, "no CUDA device available (prgpu has no CPU fallback)");
+    }
+    if (count > 64)
+      count = 64;
+    for (int d = 0; d < count; ++d) {
+      cudaDeviceProp prop;
+      PRGPU_CUDA_TRY(cudaGetDeviceProperties(&prop, d));
+      cached_major[d] = prop.major;
+      cached_minor[d] = prop.minor;
+      cached_sms[d] = prop.multiProcessorCount;
+    }
+    cached_count = count;
   }
-  if (device < 0 || device >= count)
+  if (device < 0 || device >= cached_count)
     return fail(PRGPU_EINVAL, "device ordinal out of range");
-  cudaDeviceProp prop;
-  PRGPU_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
-    return fail(PRGPU_ENODEV, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+  if (cached_major[device] != 10)
+    return fail(PRGPU_ENODEV, std::string("device is sm_") + std::to_string(cached_major[device] * 10 + cached_minor[device]) +
                                   "; prgpu kernels are built for sm_100a only");
   PRGPU_CUDA_TRY(cudaSetDevice(device));
   if (sm_count)
-    *sm_count = prop.multiProcessorCount;
+    *sm_count = cached_sms[device];
   return PRGPU_OK;
 }
-
 } // namespace prgpu
 
 using namespace prgpu;
