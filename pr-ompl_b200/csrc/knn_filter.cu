@@ -41,7 +41,8 @@ template <int DIM, int RQ>
 __global__ void __launch_bounds__(FT_THREADS)
 knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
                   int kp, const uint32_t *__restrict__ lo, uint32_t tiles_per_chunk, uint32_t tile_stride,
-                  double *__restrict__ out_key, uint32_t *__restrict__ out_idx) {
+                  const float *__restrict__ init_thresh, double *__restrict__ out_key,
+                  uint32_t *__restrict__ out_idx) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
   uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
@@ -100,7 +101,9 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
   int bc[RQ];
 #pragma unroll
   for (int u = 0; u < RQ; ++u) {
-    thr[u] = act[u] ? CUDART_INF_F : -CUDART_INF_F; // inactive: nothing ever qualifies
+    // a coarser sample's threshold (an upper bound of this sample's kp-th smallest key) spares the
+    // warm-up flood of candidates; inactive slots: nothing ever qualifies
+    thr[u] = act[u] ? (init_thresh ? init_thresh[qid[u]] : CUDART_INF_F) : -CUDART_INF_F;
     bc[u] = 0;
 #pragma unroll
     for (int c = 0; c < FT_BUF; ++c) {
@@ -163,7 +166,7 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
     }
     const float nt = __shfl_sync(0xffffffffu, key, kp - 1);
     if (lane == L) {
-      thr[u] = nt;
+      thr[u] = fminf(thr[u], nt); // (a list that is not full yet reports +inf: keep the inherited bound)
       bc[u] = 0;
     }
   };
@@ -388,13 +391,16 @@ knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__r
 
 // threshold of every query = kp-th smallest key of the sample (last entry of its merged list)
 __global__ void knn_threshold_kernel(const double *__restrict__ cand_key, const uint32_t *__restrict__ cand_idx,
-                                     uint32_t nq, int kp, float *__restrict__ thresh, uint32_t *__restrict__ counts) {
+                                     uint32_t nq, int kp, const float *coarse, float *thresh, uint32_t *counts) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq)
     return;
   const bool full = cand_idx[(size_t)q * kp + kp - 1] != PRGPU_INVALID_INDEX;
-  thresh[q] = full ? (float)cand_key[(size_t)q * kp + kp - 1] : CUDART_INF_F; // fewer than kp sampled: keep all
-  counts[q] = 0;
+  // list not full: fewer than kp sampled nodes lie below the coarser bound (or no bound: keep all)
+  const float t = full ? (float)cand_key[(size_t)q * kp + kp - 1] : (coarse ? coarse[q] : CUDART_INF_F);
+  thresh[q] = t;
+  if (counts)
+    counts[q] = 0;
 }
 
 // Pass 3: one block per query.  Exact fp64 distance (the reference's operation order) of every
@@ -551,7 +557,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   PRGPU_CUDA_TRY(cudaFuncSetAttribute(samp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   const uint32_t nsamp = (ntiles + FT_SAMPLE_STRIDE - 1) / FT_SAMPLE_STRIDE;
   const uint32_t qblocks1 = (nq + FT_THREADS - 1) / FT_THREADS;
-  uint32_t chunks1 = (uint32_t)(2 * sm_count) / qblocks1;
+  uint32_t chunks1 = (uint32_t)(8 * sm_count) / qblocks1;
   chunks1 = chunks1 < 1 ? 1 : chunks1;
   if (chunks1 > nsamp)
     chunks1 = nsamp;
@@ -583,15 +589,30 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   uint32_t *counts = sc.flags + 2 * (size_t)nq + 1;
   uint32_t *cidx = sc.flags + 3 * (size_t)nq + 1;
   PRGPU_CUDA_TRY(cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t), stream));
+  // pass 1a: a 32x coarser sub-sample (one chunk per query block) absorbs the warm-up flood of
+  // candidates; its threshold (an upper bound for 1b's) lands in `coarse_buf`, which aliases `counts`
+  // -- the counters are zeroed by the last threshold kernel, after 1b has read the coarse bounds
+  float *coarse_buf = reinterpret_cast<float *>(counts);
+  {
+    const uint32_t stride_a = FT_SAMPLE_STRIDE * 32;
+    const uint32_t nsamp_a = (ntiles + stride_a - 1) / stride_a;
+    samp<<<dim3(qblocks1, 1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, nsamp_a, stride_a, nullptr,
+                                                          sc.cand_dist, sc.cand_idx);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, nullptr, coarse_buf,
+                                                               nullptr);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+  }
   samp<<<dim3(qblocks1, chunks1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, tpc1, FT_SAMPLE_STRIDE,
-                                                            pk, pi);
+                                                            coarse_buf, pk, pi);
   PRGPU_CUDA_TRY(cudaGetLastError());
   if (chunks1 > 1) {
     rc = merge_passes(sc, (int)chunks1, nq, kp, sc.cand_idx, sc.cand_dist, stream);
     if (rc != PRGPU_OK)
       return rc;
   }
-  knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, thresh, counts);
+  knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, coarse_buf, thresh,
+                                                             counts);
   PRGPU_CUDA_TRY(cudaGetLastError());
 
   // ---- pass 2: full scan collecting every node at or below the threshold ----
