@@ -277,7 +277,8 @@ template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS)
 knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
                    const uint32_t *__restrict__ lo, const float *__restrict__ thresh, uint32_t tiles_per_chunk,
-                   uint32_t cap, uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx) {
+                   uint32_t cap, uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx,
+                   float *__restrict__ cand_key) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][CT_TILE][2]   node records
   float4 *pairs = tile + 2 * CT_TILE * 2;                                  // [CT_TILE/2][4]    pair records
@@ -322,8 +323,10 @@ knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__r
   auto emit = [&](int u, float key, uint32_t gi) {
     if (key <= thr[u] && gi >= my_lo[u] && gi < n) {
       const uint32_t slot = atomicAdd(cand_count + qid[u], 1u);
-      if (slot < cap)
+      if (slot < cap) {
         cand_idx[(size_t)qid[u] * cap + slot] = gi;
+        cand_key[(size_t)qid[u] * cap + slot] = key;
+      }
     }
   };
   // keys of the node pair whose record is (v0..v3) for query slot u
@@ -403,109 +406,175 @@ __global__ void knn_threshold_kernel(const double *__restrict__ cand_key, const 
     counts[q] = 0;
 }
 
-// Pass 3: one block per query.  Exact fp64 distance (the reference's operation order) of every
-// candidate, k rounds of block-wide arg-min under (distance, index), then the proof: every discarded
-// node has key > T_q, its fp32 key is within eps of the real |x|^2 - 2 q.x, hence its exact squared
-// distance is >= T_q - eps + |q|^2; the query is final iff the k-th selected squared distance lies
-// strictly below that.  Unproven queries (and overflowed buffers) are flagged for the exact kernel.
+// Pass 3: one block per query, two levels.
+//  (a) on the stored fp32 keys: the k-th smallest key kk of the candidates; a candidate whose key exceeds
+//      kk + 2 eps has an exact value above that of each of the k smallest-key candidates (all keys are
+//      within eps of the real |x|^2 - 2 q.x), so only the survivors with key <= kk + 2 eps -- usually
+//      k plus a few -- can be among the k nearest;
+//  (b) exact fp64 distance (the reference's operation order) of the survivors only, k rounds of arg-min
+//      under (distance, index), then the proof against the nodes the scan discarded (key > T_q): their
+//      exact squared distance is >= T_q - eps + |q|^2, which must lie strictly above the k-th selected.
+// Unproven queries, overflowed candidate buffers and survivor lists longer than 64 are flagged for the
+// exact kernel.
 constexpr int SEL_THREADS = 128;
+constexpr int SEL_MAX_SURVIVORS = 64;
 template <int DIM>
 __global__ void __launch_bounds__(SEL_THREADS)
 knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t index_base, const double *__restrict__ xmax2,
                   const double *__restrict__ queries, const float *__restrict__ thresh, uint32_t cap,
-                  const uint32_t *__restrict__ cand_count, const uint32_t *__restrict__ cand_idx, int k,
-                  uint32_t *__restrict__ idx_out, double *__restrict__ dist_out, uint32_t *__restrict__ flags) {
+                  const uint32_t *__restrict__ cand_count, const uint32_t *__restrict__ cand_idx,
+                  const float *__restrict__ cand_key, int k, uint32_t *__restrict__ idx_out,
+                  double *__restrict__ dist_out, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char sel_raw[];
-  double *sd = reinterpret_cast<double *>(sel_raw);             // [cap]
-  uint32_t *si = reinterpret_cast<uint32_t *>(sd + cap);        // [cap]
-  __shared__ double red_d[SEL_THREADS / 32];
-  __shared__ uint32_t red_i[SEL_THREADS / 32], red_p[SEL_THREADS / 32];
-  __shared__ uint32_t win_p;
+  float *okey = reinterpret_cast<float *>(sel_raw); // [cap] keys as stored
+  float *wkey = okey + cap;                         // [cap] working copy (selected entries -> +inf)
+  __shared__ float red_k[SEL_THREADS / 32];
+  __shared__ uint32_t red_p[SEL_THREADS / 32];
+  __shared__ double sv_d[SEL_MAX_SURVIVORS];
+  __shared__ uint32_t sv_i[SEL_MAX_SURVIVORS];
+  __shared__ uint32_t n_sv;
+  __shared__ float s_kk;
+  __shared__ double s_eps, s_qn2;
   const uint32_t q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cnt = cand_count[q];
-  if (cnt > cap) { // buffer overflow: cannot be decided here
+  auto flag_me = [&]() {
     if (tid == 0) {
       const uint32_t slot = atomicAdd(flags, 1u);
       flags[1 + slot] = q;
     }
+  };
+  if (cnt > cap) { // buffer overflow: cannot be decided here
+    flag_me();
     return;
   }
   double qx[DIM];
-  double qn2 = 0.0;
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) {
+  for (int d = 0; d < DIM; ++d)
     qx[d] = queries[(size_t)q * DIM + d];
-    qn2 += qx[d] * qx[d];
-  }
-  for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
-    const uint32_t i = cand_idx[(size_t)q * cap + c];
-    double x[DIM];
+  if (tid == 0) {
+    double qn2 = 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
-      x[d] = pts[(size_t)d * stride + i];
-    sd[c] = __dsqrt_rn(sqdist_exact<DIM>(x, qx)); // RealVectorStateSpace::distance(node, query)
-    si[c] = i;
+      qn2 += qx[d] * qx[d];
+    const double xn = sqrt(*xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
+    s_eps = 16.0 * 5.9604644775390625e-08 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
+    s_qn2 = qn2;
+    n_sv = 0;
+  }
+  for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
+    const float kv = cand_key[(size_t)q * cap + c];
+    okey[c] = kv;
+    wkey[c] = kv;
   }
   __syncthreads();
-  double dk = CUDART_INF;
-  for (int r = 0; r < k; ++r) {
-    double bd = CUDART_INF;
-    uint32_t bi = PRGPU_INVALID_INDEX, bp = 0xFFFFFFFFu;
+  // (a) k-th smallest stored key (k rounds of block-wide arg-min)
+  const int rounds = (int)min((uint32_t)k, cnt);
+  for (int r = 0; r < rounds; ++r) {
+    float bk = CUDART_INF_F;
+    uint32_t bp = 0xFFFFFFFFu;
     for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
-      const double d = sd[c];
-      const uint32_t i = si[c];
-      if (d < bd || (d == bd && i < bi)) {
-        bd = d;
-        bi = i;
+      const float v = wkey[c];
+      if (v < bk || (v == bk && c < bp)) {
+        bk = v;
         bp = c;
       }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      const double od = __shfl_xor_sync(0xffffffffu, bd, off);
-      const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      const float ok = __shfl_xor_sync(0xffffffffu, bk, off);
       const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
-      if (od < bd || (od == bd && oi < bi)) {
-        bd = od;
-        bi = oi;
+      if (ok < bk || (ok == bk && op < bp)) {
+        bk = ok;
         bp = op;
       }
     }
     if (lane == 0) {
-      red_d[warp] = bd;
-      red_i[warp] = bi;
+      red_k[warp] = bk;
       red_p[warp] = bp;
     }
     __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < SEL_THREADS / 32; ++w)
-        if (red_d[w] < bd || (red_d[w] == bd && red_i[w] < bi)) {
-          bd = red_d[w];
-          bi = red_i[w];
+        if (red_k[w] < bk || (red_k[w] == bk && red_p[w] < bp)) {
+          bk = red_k[w];
           bp = red_p[w];
         }
-      dist_out[(size_t)q * k + r] = bd;
-      idx_out[(size_t)q * k + r] = bi == PRGPU_INVALID_INDEX ? bi : bi + index_base;
-      win_p = bp;
-      if (bp != 0xFFFFFFFFu) { // remove the winner
-        sd[bp] = CUDART_INF;
-        si[bp] = PRGPU_INVALID_INDEX;
-      }
-      dk = bd;
+      if (bp != 0xFFFFFFFFu)
+        wkey[bp] = CUDART_INF_F;
+      s_kk = bk;
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    const float T = thresh[q];
-    if (T < CUDART_INF_F) { // nodes were discarded: prove they cannot matter
-      const double xn = sqrt(*xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
-      const double eps = 16.0 * 5.9604644775390625e-08 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
-      const double bound = (double)T - eps + qn2; // lower bound of the exact squared distance of any discarded node
-      const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (qn2 + 1.0);
-      if (!(sk < bound)) {
-        const uint32_t slot = atomicAdd(flags, 1u);
-        flags[1 + slot] = q;
+  // survivors: everything whose key is within 2 eps of the k-th smallest key (all, if fewer than k)
+  const float cut = cnt <= (uint32_t)k ? CUDART_INF_F : (float)((double)s_kk + 2.0 * s_eps) * (1.0f + 1e-6f) + 1e-30f;
+  for (uint32_t c = tid; c < cnt; c += SEL_THREADS)
+    if (okey[c] <= cut) {
+      const uint32_t slot = atomicAdd(&n_sv, 1u);
+      if (slot < SEL_MAX_SURVIVORS)
+        sv_i[slot] = cand_idx[(size_t)q * cap + c];
+    }
+  __syncthreads();
+  const uint32_t ns = n_sv;
+  if (ns > SEL_MAX_SURVIVORS) { // massive ties around the k-th key
+    flag_me();
+    return;
+  }
+  // (b) exact distances of the survivors
+  if ((uint32_t)tid < ns) {
+    const uint32_t i = sv_i[tid];
+    double x[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+      x[d] = pts[(size_t)d * stride + i];
+    sv_d[tid] = __dsqrt_rn(sqdist_exact<DIM>(x, qx)); // RealVectorStateSpace::distance(node, query)
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double dk = CUDART_INF;
+    for (int r = 0; r < k; ++r) {
+      double bd = CUDART_INF;
+      uint32_t bi = PRGPU_INVALID_INDEX, bp = 0xFFFFFFFFu;
+      for (uint32_t c = lane; c < ns; c += 32) {
+        const double d = sv_d[c];
+        const uint32_t i = sv_i[c];
+        if (d < bd || (d == bd && i < bi)) {
+          bd = d;
+          bi = i;
+          bp = c;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
+        if (od < bd || (od == bd && oi < bi)) {
+          bd = od;
+          bi = oi;
+          bp = op;
+        }
+      }
+      if (lane == 0) {
+        dist_out[(size_t)q * k + r] = bd;
+        idx_out[(size_t)q * k + r] = bi == PRGPU_INVALID_INDEX ? bi : bi + index_base;
+        if (bp != 0xFFFFFFFFu) {
+          sv_d[bp] = CUDART_INF;
+          sv_i[bp] = PRGPU_INVALID_INDEX;
+        }
+      }
+      __syncwarp();
+      dk = bd;
+    }
+    if (lane == 0) {
+      const float T = thresh[q];
+      if (T < CUDART_INF_F) { // nodes were discarded by the scan: prove they cannot matter
+        const double bound = (double)T - s_eps + s_qn2; // lower bound of any discarded node's exact squared distance
+        const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (s_qn2 + 1.0);
+        if (!(sk < bound)) {
+          const uint32_t slot = atomicAdd(flags, 1u);
+          flags[1 + slot] = q;
+        }
       }
     }
   }
@@ -575,8 +644,8 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
     pk = sc.part_dist;
     pi = sc.part_idx;
   }
-  // flags | thresholds | counts | candidate indices
-  const size_t need_words = ((size_t)nq + 1) + (size_t)nq + (size_t)nq + (size_t)nq * cap;
+  // flags | thresholds | counts | candidate indices | candidate keys
+  const size_t need_words = ((size_t)nq + 1) + (size_t)nq + (size_t)nq + 2 * (size_t)nq * cap;
   if (sc.flags_capacity < need_words) {
     if (sc.flags)
       cudaFree(sc.flags);
@@ -588,6 +657,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   float *thresh = reinterpret_cast<float *>(sc.flags + (size_t)nq + 1);
   uint32_t *counts = sc.flags + 2 * (size_t)nq + 1;
   uint32_t *cidx = sc.flags + 3 * (size_t)nq + 1;
+  float *ckey = reinterpret_cast<float *>(cidx + (size_t)nq * cap);
   PRGPU_CUDA_TRY(cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t), stream));
   // pass 1a: a 32x coarser sub-sample (one chunk per query block) absorbs the warm-up flood of
   // candidates; its threshold (an upper bound for 1b's) lands in `coarse_buf`, which aliases `counts`
@@ -632,17 +702,17 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   if (timer)
     timer->begin(stream);
   coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf, t.n, queries, nq, lo, thresh, tiles_per_chunk, cap,
-                                                           counts, cidx);
+                                                           counts, cidx, ckey);
   if (timer)
     timer->end(stream);
   PRGPU_CUDA_TRY(cudaGetLastError());
 
   // ---- pass 3: exact re-rank of the candidates + proof ----
-  const size_t smem3 = (size_t)cap * 12;
+  const size_t smem3 = (size_t)cap * 8;
   auto sel = knn_select_kernel<DIM>;
   PRGPU_CUDA_TRY(cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-  sel<<<nq, SEL_THREADS, smem3, stream>>>(t.pts, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts, cidx, k,
-                                         idx_out, dist_out, sc.flags);
+  sel<<<nq, SEL_THREADS, smem3, stream>>>(t.pts, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts, cidx, ckey,
+                                         k, idx_out, dist_out, sc.flags);
   PRGPU_CUDA_TRY(cudaGetLastError());
   ++sc.filter_calls;
 
