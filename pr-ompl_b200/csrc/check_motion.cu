@@ -306,7 +306,8 @@ size_t obstacle_smem(const DeviceWorld &w) { return obstacle_tables_bytes(w); }
 
 #define PRGPU_SP_DISPATCH(S, ...)                                                                  \
   do {                                                                                             \
-    if ((S) <= 8) { constexpr int SP = 8; __VA_ARGS__; }                                           \
+    if (w.grid_n[0] > 0) { constexpr int SP = 0; __VA_ARGS__; }                                    \
+    else if ((S) <= 8) { constexpr int SP = 8; __VA_ARGS__; }                                      \
     else if ((S) <= 16) { constexpr int SP = 16; __VA_ARGS__; }                                    \
     else if ((S) <= 24) { constexpr int SP = 24; __VA_ARGS__; }                                    \
     else { constexpr int SP = 32; __VA_ARGS__; }                                                   \

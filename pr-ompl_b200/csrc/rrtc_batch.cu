@@ -312,7 +312,9 @@ int rrtc_batch_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const Rrtc
     PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<n_queries, RB_THREADS, smem, stream>>>(w_dev, p, b, n_queries);                         \
   } while (0)
-  if (w.S <= 8)
+  if (w.grid_n[0] > 0)
+    PRGPU_RB_LAUNCH(0);
+  else if (w.S <= 8)
     PRGPU_RB_LAUNCH(8);
   else if (w.S <= 16)
     PRGPU_RB_LAUNCH(16);

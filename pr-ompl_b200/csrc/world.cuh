@@ -472,11 +472,14 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
 }
 
 // validity of one state through whichever broad phase the world has
+// SP == 0 selects the grid path at compile time, so kernels instantiated for worlds with a grid never
+// carry the brute-force filter's register footprint (the host dispatches on grid_n[0] > 0).
 template <int SP>
 __device__ __forceinline__ bool state_valid_any(const DeviceWorld *wp, const ObstacleTables *tp, const double *q) {
-  if (wp->grid_n[0] > 0)
+  if constexpr (SP == 0)
     return state_valid_grid(wp, tp, q);
-  return state_valid_fast<SP>(*wp, tp->os, tp->ob, q);
+  else
+    return state_valid_fast<SP>(*wp, tp->os, tp->ob, q);
 }
 
 // out-of-line variant for kernels that test states from several places (keeps their register
