@@ -16,7 +16,7 @@
 namespace prgpu {
 namespace {
 
-constexpr int RB_THREADS = 128;
+constexpr int RB_THREADS = 64;
 enum { GS_TRAPPED = 0, GS_ADVANCED = 1, GS_REACHED = 2 };
 enum { ST_INVALID_START = 1, ST_INVALID_GOAL = 2, ST_TIMEOUT = 4, ST_EXACT = 6 }; // PlannerStatus values
 
