@@ -347,6 +347,9 @@ __device__ __forceinline__ void load_obstacles(const DeviceWorld &w, float4 *s_o
 }
 
 // ---- grid path: per link sphere, only the obstacles listed in the sphere centre's cell ------------
+// delta bounds |fp32 distance - exact distance| of a (sphere, obstacle) pair.  Three outcomes per
+// candidate pair: farther than r+R+delta -> free; nearer than r+R-delta -> colliding (both certain in
+// fp32); in between -> the fp64 chain and the specification's formula decide.
 struct ArmTableF32 { // fp32 copy of the arm for the filter path (shared memory)
   float dh[WORLD_MAX_DOF][5];        // a, d, cos(alpha), sin(alpha), theta0
   float4 sphere[WORLD_MAX_S];        // local x,y,z and radius + delta, ordered by link
@@ -456,14 +459,23 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
           const float ex = fmaxf(fabsf(cx - bc.x) - bh.x, 0.0f);
           const float ey = fmaxf(fabsf(cy - bc.y) - bh.y, 0.0f);
           const float ez = fmaxf(fabsf(cz - bc.z) - bh.z, 0.0f);
-          if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < rs * rs && exact_pair_hit(w, q, arm.sphere_id[j], (int)o, true))
-            return false;
+          const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+          if (d2 < rs * rs) {
+            // deeper than the fp32 error bound: certainly colliding; only the thin band needs fp64
+            const float rin = rs - 2.0f * w.delta;
+            if ((rin > 0.f && d2 < rin * rin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)o, true))
+              return false;
+          }
         } else {
           const float4 ob = t.os[id];
           const float dx = cx - ob.x, dy = cy - ob.y, dz = cz - ob.z;
           const float thr = rs + ob.w; // grid tables keep the obstacle radius in .w
-          if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < thr * thr && exact_pair_hit(w, q, arm.sphere_id[j], (int)id, false))
-            return false;
+          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          if (d2 < thr * thr) {
+            const float tin = thr - 2.0f * w.delta;
+            if ((tin > 0.f && d2 < tin * tin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)id, false))
+              return false;
+          }
         }
       }
     }
