@@ -1,0 +1,74 @@
+"""Parity at BASELINE.json's full sizes, through size-independent properties and oracle spot checks."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_knn_sweep_full_size(P, O, synth):
+    """N=1e7, Q=4096, k=16 and k=1: the fast path equals the exact kernel on every query; a spread
+    subset equals the CPU oracle; rows are sorted; reported distances are the reference's distance of the
+    reported nodes."""
+    import torch
+    n, nq = 10_000_000, 4096
+    pts = synth.cloud(0, n)
+    q = synth.cloud(1, nq)
+    t = P.KnnIndex(7, capacity=n)
+    t.add(pts)
+    sub = np.arange(0, nq, 128)
+    for k in (16, 1):
+        t.set_search_mode(False)
+        fi, fd = t.nearest_k(q, k)
+        st = t.search_stats()
+        assert st["filter_calls"] > 0
+        t.set_search_mode(True)
+        ei, ed = t.nearest_k(q, k)
+        assert np.array_equal(fi, ei) and np.array_equal(fd, ed)
+        oi, od = O.knn(pts, q[sub], k, nthreads=16)
+        assert np.array_equal(fi[sub], oi) and np.array_equal(fd[sub], od)
+        assert np.all(np.diff(fd, axis=1) >= 0)
+        rows = np.arange(0, nq, 37)
+        d = np.sqrt(((pts[fi[rows, 0]] - q[rows]) ** 2).sum(1))
+        assert np.allclose(d, fd[rows, 0], rtol=1e-13)
+    t.close()
+    torch.cuda.empty_cache()
+
+
+def test_check_motion_full_size(P, O, synth, gpu_world, oracle_world):
+    """1e6 edges at 0.01 rad: flattened two-phase path; a 16k-edge subset equals the oracle outside the
+    contact band; the verdict is independent of batch composition (idempotence on a re-ordered batch)."""
+    n = 1_000_000
+    a, b = synth.edges(2, n)
+    v = gpu_world.check_motion_batch(a, b, 0.01)
+    assert 0.45 < v.mean() < 0.65
+    sub = np.arange(0, n, 61)
+    ov, oc, _ = oracle_world.check_motion_batch(a[sub], b[sub], 0.01, nthreads=16)
+    diff = v[sub] != ov
+    assert not np.any(diff & (np.abs(oc) >= 1e-6)), np.argwhere(diff)[:5]
+    perm = np.random.default_rng(0).permutation(n)[:200_000]
+    v2 = gpu_world.check_motion_batch(a[perm], b[perm], 0.01)
+    assert np.array_equal(v2, v[perm])
+    # small-batch kernel (warp per edge) agrees with the flattened kernels
+    v3 = gpu_world.check_motion_batch(a[:3000], b[:3000], 0.01)
+    assert np.array_equal(v3, v[:3000])
+
+
+def test_rrtc_4096_queries(P, O, synth, gpu_world, oracle_world):
+    """4096 independent queries: a spread subset reproduces the oracle's trees exactly; solved queries
+    return start..goal paths."""
+    n = 4096
+    q = synth.cloud(4, 8 * n)
+    v = gpu_world.is_valid_batch(q)
+    qv = q[v == 1]
+    starts, goals = np.ascontiguousarray(qv[0:2 * n:2]), np.ascontiguousarray(qv[1:2 * n:2])
+    rb = P.RrtcBatch(gpu_world, n, -np.pi, np.pi, extension_type="ext-con", seed=4, max_iters=1000, max_nodes=2048)
+    rb.run(starts, goals)
+    s = rb.summary()
+    assert (s["status"] == 6).mean() > 0.9
+    for qi in range(0, n, 293):
+        ref = oracle_world.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=(0, 1), seed=4, query=qi,
+                                      max_iters=1000, max_nodes=4096)
+        assert s["status"][qi] == ref["status"] and s["iterations"][qi] == ref["iterations"]
+        got = rb.fetch(qi, int(s["n_start"][qi]), int(s["n_goal"][qi]))
+        for key in ("start_parent", "goal_parent", "start_states", "goal_states", "path"):
+            assert np.array_equal(got[key], ref[key]), (qi, key)
