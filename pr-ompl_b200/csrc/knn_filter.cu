@@ -265,6 +265,83 @@ knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
     }
 }
 
+// Pass 1a: coarse threshold of every query from a small strided sub-sample.  One thread = one query;
+// the KP smallest keys live in registers as a sorted array updated by a branch-free insertion network
+// (new[e] = min(old[e], max(old[e-1], x))), entered only when some lane of the warp has a key below its
+// current KP-th -- there is no per-lane divergent code and no shared-memory list.
+constexpr int PS_KP = KNN_FILTER_MAX_K + KNN_FILTER_MARGIN;
+template <int DIM>
+__global__ void __launch_bounds__(FT_THREADS)
+knn_presample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
+                     int kp, const uint32_t *__restrict__ lo, uint32_t tile_stride, float *__restrict__ coarse) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
+  const int tid = threadIdx.x;
+  const uint32_t q = blockIdx.x * FT_THREADS + tid;
+  const bool act = q < nq;
+  float q2[7];
+#pragma unroll
+  for (int d = 0; d < 7; ++d)
+    q2[d] = (act && d < DIM) ? (float)(-2.0 * queries[(size_t)q * DIM + d]) : 0.f;
+  const uint32_t my_lo = (act && lo) ? lo[q] : 0u;
+  float keys[PS_KP];
+#pragma unroll
+  for (int e = 0; e < PS_KP; ++e)
+    keys[e] = CUDART_INF_F;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const uint32_t ntiles = (n + FT_TILE - 1) / FT_TILE;
+  const uint32_t nsamp = (ntiles + tile_stride - 1) / tile_stride;
+  auto issue = [&](uint32_t t, int buf) {
+    mbar_expect_tx(&bars[buf], FT_TILE * 32);
+    bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * tile_stride * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
+  };
+  if (tid == 0 && nsamp > 0)
+    issue(0, 0);
+  for (uint32_t t = 0; t < nsamp; ++t) {
+    const int buf = t & 1;
+    if (tid == 0 && t + 1 < nsamp)
+      issue(t + 1, buf ^ 1);
+    mbar_wait(&bars[buf], (t >> 1) & 1);
+    const float4 *T = tile + buf * FT_TILE * 2;
+    const uint32_t base = t * tile_stride * FT_TILE;
+    const uint32_t jmax = min((uint32_t)FT_TILE, n - base);
+    for (uint32_t j = 0; j < jmax; ++j) {
+      const float4 a = T[2 * j], b = T[2 * j + 1];
+      float x = b.w;
+      x = fmaf(q2[0], a.x, x);
+      if (DIM > 1) x = fmaf(q2[1], a.y, x);
+      if (DIM > 2) x = fmaf(q2[2], a.z, x);
+      if (DIM > 3) x = fmaf(q2[3], a.w, x);
+      if (DIM > 4) x = fmaf(q2[4], b.x, x);
+      if (DIM > 5) x = fmaf(q2[5], b.y, x);
+      if (DIM > 6) x = fmaf(q2[6], b.z, x);
+      if (!act || base + j < my_lo)
+        x = CUDART_INF_F;
+      if (__any_sync(0xffffffffu, x < keys[PS_KP - 1])) {
+#pragma unroll
+        for (int e = PS_KP - 1; e >= 1; --e)
+          keys[e] = fminf(keys[e], fmaxf(keys[e - 1], x));
+        keys[0] = fminf(keys[0], x);
+      }
+    }
+    __syncthreads();
+  }
+  if (act) {
+    float t = CUDART_INF_F;
+#pragma unroll
+    for (int e = 0; e < PS_KP; ++e)
+      if (e == kp - 1)
+        t = keys[e];
+    coarse[q] = t; // +inf when fewer than kp sampled nodes are candidates
+  }
+}
+
 // Pass 2: full scan.  A node is a candidate of query q iff key(q, node) <= T_q (the threshold from
 // the sample pass) and node >= lo_q; candidates are appended to the query's global buffer.  The hot
 // loop holds no per-query state besides the threshold.  Each tile (one bulk copy of 32-byte node
@@ -665,12 +742,9 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   float *coarse_buf = reinterpret_cast<float *>(counts);
   {
     const uint32_t stride_a = FT_SAMPLE_STRIDE * 32;
-    const uint32_t nsamp_a = (ntiles + stride_a - 1) / stride_a;
-    samp<<<dim3(qblocks1, 1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, nsamp_a, stride_a, nullptr,
-                                                          sc.cand_dist, sc.cand_idx);
-    PRGPU_CUDA_TRY(cudaGetLastError());
-    knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, nullptr, coarse_buf,
-                                                               nullptr);
+    const size_t smem0 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t);
+    knn_presample_kernel<DIM><<<qblocks1, FT_THREADS, smem0, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, stride_a,
+                                                                      coarse_buf);
     PRGPU_CUDA_TRY(cudaGetLastError());
   }
   samp<<<dim3(qblocks1, chunks1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, tpc1, FT_SAMPLE_STRIDE,
