@@ -303,7 +303,7 @@ def run_ours(args, rank, local_rank, world):
             if record:
                 kernel_ms.append(tree.last_kernel_ms())
 
-        launches_per_step = 6 + (1 if world > 1 else 0)  # pre-sample, sample, merge, threshold, collect, select
+        launches_per_step = 7 + (1 if world > 1 else 0)  # pre-sample, threshold, sample, merge, threshold, collect, select
         units_per_step = Q
         metric, unit = "kNN queries/s", "queries/s"
         algo_bytes = n_local * 56 + Q * 56 + Q * k * 12

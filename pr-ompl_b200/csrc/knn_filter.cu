@@ -5,7 +5,7 @@
 // (>= 128 queries per tree pass, k <= 24) almost all of that work only establishes that a node is
 // NOT among the k nearest.  This path does that part in fp32:
 //   key(q,x) = |x|^2 - 2 q.x  (= |q-x|^2 - |q|^2) from an fp32 mirror of the tree (8 floats per node).
-//   1. knn_filter_kernel on every 64th tile: T_q = (k+2)-th smallest key of the sample, an upper
+//   1. knn_sample_kernel on every 64th tile: T_q = (k+2)-th smallest key of the sample, an upper
 //      bound of the (k+2)-th smallest key of the whole tree.
 //   2. knn_collect_kernel: one pass over the tree, 7 FFMA + 1 compare per pair, each node tile
 //      broadcast from shared memory to 4 queries per thread; nodes with key <= T_q (~ (k+2)*64 per
@@ -29,251 +29,20 @@ namespace {
 constexpr int FT_TILE = 128;     // nodes per tile (32 bytes each)
 constexpr int FT_THREADS = 128;  // queries per block
 
-constexpr int FT_RQ = 4;         // queries per thread (register tile: halves the shared-memory reads per pair)
-constexpr int FT_BUF = 8;        // per-query register buffer of pending candidates
+constexpr int FT_RQ = 4;         // queries per thread in the collect pass (register tile over the broadcast node tile)
 
-// Keeps, per query, the kp smallest keys seen so far.  The hot loop only compares against a
-// register threshold and appends the rare qualifying candidate to a small register buffer; when a
-// lane's buffer is nearly full the WARP merges that lane's list (kp entries in shared memory) with
-// its buffer -- 32 items, one per lane, one bitonic sort -- and hands the tightened threshold back.
-// No divergent per-lane insertion loops remain.
-template <int DIM, int RQ>
-__global__ void __launch_bounds__(FT_THREADS)
-knn_filter_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
-                  int kp, const uint32_t *__restrict__ lo, uint32_t tiles_per_chunk, uint32_t tile_stride,
-                  const float *__restrict__ init_thresh, double *__restrict__ out_key,
-                  uint32_t *__restrict__ out_idx) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
-  float *lkey = reinterpret_cast<float *>(bars + 2);                       // [RQ][THREADS][kp]
-  uint32_t *lidx = reinterpret_cast<uint32_t *>(lkey + (size_t)RQ * kp * FT_THREADS);
-  __shared__ uint32_t s_lo_min;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  uint32_t qid[RQ];
-  bool act[RQ];
-  float q2[RQ][7];
-  uint32_t my_lo[RQ];
-#pragma unroll
-  for (int u = 0; u < RQ; ++u) {
-    qid[u] = (blockIdx.x * RQ + u) * FT_THREADS + tid;
-    act[u] = qid[u] < nq;
-#pragma unroll
-    for (int d = 0; d < 7; ++d)
-      q2[u][d] = (act[u] && d < DIM) ? (float)(-2.0 * queries[(size_t)qid[u] * DIM + d]) : 0.f;
-    my_lo[u] = (act[u] && lo) ? lo[qid[u]] : 0u;
-  }
-  if (tid == 0) {
-    s_lo_min = 0xFFFFFFFFu;
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
-  for (int e = 0; e < RQ * kp; ++e) {
-    const int u = e / kp, j = e - u * kp;
-    lkey[((size_t)u * FT_THREADS + tid) * kp + j] = CUDART_INF_F;
-    lidx[((size_t)u * FT_THREADS + tid) * kp + j] = PRGPU_INVALID_INDEX;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < RQ; ++u)
-    if (act[u])
-      atomicMin(&s_lo_min, my_lo[u]);
-  __syncthreads();
-
-  // this block visits the sampled tiles s*tile_stride, s in [t0, t1)
-  const uint32_t ntiles = (n + FT_TILE - 1) / FT_TILE;
-  const uint32_t nsamp = (ntiles + tile_stride - 1) / tile_stride;
-  uint32_t t0 = blockIdx.y * tiles_per_chunk;
-  const uint32_t t1 = min(t0 + tiles_per_chunk, nsamp);
-  if (s_lo_min != 0xFFFFFFFFu)
-    t0 = max(t0, s_lo_min / FT_TILE / tile_stride);
-
-  auto issue = [&](uint32_t t, int buf) {
-    mbar_expect_tx(&bars[buf], FT_TILE * 32);
-    bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * tile_stride * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
-  };
-
-  float thr[RQ];            // upper bound of the kp-th smallest key of each query
-  float bk[RQ][FT_BUF];     // pending candidates
-  uint32_t bi[RQ][FT_BUF];
-  int bc[RQ];
-#pragma unroll
-  for (int u = 0; u < RQ; ++u) {
-    // a coarser sample's threshold (an upper bound of this sample's kp-th smallest key) spares the
-    // warm-up flood of candidates; inactive slots: nothing ever qualifies
-    thr[u] = act[u] ? (init_thresh ? init_thresh[qid[u]] : CUDART_INF_F) : -CUDART_INF_F;
-    bc[u] = 0;
-#pragma unroll
-    for (int c = 0; c < FT_BUF; ++c) {
-      bk[u][c] = CUDART_INF_F;
-      bi[u][c] = PRGPU_INVALID_INDEX;
-    }
-  }
-  auto offer = [&](int u, float key, uint32_t gi) {
-    if (key < thr[u] && gi >= my_lo[u]) {
-#pragma unroll
-      for (int c = 0; c < FT_BUF; ++c)
-        if (bc[u] == c) {
-          bk[u][c] = key;
-          bi[u][c] = gi;
-        }
-      ++bc[u];
-    }
-  };
-  // warp-cooperative merge of lane L's list and buffer (query slot u); all 32 lanes participate
-  auto compact = [&](int u, int L) {
-    const int cnt = __shfl_sync(0xffffffffu, bc[u], L);
-    if (cnt == 0)
-      return;
-    const int wt = (tid & ~31) + L; // thread whose list is merged
-    float *K = lkey + ((size_t)u * FT_THREADS + wt) * kp;
-    uint32_t *I = lidx + ((size_t)u * FT_THREADS + wt) * kp;
-    float key = CUDART_INF_F;
-    uint32_t idx = PRGPU_INVALID_INDEX;
-    if (lane < kp) {
-      key = K[lane];
-      idx = I[lane];
-    }
-#pragma unroll
-    for (int c = 0; c < FT_BUF; ++c) {
-      const float vk = __shfl_sync(0xffffffffu, bk[u][c], L);
-      const uint32_t vi = __shfl_sync(0xffffffffu, bi[u][c], L);
-      if (lane == kp + c && c < cnt) {
-        key = vk;
-        idx = vi;
-      }
-    }
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-      for (int strd = size >> 1; strd > 0; strd >>= 1) {
-        const float ok = __shfl_xor_sync(0xffffffffu, key, strd);
-        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, strd);
-        const bool keep_min = (((lane & size) == 0) == ((lane & strd) == 0));
-        const bool other_less = ok < key || (ok == key && oi < idx);
-        const bool other_more = key < ok || (ok == key && idx < oi);
-        if (keep_min ? other_less : other_more) {
-          key = ok;
-          idx = oi;
-        }
-      }
-    }
-    if (lane < kp) {
-      K[lane] = key;
-      I[lane] = idx;
-    }
-    const float nt = __shfl_sync(0xffffffffu, key, kp - 1);
-    if (lane == L) {
-      thr[u] = fminf(thr[u], nt); // (a list that is not full yet reports +inf: keep the inherited bound)
-      bc[u] = 0;
-    }
-  };
-  auto compact_if = [&](bool need) {
-    unsigned mask = __ballot_sync(0xffffffffu, need);
-    while (mask) {
-      const int L = __ffs(mask) - 1;
-      mask &= mask - 1;
-#pragma unroll
-      for (int u = 0; u < RQ; ++u)
-        compact(u, L);
-    }
-    __syncwarp();
-  };
-  auto key_of = [&](int u, const float4 &a, const float4 &b) {
-    float acc = b.w; // |x|^2
-    acc = fmaf(q2[u][0], a.x, acc);
-    if (DIM > 1) acc = fmaf(q2[u][1], a.y, acc);
-    if (DIM > 2) acc = fmaf(q2[u][2], a.z, acc);
-    if (DIM > 3) acc = fmaf(q2[u][3], a.w, acc);
-    if (DIM > 4) acc = fmaf(q2[u][4], b.x, acc);
-    if (DIM > 5) acc = fmaf(q2[u][5], b.y, acc);
-    if (DIM > 6) acc = fmaf(q2[u][6], b.z, acc);
-    return acc;
-  };
-
-  if (tid == 0 && t0 < t1)
-    issue(t0, 0);
-  for (uint32_t t = t0; t < t1; ++t) {
-    const int buf = (t - t0) & 1;
-    const uint32_t parity = ((t - t0) >> 1) & 1;
-    if (tid == 0 && t + 1 < t1)
-      issue(t + 1, buf ^ 1);
-    mbar_wait(&bars[buf], parity);
-    {
-      const float4 *T = tile + buf * FT_TILE * 2;
-      const uint32_t base = t * tile_stride * FT_TILE;
-      const uint32_t jmax = min((uint32_t)FT_TILE, n - base);
-      uint32_t j = 0;
-      for (; j + 3 < jmax; j += 4) {
-        const float4 a0 = T[2 * j], b0 = T[2 * j + 1], a1 = T[2 * j + 2], b1 = T[2 * j + 3];
-        const float4 a2 = T[2 * j + 4], b2 = T[2 * j + 5], a3 = T[2 * j + 6], b3 = T[2 * j + 7];
-        bool any = false;
-#pragma unroll
-        for (int u = 0; u < RQ; ++u) {
-          const float k0 = key_of(u, a0, b0), k1 = key_of(u, a1, b1), k2 = key_of(u, a2, b2), k3 = key_of(u, a3, b3);
-          if (fminf(fminf(k0, k1), fminf(k2, k3)) < thr[u]) {
-            offer(u, k0, base + j);
-            offer(u, k1, base + j + 1);
-            offer(u, k2, base + j + 2);
-            offer(u, k3, base + j + 3);
-            any = true;
-          }
-        }
-        if (__any_sync(0xffffffffu, any)) {
-          bool need = false;
-#pragma unroll
-          for (int u = 0; u < RQ; ++u)
-            need = need || bc[u] > FT_BUF - 4; // the next group may add up to 4
-          compact_if(need);
-        }
-      }
-      for (; j < jmax; ++j) {
-        const float4 a0 = T[2 * j], b0 = T[2 * j + 1];
-#pragma unroll
-        for (int u = 0; u < RQ; ++u)
-          offer(u, key_of(u, a0, b0), base + j);
-        bool need = false;
-#pragma unroll
-        for (int u = 0; u < RQ; ++u)
-          need = need || bc[u] > FT_BUF - 4;
-        compact_if(need);
-      }
-    }
-    __syncthreads();
-  }
-  {
-    bool need = false;
-#pragma unroll
-    for (int u = 0; u < RQ; ++u)
-      need = need || bc[u] > 0;
-    compact_if(need);
-  }
-#pragma unroll
-  for (int u = 0; u < RQ; ++u)
-    if (act[u]) {
-      const float *K = lkey + ((size_t)u * FT_THREADS + tid) * kp;
-      const uint32_t *I = lidx + ((size_t)u * FT_THREADS + tid) * kp;
-      double *od = out_key + ((size_t)blockIdx.y * nq + qid[u]) * kp;
-      uint32_t *oi = out_idx + ((size_t)blockIdx.y * nq + qid[u]) * kp;
-      for (int e = 0; e < kp; ++e) {
-        const uint32_t i = I[e];
-        od[e] = i == PRGPU_INVALID_INDEX ? CUDART_INF : (double)K[e];
-        oi[e] = i;
-      }
-    }
-}
-
-// Pass 1a: coarse threshold of every query from a small strided sub-sample.  One thread = one query;
-// the KP smallest keys live in registers as a sorted array updated by a branch-free insertion network
-// (new[e] = min(old[e], max(old[e-1], x))), entered only when some lane of the warp has a key below its
-// current KP-th -- there is no per-lane divergent code and no shared-memory list.
+// Pass 1 (run twice: a 32x coarser pre-sample, then the sample proper seeded with the pre-sample's
+// threshold): the KP smallest keys of every query over a strided sub-sample of the tree.  One thread =
+// one query; the keys live in registers as a sorted array updated by a branch-free insertion network
+// (new[e] = min(old[e], max(old[e-1], x))), entered only when some lane of the warp has a key below
+// its current KP-th -- no per-lane divergent code, no shared-memory lists.  Node chunks (blockIdx.y)
+// emit their sorted keys as partial lists, merged like any other partial top-k tables.
 constexpr int PS_KP = KNN_FILTER_MAX_K + KNN_FILTER_MARGIN;
 template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS)
-knn_presample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
-                     int kp, const uint32_t *__restrict__ lo, uint32_t tile_stride, float *__restrict__ coarse) {
+knn_sample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
+                  int kp, const uint32_t *__restrict__ lo, uint32_t tile_stride, uint32_t tiles_per_chunk,
+                  const float *__restrict__ seed, double *__restrict__ out_key, uint32_t *__restrict__ out_idx) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][FT_TILE][2]
   uint64_t *bars = reinterpret_cast<uint64_t *>(tile + 2 * FT_TILE * 2);   // [2]
@@ -285,10 +54,13 @@ knn_presample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *_
   for (int d = 0; d < 7; ++d)
     q2[d] = (act && d < DIM) ? (float)(-2.0 * queries[(size_t)q * DIM + d]) : 0.f;
   const uint32_t my_lo = (act && lo) ? lo[q] : 0u;
+  // seeding every slot with a known upper bound of the kp-th smallest key keeps the result an upper
+  // bound and spares the warm-up flood
+  const float s0 = (act && seed) ? seed[q] : CUDART_INF_F;
   float keys[PS_KP];
 #pragma unroll
   for (int e = 0; e < PS_KP; ++e)
-    keys[e] = CUDART_INF_F;
+    keys[e] = s0;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -297,17 +69,19 @@ knn_presample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *_
   __syncthreads();
   const uint32_t ntiles = (n + FT_TILE - 1) / FT_TILE;
   const uint32_t nsamp = (ntiles + tile_stride - 1) / tile_stride;
+  const uint32_t t0 = blockIdx.y * tiles_per_chunk;
+  const uint32_t t1 = min(t0 + tiles_per_chunk, nsamp);
   auto issue = [&](uint32_t t, int buf) {
     mbar_expect_tx(&bars[buf], FT_TILE * 32);
     bulk_g2s(tile + buf * FT_TILE * 2, ptsf + (size_t)t * tile_stride * FT_TILE * 8, FT_TILE * 32, &bars[buf]);
   };
-  if (tid == 0 && nsamp > 0)
-    issue(0, 0);
-  for (uint32_t t = 0; t < nsamp; ++t) {
-    const int buf = t & 1;
-    if (tid == 0 && t + 1 < nsamp)
+  if (tid == 0 && t0 < t1)
+    issue(t0, 0);
+  for (uint32_t t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    if (tid == 0 && t + 1 < t1)
       issue(t + 1, buf ^ 1);
-    mbar_wait(&bars[buf], (t >> 1) & 1);
+    mbar_wait(&bars[buf], ((t - t0) >> 1) & 1);
     const float4 *T = tile + buf * FT_TILE * 2;
     const uint32_t base = t * tile_stride * FT_TILE;
     const uint32_t jmax = min((uint32_t)FT_TILE, n - base);
@@ -332,13 +106,15 @@ knn_presample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *_
     }
     __syncthreads();
   }
-  if (act) {
-    float t = CUDART_INF_F;
+  if (act) { // partial list (chunk, query): kp keys ascending; the index only has to be unique
+    double *od = out_key + ((size_t)blockIdx.y * nq + q) * kp;
+    uint32_t *oi = out_idx + ((size_t)blockIdx.y * nq + q) * kp;
 #pragma unroll
     for (int e = 0; e < PS_KP; ++e)
-      if (e == kp - 1)
-        t = keys[e];
-    coarse[q] = t; // +inf when fewer than kp sampled nodes are candidates
+      if (e < kp) {
+        od[e] = keys[e] < CUDART_INF_F ? (double)keys[e] : CUDART_INF;
+        oi[e] = keys[e] < CUDART_INF_F ? blockIdx.y * (uint32_t)kp + (uint32_t)e : PRGPU_INVALID_INDEX;
+      }
   }
 }
 
@@ -696,15 +472,15 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   if (cap > 4096)
     cap = 4096;
 
-  // ---- pass 1: thresholds from a 1/32 sample (list-maintaining kernel on few tiles) ----
-  // (one query per thread and few node chunks: every (query, chunk) list pays a warm-up transient)
-  const size_t smem1 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t) + (size_t)kp * FT_THREADS * 8;
-  auto samp = knn_filter_kernel<DIM, 1>;
-  PRGPU_CUDA_TRY(cudaFuncSetAttribute(samp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  // ---- pass 1: thresholds from strided sub-samples (pre-sample, then the sample seeded with it) ----
+  const size_t smem1 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t);
+  auto samp = knn_sample_kernel<DIM>;
   const uint32_t nsamp = (ntiles + FT_SAMPLE_STRIDE - 1) / FT_SAMPLE_STRIDE;
   const uint32_t qblocks1 = (nq + FT_THREADS - 1) / FT_THREADS;
-  uint32_t chunks1 = (uint32_t)(8 * sm_count) / qblocks1;
+  uint32_t chunks1 = (uint32_t)(4 * sm_count) / qblocks1;
   chunks1 = chunks1 < 1 ? 1 : chunks1;
+  if (chunks1 > 128)
+    chunks1 = 128;
   if (chunks1 > nsamp)
     chunks1 = nsamp;
   const uint32_t tpc1 = (nsamp + chunks1 - 1) / chunks1;
@@ -736,18 +512,21 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   uint32_t *cidx = sc.flags + 3 * (size_t)nq + 1;
   float *ckey = reinterpret_cast<float *>(cidx + (size_t)nq * cap);
   PRGPU_CUDA_TRY(cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t), stream));
-  // pass 1a: a 32x coarser sub-sample (one chunk per query block) absorbs the warm-up flood of
-  // candidates; its threshold (an upper bound for 1b's) lands in `coarse_buf`, which aliases `counts`
-  // -- the counters are zeroed by the last threshold kernel, after 1b has read the coarse bounds
+  // pre-sample: one chunk, 32x coarser; its kp-th key seeds the sample pass.  The bound is kept in
+  // `coarse_buf`, which aliases `counts`: the counters are zeroed by the last threshold kernel, after the
+  // sample pass has read its seeds.
   float *coarse_buf = reinterpret_cast<float *>(counts);
   {
     const uint32_t stride_a = FT_SAMPLE_STRIDE * 32;
-    const size_t smem0 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t);
-    knn_presample_kernel<DIM><<<qblocks1, FT_THREADS, smem0, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, stride_a,
-                                                                      coarse_buf);
+    const uint32_t nsamp_a = (ntiles + stride_a - 1) / stride_a;
+    samp<<<dim3(qblocks1, 1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, stride_a, nsamp_a, nullptr,
+                                                          sc.cand_dist, sc.cand_idx);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, nullptr, coarse_buf,
+                                                               nullptr);
     PRGPU_CUDA_TRY(cudaGetLastError());
   }
-  samp<<<dim3(qblocks1, chunks1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, tpc1, FT_SAMPLE_STRIDE,
+  samp<<<dim3(qblocks1, chunks1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, FT_SAMPLE_STRIDE, tpc1,
                                                             coarse_buf, pk, pi);
   PRGPU_CUDA_TRY(cudaGetLastError());
   if (chunks1 > 1) {
