@@ -221,14 +221,24 @@ knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__r
     for (; p + 1 < npair; p += 2) {
       const float4 a0 = pairs[4 * p], a1 = pairs[4 * p + 1], a2 = pairs[4 * p + 2], a3 = pairs[4 * p + 3];
       const float4 b0 = pairs[4 * p + 4], b1 = pairs[4 * p + 5], b2 = pairs[4 * p + 6], b3 = pairs[4 * p + 7];
+      // all 2*RQ key chains first (independent FFMA2 chains interleave), the rare emits afterwards
+      float2 ka[FT_RQ], kb[FT_RQ];
 #pragma unroll
       for (int u = 0; u < FT_RQ; ++u) {
-        const float2 ka = keys_of(u, a0, a1, a2, a3), kb = keys_of(u, b0, b1, b2, b3);
-        if (fminf(fminf(ka.x, ka.y), fminf(kb.x, kb.y)) <= thr[u]) {
-          emit(u, ka.x, base + 2 * p);
-          emit(u, ka.y, base + 2 * p + 1);
-          emit(u, kb.x, base + 2 * p + 2);
-          emit(u, kb.y, base + 2 * p + 3);
+        ka[u] = keys_of(u, a0, a1, a2, a3);
+        kb[u] = keys_of(u, b0, b1, b2, b3);
+      }
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < FT_RQ; ++u)
+        any = any || fminf(fminf(ka[u].x, ka[u].y), fminf(kb[u].x, kb[u].y)) <= thr[u];
+      if (any) {
+#pragma unroll
+        for (int u = 0; u < FT_RQ; ++u) {
+          emit(u, ka[u].x, base + 2 * p);
+          emit(u, ka[u].y, base + 2 * p + 1);
+          emit(u, kb[u].x, base + 2 * p + 2);
+          emit(u, kb[u].y, base + 2 * p + 3);
         }
       }
     }
