@@ -125,9 +125,13 @@ knn_sample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
 // fma.rn.f32x2 (FFMA2, sm_100) advances the keys of two nodes for one query: 3.5 issue slots per
 // (query, node) pair instead of 7, with the pair tile broadcast to 4 queries per thread.
 constexpr int CT_TILE = 256; // nodes per tile of the collect kernel
+#ifndef CT_MINB
+#define CT_MINB 8 // resident blocks per SM the collect kernel is compiled for (64 registers)
+#endif
+constexpr uint32_t CT_WAVES = 32; // grid size of the collect kernel in units of resident blocks
 
 template <int DIM>
-__global__ void __launch_bounds__(FT_THREADS)
+__global__ void __launch_bounds__(FT_THREADS, CT_MINB)
 knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
                    const uint32_t *__restrict__ lo, const float *__restrict__ thresh, uint32_t tiles_per_chunk,
                    uint32_t cap, uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx,
@@ -558,6 +562,9 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   const uint32_t ntiles2 = (t.n + CT_TILE - 1) / CT_TILE;
   uint32_t chunks = (uint32_t)(per_sm * sm_count) / qblocks;
   chunks = chunks < 1 ? 1 : chunks;
+  // many short blocks instead of one wave of long ones: the blocks resident on an SM do not advance at
+  // the same rate, and a one-wave grid ran its last third at 4.4 of 6 warps per scheduler (ncu r01d)
+  chunks *= CT_WAVES;
   if (chunks > ntiles2)
     chunks = ntiles2;
   const uint32_t tiles_per_chunk = (ntiles2 + chunks - 1) / chunks;
