@@ -77,7 +77,7 @@ static int knn_reserve(prgpu_knn *h, uint64_t need) {
   float *nf = nullptr;
   PRGPU_CUDA_TRY(cudaMalloc(&np, (size_t)h->dim * cap * sizeof(double)));
   if (h->dim <= 7)
-    PRGPU_CUDA_TRY(cudaMalloc(&nf, (size_t)cap * 8 * sizeof(float)));
+    PRGPU_CUDA_TRY(cudaMalloc(&nf, (size_t)cap * 18 * sizeof(float))); // fp32 mirror | TF32 mirror | |x|^2 pairs
   if (!h->xmax2) {
     PRGPU_CUDA_TRY(cudaMalloc(&h->xmax2, sizeof(double)));
     PRGPU_CUDA_TRY(cudaMemsetAsync(h->xmax2, 0, sizeof(double), h->stream));
@@ -86,8 +86,13 @@ static int knn_reserve(prgpu_knn *h, uint64_t need) {
     for (int d = 0; d < h->dim; ++d)
       PRGPU_CUDA_TRY(cudaMemcpyAsync(np + (size_t)d * cap, h->pts + (size_t)d * h->stride,
                                      h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if (nf && h->ptsf)
+    if (nf && h->ptsf) {
       PRGPU_CUDA_TRY(cudaMemcpyAsync(nf, h->ptsf, h->n * 8 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(nf + cap * 8, h->ptsf + h->stride * 8, h->n * 8 * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, h->stream));
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(nf + cap * 16, h->ptsf + h->stride * 16, (h->n + 1) / 2 * 4 * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, h->stream));
+    }
     PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
     cudaFree(h->pts);
     if (h->ptsf)

@@ -297,6 +297,11 @@ topk_merge_kernel(const uint32_t *__restrict__ idx_parts, const double *__restri
   warp_merge(get, P, k, dist_out + ((size_t)g * nq + q) * k, idx_out + ((size_t)g * nq + q) * k);
 }
 
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
 // row-major (n x dim) -> fp64 SoA at `offset`, plus the fp32 mirror (8 floats per node, |x|^2 in slot 7)
 // and the running maximum of |x|^2
 __global__ void transpose_append_kernel(const double *__restrict__ aos, uint64_t n, int dim,
@@ -318,6 +323,14 @@ __global__ void transpose_append_kernel(const double *__restrict__ aos, uint64_t
       float4 *o = reinterpret_cast<float4 *>(ptsf + (offset + i) * 8);
       o[0] = make_float4(f[0], f[1], f[2], f[3]);
       o[1] = make_float4(f[4], f[5], f[6], f[7]);
+      // TF32 mirror for the tensor-core scan: coordinates rounded to nearest TF32, 1.0 in slot 7 (the
+      // multiplier of the per-query threshold), |x|^2 kept in fp32 in its own (pair-duplicated) array
+      float4 *ot = reinterpret_cast<float4 *>(ptsf + stride * 8 + (offset + i) * 8);
+      ot[0] = make_float4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
+      ot[1] = make_float4(to_tf32(f[4]), to_tf32(f[5]), to_tf32(f[6]), 1.0f);
+      float *nd = ptsf + stride * 16 + ((offset + i) >> 1) * 4 + ((offset + i) & 1); // (n2a, n2b, n2a, n2b) per node pair:
+      nd[0] = f[7];                                                                  // the C fragment of one MMA lane
+      nd[2] = f[7];
     }
   }
 #pragma unroll

@@ -30,6 +30,9 @@ struct KnnScratch {                // per-handle device scratch for partial resu
 //         is allocated (not necessarily initialised) up to `stride` per dimension.  The reference values.
 //  ptsf : fp32 mirror for the filter pass, 8 floats per node: x_0..x_6 rounded to fp32 (0 beyond dim) and
 //         |x|^2 in slot 7.  NULL when dim == 8 (no free slot): such trees always take the exact path.
+//         The same allocation continues with the TF32 mirror of the tensor-core scan (ptsf + 8 * stride:
+//         8 floats per node, x_0..x_6 rounded to TF32, 1.0 in slot 7) and the fp32 |x|^2 array
+//         (ptsf + 16 * stride: 4 floats per node pair, (n2a, n2b, n2a, n2b)).
 //  xmax2: device scalar, max |x|^2 over the nodes (bounds the filter's rounding error).
 struct KnnTreeView {
   const double *pts;

@@ -29,7 +29,6 @@ namespace {
 constexpr int FT_TILE = 128;     // nodes per tile (32 bytes each)
 constexpr int FT_THREADS = 128;  // queries per block
 
-constexpr int FT_RQ = 4;         // queries per thread in the collect pass (register tile over the broadcast node tile)
 
 // Pass 1 (run twice: a 32x coarser pre-sample, then the sample proper seeded with the pre-sample's
 // threshold): the KP smallest keys of every query over a strided sub-sample of the tree.  One thread =
@@ -118,85 +117,107 @@ knn_sample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
   }
 }
 
-// Pass 2: full scan.  A node is a candidate of query q iff key(q, node) <= T_q (the threshold from
-// the sample pass) and node >= lo_q; candidates are appended to the query's global buffer.  The hot
-// loop holds no per-query state besides the threshold.  Each tile (one bulk copy of 32-byte node
-// records) is re-laid in shared memory as node PAIRS, coordinate-interleaved, so that one packed
-// fma.rn.f32x2 (FFMA2, sm_100) advances the keys of two nodes for one query: 3.5 issue slots per
-// (query, node) pair instead of 7, with the pair tile broadcast to 4 queries per thread.
-constexpr int CT_TILE = 256; // nodes per tile of the collect kernel
+// Pass 2: full scan on the tensor cores.  For query q and node x the scan evaluates
+//     D(q, x) = |x|^2 - 2 q.x - T_q
+// as one 16x8x8 TF32 mma.sync per 16 queries x 8 nodes: A = 16 queries x 8 slots (-2 q_d rounded to
+// TF32 in slots 0..6, -T_q in slot 7), B = 8 slots x 8 nodes (the TF32 mirror record, 1.0 in slot 7),
+// C = |x|^2 in fp32.  A node is a candidate of q iff the sign bit of D is set and node >= lo_q; the
+// candidate's D is stored as its key (same order as the key itself for one query).  The hot loop is
+// 2 LDS.64 + 4 MMA + 8 LOP3 + 1 branch per 64 queries x 8 nodes and holds no per-query state besides
+// the A fragments.  The contraction is only 7 long, so this is not a GEMM worth the tcgen05/TMEM path:
+// the output (one value per pair, consumed in place) is the bottleneck, TMEM read-out runs at 16
+// values/clk/SM, while the warp-level MMA leaves D in registers at 60 values/clk/SM (measured,
+// scripts/ubench/mma_tf32.cu) against 18/clk/SM for 7 FFMA per pair.
+//
+// Error of D against the real |x|^2 - 2 q.x - T_q (eps_tc in knn_select_kernel): both factors of every
+// product are within 2^-11 (1 + 2^-12) relative of the fp64 values (fp32 then TF32 rounding), products
+// of TF32 numbers are exact, so the dot product is off by at most 2^-9 (1 + 2^-10) |q| |x|
+// (Cauchy-Schwarz on 2 |q_d| |x_d| 2^-10); the accumulation of 8 products and C in the tensor core
+// (>= fp32 precision, truncating) is bounded generously by 2^-18 ((|x| + |q|)^2 + |T_q|).
+constexpr int CT_TILE = 256;      // nodes per tile of the collect kernel
+constexpr int CT_MT = 4;          // 16-query MMA row blocks per warp
+constexpr int CT_QPB = (FT_THREADS / 32) * CT_MT * 16; // queries per block (256)
 #ifndef CT_MINB
 #define CT_MINB 8 // resident blocks per SM the collect kernel is compiled for (64 registers)
 #endif
 constexpr uint32_t CT_WAVES = 32; // grid size of the collect kernel in units of resident blocks
 
+__device__ __forceinline__ uint32_t tf32_bits(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return u;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], float2 b, const float4 &c) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "f"(c.x),
+        "f"(c.y), "f"(c.z), "f"(c.w));
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS, CT_MINB)
-knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
-                   const uint32_t *__restrict__ lo, const float *__restrict__ thresh, uint32_t tiles_per_chunk,
-                   uint32_t cap, uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx,
-                   float *__restrict__ cand_key) {
+knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f, uint32_t n,
+                   const double *__restrict__ queries, uint32_t nq, const uint32_t *__restrict__ lo,
+                   const float *__restrict__ thresh, uint32_t tiles_per_chunk, uint32_t cap,
+                   uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx, float *__restrict__ cand_key) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                     // [2][CT_TILE][2]   node records
-  float4 *pairs = tile + 2 * CT_TILE * 2;                                  // [CT_TILE/2][4]    pair records
-  uint64_t *bars = reinterpret_cast<uint64_t *>(pairs + (CT_TILE / 2) * 4); // [2]
+  float *recs = reinterpret_cast<float *>(smem_raw);                        // [2][CT_TILE][8] TF32 records
+  float *n2s = recs + 2 * CT_TILE * 8;                                      // [2][CT_TILE/2][4] |x|^2 pairs
+  uint64_t *bars = reinterpret_cast<uint64_t *>(n2s + 2 * CT_TILE * 2);     // [2]
   __shared__ uint32_t s_lo_min;
-  const int tid = threadIdx.x;
-  uint32_t qid[FT_RQ], my_lo[FT_RQ];
-  float2 q2[FT_RQ][7]; // (-2 q_d, -2 q_d)
-  float thr[FT_RQ];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const uint32_t qbase = blockIdx.x * CT_QPB + warp * (CT_MT * 16);
+  // A fragments.  MMA slot s <-> coordinate: slot t <-> 2t, slot t+4 <-> 2t+1, so that the B fragment of
+  // a lane (slots t and t+4 of node g) is one 8-byte word of the node record.
+  auto aval = [&](uint32_t row, int d) -> uint32_t {
+    if (row >= nq)
+      return 0u; // D = |x|^2 >= +0: never a candidate
+    if (d < DIM)
+      return tf32_bits((float)(-2.0 * queries[(size_t)row * DIM + d]));
+    if (d == 7)
+      return __float_as_uint(-thresh[row]); // already a TF32 number (knn_threshold_kernel)
+    return 0u;
+  };
+  uint32_t a[CT_MT][4];
 #pragma unroll
-  for (int u = 0; u < FT_RQ; ++u) {
-    qid[u] = (blockIdx.x * FT_RQ + u) * FT_THREADS + tid;
-    const bool act = qid[u] < nq;
-#pragma unroll
-    for (int d = 0; d < 7; ++d) {
-      const float v = (act && d < DIM) ? (float)(-2.0 * queries[(size_t)qid[u] * DIM + d]) : 0.f;
-      q2[u][d] = make_float2(v, v);
-    }
-    my_lo[u] = (act && lo) ? lo[qid[u]] : (act ? 0u : 0xFFFFFFFFu);
-    thr[u] = act ? thresh[qid[u]] : -CUDART_INF_F;
+  for (int mt = 0; mt < CT_MT; ++mt) {
+    const uint32_t r0 = qbase + mt * 16 + g, r1 = r0 + 8;
+    a[mt][0] = aval(r0, 2 * t4);
+    a[mt][1] = aval(r1, 2 * t4);
+    a[mt][2] = aval(r0, 2 * t4 + 1);
+    a[mt][3] = aval(r1, 2 * t4 + 1);
   }
   if (tid == 0) {
-    s_lo_min = 0xFFFFFFFFu;
+    s_lo_min = lo ? 0xFFFFFFFFu : 0u;
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
-#pragma unroll
-  for (int u = 0; u < FT_RQ; ++u)
-    atomicMin(&s_lo_min, my_lo[u]);
-  __syncthreads();
+  if (lo) {
+    for (uint32_t r = blockIdx.x * CT_QPB + tid; r < min(nq, (blockIdx.x + 1) * CT_QPB); r += FT_THREADS)
+      atomicMin(&s_lo_min, lo[r]);
+    __syncthreads();
+  }
   const uint32_t ntiles = (n + CT_TILE - 1) / CT_TILE;
   uint32_t t0 = blockIdx.y * tiles_per_chunk;
   const uint32_t t1 = min(t0 + tiles_per_chunk, ntiles);
   if (s_lo_min != 0xFFFFFFFFu)
     t0 = max(t0, s_lo_min / CT_TILE);
   auto issue = [&](uint32_t t, int buf) {
-    mbar_expect_tx(&bars[buf], CT_TILE * 32);
-    bulk_g2s(tile + buf * CT_TILE * 2, ptsf + (size_t)t * CT_TILE * 8, CT_TILE * 32, &bars[buf]);
+    mbar_expect_tx(&bars[buf], CT_TILE * 40);
+    bulk_g2s(recs + buf * CT_TILE * 8, ptst + (size_t)t * CT_TILE * 8, CT_TILE * 32, &bars[buf]);
+    bulk_g2s(n2s + buf * CT_TILE * 2, n2f + (size_t)t * CT_TILE * 2, CT_TILE * 8, &bars[buf]);
   };
-  auto emit = [&](int u, float key, uint32_t gi) {
-    if (key <= thr[u] && gi >= my_lo[u] && gi < n) {
-      const uint32_t slot = atomicAdd(cand_count + qid[u], 1u);
+  auto emit = [&](uint32_t row, uint32_t gi, float dv) {
+    if (gi < n && row < nq && (!lo || gi >= lo[row])) {
+      const uint32_t slot = atomicAdd(cand_count + row, 1u);
       if (slot < cap) {
-        cand_idx[(size_t)qid[u] * cap + slot] = gi;
-        cand_key[(size_t)qid[u] * cap + slot] = key;
+        cand_idx[(size_t)row * cap + slot] = gi;
+        cand_key[(size_t)row * cap + slot] = dv;
       }
     }
-  };
-  // keys of the node pair whose record is (v0..v3) for query slot u
-  auto keys_of = [&](int u, const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3) {
-    float2 acc = make_float2(v3.z, v3.w); // (|x_a|^2, |x_b|^2)
-    acc = __ffma2_rn(q2[u][0], make_float2(v0.x, v0.y), acc);
-    if (DIM > 1) acc = __ffma2_rn(q2[u][1], make_float2(v0.z, v0.w), acc);
-    if (DIM > 2) acc = __ffma2_rn(q2[u][2], make_float2(v1.x, v1.y), acc);
-    if (DIM > 3) acc = __ffma2_rn(q2[u][3], make_float2(v1.z, v1.w), acc);
-    if (DIM > 4) acc = __ffma2_rn(q2[u][4], make_float2(v2.x, v2.y), acc);
-    if (DIM > 5) acc = __ffma2_rn(q2[u][5], make_float2(v2.z, v2.w), acc);
-    if (DIM > 6) acc = __ffma2_rn(q2[u][6], make_float2(v3.x, v3.y), acc);
-    return acc;
   };
   if (tid == 0 && t0 < t1)
     issue(t0, 0);
@@ -206,57 +227,42 @@ knn_collect_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__r
     if (tid == 0 && t + 1 < t1)
       issue(t + 1, buf ^ 1);
     mbar_wait(&bars[buf], parity);
-    // node records -> pair records: (x0a,x0b,x1a,x1b) (x2a,x2b,x3a,x3b) (x4a,x4b,x5a,x5b) (x6a,x6b,n2a,n2b)
-    {
-      const float4 *T = tile + buf * CT_TILE * 2;
-#pragma unroll
-      for (int it = 0; it < (CT_TILE / 2 * 2) / FT_THREADS; ++it) {
-        const int w = it * FT_THREADS + tid; // (pair, half)
-        const int p = w >> 1, h = w & 1;
-        const float4 a = T[2 * (2 * p) + h], b = T[2 * (2 * p + 1) + h];
-        pairs[4 * p + 2 * h] = make_float4(a.x, b.x, a.y, b.y);
-        pairs[4 * p + 2 * h + 1] = make_float4(a.z, b.z, a.w, b.w);
-      }
-    }
-    __syncthreads();
+    const float2 *R = reinterpret_cast<const float2 *>(recs + buf * CT_TILE * 8) + g * 4 + t4;
+    const float4 *N2 = reinterpret_cast<const float4 *>(n2s + buf * CT_TILE * 2) + t4;
     const uint32_t base = t * CT_TILE;
-    const uint32_t npair = (min((uint32_t)CT_TILE, n - base) + 1) / 2;
-    uint32_t p = 0;
-    for (; p + 1 < npair; p += 2) {
-      const float4 a0 = pairs[4 * p], a1 = pairs[4 * p + 1], a2 = pairs[4 * p + 2], a3 = pairs[4 * p + 3];
-      const float4 b0 = pairs[4 * p + 4], b1 = pairs[4 * p + 5], b2 = pairs[4 * p + 6], b3 = pairs[4 * p + 7];
-      // all 2*RQ key chains first (independent FFMA2 chains interleave), the rare emits afterwards
-      float2 ka[FT_RQ], kb[FT_RQ];
+#pragma unroll 2
+    for (int nt = 0; nt < CT_TILE / 8; ++nt) {
+      const float2 b = R[nt * 32];  // node nt*8+g, slots (t, t+4)
+      const float4 c = N2[nt * 4];  // |x|^2 of nodes nt*8+2t, nt*8+2t+1 (the lane's two output columns), twice
+      float d[CT_MT][4];
 #pragma unroll
-      for (int u = 0; u < FT_RQ; ++u) {
-        ka[u] = keys_of(u, a0, a1, a2, a3);
-        kb[u] = keys_of(u, b0, b1, b2, b3);
-      }
-      bool any = false;
+      for (int mt = 0; mt < CT_MT; ++mt)
+        mma_tf32_16x8x8(d[mt], a[mt], b, c);
+      uint32_t m = 0;
 #pragma unroll
-      for (int u = 0; u < FT_RQ; ++u)
-        any = any || fminf(fminf(ka[u].x, ka[u].y), fminf(kb[u].x, kb[u].y)) <= thr[u];
-      if (any) {
+      for (int mt = 0; mt < CT_MT; ++mt)
+        m |= __float_as_uint(d[mt][0]) | __float_as_uint(d[mt][1]) | __float_as_uint(d[mt][2]) |
+             __float_as_uint(d[mt][3]);
+      if (m & 0x80000000u) {
 #pragma unroll
-        for (int u = 0; u < FT_RQ; ++u) {
-          emit(u, ka[u].x, base + 2 * p);
-          emit(u, ka[u].y, base + 2 * p + 1);
-          emit(u, kb[u].x, base + 2 * p + 2);
-          emit(u, kb[u].y, base + 2 * p + 3);
-        }
-      }
-    }
-    for (; p < npair; ++p) {
-      const float4 a0 = pairs[4 * p], a1 = pairs[4 * p + 1], a2 = pairs[4 * p + 2], a3 = pairs[4 * p + 3];
+        for (int mt = 0; mt < CT_MT; ++mt)
 #pragma unroll
-      for (int u = 0; u < FT_RQ; ++u) {
-        const float2 ka = keys_of(u, a0, a1, a2, a3);
-        emit(u, ka.x, base + 2 * p);
-        emit(u, ka.y, base + 2 * p + 1);
+          for (int j = 0; j < 4; ++j)
+            if (__float_as_uint(d[mt][j]) & 0x80000000u)
+              emit(qbase + mt * 16 + g + (j >> 1) * 8, base + nt * 8 + 2 * t4 + (j & 1), d[mt][j]);
       }
     }
     __syncthreads();
   }
+}
+
+// smallest TF32 number >= v (v finite or +inf)
+__device__ __forceinline__ float tf32_round_up(float v) {
+  uint32_t b = __float_as_uint(v);
+  if ((b & 0x7F800000u) == 0x7F800000u)
+    return v;
+  b = (b & 0x80000000u) ? (b & ~0x1FFFu) : ((b + 0x1FFFu) & ~0x1FFFu);
+  return __uint_as_float(b);
 }
 
 // threshold of every query = kp-th smallest key of the sample (last entry of its merged list)
@@ -268,28 +274,30 @@ __global__ void knn_threshold_kernel(const double *__restrict__ cand_key, const 
   const bool full = cand_idx[(size_t)q * kp + kp - 1] != PRGPU_INVALID_INDEX;
   // list not full: fewer than kp sampled nodes lie below the coarser bound (or no bound: keep all)
   const float t = full ? (float)cand_key[(size_t)q * kp + kp - 1] : (coarse ? coarse[q] : CUDART_INF_F);
-  thresh[q] = t;
+  thresh[q] = tf32_round_up(t); // the scan multiplies it on the tensor cores: must be a TF32 number
   if (counts)
     counts[q] = 0;
 }
 
-// Pass 3: one block per query, two levels.
-//  (a) on the stored fp32 keys: the k-th smallest key kk of the candidates; a candidate whose key exceeds
-//      kk + 2 eps has an exact value above that of each of the k smallest-key candidates (all keys are
-//      within eps of the real |x|^2 - 2 q.x), so only the survivors with key <= kk + 2 eps -- usually
-//      k plus a few -- can be among the k nearest;
-//  (b) exact fp64 distance (the reference's operation order) of the survivors only, k rounds of arg-min
-//      under (distance, index), then the proof against the nodes the scan discarded (key > T_q): their
-//      exact squared distance is >= T_q - eps + |q|^2, which must lie strictly above the k-th selected.
-// Unproven queries, overflowed candidate buffers and survivor lists longer than 64 are flagged for the
-// exact kernel.
+// Pass 3: one block per query, three levels.
+//  (a) on the stored TF32 keys D: the k-th smallest, kk.  Every D is within eps_tc of the real value, so
+//      a candidate with D > kk + 2 eps_tc has a real key above that of each of the k smallest-D
+//      candidates and cannot be among the k nearest: the others (a few dozen) are the level-1 survivors;
+//  (b) their keys are recomputed with the fp32 FMA chain of the sample pass (error eps_32, a thousand
+//      times smaller) and cut again at (k-th smallest) + 2 eps_32: usually k plus a few remain;
+//  (c) exact fp64 distance (the reference's operation order) of those, k rounds of arg-min under
+//      (distance, index), then the proof against the nodes the scan discarded (D >= +0): their exact
+//      squared distance is >= T_q - eps_tc + |q|^2, which must lie strictly above the k-th selected.
+// Unproven queries, overflowed candidate buffers and over-long survivor lists are flagged for the exact
+// kernel.
 constexpr int SEL_THREADS = 128;
-constexpr int SEL_MAX_SURVIVORS = 64;
+constexpr int SEL_MAX_L1 = 512;        // level-1 survivors
+constexpr int SEL_MAX_SURVIVORS = 64;  // level-2 survivors
 template <int DIM>
 __global__ void __launch_bounds__(SEL_THREADS)
-knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t index_base, const double *__restrict__ xmax2,
-                  const double *__restrict__ queries, const float *__restrict__ thresh, uint32_t cap,
-                  const uint32_t *__restrict__ cand_count, const uint32_t *__restrict__ cand_idx,
+knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf, uint64_t stride, uint32_t index_base,
+                  const double *__restrict__ xmax2, const double *__restrict__ queries, const float *__restrict__ thresh,
+                  uint32_t cap, const uint32_t *__restrict__ cand_count, const uint32_t *__restrict__ cand_idx,
                   const float *__restrict__ cand_key, int k, uint32_t *__restrict__ idx_out,
                   double *__restrict__ dist_out, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char sel_raw[];
@@ -297,11 +305,13 @@ knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t inde
   float *wkey = okey + cap;                         // [cap] working copy (selected entries -> +inf)
   __shared__ float red_k[SEL_THREADS / 32];
   __shared__ uint32_t red_p[SEL_THREADS / 32];
+  __shared__ uint32_t l1_i[SEL_MAX_L1];
+  __shared__ float l1_k[SEL_MAX_L1], l1_w[SEL_MAX_L1];
   __shared__ double sv_d[SEL_MAX_SURVIVORS];
   __shared__ uint32_t sv_i[SEL_MAX_SURVIVORS];
-  __shared__ uint32_t n_sv;
+  __shared__ uint32_t n_l1, n_sv;
   __shared__ float s_kk;
-  __shared__ double s_eps, s_qn2;
+  __shared__ double s_eps_tc, s_eps32, s_qn2;
   const uint32_t q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cnt = cand_count[q];
@@ -319,14 +329,19 @@ knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t inde
 #pragma unroll
   for (int d = 0; d < DIM; ++d)
     qx[d] = queries[(size_t)q * DIM + d];
+  const float T = thresh[q];
   if (tid == 0) {
     double qn2 = 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
       qn2 += qx[d] * qx[d];
     const double xn = sqrt(*xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
-    s_eps = 16.0 * 5.9604644775390625e-08 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
+    const double u24 = 5.9604644775390625e-08;
+    s_eps32 = 16.0 * u24 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
+    const double at = T < CUDART_INF_F ? fabs((double)T) : 0.0;
+    s_eps_tc = 1.01 * 0.001953125 * qn * xn + 3.814697265625e-06 * ((xn + qn) * (xn + qn) + at) + 1e-30;
     s_qn2 = qn2;
+    n_l1 = 0;
     n_sv = 0;
   }
   for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
@@ -335,51 +350,92 @@ knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t inde
     wkey[c] = kv;
   }
   __syncthreads();
-  // (a) k-th smallest stored key (k rounds of block-wide arg-min)
-  const int rounds = (int)min((uint32_t)k, cnt);
-  for (int r = 0; r < rounds; ++r) {
-    float bk = CUDART_INF_F;
-    uint32_t bp = 0xFFFFFFFFu;
-    for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
-      const float v = wkey[c];
-      if (v < bk || (v == bk && c < bp)) {
-        bk = v;
-        bp = c;
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float ok = __shfl_xor_sync(0xffffffffu, bk, off);
-      const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
-      if (ok < bk || (ok == bk && op < bp)) {
-        bk = ok;
-        bp = op;
-      }
-    }
-    if (lane == 0) {
-      red_k[warp] = bk;
-      red_p[warp] = bp;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < SEL_THREADS / 32; ++w)
-        if (red_k[w] < bk || (red_k[w] == bk && red_p[w] < bp)) {
-          bk = red_k[w];
-          bp = red_p[w];
+  // k-th smallest entry of w[0..m) by k rounds of block-wide arg-min (selected entries are overwritten)
+  auto kth_smallest = [&](float *w, uint32_t m) {
+    const int rounds = (int)min((uint32_t)k, m);
+    for (int r = 0; r < rounds; ++r) {
+      float bk = CUDART_INF_F;
+      uint32_t bp = 0xFFFFFFFFu;
+      for (uint32_t c = tid; c < m; c += SEL_THREADS) {
+        const float v = w[c];
+        if (v < bk || (v == bk && c < bp)) {
+          bk = v;
+          bp = c;
         }
-      if (bp != 0xFFFFFFFFu)
-        wkey[bp] = CUDART_INF_F;
-      s_kk = bk;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, bk, off);
+        const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
+        if (ok < bk || (ok == bk && op < bp)) {
+          bk = ok;
+          bp = op;
+        }
+      }
+      if (lane == 0) {
+        red_k[warp] = bk;
+        red_p[warp] = bp;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w2 = 1; w2 < SEL_THREADS / 32; ++w2)
+          if (red_k[w2] < bk || (red_k[w2] == bk && red_p[w2] < bp)) {
+            bk = red_k[w2];
+            bp = red_p[w2];
+          }
+        if (bp != 0xFFFFFFFFu)
+          w[bp] = CUDART_INF_F;
+        s_kk = bk;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  // survivors: everything whose key is within 2 eps of the k-th smallest key (all, if fewer than k)
-  const float cut = cnt <= (uint32_t)k ? CUDART_INF_F : (float)((double)s_kk + 2.0 * s_eps) * (1.0f + 1e-6f) + 1e-30f;
+  };
+  // (a) level-1 survivors on the stored keys
+  kth_smallest(wkey, cnt);
+  const float cut1 =
+      cnt <= (uint32_t)k ? CUDART_INF_F : (float)((double)s_kk + 2.0 * s_eps_tc) * (1.0f + 1e-6f) + 1e-30f;
   for (uint32_t c = tid; c < cnt; c += SEL_THREADS)
-    if (okey[c] <= cut) {
+    if (okey[c] <= cut1) {
+      const uint32_t slot = atomicAdd(&n_l1, 1u);
+      if (slot < SEL_MAX_L1)
+        l1_i[slot] = cand_idx[(size_t)q * cap + c];
+    }
+  __syncthreads();
+  const uint32_t n1 = n_l1;
+  if (n1 > SEL_MAX_L1) {
+    flag_me();
+    return;
+  }
+  // (b) fp32 keys of the level-1 survivors (the chain of knn_sample_kernel), cut again
+  {
+    float q2[7];
+#pragma unroll
+    for (int d = 0; d < 7; ++d)
+      q2[d] = d < DIM ? (float)(-2.0 * qx[d < DIM ? d : 0]) : 0.f;
+    for (uint32_t c = tid; c < n1; c += SEL_THREADS) {
+      const float4 *rec = reinterpret_cast<const float4 *>(ptsf + (size_t)l1_i[c] * 8);
+      const float4 a = rec[0], b = rec[1];
+      float x = b.w;
+      x = fmaf(q2[0], a.x, x);
+      if (DIM > 1) x = fmaf(q2[1], a.y, x);
+      if (DIM > 2) x = fmaf(q2[2], a.z, x);
+      if (DIM > 3) x = fmaf(q2[3], a.w, x);
+      if (DIM > 4) x = fmaf(q2[4], b.x, x);
+      if (DIM > 5) x = fmaf(q2[5], b.y, x);
+      if (DIM > 6) x = fmaf(q2[6], b.z, x);
+      l1_k[c] = x;
+      l1_w[c] = x;
+    }
+  }
+  __syncthreads();
+  kth_smallest(l1_w, n1);
+  const float cut2 =
+      n1 <= (uint32_t)k ? CUDART_INF_F : (float)((double)s_kk + 2.0 * s_eps32) * (1.0f + 1e-6f) + 1e-30f;
+  for (uint32_t c = tid; c < n1; c += SEL_THREADS)
+    if (l1_k[c] <= cut2) {
       const uint32_t slot = atomicAdd(&n_sv, 1u);
       if (slot < SEL_MAX_SURVIVORS)
-        sv_i[slot] = cand_idx[(size_t)q * cap + c];
+        sv_i[slot] = l1_i[c];
     }
   __syncthreads();
   const uint32_t ns = n_sv;
@@ -387,7 +443,7 @@ knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t inde
     flag_me();
     return;
   }
-  // (b) exact distances of the survivors
+  // (c) exact distances of the survivors
   if ((uint32_t)tid < ns) {
     const uint32_t i = sv_i[tid];
     double x[DIM];
@@ -434,9 +490,8 @@ knn_select_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t inde
       dk = bd;
     }
     if (lane == 0) {
-      const float T = thresh[q];
       if (T < CUDART_INF_F) { // nodes were discarded by the scan: prove they cannot matter
-        const double bound = (double)T - s_eps + s_qn2; // lower bound of any discarded node's exact squared distance
+        const double bound = (double)T - s_eps_tc + s_qn2; // lower bound of any discarded node's exact squared distance
         const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (s_qn2 + 1.0);
         if (!(sk < bound)) {
           const uint32_t slot = atomicAdd(flags, 1u);
@@ -478,7 +533,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
                 KernelTimer *timer) {
   const int kp = k + KNN_FILTER_MARGIN;
   const uint32_t ntiles = (t.n + FT_TILE - 1) / FT_TILE;
-  const uint32_t qblocks = (nq + FT_RQ * FT_THREADS - 1) / (FT_RQ * FT_THREADS);
+  const uint32_t qblocks = (nq + CT_QPB - 1) / CT_QPB;
   // candidate buffer per query: the sample's kp-th smallest key admits ~kp*stride nodes of the full tree
   uint32_t cap = 1;
   while (cap < 3u * (uint32_t)kp * FT_SAMPLE_STRIDE)
@@ -553,7 +608,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   PRGPU_CUDA_TRY(cudaGetLastError());
 
   // ---- pass 2: full scan collecting every node at or below the threshold ----
-  const size_t smem2 = (size_t)2 * CT_TILE * 32 + (size_t)(CT_TILE / 2) * 64 + 2 * sizeof(uint64_t);
+  const size_t smem2 = (size_t)2 * CT_TILE * 40 + 2 * sizeof(uint64_t);
   auto coll = knn_collect_kernel<DIM>;
   int per_sm = 0;
   PRGPU_CUDA_TRY(cudaFuncSetAttribute(coll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -571,8 +626,8 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   chunks = (ntiles2 + tiles_per_chunk - 1) / tiles_per_chunk;
   if (timer)
     timer->begin(stream);
-  coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf, t.n, queries, nq, lo, thresh, tiles_per_chunk, cap,
-                                                           counts, cidx, ckey);
+  coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf + 8 * t.stride, t.ptsf + 16 * t.stride, t.n, queries,
+                                                           nq, lo, thresh, tiles_per_chunk, cap, counts, cidx, ckey);
   if (timer)
     timer->end(stream);
   PRGPU_CUDA_TRY(cudaGetLastError());
@@ -581,8 +636,8 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   const size_t smem3 = (size_t)cap * 8;
   auto sel = knn_select_kernel<DIM>;
   PRGPU_CUDA_TRY(cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-  sel<<<nq, SEL_THREADS, smem3, stream>>>(t.pts, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts, cidx, ckey,
-                                         k, idx_out, dist_out, sc.flags);
+  sel<<<nq, SEL_THREADS, smem3, stream>>>(t.pts, t.ptsf, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts,
+                                         cidx, ckey, k, idx_out, dist_out, sc.flags);
   PRGPU_CUDA_TRY(cudaGetLastError());
   ++sc.filter_calls;
 
