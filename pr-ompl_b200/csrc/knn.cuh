@@ -43,8 +43,8 @@ struct KnnTreeView {
   uint32_t index_base;
 };
 
-constexpr int KNN_FILTER_MARGIN = 2;   // the threshold is the (k+2)-th smallest key of the sample
-constexpr int KNN_FILTER_MAX_K = 16;   // k + margin + the 8-entry candidate buffer must fit one warp
+constexpr int KNN_FILTER_SAMPLE_RANK = 8; // the threshold is the 8-th smallest key of a 1/64 sample of the tree
+constexpr int KNN_FILTER_MAX_K = 16;   // largest k the filter path serves
 
 // exact search (always bit-identical to the reference); knn_search picks the filter path
 // (fp32 scan -> fp64 re-rank of k+8 candidates -> proof check -> exact fallback for unproven

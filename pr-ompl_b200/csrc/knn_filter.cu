@@ -1,22 +1,23 @@
-// K1 fast path: fp32 filter scan + fp64 re-rank with a proof of exactness.
+// K1 fast path: TF32 tensor-core scan + fp32 / fp64 re-rank with a proof of exactness.
 //
 // The exact kernel (knn.cu) spends 20 FP64 instructions per (query, node) pair because the
 // reference's distance forbids FMA and runs on the half-rate FP64 pipe.  For the batched shapes
-// (>= 128 queries per tree pass, k <= 24) almost all of that work only establishes that a node is
-// NOT among the k nearest.  This path does that part in fp32:
-//   key(q,x) = |x|^2 - 2 q.x  (= |q-x|^2 - |q|^2) from an fp32 mirror of the tree (8 floats per node).
-//   1. knn_sample_kernel on every 64th tile: T_q = (k+2)-th smallest key of the sample, an upper
-//      bound of the (k+2)-th smallest key of the whole tree.
-//   2. knn_collect_kernel: one pass over the tree, 7 FFMA + 1 compare per pair, each node tile
-//      broadcast from shared memory to 4 queries per thread; nodes with key <= T_q (~ (k+2)*64 per
-//      query) are appended to the query's candidate buffer.  No per-query state is updated in the loop.
-//   3. knn_select_kernel: one block per query recomputes the reference's exact fp64 distance of the
-//      candidates, selects the k first under (distance, index) -- and PROVES that no discarded node
-//      can precede them: a discarded node has key > T_q, the fp32 key is within
-//      eps = 16 * 2^-24 * (max|x| + |q|)^2 of the real value (9.1 u (|x|+|q|)^2 by the running-error
-//      bound of the 8-term FMA chain, rounded inputs included), so its exact squared distance is
-//      >= T_q - eps + |q|^2.  If the k-th exact squared distance is not strictly below that bound
-//      (ties at the cut, heavy duplication) or the buffer overflowed, the query is flagged.
+// (>= 128 queries per tree pass, k <= 16) almost all of that work only establishes that a node is
+// NOT among the k nearest.  This path does that part at reduced precision with rigorous error bounds:
+//   key(q,x) = |x|^2 - 2 q.x  (= |q-x|^2 - |q|^2).
+//   1. knn_sample_kernel (fp32 FMA, fp32 mirror of the tree) on every 64th tile: T_q = 8-th smallest
+//      key of the sample.  About 8*64 nodes of the whole tree lie below it; the chance that fewer
+//      than 16 do is that of a Gamma(8) variate below 1/8, 1.5e-12.
+//   2. knn_collect_kernel: one pass over the TF32 mirror on the tensor cores (mma.sync m16n8k8),
+//      D = key - T_q for 16 queries x 8 nodes per instruction; nodes with the sign bit of D set are
+//      appended to the query's candidate buffer.  No per-query state is updated in the loop.
+//   3. knn_select_kernel: one block per query cuts the candidates by their TF32 keys, then by
+//      recomputed fp32 keys, recomputes the reference's exact fp64 distance of the few survivors,
+//      selects the k first under (distance, index) -- and PROVES that no discarded node can precede
+//      them: a discarded node has D >= +0 and D is within eps_tc of the real value, so its exact squared
+//      distance is >= T_q - eps_tc + |q|^2.  If the k-th exact squared distance is not strictly below
+//      that bound (ties at the cut, heavy duplication, clusters far tighter than the TF32 error) or a
+//      buffer overflowed, the query is flagged.
 //   4. flagged queries are re-run through the exact kernel.  Results are therefore bit-identical to
 //      knn_search_exact for every input.
 #include <math_constants.h>
@@ -36,7 +37,7 @@ constexpr int FT_THREADS = 128;  // queries per block
 // (new[e] = min(old[e], max(old[e-1], x))), entered only when some lane of the warp has a key below
 // its current KP-th -- no per-lane divergent code, no shared-memory lists.  Node chunks (blockIdx.y)
 // emit their sorted keys as partial lists, merged like any other partial top-k tables.
-constexpr int PS_KP = KNN_FILTER_MAX_K + KNN_FILTER_MARGIN;
+constexpr int PS_KP = KNN_FILTER_SAMPLE_RANK;
 template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS)
 knn_sample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__restrict__ queries, uint32_t nq,
@@ -134,7 +135,17 @@ knn_sample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
 // of TF32 numbers are exact, so the dot product is off by at most 2^-9 (1 + 2^-10) |q| |x|
 // (Cauchy-Schwarz on 2 |q_d| |x_d| 2^-10); the accumulation of 8 products and C in the tensor core
 // (>= fp32 precision, truncating) is bounded generously by 2^-18 ((|x| + |q|)^2 + |T_q|).
-constexpr int CT_TILE = 256;      // nodes per tile of the collect kernel
+#ifndef CT_TILE_N
+#define CT_TILE_N 256
+#endif
+#ifndef CT_STAGES_N
+#define CT_STAGES_N 2
+#endif
+#ifndef CT_SWPIPE
+#define CT_SWPIPE 1
+#endif
+constexpr int CT_TILE = CT_TILE_N;      // nodes per tile of the collect kernel
+constexpr int CT_STAGES = CT_STAGES_N;      // tiles in flight per block
 constexpr int CT_MT = 4;          // 16-query MMA row blocks per warp
 constexpr int CT_QPB = (FT_THREADS / 32) * CT_MT * 16; // queries per block (256)
 #ifndef CT_MINB
@@ -161,9 +172,10 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
                    const float *__restrict__ thresh, uint32_t tiles_per_chunk, uint32_t cap,
                    uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx, float *__restrict__ cand_key) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float *recs = reinterpret_cast<float *>(smem_raw);                        // [2][CT_TILE][8] TF32 records
-  float *n2s = recs + 2 * CT_TILE * 8;                                      // [2][CT_TILE/2][4] |x|^2 pairs
-  uint64_t *bars = reinterpret_cast<uint64_t *>(n2s + 2 * CT_TILE * 2);     // [2]
+  float *recs = reinterpret_cast<float *>(smem_raw);                        // [CT_STAGES][CT_TILE][8]   TF32 records
+  float *n2s = recs + CT_STAGES * CT_TILE * 8;                              // [CT_STAGES][CT_TILE/2][4] |x|^2 pairs
+  uint64_t *full = reinterpret_cast<uint64_t *>(n2s + CT_STAGES * CT_TILE * 2); // [CT_STAGES] tile landed
+  uint64_t *empty = full + CT_STAGES;                                       // [CT_STAGES] tile consumed by every warp
   __shared__ uint32_t s_lo_min;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
@@ -190,8 +202,10 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
   }
   if (tid == 0) {
     s_lo_min = lo ? 0xFFFFFFFFu : 0u;
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < CT_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], FT_THREADS / 32);
+    }
     mbar_fence_init();
   }
   __syncthreads();
@@ -205,10 +219,16 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
   const uint32_t t1 = min(t0 + tiles_per_chunk, ntiles);
   if (s_lo_min != 0xFFFFFFFFu)
     t0 = max(t0, s_lo_min / CT_TILE);
-  auto issue = [&](uint32_t t, int buf) {
-    mbar_expect_tx(&bars[buf], CT_TILE * 40);
-    bulk_g2s(recs + buf * CT_TILE * 8, ptst + (size_t)t * CT_TILE * 8, CT_TILE * 32, &bars[buf]);
-    bulk_g2s(n2s + buf * CT_TILE * 2, n2f + (size_t)t * CT_TILE * 2, CT_TILE * 8, &bars[buf]);
+  const uint32_t ntl = t1 > t0 ? t1 - t0 : 0;
+  // A ring of CT_STAGES tiles with full/empty barriers and no block-wide barrier: the warps of a block
+  // drift up to CT_STAGES - 1 tiles apart (the rare emit paths make their pace uneven).
+  auto issue = [&](uint32_t i) { // local tile i -> slot i % CT_STAGES
+    const uint32_t slot = i % CT_STAGES, use = i / CT_STAGES;
+    if (use > 0)
+      mbar_wait(&empty[slot], (use - 1) & 1);
+    mbar_expect_tx(&full[slot], CT_TILE * 40);
+    bulk_g2s(recs + slot * CT_TILE * 8, ptst + (size_t)(t0 + i) * CT_TILE * 8, CT_TILE * 32, &full[slot]);
+    bulk_g2s(n2s + slot * CT_TILE * 2, n2f + (size_t)(t0 + i) * CT_TILE * 2, CT_TILE * 8, &full[slot]);
   };
   auto emit = [&](uint32_t row, uint32_t gi, float dv) {
     if (gi < n && row < nq && (!lo || gi >= lo[row])) {
@@ -219,25 +239,25 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
       }
     }
   };
-  if (tid == 0 && t0 < t1)
-    issue(t0, 0);
-  for (uint32_t t = t0; t < t1; ++t) {
-    const int buf = (t - t0) & 1;
-    const uint32_t parity = ((t - t0) >> 1) & 1;
-    if (tid == 0 && t + 1 < t1)
-      issue(t + 1, buf ^ 1);
-    mbar_wait(&bars[buf], parity);
-    const float2 *R = reinterpret_cast<const float2 *>(recs + buf * CT_TILE * 8) + g * 4 + t4;
-    const float4 *N2 = reinterpret_cast<const float4 *>(n2s + buf * CT_TILE * 2) + t4;
-    const uint32_t base = t * CT_TILE;
-#pragma unroll 2
-    for (int nt = 0; nt < CT_TILE / 8; ++nt) {
+  if (tid == 0)
+    for (uint32_t i = 0; i + 1 < CT_STAGES && i < ntl; ++i)
+      issue(i);
+  for (uint32_t i = 0; i < ntl; ++i) {
+    if (tid == 0 && i + CT_STAGES - 1 < ntl)
+      issue(i + CT_STAGES - 1);
+    const uint32_t slot = i % CT_STAGES;
+    mbar_wait(&full[slot], (i / CT_STAGES) & 1);
+    const float2 *R = reinterpret_cast<const float2 *>(recs + slot * CT_TILE * 8) + g * 4 + t4;
+    const float4 *N2 = reinterpret_cast<const float4 *>(n2s + slot * CT_TILE * 2) + t4;
+    const uint32_t base = (t0 + i) * CT_TILE;
+    auto load_mma = [&](int nt, float (&d)[CT_MT][4]) {
       const float2 b = R[nt * 32];  // node nt*8+g, slots (t, t+4)
       const float4 c = N2[nt * 4];  // |x|^2 of nodes nt*8+2t, nt*8+2t+1 (the lane's two output columns), twice
-      float d[CT_MT][4];
 #pragma unroll
       for (int mt = 0; mt < CT_MT; ++mt)
         mma_tf32_16x8x8(d[mt], a[mt], b, c);
+    };
+    auto check = [&](int nt, float (&d)[CT_MT][4]) {
       uint32_t m = 0;
 #pragma unroll
       for (int mt = 0; mt < CT_MT; ++mt)
@@ -246,13 +266,38 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
       if (m & 0x80000000u) {
 #pragma unroll
         for (int mt = 0; mt < CT_MT; ++mt)
+          if ((__float_as_uint(d[mt][0]) | __float_as_uint(d[mt][1]) | __float_as_uint(d[mt][2]) |
+               __float_as_uint(d[mt][3])) & 0x80000000u) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (__float_as_uint(d[mt][j]) & 0x80000000u)
-              emit(qbase + mt * 16 + g + (j >> 1) * 8, base + nt * 8 + 2 * t4 + (j & 1), d[mt][j]);
+            for (int j = 0; j < 4; ++j)
+              if (__float_as_uint(d[mt][j]) & 0x80000000u)
+                emit(qbase + mt * 16 + g + (j >> 1) * 8, base + nt * 8 + 2 * t4 + (j & 1), d[mt][j]);
+          }
       }
+    };
+    // software pipeline: the MMAs of the next 8 nodes are in flight while the signs of these are tested
+#if CT_SWPIPE
+    float dA[CT_MT][4], dB[CT_MT][4];
+    load_mma(0, dA);
+#pragma unroll 1
+    for (int nt = 0; nt < CT_TILE / 8; nt += 2) {
+      load_mma(nt + 1, dB);
+      check(nt, dA);
+      if (nt + 2 < CT_TILE / 8)
+        load_mma(nt + 2, dA);
+      check(nt + 1, dB);
     }
-    __syncthreads();
+#else
+#pragma unroll 1
+    for (int nt = 0; nt < CT_TILE / 8; ++nt) {
+      float dA[CT_MT][4];
+      load_mma(nt, dA);
+      check(nt, dA);
+    }
+#endif
+    __syncwarp();
+    if (lane == 0)
+      mbar_arrive(&empty[slot]);
   }
 }
 
@@ -531,7 +576,7 @@ template <int DIM>
 int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k, const uint32_t *lo,
                 uint32_t *idx_out, double *dist_out, KnnScratch &sc, int sm_count, cudaStream_t stream,
                 KernelTimer *timer) {
-  const int kp = k + KNN_FILTER_MARGIN;
+  const int kp = KNN_FILTER_SAMPLE_RANK;
   const uint32_t ntiles = (t.n + FT_TILE - 1) / FT_TILE;
   const uint32_t qblocks = (nq + CT_QPB - 1) / CT_QPB;
   // candidate buffer per query: the sample's kp-th smallest key admits ~kp*stride nodes of the full tree
@@ -608,7 +653,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   PRGPU_CUDA_TRY(cudaGetLastError());
 
   // ---- pass 2: full scan collecting every node at or below the threshold ----
-  const size_t smem2 = (size_t)2 * CT_TILE * 40 + 2 * sizeof(uint64_t);
+  const size_t smem2 = (size_t)CT_STAGES * CT_TILE * 40 + 2 * CT_STAGES * sizeof(uint64_t);
   auto coll = knn_collect_kernel<DIM>;
   int per_sm = 0;
   PRGPU_CUDA_TRY(cudaFuncSetAttribute(coll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
