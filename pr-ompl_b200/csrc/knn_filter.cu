@@ -141,10 +141,7 @@ knn_sample_kernel(const float *__restrict__ ptsf, uint32_t n, const double *__re
 #ifndef CT_STAGES_N
 #define CT_STAGES_N 2
 #endif
-#ifndef CT_SWPIPE
-#define CT_SWPIPE 1
-#endif
-constexpr int CT_TILE = CT_TILE_N;      // nodes per tile of the collect kernel
+constexpr int CT_TILE = CT_TILE_N;      // nodes per tile of the collect kernel (32 groups of 8: one history word)
 constexpr int CT_STAGES = CT_STAGES_N;      // tiles in flight per block
 constexpr int CT_MT = 4;          // 16-query MMA row blocks per warp
 constexpr int CT_QPB = (FT_THREADS / 32) * CT_MT * 16; // queries per block (256)
@@ -257,44 +254,35 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
       for (int mt = 0; mt < CT_MT; ++mt)
         mma_tf32_16x8x8(d[mt], a[mt], b, c);
     };
-    auto check = [&](int nt, float (&d)[CT_MT][4]) {
+    // hot loop, straight-line: the sign bits of the 16 outputs of a lane are OR-ed and shifted into a
+    // 32-bit history (one bit per 8-node group); nothing else is decided here
+    uint32_t hist = 0;
+#pragma unroll
+    for (int nt = 0; nt < CT_TILE / 8; ++nt) {
+      float d[CT_MT][4];
+      load_mma(nt, d);
       uint32_t m = 0;
 #pragma unroll
       for (int mt = 0; mt < CT_MT; ++mt)
         m |= __float_as_uint(d[mt][0]) | __float_as_uint(d[mt][1]) | __float_as_uint(d[mt][2]) |
              __float_as_uint(d[mt][3]);
-      if (m & 0x80000000u) {
-#pragma unroll
-        for (int mt = 0; mt < CT_MT; ++mt)
-          if ((__float_as_uint(d[mt][0]) | __float_as_uint(d[mt][1]) | __float_as_uint(d[mt][2]) |
-               __float_as_uint(d[mt][3])) & 0x80000000u) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (__float_as_uint(d[mt][j]) & 0x80000000u)
-                emit(qbase + mt * 16 + g + (j >> 1) * 8, base + nt * 8 + 2 * t4 + (j & 1), d[mt][j]);
-          }
-      }
-    };
-    // software pipeline: the MMAs of the next 8 nodes are in flight while the signs of these are tested
-#if CT_SWPIPE
-    float dA[CT_MT][4], dB[CT_MT][4];
-    load_mma(0, dA);
-#pragma unroll 1
-    for (int nt = 0; nt < CT_TILE / 8; nt += 2) {
-      load_mma(nt + 1, dB);
-      check(nt, dA);
-      if (nt + 2 < CT_TILE / 8)
-        load_mma(nt + 2, dA);
-      check(nt + 1, dB);
+      hist = __funnelshift_l(m, hist, 1); // (hist << 1) | sign(m): group nt ends at bit 31 - nt
     }
-#else
-#pragma unroll 1
-    for (int nt = 0; nt < CT_TILE / 8; ++nt) {
-      float dA[CT_MT][4];
-      load_mma(nt, dA);
-      check(nt, dA);
+    // rare path: the 8-node groups in which some lane saw a candidate (about 3 %) are evaluated again
+    // and their candidates appended
+    uint32_t todo = __reduce_or_sync(0xffffffffu, hist);
+    while (todo) {
+      const int nt = __clz(todo);
+      todo &= ~(0x80000000u >> nt);
+      float d[CT_MT][4];
+      load_mma(nt, d);
+#pragma unroll
+      for (int mt = 0; mt < CT_MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (__float_as_uint(d[mt][j]) & 0x80000000u)
+            emit(qbase + mt * 16 + g + (j >> 1) * 8, base + nt * 8 + 2 * t4 + (j & 1), d[mt][j]);
     }
-#endif
     __syncwarp();
     if (lane == 0)
       mbar_arrive(&empty[slot]);
@@ -589,28 +577,16 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   // ---- pass 1: thresholds from strided sub-samples (pre-sample, then the sample seeded with it) ----
   const size_t smem1 = (size_t)2 * FT_TILE * 32 + 2 * sizeof(uint64_t);
   auto samp = knn_sample_kernel<DIM>;
-  const uint32_t nsamp = (ntiles + FT_SAMPLE_STRIDE - 1) / FT_SAMPLE_STRIDE;
   const uint32_t qblocks1 = (nq + FT_THREADS - 1) / FT_THREADS;
-  uint32_t chunks1 = (uint32_t)(4 * sm_count) / qblocks1;
-  chunks1 = chunks1 < 1 ? 1 : chunks1;
-  if (chunks1 > 128)
-    chunks1 = 128;
-  if (chunks1 > nsamp)
-    chunks1 = nsamp;
-  const uint32_t tpc1 = (nsamp + chunks1 - 1) / chunks1;
-  chunks1 = (nsamp + tpc1 - 1) / tpc1;
+  // enough node chunks to fill the machine with one-thread-per-query blocks (the partial lists are merged)
+  uint32_t chunks_max = (uint32_t)(16 * sm_count) / qblocks1;
+  chunks_max = chunks_max < 1 ? 1 : (chunks_max > 128 ? 128 : chunks_max);
   int rc = scratch_reserve(sc.cand_dist, sc.cand_idx, sc.cand_capacity, (size_t)nq * kp);
   if (rc != PRGPU_OK)
     return rc;
-  double *pk = sc.cand_dist;
-  uint32_t *pi = sc.cand_idx;
-  if (chunks1 > 1) {
-    rc = scratch_reserve(sc.part_dist, sc.part_idx, sc.part_capacity, (size_t)chunks1 * nq * kp);
-    if (rc != PRGPU_OK)
-      return rc;
-    pk = sc.part_dist;
-    pi = sc.part_idx;
-  }
+  rc = scratch_reserve(sc.part_dist, sc.part_idx, sc.part_capacity, (size_t)chunks_max * nq * kp);
+  if (rc != PRGPU_OK)
+    return rc;
   // flags | thresholds | counts | candidate indices | candidate keys
   const size_t need_words = ((size_t)nq + 1) + (size_t)nq + (size_t)nq + 2 * (size_t)nq * cap;
   if (sc.flags_capacity < need_words) {
@@ -626,31 +602,35 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   uint32_t *cidx = sc.flags + 3 * (size_t)nq + 1;
   float *ckey = reinterpret_cast<float *>(cidx + (size_t)nq * cap);
   PRGPU_CUDA_TRY(cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t), stream));
-  // pre-sample: one chunk, 32x coarser; its kp-th key seeds the sample pass.  The bound is kept in
-  // `coarse_buf`, which aliases `counts`: the counters are zeroed by the last threshold kernel, after the
-  // sample pass has read its seeds.
+  // one sampling pass over every `stride`-th tile: kp-th smallest key of each query -> `out`
+  auto sample_pass = [&](uint32_t stride, const float *seed, float *out, uint32_t *zero_counts) -> int {
+    const uint32_t nsamp = (ntiles + stride - 1) / stride;
+    uint32_t ch = chunks_max > nsamp ? nsamp : chunks_max;
+    const uint32_t tpc = (nsamp + ch - 1) / ch;
+    ch = (nsamp + tpc - 1) / tpc;
+    samp<<<dim3(qblocks1, ch), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, stride, tpc, seed,
+                                                         ch > 1 ? sc.part_dist : sc.cand_dist,
+                                                         ch > 1 ? sc.part_idx : sc.cand_idx);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    if (ch > 1) {
+      const int mrc = merge_passes(sc, (int)ch, nq, kp, sc.cand_idx, sc.cand_dist, stream);
+      if (mrc != PRGPU_OK)
+        return mrc;
+    }
+    knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, seed, out, zero_counts);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    return PRGPU_OK;
+  };
+  // pre-sample, 32x coarser: its kp-th key seeds the sample pass.  The bound is kept in `coarse_buf`, which
+  // aliases `counts`: the counters are zeroed by the last threshold kernel, after the sample pass has
+  // read its seeds.
   float *coarse_buf = reinterpret_cast<float *>(counts);
-  {
-    const uint32_t stride_a = FT_SAMPLE_STRIDE * 32;
-    const uint32_t nsamp_a = (ntiles + stride_a - 1) / stride_a;
-    samp<<<dim3(qblocks1, 1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, stride_a, nsamp_a, nullptr,
-                                                          sc.cand_dist, sc.cand_idx);
-    PRGPU_CUDA_TRY(cudaGetLastError());
-    knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, nullptr, coarse_buf,
-                                                               nullptr);
-    PRGPU_CUDA_TRY(cudaGetLastError());
-  }
-  samp<<<dim3(qblocks1, chunks1), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, FT_SAMPLE_STRIDE, tpc1,
-                                                            coarse_buf, pk, pi);
-  PRGPU_CUDA_TRY(cudaGetLastError());
-  if (chunks1 > 1) {
-    rc = merge_passes(sc, (int)chunks1, nq, kp, sc.cand_idx, sc.cand_dist, stream);
-    if (rc != PRGPU_OK)
-      return rc;
-  }
-  knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, coarse_buf, thresh,
-                                                             counts);
-  PRGPU_CUDA_TRY(cudaGetLastError());
+  rc = sample_pass(FT_SAMPLE_STRIDE * 32, nullptr, coarse_buf, nullptr);
+  if (rc != PRGPU_OK)
+    return rc;
+  rc = sample_pass(FT_SAMPLE_STRIDE, coarse_buf, thresh, counts);
+  if (rc != PRGPU_OK)
+    return rc;
 
   // ---- pass 2: full scan collecting every node at or below the threshold ----
   const size_t smem2 = (size_t)CT_STAGES * CT_TILE * 40 + 2 * CT_STAGES * sizeof(uint64_t);
