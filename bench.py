@@ -55,6 +55,16 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    """Dense bf16 tensor TFLOP/s (sustained: the kernel is timed inside a long step)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained, cuBLAS bf16)"
+    except Exception:
+        return 2250.0, "fallback (B200_PROFILING.md nominal dense bf16)"
+
+
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full summary, else None."""
     try:
@@ -303,7 +313,7 @@ def run_ours(args, rank, local_rank, world):
             if record:
                 kernel_ms.append(tree.last_kernel_ms())
 
-        launches_per_step = 7 + (1 if world > 1 else 0)  # pre-sample, threshold, sample, merge, threshold, collect, select
+        launches_per_step = 8 + (1 if world > 1 else 0)  # (sample, merge, threshold) x 2, collect, select
         units_per_step = Q
         metric, unit = "kNN queries/s", "queries/s"
         algo_bytes = n_local * 56 + Q * 56 + Q * k * 12
@@ -314,6 +324,8 @@ def run_ours(args, rank, local_rank, world):
                            f"all-gather of per-shard top-{k} + merge kernel",
             "l2": f"inputs larger than L2 ({n_local * 56 / 1e6:.0f} MB tree shard per GPU, fp64 SoA)",
             "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks",
+            "arithmetic": "TF32 tensor-core filter -> fp32 re-cut -> fp64 exact distances + proof; results "
+                          "bit-identical to the fp64 reference",
         }
 
         def e2e_step():
@@ -540,17 +552,25 @@ def run_ours(args, rank, local_rank, world):
             "kernel": kernel_name, "kernel_ms": kms, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes}
     if args.workload == "knn":
-        # what actually binds this kernel: FP32 issue.  The scan evaluates one
-        # (query, node) pair with 7 FFMA; 128 FP32 lanes per SM per clock, 148 SMs.
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        fp32_peak_pairs = 148 * 128 * sm_mhz * 1e6 / 7.0
+        # The scan is tensor-bound: D = |x|^2 - 2 q.x - T_q for 16 queries x 8 nodes per TF32
+        # mma.sync (m16n8k8 = 2048 flop); the 8-long contraction makes the OUTPUT the bottleneck,
+        # which is why the warp-level MMA (results in registers) is used and not tcgen05/TMEM.
         pairs = n_local * args.queries / (kms * 1e-3)
-        roof["issue"] = {"bound": "fp32 FFMA issue", "achieved_pairs_per_s": pairs,
-                         "peak_pairs_per_s": fp32_peak_pairs, "frac": pairs / fp32_peak_pairs,
-                         "note": "knn_collect_kernel: 7 FFMA per (query,node) pair at the sampled SM clock; the "
-                                 "exact fp64 re-rank and the proof run on ~1.5k candidates per query"}
-        roof["bytes_note"] = ("algorithmic bytes use SURVEY §8(d)'s fp64 formula 56*N + 56*Q + 12*Q*k; the scan "
-                              "itself streams the 32 B/node fp32 mirror")
+        tpeak, tsrc = tensor_peak()
+        tf = pairs * 16.0 / 1e12
+        mma_peak_tf = 278.0   # TF32 mma.sync m16n8k8 issue peak measured on this pool (scripts/ubench/mma_tf32.cu)
+        roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                "traffic": ncu_traffic(kernel_name), "kernel": kernel_name, "kernel_ms": kms, "peak_source": tsrc,
+                "flops_per_launch": n_local * args.queries * 16.0,
+                "tf32_mma_sync": {"peak": mma_peak_tf, "frac": tf / mma_peak_tf, "pairs_per_s": pairs,
+                                  "note": "peak = measured issue rate of mma.sync.m16n8k8 TF32 (917 warp-MMA/us/SM); "
+                                          "the same loop fed from shared memory with the sign test tops out at "
+                                          "610 warp-MMA/us/SM in isolation (scripts/ubench/mma_loop.cu)"},
+                "hbm": {"achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": algo_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": algo_bytes,
+                        "note": "SURVEY §8(d)'s fp64 formula 56*N + 56*Q + 12*Q*k; the scan itself streams the "
+                                "40 B/node TF32 mirror"}}
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

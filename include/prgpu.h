@@ -74,9 +74,11 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
 int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64_t nq, int k,
                                const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, void *stream);
 /* Search strategy.  By default batched calls (>= 128 queries, k <= 16, dim <= 7, >= 8192 points) use an
- * fp32 filter scan followed by an exact fp64 re-rank of k+8 candidates with a per-query proof that no
- * discarded point can precede them; unproven queries are re-run by the exact fp64 kernel, so the
- * results are bit-identical either way.  force_exact != 0 disables the filter. */
+ * TF32 tensor-core filter scan followed by an fp32 re-cut and an exact fp64 re-rank of the few surviving
+ * candidates, with a per-query proof that no discarded point can precede them; unproven queries are
+ * re-run by the exact fp64 kernel, so the results are bit-identical either way.  The filter path
+ * synchronises the stream once per call (it reads the number of unproven queries).  force_exact != 0
+ * disables the filter. */
 int prgpu_knn_set_search_mode(prgpu_knn_t *h, int force_exact);
 /* number of calls served by the filter path and of queries that needed the exact fallback */
 int prgpu_knn_search_stats(prgpu_knn_t *h, uint64_t *filter_calls, uint64_t *fallback_queries);
