@@ -163,6 +163,15 @@ def test_filter_path_adversarial_ties(P, O, synth):
     # (d) far from the origin: the error bound grows with |x|^2, the proof gets harder, results stay exact
     pts = synth.cloud(10, 40000) * 0.01 + 250.0
     _both_modes(P, O, pts, synth.cloud(11, 300) * 0.01 + 250.0, 5)
+    # (e) blobs much tighter than the TF32 error of the tensor-core scan (2^-9 |q||x| ~ 0.05 here): the
+    #     level-1 cut keeps whole blobs, the fp32 re-cut or the exact fallback has to sort them out
+    centres = synth.cloud(12, 64)
+    pts = (centres[:, None, :] + rng.normal(0.0, 0.02, (64, 600, 7))).reshape(-1, 7)
+    q = np.vstack([centres + rng.normal(0.0, 0.02, centres.shape), synth.cloud(13, 192)])
+    _both_modes(P, O, pts, q, 16)
+    # (f) very large and very small coordinate scales (TF32 keeps the fp32 exponent range)
+    for scale in (1e6, 1e-6):
+        _both_modes(P, O, synth.cloud(14, 20000) * scale, synth.cloud(15, 256) * scale, 7)
 
 
 def test_filter_path_suffix_mask_and_dims(P, O, synth):
@@ -171,3 +180,25 @@ def test_filter_path_suffix_mask_and_dims(P, O, synth):
     _both_modes(P, O, synth.cloud(0, n), synth.cloud(1, nq), 5, lo=lo)
     for dim in (2, 3, 6):
         _both_modes(P, O, synth.cloud(0, 30000, dim=dim), synth.cloud(1, 300, dim=dim), 6)
+
+
+def test_filter_path_incremental_adds_and_growth(P, O, synth):
+    # the fp32 / TF32 mirrors and the pair-wise |x|^2 array must survive odd offsets and reallocation
+    pts = synth.cloud(20, 30011)
+    q = synth.cloud(21, 300)
+    t = P.KnnIndex(7)                      # no capacity hint: grows by doubling
+    cuts = [0, 4097, 4098, 4099, 4100, 9001, 20000, 30011]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        t.add(pts[a:b])
+        if b >= 9001:                      # query between adds, as a planner does
+            gi, gd = t.nearest_k(q, 5)
+            oi, od = O.knn(pts[:b], q, 5, nthreads=8)
+            assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    st = t.search_stats()
+    assert st["filter_calls"] >= 3 and st["fallback_queries"] == 0
+    t.clear()
+    t.add(pts[:10001][::-1].copy())        # stale mirror contents beyond n must not leak
+    gi, gd = t.nearest_k(q, 3)
+    oi, od = O.knn(pts[:10001][::-1].copy(), q, 3, nthreads=8)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    t.close()
