@@ -560,7 +560,11 @@ def run_ours(args, rank, local_rank, world):
         tf = pairs * 16.0 / 1e12
         mma_peak_tf = 278.0   # TF32 mma.sync m16n8k8 issue peak measured on this pool (scripts/ubench/mma_tf32.cu)
         roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                "traffic": ncu_traffic(kernel_name), "kernel": kernel_name, "kernel_ms": kms, "peak_source": tsrc,
+                "traffic": (None if ncu_traffic(kernel_name) is None else
+                            int(ncu_traffic(kernel_name) * (n_local / float(N)))),
+                "traffic_note": "ncu dram read+write bytes of one launch over the full tree (profiles/"
+                                "r01e_*), scaled to this rank's shard",
+                "kernel": kernel_name, "kernel_ms": kms, "peak_source": tsrc,
                 "flops_per_launch": n_local * args.queries * 16.0,
                 "tf32_mma_sync": {"peak": mma_peak_tf, "frac": tf / mma_peak_tf, "pairs_per_s": pairs,
                                   "note": "peak = measured issue rate of mma.sync.m16n8k8 TF32 (917 warp-MMA/us/SM); "
