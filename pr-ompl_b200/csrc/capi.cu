@@ -543,6 +543,80 @@ int prgpu_world_create(int device, int dof, const double *dh, int ns, const int3
   H.ob_d = w->ob_d.as<double>();
   H.cell_start = w->cell_start.as<uint32_t>();
   H.cell_item = w->cell_item.as<uint16_t>();
+
+  // ---- clearance field + joint lever arms (conservative advancement along edges) ---------------
+  H.df = nullptr;
+  H.df_n[0] = H.df_n[1] = H.df_n[2] = 0;
+  H.df_inv = H.df_out = 0.f;
+  for (int i = 0; i < WORLD_MAX_DOF; ++i) {
+    // joint i turns about the z axis of frame i; a sphere on frame l > i is at most the chain length
+    // from that frame's origin plus its local offset away from it
+    double best = 0.0;
+    for (int sidx = 0; sidx < ns; ++sidx) {
+      const int l = sphere_link[sidx];
+      if (i >= dof || l < i + 1)
+        continue;
+      double len = std::sqrt(sphere_xyzr[4 * sidx] * sphere_xyzr[4 * sidx] + sphere_xyzr[4 * sidx + 1] * sphere_xyzr[4 * sidx + 1] +
+                             sphere_xyzr[4 * sidx + 2] * sphere_xyzr[4 * sidx + 2]);
+      for (int m2 = i; m2 < l; ++m2)
+        len += std::sqrt(dh[5 * m2] * dh[5 * m2] + dh[5 * m2 + 1] * dh[5 * m2 + 1]);
+      best = std::max(best, len);
+    }
+    H.rho[i] = (float)(best * (1.0 + 1e-6));
+  }
+  if (use_grid && !getenv("PRGPU_NO_DFIELD")) {
+    const double margin = 0.25; // the field's box: the obstacles' bounding box grown by this much
+    double lo3[3] = {1e300, 1e300, 1e300}, hi3[3] = {-1e300, -1e300, -1e300};
+    for (int o = 0; o < nos; ++o)
+      for (int c = 0; c < 3; ++c) {
+        lo3[c] = std::min(lo3[c], obs_spheres[4 * o + c] - obs_spheres[4 * o + 3]);
+        hi3[c] = std::max(hi3[c], obs_spheres[4 * o + c] + obs_spheres[4 * o + 3]);
+      }
+    for (int o = 0; o < nob; ++o)
+      for (int c = 0; c < 3; ++c) {
+        lo3[c] = std::min(lo3[c], obs_boxes[6 * o + c] - obs_boxes[6 * o + 3 + c]);
+        hi3[c] = std::max(hi3[c], obs_boxes[6 * o + c] + obs_boxes[6 * o + 3 + c]);
+      }
+    double vol = 1.0;
+    for (int c = 0; c < 3; ++c) {
+      lo3[c] -= margin;
+      hi3[c] += margin;
+      vol *= hi3[c] - lo3[c];
+    }
+    // about a million cells (4 MB, L2 resident), never finer than 2 cm
+    const float inv_f = (float)(1.0 / std::max(0.02, std::cbrt(vol / 1.0e6)));
+    const double cell = 1.0 / (double)inv_f; // the lookup multiplies by inv_f: build with the same number
+    int n3[3];
+    double org[3];
+    uint64_t ncell = 1;
+    for (int c = 0; c < 3; ++c) {
+      org[c] = (double)(float)lo3[c];
+      n3[c] = std::max(1, (int)std::ceil((hi3[c] - org[c]) / cell));
+      ncell *= (uint64_t)n3[c];
+    }
+    // slack: fp32 position error of a centre (delta), its effect on the cell index, rounding of the lookup
+    const double slack = delta + 2e-4;
+    // a centre outside the box is >= margin - (org rounding) away from every obstacle
+    const double out = margin - 1e-3 - slack;
+    if (ncell <= (1ull << 23) && out > 0.0) {
+      rc = w->df.reserve(ncell * sizeof(float));
+      if (rc == PRGPU_OK)
+        rc = dfield_build_launch(H.os_d, nos, H.ob_d, nob, n3, org, cell, slack, 1.0e3, w->df.as<float>(), w->stream);
+      if (rc == PRGPU_OK && cudaStreamSynchronize(w->stream) != cudaSuccess)
+        rc = fail(PRGPU_ECUDA, "clearance field build failed");
+      if (rc != PRGPU_OK) {
+        prgpu_world_destroy(w);
+        return rc;
+      }
+      H.df = w->df.as<float>();
+      for (int c = 0; c < 3; ++c) {
+        H.df_n[c] = n3[c];
+        H.df_org[c] = (float)org[c];
+      }
+      H.df_inv = inv_f;
+      H.df_out = (float)out;
+    }
+  }
   e = cudaMalloc(&w->dev, sizeof(DeviceWorld));
   if (e == cudaSuccess)
     e = cudaMemcpy(w->dev, &H, sizeof(DeviceWorld), cudaMemcpyHostToDevice);
@@ -566,11 +640,13 @@ int prgpu_world_destroy(prgpu_world_t *w) {
   w->ob_d.release();
   w->cell_start.release();
   w->cell_item.release();
+  w->df.release();
   w->d_a.release();
   w->d_b.release();
   w->d_valid.release();
   w->d_pose.release();
-  for (void *p : {(void *)w->cm_scratch.owed, (void *)w->cm_scratch.off, w->cm_scratch.tmp, (void *)w->cm_scratch.item_edge})
+  for (void *p : {(void *)w->cm_scratch.owed, (void *)w->cm_scratch.off, w->cm_scratch.tmp, (void *)w->cm_scratch.item_edge,
+                  (void *)w->cm_scratch.gaps})
     if (p)
       cudaFree(p);
   w->timer.destroy();

@@ -58,7 +58,7 @@ struct prgpu_world {
   cudaStream_t stream = nullptr;
   prgpu::DeviceWorld host; // copy of the device struct (device pointers inside)
   prgpu::DeviceWorld *dev = nullptr;
-  prgpu::DevBuf os_f, ob_f, os_d, ob_d, cell_start, cell_item;
+  prgpu::DevBuf os_f, ob_f, os_d, ob_d, cell_start, cell_item, df;
   prgpu::DevBuf d_a, d_b, d_valid, d_pose;
   prgpu::CmScratch cm_scratch;
   prgpu::KernelTimer timer;

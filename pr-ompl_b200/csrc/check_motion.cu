@@ -113,11 +113,18 @@ check_motion_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict
 // The warp-per-edge kernel above leaves lanes idle (an edge's state count is rarely a multiple of 32)
 // and can only stop an edge between rounds.  For large batches the tested sets are flattened instead:
 //   phase A: up to 8 states per edge, spread evenly over its tested set (stride m = ceil(np/8)), 8
-//            lanes per edge; an edge with an invalid sample is finished, and so is one with np <= 8;
+//            lanes per edge; an edge with an invalid sample is finished, and so is one with np <= 8.
+//            A free sample also returns a lower bound C of its clearance (clearance field, world.cuh);
+//            no link-sphere centre moves by more than travel = sum_i |to_i - from_i| rho_i / nd between
+//            neighbouring tested states, so the floor(C / travel) states on either side of the sample
+//            are free WITHOUT being tested (conservative advancement): they are struck off the gap
+//            between this sample and the next;
 //   scan   : exclusive prefix sum of the states still owed by undecided edges;
-//   phase B: one thread per owed state, found by binary search in the prefix sums; a thread first
-//            looks at the edge's verdict and skips the state if the edge is already invalid.
-// Every lane of both phases carries a state, and the result is the same AND over the same set.
+//   expand : owed item -> (edge, tested-state index);
+//   phase B: one thread per owed state; a thread first looks at the edge's verdict and skips the state
+//            if the edge is already invalid.
+// Every lane of both phases carries a state, and the result is the AND over the reference's tested set
+// (the struck-off states are proven free, not assumed).
 
 struct EdgePlan {
   uint32_t np, nd, extra, stride; // tested-set size, segment count, 1 if `from` is tested, sample stride
@@ -185,7 +192,7 @@ template <int SP>
 __global__ void __launch_bounds__(CM_THREADS)
 cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
                   uint32_t n, double resolution, int mode, int check_first, uint8_t *__restrict__ valid,
-                  uint32_t *__restrict__ owed) {
+                  uint32_t *__restrict__ owed, uint2 *__restrict__ gaps) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
   const ObstacleTables tabs = load_tables(w, s_obs);
@@ -199,6 +206,10 @@ cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
     EdgePlan pl;
     pl.np = 0;
     pl.stride = 1;
+    pl.nd = 0;
+    pl.extra = 0;
+    pl.step = 0.0;
+    uint32_t reach = 0; // states on either side of this lane's sample that its clearance certifies as free
     if (e < n) {
       double a[WORLD_MAX_DOF], b[WORLD_MAX_DOF];
 #pragma unroll
@@ -211,35 +222,82 @@ cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
       if (p < pl.np) {
         double q[WORLD_MAX_DOF];
         edge_state(pl, a, b, mode, p, q);
-        good = state_valid_any<SP>(wp, &tabs, q);
+        float clear = 0.f;
+        good = state_valid_any<SP>(wp, &tabs, q, &clear);
+        if (good && clear > 0.f) {
+          // no link-sphere centre moves by more than `travel` between neighbouring tested states
+          double travel = 0.0;
+#pragma unroll
+          for (int i = 0; i < WORLD_MAX_DOF; ++i)
+            travel += fabs(b[i] - a[i]) * (double)(i < dof ? w.rho[i] : 0.f);
+          travel *= (mode == PRGPU_MODE_OMPL_DISCRETE ? 1.0 / (double)pl.nd : pl.step) * (1.0 + 1e-6);
+          const double r = travel > 0.0 ? floor((double)clear / travel) : (double)pl.np;
+          reach = r >= (double)pl.np ? pl.np : (uint32_t)r;
+        }
       }
     }
     const unsigned bad = __ballot_sync(0xffffffffu, !good);
+    const int gbase = (threadIdx.x & 31) & ~7;
+    const uint32_t reach_next = __shfl_sync(0xffffffffu, reach, gbase + ((slot + 1) & 7));
+    const uint32_t reach_first = __shfl_sync(0xffffffffu, reach, gbase);
+    // this lane's gap: the tested states strictly between its sample and the next one (or the end)
+    uint32_t cnt = 0, lo = 0;
+    const bool ok = ((bad >> gbase) & 0xFFu) == 0;
+    const uint32_t p = slot * pl.stride;
+    if (e < n && ok && p < pl.np && pl.stride > 1) {
+      const uint32_t pe = min(p + pl.stride, pl.np); // next sample or one past the last state
+      const bool last = pe == pl.np;                  // no sample at pe
+      uint32_t left = reach, right;
+      if (mode == PRGPU_MODE_OMPL_DISCRETE) {
+        // p = 0 is the END state `to`; the states after it in p order start at `from`
+        if (slot == 0)
+          left = 0;
+        right = last ? reach_first : reach_next; // the trailing states run up to `to` (sample 0)
+      } else {
+        right = last ? 0u : reach_next;
+      }
+      const uint64_t l = (uint64_t)p + 1 + left, h = (uint64_t)pe - 1; // h inclusive before the right cut
+      if (h >= l && h - l + 1 > (uint64_t)right) {
+        lo = (uint32_t)l;
+        cnt = (uint32_t)(h - l + 1 - right);
+      }
+    }
+    if (e < n)
+      gaps[(size_t)e * 8 + slot] = make_uint2(lo, cnt);
+    uint32_t tot = cnt;
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
     if (e < n && slot == 0) {
-      const bool ok = ((bad >> ((threadIdx.x & 31) & ~7)) & 0xFFu) == 0;
-      const uint32_t sampled = (pl.np + pl.stride - 1) / pl.stride;
       valid[e] = ok ? 1 : 0;
-      owed[e] = ok ? pl.np - sampled : 0u;
+      owed[e] = ok ? tot : 0u;
     }
   }
 }
 
-// item g of the owed states belongs to edge item_edge[g]
+// item g of the owed states is tested state item_p[g] of edge item_edge[g]
 __global__ void cm_expand_kernel(uint32_t n, const uint32_t *__restrict__ owed, const uint32_t *__restrict__ off,
-                                 uint32_t *__restrict__ item_edge) {
+                                 const uint2 *__restrict__ gaps, uint32_t *__restrict__ item_edge,
+                                 uint32_t *__restrict__ item_p) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n)
+  if (e >= n || owed[e] == 0)
     return;
-  const uint32_t c = owed[e], o = off[e];
-  for (uint32_t i = 0; i < c; ++i)
-    item_edge[o + i] = e;
+  uint32_t o = off[e];
+  for (int s = 0; s < 8; ++s) {
+    const uint2 g = gaps[(size_t)e * 8 + s];
+    for (uint32_t i = 0; i < g.y; ++i) {
+      item_edge[o] = e;
+      item_p[o] = g.x + i;
+      ++o;
+    }
+  }
 }
 
 template <int SP>
 __global__ void __launch_bounds__(CM_THREADS)
 cm_phase_b_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
                   uint32_t total, double resolution, int mode, int check_first, volatile uint8_t *valid,
-                  const uint32_t *__restrict__ off, const uint32_t *__restrict__ item_edge) {
+                  const uint32_t *__restrict__ item_edge, const uint32_t *__restrict__ item_p) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
   const ObstacleTables tabs = load_tables(w, s_obs);
@@ -257,9 +315,7 @@ cm_phase_b_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
       b[i] = i < dof ? to[(size_t)e * dof + i] : 0.0;
     }
     const EdgePlan pl = plan_edge(a, b, resolution, mode, check_first);
-    const uint32_t r = g - off[e];
-    const uint32_t m1 = pl.stride - 1; // >= 1 whenever states are owed
-    const uint32_t p = (r / m1) * pl.stride + (r % m1) + 1; // r-th state that is not a multiple of the stride
+    const uint32_t p = item_p[g];
     double q[WORLD_MAX_DOF];
     edge_state(pl, a, b, mode, p, q);
     if (!state_valid_any<SP>(wp, &tabs, q))
@@ -300,6 +356,39 @@ __global__ void fk_kernel(const DeviceWorld *__restrict__ wp, const double *__re
     pose12[i * 12 + k] = F[12 * w.dof + k];
 }
 
+// clearance field: one thread per cell, exact fp64 distance from the cell's box to every obstacle
+__global__ void dfield_build_kernel(const double *__restrict__ os_d, int n_os, const double *__restrict__ ob_d, int n_ob,
+                                    int nx, int ny, int nz, double ox, double oy, double oz, double cell, double slack,
+                                    double cap, float *__restrict__ df) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t ncell = (size_t)nx * ny * nz;
+  if (i >= ncell)
+    return;
+  const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((size_t)nx * ny));
+  const double lo[3] = {ox + x * cell, oy + y * cell, oz + z * cell};
+  const double hi[3] = {lo[0] + cell, lo[1] + cell, lo[2] + cell};
+  double best = cap;
+  for (int o = 0; o < n_os; ++o) {
+    double d2 = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      const double v = os_d[4 * o + c];
+      const double g = fmax(fmax(lo[c] - v, v - hi[c]), 0.0);
+      d2 += g * g;
+    }
+    best = fmin(best, sqrt(d2) - os_d[4 * o + 3]);
+  }
+  for (int o = 0; o < n_ob; ++o) {
+    double d2 = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      const double bl = ob_d[6 * o + c] - ob_d[6 * o + 3 + c], bh = ob_d[6 * o + c] + ob_d[6 * o + 3 + c];
+      const double g = fmax(fmax(bl - hi[c], lo[c] - bh), 0.0);
+      d2 += g * g;
+    }
+    best = fmin(best, sqrt(d2));
+  }
+  df[i] = __double2float_rd(best * (1.0 - 1e-12) - slack);
+}
+
 size_t obstacle_smem(const DeviceWorld &w) { return obstacle_tables_bytes(w); }
 
 } // namespace
@@ -338,12 +427,16 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
           cudaFree(scratch->off);
         if (scratch->tmp)
           cudaFree(scratch->tmp);
+        if (scratch->gaps)
+          cudaFree(scratch->gaps);
+        scratch->gaps = nullptr;
         scratch->owed = scratch->off = nullptr;
         scratch->tmp = nullptr;
         scratch->cap = 0;
         const size_t cap = std::max<size_t>(m, std::min<uint64_t>(n, PASS));
         PRGPU_CUDA_TRY(cudaMalloc(&scratch->owed, cap * sizeof(uint32_t)));
         PRGPU_CUDA_TRY(cudaMalloc(&scratch->off, cap * sizeof(uint32_t)));
+        PRGPU_CUDA_TRY(cudaMalloc(&scratch->gaps, cap * 8 * sizeof(uint2)));
         PRGPU_CUDA_TRY(cudaMalloc(&scratch->tmp, std::max<size_t>(tmp, 16) * 2));
         scratch->cap = cap;
         scratch->tmp_bytes = std::max<size_t>(tmp, 16) * 2;
@@ -357,7 +450,8 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
         auto kb = cm_phase_b_kernel<SP>;
         PRGPU_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PRGPU_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ka<<<blocks_a, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed);
+        ka<<<blocks_a, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed,
+                                                   scratch->gaps);
         size_t tb2 = scratch->tmp_bytes;
         PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scratch->tmp, tb2, scratch->owed, scratch->off, (int)m, stream));
         // number of owed states (one small read-back per pass sizes the item table and the grid)
@@ -372,13 +466,15 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
               cudaFree(scratch->item_edge);
             scratch->item_edge = nullptr;
             scratch->item_cap = 0;
-            PRGPU_CUDA_TRY(cudaMalloc(&scratch->item_edge, (size_t)total * 5 / 4 * sizeof(uint32_t)));
+            PRGPU_CUDA_TRY(cudaMalloc(&scratch->item_edge, (size_t)total * 5 / 4 * 2 * sizeof(uint32_t)));
             scratch->item_cap = (size_t)total * 5 / 4;
           }
-          cm_expand_kernel<<<(m + 255) / 256, 256, 0, stream>>>(m, scratch->owed, scratch->off, scratch->item_edge);
+          uint32_t *item_p = scratch->item_edge + scratch->item_cap;
+          cm_expand_kernel<<<(m + 255) / 256, 256, 0, stream>>>(m, scratch->owed, scratch->off, scratch->gaps,
+                                                                scratch->item_edge, item_p);
           const unsigned nb = (unsigned)std::min<uint64_t>(((uint64_t)total + CM_THREADS - 1) / CM_THREADS, blocks_b);
-          kb<<<nb, CM_THREADS, smem, stream>>>(w_dev, fa, tb, total, resolution, mode, check_first, vd, scratch->off,
-                                               scratch->item_edge);
+          kb<<<nb, CM_THREADS, smem, stream>>>(w_dev, fa, tb, total, resolution, mode, check_first, vd,
+                                               scratch->item_edge, item_p);
         }
       });
       PRGPU_CUDA_TRY(cudaGetLastError());
@@ -407,6 +503,16 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
   });
   if (timer)
     timer->end(stream);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
+int dfield_build_launch(const double *os_d, int n_os, const double *ob_d, int n_ob, const int *n3, const double *org,
+                        double cell, double slack, double cap, float *df_dev, cudaStream_t stream) {
+  const size_t ncell = (size_t)n3[0] * n3[1] * n3[2];
+  dfield_build_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, stream>>>(os_d, n_os, ob_d, n_ob, n3[0], n3[1], n3[2],
+                                                                          org[0], org[1], org[2], cell, slack, cap,
+                                                                          df_dev);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

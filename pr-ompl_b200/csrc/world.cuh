@@ -36,6 +36,18 @@ struct DeviceWorld {
   uint32_t grid_items;               // total list length
   const uint32_t *cell_start;        // ncell+1
   const uint16_t *cell_item;         // obstacle index, bit 15 set for boxes
+  // clearance field: df[cell] <= distance from ANY point of the (fine) cell to the nearest obstacle,
+  // minus the fp32 position error and a cell-index slack.  A link sphere whose centre lies in a cell
+  // with df > radius is certainly free (one load instead of the cell's obstacle list), and
+  // min_j(df - r_j) is a lower bound of the state's clearance: the states of an edge within that
+  // distance (in workspace motion, bounded through rho[]) of a tested state are free without being
+  // tested.  df == nullptr: no field.  Outside the field's box every obstacle is >= df_out away.
+  const float *df;
+  int df_n[3];
+  float df_org[3], df_inv, df_out;
+  // rho[i]: upper bound, over all configurations and link spheres, of the distance between a sphere centre
+  // and the axis of joint i -- a unit change of joint i moves no sphere centre by more than rho[i]
+  float rho[WORLD_MAX_DOF];
 };
 constexpr int WORLD_GRID_MAX_CELLS = 8192;
 constexpr int WORLD_GRID_MAX_ITEMS = 32768;
@@ -411,7 +423,10 @@ __device__ __forceinline__ ObstacleTables load_tables(const DeviceWorld &w, floa
   return t;
 }
 
-static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q) {
+// `clear` (optional): receives a lower bound of the state's clearance (metres) when every link sphere was
+// certified by the clearance field, else 0.
+static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
+                                                     float *clear = nullptr) {
   const DeviceWorld &w = *wp;
   const ObstacleTables &t = *tp;
   const ArmTableF32 &arm = *t.arm;
@@ -421,6 +436,10 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
   float r00 = 1.f, r01 = 0.f, r02 = 0.f, p0 = 0.f;
   float r10 = 0.f, r11 = 1.f, r12 = 0.f, p1 = 0.f;
   float r20 = 0.f, r21 = 0.f, r22 = 1.f, p2 = 0.f;
+  const float *df = w.df;
+  const int dnx = w.df_n[0], dny = w.df_n[1], dnz = w.df_n[2];
+  const float dox = w.df_org[0], doy = w.df_org[1], doz = w.df_org[2], dinv = w.df_inv, dout = w.df_out;
+  float cmin = CUDART_INF_F;
   for (int i = 0; i <= w.dof; ++i) {
     if (i > 0) {
       float st, ct;
@@ -445,12 +464,24 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
       const float cx = r00 * sp.x + r01 * sp.y + r02 * sp.z + p0;
       const float cy = r10 * sp.x + r11 * sp.y + r12 * sp.z + p1;
       const float cz = r20 * sp.x + r21 * sp.y + r22 * sp.z + p2;
+      const float rs = sp.w;
+      if (df) { // clearance field first: most free spheres are settled by one load
+        const float fx = (cx - dox) * dinv, fy = (cy - doy) * dinv, fz = (cz - doz) * dinv;
+        float dv = dout;
+        if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)dnx && fy < (float)dny && fz < (float)dnz)
+          dv = __ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx);
+        const float cj = dv - rs;
+        if (cj > 0.f) {
+          cmin = fminf(cmin, cj);
+          continue;
+        }
+        cmin = 0.f;
+      }
       const float gx = (cx - ox) * ginv, gy = (cy - oy) * ginv, gz = (cz - oz) * ginv;
       // outside the grid (or NaN): no inflated obstacle box contains the centre
       if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float)nx && gy < (float)ny && gz < (float)nz))
         continue;
       const int cell = ((int)gz * ny + (int)gy) * nx + (int)gx;
-      const float rs = sp.w;
       for (uint32_t it = t.cell_start[cell]; it < t.cell_start[cell + 1]; ++it) {
         const uint32_t id = t.cell_item[it];
         if (id & 0x8000u) {
@@ -480,6 +511,8 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
       }
     }
   }
+  if (clear)
+    *clear = (df && cmin < CUDART_INF_F) ? cmin : 0.f;
   return true;
 }
 
@@ -487,11 +520,15 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
 // SP == 0 selects the grid path at compile time, so kernels instantiated for worlds with a grid never
 // carry the brute-force filter's register footprint (the host dispatches on grid_n[0] > 0).
 template <int SP>
-__device__ __forceinline__ bool state_valid_any(const DeviceWorld *wp, const ObstacleTables *tp, const double *q) {
+__device__ __forceinline__ bool state_valid_any(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
+                                                float *clear = nullptr) {
   if constexpr (SP == 0)
-    return state_valid_grid(wp, tp, q);
-  else
+    return state_valid_grid(wp, tp, q, clear);
+  else {
+    if (clear)
+      *clear = 0.f;
     return state_valid_fast<SP>(*wp, tp->os, tp->ob, q);
+  }
 }
 
 // out-of-line variant for kernels that test states from several places (keeps their register
