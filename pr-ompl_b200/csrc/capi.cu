@@ -646,7 +646,7 @@ int prgpu_world_destroy(prgpu_world_t *w) {
   w->d_valid.release();
   w->d_pose.release();
   for (void *p : {(void *)w->cm_scratch.owed, (void *)w->cm_scratch.off, w->cm_scratch.tmp, (void *)w->cm_scratch.item_edge,
-                  (void *)w->cm_scratch.gaps})
+                  (void *)w->cm_scratch.gaps, (void *)w->cm_scratch.queue, (void *)w->cm_scratch.queue_n})
     if (p)
       cudaFree(p);
   w->timer.destroy();

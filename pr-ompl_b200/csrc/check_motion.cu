@@ -114,7 +114,10 @@ check_motion_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict
 // and can only stop an edge between rounds.  For large batches the tested sets are flattened instead:
 //   phase A: up to 8 states per edge, spread evenly over its tested set (stride m = ceil(np/8)), 8
 //            lanes per edge; an edge with an invalid sample is finished, and so is one with np <= 8.
-//            A free sample also returns a lower bound C of its clearance (clearance field, world.cuh);
+//            Three kernels, so that every lane of each does the same kind of work: `sample` tests the
+//            samples against the clearance field only, `resolve` takes the samples the field could not
+//            certify through the obstacle lists, `gaps` sizes what is left.
+//            A certified sample also has a lower bound C of its clearance (clearance field, world.cuh);
 //            no link-sphere centre moves by more than travel = sum_i |to_i - from_i| rho_i / nd between
 //            neighbouring tested states, so the floor(C / travel) states on either side of the sample
 //            are free WITHOUT being tested (conservative advancement): they are struck off the gap
@@ -188,28 +191,26 @@ __device__ __forceinline__ void edge_state(const EdgePlan &pl, const double *a, 
   }
 }
 
+// phase A, step 1: the 8 samples of every edge against the clearance field only.  A certified sample
+// leaves its reach (the number of neighbouring states its clearance covers); the others are queued with
+// the mask of their uncertified spheres.  Every lane does the same work: no obstacle lists here.
 template <int SP>
 __global__ void __launch_bounds__(CM_THREADS)
-cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
-                  uint32_t n, double resolution, int mode, int check_first, uint8_t *__restrict__ valid,
-                  uint32_t *__restrict__ owed, uint2 *__restrict__ gaps) {
+cm_sample_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
+                 uint32_t n, double resolution, int mode, int check_first, uint8_t *__restrict__ valid,
+                 uint32_t *__restrict__ np_out, uint2 *__restrict__ gaps, uint2 *__restrict__ queue,
+                 uint32_t *__restrict__ queue_n) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
   const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
   const int dof = w.dof;
+  const int lane = threadIdx.x & 31;
   const uint32_t groups_total = gridDim.x * (CM_THREADS / 8);
   for (uint32_t e0 = blockIdx.x * (CM_THREADS / 8); e0 < n; e0 += groups_total) {
     const uint32_t e = e0 + (threadIdx.x >> 3);
     const uint32_t slot = threadIdx.x & 7;
-    bool good = true;
-    EdgePlan pl;
-    pl.np = 0;
-    pl.stride = 1;
-    pl.nd = 0;
-    pl.extra = 0;
-    pl.step = 0.0;
-    uint32_t reach = 0; // states on either side of this lane's sample that its clearance certifies as free
+    uint32_t reach = 0, unc = 0;
     if (e < n) {
       double a[WORLD_MAX_DOF], b[WORLD_MAX_DOF];
 #pragma unroll
@@ -217,62 +218,131 @@ cm_phase_a_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__
         a[i] = i < dof ? from[(size_t)e * dof + i] : 0.0;
         b[i] = i < dof ? to[(size_t)e * dof + i] : 0.0;
       }
-      pl = plan_edge(a, b, resolution, mode, check_first);
+      const EdgePlan pl = plan_edge(a, b, resolution, mode, check_first);
+      if (slot == 0) {
+        np_out[e] = pl.np;
+        valid[e] = 1;
+      }
       const uint32_t p = slot * pl.stride;
       if (p < pl.np) {
         double q[WORLD_MAX_DOF];
         edge_state(pl, a, b, mode, p, q);
-        float clear = 0.f;
-        good = state_valid_any<SP>(wp, &tabs, q, &clear);
-        if (good && clear > 0.f) {
-          // no link-sphere centre moves by more than `travel` between neighbouring tested states
-          double travel = 0.0;
+        // no link-sphere centre moves by more than `travel` between neighbouring tested states
+        float travel = 0.f;
 #pragma unroll
-          for (int i = 0; i < WORLD_MAX_DOF; ++i)
-            travel += fabs(b[i] - a[i]) * (double)(i < dof ? w.rho[i] : 0.f);
-          travel *= (mode == PRGPU_MODE_OMPL_DISCRETE ? 1.0 / (double)pl.nd : pl.step) * (1.0 + 1e-6);
-          const double r = travel > 0.0 ? floor((double)clear / travel) : (double)pl.np;
-          reach = r >= (double)pl.np ? pl.np : (uint32_t)r;
+        for (int i = 0; i < WORLD_MAX_DOF; ++i)
+          travel += (float)fabs(b[i] - a[i]) * (i < dof ? w.rho[i] : 0.f);
+        travel *= (float)(mode == PRGPU_MODE_OMPL_DISCRETE ? 1.0 / (double)pl.nd : pl.step) * (1.0f + 1e-5f);
+        unc = 0xFFFFFFFFu;
+        if constexpr (SP == 0) {
+          if (w.df) {
+            float clear = 0.f;
+            unc = state_certify_grid(wp, &tabs, q, &clear);
+            if (unc == 0 && clear > 0.f) {
+              const float r = travel > 0.f ? floorf(clear / travel * (1.0f - 1e-5f)) : (float)pl.np;
+              reach = r >= (float)pl.np ? pl.np : (uint32_t)r;
+            }
+          }
         }
       }
+      gaps[(size_t)e * 8 + slot] = make_uint2(reach, 0u);
     }
-    const unsigned bad = __ballot_sync(0xffffffffu, !good);
-    const int gbase = (threadIdx.x & 31) & ~7;
-    const uint32_t reach_next = __shfl_sync(0xffffffffu, reach, gbase + ((slot + 1) & 7));
-    const uint32_t reach_first = __shfl_sync(0xffffffffu, reach, gbase);
-    // this lane's gap: the tested states strictly between its sample and the next one (or the end)
-    uint32_t cnt = 0, lo = 0;
-    const bool ok = ((bad >> gbase) & 0xFFu) == 0;
-    const uint32_t p = slot * pl.stride;
-    if (e < n && ok && p < pl.np && pl.stride > 1) {
-      const uint32_t pe = min(p + pl.stride, pl.np); // next sample or one past the last state
-      const bool last = pe == pl.np;                  // no sample at pe
-      uint32_t left = reach, right;
-      if (mode == PRGPU_MODE_OMPL_DISCRETE) {
-        // p = 0 is the END state `to`; the states after it in p order start at `from`
-        if (slot == 0)
-          left = 0;
-        right = last ? reach_first : reach_next; // the trailing states run up to `to` (sample 0)
-      } else {
-        right = last ? 0u : reach_next;
-      }
-      const uint64_t l = (uint64_t)p + 1 + left, h = (uint64_t)pe - 1; // h inclusive before the right cut
-      if (h >= l && h - l + 1 > (uint64_t)right) {
-        lo = (uint32_t)l;
-        cnt = (uint32_t)(h - l + 1 - right);
-      }
-    }
-    if (e < n)
-      gaps[(size_t)e * 8 + slot] = make_uint2(lo, cnt);
-    uint32_t tot = cnt;
-    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
-    if (e < n && slot == 0) {
-      valid[e] = ok ? 1 : 0;
-      owed[e] = ok ? tot : 0u;
+    // queue the uncertified samples (one atomic per warp)
+    const unsigned bal = __ballot_sync(0xffffffffu, unc != 0);
+    if (bal) {
+      const int leader = __ffs(bal) - 1;
+      uint32_t base = 0;
+      if (lane == leader)
+        base = atomicAdd(queue_n, (uint32_t)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (unc != 0)
+        queue[base + __popc(bal & ((1u << lane) - 1u))] = make_uint2(e * 8u + slot, unc);
     }
   }
+}
+
+// phase A, step 2: the queued samples walk the obstacle lists of their uncertified spheres (worlds without a
+// clearance field: the whole test).  An invalid sample finishes its edge.
+template <int SP>
+__global__ void __launch_bounds__(CM_THREADS)
+cm_resolve_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
+                  double resolution, int mode, int check_first, volatile uint8_t *valid,
+                  const uint2 *__restrict__ queue, const uint32_t *__restrict__ queue_n) {
+  const DeviceWorld &w = *wp;
+  extern __shared__ float4 s_obs[];
+  const ObstacleTables tabs = load_tables(w, s_obs);
+  __syncthreads();
+  const int dof = w.dof;
+  const uint32_t total = *queue_n;
+  for (uint32_t g = blockIdx.x * CM_THREADS + threadIdx.x; g < total; g += gridDim.x * CM_THREADS) {
+    const uint2 item = queue[g];
+    const uint32_t e = item.x >> 3, slot = item.x & 7u;
+    if (valid[e] == 0)
+      continue;
+    double a[WORLD_MAX_DOF], b[WORLD_MAX_DOF];
+#pragma unroll
+    for (int i = 0; i < WORLD_MAX_DOF; ++i) {
+      a[i] = i < dof ? from[(size_t)e * dof + i] : 0.0;
+      b[i] = i < dof ? to[(size_t)e * dof + i] : 0.0;
+    }
+    const EdgePlan pl = plan_edge(a, b, resolution, mode, check_first);
+    double q[WORLD_MAX_DOF];
+    edge_state(pl, a, b, mode, slot * pl.stride, q);
+    bool good;
+    if constexpr (SP == 0)
+      good = w.df ? state_lists_grid(wp, &tabs, q, item.y) : state_valid_grid(wp, &tabs, q);
+    else
+      good = state_valid_any<SP>(wp, &tabs, q);
+    if (!good)
+      valid[e] = 0;
+  }
+}
+
+// phase A, step 3: what the samples leave untested.  Lane `slot` of an edge owns the tested states
+// strictly between its sample and the next one (or the end); the reaches of the two samples strike
+// states off both ends of that gap.
+__global__ void __launch_bounds__(CM_THREADS)
+cm_gaps_kernel(uint32_t n, int mode, const uint8_t *__restrict__ valid, uint32_t *__restrict__ owed,
+               uint2 *__restrict__ gaps) {
+  const uint32_t idx = blockIdx.x * CM_THREADS + threadIdx.x;
+  const uint32_t e = idx >> 3, slot = idx & 7u;
+  const bool in = e < n;
+  const uint32_t np = in ? owed[e] : 0u; // the sample kernel left the tested-set size here
+  const uint32_t reach = in ? gaps[idx].x : 0u;
+  const bool ok = in && valid[e] != 0;
+  __syncwarp();
+  const uint32_t stride = max(1u, (np + 7u) / 8u);
+  const int gbase = (threadIdx.x & 31) & ~7;
+  const uint32_t reach_next = __shfl_sync(0xffffffffu, reach, gbase + ((slot + 1) & 7));
+  const uint32_t reach_first = __shfl_sync(0xffffffffu, reach, gbase);
+  uint32_t cnt = 0, lo = 0;
+  const uint32_t p = slot * stride;
+  if (ok && p < np && stride > 1) {
+    const uint32_t pe = min(p + stride, np); // next sample or one past the last state
+    const bool last = pe == np;               // no sample at pe
+    uint32_t left = reach, right;
+    if (mode == PRGPU_MODE_OMPL_DISCRETE) {
+      // p = 0 is the END state `to`; the states after it in p order start at `from`
+      if (slot == 0)
+        left = 0;
+      right = last ? reach_first : reach_next; // the trailing states run up to `to` (sample 0)
+    } else {
+      right = last ? 0u : reach_next;
+    }
+    const uint64_t l = (uint64_t)p + 1 + left, h = (uint64_t)pe - 1; // h inclusive before the right cut
+    if (h >= l && h - l + 1 > (uint64_t)right) {
+      lo = (uint32_t)l;
+      cnt = (uint32_t)(h - l + 1 - right);
+    }
+  }
+  if (in)
+    gaps[idx] = make_uint2(lo, cnt);
+  uint32_t tot = cnt;
+  tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+  tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+  tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+  if (in && slot == 0)
+    owed[e] = ok ? tot : 0u;
 }
 
 // item g of the owed states is tested state item_p[g] of edge item_edge[g]
@@ -429,7 +499,12 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
           cudaFree(scratch->tmp);
         if (scratch->gaps)
           cudaFree(scratch->gaps);
-        scratch->gaps = nullptr;
+        if (scratch->queue)
+          cudaFree(scratch->queue);
+        if (scratch->queue_n)
+          cudaFree(scratch->queue_n);
+        scratch->gaps = scratch->queue = nullptr;
+        scratch->queue_n = nullptr;
         scratch->owed = scratch->off = nullptr;
         scratch->tmp = nullptr;
         scratch->cap = 0;
@@ -437,6 +512,8 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
         PRGPU_CUDA_TRY(cudaMalloc(&scratch->owed, cap * sizeof(uint32_t)));
         PRGPU_CUDA_TRY(cudaMalloc(&scratch->off, cap * sizeof(uint32_t)));
         PRGPU_CUDA_TRY(cudaMalloc(&scratch->gaps, cap * 8 * sizeof(uint2)));
+        PRGPU_CUDA_TRY(cudaMalloc(&scratch->queue, cap * 8 * sizeof(uint2)));
+        PRGPU_CUDA_TRY(cudaMalloc(&scratch->queue_n, sizeof(uint32_t)));
         PRGPU_CUDA_TRY(cudaMalloc(&scratch->tmp, std::max<size_t>(tmp, 16) * 2));
         scratch->cap = cap;
         scratch->tmp_bytes = std::max<size_t>(tmp, 16) * 2;
@@ -446,12 +523,19 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
       const unsigned blocks_a = (unsigned)std::min<uint64_t>((m + CM_THREADS / 8 - 1) / (CM_THREADS / 8), (uint64_t)sm_count * 16);
       const unsigned blocks_b = (unsigned)sm_count * 8;
       PRGPU_SP_DISPATCH(w.S, {
-        auto ka = cm_phase_a_kernel<SP>;
+        auto ka = cm_sample_kernel<SP>;
+        auto kr = cm_resolve_kernel<SP>;
         auto kb = cm_phase_b_kernel<SP>;
         PRGPU_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PRGPU_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PRGPU_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PRGPU_CUDA_TRY(cudaMemsetAsync(scratch->queue_n, 0, sizeof(uint32_t), stream));
         ka<<<blocks_a, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed,
-                                                   scratch->gaps);
+                                                   scratch->gaps, scratch->queue, scratch->queue_n);
+        kr<<<blocks_b, CM_THREADS, smem, stream>>>(w_dev, fa, tb, resolution, mode, check_first, vd, scratch->queue,
+                                                   scratch->queue_n);
+        cm_gaps_kernel<<<(unsigned)(((uint64_t)m * 8 + CM_THREADS - 1) / CM_THREADS), CM_THREADS, 0, stream>>>(
+            m, mode, vd, scratch->owed, scratch->gaps);
         size_t tb2 = scratch->tmp_bytes;
         PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scratch->tmp, tb2, scratch->owed, scratch->off, (int)m, stream));
         // number of owed states (one small read-back per pass sizes the item table and the grid)

@@ -7,6 +7,8 @@ struct CmScratch { // owed-state counts, their prefix sums and the scan's tempor
   void *tmp = nullptr;
   size_t cap = 0, tmp_bytes = 0;
   uint2 *gaps = nullptr;         // per edge 8 x (first owed state, count): what phase A left untested
+  uint2 *queue = nullptr;        // samples the clearance field could not certify: (edge * 8 + slot, sphere mask)
+  uint32_t *queue_n = nullptr;
   uint32_t *item_edge = nullptr; // owed state -> edge, followed by owed state -> tested-state index
   size_t item_cap = 0;
 };

@@ -423,60 +423,112 @@ __device__ __forceinline__ ObstacleTables load_tables(const DeviceWorld &w, floa
   return t;
 }
 
-// `clear` (optional): receives a lower bound of the state's clearance (metres) when every link sphere was
-// certified by the clearance field, else 0.
-static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
-                                                     float *clear = nullptr) {
-  const DeviceWorld &w = *wp;
-  const ObstacleTables &t = *tp;
-  const ArmTableF32 &arm = *t.arm;
-  const int nx = w.grid_n[0], ny = w.grid_n[1], nz = w.grid_n[2];
-  const float ox = w.grid_org[0], oy = w.grid_org[1], oz = w.grid_org[2], ginv = w.grid_inv;
-  // current frame [R|p], fp32, in registers; the spheres of frame i are tested before moving on
-  float r00 = 1.f, r01 = 0.f, r02 = 0.f, p0 = 0.f;
-  float r10 = 0.f, r11 = 1.f, r12 = 0.f, p1 = 0.f;
-  float r20 = 0.f, r21 = 0.f, r22 = 1.f, p2 = 0.f;
+// fp32 frame [R|p] of the FK chain, in registers
+struct FrameF32 {
+  float r00, r01, r02, p0, r10, r11, r12, p1, r20, r21, r22, p2;
+  __device__ __forceinline__ void reset() {
+    r00 = 1.f; r01 = 0.f; r02 = 0.f; p0 = 0.f;
+    r10 = 0.f; r11 = 1.f; r12 = 0.f; p1 = 0.f;
+    r20 = 0.f; r21 = 0.f; r22 = 1.f; p2 = 0.f;
+  }
+  // frame i-1 -> frame i:  T <- T * [Rz(theta) Tz(d) Tx(a) Rx(alpha)]
+  __device__ __forceinline__ void advance(const ArmTableF32 &arm, const double *q, int i) {
+    float st, ct;
+    sincosf((float)q[i - 1] + arm.dh[i - 1][4], &st, &ct);
+    const float a = arm.dh[i - 1][0], d = arm.dh[i - 1][1], cA = arm.dh[i - 1][2], sA = arm.dh[i - 1][3];
+    const float l01 = -st * cA, l02 = st * sA, l03 = a * ct;
+    const float l11 = ct * cA, l12 = -ct * sA, l13 = a * st;
+    float n0, n1, n2, n3;
+    n0 = r00 * ct + r01 * st; n1 = r00 * l01 + r01 * l11 + r02 * sA; n2 = r00 * l02 + r01 * l12 + r02 * cA;
+    n3 = r00 * l03 + r01 * l13 + r02 * d + p0;
+    r00 = n0; r01 = n1; r02 = n2; p0 = n3;
+    n0 = r10 * ct + r11 * st; n1 = r10 * l01 + r11 * l11 + r12 * sA; n2 = r10 * l02 + r11 * l12 + r12 * cA;
+    n3 = r10 * l03 + r11 * l13 + r12 * d + p1;
+    r10 = n0; r11 = n1; r12 = n2; p1 = n3;
+    n0 = r20 * ct + r21 * st; n1 = r20 * l01 + r21 * l11 + r22 * sA; n2 = r20 * l02 + r21 * l12 + r22 * cA;
+    n3 = r20 * l03 + r21 * l13 + r22 * d + p2;
+    r20 = n0; r21 = n1; r22 = n2; p2 = n3;
+  }
+  __device__ __forceinline__ void centre(const float4 &sp, float &cx, float &cy, float &cz) const {
+    cx = r00 * sp.x + r01 * sp.y + r02 * sp.z + p0;
+    cy = r10 * sp.x + r11 * sp.y + r12 * sp.z + p1;
+    cz = r20 * sp.x + r21 * sp.y + r22 * sp.z + p2;
+  }
+};
+
+// Pass 1 (clearance field): fp32 FK frame by frame; the field loads of a link's spheres are issued in
+// groups of 4 and consumed only after the NEXT frame has been computed, so the L2 latency of the field
+// overlaps the sincos / frame product; no per-sphere branch.  Returns the mask of the sphere slots the
+// field could not certify (0: the state is free, and *cmin is a lower bound of its clearance).
+// Requires w.df != nullptr.
+__device__ __forceinline__ uint32_t grid_certify(const DeviceWorld &w, const ArmTableF32 &arm, const double *q,
+                                                 float *cmin_out) {
   const float *df = w.df;
   const int dnx = w.df_n[0], dny = w.df_n[1], dnz = w.df_n[2];
   const float dox = w.df_org[0], doy = w.df_org[1], doz = w.df_org[2], dinv = w.df_inv, dout = w.df_out;
   float cmin = CUDART_INF_F;
+  uint32_t unc = 0;
+  float dv0 = CUDART_INF_F, dv1 = CUDART_INF_F, dv2 = CUDART_INF_F, dv3 = CUDART_INF_F; // field - radius, in flight
+  int jb = 0;                                                                         // slot of dv0
+  FrameF32 f;
+  auto consume = [&]() {
+    cmin = fminf(fminf(cmin, dv0), fminf(dv1, fminf(dv2, dv3)));
+    unc |= (dv0 > 0.f ? 0u : 1u << jb) | (dv1 > 0.f ? 0u : 2u << jb) | (dv2 > 0.f ? 0u : 4u << jb) |
+           (dv3 > 0.f ? 0u : 8u << jb);
+  };
+  auto lookup = [&](int j) -> float {
+    const float4 sp = arm.sphere[j];
+    float cx, cy, cz;
+    f.centre(sp, cx, cy, cz);
+    const float fx = (cx - dox) * dinv, fy = (cy - doy) * dinv, fz = (cz - doz) * dinv;
+    float dv = dout; // outside the field's box (or NaN)
+    if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)dnx && fy < (float)dny && fz < (float)dnz)
+      dv = __ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx);
+    return dv - sp.w;
+  };
+  f.reset();
   for (int i = 0; i <= w.dof; ++i) {
-    if (i > 0) {
-      float st, ct;
-      sincosf((float)q[i - 1] + arm.dh[i - 1][4], &st, &ct);
-      const float a = arm.dh[i - 1][0], d = arm.dh[i - 1][1], cA = arm.dh[i - 1][2], sA = arm.dh[i - 1][3];
-      // T <- T * [Rz(theta) Tz(d) Tx(a) Rx(alpha)]
-      const float l01 = -st * cA, l02 = st * sA, l03 = a * ct;
-      const float l11 = ct * cA, l12 = -ct * sA, l13 = a * st;
-      float n0, n1, n2, n3;
-      n0 = r00 * ct + r01 * st; n1 = r00 * l01 + r01 * l11 + r02 * sA; n2 = r00 * l02 + r01 * l12 + r02 * cA;
-      n3 = r00 * l03 + r01 * l13 + r02 * d + p0;
-      r00 = n0; r01 = n1; r02 = n2; p0 = n3;
-      n0 = r10 * ct + r11 * st; n1 = r10 * l01 + r11 * l11 + r12 * sA; n2 = r10 * l02 + r11 * l12 + r12 * cA;
-      n3 = r10 * l03 + r11 * l13 + r12 * d + p1;
-      r10 = n0; r11 = n1; r12 = n2; p1 = n3;
-      n0 = r20 * ct + r21 * st; n1 = r20 * l01 + r21 * l11 + r22 * sA; n2 = r20 * l02 + r21 * l12 + r22 * cA;
-      n3 = r20 * l03 + r21 * l13 + r22 * d + p2;
-      r20 = n0; r21 = n1; r22 = n2; p2 = n3;
+    if (i > 0)
+      f.advance(arm, q, i);
+    int j = arm.link_first[i];
+    const int je = arm.link_first[i + 1];
+    while (j < je) {
+      consume(); // the previous group: its loads had a frame product (or a group) to land
+      jb = j;
+      dv0 = lookup(j);
+      dv1 = j + 1 < je ? lookup(j + 1) : CUDART_INF_F;
+      dv2 = j + 2 < je ? lookup(j + 2) : CUDART_INF_F;
+      dv3 = j + 3 < je ? lookup(j + 3) : CUDART_INF_F;
+      j += 4;
     }
+  }
+  consume();
+  *cmin_out = cmin < CUDART_INF_F ? cmin : 0.f;
+  return unc;
+}
+
+// Pass 2: FK again, and the sphere slots in `unc` walk the obstacle list of their centre's cell.
+// delta bounds |fp32 distance - exact distance| of a (sphere, obstacle) pair; three outcomes per
+// candidate pair: farther than r+R+delta -> free; nearer than r+R-delta -> colliding (both certain in
+// fp32); in between -> the fp64 chain and the specification's formula decide.
+__device__ __forceinline__ bool grid_lists(const DeviceWorld &w, const ObstacleTables &t, const double *q, uint32_t unc) {
+  const ArmTableF32 &arm = *t.arm;
+  const int nx = w.grid_n[0], ny = w.grid_n[1], nz = w.grid_n[2];
+  const float ox = w.grid_org[0], oy = w.grid_org[1], oz = w.grid_org[2], ginv = w.grid_inv;
+  FrameF32 f;
+  f.reset();
+  for (int i = 0; i <= w.dof; ++i) {
+    if (i > 0)
+      f.advance(arm, q, i);
+    if (arm.link_first[i] >= 32 || (unc >> arm.link_first[i]) == 0)
+      break; // no uncertified sphere on this or any later frame
     for (int j = arm.link_first[i]; j < arm.link_first[i + 1]; ++j) {
+      if (!((unc >> j) & 1u))
+        continue;
       const float4 sp = arm.sphere[j];
-      const float cx = r00 * sp.x + r01 * sp.y + r02 * sp.z + p0;
-      const float cy = r10 * sp.x + r11 * sp.y + r12 * sp.z + p1;
-      const float cz = r20 * sp.x + r21 * sp.y + r22 * sp.z + p2;
+      float cx, cy, cz;
+      f.centre(sp, cx, cy, cz);
       const float rs = sp.w;
-      if (df) { // clearance field first: most free spheres are settled by one load
-        const float fx = (cx - dox) * dinv, fy = (cy - doy) * dinv, fz = (cz - doz) * dinv;
-        float dv = dout;
-        if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)dnx && fy < (float)dny && fz < (float)dnz)
-          dv = __ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx);
-        const float cj = dv - rs;
-        if (cj > 0.f) {
-          cmin = fminf(cmin, cj);
-          continue;
-        }
-        cmin = 0.f;
-      }
       const float gx = (cx - ox) * ginv, gy = (cy - oy) * ginv, gz = (cz - oz) * ginv;
       // outside the grid (or NaN): no inflated obstacle box contains the centre
       if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float)nx && gy < (float)ny && gz < (float)nz))
@@ -511,9 +563,36 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
       }
     }
   }
-  if (clear)
-    *clear = (df && cmin < CUDART_INF_F) ? cmin : 0.f;
   return true;
+}
+
+// `clear` (optional): receives a lower bound of the state's clearance (metres) when every link sphere was
+// certified by the clearance field, else 0.
+static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
+                                                     float *clear = nullptr) {
+  const DeviceWorld &w = *wp;
+  uint32_t unc = 0xFFFFFFFFu;
+  if (w.df) {
+    float cmin;
+    unc = grid_certify(w, *tp->arm, q, &cmin);
+    if (unc == 0) {
+      if (clear)
+        *clear = cmin;
+      return true;
+    }
+  }
+  if (clear)
+    *clear = 0.f;
+  return grid_lists(w, *tp, q, unc);
+}
+// the two passes as separate out-of-line calls (the sample / resolve kernels of check_motion.cu)
+static __device__ __noinline__ uint32_t state_certify_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
+                                                           float *cmin) {
+  return grid_certify(*wp, *tp->arm, q, cmin);
+}
+static __device__ __noinline__ bool state_lists_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
+                                                     uint32_t unc) {
+  return grid_lists(*wp, *tp, q, unc);
 }
 
 // validity of one state through whichever broad phase the world has
