@@ -416,11 +416,11 @@ def run_ours(args, rank, local_rank, world):
             if record:
                 kernel_ms.append(world_h.last_kernel_ms())
 
-        launches_per_step = 5  # phase A, scan (2 kernels), expand, phase B
+        launches_per_step = 7  # sample, resolve, gaps, scan (2 kernels), expand, phase B (+ one memset)
         units_per_step = E  # all ranks together
         metric, unit = "validated edges/s", "edges/s"
         algo_bytes = n_local * (2 * 56 + 1)
-        kernel_name = "cm_phase_a_kernel+cm_phase_b_kernel"
+        kernel_name = "cm_sample_kernel+cm_resolve_kernel+cm_phase_b_kernel"
         config = {
             "workload": f"batched checkMotion: {E} edges at 0.01 rad, 7-DOF sphere-FK arm (16 link spheres) "
                         f"vs 256 obstacles (BASELINE.json configs[2]); edge length ~U(0,1] rad",
