@@ -66,3 +66,33 @@ def test_free_world_all_valid(P, synth, world_arrays):
     w = P.World(dh, link, xyzr, np.zeros((0, 4)), np.zeros((0, 6)))
     a, b = synth.edges(5, 300)
     assert np.all(w.check_motion_batch(a, b, 0.01) == 1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_thin_obstacles_conservative_advancement(P, O, synth, world_arrays, mode):
+    # Obstacles far thinner than the spacing of phase A's samples: an edge is typically invalid at one or
+    # two isolated states only, which conservative advancement (states struck off because a neighbouring
+    # sample has enough clearance) must never skip.  Few obstacles -> large clearances -> long reaches.
+    dh, link, xyzr, _, _ = world_arrays
+    rng = np.random.default_rng(31)
+    n_s, n_b = 40, 24
+    d = rng.normal(size=(n_s, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    sph = np.hstack([d * rng.uniform(0.25, 1.1, (n_s, 1)), rng.uniform(0.003, 0.012, (n_s, 1))])
+    sph[:, 2] = np.abs(sph[:, 2]) + 0.15
+    d = rng.normal(size=(n_b, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    half = np.full((n_b, 3), 0.15); half[np.arange(n_b), rng.integers(0, 3, n_b)] = 0.002   # thin plates
+    box = np.hstack([d * rng.uniform(0.4, 1.1, (n_b, 1)), half])
+    box[:, 2] = np.abs(box[:, 2]) + 0.25
+    gw = P.World(dh, link, xyzr, sph, box)
+    ow = O.World(dh, link, xyzr, sph, box)
+    for seed, n, max_len in ((41, 9000, 1.0), (42, 5000, 3.0), (43, 1500, 1.0)):   # flattened path twice, warp path once
+        a, b = synth.edges(seed, n, max_len=max_len)
+        res = 0.01 if mode == 0 else 0.02
+        gv = gw.check_motion_batch(a, b, res, mode=mode)
+        ov, oc, nt = ow.check_motion_batch(a, b, res, mode=mode, nthreads=8)
+        _compare(gv, ov, oc)
+        assert 0.05 < gv.mean() < 0.98
+    # states: the field + lists against the oracle
+    q = synth.cloud(44, 30000)
+    ov, oc = ow.is_valid_batch(q, nthreads=8)
+    assert _compare(gw.is_valid_batch(q), ov, oc) == 0
