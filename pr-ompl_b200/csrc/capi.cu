@@ -826,7 +826,7 @@ int prgpu_rrtc_batch_create(prgpu_world_t *w, const prgpu_rrtc_params *params, u
       (rc = h->ss.reserve(B * M * D * 8)) || (rc = h->gs.reserve(B * M * D * 8)) ||
       (rc = h->sp.reserve(B * M * 4)) || (rc = h->gp.reserve(B * M * 4)) || (rc = h->status.reserve(B * 4)) ||
       (rc = h->iters.reserve(B * 4)) || (rc = h->ns.reserve(B * 4)) || (rc = h->ng.reserve(B * 4)) ||
-      (rc = h->cs.reserve(B * 4)) || (rc = h->cg.reserve(B * 4)) || (rc = h->ovf.reserve(B * 4))) {
+      (rc = h->cs.reserve(B * 4)) || (rc = h->cg.reserve(B * 4)) || (rc = h->ovf.reserve((B + 1) * 4))) {
     prgpu_rrtc_batch_destroy(h);
     return rc;
   }
@@ -865,7 +865,8 @@ int prgpu_rrtc_batch_run_device(prgpu_rrtc_batch_t *h, const double *starts_dev,
   b.conn_start = h->cs.as<int32_t>();
   b.conn_goal = h->cg.as<int32_t>();
   b.overflow = h->ovf.as<uint32_t>();
-  int rc = rrtc_batch_launch(h->world->host, h->world->dev, h->dp, b, h->n, (cudaStream_t)stream);
+  b.work_counter = h->ovf.as<uint32_t>() + (h->n ? h->n : 1);
+  int rc = rrtc_batch_launch(h->world->host, h->world->dev, h->dp, b, h->n, h->world->sm_count, (cudaStream_t)stream);
   if (rc == PRGPU_OK)
     h->ran = true;
   return rc;

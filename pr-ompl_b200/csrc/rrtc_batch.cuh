@@ -19,7 +19,8 @@ struct RrtcDeviceBuffers {
   uint32_t *iters, *n_start, *n_goal; // B
   int32_t *conn_start, *conn_goal;    // B: ends of the solution path in each tree (-1 if none)
   uint32_t *overflow;                 // B
+  uint32_t *work_counter;             // 1: next unstarted query (zeroed by the launch)
 };
 int rrtc_batch_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const RrtcDeviceParams &p,
-                      const RrtcDeviceBuffers &b, uint32_t n_queries, cudaStream_t stream);
+                      const RrtcDeviceBuffers &b, uint32_t n_queries, int sm_count, cudaStream_t stream);
 } // namespace prgpu
