@@ -461,8 +461,10 @@ struct FrameF32 {
 // overlaps the sincos / frame product; no per-sphere branch.  Returns the mask of the sphere slots the
 // field could not certify (0: the state is free, and *cmin is a lower bound of its clearance).
 // Requires w.df != nullptr.
+// `centres` (optional, 3 floats per sphere slot): receives every sphere centre, so that the second pass of the
+// same thread need not repeat the FK chain.
 __device__ __forceinline__ uint32_t grid_certify(const DeviceWorld &w, const ArmTableF32 &arm, const double *q,
-                                                 float *cmin_out) {
+                                                 float *cmin_out, float *centres = nullptr) {
   const float *df = w.df;
   const int dnx = w.df_n[0], dny = w.df_n[1], dnz = w.df_n[2];
   const float dox = w.df_org[0], doy = w.df_org[1], doz = w.df_org[2], dinv = w.df_inv, dout = w.df_out;
@@ -480,6 +482,11 @@ __device__ __forceinline__ uint32_t grid_certify(const DeviceWorld &w, const Arm
     const float4 sp = arm.sphere[j];
     float cx, cy, cz;
     f.centre(sp, cx, cy, cz);
+    if (centres) {
+      centres[3 * j] = cx;
+      centres[3 * j + 1] = cy;
+      centres[3 * j + 2] = cz;
+    }
     const float fx = (cx - dox) * dinv, fy = (cy - doy) * dinv, fz = (cz - doz) * dinv;
     float dv = dout; // outside the field's box (or NaN)
     if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)dnx && fy < (float)dny && fz < (float)dnz)
@@ -507,14 +514,54 @@ __device__ __forceinline__ uint32_t grid_certify(const DeviceWorld &w, const Arm
   return unc;
 }
 
-// Pass 2: FK again, and the sphere slots in `unc` walk the obstacle list of their centre's cell.
+// Pass 2: the sphere slots in `unc` walk the obstacle list of their centre's cell.
 // delta bounds |fp32 distance - exact distance| of a (sphere, obstacle) pair; three outcomes per
 // candidate pair: farther than r+R+delta -> free; nearer than r+R-delta -> colliding (both certain in
 // fp32); in between -> the fp64 chain and the specification's formula decide.
-__device__ __forceinline__ bool grid_lists(const DeviceWorld &w, const ObstacleTables &t, const double *q, uint32_t unc) {
+// false: sphere slot j (centre cx,cy,cz) certainly collides or the fp64 verdict says so
+__device__ __forceinline__ bool grid_sphere_free(const DeviceWorld &w, const ObstacleTables &t, const double *q, int j,
+                                                 float cx, float cy, float cz) {
   const ArmTableF32 &arm = *t.arm;
   const int nx = w.grid_n[0], ny = w.grid_n[1], nz = w.grid_n[2];
-  const float ox = w.grid_org[0], oy = w.grid_org[1], oz = w.grid_org[2], ginv = w.grid_inv;
+  const float gx = (cx - w.grid_org[0]) * w.grid_inv, gy = (cy - w.grid_org[1]) * w.grid_inv,
+              gz = (cz - w.grid_org[2]) * w.grid_inv;
+  // outside the grid (or NaN): no inflated obstacle box contains the centre
+  if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float)nx && gy < (float)ny && gz < (float)nz))
+    return true;
+  const float rs = arm.sphere[j].w;
+  const int cell = ((int)gz * ny + (int)gy) * nx + (int)gx;
+  for (uint32_t it = t.cell_start[cell]; it < t.cell_start[cell + 1]; ++it) {
+    const uint32_t id = t.cell_item[it];
+    if (id & 0x8000u) {
+      const uint32_t o = id & 0x7FFFu;
+      const float4 bc = t.ob[2 * o], bh = t.ob[2 * o + 1];
+      const float ex = fmaxf(fabsf(cx - bc.x) - bh.x, 0.0f);
+      const float ey = fmaxf(fabsf(cy - bc.y) - bh.y, 0.0f);
+      const float ez = fmaxf(fabsf(cz - bc.z) - bh.z, 0.0f);
+      const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+      if (d2 < rs * rs) {
+        // deeper than the fp32 error bound: certainly colliding; only the thin band needs fp64
+        const float rin = rs - 2.0f * w.delta;
+        if ((rin > 0.f && d2 < rin * rin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)o, true))
+          return false;
+      }
+    } else {
+      const float4 ob = t.os[id];
+      const float dx = cx - ob.x, dy = cy - ob.y, dz = cz - ob.z;
+      const float thr = rs + ob.w; // grid tables keep the obstacle radius in .w
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      if (d2 < thr * thr) {
+        const float tin = thr - 2.0f * w.delta;
+        if ((tin > 0.f && d2 < tin * tin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)id, false))
+          return false;
+      }
+    }
+  }
+  return true;
+}
+// with the FK chain repeated (the centres were not kept: another kernel certified the state)
+__device__ __forceinline__ bool grid_lists(const DeviceWorld &w, const ObstacleTables &t, const double *q, uint32_t unc) {
+  const ArmTableF32 &arm = *t.arm;
   FrameF32 f;
   f.reset();
   for (int i = 0; i <= w.dof; ++i) {
@@ -525,43 +572,22 @@ __device__ __forceinline__ bool grid_lists(const DeviceWorld &w, const ObstacleT
     for (int j = arm.link_first[i]; j < arm.link_first[i + 1]; ++j) {
       if (!((unc >> j) & 1u))
         continue;
-      const float4 sp = arm.sphere[j];
       float cx, cy, cz;
-      f.centre(sp, cx, cy, cz);
-      const float rs = sp.w;
-      const float gx = (cx - ox) * ginv, gy = (cy - oy) * ginv, gz = (cz - oz) * ginv;
-      // outside the grid (or NaN): no inflated obstacle box contains the centre
-      if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float)nx && gy < (float)ny && gz < (float)nz))
-        continue;
-      const int cell = ((int)gz * ny + (int)gy) * nx + (int)gx;
-      for (uint32_t it = t.cell_start[cell]; it < t.cell_start[cell + 1]; ++it) {
-        const uint32_t id = t.cell_item[it];
-        if (id & 0x8000u) {
-          const uint32_t o = id & 0x7FFFu;
-          const float4 bc = t.ob[2 * o], bh = t.ob[2 * o + 1];
-          const float ex = fmaxf(fabsf(cx - bc.x) - bh.x, 0.0f);
-          const float ey = fmaxf(fabsf(cy - bc.y) - bh.y, 0.0f);
-          const float ez = fmaxf(fabsf(cz - bc.z) - bh.z, 0.0f);
-          const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-          if (d2 < rs * rs) {
-            // deeper than the fp32 error bound: certainly colliding; only the thin band needs fp64
-            const float rin = rs - 2.0f * w.delta;
-            if ((rin > 0.f && d2 < rin * rin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)o, true))
-              return false;
-          }
-        } else {
-          const float4 ob = t.os[id];
-          const float dx = cx - ob.x, dy = cy - ob.y, dz = cz - ob.z;
-          const float thr = rs + ob.w; // grid tables keep the obstacle radius in .w
-          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          if (d2 < thr * thr) {
-            const float tin = thr - 2.0f * w.delta;
-            if ((tin > 0.f && d2 < tin * tin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)id, false))
-              return false;
-          }
-        }
-      }
+      f.centre(arm.sphere[j], cx, cy, cz);
+      if (!grid_sphere_free(w, t, q, j, cx, cy, cz))
+        return false;
     }
+  }
+  return true;
+}
+// with the centres the first pass left behind
+__device__ __forceinline__ bool grid_lists_kept(const DeviceWorld &w, const ObstacleTables &t, const double *q, uint32_t unc,
+                                                const float *centres) {
+  while (unc) {
+    const int j = __ffs(unc) - 1;
+    unc &= unc - 1;
+    if (!grid_sphere_free(w, t, q, j, centres[3 * j], centres[3 * j + 1], centres[3 * j + 2]))
+      return false;
   }
   return true;
 }
@@ -571,19 +597,18 @@ __device__ __forceinline__ bool grid_lists(const DeviceWorld &w, const ObstacleT
 static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
                                                      float *clear = nullptr) {
   const DeviceWorld &w = *wp;
-  uint32_t unc = 0xFFFFFFFFu;
-  if (w.df) {
-    float cmin;
-    unc = grid_certify(w, *tp->arm, q, &cmin);
-    if (unc == 0) {
-      if (clear)
-        *clear = cmin;
-      return true;
-    }
-  }
   if (clear)
     *clear = 0.f;
-  return grid_lists(w, *tp, q, unc);
+  if (!w.df)
+    return grid_lists(w, *tp, q, 0xFFFFFFFFu);
+  float cmin, centres[3 * WORLD_MAX_S];
+  const uint32_t unc = grid_certify(w, *tp->arm, q, &cmin, centres);
+  if (unc == 0) {
+    if (clear)
+      *clear = cmin;
+    return true;
+  }
+  return grid_lists_kept(w, *tp, q, unc, centres);
 }
 // the two passes as separate out-of-line calls (the sample / resolve kernels of check_motion.cu)
 static __device__ __noinline__ uint32_t state_certify_grid(const DeviceWorld *wp, const ObstacleTables *tp, const double *q,
