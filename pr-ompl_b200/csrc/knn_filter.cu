@@ -149,6 +149,7 @@ constexpr int CT_QPB = (FT_THREADS / 32) * CT_MT * 16; // queries per block (256
 #define CT_MINB 8 // resident blocks per SM the collect kernel is compiled for (64 registers)
 #endif
 constexpr uint32_t CT_WAVES = 32; // grid size of the collect kernel in units of resident blocks
+constexpr uint32_t CT_MIN_TILES = 12; // tiles per block below which the block prologue shows
 
 __device__ __forceinline__ uint32_t tf32_bits(float v) {
   uint32_t u;
@@ -558,7 +559,7 @@ __global__ void scatter_rows_kernel(const uint32_t *__restrict__ ids, uint32_t n
   dist_out[(size_t)q * k + e] = sd[i];
 }
 
-constexpr uint32_t FT_SAMPLE_STRIDE = 64; // the sample pass visits every 64th tile
+constexpr uint32_t FT_SAMPLE_STRIDE = 64; // the sample pass visits every 64th tile (every 32nd of a tree below 4M nodes)
 
 template <int DIM>
 int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k, const uint32_t *lo,
@@ -569,7 +570,12 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   const uint32_t qblocks = (nq + CT_QPB - 1) / CT_QPB;
   // candidate buffer per query: the sample's kp-th smallest key admits ~kp*stride nodes of the full tree
   uint32_t cap = 1;
-  while (cap < 3u * (uint32_t)kp * FT_SAMPLE_STRIDE)
+  // A candidate costs the scan a replayed 8-node group, an atomic and two stores, and the select pass a
+  // key: about kp * stride of them per query whatever the tree size, so small trees (and the shards of a
+  // multi-GPU sweep) take a denser sample -- its cost shrinks with the tree.  P[fewer than 16 nodes
+  // below T_q] = P[Gamma(8) < 16/stride]: 1.5e-12 at stride 64, 1e-7 at 32.
+  const uint32_t sample_stride = t.n >= (1u << 22) ? FT_SAMPLE_STRIDE : FT_SAMPLE_STRIDE / 2;
+  while (cap < 3u * (uint32_t)kp * sample_stride)
     cap <<= 1;
   if (cap > 4096)
     cap = 4096;
@@ -625,10 +631,10 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   // aliases `counts`: the counters are zeroed by the last threshold kernel, after the sample pass has
   // read its seeds.
   float *coarse_buf = reinterpret_cast<float *>(counts);
-  rc = sample_pass(FT_SAMPLE_STRIDE * 32, nullptr, coarse_buf, nullptr);
+  rc = sample_pass(sample_stride * 32, nullptr, coarse_buf, nullptr);
   if (rc != PRGPU_OK)
     return rc;
-  rc = sample_pass(FT_SAMPLE_STRIDE, coarse_buf, thresh, counts);
+  rc = sample_pass(sample_stride, coarse_buf, thresh, counts);
   if (rc != PRGPU_OK)
     return rc;
 
@@ -644,7 +650,12 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   chunks = chunks < 1 ? 1 : chunks;
   // many short blocks instead of one wave of long ones: the blocks resident on an SM do not advance at
   // the same rate, and a one-wave grid ran its last third at 4.4 of 6 warps per scheduler (ncu r01d)
+  const uint32_t one_wave = chunks;
   chunks *= CT_WAVES;
+  // ... but a block's prologue (64 queries' A fragments per warp) has to be paid off: at least
+  // CT_MIN_TILES tiles per block while that still leaves a full wave
+  if (chunks > ntiles2 / CT_MIN_TILES)
+    chunks = ntiles2 / CT_MIN_TILES > one_wave ? ntiles2 / CT_MIN_TILES : one_wave;
   if (chunks > ntiles2)
     chunks = ntiles2;
   const uint32_t tiles_per_chunk = (ntiles2 + chunks - 1) / chunks;
