@@ -768,7 +768,7 @@ struct prgpu_rrtc_batch {
   prgpu_rrtc_params params;
   RrtcDeviceParams dp;
   uint32_t n = 0;
-  DevBuf starts, goals, ss, gs, sp, gp, status, iters, ns, ng, cs, cg, ovf;
+  DevBuf starts, goals, ss, gs, sp, gp, status, iters, ns, ng, cs, cg, ovf, resume;
   bool ran = false;
 };
 
@@ -826,7 +826,8 @@ int prgpu_rrtc_batch_create(prgpu_world_t *w, const prgpu_rrtc_params *params, u
       (rc = h->ss.reserve(B * M * D * 8)) || (rc = h->gs.reserve(B * M * D * 8)) ||
       (rc = h->sp.reserve(B * M * 4)) || (rc = h->gp.reserve(B * M * 4)) || (rc = h->status.reserve(B * 4)) ||
       (rc = h->iters.reserve(B * 4)) || (rc = h->ns.reserve(B * 4)) || (rc = h->ng.reserve(B * 4)) ||
-      (rc = h->cs.reserve(B * 4)) || (rc = h->cg.reserve(B * 4)) || (rc = h->ovf.reserve((B + 1) * 4))) {
+      (rc = h->cs.reserve(B * 4)) || (rc = h->cg.reserve(B * 4)) || (rc = h->ovf.reserve((2 * B + 4) * 4)) ||
+      (rc = h->resume.reserve(B * sizeof(RrtcLoopState)))) {
     prgpu_rrtc_batch_destroy(h);
     return rc;
   }
@@ -840,7 +841,7 @@ int prgpu_rrtc_batch_destroy(prgpu_rrtc_batch_t *h) {
   cudaSetDevice(h->world->device);
   cudaStreamSynchronize(h->world->stream);
   for (DevBuf *b : {&h->starts, &h->goals, &h->ss, &h->gs, &h->sp, &h->gp, &h->status, &h->iters, &h->ns,
-                    &h->ng, &h->cs, &h->cg, &h->ovf})
+                    &h->ng, &h->cs, &h->cg, &h->ovf, &h->resume})
     b->release();
   delete h;
   return PRGPU_OK;
@@ -865,7 +866,14 @@ int prgpu_rrtc_batch_run_device(prgpu_rrtc_batch_t *h, const double *starts_dev,
   b.conn_start = h->cs.as<int32_t>();
   b.conn_goal = h->cg.as<int32_t>();
   b.overflow = h->ovf.as<uint32_t>();
-  b.work_counter = h->ovf.as<uint32_t>() + (h->n ? h->n : 1);
+  {
+    const size_t B = h->n ? h->n : 1;
+    b.work_counter = h->ovf.as<uint32_t>() + B;
+    b.susp_count = b.work_counter + 1;
+    b.team_counter = b.work_counter + 2;
+    b.susp_list = b.work_counter + 4;
+    b.resume = h->resume.as<RrtcLoopState>();
+  }
   int rc = rrtc_batch_launch(h->world->host, h->world->dev, h->dp, b, h->n, h->world->sm_count, (cudaStream_t)stream);
   if (rc == PRGPU_OK)
     h->ran = true;

@@ -1,20 +1,29 @@
-// T1: many independent RRTConnect queries, one WARP per query, resident on the device from the first
-// sample to the solution.
+// T1: many independent RRTConnect queries, resident on the device from the first sample to the solution.
 //
 // Follows pr_ompl::RRTConnect::solve / growTree (pr_ompl/src/RRTConnect.cpp:219-376, :178-217)
 // statement by statement -- tree alternation before the TRAPPED `continue` (:267 vs :303), goal
 // seeding (:270-286), CONNECT as repeated growTree with a fresh nearest query each step (:296-300),
 // rstate overwritten by the last added state (:313-314), goal-tree edges validated from the new
 // state toward the tree (:198), one step back on the start side at the connection (:332-335).
-// The 32 lanes of a warp cooperate inside each growTree: the linear nearest scan with the
-// (distance, index) order of NearestNeighborsLinear (butterfly reduction, no shared memory), then the
-// DiscreteMotionValidator tested set spread over the lanes with a vote for the early exit.  A query is a
-// long dependent chain (sample -> nearest -> validate -> append), so its speed is set by latency, not
-// width: one warp per query needs no block barrier at all, puts twice as many queries on an SM as a
-// 64-thread block per query did, and the warps are persistent -- each takes the next unstarted query
-// from a global counter when it finishes one, so the few queries that run to the sample budget do
-// not hold finished neighbours' registers.  The obstacle tables in shared memory are shared by the
-// RB_WARPS queries of a block.
+//
+// A query is a long dependent chain (sample -> nearest -> validate -> append): its speed is set by
+// latency, not width.  Two kernels:
+//
+//  rrtc_batch_kernel  one WARP per query.  The 32 lanes cooperate inside each growTree: the linear
+//      nearest scan with the (distance, index) order of NearestNeighborsLinear (four independent fp64
+//      chains per lane, the square root only for a node that may replace the best, butterfly reduction),
+//      then the DiscreteMotionValidator tested set spread over the lanes with a vote for the early
+//      exit.  No block barrier.  Warps are persistent: each takes the next unstarted query from a
+//      global counter; the obstacle tables in shared memory serve the RB_WARPS queries of a block.
+//      A query still unsolved after RB_CUT samples is suspended (its trees are in global memory, the
+//      loop state is a few words) and queued for the second kernel.
+//
+//  rrtc_team_kernel   one BLOCK (RB_WARPS warps) per suspended query.  These are the queries that mostly
+//      get TRAPPED: an iteration whose first growTree is trapped changes nothing but the sample counter
+//      and the tree alternation, so warp w evaluates the first growTree of iteration it+w against the
+//      unchanged trees; the iterations before the first untrapped one are skipped wholesale, the warp
+//      that found it carries its iteration on (append, the other tree's CONNECT, the connection test)
+//      while the others wait.  Same samples, same order of effects, bit-identical trees.
 #include <cstdio>
 #include "rrtc_batch.cuh"
 #include "sample_stream.cuh"
@@ -22,87 +31,89 @@
 namespace prgpu {
 namespace {
 
-constexpr int RB_WARPS = 8;            // queries in flight per block
+constexpr int RB_WARPS = 8;            // queries in flight per block (first kernel) / team size (second)
 constexpr int RB_THREADS = RB_WARPS * 32;
+#ifndef RB_CUT
+#define RB_CUT 96                      // samples after which an unsolved query moves to the team kernel
+#endif
 enum { GS_TRAPPED = 0, GS_ADVANCED = 1, GS_REACHED = 2 };
 enum { ST_INVALID_START = 1, ST_INVALID_GOAL = 2, ST_TIMEOUT = 4, ST_EXACT = 6 }; // PlannerStatus values
+enum { IT_CONTINUE = 0, IT_END = 1 };
 
-struct Shared {
+struct Shared { // per warp
   double rstate[WORLD_MAX_DOF];
   double xstate[WORLD_MAX_DOF];
   double near[WORLD_MAX_DOF];
 };
 
+// One query as seen by one warp.  Every member is warp-uniform.
 template <int SP>
-__global__ void __launch_bounds__(RB_THREADS)
-rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, const RrtcDeviceBuffers b,
-                  uint32_t n_queries) {
-  const DeviceWorld &w = *wp;
-  extern __shared__ float4 s_obs[];
-  __shared__ Shared sh_all[RB_WARPS];
-  const ObstacleTables tabs = load_tables(w, s_obs);
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  Shared &sh = sh_all[threadIdx.x >> 5];
-  const int tid = lane; // lane of the query's warp
-  const int dim = p.dim;
- for (;;) { // persistent warp: next unstarted query
-  uint32_t qid = 0;
-  if (lane == 0)
-    qid = atomicAdd(b.work_counter, 1u);
-  qid = __shfl_sync(0xffffffffu, qid, 0);
-  if (qid >= n_queries)
-    return;
-  double *tS = b.start_states + (size_t)qid * p.max_nodes * dim;
-  double *tG = b.goal_states + (size_t)qid * p.max_nodes * dim;
-  int32_t *pS = b.start_parent + (size_t)qid * p.max_nodes;
-  int32_t *pG = b.goal_parent + (size_t)qid * p.max_nodes;
-  const double *start = b.starts + (size_t)qid * dim;
-  const double *goal = b.goals + (size_t)qid * dim;
-  uint32_t nS = 0, nG = 0; // uniform across the warp
-#ifdef RB_PROFILE
-  long long prof_scan = 0, prof_plan = 0, prof_valid = 0, prof_total = clock64(), prof_grows = 0, prof_states = 0;
-#endif
+struct Planner {
+  const DeviceWorld *wp;
+  const ObstacleTables *tabs;
+  const RrtcDeviceParams &p;
+  Shared &sh;
+  int tid; // lane
+  int dim;
+  uint32_t qid;
+  double *tS, *tG;
+  int32_t *pS, *pG;
+  const double *goal;
+  RrtcLoopState s;
 
-  // warp-uniform helpers ------------------------------------------------------------------
-  auto in_bounds = [&](const double *q) { // RealVectorStateSpace::satisfiesBounds
+  struct Check { // result of the first half of growTree
+    int32_t nmotion;
+    bool ok, reach;
+    double c[WORLD_MAX_DOF]; // dstate
+  };
+
+  __device__ __forceinline__ Planner(const DeviceWorld *wp_, const ObstacleTables *tabs_, const RrtcDeviceParams &p_,
+                                     const RrtcDeviceBuffers &b, Shared &sh_, int lane, uint32_t qid_)
+      : wp(wp_), tabs(tabs_), p(p_), sh(sh_), tid(lane), dim(p_.dim), qid(qid_) {
+    tS = b.start_states + (size_t)qid * p.max_nodes * dim;
+    tG = b.goal_states + (size_t)qid * p.max_nodes * dim;
+    pS = b.start_parent + (size_t)qid * p.max_nodes;
+    pG = b.goal_parent + (size_t)qid * p.max_nodes;
+    goal = b.goals + (size_t)qid * dim;
+  }
+
+  __device__ __forceinline__ bool in_bounds(const double *q) const { // RealVectorStateSpace::satisfiesBounds
     bool ok = true;
     for (int i = 0; i < dim; ++i)
       if (q[i] - 2.220446049250313e-16 > p.hi[i] || q[i] + 2.220446049250313e-16 < p.lo[i])
         ok = false;
     return ok;
-  };
-  auto single_valid = [&](const double *q) { // isValid of one state, evaluated by lane 0
+  }
+  __device__ __forceinline__ bool single_valid(const double *q) { // isValid of one state, evaluated by lane 0
     int f = 0;
     if (tid == 0) {
       double qq[WORLD_MAX_DOF];
 #pragma unroll
       for (int i = 0; i < WORLD_MAX_DOF; ++i)
         qq[i] = i < dim ? q[i] : 0.0;
-      f = (in_bounds(qq) && state_valid_call<SP>(wp, &tabs, qq)) ? 1 : 0;
+      f = (in_bounds(qq) && state_valid_call<SP>(wp, tabs, qq)) ? 1 : 0;
     }
     return __shfl_sync(0xffffffffu, f, 0) != 0;
-  };
-  auto append = [&](double *T, int32_t *P, uint32_t &n, const double *q, int32_t parent) {
+  }
+  __device__ __forceinline__ void append(double *T, int32_t *P, uint32_t &n, const double *q, int32_t parent) {
     if (tid < dim)
       T[(size_t)n * dim + tid] = q[tid];
     if (tid == 0)
       P[n] = parent;
     ++n;
     __syncwarp(); // the new node is visible to the next nearest scan
-  };
+  }
+  __device__ __forceinline__ void draw_sample(uint32_t it) { // :289
+    if (tid < dim)
+      sh.rstate[tid] = stream_uniform(p.seed, p.query_id_base + qid, it, tid, p.lo[tid], p.hi[tid]);
+    __syncwarp();
+  }
 
-  // growTree (RRTConnect.cpp:178-217); returns GrowState, sets xmotion on success
-  auto grow = [&](double *T, int32_t *P, uint32_t &n, bool tgi_start, int32_t &xmotion, bool &full) -> int {
-    // :181 nearest = first strict minimum of sqrt-distance in insertion order
-    // The scan is the latency chain of a long-running query (its trees grow to ~10^3 nodes): four nodes
-    // per lane are summed as independent chains, and the square root -- monotone, so a node whose
-    // squared sum is not below the best one cannot have a smaller distance -- is taken only for a node
-    // that may replace the best.
-#ifdef RB_PROFILE
-    long long c0 = clock64();
-    ++prof_grows;
-#endif
+  // growTree (RRTConnect.cpp:178-217), first half: nearest (:181), step clamp (:188-194), motion check (:198)
+  __device__ __forceinline__ void check(const double *T, uint32_t n, bool tgi_start, Check &r) {
+    // The scan is part of a query's latency chain: four nodes per lane are summed as independent chains,
+    // and the square root -- monotone, so a node whose squared sum is not below the best one cannot
+    // have a smaller distance -- is taken only for a node that may replace the best.
     double bd = CUDART_INF, bs = CUDART_INF;
     int32_t bi = 0x7FFFFFFF;
     double rq[WORLD_MAX_DOF];
@@ -158,38 +169,34 @@ rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, 
         bi = oi;
       }
     }
-    const int32_t nmotion = bi; // the butterfly leaves the same (distance, index) minimum in every lane
+    r.nmotion = bi; // the butterfly leaves the same (distance, index) minimum in every lane
     if (tid < dim)
-      sh.near[tid] = T[(size_t)nmotion * dim + tid];
+      sh.near[tid] = T[(size_t)r.nmotion * dim + tid];
     __syncwarp();
 
-#ifdef RB_PROFILE
-    long long c1 = clock64();
-    prof_scan += c1 - c0;
-#endif
-    // :188-194 distance and step clamp (bit exact; every thread computes the same values)
-    double a[WORLD_MAX_DOF], c[WORLD_MAX_DOF]; // a = nmotion->state, c = dstate
+    // :188-194 distance and step clamp (bit exact; every lane computes the same values)
+    double a[WORLD_MAX_DOF]; // nmotion->state
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < WORLD_MAX_DOF; ++k) {
       a[k] = k < dim ? sh.near[k] : 0.0;
-      c[k] = k < dim ? sh.rstate[k] : 0.0;
-      const double diff = __dsub_rn(a[k], c[k]);
+      r.c[k] = rq[k];
+      const double diff = __dsub_rn(a[k], r.c[k]);
       s = __dadd_rn(s, __dmul_rn(diff, diff));
     }
     const double d = __dsqrt_rn(s);
-    bool reach = true;
+    r.reach = true;
     if (d > p.range) {
       const double t = p.range / d;
 #pragma unroll
       for (int k = 0; k < WORLD_MAX_DOF; ++k)
-        c[k] = k < dim ? lerp_exact(a[k], c[k], t) : 0.0;
-      reach = false;
+        r.c[k] = k < dim ? lerp_exact(a[k], r.c[k], t) : 0.0;
+      r.reach = false;
     }
     // :198 start tree: checkMotion(nmotion, dstate); goal tree: isValid(dstate) && checkMotion(dstate, nmotion)
     // DiscreteMotionValidator: s1 = from, s2 = to; tested set {s2} U {from + (to-from) j/nd} (+ dstate itself)
-    double *from = tgi_start ? a : c;
-    double *to = tgi_start ? c : a;
+    const double *from = tgi_start ? a : r.c;
+    const double *to = tgi_start ? r.c : a;
     double s2 = 0.0;
 #pragma unroll
     for (int k = 0; k < WORLD_MAX_DOF; ++k) {
@@ -200,14 +207,9 @@ rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, 
     const uint32_t extra = tgi_start ? 0u : 1u;
     const uint32_t np = 1u + (nd >= 2 ? nd - 1 : 0u) + extra;
     const uint32_t rounds = (np + 31) / 32;
-#ifdef RB_PROFILE
-    long long c2 = clock64();
-    prof_plan += c2 - c1;
-    prof_states += np;
-#endif
-    bool ok = true;
-    for (uint32_t r = 0; r < rounds; ++r) {
-      const uint32_t pt = r + (uint32_t)tid * rounds;
+    r.ok = true;
+    for (uint32_t rd = 0; rd < rounds; ++rd) {
+      const uint32_t pt = rd + (uint32_t)tid * rounds;
       bool good = true;
       if (pt < np) {
         double q[WORLD_MAX_DOF];
@@ -225,129 +227,247 @@ rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, 
           for (int k = 0; k < WORLD_MAX_DOF; ++k)
             q[k] = lerp_exact(from[k], to[k], t);
         }
-        good = state_valid_call<SP>(wp, &tabs, q);
+        good = state_valid_call<SP>(wp, tabs, q);
       }
       if (__any_sync(0xffffffffu, !good)) {
-        ok = false;
+        r.ok = false;
         break;
       }
     }
-#ifdef RB_PROFILE
-    prof_valid += clock64() - c2;
-#endif
-    if (!ok)
+  }
+  // growTree, second half (:199-216)
+  __device__ __forceinline__ int commit(double *T, int32_t *P, uint32_t &n, const Check &r, int32_t &xmotion) {
+    if (!r.ok)
       return GS_TRAPPED; // :215
     if (n >= p.max_nodes) {
-      full = true;
+      s.full = 1;
       return GS_TRAPPED;
     }
     if (tid < dim)
-      sh.xstate[tid] = c[tid];
+      sh.xstate[tid] = r.c[tid];
     __syncwarp();
     xmotion = (int32_t)n;
-    append(T, P, n, sh.xstate, nmotion); // :200-209
-    return reach ? GS_REACHED : GS_ADVANCED;
-  };
-
-  // solve (RRTConnect.cpp:219-376) ----------------------------------------------------------
-  int status = ST_TIMEOUT;
-  int32_t connS = -1, connG = -1;
-  uint32_t it = 0;
-  bool full = false;
-  if (single_valid(start)) { // :230-236 via PlannerInputStates::nextStart
-    if (tid < dim)
-      sh.xstate[tid] = start[tid];
-    __syncwarp();
-    append(tS, pS, nS, sh.xstate, -1);
+    append(T, P, n, sh.xstate, r.nmotion); // :200-209
+    return r.reach ? GS_REACHED : GS_ADVANCED;
   }
-  if (nS == 0) {
-    status = ST_INVALID_START; // :238-242
-  } else {
-    bool startTree = true;
-    uint32_t sampledGoals = 0;
-    while (it < p.max_iters && !full) { // :263, ptc = sample budget
-      const bool growStart = startTree; // tree = startTree ? tStart : tGoal
-      bool tgi_start = startTree;
-      startTree = !startTree; // :267
-      if (nG == 0 || sampledGoals < nG / 2) { // :270
-        if (sampledGoals < 1) { // a GoalState yields one sample ever (Appendix B.7)
-          sampledGoals++;
-          if (single_valid(goal)) {
-            if (tid < dim)
-              sh.xstate[tid] = goal[tid];
-            __syncwarp();
-            append(tG, pG, nG, sh.xstate, -1);
-          }
-        }
-        if (nG == 0) // :281-285
-          break;
-      }
-      if (tid < dim) // :289
-        sh.rstate[tid] = stream_uniform(p.seed, p.query_id_base + qid, it, tid, p.lo[tid], p.hi[tid]);
+
+  // :225-257 up to the loop
+  __device__ __forceinline__ void begin(const double *start) {
+    s.it = 0;
+    s.nS = s.nG = 0;
+    s.sampledGoals = 0;
+    s.connS = s.connG = -1;
+    s.status = ST_TIMEOUT;
+    s.startTree = 1;
+    s.full = 0;
+    if (single_valid(start)) { // :230-236 via PlannerInputStates::nextStart
+      if (tid < dim)
+        sh.xstate[tid] = start[tid];
       __syncwarp();
-      ++it;
+      append(tS, pS, s.nS, sh.xstate, -1);
+    }
+    if (s.nS == 0)
+      s.status = ST_INVALID_START; // :238-242
+  }
 
-      int gs = GS_TRAPPED;
-      int32_t xmotion = -1, added = -1; // :295
-      bool second_done = false;
-      for (int phase = 0; phase < 2; ++phase) {
-        // phase 0 grows `tree` toward the sample (:296-300), phase 1 grows `otherTree` toward the
-        // node just added (:316-321)
-        const bool onStart = (phase == 0) ? growStart : !growStart;
-        const int ext = (phase == 0) ? p.ext_first : p.ext_second;
-        do {
-          gs = grow(onStart ? tS : tG, onStart ? pS : pG, onStart ? nS : nG, tgi_start, xmotion, full);
-        } while (gs == GS_ADVANCED && ext == 1);
-        if (phase == 1) {
-          second_done = true;
-          break;
-        }
-        if (xmotion < 0) // :303
-          break;
-        added = xmotion; // :307
-        xmotion = -1;
-        if (gs != GS_REACHED) { // :313-314
-          const double *src = (growStart ? tS : tG) + (size_t)added * dim;
-          __syncwarp();
+  // one pass of the solve loop (:263-376).  `pre`: the first growTree's check, already done by this warp
+  // against the current trees for this iteration's sample (team kernel), or nullptr.
+  __device__ __forceinline__ int iteration(const Check *pre) {
+    const bool growStart = s.startTree != 0; // tree = startTree ? tStart : tGoal
+    bool tgi_start = growStart;
+    s.startTree = s.startTree ? 0u : 1u; // :267
+    if (s.nG == 0 || s.sampledGoals < s.nG / 2) { // :270
+      if (s.sampledGoals < 1) { // a GoalState yields one sample ever (Appendix B.7)
+        s.sampledGoals++;
+        if (single_valid(goal)) {
           if (tid < dim)
-            sh.rstate[tid] = src[tid];
+            sh.xstate[tid] = goal[tid];
           __syncwarp();
+          append(tG, pG, s.nG, sh.xstate, -1);
         }
-        tgi_start = startTree; // :316
       }
-      if (!second_done)
-        continue;
+      if (s.nG == 0) // :281-285
+        return IT_END;
+    }
+    draw_sample(s.it);
+    ++s.it;
 
-      if (gs == GS_REACHED) { // :327 (isStartGoalPairValid is true for a GoalState)
-        int32_t startMotion = startTree ? xmotion : added; // :323-324
-        int32_t goalMotion = startTree ? added : xmotion;
-        if (pS[startMotion] >= 0) // :332-335
-          startMotion = pS[startMotion];
-        else
-          goalMotion = pG[goalMotion];
-        connS = startMotion;
-        connG = goalMotion;
-        status = ST_EXACT;
+    int gs = GS_TRAPPED;
+    int32_t xmotion = -1, added = -1; // :295
+    bool second_done = false;
+    for (int phase = 0; phase < 2; ++phase) {
+      // phase 0 grows `tree` toward the sample (:296-300), phase 1 grows `otherTree` toward the
+      // node just added (:316-321)
+      const bool onStart = (phase == 0) ? growStart : !growStart;
+      const int ext = (phase == 0) ? p.ext_first : p.ext_second;
+      do {
+        double *T = onStart ? tS : tG;
+        int32_t *P = onStart ? pS : pG;
+        uint32_t &n = onStart ? s.nS : s.nG;
+        if (pre) {
+          gs = commit(T, P, n, *pre, xmotion);
+          pre = nullptr;
+        } else {
+          Check r;
+          check(T, n, tgi_start, r);
+          gs = commit(T, P, n, r, xmotion);
+        }
+      } while (gs == GS_ADVANCED && ext == 1);
+      if (phase == 1) {
+        second_done = true;
         break;
       }
+      if (xmotion < 0) // :303
+        break;
+      added = xmotion; // :307
+      xmotion = -1;
+      if (gs != GS_REACHED) { // :313-314
+        const double *src = (growStart ? tS : tG) + (size_t)added * dim;
+        __syncwarp();
+        if (tid < dim)
+          sh.rstate[tid] = src[tid];
+        __syncwarp();
+      }
+      tgi_start = s.startTree != 0; // :316
+    }
+    if (!second_done)
+      return IT_CONTINUE;
+    if (gs == GS_REACHED) { // :327 (isStartGoalPairValid is true for a GoalState)
+      int32_t startMotion = s.startTree ? xmotion : added; // :323-324
+      int32_t goalMotion = s.startTree ? added : xmotion;
+      if (pS[startMotion] >= 0) // :332-335
+        startMotion = pS[startMotion];
+      else
+        goalMotion = pG[goalMotion];
+      s.connS = startMotion;
+      s.connG = goalMotion;
+      s.status = ST_EXACT;
+      return IT_END;
+    }
+    return IT_CONTINUE;
+  }
+
+  __device__ __forceinline__ void finish(const RrtcDeviceBuffers &b) const {
+    if (tid == 0) {
+      b.status[qid] = s.status;
+      b.iters[qid] = s.it;
+      b.n_start[qid] = s.nS;
+      b.n_goal[qid] = s.nG;
+      b.conn_start[qid] = s.connS;
+      b.conn_goal[qid] = s.connG;
+      b.overflow[qid] = s.full ? 1u : 0u;
     }
   }
-#ifdef RB_PROFILE
-  if (tid == 0 && it >= p.max_iters && (qid % 37) == 0)
-    printf("q %u it %u grows %lld states %lld total %lld scan %lld plan %lld valid %lld\n", qid, it, prof_grows, prof_states,
-           clock64() - prof_total, prof_scan, prof_plan, prof_valid);
-#endif
-  if (tid == 0) {
-    b.status[qid] = status;
-    b.iters[qid] = it;
-    b.n_start[qid] = nS;
-    b.n_goal[qid] = nG;
-    b.conn_start[qid] = connS;
-    b.conn_goal[qid] = connG;
-    b.overflow[qid] = full ? 1u : 0u;
+};
+
+template <int SP>
+__global__ void __launch_bounds__(RB_THREADS)
+rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, const RrtcDeviceBuffers b,
+                  uint32_t n_queries) {
+  const DeviceWorld &w = *wp;
+  extern __shared__ float4 s_obs[];
+  __shared__ Shared sh_all[RB_WARPS];
+  const ObstacleTables tabs = load_tables(w, s_obs);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (;;) { // persistent warp: next unstarted query
+    uint32_t qid = 0;
+    if (lane == 0)
+      qid = atomicAdd(b.work_counter, 1u);
+    qid = __shfl_sync(0xffffffffu, qid, 0);
+    if (qid >= n_queries)
+      return;
+    Planner<SP> pl(wp, &tabs, p, b, sh_all[threadIdx.x >> 5], lane, qid);
+    pl.begin(b.starts + (size_t)qid * p.dim);
+    bool ended = pl.s.status == ST_INVALID_START;
+    while (!ended && pl.s.it < p.max_iters && !pl.s.full && pl.s.it < (uint32_t)RB_CUT) // :263, ptc = sample budget
+      ended = pl.iteration(nullptr) == IT_END;
+    if (!ended && pl.s.it < p.max_iters && !pl.s.full) {
+      // suspended: the team kernel carries on from here
+      if (lane == 0) {
+        b.resume[qid] = pl.s;
+        b.susp_list[atomicAdd(b.susp_count, 1u)] = qid;
+      }
+    } else {
+      pl.finish(b);
+    }
+    __syncwarp();
   }
-  __syncwarp();
- } // next query
+}
+
+template <int SP>
+__global__ void __launch_bounds__(RB_THREADS)
+rrtc_team_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, const RrtcDeviceBuffers b) {
+  const DeviceWorld &w = *wp;
+  extern __shared__ float4 s_obs[];
+  __shared__ Shared sh_all[RB_WARPS];
+  __shared__ RrtcLoopState team_state;
+  __shared__ int team_flag[RB_WARPS]; // 0: first growTree not trapped, 1: trapped, 2: past the sample budget
+  __shared__ uint32_t team_item;
+  const ObstacleTables tabs = load_tables(w, s_obs);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_susp = *b.susp_count;
+  for (;;) { // persistent block: next suspended query
+    if (threadIdx.x == 0)
+      team_item = atomicAdd(b.team_counter, 1u);
+    __syncthreads();
+    const uint32_t item = team_item;
+    if (item >= n_susp)
+      return;
+    const uint32_t qid = b.susp_list[item];
+    Planner<SP> pl(wp, &tabs, p, b, sh_all[warp], lane, qid);
+    pl.s = b.resume[qid];
+    // a suspended query has drawn its goal sample and has a goal tree: the seeding block of
+    // `iteration` is a no-op from here on
+    for (;;) {
+      if (!(pl.s.it < p.max_iters) || pl.s.full)
+        break;
+      // speculation: warp w takes the first growTree of iteration it + w against the trees as they are
+      const uint32_t my_it = pl.s.it + (uint32_t)warp;
+      typename Planner<SP>::Check r;
+      r.ok = false;
+      int flag = 2;
+      if (my_it < p.max_iters) {
+        const bool growStart = (pl.s.startTree != 0) != ((warp & 1) != 0);
+        pl.draw_sample(my_it);
+        pl.check(growStart ? pl.tS : pl.tG, growStart ? pl.s.nS : pl.s.nG, growStart, r);
+        flag = r.ok ? 0 : 1;
+      }
+      if (lane == 0)
+        team_flag[warp] = flag;
+      __syncthreads();
+      int first = RB_WARPS;
+      for (int k = RB_WARPS - 1; k >= 0; --k)
+        if (team_flag[k] != 1)
+          first = k;
+      // the `first` iterations before it were trapped: they moved the sample counter and the alternation
+      pl.s.it += (uint32_t)first;
+      if (first & 1)
+        pl.s.startTree = pl.s.startTree ? 0u : 1u;
+      const bool run = first < RB_WARPS && team_flag[first] == 0;
+      __syncthreads(); // everyone has read the flags
+      bool ended = false;
+      if (run) {
+        if (warp == first) {
+          ended = pl.iteration(&r) == IT_END;
+          if (lane == 0) {
+            team_state = pl.s;
+            team_flag[0] = ended ? 1 : 0;
+          }
+        }
+        __syncthreads();
+        pl.s = team_state;
+        ended = team_flag[0] != 0;
+        __syncthreads(); // team_flag / team_state are rewritten by the next round
+      }
+      if (ended)
+        break;
+    }
+    if (warp == 0)
+      pl.finish(b);
+    __syncthreads();
+  }
 }
 
 } // namespace
@@ -357,16 +477,23 @@ int rrtc_batch_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const Rrtc
   if (n_queries == 0)
     return PRGPU_OK;
   const size_t smem = obstacle_tables_bytes(w);
-  PRGPU_CUDA_TRY(cudaMemsetAsync(b.work_counter, 0, sizeof(uint32_t), stream));
+  // work_counter, susp_count, team_counter are consecutive words
+  PRGPU_CUDA_TRY(cudaMemsetAsync(b.work_counter, 0, 3 * sizeof(uint32_t), stream));
 #define PRGPU_RB_LAUNCH(SPV)                                                                       \
   do {                                                                                             \
     auto kern = rrtc_batch_kernel<SPV>;                                                            \
+    auto team = rrtc_team_kernel<SPV>;                                                             \
     PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    int per_sm = 0;                                                                                \
+    PRGPU_CUDA_TRY(cudaFuncSetAttribute(team, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int per_sm = 0, per_sm_t = 0;                                                                  \
     PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RB_THREADS, smem)); \
+    PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, team, RB_THREADS, smem)); \
     const unsigned blocks = (unsigned)std::min<uint64_t>((n_queries + RB_WARPS - 1) / RB_WARPS,    \
                                                          (uint64_t)std::max(per_sm, 1) * sm_count); \
     kern<<<blocks, RB_THREADS, smem, stream>>>(w_dev, p, b, n_queries);                            \
+    const unsigned tblocks =                                                                       \
+        (unsigned)std::min<uint64_t>(n_queries, (uint64_t)std::max(per_sm_t, 1) * sm_count);       \
+    team<<<tblocks, RB_THREADS, smem, stream>>>(w_dev, p, b);                                      \
   } while (0)
   if (w.grid_n[0] > 0)
     PRGPU_RB_LAUNCH(0);
