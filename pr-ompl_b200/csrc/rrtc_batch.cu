@@ -34,7 +34,7 @@ namespace {
 constexpr int RB_WARPS = 8;            // queries in flight per block (first kernel) / team size (second)
 constexpr int RB_THREADS = RB_WARPS * 32;
 #ifndef RB_CUT
-#define RB_CUT 96                      // samples after which an unsolved query moves to the team kernel
+#define RB_CUT 256                     // samples after which an unsolved query moves to the team kernel
 #endif
 enum { GS_TRAPPED = 0, GS_ADVANCED = 1, GS_REACHED = 2 };
 enum { ST_INVALID_START = 1, ST_INVALID_GOAL = 2, ST_TIMEOUT = 4, ST_EXACT = 6 }; // PlannerStatus values
