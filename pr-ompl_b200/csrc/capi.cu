@@ -650,6 +650,11 @@ int prgpu_world_destroy(prgpu_world_t *w) {
     if (p)
       cudaFree(p);
   w->timer.destroy();
+  for (cudaEvent_t ev : w->copy_events)
+    if (ev)
+      cudaEventDestroy(ev);
+  if (w->copy_stream)
+    cudaStreamDestroy(w->copy_stream);
   if (w->dev)
     cudaFree(w->dev);
   if (w->stream)
@@ -694,13 +699,56 @@ int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double 
   if ((rc = w->d_a.reserve(bytes)) != PRGPU_OK || (rc = w->d_b.reserve(bytes)) != PRGPU_OK ||
       (rc = w->d_valid.reserve(n)) != PRGPU_OK)
     return rc;
-  PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, from, bytes, cudaMemcpyHostToDevice, w->stream));
-  PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_b.p, to, bytes, cudaMemcpyHostToDevice, w->stream));
-  rc = check_motion_launch(w->host, w->dev, w->d_a.as<double>(), w->d_b.as<double>(), n, resolution, mode,
-                           check_first, w->d_valid.as<uint8_t>(), w->sm_count, w->stream, &w->timer, &w->cm_scratch);
-  if (rc != PRGPU_OK)
+  const uint64_t CH = 1ull << 18; // edges per pipeline stage
+  if (n < 2 * CH) {
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, from, bytes, cudaMemcpyHostToDevice, w->stream));
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_b.p, to, bytes, cudaMemcpyHostToDevice, w->stream));
+    rc = check_motion_launch(w->host, w->dev, w->d_a.as<double>(), w->d_b.as<double>(), n, resolution, mode,
+                             check_first, w->d_valid.as<uint8_t>(), w->sm_count, w->stream, &w->timer, &w->cm_scratch);
+    if (rc != PRGPU_OK)
+      return rc;
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(valid, w->d_valid.p, n, cudaMemcpyDeviceToHost, w->stream));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+    return PRGPU_OK;
+  }
+  // Large batches: the upload of stage c+1 (copy stream) runs under the kernels of stage c.  Each stage's
+  // launch reads one counter back on the compute stream; the copies are already queued by then.
+  if (!w->copy_stream)
+    PRGPU_CUDA_TRY(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+  const uint64_t stages = (n + CH - 1) / CH;
+  if (w->copy_events.size() < stages) {
+    const size_t old_n = w->copy_events.size();
+    w->copy_events.resize(stages, nullptr);
+    for (size_t i = old_n; i < stages; ++i)
+      PRGPU_CUDA_TRY(cudaEventCreateWithFlags(&w->copy_events[i], cudaEventDisableTiming));
+  }
+  const int dof = w->host.dof;
+  auto upload_stage = [&](uint64_t c) -> int {
+    const uint64_t e0 = c * CH, m = std::min<uint64_t>(CH, n - e0);
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.as<double>() + e0 * dof, from + e0 * dof, m * dof * sizeof(double),
+                                   cudaMemcpyHostToDevice, w->copy_stream));
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_b.as<double>() + e0 * dof, to + e0 * dof, m * dof * sizeof(double),
+                                   cudaMemcpyHostToDevice, w->copy_stream));
+    PRGPU_CUDA_TRY(cudaEventRecord(w->copy_events[c], w->copy_stream));
+    return PRGPU_OK;
+  };
+  // the previous call's kernels may still read d_a / d_b on the compute stream only if the caller used the
+  // device entry points concurrently; order the first copy after them anyway
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  if ((rc = upload_stage(0)) != PRGPU_OK)
     return rc;
-  PRGPU_CUDA_TRY(cudaMemcpyAsync(valid, w->d_valid.p, n, cudaMemcpyDeviceToHost, w->stream));
+  for (uint64_t c = 0; c < stages; ++c) {
+    if (c + 1 < stages && (rc = upload_stage(c + 1)) != PRGPU_OK)
+      return rc;
+    const uint64_t e0 = c * CH, m = std::min<uint64_t>(CH, n - e0);
+    PRGPU_CUDA_TRY(cudaStreamWaitEvent(w->stream, w->copy_events[c], 0));
+    rc = check_motion_launch(w->host, w->dev, w->d_a.as<double>() + e0 * dof, w->d_b.as<double>() + e0 * dof, m,
+                             resolution, mode, check_first, w->d_valid.as<uint8_t>() + e0, w->sm_count, w->stream,
+                             c == 0 ? &w->timer : nullptr, &w->cm_scratch);
+    if (rc != PRGPU_OK)
+      return rc;
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(valid + e0, w->d_valid.as<uint8_t>() + e0, m, cudaMemcpyDeviceToHost, w->stream));
+  }
   PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
   return PRGPU_OK;
 }

@@ -1,5 +1,6 @@
 // Handle structs shared by the C-ABI translation units (capi.cu, capi_nnf.cu).
 #pragma once
+#include <vector>
 #include "check_motion.cuh"
 #include "knn.cuh"
 
@@ -62,5 +63,7 @@ struct prgpu_world {
   prgpu::DevBuf d_a, d_b, d_valid, d_pose;
   prgpu::CmScratch cm_scratch;
   prgpu::KernelTimer timer;
+  cudaStream_t copy_stream = nullptr;       // uploads of the staged host-buffer checkMotion
+  std::vector<cudaEvent_t> copy_events;
 };
 
