@@ -313,7 +313,7 @@ def run_ours(args, rank, local_rank, world):
             if record:
                 kernel_ms.append(tree.last_kernel_ms())
 
-        launches_per_step = 8 + (1 if world > 1 else 0)  # (sample, merge, threshold) x 2, collect, select
+        launches_per_step = 7 + (1 if world > 1 else 0)  # pre-sample, merge, threshold, sample scan, sample threshold, scan, select
         units_per_step = Q
         metric, unit = "kNN queries/s", "queries/s"
         algo_bytes = n_local * 56 + Q * 56 + Q * k * 12

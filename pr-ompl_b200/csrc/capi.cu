@@ -146,6 +146,11 @@ int prgpu_knn_destroy(prgpu_knn_t *h) {
     cudaFree(h->ptsf);
   if (h->xmax2)
     cudaFree(h->xmax2);
+  for (cudaEvent_t ev : h->copy_events)
+    if (ev)
+      cudaEventDestroy(ev);
+  if (h->copy_stream)
+    cudaStreamDestroy(h->copy_stream);
   for (void *p : {(void *)h->scratch.cand_dist, (void *)h->scratch.cand_idx, (void *)h->scratch.flags,
                   (void *)h->scratch.fb_q, (void *)h->scratch.fb_dist, (void *)h->scratch.fb_idx,
                   (void *)h->scratch.fb_lo})
@@ -240,10 +245,46 @@ int prgpu_knn_add(prgpu_knn_t *h, const double *pts, uint64_t n) {
   int rc = h->stage.reserve(bytes);
   if (rc != PRGPU_OK)
     return rc;
-  PRGPU_CUDA_TRY(cudaMemcpyAsync(h->stage.p, pts, bytes, cudaMemcpyHostToDevice, h->stream));
-  rc = prgpu_knn_add_device(h, h->stage.as<double>(), n, h->stream);
-  if (rc != PRGPU_OK)
+  const uint64_t CH = 1ull << 20; // nodes per pipeline stage
+  if (n < 2 * CH) {
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(h->stage.p, pts, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = prgpu_knn_add_device(h, h->stage.as<double>(), n, h->stream);
+    if (rc != PRGPU_OK)
+      return rc;
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PRGPU_OK;
+  }
+  // Bulk loads: the stages are copied on a second stream and transposed (fp64 SoA + the two mirrors) as
+  // they land, so only the last stage's transpose is exposed after the upload.
+  if (h->n + n >= 0xFFFFFFFFull)
+    return fail(PRGPU_ELIMIT, "knn_add: more than 2^32-2 points");
+  if ((rc = knn_reserve(h, h->n + n)) != PRGPU_OK)
     return rc;
+  if (!h->copy_stream)
+    PRGPU_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  const uint64_t stages = (n + CH - 1) / CH;
+  if (h->copy_events.size() < stages) {
+    const size_t old_n = h->copy_events.size();
+    h->copy_events.resize(stages, nullptr);
+    for (size_t i = old_n; i < stages; ++i)
+      PRGPU_CUDA_TRY(cudaEventCreateWithFlags(&h->copy_events[i], cudaEventDisableTiming));
+  }
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream)); // earlier users of the staging buffer
+  for (uint64_t c = 0; c < stages; ++c) {
+    const uint64_t i0 = c * CH, m = std::min<uint64_t>(CH, n - i0);
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(h->stage.as<double>() + i0 * h->dim, pts + i0 * h->dim, m * h->dim * sizeof(double),
+                                   cudaMemcpyHostToDevice, h->copy_stream));
+    PRGPU_CUDA_TRY(cudaEventRecord(h->copy_events[c], h->copy_stream));
+  }
+  for (uint64_t c = 0; c < stages; ++c) {
+    const uint64_t i0 = c * CH, m = std::min<uint64_t>(CH, n - i0);
+    PRGPU_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->copy_events[c], 0));
+    rc = knn_transpose_append(h->dim, h->stage.as<double>() + i0 * h->dim, m, h->pts, h->ptsf, h->xmax2, h->stride,
+                              h->n + i0, h->stream);
+    if (rc != PRGPU_OK)
+      return rc;
+  }
+  h->n += n;
   PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PRGPU_OK;
 }

@@ -52,6 +52,8 @@ struct prgpu_knn {
   prgpu::KnnScratch scratch;
   prgpu::KernelTimer timer;
   prgpu::DevBuf stage, d_q, d_lo, d_idx, d_dist;
+  cudaStream_t copy_stream = nullptr;       // uploads of bulk prgpu_knn_add calls
+  std::vector<cudaEvent_t> copy_events;
 };
 
 struct prgpu_world {

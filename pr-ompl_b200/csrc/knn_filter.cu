@@ -31,8 +31,10 @@ constexpr int FT_TILE = 128;     // nodes per tile (32 bytes each)
 constexpr int FT_THREADS = 128;  // queries per block
 
 
-// Pass 1 (run twice: a 32x coarser pre-sample, then the sample proper seeded with the pre-sample's
-// threshold): the KP smallest keys of every query over a strided sub-sample of the tree.  One thread =
+// Pass 1, fp32: the KP smallest keys of every query over a strided sub-sample of the tree (the 32x
+// coarser pre-sample of every call, and the sample proper of trees below 4M nodes, seeded with the
+// pre-sample's threshold; larger trees take their sample on the tensor cores, see
+// knn_sample_threshold_kernel).  One thread =
 // one query; the keys live in registers as a sorted array updated by a branch-free insertion network
 // (new[e] = min(old[e], max(old[e-1], x))), entered only when some lane of the warp has a key below
 // its current KP-th -- no per-lane divergent code, no shared-memory lists.  Node chunks (blockIdx.y)
@@ -167,7 +169,7 @@ template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS, CT_MINB)
 knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f, uint32_t n,
                    const double *__restrict__ queries, uint32_t nq, const uint32_t *__restrict__ lo,
-                   const float *__restrict__ thresh, uint32_t tiles_per_chunk, uint32_t cap,
+                   const float *__restrict__ thresh, uint32_t tile_stride, uint32_t tiles_per_chunk, uint32_t cap,
                    uint32_t *__restrict__ cand_count, uint32_t *__restrict__ cand_idx, float *__restrict__ cand_key) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *recs = reinterpret_cast<float *>(smem_raw);                        // [CT_STAGES][CT_TILE][8]   TF32 records
@@ -212,11 +214,12 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
       atomicMin(&s_lo_min, lo[r]);
     __syncthreads();
   }
-  const uint32_t ntiles = (n + CT_TILE - 1) / CT_TILE;
+  // the scan visits every tile_stride-th tile (1: the whole tree; > 1: the sample pass)
+  const uint32_t ntiles = ((n + CT_TILE - 1) / CT_TILE + tile_stride - 1) / tile_stride;
   uint32_t t0 = blockIdx.y * tiles_per_chunk;
   const uint32_t t1 = min(t0 + tiles_per_chunk, ntiles);
   if (s_lo_min != 0xFFFFFFFFu)
-    t0 = max(t0, s_lo_min / CT_TILE);
+    t0 = max(t0, s_lo_min / CT_TILE / tile_stride);
   const uint32_t ntl = t1 > t0 ? t1 - t0 : 0;
   // A ring of CT_STAGES tiles with full/empty barriers and no block-wide barrier: the warps of a block
   // drift up to CT_STAGES - 1 tiles apart (the rare emit paths make their pace uneven).
@@ -225,8 +228,9 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
     if (use > 0)
       mbar_wait(&empty[slot], (use - 1) & 1);
     mbar_expect_tx(&full[slot], CT_TILE * 40);
-    bulk_g2s(recs + slot * CT_TILE * 8, ptst + (size_t)(t0 + i) * CT_TILE * 8, CT_TILE * 32, &full[slot]);
-    bulk_g2s(n2s + slot * CT_TILE * 2, n2f + (size_t)(t0 + i) * CT_TILE * 2, CT_TILE * 8, &full[slot]);
+    const size_t tile = (size_t)(t0 + i) * tile_stride;
+    bulk_g2s(recs + slot * CT_TILE * 8, ptst + tile * CT_TILE * 8, CT_TILE * 32, &full[slot]);
+    bulk_g2s(n2s + slot * CT_TILE * 2, n2f + tile * CT_TILE * 2, CT_TILE * 8, &full[slot]);
   };
   auto emit = [&](uint32_t row, uint32_t gi, float dv) {
     if (gi < n && row < nq && (!lo || gi >= lo[row])) {
@@ -247,7 +251,7 @@ knn_collect_kernel(const float *__restrict__ ptst, const float *__restrict__ n2f
     mbar_wait(&full[slot], (i / CT_STAGES) & 1);
     const float2 *R = reinterpret_cast<const float2 *>(recs + slot * CT_TILE * 8) + g * 4 + t4;
     const float4 *N2 = reinterpret_cast<const float4 *>(n2s + slot * CT_TILE * 2) + t4;
-    const uint32_t base = (t0 + i) * CT_TILE;
+    const uint32_t base = (t0 + i) * tile_stride * CT_TILE;
     auto load_mma = [&](int nt, float (&d)[CT_MT][4]) {
       const float2 b = R[nt * 32];  // node nt*8+g, slots (t, t+4)
       const float4 c = N2[nt * 4];  // |x|^2 of nodes nt*8+2t, nt*8+2t+1 (the lane's two output columns), twice
@@ -311,6 +315,53 @@ __global__ void knn_threshold_kernel(const double *__restrict__ cand_key, const 
   thresh[q] = tf32_round_up(t); // the scan multiplies it on the tensor cores: must be a TF32 number
   if (counts)
     counts[q] = 0;
+}
+
+// Sample pass on the tensor cores, second half: the scan over the sample tiles (knn_collect_kernel with a
+// tile stride and the pre-sample's coarse threshold T_c) left D = key - T_c of the sample nodes below T_c
+// in the candidate buffers; one warp per query takes the kp-th smallest of them: T_q = T_c + D_kp.
+// Any value is a legal threshold (exactness never depends on it): with fewer than kp entries T_c stays.
+__global__ void knn_sample_threshold_kernel(uint32_t nq, int kp, uint32_t cap, uint32_t *__restrict__ counts,
+                                            const float *__restrict__ ckey, float *__restrict__ thresh) {
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq)
+    return;
+  const uint32_t cnt = min(counts[q], cap);
+  const float *v = ckey + (size_t)q * cap;
+  float pv = -CUDART_INF_F; // (value, position) of the previous round's pick
+  uint32_t pc = 0;
+  bool first = true;
+  for (int r = 0; r < kp && (uint32_t)r < cnt; ++r) {
+    float bv = CUDART_INF_F;
+    uint32_t bc = 0xFFFFFFFFu;
+    for (uint32_t c = lane; c < cnt; c += 32) {
+      const float x = v[c];
+      const bool after = first || x > pv || (x == pv && c > pc);
+      if (after && (x < bv || (x == bv && c < bc))) {
+        bv = x;
+        bc = c;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const uint32_t oc = __shfl_xor_sync(0xffffffffu, bc, off);
+      if (ov < bv || (ov == bv && oc < bc)) {
+        bv = ov;
+        bc = oc;
+      }
+    }
+    pv = bv;
+    pc = bc;
+    first = false;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (cnt >= (uint32_t)kp && pv < CUDART_INF_F && pv > -CUDART_INF_F)
+      thresh[q] = tf32_round_up(thresh[q] + pv);
+    counts[q] = 0;
+  }
 }
 
 // Pass 3: one block per query, three levels.
@@ -627,46 +678,61 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
     PRGPU_CUDA_TRY(cudaGetLastError());
     return PRGPU_OK;
   };
-  // pre-sample, 32x coarser: its kp-th key seeds the sample pass.  The bound is kept in `coarse_buf`, which
-  // aliases `counts`: the counters are zeroed by the last threshold kernel, after the sample pass has
-  // read its seeds.
-  float *coarse_buf = reinterpret_cast<float *>(counts);
-  rc = sample_pass(sample_stride * 32, nullptr, coarse_buf, nullptr);
-  if (rc != PRGPU_OK)
-    return rc;
-  rc = sample_pass(sample_stride, coarse_buf, thresh, counts);
+  // pre-sample (fp32 FMA, every (32 * stride)-th 128-node tile -- a subset of the sample below): its kp-th
+  // smallest key T_c admits about 32 * kp nodes of the sample
+  rc = sample_pass(sample_stride * 32, nullptr, thresh, counts);
   if (rc != PRGPU_OK)
     return rc;
 
-  // ---- pass 2: full scan collecting every node at or below the threshold ----
+  // ---- the scan kernel, used twice: over every sample_stride-th tile with T_c (sample pass), then over
+  //      the whole tree with T_q (pass 2) ----
   const size_t smem2 = (size_t)CT_STAGES * CT_TILE * 40 + 2 * CT_STAGES * sizeof(uint64_t);
   auto coll = knn_collect_kernel<DIM>;
   int per_sm = 0;
   PRGPU_CUDA_TRY(cudaFuncSetAttribute(coll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coll, FT_THREADS, smem2));
   per_sm = per_sm > 0 ? per_sm : 1;
-  const uint32_t ntiles2 = (t.n + CT_TILE - 1) / CT_TILE;
-  uint32_t chunks = (uint32_t)(per_sm * sm_count) / qblocks;
-  chunks = chunks < 1 ? 1 : chunks;
-  // many short blocks instead of one wave of long ones: the blocks resident on an SM do not advance at
-  // the same rate, and a one-wave grid ran its last third at 4.4 of 6 warps per scheduler (ncu r01d)
-  const uint32_t one_wave = chunks;
-  chunks *= CT_WAVES;
-  // ... but a block's prologue (64 queries' A fragments per warp) has to be paid off: at least
-  // CT_MIN_TILES tiles per block while that still leaves a full wave
-  if (chunks > ntiles2 / CT_MIN_TILES)
-    chunks = ntiles2 / CT_MIN_TILES > one_wave ? ntiles2 / CT_MIN_TILES : one_wave;
-  if (chunks > ntiles2)
-    chunks = ntiles2;
-  const uint32_t tiles_per_chunk = (ntiles2 + chunks - 1) / chunks;
-  chunks = (ntiles2 + tiles_per_chunk - 1) / tiles_per_chunk;
-  if (timer)
-    timer->begin(stream);
-  coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf + 8 * t.stride, t.ptsf + 16 * t.stride, t.n, queries,
-                                                           nq, lo, thresh, tiles_per_chunk, cap, counts, cidx, ckey);
-  if (timer)
-    timer->end(stream);
-  PRGPU_CUDA_TRY(cudaGetLastError());
+  auto scan = [&](uint32_t tile_stride, KernelTimer *tm) -> int {
+    const uint32_t ntiles2 = ((t.n + CT_TILE - 1) / CT_TILE + tile_stride - 1) / tile_stride;
+    uint32_t chunks = (uint32_t)(per_sm * sm_count) / qblocks;
+    chunks = chunks < 1 ? 1 : chunks;
+    // many short blocks instead of one wave of long ones: the blocks resident on an SM do not advance at
+    // the same rate, and a one-wave grid ran its last third at 4.4 of 6 warps per scheduler (ncu r01d)
+    const uint32_t one_wave = chunks;
+    chunks *= CT_WAVES;
+    // ... but a block's prologue (64 queries' A fragments per warp) has to be paid off: at least
+    // CT_MIN_TILES tiles per block while that still leaves a full wave
+    if (chunks > ntiles2 / CT_MIN_TILES)
+      chunks = ntiles2 / CT_MIN_TILES > one_wave ? ntiles2 / CT_MIN_TILES : one_wave;
+    if (chunks > ntiles2)
+      chunks = ntiles2;
+    const uint32_t tiles_per_chunk = (ntiles2 + chunks - 1) / chunks;
+    chunks = (ntiles2 + tiles_per_chunk - 1) / tiles_per_chunk;
+    if (tm)
+      tm->begin(stream);
+    coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf + 8 * t.stride, t.ptsf + 16 * t.stride, t.n, queries,
+                                                             nq, lo, thresh, tile_stride, tiles_per_chunk, cap, counts,
+                                                             cidx, ckey);
+    if (tm)
+      tm->end(stream);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    return PRGPU_OK;
+  };
+  if (t.n >= (1u << 22)) {
+    // sample pass on the tensor cores: D = key - T_c of the sample nodes below T_c, then
+    // T_q = T_c + (kp-th smallest D)
+    if ((rc = scan(sample_stride, nullptr)) != PRGPU_OK)
+      return rc;
+    knn_sample_threshold_kernel<<<(nq * 32 + 255) / 256, 256, 0, stream>>>(nq, kp, cap, counts, ckey, thresh);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+  } else {
+    // small trees: the fp32 sampler seeded with T_c is cheaper than a second strided scan launch
+    if ((rc = sample_pass(sample_stride, thresh, thresh, counts)) != PRGPU_OK)
+      return rc;
+  }
+  // ---- pass 2: full scan collecting every node below the threshold ----
+  if ((rc = scan(1, timer)) != PRGPU_OK)
+    return rc;
 
   // ---- pass 3: exact re-rank of the candidates + proof ----
   const size_t smem3 = (size_t)cap * 8;

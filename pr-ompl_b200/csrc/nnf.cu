@@ -406,59 +406,83 @@ __device__ __forceinline__ double band_get(const NnfBandDev &g, uint32_t r, uint
   return i < m.band_w ? g.Bc[m.col_off + i] : NNF_INF;
 }
 
+// One warp walks the path goal -> start.  A step has to find, in the fixed order of the full-table walk
+// -- (r-1,s), then per predecessor p in list order (r,p), (r-1,p) -- the first cell whose value explains
+// the current one.  (r-1,s) is tried alone (most steps stay on the vertex); otherwise the predecessors'
+// cells are independent loads: lane 1+2j / 2+2j take the two cells of predecessor j, a ballot picks the
+// lowest lane that matches (chunks of 15 predecessors keep the order), so such a step costs one dependent
+// round trip instead of one per rejected candidate.
 __global__ void nnf_band_backtrack_kernel(const NnfBandDev g, uint32_t *__restrict__ out_path, uint32_t cap_pairs,
                                           uint32_t *__restrict__ out_n, double *__restrict__ out_cost) {
-  if (blockIdx.x != 0 || threadIdx.x != 0)
+  if (blockIdx.x != 0 || threadIdx.x >= 32)
     return;
+  const int lane = threadIdx.x;
   uint32_t r = (uint32_t)g.R - 1, s = g.goal_pos, n = 0;
-  const double goal = band_get(g, r, s);
-  *out_cost = goal;
-  if (goal == NNF_INF) {
-    *out_n = 0;
+  double target = band_get(g, r, s);
+  if (lane == 0)
+    *out_cost = target;
+  if (target == NNF_INF) {
+    if (lane == 0)
+      *out_n = 0;
     return;
   }
   while (true) {
-    if (n < cap_pairs) {
+    if (lane == 0 && n < cap_pairs) {
       out_path[2 * n] = r;
       out_path[2 * n + 1] = s;
     }
     ++n;
     if (r == 0 && s == g.start_pos)
       break;
-    const double target = band_get(g, r, s);
     const double fv = task_distance(g.pref + 3 * (size_t)r, g.pnn + 3 * (size_t)s);
+    const NnfVertexMeta m = g.meta[s];
     bool found = false;
     uint32_t br = 0, bs = 0;
-    // same fixed order as the full-table walk: (r-1,s), then per predecessor (r,p), (r-1,p)
+    double bval = 0.0;
+    // (r-1, s) first, on its own: most steps stay on the vertex, and its value sits next to the current one
     if (r > 0) {
-      const double bu = band_get(g, r - 1, s);
+      const uint32_t i = r - 1 - m.band_lo;
+      const double bu = i < m.band_w ? g.Bc[m.col_off + i] : NNF_INF;
       if (bu != NNF_INF && fmax(bu, fv) == target) {
         found = true;
         br = r - 1;
         bs = s;
+        bval = bu;
       }
     }
-    const NnfVertexMeta m = g.meta[s];
-    for (uint32_t e = m.pred_begin; !found && e < m.pred_end; ++e) {
-      const NnfEdgeRec rec = g.edge[e];
-      if (rec.band_w_blocked & 0x80000000u)
-        continue;
-      const uint32_t pw = rec.band_w_blocked;
-      const uint32_t i0 = r - rec.band_lo;
-      const double b0 = i0 < pw ? g.Bc[rec.col_off + i0] : NNF_INF;
-      if (b0 != NNF_INF && fmax(b0, fv) == target) {
-        found = true;
-        br = r;
-        bs = g.pred_pos[e];
-        break;
+    for (uint32_t e0 = m.pred_begin; !found && e0 < m.pred_end; e0 += 15) {
+      // lanes 1..30: predecessors e0 .. e0+14, two cells each
+      double v = NNF_INF;
+      uint32_t cr = 0, cs = 0;
+      if (lane >= 1 && lane <= 30) {
+        const uint32_t e = e0 + (uint32_t)(lane - 1) / 2u;
+        if (e < m.pred_end) {
+          const NnfEdgeRec rec = g.edge[e];
+          if (!(rec.band_w_blocked & 0x80000000u)) {
+            const uint32_t pw = rec.band_w_blocked;
+            const uint32_t i0 = r - rec.band_lo;
+            if ((lane - 1) & 1) { // (r-1, p)
+              const uint32_t i1 = i0 - 1u;
+              if (r > 0 && i1 < pw)
+                v = g.Bc[rec.col_off + i1];
+              cr = r - 1;
+            } else { // (r, p)
+              if (i0 < pw)
+                v = g.Bc[rec.col_off + i0];
+              cr = r;
+            }
+            cs = g.pred_pos[e];
+          }
+        }
       }
-      const uint32_t i1 = i0 - 1u;
-      const double b1 = (r > 0 && i1 < pw) ? g.Bc[rec.col_off + i1] : NNF_INF;
-      if (b1 != NNF_INF && fmax(b1, fv) == target) {
+      const bool hit = v != NNF_INF && fmax(v, fv) == target;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        const int src = __ffs(bal) - 1;
+        br = __shfl_sync(0xffffffffu, cr, src);
+        bs = __shfl_sync(0xffffffffu, cs, src);
+        bval = __shfl_sync(0xffffffffu, v, src);
         found = true;
-        br = r - 1;
-        bs = g.pred_pos[e];
-        break;
       }
     }
     if (!found) { // cannot happen on a consistent table
@@ -467,8 +491,10 @@ __global__ void nnf_band_backtrack_kernel(const NnfBandDev g, uint32_t *__restri
     }
     r = br;
     s = bs;
+    target = bval;
   }
-  *out_n = n;
+  if (lane == 0)
+    *out_n = n;
 }
 
 } // namespace

@@ -1,4 +1,5 @@
-"""T1 parity: the device-resident batched RRTConnect (one block per query) must build, node for
+"""T1 parity: the device-resident batched RRTConnect (a warp per query, then speculative 8-warp teams for
+the queries still unsolved after 256 samples) must build, node for
 node, the trees of the reference planner: same GrowState sequence, hence same iteration count,
 parent arrays, states (bit for bit) and solution path.  Checked against the oracle port on
 seeded problems and against golden vectors recorded from the reference's own RRTConnect.cpp."""
@@ -43,6 +44,23 @@ def test_batch_matches_oracle(P, O, synth, gpu_world, oracle_world, ext, rng):
     for qi in range(n):
         ref = oracle_world.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, rng=rng, ext=EXT_CODE[ext], seed=5,
                                       query=100 + qi, max_iters=300, impl="port")
+        _compare(rb, summ, qi, ref)
+
+
+@pytest.mark.parametrize("ext", ["ext-con", "con-con"])
+def test_long_budget_goes_through_the_team_kernel(P, O, synth, gpu_world, oracle_world, ext):
+    # 1000 samples: the queries that are not solved by sample 256 are suspended and finished by the team kernel
+    # (speculative evaluation of consecutive samples); iteration counts, trees and paths must not change
+    n = 40
+    starts, goals = _problems(synth, oracle_world, n, seed=77)
+    rb = P.RrtcBatch(gpu_world, n, -np.pi, np.pi, extension_type=ext, seed=21, query_id_base=7,
+                     max_iters=1000, max_nodes=4096)
+    rb.run(starts, goals)
+    summ = rb.summary()
+    assert (summ["iterations"] > 256).sum() >= 2          # the team path is exercised
+    for qi in range(n):
+        ref = oracle_world.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=EXT_CODE[ext], seed=21,
+                                      query=7 + qi, max_iters=1000, impl="port")
         _compare(rb, summ, qi, ref)
 
 
