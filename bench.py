@@ -208,7 +208,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def plan_problems(synth, world, n, seed=4):
@@ -239,6 +239,8 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        # NCCL prints its version banner on stdout; stdout is reserved for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream().cuda_stream
     hbm_peak, peak_src = peaks()
@@ -596,7 +598,7 @@ def run_ours(args, rank, local_rank, world):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, synth)
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def cpu_baseline(args, synth):
@@ -725,19 +727,39 @@ def run_nnf(args, rank, local_rank, world):
                                           f"{len(ref) * g.n_vertices / (len(refs) * o['n_vertices']):.0f}x fewer than the GPU run), "
                                           f"{o['lazy_iters']} LazySP iterations of the oracle port incl. its setup; the "
                                           f"full-size CPU run does not finish in minutes"}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_JSON_OUT = None
+
+
+def reserve_stdout():
+    """stdout carries exactly one JSON line: whatever libraries print (the NCCL version banner, for one)
+    goes to stderr, the line is written to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
     args = parse()
+    reserve_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "nnf":
         if args.impl == "reference":
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "NNF reference arm: the literal frechet/ sources "
-                                  "need Boost.Graph and Eigen (absent); see cpu_baseline of --workload nnf"}))
+                emit_json({"impl": "reference", "unavailable": "NNF reference arm: the literal frechet/ sources "
+                                  "need Boost.Graph and Eigen (absent); see cpu_baseline of --workload nnf"})
             return
         run_nnf(args, rank, local_rank, world)
         return
