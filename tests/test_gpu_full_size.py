@@ -30,6 +30,16 @@ def test_knn_sweep_full_size(P, O, synth):
         rows = np.arange(0, nq, 37)
         d = np.sqrt(((pts[fi[rows, 0]] - q[rows]) ** 2).sum(1))
         assert np.allclose(d, fd[rows, 0], rtol=1e-13)
+    # suffix masks (NNF's "strictly deeper layers") on the large-tree path: tensor-core sample pass + scan
+    lo = np.sort(np.random.default_rng(5).integers(0, n - 50_000, nq)).astype(np.uint32)
+    lo[-8:] = n - np.arange(1, 9, dtype=np.uint32) * 3      # almost empty suffixes: fewer than k eligible nodes
+    t.set_search_mode(False)
+    fi, fd = t.nearest_k(q, 5, lo=lo)
+    t.set_search_mode(True)
+    ei, ed = t.nearest_k(q, 5, lo=lo)
+    assert np.array_equal(fi, ei) and np.array_equal(fd, ed)
+    valid = fi != 0xFFFFFFFF
+    assert np.all(fi[valid] >= np.broadcast_to(lo[:, None], fi.shape)[valid])
     t.close()
     torch.cuda.empty_cache()
 
