@@ -40,11 +40,132 @@ enum { GS_TRAPPED = 0, GS_ADVANCED = 1, GS_REACHED = 2 };
 enum { ST_INVALID_START = 1, ST_INVALID_GOAL = 2, ST_TIMEOUT = 4, ST_EXACT = 6 }; // PlannerStatus values
 enum { IT_CONTINUE = 0, IT_END = 1 };
 
+// dynamic shared memory: the obstacle tables, then per warp the centres and the work list of a validity round
+__host__ __device__ __forceinline__ size_t warp_scratch_offset(const DeviceWorld &w) {
+  return (obstacle_tables_bytes(w) + 15) & ~(size_t)15;
+}
+__host__ __device__ __forceinline__ size_t warp_scratch_bytes(const DeviceWorld &w) {
+  return ((size_t)32 * w.S * (3 * sizeof(float) + sizeof(uint16_t)) + 15) & ~(size_t)15;
+}
+
 struct Shared { // per warp
   double rstate[WORLD_MAX_DOF];
   double xstate[WORLD_MAX_DOF];
   double near[WORLD_MAX_DOF];
 };
+
+// the tested set of one edge (DiscreteMotionValidator: `to` first, then `from` if asked, then the interior)
+struct EdgeStates {
+  const double *from, *to;
+  uint32_t nd, extra, rounds, rd;
+  __device__ __forceinline__ void state(uint32_t pt, double *q) const {
+    if (pt == 0) {
+#pragma unroll
+      for (int k = 0; k < WORLD_MAX_DOF; ++k)
+        q[k] = to[k];
+    } else if (pt <= extra) {
+#pragma unroll
+      for (int k = 0; k < WORLD_MAX_DOF; ++k)
+        q[k] = from[k];
+    } else {
+      const double t = (double)(pt - extra) / (double)nd;
+#pragma unroll
+      for (int k = 0; k < WORLD_MAX_DOF; ++k)
+        q[k] = lerp_exact(from[k], to[k], t);
+    }
+  }
+  // state held by lane `st` in round `rd`
+  __device__ __forceinline__ void get(uint32_t st, double *q) const { state(rd + st * rounds, q); }
+};
+
+// One validity round of the warp: lane s holds state s (`have`, `q`).  A state test is a latency chain
+// (FK, then 16 field loads, then obstacle lists for the spheres the field cannot certify) and only ~20
+// lanes have a state, so the round is split by KIND of work instead of by state:
+//   A  each lane runs the fp32 FK chain of its state and leaves the sphere centres in shared memory;
+//   B  the (state, sphere) pairs are dealt to all 32 lanes, four field loads in flight per lane;
+//   C  the uncertified pairs are dealt to all lanes for the obstacle lists, a vote after every 32.
+// `es->get(s, q)` regenerates state s (the fp64 verdict of a thin-band pair needs it).  Requires the
+// clearance field; identical verdicts to state_valid_grid by construction (same functions).
+static __device__ __noinline__ bool round_valid(const DeviceWorld *wp, const ObstacleTables *tabs, float *cen, uint16_t *work,
+                                              int tid, bool have, const double *q, const EdgeStates *es) {
+  const DeviceWorld &w = *wp;
+  const ArmTableF32 &arm = *tabs->arm;
+  const int S = arm.link_first[w.dof + 1];
+  const unsigned hm = __ballot_sync(0xffffffffu, have);
+  const int nst = __popc(hm); // the states sit in lanes 0 .. nst-1
+  if (have) {
+    FrameF32 f;
+    f.reset();
+    for (int i = 0; i <= w.dof; ++i) {
+      if (i > 0)
+        f.advance(arm, q, i);
+      for (int j = arm.link_first[i]; j < arm.link_first[i + 1]; ++j) {
+        float cx, cy, cz;
+        f.centre(arm.sphere[j], cx, cy, cz);
+        float *c = cen + ((size_t)tid * S + j) * 3;
+        c[0] = cx;
+        c[1] = cy;
+        c[2] = cz;
+      }
+    }
+  }
+  __syncwarp();
+  const int nitems = nst * S;
+  const int dnx = w.df_n[0], dny = w.df_n[1], dnz = w.df_n[2];
+  const float dox = w.df_org[0], doy = w.df_org[1], doz = w.df_org[2], dinv = w.df_inv;
+  int nwork = 0;
+  const bool pow2 = (S & (S - 1)) == 0;
+  const int sh = 31 - __clz(S);
+  const float dout = w.df_out;
+  const float *df = w.df;
+  constexpr int RV_U = 8; // field loads in flight per lane
+  for (int base = 0; base < nitems; base += 32 * RV_U) {
+    float dv[RV_U];
+#pragma unroll
+    for (int u = 0; u < RV_U; ++u) {
+      const int it = base + u * 32 + tid;
+      dv[u] = CUDART_INF_F;
+      if (it < nitems) {
+        const float *c = cen + (size_t)it * 3;
+        const float fx = (c[0] - dox) * dinv, fy = (c[1] - doy) * dinv, fz = (c[2] - doz) * dinv;
+        const bool in = fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)dnx && fy < (float)dny && fz < (float)dnz;
+        // (outside the field's box, or NaN: the margin)
+        const float d = in ? __ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx) : dout;
+        dv[u] = d - arm.sphere[pow2 ? (it & (S - 1)) : (it % S)].w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RV_U; ++u) {
+      const int it = base + u * 32 + tid;
+      const bool unc = it < nitems && !(dv[u] > 0.f);
+      const unsigned bal = __ballot_sync(0xffffffffu, unc);
+      if (unc)
+        work[nwork + __popc(bal & ((1u << tid) - 1u))] = (uint16_t)it;
+      nwork += __popc(bal);
+    }
+  }
+  __syncwarp();
+  for (int b0 = 0; b0 < nwork; b0 += 32) {
+    bool bad = false;
+    if (b0 + tid < nwork) {
+      const int it = work[b0 + tid];
+      const int st = pow2 ? (it >> sh) : (it / S), j = pow2 ? (it & (S - 1)) : (it % S);
+      double qs[WORLD_MAX_DOF];
+      const float *c = cen + (size_t)it * 3;
+      bad = !grid_sphere_free(
+          w, *tabs,
+          [&]() {
+            es->get((uint32_t)st, qs); // only a thin-band pair gets here
+            return (const double *)qs;
+          },
+          j, c[0], c[1], c[2]);
+    }
+    if (__any_sync(0xffffffffu, bad))
+      return false;
+  }
+  return true;
+}
+
 
 // One query as seen by one warp.  Every member is warp-uniform.
 template <int SP>
@@ -59,6 +180,8 @@ struct Planner {
   double *tS, *tG;
   int32_t *pS, *pG;
   const double *goal;
+  float *cen;     // per warp: sphere centres of the states of a validity round, [32][S][3]
+  uint16_t *work; // per warp: (state, sphere slot) items the clearance field could not certify, [32 * S]
   RrtcLoopState s;
 
   struct Check { // result of the first half of growTree
@@ -68,8 +191,11 @@ struct Planner {
   };
 
   __device__ __forceinline__ Planner(const DeviceWorld *wp_, const ObstacleTables *tabs_, const RrtcDeviceParams &p_,
-                                     const RrtcDeviceBuffers &b, Shared &sh_, int lane, uint32_t qid_)
+                                     const RrtcDeviceBuffers &b, Shared &sh_, int lane, uint32_t qid_,
+                                     unsigned char *warp_scratch)
       : wp(wp_), tabs(tabs_), p(p_), sh(sh_), tid(lane), dim(p_.dim), qid(qid_) {
+    cen = reinterpret_cast<float *>(warp_scratch);
+    work = reinterpret_cast<uint16_t *>(cen + 32 * wp_->S * 3);
     tS = b.start_states + (size_t)qid * p.max_nodes * dim;
     tG = b.goal_states + (size_t)qid * p.max_nodes * dim;
     pS = b.start_parent + (size_t)qid * p.max_nodes;
@@ -208,28 +334,27 @@ struct Planner {
     const uint32_t np = 1u + (nd >= 2 ? nd - 1 : 0u) + extra;
     const uint32_t rounds = (np + 31) / 32;
     r.ok = true;
+    EdgeStates es;
+    es.from = from;
+    es.to = to;
+    es.nd = nd;
+    es.extra = extra;
+    es.rounds = rounds;
     for (uint32_t rd = 0; rd < rounds; ++rd) {
       const uint32_t pt = rd + (uint32_t)tid * rounds;
-      bool good = true;
-      if (pt < np) {
-        double q[WORLD_MAX_DOF];
-        if (pt == 0) {
-#pragma unroll
-          for (int k = 0; k < WORLD_MAX_DOF; ++k)
-            q[k] = to[k];
-        } else if (pt <= extra) {
-#pragma unroll
-          for (int k = 0; k < WORLD_MAX_DOF; ++k)
-            q[k] = from[k];
-        } else {
-          const double t = (double)(pt - extra) / (double)nd;
-#pragma unroll
-          for (int k = 0; k < WORLD_MAX_DOF; ++k)
-            q[k] = lerp_exact(from[k], to[k], t);
-        }
-        good = state_valid_call<SP>(wp, tabs, q);
+      double q[WORLD_MAX_DOF];
+      const bool have = pt < np;
+      es.rd = rd;
+      if (have)
+        es.state(pt, q);
+      bool all_good;
+      if (SP == 0 && wp->df) {
+        all_good = round_valid(wp, tabs, cen, work, tid, have, q, &es);
+      } else {
+        const bool good = have ? state_valid_call<SP>(wp, tabs, q) : true;
+        all_good = !__any_sync(0xffffffffu, !good);
       }
-      if (__any_sync(0xffffffffu, !good)) {
+      if (!all_good) {
         r.ok = false;
         break;
       }
@@ -377,7 +502,9 @@ rrtc_batch_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, 
     qid = __shfl_sync(0xffffffffu, qid, 0);
     if (qid >= n_queries)
       return;
-    Planner<SP> pl(wp, &tabs, p, b, sh_all[threadIdx.x >> 5], lane, qid);
+    Planner<SP> pl(wp, &tabs, p, b, sh_all[threadIdx.x >> 5], lane, qid,
+                   reinterpret_cast<unsigned char *>(s_obs) + warp_scratch_offset(w) +
+                       (size_t)(threadIdx.x >> 5) * warp_scratch_bytes(w));
     pl.begin(b.starts + (size_t)qid * p.dim);
     bool ended = pl.s.status == ST_INVALID_START;
     while (!ended && pl.s.it < p.max_iters && !pl.s.full && pl.s.it < (uint32_t)RB_CUT) // :263, ptc = sample budget
@@ -416,7 +543,8 @@ rrtc_team_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, c
     if (item >= n_susp)
       return;
     const uint32_t qid = b.susp_list[item];
-    Planner<SP> pl(wp, &tabs, p, b, sh_all[warp], lane, qid);
+    Planner<SP> pl(wp, &tabs, p, b, sh_all[warp], lane, qid,
+                   reinterpret_cast<unsigned char *>(s_obs) + warp_scratch_offset(w) + (size_t)warp * warp_scratch_bytes(w));
     pl.s = b.resume[qid];
     // a suspended query has drawn its goal sample and has a goal tree: the seeding block of
     // `iteration` is a no-op from here on
@@ -476,7 +604,7 @@ int rrtc_batch_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const Rrtc
                       const RrtcDeviceBuffers &b, uint32_t n_queries, int sm_count, cudaStream_t stream) {
   if (n_queries == 0)
     return PRGPU_OK;
-  const size_t smem = obstacle_tables_bytes(w);
+  const size_t smem = warp_scratch_offset(w) + RB_WARPS * warp_scratch_bytes(w);
   // work_counter, susp_count, team_counter are consecutive words
   PRGPU_CUDA_TRY(cudaMemsetAsync(b.work_counter, 0, 3 * sizeof(uint32_t), stream));
 #define PRGPU_RB_LAUNCH(SPV)                                                                       \

@@ -435,6 +435,9 @@ struct FrameF32 {
   __device__ __forceinline__ void advance(const ArmTableF32 &arm, const double *q, int i) {
     float st, ct;
     sincosf((float)q[i - 1] + arm.dh[i - 1][4], &st, &ct);
+    advance(arm, i, st, ct);
+  }
+  __device__ __forceinline__ void advance(const ArmTableF32 &arm, int i, float st, float ct) {
     const float a = arm.dh[i - 1][0], d = arm.dh[i - 1][1], cA = arm.dh[i - 1][2], sA = arm.dh[i - 1][3];
     const float l01 = -st * cA, l02 = st * sA, l03 = a * ct;
     const float l11 = ct * cA, l12 = -ct * sA, l13 = a * st;
@@ -519,7 +522,9 @@ __device__ __forceinline__ uint32_t grid_certify(const DeviceWorld &w, const Arm
 // candidate pair: farther than r+R+delta -> free; nearer than r+R-delta -> colliding (both certain in
 // fp32); in between -> the fp64 chain and the specification's formula decide.
 // false: sphere slot j (centre cx,cy,cz) certainly collides or the fp64 verdict says so
-__device__ __forceinline__ bool grid_sphere_free(const DeviceWorld &w, const ObstacleTables &t, const double *q, int j,
+// `state()` returns the fp64 joint values of the sphere's state; it is called only for a thin-band pair
+template <class StateFn>
+__device__ __forceinline__ bool grid_sphere_free(const DeviceWorld &w, const ObstacleTables &t, StateFn &&state, int j,
                                                  float cx, float cy, float cz) {
   const ArmTableF32 &arm = *t.arm;
   const int nx = w.grid_n[0], ny = w.grid_n[1], nz = w.grid_n[2];
@@ -542,7 +547,7 @@ __device__ __forceinline__ bool grid_sphere_free(const DeviceWorld &w, const Obs
       if (d2 < rs * rs) {
         // deeper than the fp32 error bound: certainly colliding; only the thin band needs fp64
         const float rin = rs - 2.0f * w.delta;
-        if ((rin > 0.f && d2 < rin * rin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)o, true))
+        if ((rin > 0.f && d2 < rin * rin) || exact_pair_hit(w, state(), arm.sphere_id[j], (int)o, true))
           return false;
       }
     } else {
@@ -552,7 +557,7 @@ __device__ __forceinline__ bool grid_sphere_free(const DeviceWorld &w, const Obs
       const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
       if (d2 < thr * thr) {
         const float tin = thr - 2.0f * w.delta;
-        if ((tin > 0.f && d2 < tin * tin) || exact_pair_hit(w, q, arm.sphere_id[j], (int)id, false))
+        if ((tin > 0.f && d2 < tin * tin) || exact_pair_hit(w, state(), arm.sphere_id[j], (int)id, false))
           return false;
       }
     }
@@ -574,7 +579,7 @@ __device__ __forceinline__ bool grid_lists(const DeviceWorld &w, const ObstacleT
         continue;
       float cx, cy, cz;
       f.centre(arm.sphere[j], cx, cy, cz);
-      if (!grid_sphere_free(w, t, q, j, cx, cy, cz))
+      if (!grid_sphere_free(w, t, [&]() { return q; }, j, cx, cy, cz))
         return false;
     }
   }
@@ -586,7 +591,7 @@ __device__ __forceinline__ bool grid_lists_kept(const DeviceWorld &w, const Obst
   while (unc) {
     const int j = __ffs(unc) - 1;
     unc &= unc - 1;
-    if (!grid_sphere_free(w, t, q, j, centres[3 * j], centres[3 * j + 1], centres[3 * j + 2]))
+    if (!grid_sphere_free(w, t, [&]() { return q; }, j, centres[3 * j], centres[3 * j + 1], centres[3 * j + 2]))
       return false;
   }
   return true;
