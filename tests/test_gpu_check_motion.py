@@ -96,3 +96,22 @@ def test_thin_obstacles_conservative_advancement(P, O, synth, world_arrays, mode
     q = synth.cloud(44, 30000)
     ov, oc = ow.is_valid_batch(q, nthreads=8)
     assert _compare(gw.is_valid_batch(q), ov, oc) == 0
+
+
+def test_field_and_grid_switches_do_not_change_verdicts(P, synth, world_arrays, monkeypatch):
+    # the clearance field (+ conservative advancement) and the obstacle grid are accelerations only
+    a, b = synth.edges(61, 20000, max_len=1.5)
+    q = synth.cloud(62, 20000)
+    ref_v = ref_s = None
+    for env in ({}, {"PRGPU_NO_DFIELD": "1"}, {"PRGPU_NO_GRID": "1"}):
+        for k in ("PRGPU_NO_DFIELD", "PRGPU_NO_GRID"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        w = P.World(*world_arrays)
+        v = w.check_motion_batch(a, b, 0.01)
+        s = w.is_valid_batch(q)
+        if ref_v is None:
+            ref_v, ref_s = v, s
+        else:
+            assert np.array_equal(v, ref_v) and np.array_equal(s, ref_s), env
