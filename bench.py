@@ -380,7 +380,7 @@ def run_ours(args, rank, local_rank, world):
                 e_.synchronize()
                 kernel_ms.append(b_.elapsed_time(e_))
 
-        launches_per_step = 1
+        launches_per_step = 2  # warp-per-query kernel + team kernel
         units_per_step = Bq
         metric, unit = "RRTConnect plans/s", "plans/s"
         kernel_name = "rrtc_batch_kernel"
