@@ -101,7 +101,10 @@ typedef struct prgpu_world prgpu_world_t;
 #define PRGPU_MAX_LINK_SPHERES 32
 #define PRGPU_MAX_OBSTACLES 4096
 /* dh: dof x 5 (a, d, cos(alpha), sin(alpha), theta0); sphere_link[s] in [0,dof];
- * sphere_xyzr: S x 4; obs_spheres: x4 (x,y,z,R); obs_boxes: x6 (cx,cy,cz,hx,hy,hz). */
+ * sphere_xyzr: S x 4; obs_spheres: x4 (x,y,z,R); obs_boxes: x6 (cx,cy,cz,hx,hy,hz).
+ * Creation also builds the broad-phase structures on the device (an obstacle grid and a clearance
+ * field of up to 2^24 fp32 cells, a few milliseconds); they only accelerate, every verdict is that of the
+ * double-precision specification (clearance < 0 <=> collision), exactly, outside the 1e-6 contact band. */
 int prgpu_world_create(int device, int dof, const double *dh, int n_link_spheres,
                        const int32_t *sphere_link, const double *sphere_xyzr, int n_obs_spheres,
                        const double *obs_spheres, int n_obs_boxes, const double *obs_boxes,
@@ -118,7 +121,10 @@ int prgpu_world_last_kernel_ms(prgpu_world_t *w, float *ms);
  *         tests `from` (the goal-tree form isValid(from) && checkMotion(from,to),
  *         pr_ompl/src/RRTConnect.cpp:198).
  * mode 1: resolution = NNF's check resolution (0.05, frechet/include/NNFrechet.hpp:277);
- *         valid = !evaluateEdge(...). */
+ *         valid = !evaluateEdge(...).
+ * States that a tested neighbour's clearance proves free are not tested (conservative advancement): the
+ * result is still the AND over the whole tested set.  The host-buffer form stages its uploads under the
+ * kernels for batches of 2^19 edges and more. */
 int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double *to, uint64_t n,
                              double resolution, int mode, int check_first, uint8_t *valid);
 int prgpu_check_motion_batch_device(prgpu_world_t *w, const double *from_dev, const double *to_dev,
@@ -135,7 +141,8 @@ int prgpu_fk_batch_device(prgpu_world_t *w, const double *q_dev, uint64_t n, dou
 
 /* ------------------------------------------------------------------------------------
  * T1: many independent RRTConnect queries (pr_ompl::RRTConnect::solve, one planner per query,
- * pr_ompl/src/RRTConnect.cpp:219-376) against one world, one thread block per query.
+ * pr_ompl/src/RRTConnect.cpp:219-376) against one world: one warp per query, then 8-warp teams for the
+ * queries still unsolved after 256 samples (same trees, iteration counts and paths as one planner each).
  * Start/goal are single configurations (ProblemDefinition::setStartAndGoalStates); samples come
  * from the counter-based stream u(seed, query_id_base + i, iteration, dim) over [lo, hi];
  * termination = max_iters uniform samples (the ptc) or a full tree.
