@@ -121,3 +121,25 @@ def test_paths_are_collision_free(P, synth, gpu_world, oracle_world):
     A, B = np.vstack(A), np.vstack(B)
     lvs = np.sqrt(7 * (2 * np.pi) ** 2) * 0.01
     assert np.all(gpu_world.check_motion_batch(A, B, lvs) == 1)
+
+
+def test_tree_capacity_in_both_kernels(P, O, synth, gpu_world, oracle_world):
+    # max_nodes is a capacity of this implementation (the reference's trees are unbounded): a query whose tree fills
+    # stops with TIMEOUT and never writes past its buffers; queries that stay below the capacity are unaffected --
+    # whether they finish in the warp kernel or, after sample 256, in the team kernel.
+    n, cap = 64, 40
+    starts, goals = _problems(synth, oracle_world, n, seed=91)
+    rb = P.RrtcBatch(gpu_world, n, -np.pi, np.pi, extension_type="ext-con", seed=33, query_id_base=0,
+                     max_iters=1000, max_nodes=cap)
+    rb.run(starts, goals)
+    summ = rb.summary()
+    assert summ["n_start"].max() <= cap and summ["n_goal"].max() <= cap
+    full = (summ["n_start"] == cap) | (summ["n_goal"] == cap)
+    assert np.all(summ["status"][full & (summ["status"] != 6)] == 4)
+    checked = 0
+    for qi in np.flatnonzero(~full)[:24]:
+        ref = oracle_world.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=EXT_CODE["ext-con"], seed=33,
+                                      query=int(qi), max_iters=1000, impl="port")
+        _compare(rb, summ, int(qi), ref)
+        checked += 1
+    assert checked >= 8
