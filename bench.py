@@ -507,6 +507,43 @@ def run_ours(args, rank, local_rank, world):
         e2e_extra["with_tree_reupload"] = {"value": units_per_step * K / e2e_s2, "unit": "queries/s",
                                            "h2d_bytes_per_step": n_local * 56 + Q * 56, "d2h_bytes_per_step": d2h}
 
+    # ---- extra (multi-GPU): the alternative partitioning.  SURVEY §8(e) / the north star shard the TREE (it is
+    #      what scales a tree beyond one GPU's memory) -- that is `value`.  A 1e7-node tree fits every GPU,
+    #      so the same sweep can also replicate the tree and split the QUERIES: no candidate exchange, and
+    #      the per-query costs (sample, candidates, select) shrink with the rank count too.
+    if world > 1 and not args.no_extra and args.workload == "knn":
+        full = P.KnnIndex(7, device=local_rank, capacity=N)
+        full.add(synth.cloud(0, N))
+        q0, q1 = rank * Q // world, (rank + 1) * Q // world
+        qs_dev = q_dev[q0:q1].contiguous()
+        li = torch.empty((q1 - q0, k), dtype=torch.int32, device=dev)
+        ld = torch.empty((q1 - q0, k), dtype=torch.float64, device=dev)
+        ai = torch.empty((Q, k), dtype=torch.int32, device=dev)
+        ad = torch.empty((Q, k), dtype=torch.float64, device=dev)
+        even = Q % world == 0
+
+        def qstep():
+            full.nearest_k_device(qs_dev, q1 - q0, k, li, ld, stream=stream)
+            if even:
+                dist.all_gather_into_tensor(ai, li)
+                dist.all_gather_into_tensor(ad, ld)
+        for _ in range(3):
+            qstep()
+        barrier()
+        b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b_.record()
+        for _ in range(K):
+            qstep()
+        e_.record()
+        torch.cuda.synchronize()
+        qms = max_over_ranks(b_.elapsed_time(e_)) / K
+        if even:
+            same = bool(torch.equal(ai, fi)) and bool(torch.equal(ad, fd))
+            extra["query_sharded"] = {"queries_per_s": Q / (qms * 1e-3), "ms_per_step": qms,
+                                      "identical_to_node_sharded": same,
+                                      "note": "tree replicated on every GPU, queries split, results all-gathered"}
+        full.close()
+
     # ---- extras (rank 0, single GPU): the other shapes of the sweep ----
     if world == 1 and not args.no_extra and args.workload == "knn":
         def time_knn(nq, kk, reps=5):
