@@ -3,6 +3,7 @@
 // string-keyed hash maps (frechet/src/NNFrechet.cpp:467-599) is here: vertex ids in creation
 // order, an edge list in creation order, a CSR of predecessors and a level-sorted vertex order.
 #include <algorithm>
+#include <cstdlib>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -599,7 +600,10 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
         if (goalCost <= h->tau_ub || h->band_full)
           break; // exact: the optimum lies inside the band (or the band is the whole table)
         // a finite cost found inside the band is an upper bound of the optimum: use it directly
-        h->tau_ub = goalCost < 1e300 ? goalCost * (1.0 + 1e-9) : h->tau_ub * 2.0;
+        // (with some headroom: the goal cost creeps up with every knocked-out edge, and a rebuild costs
+        // about ten searches)
+        static const double headroom = getenv("PRGPU_NNF_TAU_HEADROOM") ? atof(getenv("PRGPU_NNF_TAU_HEADROOM")) : 1.03;
+        h->tau_ub = goalCost < 1e300 ? goalCost * headroom : h->tau_ub * 2.0;
         if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
           return rc;
       }
