@@ -356,20 +356,45 @@ nnf_flow_dp_kernel(const NnfBandDev g, uint32_t first_pos, uint32_t epoch, volat
         Clamp gfn;
         gfn.a = -NNF_INF;
         gfn.b = NNF_INF;
-        if (active) {
-          double mm = NNF_INF;
-          for (uint32_t e = m.pred_begin; e < m.pred_end; ++e) {
-            const NnfEdgeRec rec = g.edge[e];
-            if (rec.band_w_blocked & 0x80000000u)
-              continue;
-            const uint32_t pw = rec.band_w_blocked;
-            const uint32_t i0 = r - rec.band_lo;
-            if (i0 < pw)
-              mm = fmin(mm, __ldcg(g.Bc + rec.col_off + i0));
-            const uint32_t i1 = i0 - 1u;
-            if (r > 0 && i1 < pw)
-              mm = fmin(mm, __ldcg(g.Bc + rec.col_off + i1));
+        // min over the predecessors' cells (r, p) and (r-1, p).  The records of up to 32 predecessors are
+        // fetched by different lanes and handed round by shuffles, and the cells of four predecessors are
+        // in flight at a time: a vertex costs a few memory round trips, not two per predecessor.
+        double mm = NNF_INF;
+        for (uint32_t e0 = m.pred_begin; e0 < m.pred_end; e0 += 32) {
+          const uint32_t ne = min(32u, m.pred_end - e0);
+          NnfEdgeRec mine;
+          mine.col_off = 0;
+          mine.band_lo = 0;
+          mine.band_w_blocked = 0x80000000u;
+          if (lane < ne)
+            mine = g.edge[e0 + lane];
+          for (uint32_t j0 = 0; j0 < ne; j0 += 4) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int src = (int)min(j0 + u, 31u);
+              const uint64_t co = __shfl_sync(0xffffffffu, mine.col_off, src);
+              const uint32_t bl = __shfl_sync(0xffffffffu, mine.band_lo, src);
+              uint32_t bw = __shfl_sync(0xffffffffu, mine.band_w_blocked, src);
+              if (j0 + u >= ne)
+                bw = 0x80000000u;
+              v[2 * u] = NNF_INF;
+              v[2 * u + 1] = NNF_INF;
+              if (active && !(bw & 0x80000000u)) {
+                const uint32_t i0 = r - bl;
+                if (i0 < bw)
+                  v[2 * u] = __ldcg(g.Bc + co + i0);
+                const uint32_t i1 = i0 - 1u;
+                if (r > 0 && i1 < bw)
+                  v[2 * u + 1] = __ldcg(g.Bc + co + i1);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              mm = fmin(mm, v[u]);
           }
+        }
+        if (active) {
           const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
                        dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
           const double f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
