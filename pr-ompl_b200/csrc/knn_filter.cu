@@ -364,15 +364,17 @@ __global__ void knn_sample_threshold_kernel(uint32_t nq, int kp, uint32_t cap, u
   }
 }
 
-// Pass 3: one block per query, three levels.
-//  (a) on the stored TF32 keys D: the k-th smallest, kk.  Every D is within eps_tc of the real value, so
-//      a candidate with D > kk + 2 eps_tc has a real key above that of each of the k smallest-D
-//      candidates and cannot be among the k nearest: the others (a few dozen) are the level-1 survivors;
+// Pass 3: one block per query, three levels.  Selections are done by RANK (every thread counts the entries
+// that precede its own; no rounds of block-wide arg-min, two barriers per level).
+//  (a) on the stored TF32 keys D: kk = the k-th smallest of the 128 per-thread minima, an upper bound of the
+//      k-th smallest D.  Every D is within eps_tc of the real value, so a candidate with D > kk + 2 eps_tc
+//      has a real key above that of each of k other candidates and cannot be among the k nearest: the others
+//      (a few dozen) are the level-1 survivors;
 //  (b) their keys are recomputed with the fp32 FMA chain of the sample pass (error eps_32, a thousand
 //      times smaller) and cut again at (k-th smallest) + 2 eps_32: usually k plus a few remain;
-//  (c) exact fp64 distance (the reference's operation order) of those, k rounds of arg-min under
-//      (distance, index), then the proof against the nodes the scan discarded (D >= +0): their exact
-//      squared distance is >= T_q - eps_tc + |q|^2, which must lie strictly above the k-th selected.
+//  (c) exact fp64 distance (the reference's operation order) of those; the survivor of rank r under
+//      (distance, index) is output r; then the proof against the nodes the scan discarded (D >= +0): their
+//      exact squared distance is >= T_q - eps_tc + |q|^2, which must lie strictly above the k-th selected.
 // Unproven queries, overflowed candidate buffers and over-long survivor lists are flagged for the exact
 // kernel.
 constexpr int SEL_THREADS = 128;
@@ -385,20 +387,16 @@ knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf
                   uint32_t cap, const uint32_t *__restrict__ cand_count, const uint32_t *__restrict__ cand_idx,
                   const float *__restrict__ cand_key, int k, uint32_t *__restrict__ idx_out,
                   double *__restrict__ dist_out, uint32_t *__restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char sel_raw[];
-  float *okey = reinterpret_cast<float *>(sel_raw); // [cap] keys as stored
-  float *wkey = okey + cap;                         // [cap] working copy (selected entries -> +inf)
-  __shared__ float red_k[SEL_THREADS / 32];
-  __shared__ uint32_t red_p[SEL_THREADS / 32];
+  __shared__ float tmin[SEL_THREADS];
   __shared__ uint32_t l1_i[SEL_MAX_L1];
-  __shared__ float l1_k[SEL_MAX_L1], l1_w[SEL_MAX_L1];
+  __shared__ float l1_k[SEL_MAX_L1];
   __shared__ double sv_d[SEL_MAX_SURVIVORS];
   __shared__ uint32_t sv_i[SEL_MAX_SURVIVORS];
   __shared__ uint32_t n_l1, n_sv;
   __shared__ float s_kk;
-  __shared__ double s_eps_tc, s_eps32, s_qn2;
+  __shared__ double s_eps_tc, s_eps32, s_qn2, s_dk;
   const uint32_t q = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const uint32_t cnt = cand_count[q];
   auto flag_me = [&]() {
     if (tid == 0) {
@@ -428,62 +426,39 @@ knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf
     s_qn2 = qn2;
     n_l1 = 0;
     n_sv = 0;
+    s_kk = CUDART_INF_F;
+    s_dk = CUDART_INF;
   }
-  for (uint32_t c = tid; c < cnt; c += SEL_THREADS) {
-    const float kv = cand_key[(size_t)q * cap + c];
-    okey[c] = kv;
-    wkey[c] = kv;
+  const float *ckey = cand_key + (size_t)q * cap;
+  const uint32_t *cidx = cand_idx + (size_t)q * cap;
+  // (a) an upper bound of the k-th smallest stored key: the k-th smallest of the per-thread minima
+  {
+    float mine = CUDART_INF_F;
+    for (uint32_t c = tid; c < cnt; c += SEL_THREADS)
+      mine = fminf(mine, ckey[c]);
+    tmin[tid] = mine;
   }
   __syncthreads();
-  // k-th smallest entry of w[0..m) by k rounds of block-wide arg-min (selected entries are overwritten)
-  auto kth_smallest = [&](float *w, uint32_t m) {
-    const int rounds = (int)min((uint32_t)k, m);
-    for (int r = 0; r < rounds; ++r) {
-      float bk = CUDART_INF_F;
-      uint32_t bp = 0xFFFFFFFFu;
-      for (uint32_t c = tid; c < m; c += SEL_THREADS) {
-        const float v = w[c];
-        if (v < bk || (v == bk && c < bp)) {
-          bk = v;
-          bp = c;
-        }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const float ok = __shfl_xor_sync(0xffffffffu, bk, off);
-        const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
-        if (ok < bk || (ok == bk && op < bp)) {
-          bk = ok;
-          bp = op;
-        }
-      }
-      if (lane == 0) {
-        red_k[warp] = bk;
-        red_p[warp] = bp;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        for (int w2 = 1; w2 < SEL_THREADS / 32; ++w2)
-          if (red_k[w2] < bk || (red_k[w2] == bk && red_p[w2] < bp)) {
-            bk = red_k[w2];
-            bp = red_p[w2];
-          }
-        if (bp != 0xFFFFFFFFu)
-          w[bp] = CUDART_INF_F;
-        s_kk = bk;
-      }
-      __syncthreads();
+  const uint32_t nmin = min(cnt, (uint32_t)SEL_THREADS); // threads that hold a candidate
+  if (cnt > (uint32_t)k && (uint32_t)tid < nmin) {
+    const float mine = tmin[tid];
+    uint32_t rank = 0;
+    for (uint32_t u = 0; u < nmin; ++u) {
+      const float v = tmin[u];
+      rank += (v < mine || (v == mine && u < (uint32_t)tid)) ? 1u : 0u;
     }
-  };
-  // (a) level-1 survivors on the stored keys
-  kth_smallest(wkey, cnt);
+    if (rank == (uint32_t)k - 1u)
+      s_kk = mine;
+  }
+  __syncthreads();
+  // level-1 survivors: everything whose key is within 2 eps_tc of that bound (all, if no more than k)
   const float cut1 =
       cnt <= (uint32_t)k ? CUDART_INF_F : (float)((double)s_kk + 2.0 * s_eps_tc) * (1.0f + 1e-6f) + 1e-30f;
   for (uint32_t c = tid; c < cnt; c += SEL_THREADS)
-    if (okey[c] <= cut1) {
+    if (ckey[c] <= cut1) {
       const uint32_t slot = atomicAdd(&n_l1, 1u);
       if (slot < SEL_MAX_L1)
-        l1_i[slot] = cand_idx[(size_t)q * cap + c];
+        l1_i[slot] = cidx[c];
     }
   __syncthreads();
   const uint32_t n1 = n_l1;
@@ -509,11 +484,23 @@ knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf
       if (DIM > 5) x = fmaf(q2[5], b.y, x);
       if (DIM > 6) x = fmaf(q2[6], b.z, x);
       l1_k[c] = x;
-      l1_w[c] = x;
     }
   }
+  if (tid == 0)
+    s_kk = CUDART_INF_F;
   __syncthreads();
-  kth_smallest(l1_w, n1);
+  if (n1 > (uint32_t)k)
+    for (uint32_t c = tid; c < n1; c += SEL_THREADS) { // the entry of rank k-1 is the k-th smallest fp32 key
+      const float mine = l1_k[c];
+      uint32_t rank = 0;
+      for (uint32_t u = 0; u < n1; ++u) {
+        const float v = l1_k[u];
+        rank += (v < mine || (v == mine && u < c)) ? 1u : 0u;
+      }
+      if (rank == (uint32_t)k - 1u)
+        s_kk = mine;
+    }
+  __syncthreads();
   const float cut2 =
       n1 <= (uint32_t)k ? CUDART_INF_F : (float)((double)s_kk + 2.0 * s_eps32) * (1.0f + 1e-6f) + 1e-30f;
   for (uint32_t c = tid; c < n1; c += SEL_THREADS)
@@ -528,7 +515,7 @@ knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf
     flag_me();
     return;
   }
-  // (c) exact distances of the survivors
+  // (c) exact distances of the survivors; output r = the survivor of rank r under (distance, index)
   if ((uint32_t)tid < ns) {
     const uint32_t i = sv_i[tid];
     double x[DIM];
@@ -538,51 +525,34 @@ knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf
     sv_d[tid] = __dsqrt_rn(sqdist_exact<DIM>(x, qx)); // RealVectorStateSpace::distance(node, query)
   }
   __syncthreads();
-  if (warp == 0) {
-    double dk = CUDART_INF;
-    for (int r = 0; r < k; ++r) {
-      double bd = CUDART_INF;
-      uint32_t bi = PRGPU_INVALID_INDEX, bp = 0xFFFFFFFFu;
-      for (uint32_t c = lane; c < ns; c += 32) {
-        const double d = sv_d[c];
-        const uint32_t i = sv_i[c];
-        if (d < bd || (d == bd && i < bi)) {
-          bd = d;
-          bi = i;
-          bp = c;
-        }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, bd, off);
-        const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
-        if (od < bd || (od == bd && oi < bi)) {
-          bd = od;
-          bi = oi;
-          bp = op;
-        }
-      }
-      if (lane == 0) {
-        dist_out[(size_t)q * k + r] = bd;
-        idx_out[(size_t)q * k + r] = bi == PRGPU_INVALID_INDEX ? bi : bi + index_base;
-        if (bp != 0xFFFFFFFFu) {
-          sv_d[bp] = CUDART_INF;
-          sv_i[bp] = PRGPU_INVALID_INDEX;
-        }
-      }
-      __syncwarp();
-      dk = bd;
+  if ((uint32_t)tid < ns) {
+    const double md = sv_d[tid];
+    const uint32_t mi = sv_i[tid];
+    uint32_t rank = 0;
+    for (uint32_t u = 0; u < ns; ++u) {
+      const double d = sv_d[u];
+      const uint32_t i = sv_i[u];
+      rank += (d < md || (d == md && i < mi)) ? 1u : 0u;
     }
-    if (lane == 0) {
-      if (T < CUDART_INF_F) { // nodes were discarded by the scan: prove they cannot matter
-        const double bound = (double)T - s_eps_tc + s_qn2; // lower bound of any discarded node's exact squared distance
-        const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (s_qn2 + 1.0);
-        if (!(sk < bound)) {
-          const uint32_t slot = atomicAdd(flags, 1u);
-          flags[1 + slot] = q;
-        }
-      }
+    if (rank < (uint32_t)k) {
+      dist_out[(size_t)q * k + rank] = md;
+      idx_out[(size_t)q * k + rank] = mi + index_base;
+      if (rank == (uint32_t)k - 1u)
+        s_dk = md;
+    }
+  }
+  for (uint32_t r = ns + tid; r < (uint32_t)k; r += SEL_THREADS) { // fewer than k eligible nodes: padding
+    dist_out[(size_t)q * k + r] = CUDART_INF;
+    idx_out[(size_t)q * k + r] = PRGPU_INVALID_INDEX;
+  }
+  __syncthreads();
+  if (tid == 0 && T < CUDART_INF_F) { // nodes were discarded by the scan: prove they cannot matter
+    const double dk = s_dk;
+    const double bound = (double)T - s_eps_tc + s_qn2; // lower bound of any discarded node's exact squared distance
+    const double sk = dk * dk * (1.0 + 1e-12) + 1e-12 * (s_qn2 + 1.0);
+    if (!(sk < bound)) {
+      const uint32_t slot = atomicAdd(flags, 1u);
+      flags[1 + slot] = q;
     }
   }
 }
@@ -735,11 +705,9 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
     return rc;
 
   // ---- pass 3: exact re-rank of the candidates + proof ----
-  const size_t smem3 = (size_t)cap * 8;
   auto sel = knn_select_kernel<DIM>;
-  PRGPU_CUDA_TRY(cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-  sel<<<nq, SEL_THREADS, smem3, stream>>>(t.pts, t.ptsf, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts,
-                                         cidx, ckey, k, idx_out, dist_out, sc.flags);
+  sel<<<nq, SEL_THREADS, 0, stream>>>(t.pts, t.ptsf, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts,
+                                     cidx, ckey, k, idx_out, dist_out, sc.flags);
   PRGPU_CUDA_TRY(cudaGetLastError());
   ++sc.filter_calls;
 
