@@ -563,6 +563,28 @@ def run_ours(args, rank, local_rank, world):
         tree.add_device(pts_dev, n_local, stream)
         m1 = time_knn(args.queries, 1)
         extra["knn_k1_queries_per_s"] = args.queries / (m1 * 1e-3)
+        # the rest of BASELINE.json's sweep (10^4 .. 10^7 nodes, k = 1 / 16), resident trees
+        sweep = {}
+        for n_s in (10_000, 100_000, 1_000_000):
+            if n_s >= N:
+                continue
+            ts = P.KnnIndex(7, device=local_rank, capacity=n_s)
+            ts.add_device(pts_dev[:n_s].contiguous(), n_s, stream)
+            for kk in (16, 1):
+                qd = q_dev
+                i_ = torch.empty((Q, kk), dtype=torch.int32, device=dev)
+                d_ = torch.empty((Q, kk), dtype=torch.float64, device=dev)
+                for _ in range(3):
+                    ts.nearest_k_device(qd, Q, kk, i_, d_, stream=stream)
+                b, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b.record()
+                for _ in range(10):
+                    ts.nearest_k_device(qd, Q, kk, i_, d_, stream=stream)
+                e.record()
+                torch.cuda.synchronize()
+                sweep[f"N={n_s},k={kk}"] = Q / (b.elapsed_time(e) / 10 * 1e-3)
+            ts.close()
+        extra["knn_sweep_queries_per_s"] = sweep
         ms1 = time_knn(1, 1, reps=20)
         extra["single_query_scan"] = {"ms": ms1, "hbm_gbs": n_local * 56 / (ms1 * 1e-3) / 1e9,
                                       "frac_of_hbm_peak": n_local * 56 / (ms1 * 1e-3) / 1e9 / hbm_peak}
