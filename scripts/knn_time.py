@@ -8,6 +8,7 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 dev = torch.device("cuda:0"); st = torch.cuda.current_stream().cuda_stream
 pts = torch.from_numpy(synth.cloud(0, n)).to(dev)
 t = P.KnnIndex(7, capacity=n); t.add_device(pts, n, st)
+if os.environ.get('KNN_EXACT') == '1': t.set_search_mode(True)
 q = torch.from_numpy(synth.cloud(1, nq)).to(dev)
 idx = torch.empty((nq, k), dtype=torch.int32, device=dev); dist = torch.empty((nq, k), dtype=torch.float64, device=dev)
 for _ in range(3):
