@@ -187,6 +187,7 @@ struct Planner {
   struct Check { // result of the first half of growTree
     int32_t nmotion;
     bool ok, reach;
+    double bd;               // distance of the nearest node
     double c[WORLD_MAX_DOF]; // dstate
   };
 
@@ -296,6 +297,7 @@ struct Planner {
       }
     }
     r.nmotion = bi; // the butterfly leaves the same (distance, index) minimum in every lane
+    r.bd = bd;
     if (tid < dim)
       sh.near[tid] = T[(size_t)r.nmotion * dim + tid];
     __syncwarp();
@@ -359,6 +361,24 @@ struct Planner {
         break;
       }
     }
+  }
+  // A check made against n0 nodes stays the check against n1 > n0 nodes unless one of the new nodes is
+  // strictly nearer to the sample (sh.rstate) than the nearest it found (an equal distance loses to the
+  // lower index).  Same arithmetic as the scan.
+  __device__ __forceinline__ bool still_nearest(const double *T, uint32_t n0, uint32_t n1, const Check &r) {
+    bool nearer = false;
+    for (uint32_t i = n0 + tid; i < n1; i += 32) {
+      const double *x = T + (size_t)i * dim;
+      double sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < WORLD_MAX_DOF; ++k)
+        if (k < dim) {
+          const double diff = __dsub_rn(x[k], sh.rstate[k]);
+          sq = __dadd_rn(sq, __dmul_rn(diff, diff));
+        }
+      nearer = nearer || __dsqrt_rn(sq) < r.bd;
+    }
+    return !__any_sync(0xffffffffu, nearer);
   }
   // growTree, second half (:199-216)
   __device__ __forceinline__ int commit(double *T, int32_t *P, uint32_t &n, const Check &r, int32_t &xmotion) {
@@ -529,7 +549,8 @@ rrtc_team_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, c
   extern __shared__ float4 s_obs[];
   __shared__ Shared sh_all[RB_WARPS];
   __shared__ RrtcLoopState team_state;
-  __shared__ int team_flag[RB_WARPS]; // 0: first growTree not trapped, 1: trapped, 2: past the sample budget
+  __shared__ int team_flag[RB_WARPS]; // by window slot; 0: first growTree not trapped, 1: trapped, 2: past the
+                                      // sample budget, 3: not evaluated yet
   __shared__ uint32_t team_item;
   const ObstacleTables tabs = load_tables(w, s_obs);
   __syncthreads();
@@ -547,51 +568,131 @@ rrtc_team_kernel(const DeviceWorld *__restrict__ wp, const RrtcDeviceParams p, c
                    reinterpret_cast<unsigned char *>(s_obs) + warp_scratch_offset(w) + (size_t)warp * warp_scratch_bytes(w));
     pl.s = b.resume[qid];
     // a suspended query has drawn its goal sample and has a goal tree: the seeding block of
-    // `iteration` is a no-op from here on
+    // `iteration` is a no-op from here on.
+    // Warp w owns iteration my_it (the eight warps own eight consecutive iterations, the window); `have`:
+    // r is the first growTree's check of iteration my_it against the trees as they are now.
+    uint32_t my_it = pl.s.it + (uint32_t)warp;
+    bool have = false;
+    typename Planner<SP>::Check r;
+    r.ok = false;
+#ifdef RB_ACCOUNT
+    long long pr_rounds = 0, pr_step1 = 0, pr_lazy = 0, pr_inval = 0, pr_look = 0, pr_chk = 0, pr_exec = 0, pr_t0 = clock64();
+    uint32_t pr_it0 = pl.s.it;
+#endif
+    auto speculate = [&](uint32_t base_it, uint32_t base_start_tree) { // check of iteration my_it, trees as they are
+      const bool growStart = (base_start_tree != 0) != (((my_it - base_it) & 1u) != 0);
+      pl.draw_sample(my_it);
+      pl.check(growStart ? pl.tS : pl.tG, growStart ? pl.s.nS : pl.s.nG, growStart, r);
+      have = true;
+    };
     for (;;) {
       if (!(pl.s.it < p.max_iters) || pl.s.full)
         break;
-      // speculation: warp w takes the first growTree of iteration it + w against the trees as they are
-      const uint32_t my_it = pl.s.it + (uint32_t)warp;
-      typename Planner<SP>::Check r;
-      r.ok = false;
-      int flag = 2;
-      if (my_it < p.max_iters) {
-        const bool growStart = (pl.s.startTree != 0) != ((warp & 1) != 0);
-        pl.draw_sample(my_it);
-        pl.check(growStart ? pl.tS : pl.tG, growStart ? pl.s.nS : pl.s.nG, growStart, r);
-        flag = r.ok ? 0 : 1;
+      const uint32_t slot = my_it - pl.s.it; // 0 .. RB_WARPS-1
+#ifdef RB_ACCOUNT
+      long long pc0 = clock64();
+      ++pr_rounds;
+#endif
+      // (1) the checks of the window.  The last slot is evaluated only if the others are all trapped: it
+      //     belongs to the warp that carried the previous untrapped iteration on and could not look ahead
+      if (!have && my_it < p.max_iters && slot + 1 < RB_WARPS) {
+        speculate(pl.s.it, pl.s.startTree);
+#ifdef RB_ACCOUNT
+        ++pr_step1;
+#endif
       }
       if (lane == 0)
-        team_flag[warp] = flag;
+        team_flag[slot] = my_it >= p.max_iters ? 2 : (have ? (r.ok ? 0 : 1) : 3);
       __syncthreads();
       int first = RB_WARPS;
       for (int k = RB_WARPS - 1; k >= 0; --k)
         if (team_flag[k] != 1)
           first = k;
-      // the `first` iterations before it were trapped: they moved the sample counter and the alternation
+      int first_flag = first < RB_WARPS ? team_flag[first] : 1;
+      const bool lazy = first_flag == 3; // uniform
+      __syncthreads(); // everyone has read the flags
+      if (lazy) {
+#ifdef RB_ACCOUNT
+        ++pr_lazy;
+#endif
+        if ((int)slot == first) {
+          speculate(pl.s.it, pl.s.startTree);
+          if (lane == 0)
+            team_flag[slot] = r.ok ? 0 : 1;
+        }
+        __syncthreads();
+        first_flag = team_flag[first];
+        if (first_flag == 1)
+          first = RB_WARPS; // it was the last slot: the whole window is trapped
+        __syncthreads();
+      }
+#ifdef RB_ACCOUNT
+      pr_chk += clock64() - pc0;
+      long long pe0 = clock64();
+#endif
+      // (2) the `first` iterations before it were trapped: they moved the sample counter and the alternation
+      const bool run = first < RB_WARPS && first_flag == 0;
+      const uint32_t old_nS = pl.s.nS, old_nG = pl.s.nG;
       pl.s.it += (uint32_t)first;
       if (first & 1)
         pl.s.startTree = pl.s.startTree ? 0u : 1u;
-      const bool run = first < RB_WARPS && team_flag[first] == 0;
-      __syncthreads(); // everyone has read the flags
+      const bool executor = run && (int)slot == first;
+      const bool freed = (int)slot < first || executor; // my iteration is consumed: take the next free one
       bool ended = false;
-      if (run) {
-        if (warp == first) {
-          ended = pl.iteration(&r) == IT_END;
-          if (lane == 0) {
-            team_state = pl.s;
-            team_flag[0] = ended ? 1 : 0;
-          }
+      if (executor) {
+        ended = pl.iteration(&r) == IT_END;
+        if (lane == 0) {
+          team_state = pl.s;
+          team_flag[0] = ended ? 1 : 0;
         }
+        my_it += RB_WARPS;
+        have = false;
+      } else {
+        if (freed) {
+          my_it += RB_WARPS;
+          have = false;
+        }
+        // (3) look ahead while the executor works: whoever has no check for its iteration (a freed warp, or
+        //     the owner of the last slot whose check was not needed) makes it against the trees as they
+        //     were; validated below against what the executor appends
+        if (run && !have && my_it < p.max_iters) {
+          speculate(pl.s.it, pl.s.startTree);
+#ifdef RB_ACCOUNT
+          ++pr_look;
+#endif
+        }
+      }
+      if (run) {
         __syncthreads();
+        const uint32_t cur_it = pl.s.it; // iteration the executor carried on
+        const uint32_t cur_start = pl.s.startTree;
         pl.s = team_state;
         ended = team_flag[0] != 0;
-        __syncthreads(); // team_flag / team_state are rewritten by the next round
+        if (!ended && have) {
+          // the tree my check was made against: parity of my_it relative to the executed iteration
+          const bool growStart = (cur_start != 0) != (((my_it - cur_it) & 1u) != 0);
+          const bool okn = growStart ? pl.still_nearest(pl.tS, old_nS, pl.s.nS, r)
+                                     : pl.still_nearest(pl.tG, old_nG, pl.s.nG, r);
+          if (!okn) {
+            have = false;
+#ifdef RB_ACCOUNT
+            ++pr_inval;
+#endif
+          }
+        }
       }
+      __syncthreads(); // team_flag / team_state are rewritten by the next round
+#ifdef RB_ACCOUNT
+      pr_exec += clock64() - pe0;
+#endif
       if (ended)
         break;
     }
+#ifdef RB_ACCOUNT
+    if (lane == 0 && pl.s.it >= p.max_iters && (qid % 29) == 0)
+      printf("TEAM q %u w %d its %u rounds %lld step1 %lld lazy %lld look %lld inval %lld chk %lld exec %lld total %lld\n", qid, warp,
+             pl.s.it - pr_it0, pr_rounds, pr_step1, pr_lazy, pr_look, pr_inval, pr_chk, pr_exec, clock64() - pr_t0);
+#endif
     if (warp == 0)
       pl.finish(b);
     __syncthreads();
