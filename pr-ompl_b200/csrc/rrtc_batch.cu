@@ -22,8 +22,10 @@
 //      get TRAPPED: an iteration whose first growTree is trapped changes nothing but the sample counter
 //      and the tree alternation, so warp w evaluates the first growTree of iteration it+w against the
 //      unchanged trees; the iterations before the first untrapped one are skipped wholesale, the warp
-//      that found it carries its iteration on (append, the other tree's CONNECT, the connection test)
-//      while the others wait.  Same samples, same order of effects, bit-identical trees.
+//      that found it carries its iteration on (append, the other tree's CONNECT, the connection test).
+//      Meanwhile the warps without a check for their next iteration make it against the trees as they
+//      were; it is kept iff no appended node is strictly nearer to its sample than the nearest it found.
+//      Same samples, same order of effects, bit-identical trees.
 #include <cstdio>
 #include "rrtc_batch.cuh"
 #include "sample_stream.cuh"
