@@ -47,7 +47,7 @@ def test_batch_matches_oracle(P, O, synth, gpu_world, oracle_world, ext, rng):
         _compare(rb, summ, qi, ref)
 
 
-@pytest.mark.parametrize("ext", ["ext-con", "con-con"])
+@pytest.mark.parametrize("ext", EXTS)
 def test_long_budget_goes_through_the_team_kernel(P, O, synth, gpu_world, oracle_world, ext):
     # 1000 samples: the queries that are not solved by sample 256 are suspended and finished by the team kernel
     # (speculative evaluation of consecutive samples); iteration counts, trees and paths must not change
