@@ -17,8 +17,10 @@
 // LPA* keeps whichever its heap and hash containers reach first (implementation-defined);
 // here the rule is fixed: first minimum in the order [(r-1,n)], then for each NN predecessor p
 // in edge-creation order [(r,p), (r-1,p)].  The bottleneck cost is unaffected by that choice.
-// The literal reference cannot be compiled here (Boost.Graph and Eigen are absent), so this
-// port is pinned by hand-computed cases in tests/test_oracle_nnf.py, not by a compiled reference.
+// Pinned against the reference itself: frechet/src/*.cpp compiled unmodified into
+// oracle/_ref/libref_frechet.so (oracle/Makefile, oracle/ref_nnf_driver.cpp) and the golden vectors
+// generated from it (tests/golden/make_golden_nnf.py, tests/test_oracle_nnf_ref.py), plus the
+// independent checks of tests/test_oracle_nnf.py.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>

@@ -1,7 +1,7 @@
 /* ORACLE / TEST INFRASTRUCTURE ONLY.
  * C ABI of the CPU oracle (liboracle.so) and of the compiled reference
  * (oracle/_ref/libref_rrtconnect.so exports ref_rrtc_solve with the signature of
- * orc_rrtc_solve).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * orc_rrtc_solve; oracle/_ref/libref_frechet.so exports ref_nnf_run).  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load these libraries.
  * Parity unpinned upstream: the reference ships no tests, fixtures or golden
  * vectors; the oracle is pinned instead against the
@@ -61,8 +61,9 @@ int orc_rrtc_solve(const void *world, int dim, const double *lo, const double *h
                    double resolution_fraction, uint64_t seed, uint64_t query_id, uint32_t max_iters,
                    uint32_t max_nodes, uint32_t max_path, orc_rrtc_result *res, double *start_states,
                    int32_t *start_parent, double *goal_states, int32_t *goal_parent, double *path);
-/* ---- NNF (flat-array port of frechet/src/{NNFrechet,LPAStar,util}.cpp; the literal reference
- * needs Boost.Graph + Eigen, absent here, so there is no compiled-reference counterpart) ---- */
+/* ---- NNF (flat-array port of frechet/src/{NNFrechet,LPAStar,util}.cpp; the literal reference is
+ * compiled unmodified into oracle/_ref/libref_frechet.so over the stand-ins of oracle/compat/ and is
+ * driven through ref_nnf_run below) ---- */
 /* util.cpp:3-21 linDoubleSpace/linIntSpace: (int)(min + i*delta), delta = (max-min)/(N-1) */
 void orc_lin_int_space(double mn, double mx, uint64_t n, int32_t *out);
 /* NNFrechet.cpp:398-448: IK budget per super-sampled reference index: counts[0] = counts[R-1] = M,
@@ -86,6 +87,30 @@ int orc_nnf_run(const void *world, int R, const double *ref_pose12, int k, int D
                 const uint32_t *layer_counts, const double *ik_states, uint32_t max_lazy_iters, int nthreads,
                 orc_nnf_result *res, uint32_t *knn_out, double *vertex_states, double *vertex_pose12,
                 uint32_t cap_vertices, uint32_t *path_vertices, uint32_t cap_path, double *goal_cost_trace);
+
+/* ---- the reference's own NNFrechet::NNFrechet (oracle/ref_nnf_driver.cpp -> oracle/_ref/libref_frechet.so;
+ * libref_frechet_rev.so = same sources with the stand-in graph's edge-list iteration order reversed) ---- */
+typedef struct {
+  uint32_t R;               /* size of the sub-sampled reference path (NNFrechet.cpp:235-252) */
+  uint32_t n_vertices, n_edges, n_ik; /* NN graph */
+  uint64_t n_tpg_vertices, n_tpg_edges;
+  int32_t solved;           /* solve() returned EXACT_SOLUTION */
+  double final_error;       /* mFinalError (NNFrechet.hpp:282) */
+  double goal_cost;         /* LPAStar::mDistanceMap[goal] after the last search */
+  uint32_t path_len;
+  uint32_t n_evaluated, n_collisions;
+  uint32_t overflow;
+  double setup_seconds, solve_seconds;
+} ref_nnf_result;
+/* ref_full_pose12: the caller's reference path BEFORE subsampleRefPath; ik_states: pre-drawn IK solutions
+ * handed out in the reference's call order.  search_only != 0: setup() + one computeShortestPath +
+ * extractNNPath (first-search cost); otherwise solve(solve_seconds). */
+int ref_nnf_run(const void *world, uint32_t n_ref_full, const double *ref_full_pose12, int W, int M, int k, int D,
+                int seed, const double *ik_states, uint32_t n_ik_avail, double solve_seconds, int search_only,
+                ref_nnf_result *res, double *ref_sub_pose12, uint32_t cap_ref, uint32_t *ik_call_counts,
+                uint32_t *knn_out, double *vertex_states, double *vertex_pose12, uint32_t cap_vertices,
+                uint32_t *nn_edges, uint8_t *nn_edge_flags, uint32_t cap_edges, double *path_states,
+                uint32_t cap_path);
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,14 @@ class NnfResult(C.Structure):
                 ("n_collisions", C.c_uint32), ("overflow", C.c_uint32)]
 
 
+class RefNnfResult(C.Structure):
+    _fields_ = [("R", C.c_uint32), ("n_vertices", C.c_uint32), ("n_edges", C.c_uint32), ("n_ik", C.c_uint32),
+                ("n_tpg_vertices", C.c_uint64), ("n_tpg_edges", C.c_uint64), ("solved", C.c_int32),
+                ("final_error", C.c_double), ("goal_cost", C.c_double), ("path_len", C.c_uint32),
+                ("n_evaluated", C.c_uint32), ("n_collisions", C.c_uint32), ("overflow", C.c_uint32),
+                ("setup_seconds", C.c_double), ("solve_seconds", C.c_double)]
+
+
 class RrtcResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("iterations", C.c_uint32), ("n_start", C.c_uint32),
                 ("n_goal", C.c_uint32), ("path_len", C.c_uint32), ("overflow", C.c_uint32)]
@@ -88,6 +96,59 @@ def ref():
         L.ref_rrtc_solve.argtypes = _RRTC_ARGS
         _ref = L
     return _ref
+
+
+_ref_nnf = {}
+
+
+def ref_nnf(reverse_order=False):
+    """The reference's own frechet/src/*.cpp compiled over ompl_min + oracle/compat (mini-BGL), or None if
+    never built.  reverse_order: the build whose stand-in hash_setS edge lists iterate backwards."""
+    if reverse_order not in _ref_nnf:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_frechet_rev.so" if reverse_order else "libref_frechet.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_nnf_run.argtypes = [C.c_void_p, C.c_uint32, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp,
+                                  C.c_uint32, C.c_double, C.c_int, C.POINTER(RefNnfResult), c_dp, C.c_uint32,
+                                  c_u32p, c_u32p, c_dp, c_dp, C.c_uint32, c_u32p, c_u8p, C.c_uint32, c_dp,
+                                  C.c_uint32]
+        _ref_nnf[reverse_order] = L
+    return _ref_nnf[reverse_order]
+
+
+def ref_nnf_run(world, ref_full_pose12, W, M, k, D, ik_states, seed=1, solve_seconds=600.0, search_only=False,
+                reverse_order=False):
+    """NNFrechet::NNFrechet(si, W, M, k, D, seed) of the compiled reference: setRefPath(ref_full) ...
+    setup(); solve(solve_seconds).  ik_states are handed out by the IK callback in call order."""
+    L = ref_nnf(reverse_order)
+    assert L is not None, "oracle/_ref/libref_frechet.so was never built"
+    ref = np.ascontiguousarray(ref_full_pose12, dtype=np.float64).reshape(-1, 12)
+    ik = np.ascontiguousarray(ik_states, dtype=np.float64).reshape(-1, world.dof)
+    n_ik = len(ik)
+    R = (W - 1) * (D + 1) + 1
+    cap_v = 2 + n_ik + n_ik * k * D
+    cap_e = 2 * M + n_ik * k * (D + 1) + 16
+    cap_p = 4 * R + 64
+    res = RefNnfResult()
+    ref_sub = np.zeros((R, 12))
+    calls = np.zeros(R, dtype=np.uint32)
+    knn_out = np.empty((n_ik, k), dtype=np.uint32)
+    vs = np.zeros((cap_v, world.dof))
+    vp = np.zeros((cap_v, 12))
+    edges = np.zeros((cap_e, 2), dtype=np.uint32)
+    flags = np.zeros(cap_e, dtype=np.uint8)
+    path = np.zeros((cap_p, world.dof))
+    rc = L.ref_nnf_run(world.h, len(ref), _dp(ref), W, M, k, D, seed, _dp(ik), n_ik, float(solve_seconds),
+                       int(search_only), C.byref(res), _dp(ref_sub), R, calls.ctypes.data_as(c_u32p),
+                       knn_out.ctypes.data_as(c_u32p), _dp(vs), _dp(vp), cap_v, edges.ctypes.data_as(c_u32p),
+                       flags.ctypes.data_as(c_u8p), cap_e, _dp(path), cap_p)
+    assert rc == 0 and res.overflow == 0, (rc, res.overflow)
+    out = {f[0]: getattr(res, f[0]) for f in RefNnfResult._fields_}
+    out.update(ref=ref_sub[:res.R], ik_call_counts=calls[:res.R], knn=knn_out[:res.n_ik], states=vs[:res.n_vertices],
+               pose=vp[:res.n_vertices], edges=edges[:res.n_edges], edge_flags=flags[:res.n_edges],
+               path_states=path[:res.path_len].copy())
+    return out
 
 
 def knn(pts, queries, k, lo=None, nthreads=1):

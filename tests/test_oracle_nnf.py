@@ -1,5 +1,5 @@
-"""CPU tests pinning the NNF oracle port (oracle/nnf_port.cpp).  The literal frechet/ sources need
-Boost.Graph and Eigen (absent), so there is no compiled reference for NNF; the port is pinned by
+"""CPU tests pinning the NNF oracle port (oracle/nnf_port.cpp) by independent means (the comparison
+with the compiled reference and its golden vectors is tests/test_oracle_nnf_ref.py):
 (1) the reference's documented quirks (linIntSpace truncation), (2) an
 independent Python restatement of libstdc++'s minstd_rand0 + uniform_int_distribution for the IK
 budget (frechet/src/NNFrechet.cpp:310-343), (3) an independent algorithm for the min-bottleneck
