@@ -223,6 +223,13 @@ int prgpu_nnf_graph_info(prgpu_nnf_t *h, uint32_t *n_vertices, uint32_t *n_edges
 int prgpu_nnf_get_knn(prgpu_nnf_t *h, uint32_t *knn);
 /* all NN-graph vertices: configuration (n_vertices x dof; zeros for the two dummies) and pose */
 int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12);
+/* how findKnnNodes was executed at create time: calls that took the tensor-core filter path of K1 and
+ * queries that had to be re-run by the exact kernel (see prgpu_knn_search_stats) */
+int prgpu_nnf_knn_stats(prgpu_nnf_t *h, uint64_t *filter_calls, uint64_t *fallback_queries);
+/* NN-graph edges in creation order (n_edges x 2: source, target) and per-edge LazySP state:
+ * bit 0 = evaluated (the EProp::evaluated marker, NNFrechet.cpp:658-660), bit 1 = knocked out
+ * (markEdgeInCollision, :685-702).  Either pointer may be NULL. */
+int prgpu_nnf_get_edges(prgpu_nnf_t *h, uint32_t *edges, uint8_t *flags);
 /* path_vertices: NN-graph vertex ids of the solution (cap_path entries); goal_cost_trace: goal
  * cost of every search (max_lazy_iters entries) or NULL.  May be called again to continue. */
 int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *res, uint32_t *path_vertices,

@@ -362,3 +362,61 @@ extern "C" int orc_nnf_run(const void *world, int R, const double *ref_pose12, i
   }
   return 0;
 }
+
+// Independent of the DP above: forward reachability over the tensor-product cells with weight <= tau,
+// row by row, pushing along out-edges in a topological order of the NN graph (Kahn).
+extern "C" int orc_nnf_reachable(int R, const double *ref_pose12, uint32_t V, const double *pose12, uint32_t E,
+                                 const uint32_t *edges, const uint8_t *blocked, double tau, int strict) {
+  std::vector<uint32_t> off(V + 1, 0), succ(E), indeg(V, 0);
+  for (uint32_t e = 0; e < E; ++e) {
+    if (blocked && blocked[e])
+      continue;
+    off[edges[2 * (size_t)e] + 1]++;
+  }
+  for (uint32_t v = 0; v < V; ++v)
+    off[v + 1] += off[v];
+  {
+    std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+    for (uint32_t e = 0; e < E; ++e) {
+      if (blocked && blocked[e])
+        continue;
+      succ[cur[edges[2 * (size_t)e]]++] = edges[2 * (size_t)e + 1];
+      indeg[edges[2 * (size_t)e + 1]]++;
+    }
+  }
+  std::vector<uint32_t> topo;
+  topo.reserve(V);
+  for (uint32_t v = 0; v < V; ++v)
+    if (indeg[v] == 0)
+      topo.push_back(v);
+  for (size_t i = 0; i < topo.size(); ++i)
+    for (uint32_t o = off[topo[i]]; o < off[topo[i] + 1]; ++o)
+      if (--indeg[succ[o]] == 0)
+        topo.push_back(succ[o]);
+  if (topo.size() != V)
+    return -2;
+  std::vector<uint8_t> cur(V, 0), next(V, 0);
+  cur[0] = 1; // (0, c0)
+  for (int r = 0; r < R; ++r) {
+    const double *pr = ref_pose12 + 12 * (size_t)r;
+    std::fill(next.begin(), next.end(), 0);
+    for (uint32_t v : topo) {
+      if (!cur[v])
+        continue;
+      const double f = taskDistance(pr, pose12 + 12 * (size_t)v);
+      if (strict ? !(f < tau) : !(f <= tau)) {
+        cur[v] = 0;
+        continue;
+      }
+      next[v] = 1; // step A
+      for (uint32_t o = off[v]; o < off[v + 1]; ++o) {
+        cur[succ[o]] = 1;  // step B
+        next[succ[o]] = 1; // step C
+      }
+    }
+    if (r == R - 1)
+      return cur[1] ? 1 : 0;
+    cur.swap(next);
+  }
+  return 0;
+}

@@ -87,6 +87,14 @@ int orc_nnf_run(const void *world, int R, const double *ref_pose12, int k, int D
                 const uint32_t *layer_counts, const double *ik_states, uint32_t max_lazy_iters, int nthreads,
                 orc_nnf_result *res, uint32_t *knn_out, double *vertex_states, double *vertex_pose12,
                 uint32_t cap_vertices, uint32_t *path_vertices, uint32_t cap_path, double *goal_cost_trace);
+/* Independent check of a bottleneck cost (NOT the DP recurrence of orc_nnf_run): is the goal cell
+ * (R-1, c1) reachable from (0, c0) through tensor-product cells whose task distance is <= tau
+ * (strict != 0: < tau), along product edges A/B/C of NNFrechet.cpp:567-596 whose NN edge is not
+ * blocked?  pose12: V x 12; edges: E x 2 (source, target) with source before target in some
+ * topological order (any NN graph built by buildNNGraph); blocked: E bytes or NULL.
+ * A cost c is the min-bottleneck cost iff reachable(c, 0) && !reachable(c, 1). */
+int orc_nnf_reachable(int R, const double *ref_pose12, uint32_t V, const double *pose12, uint32_t E,
+                      const uint32_t *edges, const uint8_t *blocked, double tau, int strict);
 
 /* ---- the reference's own NNFrechet::NNFrechet (oracle/ref_nnf_driver.cpp -> oracle/_ref/libref_frechet.so;
  * libref_frechet_rev.so = same sources with the stand-in graph's edge-list iteration order reversed) ---- */

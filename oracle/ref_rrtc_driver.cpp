@@ -68,6 +68,13 @@ public:
 };
 } // namespace
 
+static uint32_t g_first_iters = 0;
+static int g_clear_between = 0;
+extern "C" void ref_set_two_phase(uint32_t first_iters, int clear_between) {
+  g_first_iters = first_iters;
+  g_clear_between = clear_between;
+}
+
 extern "C" int ref_rrtc_solve(const void *world, int dim, const double *lo, const double *hi,
                               const double *start, const double *goal, double range, int ext_first,
                               int ext_second, double resolution_fraction, uint64_t seed,
@@ -109,8 +116,23 @@ extern "C" int ref_rrtc_solve(const void *world, int dim, const double *lo, cons
         ext_second ? pr_ompl::RRTConnect::EXTTYPE_CONNECT : pr_ompl::RRTConnect::EXTTYPE_EXTEND));
     planner.setProblemDefinition(pdef);
     planner.setup();
-    ob::PlannerTerminationCondition ptc([&counter, max_iters] { return counter.count >= max_iters; });
-    ob::PlannerStatus st = planner.solve(ptc);
+    ob::PlannerStatus st = ob::PlannerStatus::UNKNOWN;
+    if (g_first_iters) { // solve() twice: continue the trees (RRTConnect.cpp:230-236 finds no new start), or
+                         // clear() (:166-176) and start over with the sample counter back at 0
+      const uint32_t first = g_first_iters;
+      st = planner.solve(ob::PlannerTerminationCondition([&counter, first] { return counter.count >= first; }));
+      if (g_clear_between) {
+        planner.clear();
+        pdef->clearSolutionPaths();
+        counter.count = 0;
+        planner.setup();
+        st = ob::PlannerStatus::UNKNOWN;
+      }
+    }
+    if (st != ob::PlannerStatus::EXACT_SOLUTION) {
+      ob::PlannerTerminationCondition ptc([&counter, max_iters] { return counter.count >= max_iters; });
+      st = planner.solve(ptc);
+    }
 
     std::memset(res, 0, sizeof(*res));
     res->status = (int32_t)(ob::PlannerStatus::StatusType)st;

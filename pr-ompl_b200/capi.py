@@ -82,6 +82,8 @@ SIGNATURES = {
     "prgpu_nnf_graph_info": (C.c_int, [c_vp, c_u32p, c_u32p, c_u32p]),
     "prgpu_nnf_get_knn": (C.c_int, [c_vp, c_vp]),
     "prgpu_nnf_get_vertices": (C.c_int, [c_vp, c_vp, c_vp]),
+    "prgpu_nnf_knn_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "prgpu_nnf_get_edges": (C.c_int, [c_vp, c_vp, c_vp]),
     "prgpu_nnf_solve": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, C.c_uint32, c_vp]),
     "prgpu_nnf_set_mode": (C.c_int, [c_vp, C.c_int]),
     "prgpu_nnf_band_info": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), c_u32p]),
@@ -377,6 +379,18 @@ class Nnf:
         po = np.empty((self.n_vertices, 12))
         _check(lib().prgpu_nnf_get_vertices(self.h, _ptr(st), _ptr(po)))
         return st, po
+
+    def knn_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(lib().prgpu_nnf_knn_stats(self.h, C.byref(a), C.byref(b)))
+        return dict(filter_calls=a.value, fallback_queries=b.value)
+
+    def edges(self):
+        """NN-graph edge list (creation order) and flags (bit 0 evaluated, bit 1 knocked out)."""
+        ed = np.empty((self.n_edges, 2), dtype=np.uint32)
+        fl = np.empty(self.n_edges, dtype=np.uint8)
+        _check(lib().prgpu_nnf_get_edges(self.h, _ptr(ed), _ptr(fl)))
+        return ed, fl
 
     def solve(self, max_lazy_iters=1000, cap_path=65536):
         res = NnfResult()

@@ -68,36 +68,61 @@ int prgpu_device_count(void) {
 
 /* ---------------------------------------------- K1 ---------------------------------------------- */
 
+// Grows the tree buffers.  Callers may append on their own stream (prgpu_knn_add_device), so nothing here
+// may be ordered only against h->stream: the first allocation zeroes xmax2 and waits for it; a regrow waits
+// for the whole device (pending appends into the old buffers, on whatever stream they were issued) before
+// copying, and for the copies before the old buffers are freed and the new ones handed out.  The handle is
+// left untouched unless everything succeeded.
 static int knn_reserve(prgpu_knn *h, uint64_t need) {
   if (need <= h->stride)
     return PRGPU_OK;
   uint64_t cap = std::max<uint64_t>(need, std::max<uint64_t>(2 * h->stride, 4096));
   cap = round_up(cap, KNN_TILE);
-  double *np = nullptr;
+  double *np = nullptr, *nx = nullptr;
   float *nf = nullptr;
-  PRGPU_CUDA_TRY(cudaMalloc(&np, (size_t)h->dim * cap * sizeof(double)));
-  if (h->dim <= 7)
-    PRGPU_CUDA_TRY(cudaMalloc(&nf, (size_t)cap * 18 * sizeof(float))); // fp32 mirror | TF32 mirror | |x|^2 pairs
-  if (!h->xmax2) {
-    PRGPU_CUDA_TRY(cudaMalloc(&h->xmax2, sizeof(double)));
-    PRGPU_CUDA_TRY(cudaMemsetAsync(h->xmax2, 0, sizeof(double), h->stream));
+  cudaError_t e = cudaMalloc(&np, (size_t)h->dim * cap * sizeof(double));
+  if (e == cudaSuccess && h->dim <= 7)
+    e = cudaMalloc(&nf, (size_t)cap * 18 * sizeof(float)); // fp32 mirror | TF32 mirror | |x|^2 pairs
+  if (e == cudaSuccess && !h->xmax2) {
+    e = cudaMalloc(&nx, sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMemsetAsync(nx, 0, sizeof(double), h->stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(h->stream); // an append on a foreign stream may follow immediately
+  }
+  if (e == cudaSuccess && h->pts && h->n) {
+    e = cudaDeviceSynchronize(); // appends still in flight on the caller's stream(s)
+    for (int d = 0; d < h->dim && e == cudaSuccess; ++d)
+      e = cudaMemcpyAsync(np + (size_t)d * cap, h->pts + (size_t)d * h->stride, h->n * sizeof(double),
+                          cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess && nf && h->ptsf) {
+      e = cudaMemcpyAsync(nf, h->ptsf, h->n * 8 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(nf + cap * 8, h->ptsf + h->stride * 8, h->n * 8 * sizeof(float), cudaMemcpyDeviceToDevice,
+                            h->stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(nf + cap * 16, h->ptsf + h->stride * 16, (h->n + 1) / 2 * 4 * sizeof(float),
+                            cudaMemcpyDeviceToDevice, h->stream);
+    }
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(h->stream);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(np);
+    cudaFree(nf);
+    cudaFree(nx);
+    cudaGetLastError();
+    return fail(PRGPU_ECUDA, std::string("knn_reserve: ") + cudaGetErrorString(e));
   }
   if (h->pts) {
-    for (int d = 0; d < h->dim; ++d)
-      PRGPU_CUDA_TRY(cudaMemcpyAsync(np + (size_t)d * cap, h->pts + (size_t)d * h->stride,
-                                     h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if (nf && h->ptsf) {
-      PRGPU_CUDA_TRY(cudaMemcpyAsync(nf, h->ptsf, h->n * 8 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-      PRGPU_CUDA_TRY(cudaMemcpyAsync(nf + cap * 8, h->ptsf + h->stride * 8, h->n * 8 * sizeof(float),
-                                     cudaMemcpyDeviceToDevice, h->stream));
-      PRGPU_CUDA_TRY(cudaMemcpyAsync(nf + cap * 16, h->ptsf + h->stride * 16, (h->n + 1) / 2 * 4 * sizeof(float),
-                                     cudaMemcpyDeviceToDevice, h->stream));
-    }
-    PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->n)
+      cudaDeviceSynchronize(); // nothing to copy, but a search may still be reading the old buffers
     cudaFree(h->pts);
     if (h->ptsf)
       cudaFree(h->ptsf);
   }
+  if (nx)
+    h->xmax2 = nx;
   h->pts = np;
   h->ptsf = nf;
   h->stride = cap;

@@ -48,6 +48,7 @@ struct prgpu_nnf {
   uint64_t band_cells = 0;
   uint32_t band_rebuilds = 0;
   uint32_t total_iters = 0, n_evaluated = 0, n_collisions = 0;
+  uint64_t knn_filter_calls = 0, knn_fallback_queries = 0;
 };
 
 namespace {
@@ -281,6 +282,13 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
       std::memcpy(h->knn.data() + (size_t)(M0 + ML) * k, res.data() + (size_t)M0 * k, (size_t)nInterior * k * 4);
     } while (0);
     cudaStreamSynchronize(s);
+    for (prgpu_knn_t *idx : {A, B}) {
+      uint64_t fc = 0, fq = 0;
+      if (idx && prgpu_knn_search_stats(idx, &fc, &fq) == PRGPU_OK) {
+        h->knn_filter_calls += fc;
+        h->knn_fallback_queries += fq;
+      }
+    }
     prgpu_knn_destroy(A);
     prgpu_knn_destroy(B);
     cleanup();
@@ -528,6 +536,30 @@ int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12) {
     std::memcpy(states, h->states.data(), h->states.size() * 8);
   if (pose12)
     std::memcpy(pose12, h->pose.data(), h->pose.size() * 8);
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_knn_stats(prgpu_nnf_t *h, uint64_t *filter_calls, uint64_t *fallback_queries) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "nnf_knn_stats: NULL handle");
+  if (filter_calls)
+    *filter_calls = h->knn_filter_calls;
+  if (fallback_queries)
+    *fallback_queries = h->knn_fallback_queries;
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_get_edges(prgpu_nnf_t *h, uint32_t *edges, uint8_t *flags) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "nnf_get_edges: NULL handle");
+  for (uint32_t e = 0; e < h->E; ++e) {
+    if (edges) {
+      edges[2 * (size_t)e] = h->edges[e].first;
+      edges[2 * (size_t)e + 1] = h->edges[e].second;
+    }
+    if (flags)
+      flags[e] = (uint8_t)((h->evaluated[e] ? 1 : 0) | (h->blocked[e] ? 2 : 0));
+  }
   return PRGPU_OK;
 }
 

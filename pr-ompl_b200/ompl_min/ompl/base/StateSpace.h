@@ -30,10 +30,24 @@ protected:
 typedef std::shared_ptr<StateSampler> StateSamplerPtr;
 typedef std::function<StateSamplerPtr(const StateSpace *)> StateSamplerAllocator;
 
+/// upstream ompl/base/StateSpaceTypes.h (the values the planners' drop-in classes test against)
+enum StateSpaceType {
+  STATE_SPACE_UNKNOWN = 0,
+  STATE_SPACE_REAL_VECTOR = 1,
+  STATE_SPACE_SO2 = 2,
+  STATE_SPACE_SO3 = 3,
+  STATE_SPACE_SE2 = 4,
+  STATE_SPACE_SE3 = 5,
+  STATE_SPACE_TIME = 6,
+  STATE_SPACE_DISCRETE = 7,
+  STATE_SPACE_TYPE_COUNT
+};
+
 class StateSpace {
 public:
   typedef State StateType;
-  StateSpace() : name_("Space") {}
+  StateSpace() : name_("Space"), type_(STATE_SPACE_UNKNOWN) {}
+  int getType() const { return type_; }
   virtual ~StateSpace() {}
   StateSpace(const StateSpace &) = delete;
   StateSpace &operator=(const StateSpace &) = delete;
@@ -101,6 +115,7 @@ public:
 
 protected:
   std::string name_;
+  int type_;
   StateSamplerAllocator ssa_;
   double longestValidSegmentFraction_ = 0.01;
   double longestValidSegment_ = 0.0;

@@ -31,6 +31,7 @@ public:
   explicit RealVectorStateSpace(unsigned int dim = 0)
       : dimension_(dim), bounds_(dim), stateBytes_(dim * sizeof(double)) {
     setName("RealVector" + getName());
+    type_ = STATE_SPACE_REAL_VECTOR;
   }
   void addDimension(double minBound = 0.0, double maxBound = 0.0) {
     dimension_++;

@@ -20,16 +20,34 @@ NNFrechet::NNFrechet(const ob::SpaceInformationPtr &si, int numWaypoints, int ik
       ikMultiplier_(ikMultiplier), numNN_(numNN), discretization_(discretization) {
   rng_.seed(seed);
 }
-NNFrechet::~NNFrechet() {
+NNFrechet::~NNFrechet() { releaseGraph(); }
+
+void NNFrechet::releaseGraph() {
   prgpu_nnf_destroy(handle_);
+  handle_ = nullptr;
   for (ob::State *s : ikStates_)
     si_->freeState(s);
+  ikStates_.clear();
+  layerCounts_.clear();
+  pathVertices_.clear();
+  vertexStates_.clear();
+  finalError_ = goalCost_ = 0.0;
+  lazyIters_ = nEvaluated_ = nCollisions_ = 0;
+}
+
+void NNFrechet::clear() {
+  ob::Planner::clear();
+  releaseGraph();
+  if (!originalRefPath_.empty())
+    refPath_ = originalRefPath_; // setup() sub-samples in place (as the reference does, NNFrechet.cpp:201)
+  setup_ = false;
 }
 
 void NNFrechet::setRefPath(std::vector<Eigen::Isometry3d> &referencePath) {
   if (referencePath.size() <= 1)
     throw ompl::Exception("referencePath is empty!");
   refPath_ = referencePath;
+  originalRefPath_.clear();
 }
 void NNFrechet::setFKFunc(std::function<Eigen::Isometry3d(ob::State *)> fkFunc) {
   if (!fkFunc)
@@ -96,12 +114,17 @@ void NNFrechet::setup() {
     throw ompl::Exception("Task-space distance function not set!");
   if (!world_)
     throw ompl::Exception("NNFrechet", "device world not set (setWorld)");
+  requireRealVectorSpace(space_.get(), "NNFrechet");
   const auto t0 = std::chrono::steady_clock::now();
   const int dof = world_->dof();
+  // setup() may be called again (after clear() or a parameter change): start from nothing
+  releaseGraph();
   if ((int)space_->getDimension() != dof)
     throw ompl::Exception("NNFrechet", "state dimension differs from the world's dof");
 
-  refPath_ = subsampleRefPath(refPath_);
+  if (originalRefPath_.empty())
+    originalRefPath_ = refPath_;
+  refPath_ = subsampleRefPath(originalRefPath_);
   const int R = (int)refPath_.size();
 
   // IK budget: both end waypoints get ikMultiplier solutions, the rest of numWaypoints*ikMultiplier
@@ -139,8 +162,6 @@ void NNFrechet::setup() {
   p.num_nn = numNN_;
   p.discretization = discretization_;
   p.check_resolution = checkResolution_;
-  prgpu_nnf_destroy(handle_);
-  handle_ = nullptr;
   check(prgpu_nnf_create(world_->handle(), &p, R, ref12.data(), layerCounts_.data(), ik.data(), &handle_),
         "NNFrechet::setup");
   uint32_t nv = 0;

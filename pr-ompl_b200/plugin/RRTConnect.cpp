@@ -57,6 +57,9 @@ std::string RRTConnect::getExtensionTypesString() const {
 
 void RRTConnect::setup() {
   ob::Planner::setup();
+  // nearest() is Euclidean over `dim` contiguous doubles on the device while the step clamp uses
+  // si_->distance / interpolate: the two agree for RealVectorStateSpace only
+  requireRealVectorSpace(si_->getStateSpace().get(), "RRTConnect");
   ompl::tools::SelfConfig(si_, getName()).configurePlannerRange(range_);
   const int dim = (int)si_->getStateDimension();
   for (Tree &t : trees_) {

@@ -14,9 +14,15 @@
 namespace ob = ompl::base;
 namespace og = ompl::geometric;
 static thread_local std::string g_err;
+static uint32_t g_first_iters = 0;
+static int g_clear_between = 0;
 
 extern "C" {
 const char *plg_last_error(void) { return g_err.c_str(); }
+void plg_set_two_phase(uint32_t first_iters, int clear_between) {
+  g_first_iters = first_iters;
+  g_clear_between = clear_between;
+}
 
 void *plg_world_create(int device, int dof, const double *dh, int ns, const int32_t *link, const double *xyzr,
                        int nos, const double *os, int nob, const double *obx) {
@@ -79,8 +85,21 @@ int plg_rrtc_solve(void *worldp, int dim, const double *lo, const double *hi, co
     }
     planner.setProblemDefinition(pdef);
     planner.setup();
-    ob::PlannerStatus st =
-        planner.solve(ob::PlannerTerminationCondition([&counter, max_iters] { return counter.count >= max_iters; }));
+    ob::PlannerStatus st = ob::PlannerStatus::UNKNOWN;
+    if (g_first_iters) { // solve() twice: continue the trees, or clear() and start over
+      const uint32_t first = g_first_iters;
+      st = planner.solve(ob::PlannerTerminationCondition([&counter, first] { return counter.count >= first; }));
+      if (g_clear_between) {
+        planner.clear();
+        pdef->clearSolutionPaths();
+        counter.count = 0;
+        planner.setup();
+        st = ob::PlannerStatus::UNKNOWN;
+      }
+    }
+    if (st != ob::PlannerStatus::EXACT_SOLUTION)
+      st = planner.solve(
+          ob::PlannerTerminationCondition([&counter, max_iters] { return counter.count >= max_iters; }));
 
     std::memset(res, 0, sizeof(*res));
     res->status = (int32_t)(ob::PlannerStatus::StatusType)st;
@@ -122,6 +141,42 @@ int plg_rrtc_solve(void *worldp, int dim, const double *lo, const double *hi, co
       pd_counts[1] = data.numEdges();
       pd_counts[2] = data.numStartVertices();
       pd_counts[3] = data.numGoalVertices();
+    }
+    return 0;
+  } catch (std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+int plg_batched_rrtc_solve(void *worldp, int dim, const double *lo, const double *hi, uint32_t n,
+                           const double *starts, const double *goals, double range, const char *extension_type,
+                           double resolution_fraction, uint64_t seed, uint64_t query_id_base, uint32_t max_iters,
+                           uint32_t max_nodes, int32_t *status, uint32_t *iterations, uint32_t *n_start,
+                           uint32_t *n_goal, uint32_t *path_len, double *paths, uint32_t max_path) {
+  try {
+    const pr_gpu::GpuWorldPtr &world = *static_cast<pr_gpu::GpuWorldPtr *>(worldp);
+    ob::RealVectorBounds bounds(dim);
+    for (int i = 0; i < dim; ++i) {
+      bounds.setLow(i, lo[i]);
+      bounds.setHigh(i, hi[i]);
+    }
+    pr_gpu::BatchedRRTConnect batch(world, bounds, n);
+    batch.setRange(range);
+    batch.setStateValidityCheckingResolution(resolution_fraction);
+    batch.setExtensionTypesString(extension_type);
+    batch.setSampleStream(seed, query_id_base);
+    batch.setLimits(max_iters, max_nodes);
+    std::vector<pr_gpu::BatchedRRTConnect::Result> r = batch.solve(starts, goals);
+    for (uint32_t q = 0; q < n; ++q) {
+      status[q] = (int32_t)r[q].status;
+      iterations[q] = r[q].iterations;
+      n_start[q] = r[q].startTreeSize;
+      n_goal[q] = r[q].goalTreeSize;
+      std::vector<std::vector<double>> p = batch.path(q);
+      path_len[q] = (uint32_t)p.size();
+      for (std::size_t i = 0; i < p.size() && i < max_path; ++i)
+        std::memcpy(paths + ((std::size_t)q * max_path + i) * dim, p[i].data(), sizeof(double) * dim);
     }
     return 0;
   } catch (std::exception &e) {

@@ -21,6 +21,18 @@ int plg_rrtc_solve(void *world, int dim, const double *lo, const double *hi, con
                    uint64_t seed, uint64_t query_id, uint32_t max_iters, uint32_t max_nodes, uint32_t max_path,
                    plg_rrtc_result *res, double *start_states, int32_t *start_parent, double *goal_states,
                    int32_t *goal_parent, double *path, uint32_t *planner_data_counts /* 4: vertices, edges, starts, goals */);
+/* The next plg_rrtc_solve call stops after first_iters samples (use an even number: the tree alternation
+ * restarts with the start tree on every solve(), RRTConnect.cpp:263-268), then -- clear_between != 0:
+ * clear() and setup() again, sample counter back to 0 (RRTConnect.cpp:166-176) -- calls solve() a second
+ * time up to max_iters.  first_iters == 0 restores the single-call behaviour. */
+void plg_set_two_phase(uint32_t first_iters, int clear_between);
+/* pr_gpu::BatchedRRTConnect through the plugin library: n queries, per query status / iterations / tree
+ * sizes / path (paths: n x max_path x dim). */
+int plg_batched_rrtc_solve(void *world, int dim, const double *lo, const double *hi, uint32_t n,
+                           const double *starts, const double *goals, double range, const char *extension_type,
+                           double resolution_fraction, uint64_t seed, uint64_t query_id_base, uint32_t max_iters,
+                           uint32_t max_nodes, int32_t *status, uint32_t *iterations, uint32_t *n_start,
+                           uint32_t *n_goal, uint32_t *path_len, double *paths, uint32_t max_path);
 /* exercises the OMPL-facing classes directly: returns 0 if every check passes */
 int plg_selftest_interfaces(void *world, const double *states, uint32_t n, uint8_t *is_valid_out,
                             uint8_t *motion_out /* n-1 consecutive edges */, uint32_t *nearest_out /* n */);

@@ -6,22 +6,58 @@
 // first strict minimum in insertion order (the order of OMPL's linear structure).
 //
 // The elements are opaque to OMPL's NN interface (only the distance functor looks inside), so a
-// GPU structure needs the coordinates: install setCoordinateAccessor(fn, dim) before the first
-// add().  The distance function given through setDistanceFunction() is kept for API
-// compatibility but never evaluated: distances are RealVectorStateSpace::distance, bit for bit.
+// GPU structure needs the coordinates.  Two ways:
+//  * default accessor: if an element is a pointer to something with a member `state` (an
+//    ompl::base::State* -- the shape of every OMPL planner's Motion, pr_ompl/include/pr_ompl/RRTConnect.h:
+//    129-151), the coordinates are state->as<RealVectorStateSpace::StateType>()->values.  The member is
+//    reached through the deduced element type, so the reference's *protected* nested Motion class works
+//    unmodified.  The dimension comes from the state space given to the constructor (what
+//    SelfConfig::getDefaultNearestNeighbors passes) or, for the default-constructed structure that
+//    setNearestNeighbors<NN>() creates (RRTConnect.h:113-118), from setDefaultDimension();
+//  * setCoordinateAccessor(fn, dim) for any other element type.
+// The distance function given through setDistanceFunction() is kept for API compatibility but never
+// evaluated: distances are RealVectorStateSpace::distance, bit for bit.
 #ifndef PR_GPU_GPUNEARESTNEIGHBORS_H
 #define PR_GPU_GPUNEARESTNEIGHBORS_H
 #include <algorithm>
 #include <functional>
 #include <vector>
+#include <type_traits>
+#include <ompl/base/spaces/RealVectorStateSpace.h>
 #include <ompl/datastructures/NearestNeighbors.h>
 #include "pr_gpu/Error.h"
 namespace pr_gpu {
+namespace detail {
+template <class T, class = void> struct HasStateMember : std::false_type {};
+template <class T>
+struct HasStateMember<T, decltype(void(std::declval<const T &>()->state))> : std::true_type {};
+template <class T>
+typename std::enable_if<HasStateMember<T>::value, const double *>::type motionCoordinates(const T &e) {
+  return e->state->template as<ompl::base::RealVectorStateSpace::StateType>()->values;
+}
+template <class T>
+typename std::enable_if<!HasStateMember<T>::value, const double *>::type motionCoordinates(const T &) {
+  throw ompl::Exception("GpuNearestNeighbors",
+                        "element type has no `state` member: call setCoordinateAccessor(fn, dim) before add()");
+}
+inline int &defaultDimension() {
+  static int dim = 0;
+  return dim;
+}
+} // namespace detail
+/// dimension used by default-constructed GpuNearestNeighbors (the setNearestNeighbors<NN>() path)
+inline void setDefaultDimension(int dim) { detail::defaultDimension() = dim; }
+
 template <typename _T> class GpuNearestNeighbors : public ompl::NearestNeighbors<_T> {
 public:
   typedef std::function<const double *(const _T &)> CoordinateAccessor;
 
   GpuNearestNeighbors() : handle_(nullptr), dim_(0), device_(0) {}
+  explicit GpuNearestNeighbors(const std::shared_ptr<ompl::base::StateSpace> &space)
+      : handle_(nullptr), dim_(0), device_(0) {
+    requireRealVectorSpace(space.get(), "GpuNearestNeighbors");
+    dim_ = (int)space->getDimension();
+  }
   ~GpuNearestNeighbors() override { prgpu_knn_destroy(handle_); }
   GpuNearestNeighbors(const GpuNearestNeighbors &) = delete;
   GpuNearestNeighbors &operator=(const GpuNearestNeighbors &) = delete;
@@ -122,8 +158,13 @@ public:
 
 private:
   void ensure() {
+    if (dim_ <= 0)
+      dim_ = detail::defaultDimension();
+    if (!coords_ && dim_ > 0)
+      coords_ = [](const _T &e) { return detail::motionCoordinates(e); };
     if (!coords_ || dim_ <= 0)
-      throw ompl::Exception("GpuNearestNeighbors", "setCoordinateAccessor(fn, dim) must be called before add()");
+      throw ompl::Exception("GpuNearestNeighbors", "unknown dimension: construct with the state space, call "
+                                                   "pr_gpu::setDefaultDimension(dim) or setCoordinateAccessor(fn, dim)");
     if (!handle_)
       check(prgpu_knn_create(device_, dim_, 1024, &handle_), "GpuNearestNeighbors");
   }
@@ -136,7 +177,7 @@ private:
 
 // hook for ompl_min's SelfConfig::getDefaultNearestNeighbors in the product build
 template <typename T>
-ompl::NearestNeighbors<T> *ompl_min_default_nn(const std::shared_ptr<ompl::base::StateSpace> &) {
-  return new pr_gpu::GpuNearestNeighbors<T>();
+ompl::NearestNeighbors<T> *ompl_min_default_nn(const std::shared_ptr<ompl::base::StateSpace> &space) {
+  return new pr_gpu::GpuNearestNeighbors<T>(space);
 }
 #endif

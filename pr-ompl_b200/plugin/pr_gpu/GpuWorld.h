@@ -43,6 +43,7 @@ class GpuStateValidityChecker : public ompl::base::StateValidityChecker {
 public:
   GpuStateValidityChecker(const ompl::base::SpaceInformationPtr &si, const GpuWorldPtr &world)
       : ompl::base::StateValidityChecker(si), world_(world) {
+    requireRealVectorSpace(si->getStateSpace().get(), "GpuStateValidityChecker");
     if ((int)si->getStateDimension() != world->dof())
       throw ompl::Exception("GpuStateValidityChecker", "state dimension differs from the world's dof");
   }
@@ -65,7 +66,11 @@ private:
 class GpuMotionValidator : public ompl::base::MotionValidator {
 public:
   GpuMotionValidator(const ompl::base::SpaceInformationPtr &si, const GpuWorldPtr &world)
-      : ompl::base::MotionValidator(si), world_(world) {}
+      : ompl::base::MotionValidator(si), world_(world) {
+    requireRealVectorSpace(si->getStateSpace().get(), "GpuMotionValidator");
+    if ((int)si->getStateDimension() != world->dof())
+      throw ompl::Exception("GpuMotionValidator", "state dimension differs from the world's dof");
+  }
   bool checkMotion(const ompl::base::State *s1, const ompl::base::State *s2) const override {
     uint8_t v = 0;
     check(prgpu_check_motion_batch(world_->handle(), reals(si_, s1), reals(si_, s2), 1,

@@ -42,6 +42,7 @@ public:
   ompl::base::PlannerStatus solve(const ompl::base::PlannerTerminationCondition &ptc) override;
   ompl::base::PlannerStatus solve(double solveTime);
   void setup() override;
+  void clear() override;
 
   // statistics the reference only logs (frechet/src/NNFrechet.cpp:162-171)
   double finalError() const { return finalError_; }
@@ -53,6 +54,7 @@ public:
   const std::vector<unsigned> &pathVertices() const { return pathVertices_; }
 
 private:
+  void releaseGraph();
   std::vector<Eigen::Isometry3d> subsampleRefPath(const std::vector<Eigen::Isometry3d> &path) const;
 
   ompl::base::StateSpacePtr space_;
@@ -61,7 +63,7 @@ private:
   int numWaypoints_ = 5, ikMultiplier_ = 5, numNN_ = 5, discretization_ = 3; // NNFrechet.hpp:262-274
   double checkResolution_ = 0.05;                                             // NNFrechet.hpp:277
   std::default_random_engine rng_;
-  std::vector<Eigen::Isometry3d> refPath_;
+  std::vector<Eigen::Isometry3d> refPath_, originalRefPath_;
   std::function<Eigen::Isometry3d(ompl::base::State *)> fk_;
   std::function<std::vector<ompl::base::State *>(Eigen::Isometry3d &, int)> ik_;
   std::function<double(Eigen::Isometry3d &, Eigen::Isometry3d &)> dist_;

@@ -81,6 +81,8 @@ def lib():
         L.orc_nnf_run.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_int, C.c_double, c_u32p, c_dp,
                                   C.c_uint32, C.c_int, C.POINTER(NnfResult), c_u32p, c_dp, c_dp, C.c_uint32,
                                   c_u32p, C.c_uint32, c_dp]
+        L.orc_nnf_reachable.argtypes = [C.c_int, c_dp, C.c_uint32, c_dp, C.c_uint32, c_u32p, c_u8p, C.c_double,
+                                        C.c_int]
         _lib = L
     return _lib
 
@@ -94,6 +96,7 @@ def ref():
             return None
         L = C.CDLL(path)
         L.ref_rrtc_solve.argtypes = _RRTC_ARGS
+        L.ref_set_two_phase.argtypes = [C.c_uint32, C.c_int]
         _ref = L
     return _ref
 
@@ -254,6 +257,21 @@ def nnf_layer_counts(seed, R, W, M):
     out = np.empty(R, dtype=np.uint32)
     lib().orc_nnf_layer_counts(seed, R, W, M, out.ctypes.data_as(c_u32p))
     return out
+
+
+def nnf_reachable(ref_pose12, pose12, edges, tau, strict=False, blocked=None):
+    """Independent bottleneck check: goal reachable through TPG cells with task distance <= tau (< if strict)?"""
+    ref = np.ascontiguousarray(ref_pose12, dtype=np.float64).reshape(-1, 12)
+    pose = np.ascontiguousarray(pose12, dtype=np.float64).reshape(-1, 12)
+    ed = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
+    bl = None
+    if blocked is not None:
+        blocked = np.ascontiguousarray(blocked, dtype=np.uint8)
+        bl = blocked.ctypes.data_as(c_u8p)
+    rc = lib().orc_nnf_reachable(len(ref), _dp(ref), len(pose), _dp(pose), len(ed), ed.ctypes.data_as(c_u32p), bl,
+                                 float(tau), int(strict))
+    assert rc in (0, 1), rc
+    return bool(rc)
 
 
 def nnf_run(world, ref_pose12, layer_counts, ik_states, k=5, D=3, check_res=0.05, max_lazy_iters=1000,

@@ -202,3 +202,30 @@ def test_filter_path_incremental_adds_and_growth(P, O, synth):
     oi, od = O.knn(pts[:10001][::-1].copy(), q, 3, nthreads=8)
     assert np.array_equal(gi, oi) and np.array_equal(gd, od)
     t.close()
+
+
+def test_add_device_on_foreign_stream_after_create_and_regrow(P, O, synth):
+    """prgpu_knn_add_device runs on the CALLER's stream: the handle's own bookkeeping (zeroing max|x|^2 at
+    create, copying the buffers on a regrow) must be ordered against it.  A lost max|x|^2 would collapse
+    the filter path's error bounds, lost points would change the answers."""
+    import torch
+    pts = synth.cloud(5, 60000) * 1.0
+    q = synth.cloud(6, 512)
+    stream = torch.cuda.Stream()
+    t = torch.from_numpy(pts).cuda()
+    torch.cuda.synchronize()
+    for rep in range(3):
+        tree = P.KnnIndex(7, capacity=8192)                      # capacity hint: buffers + max|x|^2 exist
+        with torch.cuda.stream(stream):
+            tree.add_device(t[:8000], 8000, stream.cuda_stream)           # right after create
+            tree.add_device(t[8000:20000], 12000, stream.cuda_stream)     # regrow with an append in flight
+            tree.add_device(t[20000:], 40000, stream.cuda_stream)         # and again
+        stream.synchronize()
+        assert tree.size() == 60000
+        assert np.array_equal(tree.points(0, 60000), pts)
+        gi, gd = tree.nearest_k(q, 16)                           # >= 8192 nodes, >= 128 queries: filter path
+        oi, od = O.knn(pts, q, 16, nthreads=8)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+        st = tree.search_stats()
+        assert st["filter_calls"] >= 1 and st["fallback_queries"] == 0
+        tree.close()

@@ -60,7 +60,7 @@ def test_plugin_nnfrechet_matches_reference_goldens(P, O, synth, name):
     tseed, pseed, W, M, k, D, ns, nb = [int(x) for x in c["params"]]
     dh, link, xyzr = synth.default_arm()
     sph, box = G.case_world_arrays(synth, c)
-    pw = PL.World(dh, link, xyzr, sph, box)
+    pw = PL.PluginWorld(dh, link, xyzr, sph, box)
     ow = O.World(dh, link, xyzr, sph, box)
     g = pw.nnf_run(W, M, k, D, pseed, c["ref_full"], c["ik"], solve_seconds=60.0)
     assert np.array_equal(g["layer_counts"], c["ik_call_counts"])
@@ -70,3 +70,68 @@ def test_plugin_nnfrechet_matches_reference_goldens(P, O, synth, name):
         assert _close(g["goal_cost"], float(c["goal_cost"]), 1e-12)
         G.check_solution_path(c, g["path"], ow)
         assert np.array_equal(g["path_states"], c["states"][g["path"]])
+
+
+def _problem(O, synth, dh, seed, W, M, D):
+    R = (W - 1) * (D + 1) + 1
+    q, poses = synth.nnf_reference(seed, 2 * R + 5, dh)
+    ids = O.lin_int_space(0, len(q) - 1, R)
+    counts = O.nnf_layer_counts(1, R, W, M)
+    ik = synth.nnf_ik_states(2, q[ids], counts)
+    return poses[ids], counts, ik
+
+
+def test_nnf_knn_takes_filter_path_and_matches_oracle(P, O, synth):
+    """findKnnNodes over >= 8192 IK nodes with Gaussian (not fp32-representable) states: the device takes
+    K1's tensor-core filter path; choices must still equal the oracle's full-sort findKnnNodes."""
+    dh, link, xyzr = synth.default_arm()
+    gw = P.World(dh, link, xyzr, np.zeros((0, 4)), np.zeros((0, 6)))
+    ow = O.World(dh, link, xyzr, np.zeros((0, 4)), np.zeros((0, 6)))
+    W, M, k, D = 80, 128, 5, 1
+    ref, counts, ik = _problem(O, synth, dh, 6, W, M, D)
+    assert len(ik) == 10240 and not np.array_equal(ik, ik.astype(np.float32).astype(np.float64))
+    g = P.Nnf(gw, ref, counts, ik, num_nn=k, discretization=D)
+    stats = g.knn_stats()
+    assert stats["filter_calls"] >= 1, stats            # the interior index (9984 nodes) was filtered
+    o = O.nnf_run(ow, ref, counts, ik, k=k, D=D, max_lazy_iters=0, nthreads=8)
+    assert np.array_equal(g.knn(), o["knn"])
+    st, po = g.vertices()
+    assert np.array_equal(st, o["states"]) and np.allclose(po, o["pose"], rtol=0, atol=1e-12)
+    # and the first search's cost against the independent reachability check
+    r = g.solve(max_lazy_iters=1)
+    ed, _ = g.edges()
+    c = r["goal_cost_trace"][0]
+    assert O.nnf_reachable(ref, po, ed, c) and not O.nnf_reachable(ref, po, ed, c, strict=True)
+
+
+def test_nnf_full_size_costs_vs_independent_reachability(P, O, synth, world_arrays):
+    """BASELINE configs[3]: W=200 waypoints, M=1024 IK samples per layer, 7-DOF arm (k=5, D=1): 399 x 1.2e6
+    tensor-product cells.  The device's first-search cost and LazySP's final cost must be exactly the
+    thresholds at which the goal becomes reachable (independent algorithm, no DP recurrence); every
+    knocked-out edge must collide and every path edge be free under the specification's evaluateEdge."""
+    dh, link, xyzr, sph, box = world_arrays
+    gw = P.World(dh, link, xyzr, sph, box)
+    ow = O.World(dh, link, xyzr, sph, box)
+    W, M, k, D = 200, 1024, 5, 1
+    ref, counts, ik = _problem(O, synth, dh, 4, W, M, D)
+    g = P.Nnf(gw, ref, counts, ik, num_nn=k, discretization=D)
+    assert g.n_ik == W * M and g.knn_stats()["filter_calls"] >= 1
+    st, po = g.vertices()
+    ed, _ = g.edges()
+    r = g.solve(max_lazy_iters=20000)
+    first = r["goal_cost_trace"][0]
+    assert O.nnf_reachable(ref, po, ed, first) and not O.nnf_reachable(ref, po, ed, first, strict=True)
+    _, fl = g.edges()
+    blocked = (fl & 2) != 0
+    assert blocked.sum() == r["n_collisions"] and ((fl & 1) != 0).sum() == r["n_evaluated"]
+    if r["solved"]:
+        final = r["goal_cost"]
+        assert O.nnf_reachable(ref, po, ed, final, blocked=blocked)
+        assert not O.nnf_reachable(ref, po, ed, final, strict=True, blocked=blocked)
+        path = r["path"].astype(np.int64)
+        ok, clear, _ = ow.check_motion_batch(st[path[:-1]], st[path[1:]], 0.05, mode=1, nthreads=8)
+        assert np.all((ok == 1) | (np.abs(clear) < 1e-6))
+        assert G.coupling_cost(ref, po, path) == final
+    b = np.where(blocked)[0]
+    ok, clear, _ = ow.check_motion_batch(st[ed[b, 0]], st[ed[b, 1]], 0.05, mode=1, nthreads=8)
+    assert np.all((ok == 0) | (np.abs(clear) < 1e-6))

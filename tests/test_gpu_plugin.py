@@ -95,3 +95,100 @@ def test_nnfrechet_planner_matches_oracle(O, synth, world_arrays):
         if o["solved"]:
             assert abs(g["final_error"] - o["final_error"]) <= 1e-5 * o["final_error"]
             assert np.array_equal(g["path_states"], o["states"][o["path"]])
+
+
+# ---- Drop-in A: the reference's own RRTConnect.cpp (unmodified) over the GPU interfaces ----------------
+
+@pytest.fixture(scope="module")
+def dropin_world(world_arrays):
+    import plugin_lib
+    L = plugin_lib.dropin()
+    if L is None:
+        pytest.skip("oracle/_ref/libdropin_a.so not built (needs /root/reference at build time)")
+    return plugin_lib.PluginWorld(*world_arrays, library=L)
+
+
+@pytest.mark.parametrize("nn_path", [0, 1])
+def test_dropin_a_reference_planner_over_gpu_interfaces(dropin_world, nn_path):
+    """pr_ompl::RRTConnect exactly as shipped by the reference, with GpuNearestNeighbors<Motion*> obtained
+    from SelfConfig::getDefaultNearestNeighbors (nn_path 0) or setNearestNeighbors<NN>() (nn_path 1) and the
+    GPU validity checker / motion validator underneath, reproduces the golden trees recorded from the same
+    source over the CPU defaults."""
+    import plugin_lib
+    plugin_lib.dropin().dropin_set_nn_path(nn_path)
+    g = np.load(os.path.join(HERE, "golden", "rrtc_golden.npz"))
+    for qi in range(8):
+        for ext in EXTS:
+            for rng in ((0.0, 0.9) if nn_path == 0 else (0.9,)):
+                r, pd = dropin_world.rrtc_solve(g["starts"][qi], g["goals"][qi], -np.pi, np.pi, rng=rng,
+                                                extension_type=ext, seed=11, query=qi, max_iters=400)
+                key = "q%d_%s_r%s" % (qi, ext, rng)
+                ref = dict(status=int(g[key + "_meta"][0]), iterations=int(g[key + "_meta"][1]),
+                           start_parent=g[key + "_sp"], goal_parent=g[key + "_gp"], start_states=g[key + "_ss"],
+                           goal_states=g[key + "_gs"], path=g[key + "_path"])
+                assert _same(r, ref), key
+    plugin_lib.dropin().dropin_set_nn_path(0)
+
+
+def test_dropin_a_single_planner_rate_is_reported(dropin_world, oracle_world, synth):
+    """One planner instance = one launch + sync per growTree: state the rate instead of hiding it."""
+    q = synth.cloud(4, 400)
+    v, _ = oracle_world.is_valid_batch(q, 8)
+    qv = q[v == 1]
+    starts, goals = qv[0:32:2], qv[1:32:2]
+    sec, solved, iters = dropin_world.rrtc_bench(starts, goals, -np.pi, np.pi, max_iters=200)
+    assert sec > 0 and iters >= len(starts)
+    print("drop-in A: %.1f plans/s, %.0f us per sample, %d/%d solved" %
+          (len(starts) / sec, 1e6 * sec / iters, solved, len(starts)))
+
+
+@pytest.mark.parametrize("which", ["plugin", "dropin"])
+def test_second_solve_resumes_and_clear_restarts(which, plugin_world, world_arrays, oracle_world, synth):
+    """SURVEY §8(f)1 (semantics pinned on the reference in tests/test_oracle.py::
+    test_reference_resume_and_clear_semantics): a second solve() continues the device-resident trees; clear()
+    empties them (prgpu_knn_clear) and the next solve() equals a fresh planner's."""
+    import plugin_lib
+    if which == "dropin":
+        if plugin_lib.dropin() is None:
+            pytest.skip("oracle/_ref/libdropin_a.so not built")
+        w = plugin_lib.PluginWorld(*world_arrays, library=plugin_lib.dropin())
+    else:
+        w = plugin_world
+    q = synth.cloud(91, 200)
+    v, _ = oracle_world.is_valid_batch(q, 8)
+    qv = q[v == 1]
+    try:
+        for i in range(3):
+            for ext, code in (("ext-con", (0, 1)), ("con-con", (1, 1))):
+                single = oracle_world.rrtc_solve(qv[2 * i], qv[2 * i + 1], -np.pi, np.pi, rng=0.6, ext=code, seed=2,
+                                                 query=i, max_iters=120)
+                for first, clear in ((2, False), (40, False), (30, True)):
+                    w.set_two_phase(first, clear)
+                    r, pd = w.rrtc_solve(qv[2 * i], qv[2 * i + 1], -np.pi, np.pi, rng=0.6, extension_type=ext, seed=2,
+                                         query=i, max_iters=120)
+                    assert _same(r, single), (which, i, ext, first, clear)
+                    n = len(single["start_parent"]) + len(single["goal_parent"])
+                    assert pd[0] == n            # getPlannerData after the second solve: every node once
+    finally:
+        w.set_two_phase(0, False)
+
+
+def test_batched_planner_class_through_plugin_library(plugin_world, oracle_world, synth):
+    """pr_gpu::BatchedRRTConnect (plugin/pr_gpu/BatchedRRTConnect.h) through libprgpu_plugin.so: every query
+    equals what one reference planner instance does with CounterSampler(seed, base + i)."""
+    q = synth.cloud(4, 600)
+    v, _ = oracle_world.is_valid_batch(q, 8)
+    qv = q[v == 1]
+    n = 48
+    starts, goals = qv[0:2 * n:2], qv[1:2 * n:2]
+    for ext, code in (("ext-con", (0, 1)), ("con-ext", (1, 0))):
+        b = plugin_world.batched_rrtc_solve(starts, goals, -np.pi, np.pi, rng=0.0, extension_type=ext, seed=5,
+                                            query_base=100, max_iters=300)
+        for i in range(n):
+            o = oracle_world.rrtc_solve(starts[i], goals[i], -np.pi, np.pi, rng=0.0, ext=code, seed=5, query=100 + i,
+                                        max_iters=300)
+            assert (b["status"][i], b["iterations"][i]) == (o["status"], o["iterations"]), (ext, i)
+            assert (b["n_start"][i], b["n_goal"][i]) == (len(o["start_parent"]), len(o["goal_parent"]))
+            assert np.array_equal(b["paths"][i], o["path"]), (ext, i)
+    with pytest.raises(RuntimeError):
+        plugin_world.batched_rrtc_solve(starts[:2], goals[:2], -np.pi, np.pi, extension_type="bad")

@@ -158,3 +158,31 @@ def test_rrtconnect_invalid_endpoints(O, synth, oracle_world):
     assert r["status"] == 4 and len(r["goal_parent"]) == 0               # goal never sampled -> TIMEOUT
     r = oracle_world.rrtc_solve(good[0], good[0], -np.pi, np.pi, max_iters=50, impl="port")
     assert r["status"] == 6                                              # start == goal connects at once
+
+
+def test_reference_resume_and_clear_semantics(O, synth, oracle_world):
+    """What the GPU planner classes are held to, established on the reference itself: a second
+    solve() continues the existing trees -- identical to one uninterrupted solve when the first stopped after
+    an even number of samples (the tree alternation restarts with the start tree, RRTConnect.cpp:263-268) --
+    and clear() + setup() + solve() equals a fresh planner (RRTConnect.cpp:166-176)."""
+    ref = O.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    q = synth.cloud(91, 200)
+    v, _ = oracle_world.is_valid_batch(q, 8)
+    qv = q[v == 1]
+    try:
+        for i in range(4):
+            for ext in ((0, 1), (1, 1)):
+                kw = dict(rng=0.6, ext=ext, seed=2, query=i, max_iters=120, impl="ref")
+                ref.ref_set_two_phase(0, 0)
+                single = oracle_world.rrtc_solve(qv[2 * i], qv[2 * i + 1], -np.pi, np.pi, **kw)
+                for first in (2, 10, 40):
+                    ref.ref_set_two_phase(first, 0)
+                    resumed = oracle_world.rrtc_solve(qv[2 * i], qv[2 * i + 1], -np.pi, np.pi, **kw)
+                    assert all(np.array_equal(single[k], resumed[k]) for k in single), (i, ext, first)
+                ref.ref_set_two_phase(30, 1)
+                cleared = oracle_world.rrtc_solve(qv[2 * i], qv[2 * i + 1], -np.pi, np.pi, **kw)
+                assert all(np.array_equal(single[k], cleared[k]) for k in single), (i, ext, "clear")
+    finally:
+        ref.ref_set_two_phase(0, 0)

@@ -110,3 +110,19 @@ def test_reference_random_problems_vs_port(O, synth):
         assert np.array_equal(r["pose"], o["pose"])
         assert f["goal_cost"] == o["goal_cost_trace"][0]
         assert (r["solved"], r["goal_cost"]) == (o["solved"], o["goal_cost"])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_reachability_check_agrees_with_reference_costs(O, name):
+    """orc_nnf_reachable (used for the full-size GPU test) brackets the reference's own costs exactly."""
+    c = CASES[name]
+    first = float(c["first_goal_cost"])
+    assert O.nnf_reachable(c["ref_sub"], c["pose"], c["edges"], first)
+    assert not O.nnf_reachable(c["ref_sub"], c["pose"], c["edges"], first, strict=True)
+    blocked = (c["edge_flags_order_dependent"] & 2) != 0
+    final = float(c["goal_cost"])
+    if int(c["solved"]):
+        assert O.nnf_reachable(c["ref_sub"], c["pose"], c["edges"], final, blocked=blocked)
+        assert not O.nnf_reachable(c["ref_sub"], c["pose"], c["edges"], final, strict=True, blocked=blocked)
+    else:
+        assert not O.nnf_reachable(c["ref_sub"], c["pose"], c["edges"], 1e300, blocked=blocked)
