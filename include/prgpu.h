@@ -243,6 +243,14 @@ int prgpu_nnf_band_info(prgpu_nnf_t *h, double *tau, uint64_t *cells, uint32_t *
 /* duration of the latest search kernel (measurement aid, always on) */
 int prgpu_nnf_last_dp_ms(prgpu_nnf_t *h, float *ms);
 
+/* ------------------------------------------------------------------------------------
+ * Measurement aids (no counterpart in the reference)
+ * ---------------------------------------------------------------------------------- */
+/* kernels launched by this library in this process so far */
+uint64_t prgpu_diag_launch_count(void);
+/* live micro-benchmark: issue peak of mma.sync.m16n8k8 TF32 (the instruction K1's scan uses), TFLOP/s */
+int prgpu_diag_mma_tf32_peak(int device, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ SIGNATURES = {
     "prgpu_rrtc_batch_summary": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "prgpu_rrtc_batch_fetch": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, c_vp, c_vp, C.POINTER(C.c_uint32),
                                          c_vp, C.c_uint32]),
+    "prgpu_diag_launch_count": (C.c_uint64, []),
+    "prgpu_diag_mma_tf32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "prgpu_nnf_create": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
     "prgpu_nnf_destroy": (C.c_int, [c_vp]),
     "prgpu_nnf_graph_info": (C.c_int, [c_vp, c_u32p, c_u32p, c_u32p]),

@@ -17,7 +17,7 @@ int fail(int code, const std::string &msg) {
   return code;
 }
 
-static int select_device(int device, int *sm_count) {
+int select_device(int device, int *sm_count) {
   // cudaGetDeviceProperties costs milliseconds: query each device once
   static int cached_count = -1;
   static int cached_major[64], cached_minor[64], cached_sms[64];

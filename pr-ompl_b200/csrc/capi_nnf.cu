@@ -709,7 +709,7 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
           h->blocked[eid] = 1;
           ++h->n_collisions;
           nnf_block_edge_kernel<<<1, 1, 0, s>>>(h->d_edge.as<NnfEdgeRec>(), h->slot_of_eid[eid],
-                                                h->d_blocked.as<uint8_t>(), eid);
+                                                h->d_blocked.as<uint8_t>(), eid); PRGPU_COUNT_LAUNCH(1);
           PRGPU_CUDA_TRY(cudaGetLastError());
           h->dirty_level = std::min(h->dirty_level, h->level_of_vertex[h->edges[eid].second]);
           collisionFree = false;

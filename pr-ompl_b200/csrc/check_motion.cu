@@ -531,13 +531,13 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
         PRGPU_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PRGPU_CUDA_TRY(cudaMemsetAsync(scratch->queue_n, 0, sizeof(uint32_t), stream));
         ka<<<blocks_a, CM_THREADS, smem, stream>>>(w_dev, fa, tb, m, resolution, mode, check_first, vd, scratch->owed,
-                                                   scratch->gaps, scratch->queue, scratch->queue_n);
+                                                   scratch->gaps, scratch->queue, scratch->queue_n); PRGPU_COUNT_LAUNCH(1);
         kr<<<blocks_b, CM_THREADS, smem, stream>>>(w_dev, fa, tb, resolution, mode, check_first, vd, scratch->queue,
-                                                   scratch->queue_n);
+                                                   scratch->queue_n); PRGPU_COUNT_LAUNCH(1);
         cm_gaps_kernel<<<(unsigned)(((uint64_t)m * 8 + CM_THREADS - 1) / CM_THREADS), CM_THREADS, 0, stream>>>(
-            m, mode, vd, scratch->owed, scratch->gaps);
+            m, mode, vd, scratch->owed, scratch->gaps); PRGPU_COUNT_LAUNCH(1);
         size_t tb2 = scratch->tmp_bytes;
-        PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scratch->tmp, tb2, scratch->owed, scratch->off, (int)m, stream));
+        PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scratch->tmp, tb2, scratch->owed, scratch->off, (int)m, stream)); PRGPU_COUNT_LAUNCH(2);
         // number of owed states (one small read-back per pass sizes the item table and the grid)
         uint32_t last_off = 0, last_owed = 0;
         PRGPU_CUDA_TRY(cudaMemcpyAsync(&last_off, scratch->off + (m - 1), 4, cudaMemcpyDeviceToHost, stream));
@@ -555,10 +555,10 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
           }
           uint32_t *item_p = scratch->item_edge + scratch->item_cap;
           cm_expand_kernel<<<(m + 255) / 256, 256, 0, stream>>>(m, scratch->owed, scratch->off, scratch->gaps,
-                                                                scratch->item_edge, item_p);
+                                                                scratch->item_edge, item_p); PRGPU_COUNT_LAUNCH(1);
           const unsigned nb = (unsigned)std::min<uint64_t>(((uint64_t)total + CM_THREADS - 1) / CM_THREADS, blocks_b);
           kb<<<nb, CM_THREADS, smem, stream>>>(w_dev, fa, tb, total, resolution, mode, check_first, vd,
-                                               scratch->item_edge, item_p);
+                                               scratch->item_edge, item_p); PRGPU_COUNT_LAUNCH(1);
         }
       });
       PRGPU_CUDA_TRY(cudaGetLastError());
@@ -583,7 +583,7 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
     auto kern = check_motion_kernel<SP>;
     PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, CM_THREADS, smem, stream>>>(w_dev, from_dev, to_dev, n, resolution, mode,
-                                                         check_first, valid_dev);
+                                                         check_first, valid_dev); PRGPU_COUNT_LAUNCH(1);
   });
   if (timer)
     timer->end(stream);
@@ -596,7 +596,7 @@ int dfield_build_launch(const double *os_d, int n_os, const double *ob_d, int n_
   const size_t ncell = (size_t)n3[0] * n3[1] * n3[2];
   dfield_build_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, stream>>>(os_d, n_os, ob_d, n_ob, n3[0], n3[1], n3[2],
                                                                           org[0], org[1], org[2], cell, slack, cap,
-                                                                          df_dev);
+                                                                          df_dev); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
@@ -612,7 +612,7 @@ int is_valid_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double
   PRGPU_SP_DISPATCH(w.S, {
     auto kern = is_valid_kernel<SP>;
     PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)blocks, CM_THREADS, smem, stream>>>(w_dev, q_dev, n, valid_dev);
+    kern<<<(unsigned)blocks, CM_THREADS, smem, stream>>>(w_dev, q_dev, n, valid_dev); PRGPU_COUNT_LAUNCH(1);
   });
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
@@ -621,7 +621,7 @@ int is_valid_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double
 int fk_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double *q_dev, uint64_t n, double *pose12_dev, cudaStream_t stream) {
   if (n == 0)
     return PRGPU_OK;
-  fk_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(w_dev, q_dev, n, pose12_dev);
+  fk_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(w_dev, q_dev, n, pose12_dev); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

@@ -11,6 +11,8 @@ namespace prgpu {
 // thread-local error text behind prgpu_last_error()
 void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
+// cudaSetDevice + "is this an sm_100 part" check shared by every create call (capi.cu)
+int select_device(int device, int *sm_count);
 
 #define PRGPU_CUDA_TRY(expr)                                                                       \
   do {                                                                                             \
@@ -19,6 +21,11 @@ int fail(int code, const std::string &msg);
       return ::prgpu::fail(_e == cudaErrorMemoryAllocation ? PRGPU_ENOMEM : PRGPU_ECUDA,           \
                            std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
   } while (0)
+
+// number of kernels this library has launched in this process (prgpu_diag_launch_count): bench.py's
+// gpu_launches is the difference of two readings around its timed region, not a constant
+extern unsigned long long g_launch_count;
+#define PRGPU_COUNT_LAUNCH(n) (::prgpu::g_launch_count += (n))
 
 // optional CUDA-event bracket around a handle's dominant kernel (bench.py's live roofline timing)
 struct KernelTimer {

@@ -392,7 +392,7 @@ int launch_tile(const double *pts, uint64_t stride, uint32_t n, uint32_t index_b
     auto kern = knn_tile_kernel<DIM, KONE, BCAST>;                                                 \
     PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, KNN_THREADS, smem, stream>>>(pts, stride, n, index_base, queries, nq, k, nsplit_log2, \
-                                              lo, tiles_per_chunk, od, oi);                        \
+                                              lo, tiles_per_chunk, od, oi); PRGPU_COUNT_LAUNCH(1);                        \
   } while (0)
   if (k == 1) {
     if (nsplit == 1)
@@ -439,7 +439,7 @@ int topk_merge(const uint32_t *idx_parts, const double *dist_parts, int nparts, 
   if (nq == 0)
     return PRGPU_OK;
   topk_merge_kernel<<<dim3((nq + 3) / 4, 1), 128, 0, stream>>>(idx_parts, dist_parts, nparts, MERGE_GROUP, nq,
-                                                              k, idx_out, dist_out);
+                                                              k, idx_out, dist_out); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
@@ -459,7 +459,7 @@ int merge_passes(KnnScratch &sc, int nparts, uint32_t nq, int k, uint32_t *idx_o
     uint32_t *di = into2 ? sc.part2_idx : sc.part_idx;
     double *dd = into2 ? sc.part2_dist : sc.part_dist;
     topk_merge_kernel<<<dim3((nq + 3) / 4, groups), 128, 0, stream>>>(si, sd, nparts, MERGE_GROUP, nq, k, di,
-                                                                   dd);
+                                                                   dd); PRGPU_COUNT_LAUNCH(1);
     PRGPU_CUDA_TRY(cudaGetLastError());
     si = di;
     sd = dd;
@@ -560,7 +560,7 @@ int knn_transpose_append(int dim, const double *aos_dev, uint64_t n_new, double 
   if (n_new == 0)
     return PRGPU_OK;
   transpose_append_kernel<<<(unsigned)((n_new + 255) / 256), 256, 0, stream>>>(aos_dev, n_new, dim, pts_soa, ptsf,
-                                                                            xmax2, stride, offset);
+                                                                            xmax2, stride, offset); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
@@ -569,7 +569,7 @@ int knn_gather_points(int dim, const double *pts_soa, uint64_t stride, uint64_t 
   if (n == 0)
     return PRGPU_OK;
   gather_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pts_soa, stride, first, n, dim,
-                                                                      aos_dev);
+                                                                      aos_dev); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

@@ -637,14 +637,14 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
     ch = (nsamp + tpc - 1) / tpc;
     samp<<<dim3(qblocks1, ch), FT_THREADS, smem1, stream>>>(t.ptsf, t.n, queries, nq, kp, lo, stride, tpc, seed,
                                                          ch > 1 ? sc.part_dist : sc.cand_dist,
-                                                         ch > 1 ? sc.part_idx : sc.cand_idx);
+                                                         ch > 1 ? sc.part_idx : sc.cand_idx); PRGPU_COUNT_LAUNCH(1);
     PRGPU_CUDA_TRY(cudaGetLastError());
     if (ch > 1) {
       const int mrc = merge_passes(sc, (int)ch, nq, kp, sc.cand_idx, sc.cand_dist, stream);
       if (mrc != PRGPU_OK)
         return mrc;
     }
-    knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, seed, out, zero_counts);
+    knn_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(sc.cand_dist, sc.cand_idx, nq, kp, seed, out, zero_counts); PRGPU_COUNT_LAUNCH(1);
     PRGPU_CUDA_TRY(cudaGetLastError());
     return PRGPU_OK;
   };
@@ -682,7 +682,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
       tm->begin(stream);
     coll<<<dim3(qblocks, chunks), FT_THREADS, smem2, stream>>>(t.ptsf + 8 * t.stride, t.ptsf + 16 * t.stride, t.n, queries,
                                                              nq, lo, thresh, tile_stride, tiles_per_chunk, cap, counts,
-                                                             cidx, ckey);
+                                                             cidx, ckey); PRGPU_COUNT_LAUNCH(1);
     if (tm)
       tm->end(stream);
     PRGPU_CUDA_TRY(cudaGetLastError());
@@ -693,7 +693,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
     // T_q = T_c + (kp-th smallest D)
     if ((rc = scan(sample_stride, nullptr)) != PRGPU_OK)
       return rc;
-    knn_sample_threshold_kernel<<<(nq * 32 + 255) / 256, 256, 0, stream>>>(nq, kp, cap, counts, ckey, thresh);
+    knn_sample_threshold_kernel<<<(nq * 32 + 255) / 256, 256, 0, stream>>>(nq, kp, cap, counts, ckey, thresh); PRGPU_COUNT_LAUNCH(1);
     PRGPU_CUDA_TRY(cudaGetLastError());
   } else {
     // small trees: the fp32 sampler seeded with T_c is cheaper than a second strided scan launch
@@ -707,7 +707,7 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   // ---- pass 3: exact re-rank of the candidates + proof ----
   auto sel = knn_select_kernel<DIM>;
   sel<<<nq, SEL_THREADS, 0, stream>>>(t.pts, t.ptsf, t.stride, t.index_base, t.xmax2, queries, thresh, cap, counts,
-                                     cidx, ckey, k, idx_out, dist_out, sc.flags);
+                                     cidx, ckey, k, idx_out, dist_out, sc.flags); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   ++sc.filter_calls;
 
@@ -733,14 +733,14 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
     sc.fb_capacity = cap;
   }
   gather_queries_kernel<<<(nflag + 127) / 128, 128, 0, stream>>>(queries, lo, DIM, sc.flags + 1, nflag, sc.fb_q,
-                                                                sc.fb_lo);
+                                                                sc.fb_lo); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   rc = knn_search_exact(DIM, t, sc.fb_q, nflag, k, lo ? sc.fb_lo : nullptr, sc.fb_idx, sc.fb_dist, sc, sm_count,
                         stream, nullptr);
   if (rc != PRGPU_OK)
     return rc;
   scatter_rows_kernel<<<(nflag * k + 127) / 128, 128, 0, stream>>>(sc.flags + 1, nflag, k, sc.fb_idx, sc.fb_dist,
-                                                                  idx_out, dist_out);
+                                                                  idx_out, dist_out); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

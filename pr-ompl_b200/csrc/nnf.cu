@@ -530,7 +530,7 @@ int nnf_subsample_launch(const DeviceWorld *w_dev, int dof, uint32_t n_new, uint
   if (n_new == 0)
     return PRGPU_OK;
   nnf_subsample_kernel<<<(n_new + 127) / 128, 128, 0, stream>>>(w_dev, dof, n_new, first_vertex, src, dst, step, D,
-                                                               states, pose12);
+                                                               states, pose12); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
@@ -539,7 +539,7 @@ int nnf_translations_launch(const double *pose12, const uint32_t *vertex_of_pos,
                             cudaStream_t stream) {
   if (n == 0)
     return PRGPU_OK;
-  nnf_translations_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose12, vertex_of_pos, n, out3);
+  nnf_translations_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose12, vertex_of_pos, n, out3); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
@@ -554,7 +554,7 @@ int nnf_dp_launch(const NnfGraphDev &g, int sm_count, cudaStream_t stream, Kerne
   void *args[] = {&arg};
   if (timer)
     timer->begin(stream);
-  PRGPU_CUDA_TRY(cudaLaunchCooperativeKernel((void *)nnf_dp_kernel, grid, block, args, 0, stream));
+  PRGPU_CUDA_TRY(cudaLaunchCooperativeKernel((void *)nnf_dp_kernel, grid, block, args, 0, stream)); PRGPU_COUNT_LAUNCH(1);
   if (timer)
     timer->end(stream);
   return PRGPU_OK;
@@ -563,14 +563,14 @@ int nnf_dp_launch(const NnfGraphDev &g, int sm_count, cudaStream_t stream, Kerne
 int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, unsigned long long *rowmin_bits,
                       cudaStream_t stream) {
   PRGPU_CUDA_TRY(cudaMemsetAsync(rowmin_bits, 0xFF, (size_t)R * sizeof(unsigned long long), stream));
-  nnf_rowmin_kernel<<<dim3((V + 255) / 256, R), 256, 0, stream>>>(R, V, pnn, pref, rowmin_bits);
+  nnf_rowmin_kernel<<<dim3((V + 255) / 256, R), 256, 0, stream>>>(R, V, pnn, pref, rowmin_bits); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
 
 int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, double tau, uint32_t *band_lo,
                     unsigned long long *band_w64, cudaStream_t stream) {
-  nnf_band_kernel<<<(V + 127) / 128, 128, 0, stream>>>(R, V, pnn, pref, tau, band_lo, band_w64);
+  nnf_band_kernel<<<(V + 127) / 128, 128, 0, stream>>>(R, V, pnn, pref, tau, band_lo, band_w64); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
@@ -581,14 +581,14 @@ int nnf_band_pack_launch(uint32_t V, uint32_t E, const uint32_t *band_lo, const 
                          cudaStream_t stream) {
   (void)E;
   nnf_band_pack_kernel<<<(V + 127) / 128, 128, 0, stream>>>(V, band_lo, band_w64, col_off, pred_off, pred_pos,
-                                                            pred_eid, blocked, meta, edge);
+                                                            pred_eid, blocked, meta, edge); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
 
 int nnf_exclusive_scan_u64(const unsigned long long *in, unsigned long long *out, uint32_t n, void *temp,
                            size_t &temp_bytes, cudaStream_t stream) {
-  PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, stream));
+  PRGPU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, stream)); if (temp) PRGPU_COUNT_LAUNCH(2);
   return PRGPU_OK;
 }
 
@@ -628,7 +628,7 @@ int nnf_band_dp_launch(const NnfBandDev &g, uint32_t first_level, cudaStream_t s
   cfg.numAttrs = 1;
   if (timer)
     timer->begin(stream);
-  PRGPU_CUDA_TRY(cudaLaunchKernelEx(&cfg, nnf_band_dp_kernel, g, first_level));
+  PRGPU_CUDA_TRY(cudaLaunchKernelEx(&cfg, nnf_band_dp_kernel, g, first_level)); PRGPU_COUNT_LAUNCH(1);
   if (timer)
     timer->end(stream);
   return PRGPU_OK;
@@ -648,7 +648,7 @@ int nnf_flow_dp_launch(const NnfBandDev &g, uint32_t first_pos, uint32_t epoch, 
   if (timer)
     timer->begin(stream);
   // cooperative launch: guarantees that all blocks are co-resident (warps wait on one another's flags)
-  PRGPU_CUDA_TRY(cudaLaunchCooperativeKernel((void *)nnf_flow_dp_kernel, grid, block, args, 0, stream));
+  PRGPU_CUDA_TRY(cudaLaunchCooperativeKernel((void *)nnf_flow_dp_kernel, grid, block, args, 0, stream)); PRGPU_COUNT_LAUNCH(1);
   if (timer)
     timer->end(stream);
   return PRGPU_OK;
@@ -656,14 +656,14 @@ int nnf_flow_dp_launch(const NnfBandDev &g, uint32_t first_pos, uint32_t epoch, 
 
 int nnf_band_backtrack_launch(const NnfBandDev &g, uint32_t *out_path, uint32_t cap_pairs, uint32_t *out_n,
                               double *out_cost, cudaStream_t stream) {
-  nnf_band_backtrack_kernel<<<1, 32, 0, stream>>>(g, out_path, cap_pairs, out_n, out_cost);
+  nnf_band_backtrack_kernel<<<1, 32, 0, stream>>>(g, out_path, cap_pairs, out_n, out_cost); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
 
 int nnf_backtrack_launch(const NnfGraphDev &g, uint32_t *out_path, uint32_t cap_pairs, uint32_t *out_n,
                          double *out_cost, cudaStream_t stream) {
-  nnf_backtrack_kernel<<<1, 32, 0, stream>>>(g, out_path, cap_pairs, out_n, out_cost);
+  nnf_backtrack_kernel<<<1, 32, 0, stream>>>(g, out_path, cap_pairs, out_n, out_cost); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

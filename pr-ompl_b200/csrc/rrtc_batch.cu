@@ -721,10 +721,10 @@ int rrtc_batch_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const Rrtc
     PRGPU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, team, RB_THREADS, smem)); \
     const unsigned blocks = (unsigned)std::min<uint64_t>((n_queries + RB_WARPS - 1) / RB_WARPS,    \
                                                          (uint64_t)std::max(per_sm, 1) * sm_count); \
-    kern<<<blocks, RB_THREADS, smem, stream>>>(w_dev, p, b, n_queries);                            \
+    kern<<<blocks, RB_THREADS, smem, stream>>>(w_dev, p, b, n_queries); PRGPU_COUNT_LAUNCH(1);                            \
     const unsigned tblocks =                                                                       \
         (unsigned)std::min<uint64_t>(n_queries, (uint64_t)std::max(per_sm_t, 1) * sm_count);       \
-    team<<<tblocks, RB_THREADS, smem, stream>>>(w_dev, p, b);                                      \
+    team<<<tblocks, RB_THREADS, smem, stream>>>(w_dev, p, b); PRGPU_COUNT_LAUNCH(1);                                      \
   } while (0)
   if (w.grid_n[0] > 0)
     PRGPU_RB_LAUNCH(0);
