@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native pr-ompl hot path.
+"""bench.py -- benchmark of the B200-native pr-ompl hot path (BASELINE.json: "validated edges/s, kNN
+queries/s, plans/s at 1/2/4/8 B200 vs host-CPU OMPL").
 
-Default workload (BASELINE.json configs[1], "batched kNN sweep"): one tree of 10^7 7-DOF
-nodes, 4096 queries, k=16.  A step is one pass of the hot path over that batch:
-  ours       : prgpu_knn_nearest_k_device (search kernel + partial-list merge kernel); with
-               --gpus N the tree is node-sharded over the ranks and a step also contains the NCCL
-               all-gather of the per-shard top-k candidates and the merge kernel (strong scaling).
-  reference  : (--impl reference) the CPU linear-scan NearestNeighbors the reference would use
-               (oracle port: the reference's own NN code lives in un-vendored OMPL), all host
-               threads, on a bounded sample of the same queries against the same tree.
-Other BASELINE configs are reachable with --workload check_motion (10^6 edges, 0.01 rad, 256
-obstacles) and --workload rrtc (4096 independent RRTConnect queries, split over the GPUs); a
-short pass of both is also reported under "extra" of the default run.  Prints ONE JSON line
-(rank 0).
+Headline line (the default, `--workload knn`): BASELINE.json configs[1], the batched kNN sweep -- one tree
+of 10^7 7-DOF nodes, 4096 queries, k=16.  A step is one pass of the hot path over that batch:
+  ours       : prgpu_knn_nearest_k_device; with --gpus N the tree is node-sharded over the ranks and a step
+               also contains the all-gather of the per-shard top-k candidates and the merge kernel
+               (strong scaling).
+  reference  : (--impl reference) the CPU nearest-neighbour structure the reference would use -- a k-d tree
+               with NearestNeighborsLinear's answers (oracle/kdtree.cpp; OMPL's GNAT is un-vendored), all
+               host threads, on a bounded sample of the same queries against the same tree.
+The default run ALSO measures the other two metrics BASELINE.json names, each as a complete block under
+`extra` (value, e2e, roofline, cpu_baseline at N=1), split over the ranks when --gpus N:
+  extra.check_motion : configs[2], 10^6 edges at 0.01 rad, 256 obstacles   (validated edges/s)
+  extra.rrtc         : configs[4], 4096 independent RRTConnect queries     (plans/s)
+and at N=1 extra.nnf (configs[3], W=200 / M=1024) and extra.dropin_a (one planner instance at a time through
+the unmodified reference planner source: the latency-bound path, stated rather than hidden).
+`--workload check_motion|rrtc|nnf` makes one of those the headline line instead.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -46,6 +50,28 @@ def parse():
     return ap.parse_args()
 
 
+# ------------------------------------------------------------------------------------------------
+# workload names: ONE place, so that our arm and the reference arm print identical config.workload
+# ------------------------------------------------------------------------------------------------
+def workload_string(args, wl):
+    if wl == "knn":
+        return (f"batched kNN sweep: N={args.nodes} nodes, 7-DOF, Q={args.queries}, k={args.k} "
+                f"(BASELINE.json configs[1])")
+    if wl == "check_motion":
+        return (f"batched checkMotion: {args.edges} edges at 0.01 rad, 7-DOF sphere-FK arm (16 link spheres) vs "
+                f"256 obstacles (BASELINE.json configs[2]); edge length ~U(0,1] rad")
+    if wl == "rrtc":
+        return (f"{args.plans} independent RRTConnect queries (ext-con, default range, 0.01 resolution), 7-DOF "
+                f"sphere-FK arm vs 256 obstacles, <= {args.plan_iters} samples each (BASELINE.json configs[4], "
+                f"query-sharded)")
+    return ("NNF Frechet following: W=200 waypoints, 1024 IK samples per layer, k=5, D=1, 7-DOF arm, 32 obstacles "
+            "(BASELINE.json configs[3])")
+
+
+METRICS = {"knn": ("kNN queries/s", "queries/s"), "check_motion": ("validated edges/s", "edges/s"),
+           "rrtc": ("RRTConnect plans/s", "plans/s"), "nnf": ("NNF plans/s", "plans/s")}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -65,13 +91,25 @@ def tensor_peak():
         return 2250.0, "fallback (B200_PROFILING.md nominal dense bf16)"
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full summary, else None."""
+def ncu_summary(kernel):
+    """Per-launch ncu figures of `kernel` from the committed `ncu --set full` summary (profiles/ncu_summary.json,
+    written by scripts/ncu_summary.py): dram bytes, issue-slot utilisation, lanes per instruction.  These come
+    from a profiler run of the same command, never from this run."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
             return json.load(f).get(kernel)
     except Exception:
         return None
+
+
+def ncu_traffic(kernels):
+    total, seen = 0, False
+    for k in kernels:
+        s = ncu_summary(k)
+        if s and s.get("dram_bytes") is not None:
+            total += int(s["dram_bytes"])
+            seen = True
+    return total if seen else None
 
 
 class ClockSampler:
@@ -131,86 +169,6 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-# --------------------------------------------------------------------------------------------
-# reference arm: the CPU implementation the reference would run, on the box's host cores
-# --------------------------------------------------------------------------------------------
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    import numpy as np
-    import oracle_lib as O
-    import prgpu_loader
-    synth = prgpu_loader.load().synth
-    O.build()
-    cores = host_cores()
-    if args.workload == "knn":
-        pts = synth.cloud(0, args.nodes)
-        q = synth.cloud(1, args.queries)
-        per_step = min(args.queries, 8 * cores)
-        def step(i):
-            lo = (i * per_step) % max(1, args.queries - per_step + 1)
-            O.knn(pts, q[lo:lo + per_step], args.k, nthreads=cores)
-        units, unit, metric = per_step, "queries/s", "kNN queries/s"
-        sample = (f"{per_step} of the {args.queries} queries per step against the full {args.nodes}-node "
-                  f"tree, k={args.k}, linear scan (NearestNeighborsLinear semantics), {cores} threads")
-        config = {"workload": f"batched kNN sweep: N={args.nodes} nodes, 7-DOF, Q={args.queries}, k={args.k}"}
-    elif args.workload == "rrtc":
-        from concurrent.futures import ThreadPoolExecutor
-        dh, link, xyzr = synth.default_arm()
-        sph, box = synth.obstacles(3)
-        W = O.World(dh, link, xyzr, sph, box)
-        starts, goals = plan_problems(synth, W, args.plans)
-        impl = "ref" if O.ref() is not None else "port"
-        per_step = min(args.plans, 16 * cores)
-        pool = ThreadPoolExecutor(cores)
-        def one(qi):
-            return W.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=(0, 1), seed=4, query=qi,
-                                max_iters=args.plan_iters, max_nodes=4096, impl=impl)["status"]
-        def step(i):
-            lo = (i * per_step) % max(1, args.plans - per_step + 1)
-            list(pool.map(one, range(lo, lo + per_step)))
-        units, unit, metric = per_step, "plans/s", "RRTConnect plans/s"
-        sample = (f"{per_step} of the {args.plans} queries per step, one query per thread, "
-                  + ("the reference's own pr_ompl/src/RRTConnect.cpp over the OMPL-API stand-in (oracle/_ref)"
-                     if impl == "ref" else "oracle port of RRTConnect.cpp") + f", {cores} threads")
-        config = {"workload": f"{args.plans} independent RRTConnect queries (ext-con), 7-DOF, 256 obstacles, "
-                              f"<= {args.plan_iters} samples each"}
-        kind = "reference" if impl == "ref" else "port"
-    else:
-        dh, link, xyzr = synth.default_arm()
-        sph, box = synth.obstacles(3)
-        W = O.World(dh, link, xyzr, sph, box)
-        a, b = synth.edges(2, args.edges)
-        per_step = min(args.edges, 1500 * cores)
-        def step(i):
-            lo = (i * per_step) % max(1, args.edges - per_step + 1)
-            W.check_motion_batch(a[lo:lo + per_step], b[lo:lo + per_step], 0.01, want_clearance=False,
-                                 nthreads=cores)
-        units, unit, metric = per_step, "edges/s", "validated edges/s"
-        sample = (f"{per_step} of the {args.edges} edges per step, DiscreteMotionValidator bisection with "
-                  f"early exit over the double-precision synthetic checker, {cores} threads")
-        config = {"workload": f"batched checkMotion: {args.edges} edges, 0.01 rad, 7-DOF sphere-FK arm vs "
-                              f"256 obstacles"}
-    for i in range(args.warmup):
-        step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    dt = time.perf_counter() - t0
-    value = units * args.steps / dt
-    line = {
-        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config,
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores,
-                         "kind": kind if args.workload == "rrtc" else "port", "sample": sample},
-        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    emit_json(line)
-
-
 def plan_problems(synth, world, n, seed=4):
     """n valid (start, goal) pairs: BASELINE 'independent RRTConnect queries', seed 4.  `world` is any
     object with is_valid_batch (the device world in our arm, the oracle world in the reference arm)."""
@@ -222,297 +180,407 @@ def plan_problems(synth, world, n, seed=4):
     return np.ascontiguousarray(qv[0:2 * n:2]), np.ascontiguousarray(qv[1:2 * n:2])
 
 
-# --------------------------------------------------------------------------------------------
-# our arm
-# --------------------------------------------------------------------------------------------
-def run_ours(args, rank, local_rank, world):
-    import numpy as np
-    import torch
+def nnf_problem(synth, dh, W, M, D, tseed=5, pseed=1):
+    """NNF config of BASELINE.json: W waypoints, M IK samples per layer; the IK budget per waypoint is the
+    reference's own multinomial (std::default_random_engine draws, NNFrechet.cpp:310-343, restated in
+    synth); synthetic IK = trajectory configuration + N(0, 0.15^2) joint noise."""
+    R = (W - 1) * (D + 1) + 1
+    q, poses = synth.nnf_reference(tseed, 2 * R + 5, dh)
+    ids = synth.lin_int_space(0, len(q) - 1, R)
+    counts = synth.nnf_layer_counts(pseed, R, W, M)
+    ik = synth.nnf_ik_states(2, q[ids], counts)
+    return poses, poses[ids], counts, ik
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baselines (the oracle / compiled reference as the thing timed -- allowed in this leg only)
+# ------------------------------------------------------------------------------------------------
+class CpuArm:
+    """The reference's CPU implementation of one workload on this box's host cores.  prepare() builds the
+    state that our arm also keeps outside its timed region (the tree / the world); run(lo, n) processes
+    units [lo, lo+n) and returns nothing."""
+
+    def __init__(self, args, wl, synth):
+        import numpy as np
+        import oracle_lib as O
+        O.build()
+        self.O, self.np, self.args, self.wl = O, np, args, wl
+        self.cores = host_cores()
+        self.extra = {}
+        if wl == "knn":
+            self.pts = synth.cloud(0, args.nodes)
+            self.q = synth.cloud(1, args.queries)
+            t0 = time.perf_counter()
+            self.tree = O.KdTree(self.pts)
+            self.extra["kdtree_build_s"] = time.perf_counter() - t0
+            self.total = args.queries
+            self.kind = "port"
+            self.what = ("k-d tree with NearestNeighborsLinear's answers, bit for bit (oracle/kdtree.cpp; the reference "
+                         "takes OMPL's GNAT from SelfConfig::getDefaultNearestNeighbors, pr_ompl/src/RRTConnect.cpp:"
+                         "131-134, un-vendored); tree built once outside the timed region like the device tree")
+        else:
+            dh, link, xyzr = synth.default_arm()
+            sph, box = synth.obstacles(3)
+            self.W = O.World(dh, link, xyzr, sph, box)
+            if wl == "rrtc":
+                from concurrent.futures import ThreadPoolExecutor
+                self.starts, self.goals = plan_problems(synth, self.W, args.plans)
+                self.impl = "ref" if O.ref() is not None else "port"
+                self.pool = ThreadPoolExecutor(self.cores)
+                self.total = args.plans
+                self.kind = "reference" if self.impl == "ref" else "port"
+                self.what = ("one query per thread, " +
+                             ("the reference's own pr_ompl/src/RRTConnect.cpp compiled unmodified over the OMPL-API "
+                              "stand-in with NearestNeighborsLinear + DiscreteMotionValidator (oracle/_ref)"
+                              if self.impl == "ref" else "oracle port of RRTConnect.cpp"))
+            else:
+                self.a, self.b = synth.edges(2, args.edges)
+                self.total = args.edges
+                self.kind = "port"
+                self.what = ("DiscreteMotionValidator bisection with early exit over the double-precision synthetic "
+                             "checker, threads over edges")
+
+    def run(self, lo, n):
+        O, a = self.O, self.args
+        if self.wl == "knn":
+            self.tree.knn(self.q[lo:lo + n], a.k, nthreads=self.cores)
+        elif self.wl == "rrtc":
+            np = self.np
+
+            def one(qi):
+                return self.W.rrtc_solve(self.starts[qi], self.goals[qi], -np.pi, np.pi, ext=(0, 1), seed=4, query=qi,
+                                         max_iters=a.plan_iters, max_nodes=4096, impl=self.impl)["status"]
+            list(self.pool.map(one, range(lo, lo + n)))
+        else:
+            self.W.check_motion_batch(self.a[lo:lo + n], self.b[lo:lo + n], 0.01, want_clearance=False,
+                                      nthreads=self.cores)
+
+    def sample_size(self, per_core):
+        return min(self.total, per_core * self.cores)
+
+    def linear_scan_rate(self, nq):
+        """kNN only: the structure whose SEMANTICS we match (NearestNeighborsLinear), for scale."""
+        t0 = time.perf_counter()
+        self.O.knn(self.pts, self.q[:nq], self.args.k, nthreads=self.cores)
+        return nq / (time.perf_counter() - t0)
+
+
+PER_CORE = {"knn": 256, "check_motion": 6000, "rrtc": 128}
+
+
+def cpu_baseline(args, wl, synth):
+    """Bounded sample of the same workload on this box's host cores (rank 0, N=1 only)."""
+    arm = CpuArm(args, wl, synth)
+    ns = arm.sample_size(PER_CORE[wl])
+    arm.run(0, min(ns, arm.cores))          # warm-up
+    t0 = time.perf_counter()
+    arm.run(0, ns)
+    dt = time.perf_counter() - t0
+    unit = METRICS[wl][1]
+    out = {"value": ns / dt, "unit": unit, "cores": arm.cores, "kind": arm.kind,
+           "sample": f"first {ns} of the {arm.total} units; {arm.what}; {arm.cores} threads"}
+    if wl == "knn":
+        nl = min(args.queries, 2 * arm.cores)
+        out["structure"] = "kdtree"
+        out["linear_scan"] = {"value": arm.linear_scan_rate(nl), "unit": unit,
+                              "sample": f"first {nl} queries, NearestNeighborsLinear semantics (oracle port orc_knn)"}
+        out.update(arm.extra)
+    return out
+
+
+def run_reference(args, rank):
+    """--impl reference: same metric / unit / config.workload as our arm, timed on the host cores."""
+    if rank != 0:
+        return
     import prgpu_loader
-    P = prgpu_loader.load()
-    synth = P.synth
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the prgpu hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        # NCCL prints its version banner on stdout; stdout is reserved for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    hbm_peak, peak_src = peaks()
-    K, Wm = args.steps, max(args.warmup, 3)
+    synth = prgpu_loader.load().synth
+    wl = args.workload
+    if wl == "nnf":
+        return run_reference_nnf(args, synth)
+    arm = CpuArm(args, wl, synth)
+    per_step = arm.sample_size({"knn": 64, "check_motion": 1500, "rrtc": 16}[wl])
+    span = max(1, arm.total - per_step + 1)
+    for i in range(args.warmup):
+        arm.run((i * per_step) % span, per_step)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        arm.run(((args.warmup + i) * per_step) % span, per_step)
+    dt = time.perf_counter() - t0
+    metric, unit = METRICS[wl]
+    value = per_step * args.steps / dt
+    cb = {"value": value, "unit": unit, "cores": arm.cores, "kind": arm.kind,
+          "sample": f"{per_step} of the {arm.total} units per step; {arm.what}; {arm.cores} threads"}
+    cb.update(arm.extra)
+    emit_json({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_string(args, wl)},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
 
-    def barrier():
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if not dist:
+def run_reference_nnf(args, synth):
+    """NNF on the CPU: the literal reference (frechet/src/*.cpp compiled unmodified, oracle/_ref) holds a
+    string-keyed Boost graph per tensor-product node and cannot hold the 4.9e8-cell BASELINE problem, so it
+    is timed at the largest size it finishes in seconds; the flat-array oracle port is timed at a reduced
+    size too.  Both are scaled-down samples of the same workload, stated as such."""
+    import oracle_lib as O
+    O.build()
+    dh, link, xyzr = synth.default_arm()
+    sph, box = synth.obstacles(3, n_spheres=16, n_boxes=16)
+    ow = O.World(dh, link, xyzr, sph, box)
+    cores = host_cores()
+    k, D = 5, 1
+    out = {}
+    if O.ref_nnf() is not None:
+        Ws, Ms = 30, 40
+        full, ref, counts, ik = nnf_problem(synth, dh, Ws, Ms, D)
+        t0 = time.perf_counter()
+        r = O.ref_nnf_run(ow, full, Ws, Ms, k, D, ik, seed=1, solve_seconds=120.0)
+        dt = time.perf_counter() - t0
+        out["literal_reference"] = {"plans_per_s": 1.0 / dt, "setup_s": r["setup_seconds"], "solve_s": r["solve_seconds"],
+                                    "tpg_cells": int(r["n_tpg_vertices"]), "solved": int(r["solved"]),
+                                    "sample": f"W={Ws}, M={Ms}: the reference's own frechet/ sources (oracle/_ref), 1 thread"}
+    Ws, Ms = 50, 256
+    full, ref, counts, ik = nnf_problem(synth, dh, Ws, Ms, D)
+    t0 = time.perf_counter()
+    o = O.nnf_run(ow, ref, counts, ik, k=k, D=D, max_lazy_iters=4000, nthreads=cores)
+    dt = time.perf_counter() - t0
+    metric, unit = METRICS["nnf"]
+    value = 1.0 / dt
+    sample = (f"REDUCED problem W={Ws}, M={Ms} ({len(ref) * o['n_vertices']:.3g} TPG cells): oracle port of NNFrechet "
+              f"(flat arrays), setup + {o['lazy_iters']} LazySP iterations, {cores} threads for findKnnNodes")
+    emit_json({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": 1,
+        "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "replicas only",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_string(args, "nnf")},
+        "cpu_baseline": dict({"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample}, **out),
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    })
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self, args, rank, local_rank, world):
+        import numpy as np
+        import torch
+        import prgpu_loader
+        self.np, self.torch = np, torch
+        self.P = prgpu_loader.load()
+        self.synth = self.P.synth
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the prgpu hot path has no CPU fallback")
+        torch.cuda.set_device(local_rank)
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist_mod
+            self.dist = dist_mod
+            # NCCL prints its version banner on stdout; stdout is reserved for the one JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            self.dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.hbm_peak, self.peak_src = peaks()
+        self.K, self.Wm = args.steps, max(args.warmup, 3)
+        self.flush = None
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if not self.dist:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    extra = {}
-    if args.workload == "knn":
-        N, Q, k = args.nodes, args.queries, args.k
-        pts_all = synth.cloud(0, N)
-        q_host = torch.from_numpy(synth.cloud(1, Q)).pin_memory()
-        b0, b1 = rank * N // world, (rank + 1) * N // world
-        pts_host = torch.from_numpy(pts_all[b0:b1]).pin_memory()
-        del pts_all
-        n_local = b1 - b0
-        tree = P.KnnIndex(7, device=local_rank, capacity=n_local)
-        tree.set_index_base(b0)
-        pts_dev = pts_host.to(dev, non_blocking=True)
-        q_dev = q_host.to(dev, non_blocking=True)
-        tree.add_device(pts_dev, n_local, stream)
-        idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
-        dd = torch.empty((Q, k), dtype=torch.float64, device=dev)
-        if world > 1:
-            gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
-            gd = torch.empty((world, Q, k), dtype=torch.float64, device=dev)
-            fi = torch.empty((Q, k), dtype=torch.int32, device=dev)
-            fd = torch.empty((Q, k), dtype=torch.float64, device=dev)
-        tree.set_profiling(True)
-        kernel_ms = []
+    def launches(self):
+        return int(self.P.lib().prgpu_diag_launch_count())
 
-        bufs = dict(idx=idx, dist=dd)
-        if world > 1:
-            bufs.update(gidx=gi, gdist=gd, fidx=fi, fdist=fd)
-
-        def local_search(qd, nq_, k_, io, do):
-            tree.nearest_k_device(qd, nq_, k_, io, do, stream=stream)
-
-        def merge(gi_, gd_, nparts, nq_, k_, fi_, fd_):
-            P.topk_merge_device(local_rank, gi_, gd_, nparts, nq_, k_, fi_, fd_, stream)
-
-        trace = os.environ.get("PRGPU_BENCH_TRACE") == "1"
-
-        def step(record=False):
-            if trace and record:
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-                ev[0].record()
-                local_search(q_dev, Q, k, idx, dd)
-                ev[1].record()
-                if world > 1:
-                    dist.all_gather_into_tensor(gi.view(world * Q, k), idx)
-                    dist.all_gather_into_tensor(gd.view(world * Q, k), dd)
-                    merge(gi, gd, world, Q, k, fi, fd)
-                ev[2].record()
-                torch.cuda.synchronize()
-                print(f"[rank {rank}] local search {ev[0].elapsed_time(ev[1]):.3f} ms, gather+merge "
-                      f"{ev[1].elapsed_time(ev[2]):.3f} ms, dominant kernel {tree.last_kernel_ms():.3f} ms",
-                      file=sys.stderr, flush=True)
-                kernel_ms.append(tree.last_kernel_ms())
-                return
-            P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
-            if record:
-                kernel_ms.append(tree.last_kernel_ms())
-
-        launches_per_step = 7 + (1 if world > 1 else 0)  # pre-sample, merge, threshold, sample scan, sample threshold, scan, select
-        units_per_step = Q
-        metric, unit = "kNN queries/s", "queries/s"
-        algo_bytes = n_local * 56 + Q * 56 + Q * k * 12
-        kernel_name = "knn_collect_kernel"
-        config = {
-            "workload": f"batched kNN sweep: N={N} nodes, 7-DOF, Q={Q}, k={k} (BASELINE.json configs[1])",
-            "parallelism": "single GPU" if world == 1 else f"tree nodes sharded over {world} GPUs + NCCL "
-                           f"all-gather of per-shard top-{k} + merge kernel",
-            "l2": f"inputs larger than L2 ({n_local * 56 / 1e6:.0f} MB tree shard per GPU, fp64 SoA)",
-            "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks; the tree is the NearestNeighbors "
-                          "structure's state (as in the CPU reference arm), pinned host queries in / host results out "
-                          "every step; e2e.with_tree_reupload also refills the tree from host memory every step",
-            "arithmetic": "TF32 tensor-core filter -> fp32 re-cut -> fp64 exact distances + proof; results "
-                          "bit-identical to the fp64 reference",
-        }
-
-        def e2e_step(reupload=False):
-            # The reference-facing call: ompl::NearestNeighbors keeps the nodes (add once, query many
-            # times), so the step's inputs are the QUERIES: pinned host queries in, host results out, the
-            # tree is the structure's state -- exactly what the CPU reference arm does with its tree in
-            # host memory.  reupload=True also refills the whole tree from host memory first (reported
-            # separately as e2e.with_tree_reupload).
-            if reupload:
-                tree.clear()
-                P.capi._check(P.lib().prgpu_knn_add(tree.h, P.capi._ptr(pts_host), n_local))
-            if world == 1:
-                P.capi._check(P.lib().prgpu_knn_nearest_k(tree.h, P.capi._ptr(q_host), Q, k, None,
-                                                          P.capi._ptr(e2e_idx), P.capi._ptr(e2e_dist)))
-            else:
-                q_dev.copy_(q_host, non_blocking=True)
-                P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
-                e2e_idx.copy_(fi, non_blocking=True)
-                e2e_dist.copy_(fd, non_blocking=True)
-                torch.cuda.synchronize()
-
-        e2e_idx = torch.empty((Q, k), dtype=torch.int32).pin_memory()
-        e2e_dist = torch.empty((Q, k), dtype=torch.float64).pin_memory()
-        h2d = Q * 56
-        d2h = Q * k * 12
-    elif args.workload == "rrtc":
-        Bq = args.plans
-        dh, link, xyzr = synth.default_arm()
-        sph, box = synth.obstacles(3)
-        world_h = P.World(dh, link, xyzr, sph, box, device=local_rank)
-        starts_all, goals_all = plan_problems(synth, world_h, Bq)
-        p0, p1 = P.sharded.shard_bounds(Bq, world)[rank]
-        n_local = p1 - p0
-        s_host = torch.from_numpy(starts_all[p0:p1].copy()).pin_memory()
-        g_host = torch.from_numpy(goals_all[p0:p1].copy()).pin_memory()
-        s_dev, g_dev = s_host.to(dev), g_host.to(dev)
-        rb = P.RrtcBatch(world_h, n_local, -np.pi, np.pi, extension_type="ext-con", seed=4, query_id_base=p0,
-                         max_iters=args.plan_iters, max_nodes=2048)
-        kernel_ms = []
-
-        def step(record=False):
-            if record:
-                b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                b_.record()
-            rb.run_device(s_dev, g_dev, stream)
-            if record:
-                e_.record()
-                e_.synchronize()
-                kernel_ms.append(b_.elapsed_time(e_))
-
-        launches_per_step = 2  # warp-per-query kernel + team kernel
-        units_per_step = Bq
-        metric, unit = "RRTConnect plans/s", "plans/s"
-        kernel_name = "rrtc_batch_kernel"
-        config = {
-            "workload": f"{Bq} independent RRTConnect queries (ext-con, default range, 0.01 resolution), 7-DOF "
-                        f"sphere-FK arm vs 256 obstacles, <= {args.plan_iters} samples each (BASELINE.json "
-                        f"configs[4], query-sharded)",
-            "parallelism": "single GPU" if world == 1 else f"queries split over {world} GPUs, no collective",
-            "l2": "L2 flushed by a 256 MB write between timed iterations",
-            "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks",
-        }
-
-        def e2e_step():
-            P.capi._check(P.lib().prgpu_rrtc_batch_run(rb.h, P.capi._ptr(s_host), P.capi._ptr(g_host)))
-            rb.summary()
-        h2d = n_local * 112
-        d2h = n_local * 16
-        rb.run_device(s_dev, g_dev, stream)
-        torch.cuda.synchronize()
-        summ = rb.summary()
-        nodes = int(summ["n_start"].sum() + summ["n_goal"].sum())
-        algo_bytes = n_local * 112 + nodes * 60 + n_local * 16
-        config["solved_fraction"] = float((summ["status"] == 6).mean())
-        config["mean_samples_per_plan"] = float(summ["iterations"].mean())
-    else:
-        E = args.edges
-        dh, link, xyzr = synth.default_arm()
-        sph, box = synth.obstacles(3)
-        world_h = P.World(dh, link, xyzr, sph, box, device=local_rank)
-        a_all, b_all = synth.edges(2, E)
-        e0_, e1_ = rank * E // world, (rank + 1) * E // world
-        a_host = torch.from_numpy(a_all[e0_:e1_]).pin_memory()
-        b_host = torch.from_numpy(b_all[e0_:e1_]).pin_memory()
-        n_local = e1_ - e0_
-        a_dev, b_dev = a_host.to(dev), b_host.to(dev)
-        valid = torch.empty(n_local, dtype=torch.uint8, device=dev)
-        world_h.set_profiling(True)
-        kernel_ms = []
-
-        def step(record=False):
-            world_h.check_motion_batch_device(a_dev, b_dev, n_local, 0.01, valid, stream=stream)
-            if record:
-                kernel_ms.append(world_h.last_kernel_ms())
-
-        launches_per_step = 7  # sample, resolve, gaps, scan (2 kernels), expand, phase B (+ one memset)
-        units_per_step = E  # all ranks together
-        metric, unit = "validated edges/s", "edges/s"
-        algo_bytes = n_local * (2 * 56 + 1)
-        kernel_name = "cm_sample_kernel+cm_resolve_kernel+cm_phase_b_kernel"
-        config = {
-            "workload": f"batched checkMotion: {E} edges at 0.01 rad, 7-DOF sphere-FK arm (16 link spheres) "
-                        f"vs 256 obstacles (BASELINE.json configs[2]); edge length ~U(0,1] rad",
-            "parallelism": "single GPU" if world == 1 else f"edges split over {world} GPUs, no collective",
-            "l2": "L2 flushed by a 256 MB write between timed iterations",
-            "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks",
-        }
-        e2e_valid = torch.empty(n_local, dtype=torch.uint8).pin_memory()
-
-        def e2e_step():
-            P.capi._check(P.lib().prgpu_check_motion_batch(world_h.h, P.capi._ptr(a_host), P.capi._ptr(b_host),
-                                                           n_local, 0.01, 0, 0, P.capi._ptr(e2e_valid)))
-        h2d = n_local * 112
-        d2h = n_local
-
-    flush = None
-    if args.workload != "knn":
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    # ---- device-resident throughput (`value`) ----
-    for _ in range(Wm):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    if flush is None:
-        e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_beg.record()
-        for _ in range(K):
-            step(record=True)
-        e_end.record()
-        torch.cuda.synchronize()
-        total_ms = e_beg.elapsed_time(e_end)
-    else:
-        total_ms = 0.0
-        for _ in range(K):
-            flush.fill_(1)
-            e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e_beg.record()
-            step(record=True)
-            e_end.record()
+    def timed(self, step, flush_l2, K=None):
+        """W warm-ups, then K steps bracketed by barrier + synchronize, timed with CUDA events on the launching
+        stream; max over ranks.  flush_l2: write a 256 MB buffer between timed iterations (inputs smaller than
+        L2), otherwise the K steps are timed back to back.  Returns (ms per step, launches per step, clocks)."""
+        torch = self.torch
+        K = K or self.K
+        if flush_l2 and self.flush is None:
+            self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        for _ in range(self.Wm):
+            step()
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            sampler.start()
+        l0 = self.launches()
+        if not flush_l2:
+            b, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b.record()
+            for _ in range(K):
+                step(record=True)
+            e.record()
             torch.cuda.synchronize()
-            total_ms += e_beg.elapsed_time(e_end)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = max_over_ranks(total_ms)
-    ms_per_step = total_ms / K
-    value = units_per_step * K / (total_ms * 1e-3)
-    kms = max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+            total_ms = b.elapsed_time(e)
+        else:
+            total_ms = 0.0
+            for _ in range(K):
+                self.flush.fill_(1)
+                b, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b.record()
+                step(record=True)
+                e.record()
+                torch.cuda.synchronize()
+                total_ms += b.elapsed_time(e)
+        l1 = self.launches()
+        self.barrier()
+        clocks = sampler.stop() if self.rank == 0 else None
+        return self.max_over_ranks(total_ms) / K, (l1 - l0) / K, clocks
 
-    # ---- end to end through the C ABI with host buffers ----
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = units_per_step * K / e2e_s
-    e2e_extra = {}
-    if args.workload == "knn":
-        # the same call preceded by a refill of the tree from pinned host memory (PCIe-bound: 56 B/node)
-        for _ in range(2):
-            e2e_step(reupload=True)
-        barrier()
+    def timed_host(self, step, K=None, warm=2):
+        """End-to-end: host clock around synchronous C-ABI calls with host buffers; max over ranks."""
+        K = K or self.K
+        for _ in range(warm):
+            step()
+        self.barrier()
         t0 = time.perf_counter()
         for _ in range(K):
-            e2e_step(reupload=True)
-        torch.cuda.synchronize()
-        e2e_s2 = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        e2e_extra["with_tree_reupload"] = {"value": units_per_step * K / e2e_s2, "unit": "queries/s",
-                                           "h2d_bytes_per_step": n_local * 56 + Q * 56, "d2h_bytes_per_step": d2h}
+            step()
+        self.torch.cuda.synchronize()
+        s = self.max_over_ranks(time.perf_counter() - t0)
+        self.barrier()
+        return s / K
 
-    # ---- extra (multi-GPU): the alternative partitioning.  SURVEY §8(e) / the north star shard the TREE (it is
-    #      what scales a tree beyond one GPU's memory) -- that is `value`.  A 1e7-node tree fits every GPU,
-    #      so the same sweep can also replicate the tree and split the QUERIES: no candidate exchange, and
-    #      the per-query costs (sample, candidates, select) shrink with the rank count too.
-    if world > 1 and not args.no_extra and args.workload == "knn":
-        full = P.KnnIndex(7, device=local_rank, capacity=N)
+
+def measure_knn(env, args, want_cpu):
+    np, torch, P, synth, dist = env.np, env.torch, env.P, env.synth, env.dist
+    rank, world, dev, stream = env.rank, env.world, env.dev, env.stream
+    N, Q, k = args.nodes, args.queries, args.k
+    pts_all = synth.cloud(0, N)
+    q_host = torch.from_numpy(synth.cloud(1, Q)).pin_memory()
+    b0, b1 = rank * N // world, (rank + 1) * N // world
+    pts_host = torch.from_numpy(pts_all[b0:b1]).pin_memory()
+    del pts_all
+    n_local = b1 - b0
+    tree = P.KnnIndex(7, device=env.local_rank, capacity=n_local)
+    tree.set_index_base(b0)
+    pts_dev = pts_host.to(dev, non_blocking=True)
+    q_dev = q_host.to(dev, non_blocking=True)
+    tree.add_device(pts_dev, n_local, stream)
+    idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    dd = torch.empty((Q, k), dtype=torch.float64, device=dev)
+    bufs = dict(idx=idx, dist=dd)
+    if world > 1:
+        gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
+        gd = torch.empty((world, Q, k), dtype=torch.float64, device=dev)
+        fi = torch.empty((Q, k), dtype=torch.int32, device=dev)
+        fd = torch.empty((Q, k), dtype=torch.float64, device=dev)
+        bufs.update(gidx=gi, gdist=gd, fidx=fi, fdist=fd)
+    tree.set_profiling(True)
+    kernel_ms = []
+
+    def local_search(qd, nq_, k_, io, do):
+        tree.nearest_k_device(qd, nq_, k_, io, do, stream=stream)
+
+    def merge(gi_, gd_, nparts, nq_, k_, fi_, fd_):
+        P.topk_merge_device(env.local_rank, gi_, gd_, nparts, nq_, k_, fi_, fd_, stream)
+
+    phases = {"local_search_ms": [], "gather_merge_ms": []}
+    trace = os.environ.get("PRGPU_BENCH_TRACE") == "1"
+
+    def step(record=False):
+        P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
+        if record:
+            kernel_ms.append(tree.last_kernel_ms())
+
+    def traced_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        local_search(q_dev, Q, k, idx, dd)
+        ev[1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gi.view(world * Q, k), idx)
+            dist.all_gather_into_tensor(gd.view(world * Q, k), dd)
+            merge(gi, gd, world, Q, k, fi, fd)
+        ev[2].record()
+        torch.cuda.synchronize()
+        phases["local_search_ms"].append(ev[0].elapsed_time(ev[1]))
+        phases["gather_merge_ms"].append(ev[1].elapsed_time(ev[2]))
+
+    ms_per_step, launches, clocks = env.timed(step, flush_l2=False)
+    kms = env.max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+    # per-phase breakdown (untimed extra steps, events between the phases): what does not shrink with the shard
+    for _ in range(5):
+        traced_step()
+    env.barrier()
+    breakdown = {"local_search_ms": env.max_over_ranks(statistics.median(phases["local_search_ms"])),
+                 "gather_merge_ms": env.max_over_ranks(statistics.median(phases["gather_merge_ms"])),
+                 "dominant_kernel_ms": kms}
+    if trace:
+        print(f"[rank {rank}] {breakdown}", file=sys.stderr, flush=True)
+
+    e2e_idx = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+    e2e_dist = torch.empty((Q, k), dtype=torch.float64).pin_memory()
+
+    def e2e_step(reupload=False):
+        # The reference-facing call: ompl::NearestNeighbors keeps the nodes (add once, query many times), so
+        # the step's inputs are the QUERIES: pinned host queries in, host results out; the tree is the
+        # structure's state -- exactly what the CPU reference arm does with its tree in host memory.
+        if reupload:
+            tree.clear()
+            P.capi._check(P.lib().prgpu_knn_add(tree.h, P.capi._ptr(pts_host), n_local))
+        if world == 1:
+            P.capi._check(P.lib().prgpu_knn_nearest_k(tree.h, P.capi._ptr(q_host), Q, k, None,
+                                                      P.capi._ptr(e2e_idx), P.capi._ptr(e2e_dist)))
+        else:
+            q_dev.copy_(q_host, non_blocking=True)
+            P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
+            e2e_idx.copy_(fi, non_blocking=True)
+            e2e_dist.copy_(fd, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_s = env.timed_host(e2e_step)
+    e2e_s2 = env.timed_host(lambda: e2e_step(reupload=True), K=max(3, env.K // 3))
+    h2d, d2h = Q * 56, Q * k * 12
+    algo_bytes = n_local * 56 + Q * 56 + Q * k * 12
+    pairs = n_local * Q / (kms * 1e-3)
+    tpeak, tsrc = tensor_peak()
+    tf = pairs * 16.0 / 1e12
+    mma_peak = None
+    if rank == 0:
+        v = P.capi.C.c_double()
+        if P.lib().prgpu_diag_mma_tf32_peak(env.local_rank, P.capi.C.byref(v)) == 0:
+            mma_peak = v.value
+    summ = ncu_summary("knn_collect_kernel")
+    traffic = None if not summ or summ.get("dram_bytes") is None else int(summ["dram_bytes"] * (n_local / float(N)))
+    roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+            "traffic": traffic,
+            "traffic_note": "ncu dram read+write bytes of one launch over the full 1e7-node tree (profiles/"
+                            "ncu_summary.json), scaled to this rank's shard",
+            "kernel": "knn_collect_kernel", "kernel_ms": kms, "peak_source": tsrc,
+            "flops_per_launch": n_local * Q * 16.0,
+            "tf32_mma_sync": {"peak": mma_peak, "frac": None if not mma_peak else tf / mma_peak,
+                              "pairs_per_s": pairs,
+                              "note": "peak = issue rate of mma.sync.m16n8k8 TF32 measured live by "
+                                      "prgpu_diag_mma_tf32_peak in this run (16 warps/SM, 8 independent "
+                                      "accumulator fragments per warp)"},
+            "issue_slots_busy_pct_ncu": None if not summ else summ.get("issue_slots_busy_pct"),
+            "hbm": {"achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": env.hbm_peak, "unit": "GB/s",
+                    "frac": algo_bytes / (kms * 1e-3) / 1e9 / env.hbm_peak, "peak_source": env.peak_src,
+                    "algorithmic_bytes_per_launch": algo_bytes,
+                    "note": "SURVEY §8(d)'s fp64 formula 56*N + 56*Q + 12*Q*k; the scan itself streams the "
+                            "40 B/node TF32 mirror"}}
+    extra = {"phase_breakdown": breakdown}
+
+    # ---- the alternative partitioning (multi-GPU): tree replicated, QUERIES split ----
+    if world > 1 and not args.no_extra:
+        full = P.KnnIndex(7, device=env.local_rank, capacity=N)
         full.add(synth.cloud(0, N))
         q0, q1 = rank * Q // world, (rank + 1) * Q // world
         qs_dev = q_dev[q0:q1].contiguous()
@@ -522,21 +590,12 @@ def run_ours(args, rank, local_rank, world):
         ad = torch.empty((Q, k), dtype=torch.float64, device=dev)
         even = Q % world == 0
 
-        def qstep():
+        def qstep(record=False):
             full.nearest_k_device(qs_dev, q1 - q0, k, li, ld, stream=stream)
             if even:
                 dist.all_gather_into_tensor(ai, li)
                 dist.all_gather_into_tensor(ad, ld)
-        for _ in range(3):
-            qstep()
-        barrier()
-        b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b_.record()
-        for _ in range(K):
-            qstep()
-        e_.record()
-        torch.cuda.synchronize()
-        qms = max_over_ranks(b_.elapsed_time(e_)) / K
+        qms, _, _ = env.timed(qstep, flush_l2=False)
         if even:
             same = bool(torch.equal(ai, fi)) and bool(torch.equal(ad, fd))
             extra["query_sharded"] = {"queries_per_s": Q / (qms * 1e-3), "ms_per_step": qms,
@@ -544,255 +603,349 @@ def run_ours(args, rank, local_rank, world):
                                       "note": "tree replicated on every GPU, queries split, results all-gathered"}
         full.close()
 
-    # ---- extras (rank 0, single GPU): the other shapes of the sweep ----
-    if world == 1 and not args.no_extra and args.workload == "knn":
-        def time_knn(nq, kk, reps=5):
+    # ---- the other shapes of the sweep (single GPU) ----
+    if world == 1 and not args.no_extra:
+        def time_knn(t_, nq, kk, reps=5):
             qd = torch.from_numpy(synth.cloud(7, nq)).to(dev)
             i_ = torch.empty((nq, kk), dtype=torch.int32, device=dev)
             d_ = torch.empty((nq, kk), dtype=torch.float64, device=dev)
             for _ in range(2):
-                tree.nearest_k_device(qd, nq, kk, i_, d_, stream=stream)
+                t_.nearest_k_device(qd, nq, kk, i_, d_, stream=stream)
             b, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             b.record()
             for _ in range(reps):
-                tree.nearest_k_device(qd, nq, kk, i_, d_, stream=stream)
+                t_.nearest_k_device(qd, nq, kk, i_, d_, stream=stream)
             e.record()
             torch.cuda.synchronize()
             return b.elapsed_time(e) / reps
         tree.clear()
         tree.add_device(pts_dev, n_local, stream)
-        m1 = time_knn(args.queries, 1)
-        extra["knn_k1_queries_per_s"] = args.queries / (m1 * 1e-3)
-        # the rest of BASELINE.json's sweep (10^4 .. 10^7 nodes, k = 1 / 16), resident trees
+        extra["knn_k1_queries_per_s"] = Q / (time_knn(tree, Q, 1) * 1e-3)
         sweep = {}
         for n_s in (10_000, 100_000, 1_000_000):
             if n_s >= N:
                 continue
-            ts = P.KnnIndex(7, device=local_rank, capacity=n_s)
+            ts = P.KnnIndex(7, device=env.local_rank, capacity=n_s)
             ts.add_device(pts_dev[:n_s].contiguous(), n_s, stream)
             for kk in (16, 1):
-                qd = q_dev
-                i_ = torch.empty((Q, kk), dtype=torch.int32, device=dev)
-                d_ = torch.empty((Q, kk), dtype=torch.float64, device=dev)
-                for _ in range(3):
-                    ts.nearest_k_device(qd, Q, kk, i_, d_, stream=stream)
-                b, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                b.record()
-                for _ in range(10):
-                    ts.nearest_k_device(qd, Q, kk, i_, d_, stream=stream)
-                e.record()
-                torch.cuda.synchronize()
-                sweep[f"N={n_s},k={kk}"] = Q / (b.elapsed_time(e) / 10 * 1e-3)
+                sweep[f"N={n_s},k={kk}"] = Q / (time_knn(ts, Q, kk, reps=10) * 1e-3)
             ts.close()
         extra["knn_sweep_queries_per_s"] = sweep
-        ms1 = time_knn(1, 1, reps=20)
+        ms1 = time_knn(tree, 1, 1, reps=20)
         extra["single_query_scan"] = {"ms": ms1, "hbm_gbs": n_local * 56 / (ms1 * 1e-3) / 1e9,
-                                      "frac_of_hbm_peak": n_local * 56 / (ms1 * 1e-3) / 1e9 / hbm_peak}
-
-    if world == 1 and not args.no_extra and args.workload == "knn":
-        del pts_dev
-        tree.close()
-        torch.cuda.empty_cache()
-        dh, link, xyzr = synth.default_arm()
-        sph, box = synth.obstacles(3)
-        wx = P.World(dh, link, xyzr, sph, box, device=local_rank)
-        ea, eb = synth.edges(2, 1_000_000)
-        ea_d, eb_d = torch.from_numpy(ea).to(dev), torch.from_numpy(eb).to(dev)
-        ev = torch.empty(len(ea), dtype=torch.uint8, device=dev)
-        for _ in range(2):
-            wx.check_motion_batch_device(ea_d, eb_d, len(ea), 0.01, ev, stream=stream)
-        b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b_.record()
-        for _ in range(3):
-            wx.check_motion_batch_device(ea_d, eb_d, len(ea), 0.01, ev, stream=stream)
-        e_.record()
-        torch.cuda.synchronize()
-        extra["check_motion_1e6_edges_per_s"] = len(ea) / (b_.elapsed_time(e_) / 3 * 1e-3)
-        extra["check_motion_valid_fraction"] = float(ev.float().mean().item())
-        ps, pg = plan_problems(synth, wx, 4096)
-        rbx = P.RrtcBatch(wx, 4096, -np.pi, np.pi, extension_type="ext-con", seed=4, max_iters=1000, max_nodes=2048)
-        rbx.run(ps, pg)
-        t0 = time.perf_counter()
-        rbx.run(ps, pg)
-        extra["rrtc_4096_plans_per_s_e2e"] = 4096 / (time.perf_counter() - t0)
-        extra["rrtc_solved_fraction"] = float((rbx.summary()["status"] == 6).mean())
-
-    if rank != 0:
-        return
-    roof = {"bound": "hbm", "achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": algo_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic(kernel_name),
-            "kernel": kernel_name, "kernel_ms": kms, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": algo_bytes}
-    if args.workload == "knn":
-        # The scan is tensor-bound: D = |x|^2 - 2 q.x - T_q for 16 queries x 8 nodes per TF32
-        # mma.sync (m16n8k8 = 2048 flop); the 8-long contraction makes the OUTPUT the bottleneck,
-        # which is why the warp-level MMA (results in registers) is used and not tcgen05/TMEM.
-        pairs = n_local * args.queries / (kms * 1e-3)
-        tpeak, tsrc = tensor_peak()
-        tf = pairs * 16.0 / 1e12
-        mma_peak_tf = 278.0   # TF32 mma.sync m16n8k8 issue peak measured on this pool (scripts/ubench/mma_tf32.cu)
-        roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                "traffic": (None if ncu_traffic(kernel_name) is None else
-                            int(ncu_traffic(kernel_name) * (n_local / float(N)))),
-                "traffic_note": "ncu dram read+write bytes of one launch over the full tree (profiles/"
-                                "r01e_*), scaled to this rank's shard",
-                "kernel": kernel_name, "kernel_ms": kms, "peak_source": tsrc,
-                "flops_per_launch": n_local * args.queries * 16.0,
-                "tf32_mma_sync": {"peak": mma_peak_tf, "frac": tf / mma_peak_tf, "pairs_per_s": pairs,
-                                  "note": "peak = measured issue rate of mma.sync.m16n8k8 TF32 (917 warp-MMA/us/SM); "
-                                          "the same loop fed from shared memory with the sign test tops out at "
-                                          "610 warp-MMA/us/SM in isolation (scripts/ubench/mma_loop.cu)"},
-                "hbm": {"achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": algo_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": algo_bytes,
-                        "note": "SURVEY §8(d)'s fp64 formula 56*N + 56*Q + 12*Q*k; the scan itself streams the "
-                                "40 B/node TF32 mirror"}}
+                                      "frac_of_hbm_peak": n_local * 56 / (ms1 * 1e-3) / 1e9 / env.hbm_peak,
+                                      "note": "Q=1 (a planner's nearest() on a 1e7-node tree): the HBM-bound shape, "
+                                              "exact fp64 kernel"}
+    stats = tree.search_stats()
+    del pts_dev
+    tree.close()
+    torch.cuda.empty_cache()
+    metric, unit = METRICS["knn"]
     line = {
-        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": config, "roofline": roof,
-        "e2e": dict({"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                    **e2e_extra),
-        "gpu_launches": launches_per_step * K, "clocks": clocks, "extra": extra,
+        "metric": metric, "value": Q / (ms_per_step * 1e-3), "unit": unit, "ms_per_step": ms_per_step,
+        "scaling": "strong",
+        "config": {
+            "workload": workload_string(args, "knn"),
+            "parallelism": "single GPU" if world == 1 else f"tree nodes sharded over {world} GPUs + NCCL "
+                           f"all-gather of per-shard top-{k} + merge kernel",
+            "l2": f"inputs larger than L2 ({n_local * 56 / 1e6:.0f} MB tree shard per GPU, fp64 SoA)",
+            "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks; the tree is the "
+                          "NearestNeighbors structure's state (as in the CPU reference arm), pinned host queries in / "
+                          "host results out every step; e2e.with_tree_reupload also refills the tree from host memory",
+            "arithmetic": "TF32 tensor-core filter -> fp32 re-cut -> fp64 exact distances + proof; results "
+                          "bit-identical to the fp64 reference",
+            "filter_fallback_queries": stats["fallback_queries"],
+        },
+        "roofline": roof,
+        "e2e": {"value": Q / e2e_s, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "with_tree_reupload": {"value": Q / e2e_s2, "unit": unit,
+                                       "h2d_bytes_per_step": n_local * 56 + Q * 56, "d2h_bytes_per_step": d2h}},
+        "gpu_launches_per_step": launches, "clocks": clocks, "extra": extra,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, synth)
-    emit_json(line)
+    if want_cpu:
+        line["cpu_baseline"] = cpu_baseline(args, "knn", synth)
+    return line
 
 
-def cpu_baseline(args, synth):
-    """Oracle port timed on this box's host cores on a bounded sample of the same workload."""
-    import oracle_lib as O
-    O.build()
-    cores = host_cores()
-    if args.workload == "knn":
-        pts = synth.cloud(0, args.nodes)
-        q = synth.cloud(1, args.queries)
-        ns = min(args.queries, 32 * cores)
-        O.knn(pts, q[:cores], args.k, nthreads=cores)
-        t0 = time.perf_counter()
-        O.knn(pts, q[:ns], args.k, nthreads=cores)
-        dt = time.perf_counter() - t0
-        return {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-                "sample": f"first {ns} of the {args.queries} queries against the full {args.nodes}-node tree, "
-                          f"k={args.k}, linear scan with (distance, index) order, {cores} threads"}
+def measure_check_motion(env, args, want_cpu):
+    np, torch, P, synth = env.np, env.torch, env.P, env.synth
+    rank, world, dev, stream = env.rank, env.world, env.dev, env.stream
+    E = args.edges
     dh, link, xyzr = synth.default_arm()
     sph, box = synth.obstacles(3)
-    W = O.World(dh, link, xyzr, sph, box)
-    if args.workload == "rrtc":
-        import numpy as np
-        from concurrent.futures import ThreadPoolExecutor
-        starts, goals = plan_problems(synth, W, args.plans)
-        impl = "ref" if O.ref() is not None else "port"
-        ns = min(args.plans, 128 * cores)
+    world_h = P.World(dh, link, xyzr, sph, box, device=env.local_rank)
+    a_all, b_all = synth.edges(2, E)
+    e0_, e1_ = rank * E // world, (rank + 1) * E // world
+    a_host = torch.from_numpy(a_all[e0_:e1_]).pin_memory()
+    b_host = torch.from_numpy(b_all[e0_:e1_]).pin_memory()
+    n_local = e1_ - e0_
+    a_dev, b_dev = a_host.to(dev), b_host.to(dev)
+    valid = torch.empty(n_local, dtype=torch.uint8, device=dev)
+    world_h.set_profiling(True)
+    kernel_ms = []
 
-        def one(qi):
-            return W.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=(0, 1), seed=4, query=qi,
-                                max_iters=args.plan_iters, max_nodes=4096, impl=impl)["status"]
-        with ThreadPoolExecutor(cores) as pool:
-            list(pool.map(one, range(cores)))
-            t0 = time.perf_counter()
-            list(pool.map(one, range(ns)))
-            dt = time.perf_counter() - t0
-        return {"value": ns / dt, "unit": "plans/s", "cores": cores, "kind": "reference" if impl == "ref" else "port",
-                "sample": f"first {ns} of the {args.plans} queries, one query per thread, "
-                          + ("the reference's own RRTConnect.cpp over the OMPL-API stand-in (oracle/_ref)"
-                             if impl == "ref" else "oracle port of RRTConnect.cpp") + f", {cores} threads"}
-    a, b = synth.edges(2, args.edges)
-    ns = min(args.edges, 6000 * cores)
-    t0 = time.perf_counter()
-    W.check_motion_batch(a[:ns], b[:ns], 0.01, want_clearance=False, nthreads=cores)
-    dt = time.perf_counter() - t0
-    return {"value": ns / dt, "unit": "edges/s", "cores": cores, "kind": "port",
-            "sample": f"first {ns} of the {args.edges} edges, DiscreteMotionValidator bisection with early "
-                      f"exit over the double-precision synthetic checker, {cores} threads"}
+    def step(record=False):
+        world_h.check_motion_batch_device(a_dev, b_dev, n_local, 0.01, valid, stream=stream)
+        if record:
+            kernel_ms.append(world_h.last_kernel_ms())
+
+    ms_per_step, launches, clocks = env.timed(step, flush_l2=True)
+    kms = env.max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+    e2e_valid = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        P.capi._check(P.lib().prgpu_check_motion_batch(world_h.h, P.capi._ptr(a_host), P.capi._ptr(b_host),
+                                                       n_local, 0.01, 0, 0, P.capi._ptr(e2e_valid)))
+    e2e_s = env.timed_host(e2e_step)
+    valid_fraction = float(valid.float().mean().item())
+    algo_bytes = n_local * (2 * 56 + 1)
+    kernels = ["cm_sample_kernel", "cm_resolve_kernel", "cm_phase_b_kernel"]
+    issue = {kname: (ncu_summary(kname) or {}).get("issue_slots_busy_pct") for kname in kernels}
+    lanes = {kname: (ncu_summary(kname) or {}).get("threads_per_inst") for kname in kernels}
+    roof = {"bound": "hbm", "achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": env.hbm_peak, "unit": "GB/s",
+            "frac": algo_bytes / (kms * 1e-3) / 1e9 / env.hbm_peak, "traffic": ncu_traffic(kernels + [
+                "cm_gaps_kernel", "cm_expand_kernel"]),
+            "kernel": "+".join(kernels), "kernel_ms": kms, "peak_source": env.peak_src,
+            "algorithmic_bytes_per_launch": algo_bytes,
+            "binds": "issue / latency (fp32 FK chain + dependent L2 loads), not HBM: SURVEY §8(d) puts this kernel "
+                     "~1e3x into compute-bound territory, the HBM fraction is reported because the contract asks for it",
+            "issue_slots_busy_pct_ncu": issue, "threads_per_inst_ncu": lanes}
+    metric, unit = METRICS["check_motion"]
+    world_h.close()
+    line = {
+        "metric": metric, "value": E / (ms_per_step * 1e-3), "unit": unit, "ms_per_step": ms_per_step,
+        "scaling": "strong",
+        "config": {"workload": workload_string(args, "check_motion"),
+                   "parallelism": "single GPU" if world == 1 else f"edges split over {world} GPUs, no collective",
+                   "l2": "L2 flushed by a 256 MB write between timed iterations",
+                   "e2e_timing": "host clock around synchronous C-ABI calls (prgpu_check_motion_batch, host buffers), "
+                                 "max over ranks",
+                   "valid_fraction": valid_fraction},
+        "roofline": roof,
+        "e2e": {"value": E / e2e_s, "unit": unit, "h2d_bytes_per_step": n_local * 112, "d2h_bytes_per_step": n_local},
+        "gpu_launches_per_step": launches, "clocks": clocks, "extra": {},
+    }
+    if want_cpu:
+        line["cpu_baseline"] = cpu_baseline(args, "check_motion", synth)
+    return line
 
 
-def nnf_problem(synth, dh, W, M, D, tseed=5):
-    """NNF config of BASELINE.json: W waypoints, M IK samples per layer (multinomial over the interior
-    layers), synthetic IK = trajectory configuration + N(0, 0.15^2) joint noise."""
-    import numpy as np
-    R = (W - 1) * (D + 1) + 1
-    q, poses = synth.nnf_reference(tseed, 2 * R + 5, dh)
-    ids = synth.lin_int_space(0, len(q) - 1, R)
-    rng = np.random.default_rng(1)
-    counts = np.zeros(R, dtype=np.uint32)
-    counts[0] = counts[-1] = M
-    counts[1:-1] += np.bincount(rng.integers(1, R - 1, W * M - 2 * M), minlength=R)[1:-1].astype(np.uint32)
-    ik = synth.nnf_ik_states(2, q[ids], counts)
-    return poses[ids], counts, ik
+def measure_rrtc(env, args, want_cpu):
+    np, torch, P, synth = env.np, env.torch, env.P, env.synth
+    rank, world, dev, stream = env.rank, env.world, env.dev, env.stream
+    Bq = args.plans
+    dh, link, xyzr = synth.default_arm()
+    sph, box = synth.obstacles(3)
+    world_h = P.World(dh, link, xyzr, sph, box, device=env.local_rank)
+    starts_all, goals_all = plan_problems(synth, world_h, Bq)
+    p0, p1 = P.sharded.shard_bounds(Bq, world)[rank]
+    n_local = p1 - p0
+    s_host = torch.from_numpy(starts_all[p0:p1].copy()).pin_memory()
+    g_host = torch.from_numpy(goals_all[p0:p1].copy()).pin_memory()
+    s_dev, g_dev = s_host.to(dev), g_host.to(dev)
+    rb = P.RrtcBatch(world_h, n_local, -np.pi, np.pi, extension_type="ext-con", seed=4, query_id_base=p0,
+                     max_iters=args.plan_iters, max_nodes=2048)
+    kernel_ms = []
+
+    def step(record=False):
+        if record:
+            b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b_.record()
+        rb.run_device(s_dev, g_dev, stream)
+        if record:
+            e_.record()
+            e_.synchronize()
+            kernel_ms.append(b_.elapsed_time(e_))
+
+    ms_per_step, launches, clocks = env.timed(step, flush_l2=True)
+    kms = env.max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+
+    def e2e_step():
+        P.capi._check(P.lib().prgpu_rrtc_batch_run(rb.h, P.capi._ptr(s_host), P.capi._ptr(g_host)))
+        rb.summary()
+    e2e_s = env.timed_host(e2e_step)
+    summ = rb.summary()
+    nodes = int(summ["n_start"].sum() + summ["n_goal"].sum())
+    algo_bytes = n_local * 112 + nodes * 60 + n_local * 16
+    kernels = ["rrtc_batch_kernel", "rrtc_team_kernel"]
+    roof = {"bound": "hbm", "achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": env.hbm_peak, "unit": "GB/s",
+            "frac": algo_bytes / (kms * 1e-3) / 1e9 / env.hbm_peak, "traffic": ncu_traffic(kernels),
+            "kernel": "+".join(kernels), "kernel_ms": kms, "peak_source": env.peak_src,
+            "algorithmic_bytes_per_launch": algo_bytes,
+            "binds": "latency: a query is a dependent chain sample -> nearest -> validate -> append; the batch time is "
+                     "set by the queries that exhaust the sample budget",
+            "issue_slots_busy_pct_ncu": {kn: (ncu_summary(kn) or {}).get("issue_slots_busy_pct") for kn in kernels}}
+    metric, unit = METRICS["rrtc"]
+    line = {
+        "metric": metric, "value": Bq / (ms_per_step * 1e-3), "unit": unit, "ms_per_step": ms_per_step,
+        "scaling": "strong",
+        "config": {"workload": workload_string(args, "rrtc"),
+                   "parallelism": "single GPU" if world == 1 else f"queries split over {world} GPUs, no collective",
+                   "l2": "L2 flushed by a 256 MB write between timed iterations",
+                   "e2e_timing": "host clock around synchronous C-ABI calls (prgpu_rrtc_batch_run with host starts/goals "
+                                 "+ prgpu_rrtc_batch_summary), max over ranks",
+                   "solved_fraction": float((summ["status"] == 6).mean()),
+                   "mean_samples_per_plan": float(summ["iterations"].mean())},
+        "roofline": roof,
+        "e2e": {"value": Bq / e2e_s, "unit": unit, "h2d_bytes_per_step": n_local * 112, "d2h_bytes_per_step": n_local * 16},
+        "gpu_launches_per_step": launches, "clocks": clocks, "extra": {},
+    }
+    rb.close()
+    world_h.close()
+    if want_cpu:
+        line["cpu_baseline"] = cpu_baseline(args, "rrtc", synth)
+    return line
 
 
-def run_nnf(args, rank, local_rank, world):
-    """NNF Frechet following (BASELINE.json configs[3]): W=200 waypoints, 1024 IK samples per layer, k=5,
-    D=1, 16+16 obstacles.  Replicas only: every rank plans the same problem; rank 0 reports.
-    A step is one LazySP iteration (bottleneck search + path extraction + edge evaluation + knock-out)."""
-    import numpy as np
-    import torch
-    import prgpu_loader
-    P = prgpu_loader.load()
-    synth = P.synth
-    torch.cuda.set_device(local_rank)
+def measure_nnf(env, args, want_cpu):
+    """NNF Frechet following (BASELINE.json configs[3]).  Replicas only: every rank plans the same
+    problem; rank 0 reports.  value = complete plans (setup + LazySP solve) per second."""
+    np, torch, P, synth = env.np, env.torch, env.P, env.synth
     dh, link, xyzr = synth.default_arm()
     sph, box = synth.obstacles(3, n_spheres=16, n_boxes=16)
-    gw = P.World(dh, link, xyzr, sph, box, device=local_rank)
+    gw = P.World(dh, link, xyzr, sph, box, device=env.local_rank)
     W, M, k, D = 200, 1024, 5, 1
-    ref, counts, ik = nnf_problem(synth, dh, W, M, D)
-    # warm-up (untimed): the same problem set up once and searched for a few LazySP iterations, so that the
-    # timed instance does not pay first-use costs (module load, allocator growth)
+    _, ref, counts, ik = nnf_problem(synth, dh, W, M, D)
+    # warm-up (untimed): the same problem set up once and searched for a few LazySP iterations
     gwarm = P.Nnf(gw, ref, counts, ik, num_nn=k, discretization=D)
     gwarm.solve(max_lazy_iters=40)
     gwarm.close()
     torch.cuda.synchronize()
+    l0 = env.launches()
     t0 = time.perf_counter()
     g = P.Nnf(gw, ref, counts, ik, num_nn=k, discretization=D)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
+    # the first search sweeps the whole band (dirty level 0): the launch the roofline is quoted on
     t0 = time.perf_counter()
-    r = g.solve(max_lazy_iters=20000)
-    solve_s = time.perf_counter() - t0
-    if rank != 0:
-        return
-    hbm_peak, peak_src = peaks()
+    r1 = g.solve(max_lazy_iters=1)
+    first_search_ms = g.last_dp_ms()
     info = g.band_info()
-    dp_ms = g.last_dp_ms()
-    algo = info["cells"] * (8 + 8 * 4)  # band cells x (write + ~4 reads), DESIGN.md K3
+    r = g.solve(max_lazy_iters=20000) if not r1["solved"] else r1
+    solve_s = time.perf_counter() - t0
+    launches = env.launches() - l0
+    iters = int(r1["lazy_iters"] + (0 if r1["solved"] else r["lazy_iters"]))
+    nE = g.n_edges
+    # bytes one full-band search touches by construction: per cell one fp64 write + (1 + 2 indeg) fp64 reads,
+    # mean in-degree E/V (DESIGN.md K3)
+    indeg = nE / float(g.n_vertices)
+    algo = info["cells"] * 8.0 * (1.0 + 1.0 + 2.0 * indeg)
+    summ = ncu_summary("nnf_flow_dp_kernel")
+    metric, unit = METRICS["nnf"]
     line = {
-        "metric": "NNF LazySP searches/s", "value": r["lazy_iters"] / solve_s, "unit": "searches/s", "n_gpus": 1,
-        "steps": int(r["lazy_iters"]), "warmup": 40, "ms_per_step": solve_s / max(1, r["lazy_iters"]) * 1e3,
-        "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": f"NNF Frechet following: W={W} waypoints, {M} IK samples per layer, k={k}, D={D}, 7-DOF "
-                               f"arm, 32 obstacles (BASELINE.json configs[3]); R={len(ref)}, "
-                               f"{g.n_vertices} NN vertices, {len(ref) * g.n_vertices:.3g} TPG cells",
-                   "setup_s": setup_s, "solve_s": solve_s, "solved": int(r["solved"]),
-                   "final_frechet_error": r["final_error"], "edges_evaluated": int(r["n_evaluated"]),
-                   "edges_in_collision": int(r["n_collisions"]), "band": info},
-        "roofline": {"bound": "hbm", "achieved": algo / (dp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": algo / (dp_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic("nnf_flow_dp_kernel"),
-                     "kernel": "nnf_flow_dp_kernel", "kernel_ms": dp_ms, "peak_source": peak_src,
-                     "note": "last (incremental) search of the LazySP loop; latency-bound by the chain of dependent NN-graph levels, see DESIGN.md"},
-        "e2e": {"value": 1.0 / (setup_s + solve_s), "unit": "plans/s (setup + solve, host inputs)",
+        "metric": metric, "value": 1.0 / (setup_s + solve_s), "unit": unit,
+        "ms_per_step": (setup_s + solve_s) * 1e3, "scaling": "replicas only",
+        "config": {"workload": workload_string(args, "nnf"), "R": len(ref), "nn_vertices": g.n_vertices,
+                   "tpg_cells": len(ref) * g.n_vertices, "setup_s": setup_s, "solve_s": solve_s,
+                   "lazy_iterations": iters, "ms_per_lazy_iteration": solve_s / max(1, iters) * 1e3,
+                   "solved": int(r["solved"]), "final_frechet_error": r["final_error"],
+                   "edges_evaluated": int(r["n_evaluated"]), "edges_in_collision": int(r["n_collisions"]),
+                   "band": info, "l2": "band table 8 B/cell larger than L2 on the first search"},
+        "roofline": {"bound": "hbm", "achieved": algo / (first_search_ms * 1e-3) / 1e9, "peak": env.hbm_peak,
+                     "unit": "GB/s", "frac": algo / (first_search_ms * 1e-3) / 1e9 / env.hbm_peak,
+                     "traffic": None if not summ else summ.get("dram_bytes"), "kernel": "nnf_flow_dp_kernel",
+                     "kernel_ms": first_search_ms, "peak_source": env.peak_src,
+                     "algorithmic_bytes_per_launch": algo,
+                     "note": "the FIRST search of the solve (every band cell recomputed); later searches recompute "
+                             "only the levels at or after a knocked-out edge and are latency-bound on the level chain"},
+        "e2e": {"value": 1.0 / (setup_s + solve_s), "unit": unit,
                 "h2d_bytes_per_step": int(ik.nbytes + ref.nbytes), "d2h_bytes_per_step": int(g.n_vertices * 19 * 8)},
-        "gpu_launches": int(3 * r["lazy_iters"]), "clocks": None,
+        "gpu_launches_per_step": launches, "clocks": None, "extra": {},
     }
-    if not args.no_cpu_baseline:
+    g.close()
+    gw.close()
+    if want_cpu:
         import oracle_lib as O
         O.build()
         ow = O.World(dh, link, xyzr, sph, box)
         Ws, Ms = 50, 256
-        refs, cs, iks = nnf_problem(synth, dh, Ws, Ms, D)
+        _, refs, cs, iks = nnf_problem(synth, dh, Ws, Ms, D)
         cores = host_cores()
         t0 = time.perf_counter()
-        o = O.nnf_run(ow, refs, cs, iks, k=k, D=D, max_lazy_iters=40, nthreads=cores)
+        o = O.nnf_run(ow, refs, cs, iks, k=k, D=D, max_lazy_iters=4000, nthreads=cores)
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": o["lazy_iters"] / dt, "unit": "searches/s (incl. setup)", "cores": cores,
-                                "kind": "port",
-                                "sample": f"REDUCED problem W={Ws}, M={Ms} ({len(refs) * o['n_vertices']:.3g} TPG cells, "
-                                          f"{len(ref) * g.n_vertices / (len(refs) * o['n_vertices']):.0f}x fewer than the GPU run), "
-                                          f"{o['lazy_iters']} LazySP iterations of the oracle port incl. its setup; the "
-                                          f"full-size CPU run does not finish in minutes"}
-    emit_json(line)
+        line["cpu_baseline"] = {
+            "value": 1.0 / dt, "unit": unit, "cores": cores, "kind": "port",
+            "sample": f"REDUCED problem W={Ws}, M={Ms} ({len(refs) * o['n_vertices']:.3g} TPG cells, "
+                      f"{len(ref) * line['config']['nn_vertices'] / (len(refs) * o['n_vertices']):.0f}x fewer than the "
+                      f"GPU run): oracle port, setup + {o['lazy_iters']} LazySP iterations; the full-size CPU run does "
+                      f"not finish in minutes (see --workload nnf --impl reference for the literal reference at toy size)"}
+    return line
+
+
+def measure_dropin_a(env, args, want_cpu):
+    """One planner instance at a time through the UNMODIFIED reference planner source over the GPU
+    NearestNeighbors / validators (oracle/_ref/libdropin_a.so): a launch + sync per growTree.  SURVEY §7.3
+    item 3: this path is latency-bound and loses to the CPU for small trees -- measured, not hidden."""
+    import plugin_lib
+    np, synth = env.np, env.synth
+    L = plugin_lib.dropin()
+    if L is None:
+        return {"unavailable": "oracle/_ref/libdropin_a.so not built (needs /root/reference at build time)"}
+    dh, link, xyzr = synth.default_arm()
+    sph, box = synth.obstacles(3)
+    w = plugin_lib.PluginWorld(dh, link, xyzr, sph, box, device=env.local_rank, library=L)
+    gw = env.P.World(dh, link, xyzr, sph, box, device=env.local_rank)
+    starts, goals = plan_problems(synth, gw, args.plans)
+    gw.close()
+    n = 64
+    w.rrtc_bench(starts[:4], goals[:4], -np.pi, np.pi, max_iters=args.plan_iters, seed=4)
+    sec, solved, iters = w.rrtc_bench(starts[:n], goals[:n], -np.pi, np.pi, max_iters=args.plan_iters, seed=4)
+    out = {"plans_per_s": n / sec, "us_per_sample": 1e6 * sec / max(1, iters), "solved": int(solved), "queries": n,
+           "note": "pr_ompl::RRTConnect exactly as shipped by the reference (compiled unmodified) with "
+                   "GpuNearestNeighbors<Motion*> + GpuMotionValidator underneath, one query after the other"}
+    import oracle_lib as O
+    if want_cpu and O.ref() is not None:
+        O.build()
+        ow = O.World(dh, link, xyzr, sph, box)
+        t0 = time.perf_counter()
+        for qi in range(n):
+            ow.rrtc_solve(starts[qi], goals[qi], -np.pi, np.pi, ext=(0, 1), seed=4, query=qi,
+                          max_iters=args.plan_iters, max_nodes=4096, impl="ref")
+        out["cpu_reference_plans_per_s_1_thread"] = n / (time.perf_counter() - t0)
+    return out
+
+
+MEASURE = {"knn": measure_knn, "check_motion": measure_check_motion, "rrtc": measure_rrtc, "nnf": measure_nnf}
+
+
+def block(line):
+    """A workload's line as a block of the headline line's `extra`."""
+    keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "roofline", "e2e", "gpu_launches_per_step",
+            "cpu_baseline")
+    return {k: line[k] for k in keep if k in line}
+
+
+def run_ours(args, rank, local_rank, world):
+    env = Env(args, rank, local_rank, world)
+    want_cpu = world == 1 and not args.no_cpu_baseline and rank == 0
+    line = MEASURE[args.workload](env, args, want_cpu)
+    if args.workload == "knn" and not args.no_extra:
+        for wl in ("check_motion", "rrtc"):
+            sub = MEASURE[wl](env, args, want_cpu)
+            line["extra"][wl] = block(sub)
+        if world == 1:
+            try:
+                line["extra"]["nnf"] = block(measure_nnf(env, args, want_cpu))
+            except Exception as e:  # the headline must not die with an optional block
+                line["extra"]["nnf"] = {"error": repr(e)}
+            try:
+                line["extra"]["dropin_a"] = measure_dropin_a(env, args, want_cpu)
+            except Exception as e:
+                line["extra"]["dropin_a"] = {"error": repr(e)}
+    if rank != 0:
+        return
+    out = {
+        "metric": line["metric"], "value": line["value"], "unit": line["unit"], "n_gpus": world, "steps": env.K,
+        "warmup": env.Wm, "ms_per_step": line["ms_per_step"], "higher_is_better": True, "scaling": line["scaling"],
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": line["config"],
+        "roofline": line["roofline"], "e2e": line["e2e"],
+        "gpu_launches": int(round(line["gpu_launches_per_step"] * env.K)), "clocks": line["clocks"],
+        "extra": line["extra"],
+    }
+    if "cpu_baseline" in line:
+        out["cpu_baseline"] = line["cpu_baseline"]
+    emit_json(out)
 
 
 _JSON_OUT = None
@@ -820,14 +973,6 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload == "nnf":
-        if args.impl == "reference":
-            if rank == 0:
-                emit_json({"impl": "reference", "unavailable": "NNF reference arm: the literal frechet/ sources "
-                                  "need Boost.Graph and Eigen (absent); see cpu_baseline of --workload nnf"})
-            return
-        run_nnf(args, rank, local_rank, world)
-        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

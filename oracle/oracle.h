@@ -20,6 +20,12 @@ extern "C" {
  * (sqrt-distance, index); idx padded with 0xFFFFFFFF, dist with +inf. */
 int orc_knn(const double *pts, uint64_t n, int dim, const double *queries, uint64_t nq, int k,
             const uint32_t *lo, uint32_t *idx_out, double *dist_out, int nthreads);
+/* the same answers from a k-d tree: the GNAT-class structure the reference would really get from
+ * SelfConfig::getDefaultNearestNeighbors (oracle/kdtree.cpp) -- the honest CPU baseline */
+void *orc_kdtree_build(const double *pts, uint64_t n, int dim);
+void orc_kdtree_destroy(void *tree);
+int orc_kdtree_knn(const void *tree, const double *queries, uint64_t nq, int k, uint32_t *idx_out,
+                   double *dist_out, int nthreads);
 double orc_distance(const double *a, const double *b, int dim);
 void orc_interpolate(const double *from, const double *to, double t, int dim, double *out);
 

@@ -124,6 +124,30 @@ def lin_int_space(mn, mx, n):
     return np.array([int(mn + i * delta) for i in range(n)], dtype=np.int64)
 
 
+def nnf_layer_counts(seed, R, W, M):
+    """IK budget per super-sampled reference index, as NNFrechet draws it (frechet/src/NNFrechet.cpp:310-343,
+    418-448): both end waypoints get M, the other W*M - 2M samples fall on indices 1..R-2 by
+    std::uniform_int_distribution<int> on std::default_random_engine.  Restated for libstdc++ (minstd_rand0:
+    x <- 16807 x mod 2^31-1; the distribution scales the generator's range down with rejection); input
+    generation only -- pinned against the reference's own draws in tests/test_oracle_nnf.py."""
+    x = seed % 2147483647 or 1
+    counts = np.zeros(R, dtype=np.uint32)
+    counts[0] = counts[-1] = M
+    a, b = 1, R - 2
+    urngrange = 2147483646 - 1
+    uerange = (b - a) + 1
+    scaling = urngrange // uerange
+    past = uerange * scaling
+    for _ in range(W * M - 2 * M):
+        while True:
+            x = (x * 16807) % 2147483647
+            ret = x - 1
+            if ret < past:
+                break
+        counts[a + ret // scaling] += 1
+    return counts
+
+
 def nnf_reference(seed, n_poses, dh, dof=DOF, amplitude=0.6):
     """A smooth joint trajectory (n_poses x dof) and the end-effector poses (n_poses x 12) it traces:
     the reference path handed to NNFrechet::setRefPath."""

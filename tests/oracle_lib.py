@@ -61,6 +61,10 @@ def lib():
         L = C.CDLL(path)
         L.orc_knn.argtypes = [c_dp, C.c_uint64, C.c_int, c_dp, C.c_uint64, C.c_int, c_u32p, c_u32p, c_dp,
                               C.c_int]
+        L.orc_kdtree_build.argtypes = [c_dp, C.c_uint64, C.c_int]
+        L.orc_kdtree_build.restype = C.c_void_p
+        L.orc_kdtree_destroy.argtypes = [C.c_void_p]
+        L.orc_kdtree_knn.argtypes = [C.c_void_p, c_dp, C.c_uint64, C.c_int, c_u32p, c_dp, C.c_int]
         L.orc_distance.argtypes = [c_dp, c_dp, C.c_int]
         L.orc_distance.restype = C.c_double
         L.orc_interpolate.argtypes = [c_dp, c_dp, C.c_double, C.c_int, c_dp]
@@ -169,6 +173,28 @@ def knn(pts, queries, k, lo=None, nthreads=1):
                        nthreads)
     assert rc == 0
     return idx, dist
+
+
+class KdTree:
+    """k-d tree over the same points with orc_knn's answers (the GNAT-class CPU baseline)."""
+
+    def __init__(self, pts):
+        self.pts = np.ascontiguousarray(pts, dtype=np.float64)
+        self.dim = self.pts.shape[1]
+        self.h = lib().orc_kdtree_build(_dp(self.pts), len(self.pts), self.dim)
+
+    def knn(self, queries, k, nthreads=1):
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)
+        idx = np.empty((len(q), k), dtype=np.uint32)
+        dist = np.empty((len(q), k), dtype=np.float64)
+        rc = lib().orc_kdtree_knn(self.h, _dp(q), len(q), k, idx.ctypes.data_as(c_u32p), _dp(dist), nthreads)
+        assert rc == 0
+        return idx, dist
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_kdtree_destroy(self.h)
+            self.h = None
 
 
 class World:

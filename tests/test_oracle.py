@@ -186,3 +186,29 @@ def test_reference_resume_and_clear_semantics(O, synth, oracle_world):
                 assert all(np.array_equal(single[k], cleared[k]) for k in single), (i, ext, "clear")
     finally:
         ref.ref_set_two_phase(0, 0)
+
+
+def test_kdtree_baseline_equals_linear_scan(O, synth):
+    """The k-d tree CPU baseline (oracle/kdtree.cpp) returns orc_knn's answers bit for bit: ties, exact
+    duplicates, k > n, clustered data."""
+    rng = np.random.default_rng(0)
+    for n, nq, dup in [(1, 4, 0.0), (23, 50, 0.0), (5000, 300, 0.2), (40000, 200, 0.02)]:
+        pts = synth.cloud(7, n, dup_fraction=dup)
+        q = np.vstack([synth.cloud(8, nq), pts[rng.integers(0, n, 8)]])      # some queries ARE tree points
+        t = O.KdTree(pts)
+        for k in (1, 5, 16):
+            ki, kd = t.knn(q, k, nthreads=4)
+            li, ld = O.knn(pts, q, k, nthreads=4)
+            assert np.array_equal(ki, li) and np.array_equal(kd, ld), (n, k)
+    # all points identical, and tight clusters far apart
+    same = np.tile(synth.cloud(9, 1), (200, 1))
+    t = O.KdTree(same)
+    ki, kd = t.knn(synth.cloud(10, 5), 16)
+    li, ld = O.knn(same, synth.cloud(10, 5), 16)
+    assert np.array_equal(ki, li) and np.array_equal(kd, ld)
+    cl = np.repeat(synth.cloud(11, 20), 100, axis=0) + 1e-9 * rng.normal(size=(2000, 7))
+    t = O.KdTree(cl)
+    qq = synth.cloud(12, 64)
+    ki, kd = t.knn(qq, 16)
+    li, ld = O.knn(cl, qq, 16)
+    assert np.array_equal(ki, li) and np.array_equal(kd, ld)

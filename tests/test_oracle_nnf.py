@@ -27,33 +27,12 @@ def test_lin_int_space_truncation(O, synth):
         assert a[0] == 0 and np.all(np.diff(a) >= 0) and a[-1] in (n - 1, n - 2)
 
 
-def _minstd_uniform_counts(seed, R, W, M):
-    """libstdc++: std::default_random_engine = minstd_rand0 (x <- 16807 x mod 2^31-1);
-    uniform_int_distribution<int>(a,b) on a non-power-of-two range generator scales down with rejection."""
-    x = seed % 2147483647 or 1
-    counts = np.zeros(R, dtype=np.uint32)
-    counts[0] = counts[-1] = M
-    a, b = 1, R - 2
-    urngrange = 2147483646 - 1
-    uerange = (b - a) + 1
-    scaling = urngrange // uerange
-    past = uerange * scaling
-    for _ in range(W * M - 2 * M):
-        while True:
-            x = (x * 16807) % 2147483647
-            ret = x - 1
-            if ret < past:
-                break
-        counts[a + ret // scaling] += 1
-    return counts
-
-
 @pytest.mark.parametrize("seed,W,M,D", [(1, 5, 5, 3), (7, 12, 20, 1), (42, 30, 16, 2)])
-def test_ik_budget_matches_libstdcxx_algorithm(O, seed, W, M, D):
+def test_ik_budget_matches_libstdcxx_algorithm(O, synth, seed, W, M, D):
     R = (W - 1) * (D + 1) + 1
     c = O.nnf_layer_counts(seed, R, W, M)
     assert c.sum() == W * M and c[0] == M and c[-1] == M
-    assert np.array_equal(c, _minstd_uniform_counts(seed, R, W, M))
+    assert np.array_equal(c, synth.nnf_layer_counts(seed, R, W, M))      # pr-ompl_b200/synth.py restatement
 
 
 def _bottleneck_by_threshold(ref, res, D, k):
