@@ -390,6 +390,14 @@ class Env:
         self.K, self.Wm = args.steps, max(args.warmup, 3)
         self.flush = None
 
+    def comm(self):
+        """The library's own communicator (prgpu_comm_init over an NCCL id broadcast by torch.distributed)."""
+        if self.world == 1:
+            return None
+        if getattr(self, "_comm", None) is None:
+            self._comm = self.P.sharded.make_comm(self.P, self.dist, self.local_rank, self.rank, self.world)
+        return self._comm
+
     def barrier(self):
         if self.dist:
             self.dist.barrier()
@@ -476,6 +484,7 @@ def measure_knn(env, args, want_cpu):
     idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
     dd = torch.empty((Q, k), dtype=torch.float64, device=dev)
     bufs = dict(idx=idx, dist=dd)
+    comm = env.comm()
     if world > 1:
         gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
         gd = torch.empty((world, Q, k), dtype=torch.float64, device=dev)
@@ -495,9 +504,18 @@ def measure_knn(env, args, want_cpu):
     trace = os.environ.get("PRGPU_BENCH_TRACE") == "1"
 
     def step(record=False):
-        P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
+        # N > 1: the whole sharded step is one C-ABI call (local search, ONE all-gather of the packed
+        # (distance, index) records over the library's own NCCL communicator, merge kernel)
+        if world > 1:
+            tree.nearest_k_sharded_device(comm, q_dev, Q, k, fi, fd, stream=stream)
+        else:
+            local_search(q_dev, Q, k, idx, dd)
         if record:
             kernel_ms.append(tree.last_kernel_ms())
+
+    def torch_step():
+        # the round-1 host layer (two torch.distributed all-gathers + merge), kept as a cross-check
+        P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
 
     def traced_step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -515,6 +533,14 @@ def measure_knn(env, args, want_cpu):
 
     ms_per_step, launches, clocks = env.timed(step, flush_l2=False)
     kms = env.max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+    cross = {}
+    if world > 1:
+        ci, cd = fi.clone(), fd.clone()
+        torch_step()
+        torch.cuda.synchronize()
+        cross = {"c_abi_equals_torch_host_layer": bool(torch.equal(ci, fi)) and bool(torch.equal(cd, fd)),
+                 "redo_steps": comm.redo_steps()}
+        step()
     # per-phase breakdown (untimed extra steps, events between the phases): what does not shrink with the shard
     for _ in range(5):
         traced_step()
@@ -539,11 +565,8 @@ def measure_knn(env, args, want_cpu):
             P.capi._check(P.lib().prgpu_knn_nearest_k(tree.h, P.capi._ptr(q_host), Q, k, None,
                                                       P.capi._ptr(e2e_idx), P.capi._ptr(e2e_dist)))
         else:
-            q_dev.copy_(q_host, non_blocking=True)
-            P.sharded.sharded_nearest_k(local_search, merge, dist, world, q_dev, Q, k, bufs)
-            e2e_idx.copy_(fi, non_blocking=True)
-            e2e_dist.copy_(fd, non_blocking=True)
-            torch.cuda.synchronize()
+            P.capi._check(P.lib().prgpu_knn_nearest_k_sharded(tree.h, comm.h, P.capi._ptr(q_host), Q, k,
+                                                              P.capi._ptr(e2e_idx), P.capi._ptr(e2e_dist)))
 
     e2e_s = env.timed_host(e2e_step)
     e2e_s2 = env.timed_host(lambda: e2e_step(reupload=True), K=max(3, env.K // 3))
@@ -577,6 +600,8 @@ def measure_knn(env, args, want_cpu):
                     "note": "SURVEY §8(d)'s fp64 formula 56*N + 56*Q + 12*Q*k; the scan itself streams the "
                             "40 B/node TF32 mirror"}}
     extra = {"phase_breakdown": breakdown}
+    if cross:
+        extra["sharded_c_abi"] = cross
 
     # ---- the alternative partitioning (multi-GPU): tree replicated, QUERIES split ----
     if world > 1 and not args.no_extra:
@@ -646,8 +671,9 @@ def measure_knn(env, args, want_cpu):
         "scaling": "strong",
         "config": {
             "workload": workload_string(args, "knn"),
-            "parallelism": "single GPU" if world == 1 else f"tree nodes sharded over {world} GPUs + NCCL "
-                           f"all-gather of per-shard top-{k} + merge kernel",
+            "parallelism": "single GPU" if world == 1 else f"tree nodes sharded over {world} GPUs, one C-ABI call "
+                           f"per step (prgpu_knn_nearest_k_sharded_device): local search + ONE NCCL all-gather of "
+                           f"the packed per-shard top-{k} records + merge kernel",
             "l2": f"inputs larger than L2 ({n_local * 56 / 1e6:.0f} MB tree shard per GPU, fp64 SoA)",
             "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks; the tree is the "
                           "NearestNeighbors structure's state (as in the CPU reference arm), pinned host queries in / "

@@ -244,6 +244,43 @@ int prgpu_nnf_band_info(prgpu_nnf_t *h, double *tau, uint64_t *cells, uint32_t *
 int prgpu_nnf_last_dp_ms(prgpu_nnf_t *h, float *ms);
 
 /* ------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU.  No counterpart in the reference (single-threaded,
+ * no collectives); this is how the C++ host gets the sharded paths without Python.
+ *   rank 0:  prgpu_comm_unique_id(id)  ->  the application broadcasts the 128 bytes (MPI_Bcast, a file,
+ *            torch.distributed ...)  ->  every rank: prgpu_comm_init(device, rank, nranks, id, &comm)
+ * NCCL is bound at run time (libnccl.so.2); prgpu_comm_init_custom takes the application's own all-gather
+ * instead (an existing communicator, or the CPU/gloo tests; device = -1 makes a host-only communicator
+ * that only prgpu_comm_allgather accepts).
+ * ---------------------------------------------------------------------------------- */
+typedef struct prgpu_comm prgpu_comm_t;
+#define PRGPU_COMM_ID_BYTES 128
+/* all-gather of `bytes_per_rank` bytes from every rank into recv (rank r's block at r * bytes_per_rank),
+ * enqueued on `stream`; returns 0 on success */
+typedef int (*prgpu_allgather_fn)(void *ctx, const void *send, void *recv, uint64_t bytes_per_rank, void *stream);
+int prgpu_comm_unique_id(void *id128);
+int prgpu_comm_init(int device, int rank, int nranks, const void *id128, prgpu_comm_t **out);
+int prgpu_comm_init_custom(int device, int rank, int nranks, prgpu_allgather_fn fn, void *ctx, prgpu_comm_t **out);
+int prgpu_comm_destroy(prgpu_comm_t *c);
+int prgpu_comm_rank(const prgpu_comm_t *c);
+int prgpu_comm_size(const prgpu_comm_t *c);
+int prgpu_comm_allgather(prgpu_comm_t *c, const void *send, void *recv, uint64_t bytes_per_rank, void *stream);
+/* sharded steps that had to be repeated because some shard left queries unproven (see below) */
+int prgpu_comm_stats(const prgpu_comm_t *c, uint64_t *redo_steps);
+/* nearestK over a tree whose nodes are sharded over the ranks (each rank's handle holds its shard, with
+ * prgpu_knn_set_index_base = the shard's first global index; queries replicated): local search, ONE
+ * all-gather of the per-shard (distance, index) records, ordered merge.  Every rank receives the global
+ * result, identical to a single-GPU search of the whole tree.  Collective: all ranks must call it. */
+int prgpu_knn_nearest_k_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries_dev, uint64_t nq, int k,
+                                       uint32_t *idx_dev, double *dist_dev, void *stream);
+int prgpu_knn_nearest_k_sharded(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries, uint64_t nq, int k,
+                                uint32_t *idx, double *dist);
+/* checkMotion over an edge batch replicated on every rank: rank r validates its slice, one all-gather of
+ * 1 byte per edge; every rank receives all n verdicts.  Collective. */
+int prgpu_check_motion_batch_sharded_device(prgpu_world_t *w, prgpu_comm_t *c, const double *from_dev,
+                                            const double *to_dev, uint64_t n, double resolution, int mode,
+                                            int check_first, uint8_t *valid_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement aids (no counterpart in the reference)
  * ---------------------------------------------------------------------------------- */
 /* kernels launched by this library in this process so far */

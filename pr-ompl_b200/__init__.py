@@ -6,4 +6,4 @@ tests and bench.py; it computes nothing itself and raises if the CUDA library is
 """
 from . import synth, sharded  # noqa: F401
 from .capi import (KnnIndex, World, PrgpuError, build, lib, lib_path, topk_merge_device,  # noqa: F401
-                   INVALID_INDEX, MODE_OMPL_DISCRETE, MODE_NNF_ALPHA, RrtcBatch, RrtcParams, Nnf)
+                   INVALID_INDEX, MODE_OMPL_DISCRETE, MODE_NNF_ALPHA, RrtcBatch, RrtcParams, Nnf, Comm)

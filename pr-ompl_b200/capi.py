@@ -77,6 +77,18 @@ SIGNATURES = {
     "prgpu_rrtc_batch_summary": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "prgpu_rrtc_batch_fetch": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, c_vp, c_vp, C.POINTER(C.c_uint32),
                                          c_vp, C.c_uint32]),
+    "prgpu_comm_unique_id": (C.c_int, [c_vp]),
+    "prgpu_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_int, c_vp, C.POINTER(c_vp)]),
+    "prgpu_comm_init_custom": (C.c_int, [C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.POINTER(c_vp)]),
+    "prgpu_comm_destroy": (C.c_int, [c_vp]),
+    "prgpu_comm_rank": (C.c_int, [c_vp]),
+    "prgpu_comm_size": (C.c_int, [c_vp]),
+    "prgpu_comm_allgather": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, c_vp]),
+    "prgpu_comm_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64)]),
+    "prgpu_knn_nearest_k_sharded_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
+    "prgpu_knn_nearest_k_sharded": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp]),
+    "prgpu_check_motion_batch_sharded_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_uint64, C.c_double, C.c_int,
+                                                          C.c_int, c_vp, c_vp]),
     "prgpu_diag_launch_count": (C.c_uint64, []),
     "prgpu_diag_mma_tf32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "prgpu_nnf_create": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
@@ -211,9 +223,62 @@ class KnnIndex:
         _check(lib().prgpu_knn_nearest_k(self.h, _ptr(queries), nq, k, _ptr(lo), _ptr(idx), _ptr(dist)))
         return (idx, dist) if want_dist else idx
 
+    def nearest_k_sharded_device(self, comm, q_dev, nq, k, idx_dev, dist_dev, stream=0):
+        """Collective: this handle holds one shard of the tree (set_index_base = first global index)."""
+        _check(lib().prgpu_knn_nearest_k_sharded_device(self.h, comm.h, _ptr(q_dev), nq, k, _ptr(idx_dev),
+                                                        _ptr(dist_dev), C.c_void_p(stream)))
+
+    def nearest_k_sharded(self, comm, queries, k):
+        queries = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)
+        idx = np.empty((len(queries), k), dtype=np.uint32)
+        dist = np.empty((len(queries), k), dtype=np.float64)
+        _check(lib().prgpu_knn_nearest_k_sharded(self.h, comm.h, _ptr(queries), len(queries), k, _ptr(idx),
+                                                 _ptr(dist)))
+        return idx, dist
+
     def nearest_k_device(self, q_dev, nq, k, idx_dev, dist_dev=None, lo_dev=None, stream=0):
         _check(lib().prgpu_knn_nearest_k_device(self.h, _ptr(q_dev), nq, k, _ptr(lo_dev), _ptr(idx_dev),
                                                 _ptr(dist_dev), C.c_void_p(stream)))
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, c_vp, c_vp, c_vp, C.c_uint64, c_vp)
+
+
+class Comm:
+    """prgpu_comm_*: the communicator behind the sharded entry points (NCCL bound at run time, or a
+    caller-supplied all-gather)."""
+
+    def __init__(self, device, rank, nranks, unique_id=None, allgather=None):
+        h = c_vp()
+        self._cb = None
+        if allgather is not None:
+            self._cb = ALLGATHER_FN(allgather)      # keep the trampoline alive
+            _check(lib().prgpu_comm_init_custom(device, rank, nranks, C.cast(self._cb, c_vp), None, C.byref(h)))
+        else:
+            buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+            _check(lib().prgpu_comm_init(device, rank, nranks, C.cast(buf, c_vp), C.byref(h)))
+        self.h, self.rank, self.nranks = h, rank, nranks
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        _check(lib().prgpu_comm_unique_id(C.cast(buf, c_vp)))
+        return bytes(buf)
+
+    def allgather(self, send, recv, bytes_per_rank, stream=0):
+        _check(lib().prgpu_comm_allgather(self.h, _ptr(send), _ptr(recv), bytes_per_rank, C.c_void_p(stream)))
+
+    def redo_steps(self):
+        v = C.c_uint64()
+        _check(lib().prgpu_comm_stats(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.prgpu_comm_destroy(self.h)
+        self.h = None
+
+    __del__ = close
 
 
 def topk_merge_device(device, idx_parts, dist_parts, nparts, nq, k, idx_out, dist_out, stream=0):
@@ -264,6 +329,13 @@ class World:
                                   check_first=False, stream=0):
         _check(lib().prgpu_check_motion_batch_device(self.h, _ptr(a_dev), _ptr(b_dev), n, resolution, mode,
                                                      int(check_first), _ptr(valid_dev), C.c_void_p(stream)))
+
+    def check_motion_batch_sharded_device(self, comm, a_dev, b_dev, n, resolution, valid_dev,
+                                          mode=MODE_OMPL_DISCRETE, check_first=False, stream=0):
+        """Collective: the batch is replicated, every rank validates its slice and receives all n verdicts."""
+        _check(lib().prgpu_check_motion_batch_sharded_device(self.h, comm.h, _ptr(a_dev), _ptr(b_dev), n,
+                                                             float(resolution), mode, int(check_first),
+                                                             _ptr(valid_dev), C.c_void_p(stream)))
 
     def is_valid_batch(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)

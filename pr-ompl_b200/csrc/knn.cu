@@ -282,7 +282,7 @@ knn_tile_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, uin
 __global__ void __launch_bounds__(128)
 topk_merge_kernel(const uint32_t *__restrict__ idx_parts, const double *__restrict__ dist_parts, int nparts,
                   int group, uint32_t nq, int k, uint32_t *__restrict__ idx_out,
-                  double *__restrict__ dist_out) {
+                  double *__restrict__ dist_out, size_t idx_part_stride, size_t dist_part_stride) {
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq)
     return;
@@ -290,9 +290,10 @@ topk_merge_kernel(const uint32_t *__restrict__ idx_parts, const double *__restri
   const int first = g * group;
   const int P = min(group, nparts - first);
   auto get = [&](int l, int e, double &d, uint32_t &i) {
-    const size_t at = ((size_t)(first + l) * nq + q) * k + e;
-    d = dist_parts[at];
-    i = idx_parts[at];
+    const size_t at = (size_t)q * k + e; // part strides in elements: nq*k for a dense table, the chunk
+                                         // size for the [dist | idx] records ranks all-gather
+    d = dist_parts[(size_t)(first + l) * dist_part_stride + at];
+    i = idx_parts[(size_t)(first + l) * idx_part_stride + at];
   };
   warp_merge(get, P, k, dist_out + ((size_t)g * nq + q) * k, idx_out + ((size_t)g * nq + q) * k);
 }
@@ -439,7 +440,22 @@ int topk_merge(const uint32_t *idx_parts, const double *dist_parts, int nparts, 
   if (nq == 0)
     return PRGPU_OK;
   topk_merge_kernel<<<dim3((nq + 3) / 4, 1), 128, 0, stream>>>(idx_parts, dist_parts, nparts, MERGE_GROUP, nq,
-                                                              k, idx_out, dist_out); PRGPU_COUNT_LAUNCH(1);
+                                                              k, idx_out, dist_out, (size_t)nq * k, (size_t)nq * k); PRGPU_COUNT_LAUNCH(1);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
+int topk_merge_strided(const uint32_t *idx_parts, const double *dist_parts, size_t idx_part_stride,
+                       size_t dist_part_stride, int nparts, uint32_t nq, int k, uint32_t *idx_out, double *dist_out,
+                       cudaStream_t stream) {
+  if (nparts < 1 || nparts > MERGE_GROUP)
+    return fail(PRGPU_ELIMIT, "topk_merge: nparts must be in [1,128]");
+  if (k < 1 || k > PRGPU_MAX_K)
+    return fail(PRGPU_ELIMIT, "topk_merge: k must be in [1,PRGPU_MAX_K]");
+  if (nq == 0)
+    return PRGPU_OK;
+  topk_merge_kernel<<<dim3((nq + 3) / 4, 1), 128, 0, stream>>>(idx_parts, dist_parts, nparts, MERGE_GROUP, nq, k,
+                                                              idx_out, dist_out, idx_part_stride, dist_part_stride); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
@@ -459,7 +475,7 @@ int merge_passes(KnnScratch &sc, int nparts, uint32_t nq, int k, uint32_t *idx_o
     uint32_t *di = into2 ? sc.part2_idx : sc.part_idx;
     double *dd = into2 ? sc.part2_dist : sc.part_dist;
     topk_merge_kernel<<<dim3((nq + 3) / 4, groups), 128, 0, stream>>>(si, sd, nparts, MERGE_GROUP, nq, k, di,
-                                                                   dd); PRGPU_COUNT_LAUNCH(1);
+                                                                   dd, (size_t)nq * k, (size_t)nq * k); PRGPU_COUNT_LAUNCH(1);
     PRGPU_CUDA_TRY(cudaGetLastError());
     si = di;
     sd = dd;

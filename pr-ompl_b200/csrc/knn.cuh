@@ -55,6 +55,19 @@ int knn_search_exact(int dim, const KnnTreeView &t, const double *queries_dev, u
 int knn_search(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev,
                uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
                KernelTimer *timer = nullptr, int force_exact = 0);
+// Deferred form for callers that enqueue more work behind the search (the sharded step): the filter path
+// leaves the unproven-query list on the device (scratch.flags[0] = count, [1+i] = query ids) instead of
+// synchronising; *pending says whether such a list exists.  knn_search_finish(nflag) then re-runs those
+// queries with the exact kernel (what knn_search does by itself after its own read-back).
+int knn_search_deferred(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k,
+                        const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count,
+                        cudaStream_t stream, KernelTimer *timer, int force_exact, bool *pending);
+int knn_search_finish(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k,
+                      const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count,
+                      cudaStream_t stream, uint32_t nflag);
+int topk_merge_strided(const uint32_t *idx_parts, const double *dist_parts, size_t idx_part_stride,
+                       size_t dist_part_stride, int nparts, uint32_t nq, int k, uint32_t *idx_out, double *dist_out,
+                       cudaStream_t stream);
 int merge_passes(KnnScratch &sc, int nparts, uint32_t nq, int k, uint32_t *idx_out, double *dist_out,
                  cudaStream_t stream);
 int scratch_reserve(double *&d, uint32_t *&i, size_t &cap, size_t need);

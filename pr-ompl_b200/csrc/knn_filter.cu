@@ -582,10 +582,46 @@ __global__ void scatter_rows_kernel(const uint32_t *__restrict__ ids, uint32_t n
 
 constexpr uint32_t FT_SAMPLE_STRIDE = 64; // the sample pass visits every 64th tile (every 32nd of a tree below 4M nodes)
 
+// re-runs the `nflag` unproven queries listed in sc.flags[1..] with the exact kernel
+template <int DIM>
+int filter_fallback(const KnnTreeView &t, const double *queries, uint32_t nq, int k, const uint32_t *lo,
+                    uint32_t *idx_out, double *dist_out, KnnScratch &sc, int sm_count, cudaStream_t stream,
+                    uint32_t nflag) {
+  (void)nq;
+  if (nflag == 0)
+    return PRGPU_OK;
+  sc.fallback_queries += nflag;
+  if (sc.fb_capacity < nflag) {
+    for (void *p : {(void *)sc.fb_q, (void *)sc.fb_dist, (void *)sc.fb_idx, (void *)sc.fb_lo})
+      if (p)
+        cudaFree(p);
+    sc.fb_q = sc.fb_dist = nullptr;
+    sc.fb_idx = sc.fb_lo = nullptr;
+    sc.fb_capacity = 0;
+    const size_t cap = (size_t)nflag * 2;
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_q, cap * DIM * sizeof(double)));
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_dist, cap * KNN_FILTER_MAX_K * sizeof(double)));
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_idx, cap * KNN_FILTER_MAX_K * sizeof(uint32_t)));
+    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_lo, cap * sizeof(uint32_t)));
+    sc.fb_capacity = cap;
+  }
+  gather_queries_kernel<<<(nflag + 127) / 128, 128, 0, stream>>>(queries, lo, DIM, sc.flags + 1, nflag, sc.fb_q,
+                                                                sc.fb_lo); PRGPU_COUNT_LAUNCH(1);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  int rc = knn_search_exact(DIM, t, sc.fb_q, nflag, k, lo ? sc.fb_lo : nullptr, sc.fb_idx, sc.fb_dist, sc, sm_count,
+                            stream, nullptr);
+  if (rc != PRGPU_OK)
+    return rc;
+  scatter_rows_kernel<<<(nflag * k + 127) / 128, 128, 0, stream>>>(sc.flags + 1, nflag, k, sc.fb_idx, sc.fb_dist,
+                                                                  idx_out, dist_out); PRGPU_COUNT_LAUNCH(1);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
 template <int DIM>
 int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k, const uint32_t *lo,
                 uint32_t *idx_out, double *dist_out, KnnScratch &sc, int sm_count, cudaStream_t stream,
-                KernelTimer *timer) {
+                KernelTimer *timer, bool *deferred) {
   const int kp = KNN_FILTER_SAMPLE_RANK;
   const uint32_t ntiles = (t.n + FT_TILE - 1) / FT_TILE;
   const uint32_t qblocks = (nq + CT_QPB - 1) / CT_QPB;
@@ -712,52 +748,34 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   ++sc.filter_calls;
 
   // unproven queries (ties at the cut, heavy duplicates) take the exact kernel
+  if (deferred) { // the caller reads flags[0] itself, after whatever it enqueues behind this search
+    *deferred = true;
+    return PRGPU_OK;
+  }
   uint32_t nflag = 0;
   PRGPU_CUDA_TRY(cudaMemcpyAsync(&nflag, sc.flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   PRGPU_CUDA_TRY(cudaStreamSynchronize(stream));
-  if (nflag == 0)
-    return PRGPU_OK;
-  sc.fallback_queries += nflag;
-  if (sc.fb_capacity < nflag) {
-    for (void *p : {(void *)sc.fb_q, (void *)sc.fb_dist, (void *)sc.fb_idx, (void *)sc.fb_lo})
-      if (p)
-        cudaFree(p);
-    sc.fb_q = sc.fb_dist = nullptr;
-    sc.fb_idx = sc.fb_lo = nullptr;
-    sc.fb_capacity = 0;
-    const size_t cap = (size_t)nflag * 2;
-    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_q, cap * DIM * sizeof(double)));
-    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_dist, cap * KNN_FILTER_MAX_K * sizeof(double)));
-    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_idx, cap * KNN_FILTER_MAX_K * sizeof(uint32_t)));
-    PRGPU_CUDA_TRY(cudaMalloc(&sc.fb_lo, cap * sizeof(uint32_t)));
-    sc.fb_capacity = cap;
-  }
-  gather_queries_kernel<<<(nflag + 127) / 128, 128, 0, stream>>>(queries, lo, DIM, sc.flags + 1, nflag, sc.fb_q,
-                                                                sc.fb_lo); PRGPU_COUNT_LAUNCH(1);
-  PRGPU_CUDA_TRY(cudaGetLastError());
-  rc = knn_search_exact(DIM, t, sc.fb_q, nflag, k, lo ? sc.fb_lo : nullptr, sc.fb_idx, sc.fb_dist, sc, sm_count,
-                        stream, nullptr);
-  if (rc != PRGPU_OK)
-    return rc;
-  scatter_rows_kernel<<<(nflag * k + 127) / 128, 128, 0, stream>>>(sc.flags + 1, nflag, k, sc.fb_idx, sc.fb_dist,
-                                                                  idx_out, dist_out); PRGPU_COUNT_LAUNCH(1);
-  PRGPU_CUDA_TRY(cudaGetLastError());
-  return PRGPU_OK;
+  return filter_fallback<DIM>(t, queries, nq, k, lo, idx_out, dist_out, sc, sm_count, stream, nflag);
 }
 
 } // namespace
 
-int knn_search(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev,
-               uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
-               KernelTimer *timer, int force_exact) {
-  const bool eligible = !force_exact && t.ptsf != nullptr && dim <= 7 && k >= 1 &&
-                        k <= KNN_FILTER_MAX_K && nq >= (uint32_t)FT_THREADS && t.n >= 8192;
-  if (!eligible)
+static bool filter_eligible(int dim, const KnnTreeView &t, uint32_t nq, int k, int force_exact) {
+  return !force_exact && t.ptsf != nullptr && dim <= 7 && k >= 1 && k <= KNN_FILTER_MAX_K &&
+         nq >= (uint32_t)FT_THREADS && t.n >= 8192;
+}
+
+int knn_search_deferred(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k,
+                        const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count,
+                        cudaStream_t stream, KernelTimer *timer, int force_exact, bool *pending) {
+  if (pending)
+    *pending = false;
+  if (!filter_eligible(dim, t, nq, k, force_exact))
     return knn_search_exact(dim, t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, timer);
   switch (dim) {
 #define PRGPU_DIM_CASE(D)                                                                          \
   case D:                                                                                          \
-    return filter_path<D>(t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, timer);
+    return filter_path<D>(t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, timer, pending);
     PRGPU_DIM_CASE(1)
     PRGPU_DIM_CASE(2)
     PRGPU_DIM_CASE(3)
@@ -768,6 +786,32 @@ int knn_search(int dim, const KnnTreeView &t, const double *queries_dev, uint32_
 #undef PRGPU_DIM_CASE
   }
   return fail(PRGPU_ELIMIT, "knn: dim must be in [1,PRGPU_MAX_DIM]");
+}
+
+int knn_search_finish(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k,
+                      const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count,
+                      cudaStream_t stream, uint32_t nflag) {
+  switch (dim) {
+#define PRGPU_DIM_CASE(D)                                                                          \
+  case D:                                                                                          \
+    return filter_fallback<D>(t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, nflag);
+    PRGPU_DIM_CASE(1)
+    PRGPU_DIM_CASE(2)
+    PRGPU_DIM_CASE(3)
+    PRGPU_DIM_CASE(4)
+    PRGPU_DIM_CASE(5)
+    PRGPU_DIM_CASE(6)
+    PRGPU_DIM_CASE(7)
+#undef PRGPU_DIM_CASE
+  }
+  return fail(PRGPU_ELIMIT, "knn: dim must be in [1,PRGPU_MAX_DIM]");
+}
+
+int knn_search(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev,
+               uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
+               KernelTimer *timer, int force_exact) {
+  return knn_search_deferred(dim, t, queries_dev, nq, k, lo_dev, idx_dev, dist_dev, scratch, sm_count, stream, timer,
+                             force_exact, nullptr);
 }
 
 } // namespace prgpu

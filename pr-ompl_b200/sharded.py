@@ -33,3 +33,15 @@ def sharded_nearest_k(local_search, merge, dist, world, queries, nq, k, bufs):
     dist.all_gather_into_tensor(bufs["gdist"].view(world * nq, k), bufs["dist"])
     merge(bufs["gidx"], bufs["gdist"], world, nq, k, bufs["fidx"], bufs["fdist"])
     return bufs["fidx"], bufs["fdist"]
+
+
+def make_comm(P, dist, device, rank, world):
+    """prgpu communicator for this rank: rank 0 draws the NCCL unique id (prgpu_comm_unique_id), the 128 bytes
+    travel over the host application's own channel -- here torch.distributed -- and every rank calls
+    prgpu_comm_init.  The data path afterwards is C ABI only (prgpu_knn_nearest_k_sharded_device ...)."""
+    import torch
+    buf = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", device))
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(P.Comm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return P.Comm(device, rank, world, unique_id=bytes(buf.cpu().numpy().tobytes()))

@@ -82,3 +82,20 @@ def test_rrtc_4096_queries(P, O, synth, gpu_world, oracle_world):
         got = rb.fetch(qi, int(s["n_start"][qi]), int(s["n_goal"][qi]))
         for key in ("start_parent", "goal_parent", "start_states", "goal_states", "path"):
             assert np.array_equal(got[key], ref[key]), (qi, key)
+
+
+def test_sharded_c_abi_on_all_visible_gpus():
+    """prgpu_comm_* + prgpu_knn_nearest_k_sharded_device + prgpu_check_motion_batch_sharded_device under
+    torchrun on every GPU of the box (tests/multigpu_check.py); needs at least 2."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611",
+                        os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -80,3 +80,45 @@ def test_shard_bounds(P):
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [e - s for s, e in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _comm_worker(rank, world, port, out):
+    """prgpu_comm_init_custom with a gloo all-gather injected: the C-ABI communicator's plumbing (rank/size,
+    block placement rank r at r * bytes) on CPU, host-only communicator (device -1)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    import prgpu_loader
+    P = prgpu_loader.load()
+
+    def allgather(ctx, send, recv, nbytes, stream):
+        s = torch.frombuffer((C.c_uint8 * nbytes).from_address(send), dtype=torch.uint8)
+        r = torch.frombuffer((C.c_uint8 * (nbytes * world)).from_address(recv), dtype=torch.uint8)
+        dist.all_gather_into_tensor(r, s)
+        return 0
+
+    comm = P.Comm(-1, rank, world, allgather=allgather)
+    ok = P.lib().prgpu_comm_rank(comm.h) == rank and P.lib().prgpu_comm_size(comm.h) == world
+    n = 1000
+    send = np.full(n, rank + 1, dtype=np.uint8)
+    send[:4] = np.frombuffer(np.uint32(0xABCD0000 + rank).tobytes(), dtype=np.uint8)
+    recv = np.zeros(n * world, dtype=np.uint8)
+    comm.allgather(send, recv, n)
+    for r in range(world):
+        blk = recv[r * n:(r + 1) * n]
+        ok = ok and np.frombuffer(blk[:4].tobytes(), dtype=np.uint32)[0] == 0xABCD0000 + r and (blk[4:] == r + 1).all()
+    # the compute entry points refuse a host-only communicator (and there is no GPU here anyway)
+    comm.close()
+    with open(out + str(rank), "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_c_abi_comm_custom_allgather_two_ranks(tmp_path):
+    out = str(tmp_path / "comm")
+    mp.spawn(_comm_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out + "0").read() == "ok" and open(out + "1").read() == "ok"
