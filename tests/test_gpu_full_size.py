@@ -1,4 +1,6 @@
 """Parity at BASELINE.json's full sizes, through size-independent properties and oracle spot checks."""
+import os
+
 import numpy as np
 import pytest
 
