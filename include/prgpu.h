@@ -80,6 +80,16 @@ int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64
  * synchronises the stream once per call (it reads the number of unproven queries).  force_exact != 0
  * disables the filter. */
 int prgpu_knn_set_search_mode(prgpu_knn_t *h, int force_exact);
+/* Sub-linear search.  Batched calls without `lo` (>= 16 queries, k <= 32) over >= 2^17 points are served by a
+ * balanced k-d tree built on the device over the configuration buffer: same results bit for bit under the
+ * (distance, index) order, ~1e-3 of the pairs.  The index is built at the second such call on an unchanged
+ * point set (so a structure refilled before every search never builds one); add/clear make it stale.
+ * prgpu_knn_set_search_mode(h, 2) keeps the brute-force paths only (mode 1: the exact fp64 kernel only;
+ * mode 3: the index whenever it can answer -- no `lo`, k <= 32, >= 128 points -- built at once; mode 0: auto).
+ * indexed_nodes: points covered by a valid index (0: none); leaves_visited: 32-point leaves evaluated by
+ * all index searches so far (reading it synchronises the device).  Any pointer may be NULL. */
+int prgpu_knn_index_stats(prgpu_knn_t *h, uint64_t *indexed_nodes, float *build_ms, uint32_t *builds,
+                          uint64_t *index_calls, uint64_t *leaves_visited);
 /* number of calls served by the filter path and of queries that needed the exact fallback */
 int prgpu_knn_search_stats(prgpu_knn_t *h, uint64_t *filter_calls, uint64_t *fallback_queries);
 /* measurement aid: when on, CUDA events bracket the search kernel of every nearest_k call on

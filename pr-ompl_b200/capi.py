@@ -51,6 +51,8 @@ SIGNATURES = {
     "prgpu_knn_nearest_k": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
     "prgpu_knn_nearest_k_device": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "prgpu_knn_set_search_mode": (C.c_int, [c_vp, C.c_int]),
+    "prgpu_knn_index_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float), c_u32p,
+                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "prgpu_knn_search_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "prgpu_knn_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "prgpu_knn_last_kernel_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
@@ -181,13 +183,20 @@ class KnnIndex:
         return n.value
 
     def set_search_mode(self, force_exact):
-        """force_exact=True disables the fp32 filter path (results are identical either way)."""
+        """0 auto (k-d index, tensor-core filter or exact kernel, whichever is cheapest), 1 / True exact fp64 kernel only,
+        2 brute force without the index, 3 the index whenever it can answer.  Results are identical in every mode."""
         _check(lib().prgpu_knn_set_search_mode(self.h, int(force_exact)))
 
     def search_stats(self):
         a, b = C.c_uint64(), C.c_uint64()
         _check(lib().prgpu_knn_search_stats(self.h, C.byref(a), C.byref(b)))
         return dict(filter_calls=a.value, fallback_queries=b.value)
+
+    def index_stats(self):
+        n, ms, b, c, v = C.c_uint64(), C.c_float(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _check(lib().prgpu_knn_index_stats(self.h, C.byref(n), C.byref(ms), C.byref(b), C.byref(c), C.byref(v)))
+        return dict(indexed_nodes=n.value, build_ms=ms.value, builds=b.value, index_calls=c.value,
+                    leaves_visited=v.value)
 
     def set_profiling(self, on=True):
         _check(lib().prgpu_knn_set_profiling(self.h, int(on)))

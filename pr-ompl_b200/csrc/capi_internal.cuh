@@ -3,6 +3,7 @@
 #include <vector>
 #include "check_motion.cuh"
 #include "knn.cuh"
+#include "kdtree.cuh"
 
 namespace prgpu {
 // grow-only device buffer
@@ -36,7 +37,13 @@ struct prgpu_knn {
   double *pts = nullptr; // SoA, dim x stride
   float *ptsf = nullptr; // fp32 mirror, stride x 8 (dim <= 7 only)
   double *xmax2 = nullptr; // device scalar: max |x|^2
-  int force_exact = 0;
+  int force_exact = 0;             // search mode 1: exact brute-force kernel only
+  int no_index = 0;                // search mode 2: brute force (filter / exact) without the k-d index
+  int force_index = 0;             // search mode 3: the k-d index whenever it can answer (tests)
+  prgpu::KdIndex kd;               // sub-linear index over nodes [0, kd.n); stale when kd_valid is false
+  bool kd_valid = false;
+  unsigned kd_pending = 0;         // eligible searches seen on the current node set without an index
+  unsigned long long kd_calls = 0;
   prgpu::KnnTreeView view() const {
     prgpu::KnnTreeView v;
     v.pts = pts;
@@ -69,3 +76,7 @@ struct prgpu_world {
   std::vector<cudaEvent_t> copy_events;
 };
 
+
+// search dispatch shared by the single-GPU and the sharded entry points (capi.cu)
+int knn_dispatch(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev, uint32_t *idx_dev,
+                 double *dist_dev, cudaStream_t stream, bool *pending);

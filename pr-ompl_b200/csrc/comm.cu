@@ -224,8 +224,7 @@ int prgpu_knn_nearest_k_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const do
     bool pending = false;
     int r2;
     if (!redo) {
-      r2 = knn_search_deferred(h->dim, h->view(), queries_dev, (uint32_t)nq, k, nullptr, li, ld, h->scratch,
-                               h->sm_count, stream, &h->timer, h->force_exact, &pending);
+      r2 = knn_dispatch(h, queries_dev, (uint32_t)nq, k, nullptr, li, ld, stream, &pending);
     } else {
       r2 = knn_search_finish(h->dim, h->view(), queries_dev, (uint32_t)nq, k, nullptr, li, ld, h->scratch, h->sm_count,
                              stream, my_flags);

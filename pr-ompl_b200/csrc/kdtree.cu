@@ -1,0 +1,499 @@
+// K1, sub-linear form: a balanced k-d tree over the tree's configuration buffer, built
+// and searched on the device, returning EXACTLY what the brute-force kernels return -- the k nearest under
+// the (sqrt-distance, insertion index) order of NearestNeighborsLinear / findKnnNodes
+// (pr_ompl/src/RRTConnect.cpp:181, frechet/src/util.cpp:34-58) -- while touching ~3e3 of 1e7 nodes per query.
+//
+// Build (one sort per level, no recursion): the node order is a permutation `perm`; level l splits every
+// segment [floor(s n / 2^l), floor((s+1) n / 2^l)) at its middle position after sorting the segment by the
+// coordinate of the segment's widest cell side.  All segments of a level are sorted by ONE radix sort of
+// (segment id << 32 | order-preserving bits of the fp32-rounded coordinate).  L = ceil(log2(n / 32)) levels
+// leave leaves of 16..32 nodes, stored as fp64 SoA blocks of 32 slots (one slot per lane; unused slots hold
+// +inf) with the nodes' insertion indices.  An internal node keeps 16 bytes: split dimension, the fp32 cut
+// value, and its cell's bounds along that dimension.
+//
+// Search: one warp per query, depth-first, nearer child first.  The squared distance `rd` from the query to
+// the current cell is maintained incrementally (entering the far child replaces the split dimension's term
+// by the squared distance to the cutting plane; cells are nested boxes, so the term being replaced is known
+// from the node's own bounds) and a subtree is skipped when rd exceeds the k-th best so far.  Because the
+// sort key is the fp32 ROUNDING of a coordinate, the planes are widened by one fp32 ulp on either side; rd is
+// compared with a 1e-12 relative slack; so pruning never drops a node the reference would rank.  A leaf is
+// evaluated by the whole warp in the reference's arithmetic (sub, mul, add in dimension order, no FMA;
+// sqrt only for a node that may enter the list) and the k best live one per lane, kept sorted by ballot +
+// shuffle insertion under (distance, index).
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cmath>
+#include "kdtree.cuh"
+
+namespace prgpu {
+namespace {
+#ifndef KD_PPL
+#define KD_PPL 2
+#endif
+constexpr int KD_PPL_ = KD_PPL;       // leaf slots per lane
+constexpr int KD_LEAF = 32 * KD_PPL_; // slots per leaf
+constexpr int KD_WARPS = 8;           // queries per block
+
+__device__ __forceinline__ uint32_t ord32(float f) { // order-preserving float -> uint
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord32(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+__host__ __device__ __forceinline__ uint64_t kd_bound(uint64_t s, uint64_t n, int level) { return (s * n) >> level; }
+__device__ __forceinline__ uint32_t kd_segment(uint64_t p, uint64_t n, int level) {
+  // the s with bound(s) <= p < bound(s + 1)
+  return (uint32_t)((((p + 1) << level) + n - 1) / n - 1);
+}
+
+// global bounding box (fp32, rounded outward) by warp reduction + ordered atomics
+__global__ void kd_extent_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, int dim,
+                                 uint32_t *__restrict__ lo_ord, uint32_t *__restrict__ hi_ord) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int d = 0; d < dim; ++d) {
+    float lo = INFINITY, hi = -INFINITY;
+    if (i < n) {
+      const double x = pts[(size_t)d * stride + i];
+      lo = __double2float_rd(x);
+      hi = __double2float_ru(x);
+    }
+    for (int o = 16; o; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(lo_ord + d, ord32(lo));
+      atomicMax(hi_ord + d, ord32(hi));
+    }
+  }
+}
+__global__ void kd_root_cell_kernel(const uint32_t *lo_ord, const uint32_t *hi_ord, int dim, float *cell) {
+  const int d = threadIdx.x;
+  if (d < dim) {
+    cell[d] = unord32(lo_ord[d]);
+    cell[8 + d] = unord32(hi_ord[d]);
+  }
+}
+// per segment of level l: split dimension = widest side of its cell (16 floats: lo[8], hi[8])
+__global__ void kd_choose_dim_kernel(const float *__restrict__ cells, uint32_t nseg, int dim, uint32_t first_node,
+                                     KdNode *__restrict__ nodes) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg)
+    return;
+  const float *c = cells + (size_t)s * 16;
+  int best = 0;
+  float bw = -1.f;
+  for (int d = 0; d < dim; ++d) {
+    const float w = c[8 + d] - c[d];
+    if (w > bw) {
+      bw = w;
+      best = d;
+    }
+  }
+  KdNode nd;
+  nd.dim = (uint32_t)best;
+  nd.cut = nd.cut_lo = nd.cut_hi = 0.f;
+  nd.pad[0] = nd.pad[1] = 0.f;
+  nd.lo = c[best];
+  nd.hi = c[8 + best];
+  nodes[first_node + s] = nd;
+}
+__global__ void kd_keys_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, int level,
+                               const uint32_t *__restrict__ perm, const KdNode *__restrict__ nodes, uint32_t first_node,
+                               uint64_t *__restrict__ keys) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n)
+    return;
+  const uint32_t s = kd_segment(p, n, level);
+  const uint32_t d = nodes[first_node + s].dim;
+  const float x = __double2float_rn(pts[(size_t)d * stride + perm[p]]);
+  keys[p] = ((uint64_t)s << 32) | ord32(x);
+}
+__global__ void kd_iota_kernel(uint32_t *perm, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    perm[i] = i;
+}
+// after the sort of level l: cut value of every segment and the cells of its two children
+__global__ void kd_cut_kernel(const uint64_t *__restrict__ keys, uint32_t n, int level, uint32_t nseg,
+                              uint32_t first_node, KdNode *__restrict__ nodes, const float *__restrict__ cells,
+                              float *__restrict__ child_cells) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg)
+    return;
+  const uint64_t mid = kd_bound(2 * (uint64_t)s + 1, n, level + 1); // first position of the right half
+  const float cut = unord32((uint32_t)(keys[mid] & 0xFFFFFFFFull));
+  KdNode nd = nodes[first_node + s];
+  nd.cut = cut;
+  nd.cut_lo = nextafterf(cut, -INFINITY);
+  nd.cut_hi = nextafterf(cut, INFINITY);
+  nodes[first_node + s] = nd;
+  const float *c = cells + (size_t)s * 16;
+  float *l = child_cells + (size_t)(2 * s) * 16, *r = l + 16;
+  for (int i = 0; i < 16; ++i) {
+    l[i] = c[i];
+    r[i] = c[i];
+  }
+  // the sort key is the fp32 rounding of the coordinate: left nodes lie below the next fp32 above the cut,
+  // right nodes above the next fp32 below it
+  l[8 + nd.dim] = fminf(c[8 + nd.dim], nd.cut_hi);
+  r[nd.dim] = fmaxf(c[nd.dim], nd.cut_lo);
+}
+__global__ void kd_leaves_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, int dim, int levels,
+                                 const uint32_t *__restrict__ perm, double *__restrict__ leaf_pts,
+                                 uint32_t *__restrict__ leaf_idx) {
+  const uint32_t leaf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (leaf >= (1u << levels))
+    return;
+  const uint64_t b = kd_bound(leaf, n, levels), e = kd_bound((uint64_t)leaf + 1, n, levels);
+  for (int j = 0; j < KD_PPL_; ++j) {
+    const uint32_t slot = j * 32 + lane;
+    const bool have = b + slot < e;
+    const uint32_t src = have ? perm[b + slot] : 0u;
+    leaf_idx[(size_t)leaf * KD_LEAF + slot] = have ? src : PRGPU_INVALID_INDEX;
+    for (int d = 0; d < dim; ++d)
+      leaf_pts[((size_t)leaf * dim + d) * KD_LEAF + slot] = have ? pts[(size_t)d * stride + src] : (double)INFINITY;
+  }
+}
+
+// ---- search ----------------------------------------------------------------------------------------------
+// A treelet = a node and its descendants down to depth 3 (15 nodes), loaded by lanes 0..14 in ONE round
+// trip: lane t = 2^v - 1 + o holds the o-th node of depth v below the treelet's root.  Right after the load
+// every lane evaluates ITS node against the query (which side is nearer; by how much entering the far side
+// raises the squared cell distance), so a step of the descent is two shuffles, one add and one compare.
+struct KdTreelet {
+  double delta; // pd^2 - off^2: what entering the far child adds to the squared cell distance
+  bool left;    // the query lies on the left of the cut
+};
+__device__ __forceinline__ KdTreelet kd_load_treelet(const KdNode *__restrict__ nodes, uint32_t root,
+                                                     uint32_t first_leaf, int lane, const double *__restrict__ xq) {
+  KdTreelet t;
+  t.delta = 0.0;
+  t.left = true;
+  if (lane < 15) {
+    const int v = 31 - __clz(lane + 1);                  // depth below the root: 0..3
+    const uint32_t o = (uint32_t)(lane + 1) - (1u << v); // position inside that depth
+    const uint64_t idx = (((uint64_t)root + 1) << v) - 1 + o;
+    if (idx < first_leaf) {
+      const KdNode nd = nodes[idx];
+      const double x = xq[nd.dim];
+      t.left = x < (double)nd.cut;
+      // distance to the far half-space (planes widened by one fp32 ulp, see kd_cut_kernel)
+      const double pd = t.left ? fmax(0.0, (double)nd.cut_lo - x) : fmax(0.0, x - (double)nd.cut_hi);
+      // term of this dimension already inside the cell distance: distance to the cell's own bounds
+      const double off = fmax(0.0, fmax((double)nd.lo - x, x - (double)nd.hi));
+      t.delta = pd * pd - off * off;
+    }
+  }
+  return t;
+}
+
+#ifndef KD_MINB
+#define KD_MINB 4
+#endif
+template <int DIM>
+__global__ void __launch_bounds__(KD_WARPS * 32, KD_MINB)
+kd_search_kernel(const KdNode *__restrict__ nodes, const double *__restrict__ leaf_pts,
+                 const uint32_t *__restrict__ leaf_idx, const float *__restrict__ root_cell, int levels,
+                 uint32_t index_base,
+                 const double *__restrict__ queries, uint32_t nq, int k, uint32_t *__restrict__ idx_out,
+                 double *__restrict__ dist_out, unsigned long long *__restrict__ visited) {
+  __shared__ double sq[KD_WARPS][8];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * KD_WARPS + w;
+  if (q >= nq)
+    return;
+  double qx[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d)
+    qx[d] = queries[(size_t)q * DIM + d];
+  if (lane < DIM)
+    sq[w][lane] = queries[(size_t)q * DIM + lane];
+  __syncwarp();
+  const double *xq = sq[w];
+  // the k best so far, sorted ascending by (distance, index): lane j holds the j-th
+  double best_d = INFINITY;
+  uint32_t best_i = PRGPU_INVALID_INDEX;
+  double r2hi = INFINITY; // largest squared sum that can still enter the list
+  const uint32_t first_leaf = (1u << levels) - 1u;
+  // squared distance from the query to the root cell (0 inside the bounding box of the nodes)
+  double rd = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    const double o = fmax(0.0, fmax((double)root_cell[d] - qx[d], qx[d] - (double)root_cell[8 + d]));
+    rd += o * o;
+  }
+  // the stack lives in registers: lane i holds entry i (depth <= 27 < 32)
+  uint32_t stk_node = 0;
+  double stk_rd = 0.0;
+  int sp = 0;
+  uint32_t node = 0;
+  KdTreelet tl = kd_load_treelet(nodes, node, first_leaf, lane, xq);
+  int tv = 0;        // depth of `node` inside the held treelet
+  uint32_t to = 0;   // its position inside that depth
+  unsigned long long nvis = 0;
+  bool alive = true;
+  while (alive) {
+    // ---- descend from `node` to a leaf, nearer child first, far children onto the stack ----
+    while (node < first_leaf) {
+      if (tv > 3) { // below the held treelet: fetch the next one (one round trip per three levels)
+        tl = kd_load_treelet(nodes, node, first_leaf, lane, xq);
+        tv = 0;
+        to = 0;
+      }
+      const int src = (1 << tv) - 1 + (int)to;
+      const bool left = __shfl_sync(0xFFFFFFFFu, (int)tl.left, src) != 0;
+      const double rd_far = rd + __shfl_sync(0xFFFFFFFFu, tl.delta, src);
+      if (rd_far * (1.0 - 1e-12) <= r2hi) {
+        const uint32_t far = 2 * node + (left ? 2u : 1u);
+        if (lane == sp) {
+          stk_node = far;
+          stk_rd = rd_far;
+        }
+        ++sp;
+#ifndef KD_NO_PREFETCH
+        // the subtree will be popped later: start moving what the pop will need (a far LEAF's rows to L2;
+        // an internal node's treelet rows towards L1)
+        if (far >= first_leaf) {
+          const char *base = reinterpret_cast<const char *>(leaf_pts + (size_t)(far - first_leaf) * DIM * KD_LEAF);
+          if (lane * 128 < DIM * KD_LEAF * 8)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + lane * 128));
+        } else if (lane < 4) {
+          const uint64_t idx = (((uint64_t)far + 1) << lane) - 1;
+          if (idx < first_leaf)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + idx));
+        }
+#endif
+      }
+      node = 2 * node + (left ? 1u : 2u);
+      ++tv;
+      to = 2 * to + (left ? 0u : 1u);
+    }
+    // ---- leaf: KD_PPL slots per lane (independent loads), reference arithmetic ----
+    const uint32_t leaf = node - first_leaf;
+    const double *lp = leaf_pts + (size_t)leaf * DIM * KD_LEAF + lane;
+    double c0[KD_PPL_][DIM];
+    uint32_t my_i[KD_PPL_];
+#pragma unroll
+    for (int j = 0; j < KD_PPL_; ++j) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        c0[j][d] = lp[d * KD_LEAF + j * 32];
+      my_i[j] = leaf_idx[(size_t)leaf * KD_LEAF + j * 32 + lane];
+    }
+    // while those loads are in flight: the treelet of the subtree the stack says comes next (dropped if
+    // this leaf shrinks the bound below that subtree's distance)
+    uint32_t nx_node = 0;
+    double nx_rd = 0.0;
+    KdTreelet nx_tl = tl;
+    if (sp > 0) {
+      nx_node = __shfl_sync(0xFFFFFFFFu, stk_node, sp - 1);
+      nx_rd = __shfl_sync(0xFFFFFFFFu, stk_rd, sp - 1);
+      if (nx_node < first_leaf)
+        nx_tl = kd_load_treelet(nodes, nx_node, first_leaf, lane, xq);
+    }
+    double s[KD_PPL_];
+#pragma unroll
+    for (int j = 0; j < KD_PPL_; ++j) {
+      double a = __dsub_rn(c0[j][0], qx[0]);
+      s[j] = __dmul_rn(a, a);
+#pragma unroll
+      for (int d = 1; d < DIM; ++d) {
+        a = __dsub_rn(c0[j][d], qx[d]);
+        s[j] = __dadd_rn(s[j], __dmul_rn(a, a));
+      }
+    }
+    nvis += 1;
+#pragma unroll
+    for (int j = 0; j < KD_PPL_; ++j) {
+      unsigned cand = __ballot_sync(0xFFFFFFFFu, my_i[j] != PRGPU_INVALID_INDEX && s[j] <= r2hi);
+      while (cand) {
+        const int c = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const double cs = __shfl_sync(0xFFFFFFFFu, s[j], c);
+        const uint32_t ci = __shfl_sync(0xFFFFFFFFu, my_i[j], c);
+        if (cs > r2hi)
+          continue; // the bound shrank since the ballot
+        const double cd = __dsqrt_rn(cs);
+        // position = number of list entries that precede (cd, ci)
+        const bool before = lane < k && (best_d < cd || (best_d == cd && best_i < ci));
+        const int pos = __popc(__ballot_sync(0xFFFFFFFFu, before));
+        if (pos >= k)
+          continue;
+        const double up_d = __shfl_up_sync(0xFFFFFFFFu, best_d, 1);
+        const uint32_t up_i = __shfl_up_sync(0xFFFFFFFFu, best_i, 1);
+        if (lane == pos) {
+          best_d = cd;
+          best_i = ci;
+        } else if (lane > pos && lane < k) {
+          best_d = up_d;
+          best_i = up_i;
+        }
+        const double r = __shfl_sync(0xFFFFFFFFu, best_d, k - 1);
+        if (r < INFINITY)
+          r2hi = __dmul_ru(r, r) * (1.0 + 0x1p-50);
+      }
+    }
+    // ---- next subtree: pop until one is still within the bound ----
+    alive = false;
+    bool first_pop = true;
+    while (sp > 0) {
+      --sp;
+      const uint32_t pn = first_pop ? nx_node : __shfl_sync(0xFFFFFFFFu, stk_node, sp);
+      const double prd = first_pop ? nx_rd : __shfl_sync(0xFFFFFFFFu, stk_rd, sp);
+      if (prd * (1.0 - 1e-12) <= r2hi) {
+        node = pn;
+        rd = prd;
+        if (pn < first_leaf)
+          tl = first_pop ? nx_tl : kd_load_treelet(nodes, pn, first_leaf, lane, xq);
+        tv = 0;
+        to = 0;
+        alive = true;
+        break;
+      }
+      first_pop = false;
+    }
+  }
+  if (lane < k) {
+    idx_out[(size_t)q * k + lane] = best_i == PRGPU_INVALID_INDEX ? best_i : best_i + index_base;
+    if (dist_out)
+      dist_out[(size_t)q * k + lane] = best_d;
+  }
+  if (visited && lane == 0)
+    atomicAdd(visited, nvis);
+}
+} // namespace
+
+void KdIndex::release() {
+  for (void *p : {(void *)nodes, (void *)leaf_pts, (void *)leaf_idx, (void *)visited, (void *)root_cell})
+    if (p)
+      cudaFree(p);
+  nodes = nullptr;
+  leaf_pts = nullptr;
+  leaf_idx = nullptr;
+  visited = nullptr;
+  root_cell = nullptr;
+  n = 0;
+  levels = 0;
+}
+
+int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint32_t n, cudaStream_t stream) {
+  kd.release();
+  if (n < 2 * KD_LEAF)
+    return fail(PRGPU_EINVAL, "kd_build: too few nodes");
+  int L = 0;
+  while ((((uint64_t)n + (1ull << L) - 1) >> L) > (uint64_t)KD_LEAF)
+    ++L;
+  const uint32_t nleaf = 1u << L;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, stream);
+  uint32_t *perm_a = nullptr, *perm_b = nullptr, *ext = nullptr;
+  uint64_t *keys_a = nullptr, *keys_b = nullptr;
+  float *cells_a = nullptr, *cells_b = nullptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  auto cleanup = [&]() {
+    for (void *p : {(void *)perm_a, (void *)perm_b, (void *)ext, (void *)keys_a, (void *)keys_b, (void *)cells_a,
+                    (void *)cells_b, tmp})
+      if (p)
+        cudaFree(p);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  };
+#define KD_TRY(expr)                                                                               \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      cleanup();                                                                                   \
+      kd.release();                                                                                \
+      return fail(_e == cudaErrorMemoryAllocation ? PRGPU_ENOMEM : PRGPU_ECUDA,                    \
+                  std::string("kd_build: ") + #expr + ": " + cudaGetErrorString(_e));              \
+    }                                                                                              \
+  } while (0)
+  KD_TRY(cudaMalloc(&kd.nodes, sizeof(KdNode) * (size_t)std::max<uint32_t>(nleaf - 1, 1)));
+  KD_TRY(cudaMalloc(&kd.leaf_pts, sizeof(double) * (size_t)nleaf * dim * KD_LEAF));
+  KD_TRY(cudaMalloc(&kd.leaf_idx, sizeof(uint32_t) * (size_t)nleaf * KD_LEAF));
+  KD_TRY(cudaMalloc(&kd.visited, sizeof(unsigned long long)));
+  KD_TRY(cudaMalloc(&kd.root_cell, sizeof(float) * 16));
+  KD_TRY(cudaMemsetAsync(kd.visited, 0, sizeof(unsigned long long), stream));
+  KD_TRY(cudaMalloc(&perm_a, sizeof(uint32_t) * (size_t)n));
+  KD_TRY(cudaMalloc(&perm_b, sizeof(uint32_t) * (size_t)n));
+  KD_TRY(cudaMalloc(&keys_a, sizeof(uint64_t) * (size_t)n));
+  KD_TRY(cudaMalloc(&keys_b, sizeof(uint64_t) * (size_t)n));
+  KD_TRY(cudaMalloc(&cells_a, sizeof(float) * 16 * (size_t)nleaf));
+  KD_TRY(cudaMalloc(&cells_b, sizeof(float) * 16 * (size_t)nleaf));
+  KD_TRY(cudaMalloc(&ext, sizeof(uint32_t) * 16));
+  KD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, perm_a, perm_b, (int)n, 0, 64, stream));
+  KD_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  KD_TRY(cudaMemsetAsync(ext, 0xFF, sizeof(uint32_t) * 8, stream));     // lo: max ordered value
+  KD_TRY(cudaMemsetAsync(ext + 8, 0x00, sizeof(uint32_t) * 8, stream)); // hi: min ordered value
+  kd_extent_kernel<<<nb, 256, 0, stream>>>(pts_soa, stride, n, dim, ext, ext + 8); PRGPU_COUNT_LAUNCH(1);
+  KD_TRY(cudaMemsetAsync(cells_a, 0, sizeof(float) * 16, stream));
+  kd_root_cell_kernel<<<1, 32, 0, stream>>>(ext, ext + 8, dim, cells_a); PRGPU_COUNT_LAUNCH(1);
+  KD_TRY(cudaMemcpyAsync(kd.root_cell, cells_a, sizeof(float) * 16, cudaMemcpyDeviceToDevice, stream));
+  kd_iota_kernel<<<nb, 256, 0, stream>>>(perm_a, n); PRGPU_COUNT_LAUNCH(1);
+  for (int l = 0; l < L; ++l) {
+    const uint32_t nseg = 1u << l, first = nseg - 1u;
+    kd_choose_dim_kernel<<<(nseg + 127) / 128, 128, 0, stream>>>(cells_a, nseg, dim, first, kd.nodes); PRGPU_COUNT_LAUNCH(1);
+    kd_keys_kernel<<<nb, 256, 0, stream>>>(pts_soa, stride, n, l, perm_a, kd.nodes, first, keys_a); PRGPU_COUNT_LAUNCH(1);
+    KD_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, perm_a, perm_b, (int)n, 0, 32 + l, stream));
+    PRGPU_COUNT_LAUNCH(5);
+    kd_cut_kernel<<<(nseg + 127) / 128, 128, 0, stream>>>(keys_b, n, l, nseg, first, kd.nodes, cells_a, cells_b); PRGPU_COUNT_LAUNCH(1);
+    std::swap(perm_a, perm_b);
+    std::swap(cells_a, cells_b);
+  }
+  kd_leaves_kernel<<<(nleaf + 7) / 8, 256, 0, stream>>>(pts_soa, stride, n, dim, L, perm_a, kd.leaf_pts, kd.leaf_idx); PRGPU_COUNT_LAUNCH(1);
+  KD_TRY(cudaGetLastError());
+  cudaEventRecord(e1, stream);
+  KD_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  kd.build_ms = ms;
+  kd.n = n;
+  kd.levels = L;
+  kd.dim = dim;
+  ++kd.builds;
+  cleanup();
+  return PRGPU_OK;
+#undef KD_TRY
+}
+
+int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev, uint32_t nq, int k, uint32_t *idx_dev,
+              double *dist_dev, cudaStream_t stream, KernelTimer *timer) {
+  if (k < 1 || k > 32)
+    return fail(PRGPU_ELIMIT, "kd_search: k must be in [1,32]");
+  if (nq == 0)
+    return PRGPU_OK;
+  const unsigned blocks = (nq + KD_WARPS - 1) / KD_WARPS;
+  if (timer)
+    timer->begin(stream);
+  switch (kd.dim) {
+#define KD_CASE(D)                                                                                 \
+  case D:                                                                                          \
+    kd_search_kernel<D><<<blocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell,   \
+                                                              kd.levels, index_base, queries_dev, nq, k, idx_dev, \
+                                                              dist_dev, kd.count_visits ? kd.visited : nullptr);  \
+    break;
+    KD_CASE(1)
+    KD_CASE(2)
+    KD_CASE(3)
+    KD_CASE(4)
+    KD_CASE(5)
+    KD_CASE(6)
+    KD_CASE(7)
+    KD_CASE(8)
+#undef KD_CASE
+  default:
+    return fail(PRGPU_ELIMIT, "kd_search: dim must be in [1,8]");
+  }
+  PRGPU_COUNT_LAUNCH(1);
+  if (timer)
+    timer->end(stream);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+} // namespace prgpu

@@ -8,9 +8,9 @@ pytestmark = pytest.mark.gpu
 
 
 def test_knn_sweep_full_size(P, O, synth):
-    """N=1e7, Q=4096, k=16 and k=1: the fast path equals the exact kernel on every query; a spread
-    subset equals the CPU oracle; rows are sorted; reported distances are the reference's distance of the
-    reported nodes."""
+    """N=1e7, Q=4096, k=16 and k=1: the tensor-core filter path (mode 2) and the k-d index (mode 0, built at
+    the second batched search) equal the exact kernel (mode 1) on every query; a spread subset equals the CPU
+    oracle; rows are sorted; reported distances are the reference's distance of the reported nodes."""
     import torch
     n, nq = 10_000_000, 4096
     pts = synth.cloud(0, n)
@@ -19,13 +19,19 @@ def test_knn_sweep_full_size(P, O, synth):
     t.add(pts)
     sub = np.arange(0, nq, 128)
     for k in (16, 1):
-        t.set_search_mode(False)
+        t.set_search_mode(2)
         fi, fd = t.nearest_k(q, k)
         st = t.search_stats()
         assert st["filter_calls"] > 0
         t.set_search_mode(True)
         ei, ed = t.nearest_k(q, k)
         assert np.array_equal(fi, ei) and np.array_equal(fd, ed)
+        t.set_search_mode(0)
+        t.nearest_k(q, k)
+        ii, id_ = t.nearest_k(q, k)
+        ist = t.index_stats()
+        assert ist["indexed_nodes"] == n and ist["index_calls"] >= 1
+        assert np.array_equal(ii, ei) and np.array_equal(id_, ed)
         oi, od = O.knn(pts, q[sub], k, nthreads=16)
         assert np.array_equal(fi[sub], oi) and np.array_equal(fd[sub], od)
         assert np.all(np.diff(fd, axis=1) >= 0)

@@ -229,3 +229,68 @@ def test_add_device_on_foreign_stream_after_create_and_regrow(P, O, synth):
         st = tree.search_stats()
         assert st["filter_calls"] >= 1 and st["fallback_queries"] == 0
         tree.close()
+
+
+@pytest.mark.parametrize("n,dim", [(1 << 17, 7), (300_017, 7), (200_000, 3)])
+def test_kd_index_equals_brute_force_and_oracle(P, O, n, dim):
+    """The sub-linear path (k-d index built on the device at the second batched search of an unchanged
+    node set) returns what the brute-force kernels and the CPU oracle return, bit for bit: duplicates, ties,
+    queries that ARE tree nodes, queries far outside the nodes' bounding box, k up to 32."""
+    rng = np.random.default_rng(n)
+    pts = rng.uniform(-np.pi, np.pi, size=(n, dim))
+    pts[n // 3: n // 3 + 5000] = pts[:5000]                       # exact duplicates (index tie-break)
+    pts[-3000:] = pts[-1] + 1e-9 * rng.normal(size=(3000, dim))   # a tight cluster
+    q = rng.uniform(-np.pi, np.pi, size=(100, dim))            # < 128 queries: 1.5e8 pairs make the index pay
+    q[:40] = pts[rng.integers(0, n, 40)]
+    q[40:48] = 50.0 * rng.normal(size=(8, dim))                   # far outside the bounding box
+    q[48:56] = pts[-1]
+    tree = P.KnnIndex(dim)
+    tree.add(pts)
+    for k in (1, 16, 32):
+        tree.set_search_mode(2)                                   # brute force, no index
+        bi, bd = tree.nearest_k(q, k)
+        tree.set_search_mode(3)                                   # the index whenever it can answer
+        gi, gd = tree.nearest_k(q, k)
+        gi2, gd2 = tree.nearest_k(q, k)
+        st = tree.index_stats()
+        assert st["indexed_nodes"] == n and st["index_calls"] >= 1, st
+        oi, od = O.knn(pts, q, k, nthreads=8)
+        assert np.array_equal(bi, oi) and np.array_equal(bd, od)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+        assert np.array_equal(gi2, oi) and np.array_equal(gd2, od)
+    # an append makes the index stale: brute force until the second search rebuilds it
+    more = rng.uniform(-np.pi, np.pi, size=(1000, dim))
+    tree.add(more)
+    allp = np.vstack([pts, more])
+    assert tree.index_stats()["indexed_nodes"] == 0
+    tree.set_search_mode(0)                                       # auto: too few pairs here, brute force answers
+    gi, gd = tree.nearest_k(q, 5)
+    assert tree.index_stats()["indexed_nodes"] == 0
+    tree.set_search_mode(3)
+    for _ in range(3):
+        gi, gd = tree.nearest_k(q, 5)
+        oi, od = O.knn(allp, q, 5, nthreads=8)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    st = tree.index_stats()
+    assert st["indexed_nodes"] == n + 1000 and st["builds"] == 2
+    assert 0 < st["leaves_visited"]
+    tree.close()
+
+
+def test_kd_index_degenerate_clouds(P, O):
+    """All nodes identical / nodes on a line / heavy duplication: the splits degenerate, the answers do not."""
+    rng = np.random.default_rng(5)
+    n = 1 << 17
+    q = rng.uniform(-1, 1, size=(64, 7))
+    clouds = [np.tile(rng.uniform(-1, 1, size=(1, 7)), (n, 1)),
+              np.outer(np.linspace(-1, 1, n), np.ones(7)),
+              np.repeat(rng.uniform(-1, 1, size=(n // 64, 7)), 64, axis=0)]
+    for pts in clouds:
+        tree = P.KnnIndex(7)
+        tree.add(pts)
+        tree.set_search_mode(3)
+        gi, gd = tree.nearest_k(q, 16)
+        assert tree.index_stats()["indexed_nodes"] == n
+        oi, od = O.knn(pts, q, 16, nthreads=8)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+        tree.close()
