@@ -533,6 +533,8 @@ def measure_knn(env, args, want_cpu):
 
     ms_per_step, launches, clocks = env.timed(step, flush_l2=False)
     kms = env.max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+    ist = tree.index_stats()          # before anything below refills the tree
+    stats_main = tree.search_stats()
     cross = {}
     if world > 1:
         ci, cd = fi.clone(), fd.clone()
@@ -572,36 +574,69 @@ def measure_knn(env, args, want_cpu):
     e2e_s2 = env.timed_host(lambda: e2e_step(reupload=True), K=max(3, env.K // 3))
     h2d, d2h = Q * 56, Q * k * 12
     algo_bytes = n_local * 56 + Q * 56 + Q * k * 12
-    pairs = n_local * Q / (kms * 1e-3)
     tpeak, tsrc = tensor_peak()
-    tf = pairs * 16.0 / 1e12
     mma_peak = None
     if rank == 0:
         v = P.capi.C.c_double()
         if P.lib().prgpu_diag_mma_tf32_peak(env.local_rank, P.capi.C.byref(v)) == 0:
             mma_peak = v.value
-    summ = ncu_summary("knn_collect_kernel")
-    traffic = None if not summ or summ.get("dram_bytes") is None else int(summ["dram_bytes"] * (n_local / float(N)))
-    roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-            "traffic": traffic,
-            "traffic_note": "ncu dram read+write bytes of one launch over the full 1e7-node tree (profiles/"
-                            "ncu_summary.json), scaled to this rank's shard",
-            "kernel": "knn_collect_kernel", "kernel_ms": kms, "peak_source": tsrc,
-            "flops_per_launch": n_local * Q * 16.0,
-            "tf32_mma_sync": {"peak": mma_peak, "frac": None if not mma_peak else tf / mma_peak,
-                              "pairs_per_s": pairs,
-                              "note": "peak = issue rate of mma.sync.m16n8k8 TF32 measured live by "
-                                      "prgpu_diag_mma_tf32_peak in this run (16 warps/SM, 8 independent "
-                                      "accumulator fragments per warp)"},
-            "issue_slots_busy_pct_ncu": None if not summ else summ.get("issue_slots_busy_pct"),
-            "hbm": {"achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": env.hbm_peak, "unit": "GB/s",
-                    "frac": algo_bytes / (kms * 1e-3) / 1e9 / env.hbm_peak, "peak_source": env.peak_src,
-                    "algorithmic_bytes_per_launch": algo_bytes,
-                    "note": "SURVEY §8(d)'s fp64 formula 56*N + 56*Q + 12*Q*k; the scan itself streams the "
-                            "40 B/node TF32 mirror"}}
-    extra = {"phase_breakdown": breakdown}
+
+    def hbm_block(ms):
+        return {"achieved": algo_bytes / (ms * 1e-3) / 1e9, "peak": env.hbm_peak, "unit": "GB/s",
+                "frac": algo_bytes / (ms * 1e-3) / 1e9 / env.hbm_peak, "peak_source": env.peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes}
+
+    def scan_roofline(ms):
+        """The brute-force scan (knn_collect_kernel): tensor-bound, 16 flop per (query, node) pair."""
+        pairs = n_local * Q / (ms * 1e-3)
+        tf = pairs * 16.0 / 1e12
+        summ = ncu_summary("knn_collect_kernel")
+        traffic = None if not summ or summ.get("dram_bytes") is None else int(summ["dram_bytes"] * (n_local / float(N)))
+        return {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                "traffic": traffic,
+                "traffic_note": "ncu dram read+write bytes of one launch over the full 1e7-node tree (profiles/"
+                                "ncu_summary.json), scaled to this rank's shard",
+                "kernel": "knn_collect_kernel", "kernel_ms": ms, "peak_source": tsrc,
+                "flops_per_launch": n_local * Q * 16.0,
+                "tf32_mma_sync": {"peak": mma_peak, "frac": None if not mma_peak else tf / mma_peak,
+                                  "pairs_per_s": pairs,
+                                  "note": "peak = issue rate of mma.sync.m16n8k8 TF32 measured live by "
+                                          "prgpu_diag_mma_tf32_peak in this run (16 warps/SM, 8 independent "
+                                          "accumulator fragments per warp)"},
+                "issue_slots_busy_pct_ncu": None if not summ else summ.get("issue_slots_busy_pct"),
+                "hbm": dict(hbm_block(ms), note="SURVEY §8(d)'s fp64 formula 56*N + 56*Q + 12*Q*k; the scan itself "
+                                                "streams the 40 B/node TF32 mirror")}
+
+    indexed = ist["indexed_nodes"] > 0
+    if indexed:
+        summ = ncu_summary("kd_search_kernel")
+        roof = dict(hbm_block(kms), bound="hbm", kernel="kd_search_kernel", kernel_ms=kms,
+                    traffic=None if not summ else summ.get("dram_bytes"),
+                    issue_slots_busy_pct_ncu=None if not summ else summ.get("issue_slots_busy_pct"),
+                    binds="latency: one warp per query walks ~300 tree nodes and ~120 leaves of 64 nodes, a dependent "
+                          "chain; the algorithmic bytes are SURVEY §8(d)'s brute-force figure (the whole tree once), the "
+                          "search itself touches ~0.05 % of the tree per query but different leaves for different "
+                          "queries (ncu traffic above)",
+                    index={"build_ms": ist["build_ms"], "builds": ist["builds"],
+                           "leaves_of_64_per_query": ist["leaves_visited"] / max(1, ist["index_calls"] * Q)})
+    else:
+        roof = scan_roofline(kms)
+    extra = {"phase_breakdown": breakdown, "search_path": "k-d index" if indexed else "brute-force scan"}
     if cross:
         extra["sharded_c_abi"] = cross
+    if indexed and not args.no_extra:
+        # the same step with the index switched off: the batched brute-force / tiled scan BASELINE.json's north
+        # star names (TF32 tensor-core filter + fp64 re-rank); identical results
+        tree.set_search_mode(2)
+        kernel_ms.clear()
+        bms, _, _ = env.timed(step, flush_l2=False)
+        bk = env.max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+        extra["brute_force"] = {"queries_per_s": Q / (bms * 1e-3), "ms_per_step": bms, "roofline": scan_roofline(bk),
+                                "note": "prgpu_knn_set_search_mode(h, 2): no index; this is the path that scales with "
+                                        "the shard size when the tree is node-sharded"}
+        tree.set_search_mode(0)
+        step()
+        step()
 
     # ---- the alternative partitioning (multi-GPU): tree replicated, QUERIES split ----
     if world > 1 and not args.no_extra:
@@ -661,7 +696,7 @@ def measure_knn(env, args, want_cpu):
                                       "frac_of_hbm_peak": n_local * 56 / (ms1 * 1e-3) / 1e9 / env.hbm_peak,
                                       "note": "Q=1 (a planner's nearest() on a 1e7-node tree): the HBM-bound shape, "
                                               "exact fp64 kernel"}
-    stats = tree.search_stats()
+    stats = stats_main
     del pts_dev
     tree.close()
     torch.cuda.empty_cache()
