@@ -244,6 +244,25 @@ int prgpu_nnf_get_edges(prgpu_nnf_t *h, uint32_t *edges, uint8_t *flags);
  * cost of every search (max_lazy_iters entries) or NULL.  May be called again to continue. */
 int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *res, uint32_t *path_vertices,
                     uint32_t cap_path, double *goal_cost_trace);
+/* Host-callback form: the reference takes forward kinematics, the task-space metric and state
+ * validity as opaque user functions (frechet/include/NNFrechet.hpp:43-59, :303-312; call sites NNFrechet.cpp:295,
+ * :372 FK, :495 metric, :665,:675 isValid).  For a robot or metric the device has no model of, the host planner
+ *   1. prgpu_nnf_create_graph(): findKnnNodes for every node + the NN graph with its sub-sampled vertices
+ *      (configurations only) on the device;
+ *   2. reads the V configurations back (prgpu_nnf_get_vertices, pose12 = NULL), runs ITS FK and metric and hands
+ *      over the node-weight table weights[v * R + r] = distance(ref_pose[r], FK(state[v])) by NN-graph vertex id
+ *      (rows of the two dummy vertices: the weights of ref_pose[0] / ref_pose[R-1] themselves, NNFrechet.cpp:409,414);
+ *   3. installs an edge evaluator -- evaluateEdge (:655-683) over the caller's own validity checker: for n edges
+ *      (from, to: n x dof) write free[i] = 1 if edge i is collision-free, 0 if in collision; return 0, or non-zero
+ *      to abort the solve with an error;
+ *   4. prgpu_nnf_solve() as in the device form: the bottleneck search, path extraction and LazySP bookkeeping are
+ *      the same code, only the weights come from the table and the verdicts from the callback. */
+typedef int (*prgpu_nnf_edge_eval_fn)(void *user, const double *from, const double *to, uint32_t n, uint8_t *free_out);
+int prgpu_nnf_create_graph(int device, int dof, const prgpu_nnf_params *params, int R, const uint32_t *layer_counts,
+                           const double *ik_states, prgpu_nnf_t **out);
+int prgpu_nnf_set_weights(prgpu_nnf_t *h, const double *weights /* n_vertices x R */);
+/* also accepted by a device-form handle: replaces the device's checkMotion batch by the caller's verdicts */
+int prgpu_nnf_set_edge_evaluator(prgpu_nnf_t *h, prgpu_nnf_edge_eval_fn fn, void *user);
 /* search kernel: 0 (default) = banded column-wise DP (only cells that can lie on a path of cost
  * <= tau are stored; tau is widened until the optimum is provably inside) executed as a dataflow
  * over per-vertex ready flags; 1 = full R x V table swept by anti-diagonals; 2 = the banded DP swept

@@ -7,7 +7,7 @@
 //   FK        = SynthWorld::fk                                  (same call as oracle/nnf_port.cpp)
 //   IK        = hands out the next `numSolutions` pre-drawn states of `ik_states` (the reference's
 //               call order is first waypoint, last waypoint, then waypoints 1..R-2, NNFrechet.cpp:418-448)
-//   distance  = Euclidean distance of the pose translations
+//   distance  = Euclidean distance of the pose translations (ref_nnf_set_metric(1): plus a rotation term)
 //   validity  = SynthChecker (clearance > 0)
 // Built into oracle/_ref/libref_frechet.so (and libref_frechet_rev.so with the edge-list iteration
 // order reversed) by oracle/Makefile; exports ref_nnf_run.
@@ -54,8 +54,24 @@ double translationDistance(Eigen::Isometry3d &a, Eigen::Isometry3d &b) {
   const double dx = a(0, 3) - b(0, 3), dy = a(1, 3) - b(1, 3), dz = a(2, 3) - b(2, 3);
   return std::sqrt(dx * dx + dy * dy + dz * dz);
 }
+// a user metric with a rotation term (kind 1): translation distance + 0.25 x Frobenius norm of the
+// rotation difference -- exercises the host-callback form of the product
+int g_metric_kind = 0;
+double taskMetric(Eigen::Isometry3d &a, Eigen::Isometry3d &b) {
+  double d = translationDistance(a, b);
+  if (g_metric_kind == 1) {
+    double f = 0.0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        f += (a(r, c) - b(r, c)) * (a(r, c) - b(r, c));
+    d = d + 0.25 * std::sqrt(f);
+  }
+  return d;
+}
 const double *values(const ob::State *s) { return s->as<ob::RealVectorStateSpace::StateType>()->values; }
 } // namespace
+
+extern "C" void ref_nnf_set_metric(int kind) { g_metric_kind = kind; }
 
 extern "C" int ref_nnf_run(const void *world, uint32_t n_ref_full, const double *ref_full_pose12, int W, int M,
                            int k, int D, int seed, const double *ik_states, uint32_t n_ik_avail,
@@ -110,7 +126,7 @@ extern "C" int ref_nnf_run(const void *world, uint32_t n_ref_full, const double 
       }
       return out;
     });
-    planner.setDistanceFunc(&translationDistance);
+    planner.setDistanceFunc(&taskMetric);
 
     auto t0 = std::chrono::steady_clock::now();
     planner.setup();

@@ -101,6 +101,9 @@ SIGNATURES = {
     "prgpu_nnf_knn_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "prgpu_nnf_get_edges": (C.c_int, [c_vp, c_vp, c_vp]),
     "prgpu_nnf_solve": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, C.c_uint32, c_vp]),
+    "prgpu_nnf_create_graph": (C.c_int, [C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.POINTER(c_vp)]),
+    "prgpu_nnf_set_weights": (C.c_int, [c_vp, c_vp]),
+    "prgpu_nnf_set_edge_evaluator": (C.c_int, [c_vp, c_vp, c_vp]),
     "prgpu_nnf_set_mode": (C.c_int, [c_vp, C.c_int]),
     "prgpu_nnf_band_info": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), c_u32p]),
     "prgpu_nnf_last_dp_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
@@ -444,6 +447,58 @@ class Nnf:
         nv, ne, ni = C.c_uint32(), C.c_uint32(), C.c_uint32()
         _check(lib().prgpu_nnf_graph_info(self.h, C.byref(nv), C.byref(ne), C.byref(ni)))
         self.n_vertices, self.n_edges, self.n_ik = nv.value, ne.value, ni.value
+
+    @classmethod
+    def host_form(cls, dof, layer_counts, ik_states, num_nn=5, discretization=3, check_resolution=0.05, device=0):
+        """Host-callback form (prgpu_nnf_create_graph): the caller supplies node weights (set_weights) and
+        edge verdicts (set_edge_evaluator); the device does findKnnNodes, the NN graph and the searches."""
+        self = cls.__new__(cls)
+        self.world = None
+        self.dof = dof
+        self.k = num_nn
+        counts = np.ascontiguousarray(layer_counts, dtype=np.uint32)
+        ik = np.ascontiguousarray(ik_states, dtype=np.float64).reshape(-1, dof)
+        assert counts.sum() == len(ik)
+        self.R = len(counts)
+        p = NnfParams(num_nn, discretization, check_resolution)
+        h = c_vp()
+        _check(lib().prgpu_nnf_create_graph(device, dof, C.byref(p), len(counts), _ptr(counts), _ptr(ik), C.byref(h)))
+        self.h = h
+        nv, ne, ni = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().prgpu_nnf_graph_info(self.h, C.byref(nv), C.byref(ne), C.byref(ni)))
+        self.n_vertices, self.n_edges, self.n_ik = nv.value, ne.value, ni.value
+        return self
+
+    def states(self):
+        st = np.empty((self.n_vertices, self.dof if self.world is None else self.world.dof))
+        _check(lib().prgpu_nnf_get_vertices(self.h, _ptr(st), None))
+        return st
+
+    def set_weights(self, weights):
+        """weights[v, r] = task distance between reference pose r and the pose of NN-graph vertex v."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert w.shape == (self.n_vertices, self.R)
+        _check(lib().prgpu_nnf_set_weights(self.h, _ptr(w)))
+
+    def set_edge_evaluator(self, fn):
+        """fn(from[n, dof], to[n, dof]) -> array of n booleans, True = the edge is collision-free."""
+        dof = self.dof if self.world is None else self.world.dof
+        proto = C.CFUNCTYPE(C.c_int, c_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32,
+                            C.POINTER(C.c_uint8))
+
+        def thunk(_user, a, b, n, out):
+            try:
+                fa = np.ctypeslib.as_array(a, shape=(n, dof))
+                fb = np.ctypeslib.as_array(b, shape=(n, dof))
+                ok = np.asarray(fn(fa.copy(), fb.copy())).astype(np.uint8)
+                for i in range(n):
+                    out[i] = int(ok[i])
+                return 0
+            except Exception:  # noqa: BLE001 -- reported through the C ABI's error return
+                return 1
+
+        self._eval_cb = proto(thunk)  # keep alive
+        _check(lib().prgpu_nnf_set_edge_evaluator(self.h, C.cast(self._eval_cb, c_vp), None))
 
     def close(self):
         if getattr(self, "h", None) and _lib is not None:

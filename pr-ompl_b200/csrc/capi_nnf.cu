@@ -15,7 +15,16 @@
 using namespace prgpu;
 
 struct prgpu_nnf {
-  prgpu_world *world = nullptr;
+  prgpu_world *world = nullptr; // NULL in the host-callback form (prgpu_nnf_create_graph)
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // host-callback form: node weights handed over by the caller, edge verdicts from a callback
+  bool host_form = false, weights_set = false;
+  std::vector<double> ftab_host; // V x R by vertex id
+  DevBuf d_ftab;                 // V x R by sorted position
+  prgpu_nnf_edge_eval_fn eval_fn = nullptr;
+  void *eval_user = nullptr;
   prgpu_nnf_params params;
   int R = 0, dof = 0;
   uint32_t V = 0, E = 0, nIk = 0, Lv = 0;
@@ -76,7 +85,7 @@ __global__ void nnf_block_edge_kernel(NnfEdgeRec *edge, uint32_t slot, uint8_t *
 int nnf_build_band(prgpu_nnf *h, cudaStream_t s) {
   const int R = h->R;
   const uint32_t V = h->V;
-  int rc = nnf_band_launch(R, V, h->g.pnn, h->g.pref, h->tau_ub, h->d_band_lo.as<uint32_t>(),
+  int rc = nnf_band_launch(R, V, h->g.pnn, h->g.pref, h->g.ftab, h->tau_ub, h->d_band_lo.as<uint32_t>(),
                            h->d_band_w.as<unsigned long long>(), s);
   if (rc != PRGPU_OK)
     return rc;
@@ -114,7 +123,7 @@ int nnf_build_band(prgpu_nnf *h, cudaStream_t s) {
 
 // lower bound on the optimum: every start-goal path visits every reference row
 int nnf_initial_tau(prgpu_nnf *h, cudaStream_t s) {
-  int rc = nnf_rowmin_launch(h->R, h->V, h->g.pnn, h->g.pref, h->d_rowmin.as<unsigned long long>(), s);
+  int rc = nnf_rowmin_launch(h->R, h->V, h->g.pnn, h->g.pref, h->g.ftab, h->d_rowmin.as<unsigned long long>(), s);
   if (rc != PRGPU_OK)
     return rc;
   std::vector<double> rowmin(h->R);
@@ -153,25 +162,34 @@ int prgpu_nnf_band_info(prgpu_nnf_t *h, double *tau, uint64_t *cells, uint32_t *
 int prgpu_nnf_destroy(prgpu_nnf_t *h) {
   if (!h)
     return PRGPU_OK;
-  cudaSetDevice(h->world->device);
-  cudaStreamSynchronize(h->world->stream);
-  for (DevBuf *b : {&h->d_states, &h->d_pose, &h->d_lvl_start, &h->d_level, &h->d_pred_off, &h->d_pred_pos,
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (DevBuf *b : {&h->d_ftab, &h->d_states, &h->d_pose, &h->d_lvl_start, &h->d_level, &h->d_pred_off, &h->d_pred_pos,
                     &h->d_pred_eid, &h->d_blocked, &h->d_pnn, &h->d_pref, &h->d_B, &h->d_path, &h->d_pn, &h->d_cost,
                     &h->d_band_lo, &h->d_band_w, &h->d_col_off, &h->d_meta, &h->d_edge, &h->d_Bc, &h->d_scan_tmp,
                     &h->d_rowmin, &h->d_done})
     b->release();
   h->timer.destroy();
+  if (h->own_stream && h->stream)
+    cudaStreamDestroy(h->stream);
   delete h;
   return PRGPU_OK;
 }
+} // extern "C"
 
-int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, const double *ref_pose12,
-                     const uint32_t *layer_counts, const double *ik_states, prgpu_nnf_t **out) {
+namespace {
+// buildNNGraph + (device form) buildTensorProductGraph.  w == NULL: host-callback form -- poses and
+// node weights are the caller's (prgpu_nnf_set_weights), ref_pose12 is not used.
+int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_params *params, int R,
+                      const double *ref_pose12, const uint32_t *layer_counts, const double *ik_states,
+                      prgpu_nnf_t **out) {
   if (!out)
     return fail(PRGPU_EINVAL, "nnf_create: out is NULL");
   *out = nullptr;
-  if (!w || !params || !ref_pose12 || !layer_counts)
+  if (!params || (w && !ref_pose12) || !layer_counts)
     return fail(PRGPU_EINVAL, "nnf_create: NULL argument");
+  if (!w && (dof_in < 1 || dof_in > PRGPU_MAX_DIM))
+    return fail(PRGPU_EINVAL, "nnf_create_graph: dof out of range");
   if (R < 2)
     return fail(PRGPU_EINVAL, "nnf_create: referencePath is empty!"); // setRefPath, NNFrechet.cpp:24-25
   if (params->num_nn <= 0 || params->num_nn > PRGPU_MAX_K)
@@ -180,16 +198,34 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
     return fail(PRGPU_EINVAL, "nnf_create: discretization must be positive!");
   if (!(params->check_resolution > 0.0))
     return fail(PRGPU_EINVAL, "nnf_create: check_resolution must be positive");
-  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
-  cudaStream_t s = w->stream;
-  const int dof = w->host.dof, k = params->num_nn, D = params->discretization;
+  if (w)
+    device = w->device;
+  PRGPU_CUDA_TRY(cudaSetDevice(device));
+  const int dof = w ? w->host.dof : dof_in, k = params->num_nn, D = params->discretization;
 
   prgpu_nnf *h = new prgpu_nnf();
   h->world = w;
+  h->device = device;
+  h->host_form = w == nullptr;
+  if (w) {
+    h->stream = w->stream;
+    h->sm_count = w->sm_count;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+      e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+      delete h;
+      return fail(PRGPU_ECUDA, std::string("nnf_create_graph: ") + cudaGetErrorString(e));
+    }
+    h->own_stream = true;
+  }
+  cudaStream_t s = h->stream;
   h->params = *params;
   h->R = R;
   h->dof = dof;
-  h->ref_pose.assign(ref_pose12, ref_pose12 + (size_t)R * 12);
+  if (ref_pose12)
+    h->ref_pose.assign(ref_pose12, ref_pose12 + (size_t)R * 12);
   uint64_t N = 0;
   for (int r = 0; r < R; ++r)
     N += layer_counts[r];
@@ -235,9 +271,9 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
       if ((rc = d_ik.reserve(std::max<size_t>(N * dof * 8, 16))) != PRGPU_OK)
         break;
       cudaMemcpyAsync(d_ik.p, ik_states, N * dof * 8, cudaMemcpyHostToDevice, s);
-      if ((rc = prgpu_knn_create(w->device, dof, std::max<uint32_t>(ML, 1), &A)) != PRGPU_OK)
+      if ((rc = prgpu_knn_create(device, dof, std::max<uint32_t>(ML, 1), &A)) != PRGPU_OK)
         break;
-      if ((rc = prgpu_knn_create(w->device, dof, std::max<uint32_t>(nInterior, 1), &B)) != PRGPU_OK)
+      if ((rc = prgpu_knn_create(device, dof, std::max<uint32_t>(nInterior, 1), &B)) != PRGPU_OK)
         break;
       prgpu_knn_set_index_base(A, 2 + M0);
       prgpu_knn_set_index_base(B, 2 + M0 + ML);
@@ -349,11 +385,13 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
   if (N)
     NNF_CUDA(cudaMemcpyAsync(h->d_states.as<double>() + 2 * (size_t)dof, ik_states, N * dof * 8,
                              cudaMemcpyHostToDevice, s));
-  NNF_CUDA(cudaMemcpyAsync(h->d_pose.p, ref_pose12, 12 * 8, cudaMemcpyHostToDevice, s)); // c0 pose (:409)
-  NNF_CUDA(cudaMemcpyAsync(h->d_pose.as<double>() + 12, ref_pose12 + 12 * (size_t)(R - 1), 12 * 8,
-                           cudaMemcpyHostToDevice, s)); // c1 pose (:414)
-  NNF_TRY(fk_launch(w->host, w->dev, h->d_states.as<double>() + 2 * (size_t)dof, N,
-                    h->d_pose.as<double>() + 2 * 12, s)); // sampleIKNodes :295
+  if (w) {
+    NNF_CUDA(cudaMemcpyAsync(h->d_pose.p, ref_pose12, 12 * 8, cudaMemcpyHostToDevice, s)); // c0 pose (:409)
+    NNF_CUDA(cudaMemcpyAsync(h->d_pose.as<double>() + 12, ref_pose12 + 12 * (size_t)(R - 1), 12 * 8,
+                             cudaMemcpyHostToDevice, s)); // c1 pose (:414)
+    NNF_TRY(fk_launch(w->host, w->dev, h->d_states.as<double>() + 2 * (size_t)dof, N,
+                      h->d_pose.as<double>() + 2 * 12, s)); // sampleIKNodes :295
+  }
   {
     DevBuf d_src, d_dst, d_step;
     int rc = upload(d_src, sub_src, s);
@@ -362,7 +400,7 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
     if (rc == PRGPU_OK)
       rc = upload(d_step, sub_step, s);
     if (rc == PRGPU_OK)
-      rc = nnf_subsample_launch(w->dev, dof, (uint32_t)sub_src.size(), 2 + (uint32_t)N, d_src.as<uint32_t>(),
+      rc = nnf_subsample_launch(w ? w->dev : nullptr, dof, (uint32_t)sub_src.size(), 2 + (uint32_t)N, d_src.as<uint32_t>(),
                                 d_dst.as<uint32_t>(), d_step.as<uint32_t>(), D, h->d_states.as<double>(),
                                 h->d_pose.as<double>(), s);
     cudaStreamSynchronize(s);
@@ -372,9 +410,11 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
     NNF_TRY(rc);
   }
   h->states.resize((size_t)V * dof);
-  h->pose.resize((size_t)V * 12);
   NNF_CUDA(cudaMemcpyAsync(h->states.data(), h->d_states.p, (size_t)V * dof * 8, cudaMemcpyDeviceToHost, s));
-  NNF_CUDA(cudaMemcpyAsync(h->pose.data(), h->d_pose.p, (size_t)V * 12 * 8, cudaMemcpyDeviceToHost, s));
+  if (w) {
+    h->pose.resize((size_t)V * 12);
+    NNF_CUDA(cudaMemcpyAsync(h->pose.data(), h->d_pose.p, (size_t)V * 12 * 8, cudaMemcpyDeviceToHost, s));
+  }
 
   // ---- predecessors (by vertex, creation order), topological levels, level-sorted order ---------
   h->pred_off_v.assign(V + 1, 0);
@@ -442,7 +482,7 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
   h->blocked.assign(E, 0);
   h->known.assign(E, -1);
   NNF_TRY(upload(h->d_blocked, h->blocked, s));
-  {
+  if (w) {
     DevBuf d_vop;
     int rc = upload(d_vop, h->vertex_of_pos, s);
     if (rc == PRGPU_OK)
@@ -453,7 +493,7 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
     d_vop.release();
     NNF_TRY(rc);
   }
-  {
+  if (w) {
     std::vector<double> pref((size_t)R * 3);
     for (int r = 0; r < R; ++r) {
       pref[3 * r + 0] = ref_pose12[12 * (size_t)r + 3];
@@ -486,8 +526,9 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
   g.pred_pos = h->d_pred_pos.as<uint32_t>();
   g.pred_eid = h->d_pred_eid.as<uint32_t>();
   g.blocked = h->d_blocked.as<uint8_t>();
-  g.pnn = h->d_pnn.as<double>();
-  g.pref = h->d_pref.as<double>();
+  g.pnn = w ? h->d_pnn.as<double>() : nullptr;
+  g.pref = w ? h->d_pref.as<double>() : nullptr;
+  g.ftab = nullptr; // host-callback form: set by prgpu_nnf_set_weights
   g.B = nullptr; // allocated on first use of the full-table mode
   g.start_pos = h->pos_of_vertex[c0];
   g.goal_pos = h->pos_of_vertex[c1];
@@ -501,6 +542,7 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
   bg.pred_pos = g.pred_pos;
   bg.pnn = g.pnn;
   bg.pref = g.pref;
+  bg.ftab = nullptr;
   bg.Bc = nullptr;
   bg.start_pos = g.start_pos;
   bg.goal_pos = g.goal_pos;
@@ -508,6 +550,57 @@ int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, co
   return PRGPU_OK;
 #undef NNF_TRY
 #undef NNF_CUDA
+}
+} // namespace
+
+extern "C" {
+int prgpu_nnf_create(prgpu_world_t *w, const prgpu_nnf_params *params, int R, const double *ref_pose12,
+                     const uint32_t *layer_counts, const double *ik_states, prgpu_nnf_t **out) {
+  if (!w) {
+    if (out)
+      *out = nullptr;
+    return fail(PRGPU_EINVAL, "nnf_create: NULL argument");
+  }
+  return nnf_create_common(w, 0, 0, params, R, ref_pose12, layer_counts, ik_states, out);
+}
+
+int prgpu_nnf_create_graph(int device, int dof, const prgpu_nnf_params *params, int R, const uint32_t *layer_counts,
+                           const double *ik_states, prgpu_nnf_t **out) {
+  return nnf_create_common(nullptr, device, dof, params, R, nullptr, layer_counts, ik_states, out);
+}
+
+int prgpu_nnf_set_weights(prgpu_nnf_t *h, const double *weights) {
+  if (!h || !weights)
+    return fail(PRGPU_EINVAL, "nnf_set_weights: NULL argument");
+  if (!h->host_form)
+    return fail(PRGPU_EINVAL, "nnf_set_weights: the handle was created with a device world (prgpu_nnf_create)");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  const size_t R = (size_t)h->R, V = h->V;
+  for (size_t i = 0; i < R * V; ++i)
+    if (!(weights[i] >= 0.0))
+      return fail(PRGPU_EINVAL, "nnf_set_weights: node weights must be non-negative numbers");
+  h->ftab_host.assign(weights, weights + R * V);
+  std::vector<double> sorted(R * V);
+  for (size_t p = 0; p < V; ++p)
+    std::memcpy(sorted.data() + p * R, weights + (size_t)h->vertex_of_pos[p] * R, R * 8);
+  int rc = upload(h->d_ftab, sorted, h->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->g.ftab = h->bg.ftab = h->d_ftab.as<double>();
+  h->weights_set = true;
+  h->band_valid = false; // a new table: the band and every cost are stale
+  h->tau_ub = 0.0;
+  h->dirty_level = 0;
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_set_edge_evaluator(prgpu_nnf_t *h, prgpu_nnf_edge_eval_fn fn, void *user) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "nnf_set_edge_evaluator: NULL handle");
+  h->eval_fn = fn;
+  h->eval_user = user;
+  return PRGPU_OK;
 }
 
 int prgpu_nnf_graph_info(prgpu_nnf_t *h, uint32_t *n_vertices, uint32_t *n_edges, uint32_t *n_ik) {
@@ -534,8 +627,11 @@ int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12) {
     return fail(PRGPU_EINVAL, "nnf_get_vertices: NULL handle");
   if (states)
     std::memcpy(states, h->states.data(), h->states.size() * 8);
-  if (pose12)
+  if (pose12) {
+    if (h->host_form)
+      return fail(PRGPU_EINVAL, "nnf_get_vertices: poses belong to the caller's FK in the host-callback form");
     std::memcpy(pose12, h->pose.data(), h->pose.size() * 8);
+  }
   return PRGPU_OK;
 }
 
@@ -573,8 +669,12 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
                     uint32_t cap_path, double *goal_cost_trace) {
   if (!h || !res)
     return fail(PRGPU_EINVAL, "nnf_solve: NULL argument");
-  PRGPU_CUDA_TRY(cudaSetDevice(h->world->device));
-  cudaStream_t s = h->world->stream;
+  if (h->host_form && !h->weights_set)
+    return fail(PRGPU_EINVAL, "nnf_solve: node weights not set (prgpu_nnf_set_weights)");
+  if (h->host_form && !h->eval_fn)
+    return fail(PRGPU_EINVAL, "nnf_solve: edge evaluator not set (prgpu_nnf_set_edge_evaluator)");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
   const int R = h->R, dof = h->dof;
   const uint32_t V = h->V, c0 = 0, c1 = 1;
   std::memset(res, 0, sizeof(*res));
@@ -596,7 +696,7 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
           return rc;
         h->g.B = h->d_B.as<double>();
       }
-      rc = nnf_dp_launch(h->g, h->world->sm_count, s, &h->timer); // computeShortestPath :109-110
+      rc = nnf_dp_launch(h->g, h->sm_count, s, &h->timer); // computeShortestPath :109-110
       if (rc != PRGPU_OK)
         return rc;
       rc = nnf_backtrack_launch(h->g, h->d_path.as<uint32_t>(), cap_pairs, h->d_pn.as<uint32_t>(),
@@ -618,7 +718,7 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
           rc = nnf_band_dp_launch(h->bg, h->dirty_level, s, &h->timer);
         else
           rc = nnf_flow_dp_launch(h->bg, h->dirty_level >= h->Lv ? h->V : h->lvl_start_host[h->dirty_level],
-                                  ++h->epoch, h->d_done.as<uint32_t>(), h->world->sm_count, s, &h->timer);
+                                  ++h->epoch, h->d_done.as<uint32_t>(), h->sm_count, s, &h->timer);
         if (rc != PRGPU_OK)
           return rc;
         h->dirty_level = h->Lv; // table consistent
@@ -661,7 +761,9 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
         continue;
       if (nnPath.empty() || nnPath.back() != v)
         nnPath.push_back(v);
-      const double c = host_task_distance(h->ref_pose.data() + 12 * (size_t)r, h->pose.data() + 12 * (size_t)v);
+      const double c = h->host_form
+                           ? h->ftab_host[(size_t)v * R + r]
+                           : host_task_distance(h->ref_pose.data() + 12 * (size_t)r, h->pose.data() + 12 * (size_t)v);
       if (c > bottleneck)
         bottleneck = c;
     }
@@ -691,10 +793,15 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
         std::memcpy(to.data() + i * dof, h->states.data() + (size_t)h->edges[todo[i]].second * dof, dof * 8);
       }
       std::vector<uint8_t> ok(todo.size());
-      rc = prgpu_check_motion_batch(h->world, from.data(), to.data(), todo.size(), h->params.check_resolution,
-                                    PRGPU_MODE_NNF_ALPHA, 0, ok.data());
-      if (rc != PRGPU_OK)
-        return rc;
+      if (h->eval_fn) { // the caller's validity checker (evaluateEdge over si_->isValid, NNFrechet.cpp:655-683)
+        if (h->eval_fn(h->eval_user, from.data(), to.data(), (uint32_t)todo.size(), ok.data()) != 0)
+          return fail(PRGPU_EINVAL, "nnf_solve: the edge evaluator reported an error");
+      } else {
+        rc = prgpu_check_motion_batch(h->world, from.data(), to.data(), todo.size(), h->params.check_resolution,
+                                      PRGPU_MODE_NNF_ALPHA, 0, ok.data());
+        if (rc != PRGPU_OK)
+          return rc;
+      }
       for (size_t i = 0; i < todo.size(); ++i)
         h->known[todo[i]] = ok[i] ? 1 : 0;
     }

@@ -34,7 +34,6 @@ __global__ void nnf_subsample_kernel(const DeviceWorld *__restrict__ wp, int dof
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_new)
     return;
-  const DeviceWorld &w = *wp;
   const double t = (1.0 + (double)step[i]) / (double)(D + 1); // NNFrechet.cpp:367
   const double *a = states + (size_t)src[i] * dof;
   const double *b = states + (size_t)dst[i] * dof;
@@ -45,6 +44,9 @@ __global__ void nnf_subsample_kernel(const DeviceWorld *__restrict__ wp, int dof
   const size_t v = (size_t)first_vertex + i;
   for (int k = 0; k < dof; ++k)
     states[v * dof + k] = q[k];
+  if (!wp) // host-callback form: the user's FK runs on the host
+    return;
+  const DeviceWorld &w = *wp;
   double F[12 * (WORLD_MAX_DOF + 1)];
   fk_frames(w, q, F);
   for (int k = 0; k < 12; ++k)
@@ -65,6 +67,12 @@ __global__ void nnf_translations_kernel(const double *__restrict__ pose12, const
 __device__ __forceinline__ double task_distance(const double *a3, const double *b3) {
   const double dx = __dsub_rn(a3[0], b3[0]), dy = __dsub_rn(a3[1], b3[1]), dz = __dsub_rn(a3[2], b3[2]);
   return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+// node weight f[r,s]: the host's table (user metric, frechet/include/NNFrechet.hpp:312) or the translation metric
+__device__ __forceinline__ double node_weight(const double *__restrict__ ftab, int R, const double *__restrict__ pref,
+                                              const double *__restrict__ pnn, uint32_t r, uint32_t s) {
+  return ftab ? ftab[(size_t)s * R + r] : task_distance(pref + 3 * (size_t)r, pnn + 3 * (size_t)s);
 }
 
 __global__ void __launch_bounds__(256) nnf_dp_kernel(const NnfGraphDev g) {
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(256) nnf_dp_kernel(const NnfGraphDev g) {
             m = fmin(m, g.B[(size_t)(r - 1) * V + p]); // step C (:586-596)
         }
         if (m != NNF_INF) {
-          const double fv = task_distance(g.pref + 3 * (size_t)r, g.pnn + 3 * (size_t)s);
+          const double fv = node_weight(g.ftab, R, g.pref, g.pnn, r, s);
           best = fmax(m, fv);
         }
       }
@@ -128,7 +136,7 @@ __global__ void nnf_backtrack_kernel(const NnfGraphDev g, uint32_t *__restrict__
     if (r == 0 && s == g.start_pos)
       break;
     const double target = g.B[(size_t)r * V + s];
-    const double fv = task_distance(g.pref + 3 * (size_t)r, g.pnn + 3 * (size_t)s);
+    const double fv = node_weight(g.ftab, g.R, g.pref, g.pnn, r, s);
     bool found = false;
     uint32_t br = 0, bs = 0;
     // first predecessor (fixed order) whose cost explains this cell's cost
@@ -175,12 +183,12 @@ __global__ void nnf_backtrack_kernel(const NnfGraphDev g, uint32_t *__restrict__
 
 // lower bound on any path's bottleneck: every path visits every row, so cost >= max_r min_n f[r,n]
 __global__ void nnf_rowmin_kernel(int R, uint32_t V, const double *__restrict__ pnn, const double *__restrict__ pref,
-                                  unsigned long long *__restrict__ rowmin_bits) {
+                                  const double *__restrict__ ftab, unsigned long long *__restrict__ rowmin_bits) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t r = blockIdx.y;
   double f = NNF_INF;
   if (s < V)
-    f = task_distance(pref + 3 * (size_t)r, pnn + 3 * (size_t)s);
+    f = node_weight(ftab, R, pref, pnn, r, s);
   // non-negative doubles order like their bit patterns
   unsigned long long b = (unsigned long long)__double_as_longlong(f);
 #pragma unroll
@@ -193,15 +201,14 @@ __global__ void nnf_rowmin_kernel(int R, uint32_t V, const double *__restrict__ 
 }
 
 __global__ void nnf_band_kernel(int R, uint32_t V, const double *__restrict__ pnn, const double *__restrict__ pref,
-                                double tau, uint32_t *__restrict__ band_lo, unsigned long long *__restrict__ band_w64) {
+                                const double *__restrict__ ftab, double tau, uint32_t *__restrict__ band_lo,
+                                unsigned long long *__restrict__ band_w64) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= V)
     return;
-  const double x = pnn[3 * (size_t)s], y = pnn[3 * (size_t)s + 1], z = pnn[3 * (size_t)s + 2];
   int first = -1, last = -1;
   for (int r = 0; r < R; ++r) {
-    const double dx = __dsub_rn(pref[3 * r], x), dy = __dsub_rn(pref[3 * r + 1], y), dz = __dsub_rn(pref[3 * r + 2], z);
-    const double f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    const double f = node_weight(ftab, R, pref, pnn, (uint32_t)r, s);
     if (f <= tau) {
       if (first < 0)
         first = r;
@@ -266,7 +273,12 @@ __global__ void __launch_bounds__(BAND_THREADS) nnf_band_dp_kernel(const NnfBand
       const NnfVertexMeta m = g.meta[s];
       if (m.band_w == 0)
         continue;
-      const double px = g.pnn[3 * (size_t)s], py = g.pnn[3 * (size_t)s + 1], pz = g.pnn[3 * (size_t)s + 2];
+      double px = 0.0, py = 0.0, pz = 0.0;
+      if (!g.ftab) {
+        px = g.pnn[3 * (size_t)s];
+        py = g.pnn[3 * (size_t)s + 1];
+        pz = g.pnn[3 * (size_t)s + 2];
+      }
       double carry = NNF_INF; // x just below the band
       for (uint32_t c0 = 0; c0 < m.band_w; c0 += 32) {
         const bool active = c0 + lane < m.band_w;
@@ -288,9 +300,14 @@ __global__ void __launch_bounds__(BAND_THREADS) nnf_band_dp_kernel(const NnfBand
             if (r > 0 && i1 < pw)
               mm = fmin(mm, __ldcg(g.Bc + rec.col_off + i1));
           }
-          const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
-                       dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
-          const double f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+          double f;
+          if (g.ftab) {
+            f = g.ftab[(size_t)s * g.R + r];
+          } else {
+            const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
+                         dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
+            f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+          }
           gfn.a = f;
           gfn.b = fmax(f, mm);
           if (s == g.start_pos && r == 0)
@@ -348,7 +365,12 @@ nnf_flow_dp_kernel(const NnfBandDev g, uint32_t first_pos, uint32_t epoch, volat
       }
       __threadfence(); // acquire: the columns behind the flags
       __syncwarp();
-      const double px = g.pnn[3 * (size_t)s], py = g.pnn[3 * (size_t)s + 1], pz = g.pnn[3 * (size_t)s + 2];
+      double px = 0.0, py = 0.0, pz = 0.0;
+      if (!g.ftab) {
+        px = g.pnn[3 * (size_t)s];
+        py = g.pnn[3 * (size_t)s + 1];
+        pz = g.pnn[3 * (size_t)s + 2];
+      }
       double carry = NNF_INF;
       for (uint32_t c0 = 0; c0 < m.band_w; c0 += 32) {
         const bool active = c0 + lane < m.band_w;
@@ -395,9 +417,14 @@ nnf_flow_dp_kernel(const NnfBandDev g, uint32_t first_pos, uint32_t epoch, volat
           }
         }
         if (active) {
-          const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
-                       dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
-          const double f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+          double f;
+          if (g.ftab) {
+            f = g.ftab[(size_t)s * g.R + r];
+          } else {
+            const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
+                         dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
+            f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+          }
           gfn.a = f;
           gfn.b = fmax(f, mm);
           if (s == g.start_pos && r == 0)
@@ -459,7 +486,7 @@ __global__ void nnf_band_backtrack_kernel(const NnfBandDev g, uint32_t *__restri
     ++n;
     if (r == 0 && s == g.start_pos)
       break;
-    const double fv = task_distance(g.pref + 3 * (size_t)r, g.pnn + 3 * (size_t)s);
+    const double fv = node_weight(g.ftab, g.R, g.pref, g.pnn, r, s);
     const NnfVertexMeta m = g.meta[s];
     bool found = false;
     uint32_t br = 0, bs = 0;
@@ -560,17 +587,17 @@ int nnf_dp_launch(const NnfGraphDev &g, int sm_count, cudaStream_t stream, Kerne
   return PRGPU_OK;
 }
 
-int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, unsigned long long *rowmin_bits,
-                      cudaStream_t stream) {
+int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, const double *ftab,
+                      unsigned long long *rowmin_bits, cudaStream_t stream) {
   PRGPU_CUDA_TRY(cudaMemsetAsync(rowmin_bits, 0xFF, (size_t)R * sizeof(unsigned long long), stream));
-  nnf_rowmin_kernel<<<dim3((V + 255) / 256, R), 256, 0, stream>>>(R, V, pnn, pref, rowmin_bits); PRGPU_COUNT_LAUNCH(1);
+  nnf_rowmin_kernel<<<dim3((V + 255) / 256, R), 256, 0, stream>>>(R, V, pnn, pref, ftab, rowmin_bits); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }
 
-int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, double tau, uint32_t *band_lo,
-                    unsigned long long *band_w64, cudaStream_t stream) {
-  nnf_band_kernel<<<(V + 127) / 128, 128, 0, stream>>>(R, V, pnn, pref, tau, band_lo, band_w64); PRGPU_COUNT_LAUNCH(1);
+int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, const double *ftab, double tau,
+                    uint32_t *band_lo, unsigned long long *band_w64, cudaStream_t stream) {
+  nnf_band_kernel<<<(V + 127) / 128, 128, 0, stream>>>(R, V, pnn, pref, ftab, tau, band_lo, band_w64); PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

@@ -15,6 +15,8 @@ struct NnfGraphDev {
   const uint8_t *blocked;    // E    : 1 = edge found in collision (markEdgeInCollision)
   const double *pnn;         // V x 3: end-effector translation of sorted vertex s
   const double *pref;        // R x 3: translation of reference pose r
+  const double *ftab;        // V x R node weights f[s*R + r] handed over by the host (user metric), or NULL:
+                             // then f = |pref[r] - pnn[s]| is computed on the fly
   double *B;                 // R x V: bottleneck cost table
   uint32_t start_pos, goal_pos; // sorted positions of c0 / c1
 };
@@ -42,13 +44,14 @@ struct NnfBandDev {
   const NnfEdgeRec *edge;    // E (CSR order)
   const uint32_t *pred_pos;  // E (CSR order): sorted position of the predecessor
   const double *pnn, *pref;
+  const double *ftab;        // as NnfGraphDev::ftab
   double *Bc;
   uint32_t start_pos, goal_pos;
 };
-int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, unsigned long long *rowmin_bits,
-                      cudaStream_t stream);
-int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, double tau, uint32_t *band_lo,
-                    unsigned long long *band_w64, cudaStream_t stream);
+int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, const double *ftab,
+                      unsigned long long *rowmin_bits, cudaStream_t stream);
+int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, const double *ftab, double tau,
+                    uint32_t *band_lo, unsigned long long *band_w64, cudaStream_t stream);
 int nnf_band_pack_launch(uint32_t V, uint32_t E, const uint32_t *band_lo, const unsigned long long *band_w64,
                          const unsigned long long *col_off, const uint32_t *pred_off, const uint32_t *pred_pos,
                          const uint32_t *pred_eid, const uint8_t *blocked, NnfVertexMeta *meta, NnfEdgeRec *edge,

@@ -112,14 +112,12 @@ void NNFrechet::setup() {
     throw ompl::Exception("IK function not set!");
   if (!dist_)
     throw ompl::Exception("Task-space distance function not set!");
-  if (!world_)
-    throw ompl::Exception("NNFrechet", "device world not set (setWorld)");
   requireRealVectorSpace(space_.get(), "NNFrechet");
   const auto t0 = std::chrono::steady_clock::now();
-  const int dof = world_->dof();
+  const int dof = (int)space_->getDimension();
   // setup() may be called again (after clear() or a parameter change): start from nothing
   releaseGraph();
-  if ((int)space_->getDimension() != dof)
+  if (world_ && world_->dof() != dof)
     throw ompl::Exception("NNFrechet", "state dimension differs from the world's dof");
 
   if (originalRefPath_.empty())
@@ -162,34 +160,104 @@ void NNFrechet::setup() {
   p.num_nn = numNN_;
   p.discretization = discretization_;
   p.check_resolution = checkResolution_;
-  check(prgpu_nnf_create(world_->handle(), &p, R, ref12.data(), layerCounts_.data(), ik.data(), &handle_),
-        "NNFrechet::setup");
+  // Device form: FK, the translation metric and edge validation all run on the device model -- taken only
+  // when a world was given AND the user's callbacks agree with it (checked on every IK solution of the first
+  // and the last layer).  Otherwise the host-callback form: the callbacks are what the reference calls.
+  hostForm_ = !world_ || !callbacksMatchWorld();
   uint32_t nv = 0;
-  check(prgpu_nnf_graph_info(handle_, &nv, nullptr, nullptr), "NNFrechet::setup");
-  vertexStates_.resize((size_t)nv * dof);
-  std::vector<double> pose((size_t)nv * 12);
-  check(prgpu_nnf_get_vertices(handle_, vertexStates_.data(), pose.data()), "NNFrechet::setup");
-
-  // the device model must agree with the user's callbacks
-  if (!ikStates_.empty()) {
-    Eigen::Isometry3d userPose = fk_(ikStates_[0]);
-    double d2 = 0.0;
-    for (int r = 0; r < 3; ++r) {
-      const double diff = userPose(r, 3) - pose[2 * 12 + 4 * r + 3];
-      d2 += diff * diff;
+  if (!hostForm_) {
+    check(prgpu_nnf_create(world_->handle(), &p, R, ref12.data(), layerCounts_.data(), ik.data(), &handle_),
+          "NNFrechet::setup");
+    check(prgpu_nnf_graph_info(handle_, &nv, nullptr, nullptr), "NNFrechet::setup");
+    vertexStates_.resize((size_t)nv * dof);
+    check(prgpu_nnf_get_vertices(handle_, vertexStates_.data(), nullptr), "NNFrechet::setup");
+  } else {
+    check(prgpu_nnf_create_graph(world_ ? world_->device() : device_, dof, &p, R, layerCounts_.data(), ik.data(),
+                                 &handle_),
+          "NNFrechet::setup");
+    check(prgpu_nnf_graph_info(handle_, &nv, nullptr, nullptr), "NNFrechet::setup");
+    vertexStates_.resize((size_t)nv * dof);
+    check(prgpu_nnf_get_vertices(handle_, vertexStates_.data(), nullptr), "NNFrechet::setup");
+    // node weights through the user's FK (NNFrechet.cpp:295, :372) and metric (:495); the two dummy
+    // vertices carry the first / last reference pose (:409, :414)
+    std::vector<double> weights((size_t)nv * R);
+    ob::State *tmp = si_->allocState();
+    for (uint32_t v = 0; v < nv; ++v) {
+      Eigen::Isometry3d pose;
+      if (v == 0)
+        pose = refPath_.front();
+      else if (v == 1)
+        pose = refPath_.back();
+      else {
+        std::memcpy(space_->getValueAddressAtIndex(tmp, 0), vertexStates_.data() + (size_t)v * dof, dof * sizeof(double));
+        pose = fk_(tmp);
+      }
+      for (int r = 0; r < R; ++r)
+        weights[(size_t)v * R + r] = dist_(refPath_[r], pose);
     }
-    if (std::sqrt(d2) > 1e-9)
-      throw ompl::Exception("NNFrechet", "FK callback and device world disagree on the end-effector position");
-    Eigen::Isometry3d a = refPath_[0], b = userPose;
-    double t2 = 0.0;
-    for (int r = 0; r < 3; ++r)
-      t2 += (a(r, 3) - b(r, 3)) * (a(r, 3) - b(r, 3));
-    if (std::fabs(dist_(a, b) - std::sqrt(t2)) > 1e-9 * (1.0 + std::sqrt(t2)))
-      throw ompl::Exception("NNFrechet", "only the translation-distance task metric is available on the device");
+    si_->freeState(tmp);
+    check(prgpu_nnf_set_weights(handle_, weights.data()), "NNFrechet::setup");
+    check(prgpu_nnf_set_edge_evaluator(handle_, &NNFrechet::evaluateEdgesThunk, this), "NNFrechet::setup");
   }
   OMPL_INFORM("Tensor Product Graph has been built.");
   buildTime_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   setup_ = true;
+}
+
+// Do the user's FK and metric describe the device world (its arm model, the translation metric)?
+bool NNFrechet::callbacksMatchWorld() {
+  const int dof = world_->dof();
+  const size_t nProbe = std::min<size_t>(ikStates_.size(), (size_t)layerCounts_.front() + layerCounts_.back());
+  for (size_t i = 0; i < nProbe; ++i) {
+    double pose[12];
+    check(prgpu_fk_batch(world_->handle(), space_->getValueAddressAtIndex(ikStates_[i], 0), 1, pose), "NNFrechet::setup");
+    (void)dof;
+    Eigen::Isometry3d userPose = fk_(ikStates_[i]);
+    double d2 = 0.0;
+    for (int r = 0; r < 3; ++r) {
+      const double diff = userPose(r, 3) - pose[4 * r + 3];
+      d2 += diff * diff;
+    }
+    if (std::sqrt(d2) > 1e-9)
+      return false;
+    Eigen::Isometry3d a = refPath_[i % refPath_.size()], b = userPose;
+    double t2 = 0.0;
+    for (int r = 0; r < 3; ++r)
+      t2 += (a(r, 3) - b(r, 3)) * (a(r, 3) - b(r, 3));
+    if (std::fabs(dist_(a, b) - std::sqrt(t2)) > 1e-9 * (1.0 + std::sqrt(t2)))
+      return false;
+  }
+  return nProbe > 0;
+}
+
+// evaluateEdge (NNFrechet.cpp:655-683) over the caller's validity checker: numQ = ceil(length / resolution)
+// states at an alpha that ACCUMULATES 1/numQ (so the far endpoint may or may not be reached), first invalid
+// state decides.
+int NNFrechet::evaluateEdgesThunk(void *user, const double *from, const double *to, uint32_t n, uint8_t *freeOut) {
+  NNFrechet *self = static_cast<NNFrechet *>(user);
+  try {
+    const int dof = (int)self->space_->getDimension();
+    const ob::StateValidityCheckerPtr &checker = self->si_->getStateValidityChecker();
+    ob::State *a = self->si_->allocState(), *b = self->si_->allocState(), *x = self->si_->allocState();
+    for (uint32_t i = 0; i < n; ++i) {
+      std::memcpy(self->space_->getValueAddressAtIndex(a, 0), from + (size_t)i * dof, dof * sizeof(double));
+      std::memcpy(self->space_->getValueAddressAtIndex(b, 0), to + (size_t)i * dof, dof * sizeof(double));
+      const int numQ = (int)std::ceil(self->space_->distance(a, b) / self->checkResolution_);
+      const double step = 1.0 / numQ;
+      bool free = true;
+      for (double alpha = 0.0; alpha <= 1.0 && free; alpha += step) {
+        self->space_->interpolate(a, b, alpha, x);
+        free = checker->isValid(x);
+      }
+      freeOut[i] = free ? 1 : 0;
+    }
+    self->si_->freeState(a);
+    self->si_->freeState(b);
+    self->si_->freeState(x);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
 }
 
 ob::PlannerStatus NNFrechet::solve(const ob::PlannerTerminationCondition &ptc) {
@@ -217,7 +285,7 @@ ob::PlannerStatus NNFrechet::solve(const ob::PlannerTerminationCondition &ptc) {
   }
   searchTime_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (solutionFound) {
-    const int dof = world_->dof();
+    const int dof = (int)space_->getDimension();
     auto *out = new ompl::geometric::PathGeometric(si_);
     ob::State *tmp = si_->allocState();
     for (unsigned v : pathVertices_) {

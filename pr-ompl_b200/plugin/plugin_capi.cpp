@@ -248,9 +248,49 @@ int plg_selftest_interfaces(void *worldp, const double *states, uint32_t n, uint
   }
 }
 
+namespace {
+// metric_kind 0: Euclidean distance of the translations (the metric the device models); 1: translation
+// distance + 0.25 x Frobenius norm of the rotation difference (a user metric the device has no model of)
+double taskMetric(int kind, Eigen::Isometry3d &a, Eigen::Isometry3d &b) {
+  double s = 0.0;
+  for (int r = 0; r < 3; ++r)
+    s += (a(r, 3) - b(r, 3)) * (a(r, 3) - b(r, 3));
+  double d = std::sqrt(s);
+  if (kind == 1) {
+    double f = 0.0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        f += (a(r, c) - b(r, c)) * (a(r, c) - b(r, c));
+    d = d + 0.25 * std::sqrt(f);
+  }
+  return d;
+}
+int nnfRun(void *worldp, int metric_kind, int with_world, int *used_host_form, int W, int M, int k, int D, int seed,
+           const double *ref_pose12, uint32_t P, const double *ik_states, uint32_t n_ik_available,
+           double solve_seconds, plg_nnf_result *res, uint32_t *layer_counts, uint32_t *path_vertices,
+           uint32_t cap_path, double *path_states);
+} // namespace
+
 int plg_nnf_run(void *worldp, int W, int M, int k, int D, int seed, const double *ref_pose12, uint32_t P,
                 const double *ik_states, uint32_t n_ik_available, double solve_seconds, plg_nnf_result *res,
                 uint32_t *layer_counts, uint32_t *path_vertices, uint32_t cap_path, double *path_states) {
+  return nnfRun(worldp, 0, 1, nullptr, W, M, k, D, seed, ref_pose12, P, ik_states, n_ik_available, solve_seconds, res,
+                layer_counts, path_vertices, cap_path, path_states);
+}
+int plg_nnf_run_host(void *worldp, int metric_kind, int with_world, int *used_host_form, int W, int M, int k, int D,
+                     int seed, const double *ref_pose12, uint32_t P, const double *ik_states,
+                     uint32_t n_ik_available, double solve_seconds, plg_nnf_result *res, uint32_t *layer_counts,
+                     uint32_t *path_vertices, uint32_t cap_path, double *path_states) {
+  return nnfRun(worldp, metric_kind, with_world, used_host_form, W, M, k, D, seed, ref_pose12, P, ik_states,
+                n_ik_available, solve_seconds, res, layer_counts, path_vertices, cap_path, path_states);
+}
+} // extern "C"
+
+namespace {
+int nnfRun(void *worldp, int metric_kind, int with_world, int *used_host_form, int W, int M, int k, int D, int seed,
+           const double *ref_pose12, uint32_t P, const double *ik_states, uint32_t n_ik_available,
+           double solve_seconds, plg_nnf_result *res, uint32_t *layer_counts, uint32_t *path_vertices,
+           uint32_t cap_path, double *path_states) {
   try {
     const pr_gpu::GpuWorldPtr &world = *static_cast<pr_gpu::GpuWorldPtr *>(worldp);
     const int dim = world->dof();
@@ -261,7 +301,8 @@ int plg_nnf_run(void *worldp, int W, int M, int k, int D, int seed, const double
     for (uint32_t i = 0; i < P; ++i)
       std::memcpy(ref[i].data(), ref_pose12 + (std::size_t)i * 12, 12 * sizeof(double));
     planner.setRefPath(ref);
-    planner.setWorld(world);
+    if (with_world)
+      planner.setWorld(world);
     planner.setFKFunc([&](ob::State *s) {
       Eigen::Isometry3d out;
       double pose[12];
@@ -281,15 +322,13 @@ int plg_nnf_run(void *worldp, int W, int M, int k, int D, int seed, const double
       }
       return out;
     });
-    planner.setDistanceFunc([](Eigen::Isometry3d &a, Eigen::Isometry3d &b) {
-      double s = 0.0;
-      for (int r = 0; r < 3; ++r)
-        s += (a(r, 3) - b(r, 3)) * (a(r, 3) - b(r, 3));
-      return std::sqrt(s);
-    });
+    planner.setDistanceFunc(
+        [metric_kind](Eigen::Isometry3d &a, Eigen::Isometry3d &b) { return taskMetric(metric_kind, a, b); });
     auto pdef = std::make_shared<ob::ProblemDefinition>(si);
     planner.setProblemDefinition(pdef);
     planner.setup();
+    if (used_host_form)
+      *used_host_form = planner.usesHostCallbacks() ? 1 : 0;
     ob::PlannerStatus st = planner.solve(solve_seconds);
     std::memset(res, 0, sizeof(*res));
     res->status = (int32_t)(ob::PlannerStatus::StatusType)st;
@@ -316,4 +355,4 @@ int plg_nnf_run(void *worldp, int W, int M, int k, int D, int seed, const double
     return -1;
   }
 }
-} // extern "C"
+} // namespace

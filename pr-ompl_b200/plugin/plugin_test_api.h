@@ -47,6 +47,14 @@ typedef struct {
 int plg_nnf_run(void *world, int W, int M, int k, int D, int seed, const double *ref_pose12, uint32_t P,
                 const double *ik_states, uint32_t n_ik_available, double solve_seconds, plg_nnf_result *res,
                 uint32_t *layer_counts /* R */, uint32_t *path_vertices, uint32_t cap_path, double *path_states);
+/* the same, choosing the planner's form: metric_kind 0 = translation distance, 1 = translation + 0.25 x Frobenius
+ * norm of the rotation difference; with_world = 0 leaves setWorld() out (FK callback = the world's FK, validity =
+ * the SpaceInformation's checker, as a user of the reference would supply them).  *used_host_form reports which
+ * form setup() took. */
+int plg_nnf_run_host(void *world, int metric_kind, int with_world, int *used_host_form, int W, int M, int k, int D,
+                     int seed, const double *ref_pose12, uint32_t P, const double *ik_states,
+                     uint32_t n_ik_available, double solve_seconds, plg_nnf_result *res, uint32_t *layer_counts,
+                     uint32_t *path_vertices, uint32_t cap_path, double *path_states);
 #ifdef __cplusplus
 }
 #endif

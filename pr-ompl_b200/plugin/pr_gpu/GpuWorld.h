@@ -18,7 +18,7 @@ public:
   GpuWorld(int device, int dof, const double *dh, int nLinkSpheres, const int32_t *sphereLink,
            const double *sphereXyzr, int nObsSpheres, const double *obsSpheres, int nObsBoxes,
            const double *obsBoxes)
-      : dof_(dof), handle_(nullptr) {
+      : dof_(dof), device_(device), handle_(nullptr) {
     check(prgpu_world_create(device, dof, dh, nLinkSpheres, sphereLink, sphereXyzr, nObsSpheres, obsSpheres,
                              nObsBoxes, obsBoxes, &handle_),
           "GpuWorld");
@@ -28,9 +28,10 @@ public:
   GpuWorld &operator=(const GpuWorld &) = delete;
   prgpu_world_t *handle() const { return handle_; }
   int dof() const { return dof_; }
+  int device() const { return device_; }
 
 private:
-  int dof_;
+  int dof_, device_;
   prgpu_world_t *handle_;
 };
 typedef std::shared_ptr<GpuWorld> GpuWorldPtr;

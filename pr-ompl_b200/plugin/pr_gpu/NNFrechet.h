@@ -6,9 +6,14 @@
 // (reference-path sub-sampling, the IK budget per waypoint drawn exactly as
 // frechet/src/NNFrechet.cpp:310-343, the IK callback itself); everything else -- kNN, sub-sampled
 // edges, FK, tensor-product search, edge evaluation -- runs through prgpu_nnf_*.
-// The device needs a model, so one extra call is required: setWorld(GpuWorldPtr).  The FK and
-// distance callbacks must still be supplied (as in the reference) and are used to verify that
-// the device model agrees with them (FK of the first IK solution; translation metric).
+// Two forms, chosen in setup():
+//  * device form -- setWorld(GpuWorldPtr) was called and the user's FK / distance callbacks agree with the
+//    device model (checked on the IK solutions of the end layers): FK, the translation metric and
+//    evaluateEdge all run on the device;
+//  * host-callback form -- no world, or callbacks the device has no model of (another robot, a metric
+//    with a rotation term ...): the user's FK and metric fill the node-weight table on the host exactly as
+//    the reference calls them (NNFrechet.cpp:295,372,495), evaluateEdge runs over
+//    si_->getStateValidityChecker(), and the device does findKnnNodes, the NN graph and every bottleneck search.
 #ifndef PR_GPU_NNFRECHET_H
 #define PR_GPU_NNFRECHET_H
 #include <functional>
@@ -35,8 +40,11 @@ public:
   void setNumNN(int numNN);
   void setDiscretization(int discretization);
   void setRandomSeed(int seed);
-  /// device model used for FK and collision checking (required before setup())
+  /// device model used for FK and collision checking (optional; see the two forms above)
   void setWorld(const GpuWorldPtr &world) { world_ = world; }
+  /// CUDA device of the host-callback form when no world is given (default 0)
+  void setDevice(int device) { device_ = device; }
+  bool usesHostCallbacks() const { return hostForm_; }
 
   void setProblemDefinition(const ompl::base::ProblemDefinitionPtr &pdef) override;
   ompl::base::PlannerStatus solve(const ompl::base::PlannerTerminationCondition &ptc) override;
@@ -55,6 +63,10 @@ public:
 
 private:
   void releaseGraph();
+  bool callbacksMatchWorld();
+  static int evaluateEdgesThunk(void *user, const double *from, const double *to, uint32_t n, uint8_t *freeOut);
+  bool hostForm_ = false;
+  int device_ = 0;
   std::vector<Eigen::Isometry3d> subsampleRefPath(const std::vector<Eigen::Isometry3d> &path) const;
 
   ompl::base::StateSpacePtr space_;

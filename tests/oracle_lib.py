@@ -120,12 +120,13 @@ def ref_nnf(reverse_order=False):
                                   C.c_uint32, C.c_double, C.c_int, C.POINTER(RefNnfResult), c_dp, C.c_uint32,
                                   c_u32p, c_u32p, c_dp, c_dp, C.c_uint32, c_u32p, c_u8p, C.c_uint32, c_dp,
                                   C.c_uint32]
+        L.ref_nnf_set_metric.argtypes = [C.c_int]
         _ref_nnf[reverse_order] = L
     return _ref_nnf[reverse_order]
 
 
 def ref_nnf_run(world, ref_full_pose12, W, M, k, D, ik_states, seed=1, solve_seconds=600.0, search_only=False,
-                reverse_order=False):
+                reverse_order=False, metric=0):
     """NNFrechet::NNFrechet(si, W, M, k, D, seed) of the compiled reference: setRefPath(ref_full) ...
     setup(); solve(solve_seconds).  ik_states are handed out by the IK callback in call order."""
     L = ref_nnf(reverse_order)
@@ -146,10 +147,14 @@ def ref_nnf_run(world, ref_full_pose12, W, M, k, D, ik_states, seed=1, solve_sec
     edges = np.zeros((cap_e, 2), dtype=np.uint32)
     flags = np.zeros(cap_e, dtype=np.uint8)
     path = np.zeros((cap_p, world.dof))
-    rc = L.ref_nnf_run(world.h, len(ref), _dp(ref), W, M, k, D, seed, _dp(ik), n_ik, float(solve_seconds),
-                       int(search_only), C.byref(res), _dp(ref_sub), R, calls.ctypes.data_as(c_u32p),
-                       knn_out.ctypes.data_as(c_u32p), _dp(vs), _dp(vp), cap_v, edges.ctypes.data_as(c_u32p),
-                       flags.ctypes.data_as(c_u8p), cap_e, _dp(path), cap_p)
+    L.ref_nnf_set_metric(int(metric))  # 0 translation distance, 1 translation + rotation term
+    try:
+        rc = L.ref_nnf_run(world.h, len(ref), _dp(ref), W, M, k, D, seed, _dp(ik), n_ik, float(solve_seconds),
+                           int(search_only), C.byref(res), _dp(ref_sub), R, calls.ctypes.data_as(c_u32p),
+                           knn_out.ctypes.data_as(c_u32p), _dp(vs), _dp(vp), cap_v, edges.ctypes.data_as(c_u32p),
+                           flags.ctypes.data_as(c_u8p), cap_e, _dp(path), cap_p)
+    finally:
+        L.ref_nnf_set_metric(0)
     assert rc == 0 and res.overflow == 0, (rc, res.overflow)
     out = {f[0]: getattr(res, f[0]) for f in RefNnfResult._fields_}
     out.update(ref=ref_sub[:res.R], ik_call_counts=calls[:res.R], knn=knn_out[:res.n_ik], states=vs[:res.n_vertices],

@@ -66,6 +66,7 @@ def lib():
         L.plg_selftest_interfaces.argtypes = [c_vp, c_vp, C.c_uint32, c_vp, c_vp, c_vp]
         L.plg_nnf_run.argtypes = [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_uint32, c_vp,
                                   C.c_uint32, C.c_double, C.POINTER(PlgNnfResult), c_vp, c_vp, C.c_uint32, c_vp]
+        L.plg_nnf_run_host.argtypes = [c_vp, C.c_int, C.c_int, C.POINTER(C.c_int)] + L.plg_nnf_run.argtypes[1:]
         _lib = L
     return _lib
 
@@ -143,6 +144,28 @@ class PluginWorld:
         return dict(status=res.status, lazy_iters=res.lazy_iters, n_evaluated=res.n_evaluated,
                     n_collisions=res.n_collisions, final_error=res.final_error, goal_cost=res.goal_cost,
                     layer_counts=counts, path=pv[:res.path_len].copy(), path_states=ps[:res.path_len].copy())
+
+    def nnf_run_host(self, W, M, k, D, seed, ref_pose12, ik_states, metric=0, with_world=False, solve_seconds=20.0,
+                     cap_path=65536):
+        """NNFrechet::NNFrechet in the form setup() chooses: metric 1 (rotation term) or with_world=False
+        must end in the host-callback form."""
+        ref = np.ascontiguousarray(ref_pose12, dtype=np.float64).reshape(-1, 12)
+        ik = np.ascontiguousarray(ik_states, dtype=np.float64).reshape(-1, self.dof)
+        R = (W - 1) * (D + 1) + 1
+        res = PlgNnfResult()
+        counts = np.zeros(R, dtype=np.uint32)
+        pv = np.zeros(cap_path, dtype=np.uint32)
+        ps = np.zeros((cap_path, self.dof))
+        host = C.c_int(-1)
+        rc = self.L.plg_nnf_run_host(self.h, int(metric), int(with_world), C.byref(host), W, M, k, D, seed, _p(ref),
+                                     len(ref), _p(ik), len(ik), float(solve_seconds), C.byref(res), _p(counts),
+                                     _p(pv), cap_path, _p(ps))
+        if rc != 0:
+            raise RuntimeError(self.L.plg_last_error().decode())
+        return dict(status=res.status, lazy_iters=res.lazy_iters, n_evaluated=res.n_evaluated,
+                    n_collisions=res.n_collisions, final_error=res.final_error, goal_cost=res.goal_cost,
+                    layer_counts=counts, path=pv[:res.path_len].copy(), path_states=ps[:res.path_len].copy(),
+                    host_form=host.value)
 
     def set_two_phase(self, first_iters, clear_between=False):
         self.L.plg_set_two_phase(int(first_iters), int(clear_between))

@@ -135,3 +135,137 @@ def test_nnf_full_size_costs_vs_independent_reachability(P, O, synth, world_arra
     b = np.where(blocked)[0]
     ok, clear, _ = ow.check_motion_batch(st[ed[b, 0]], st[ed[b, 1]], 0.05, mode=1, nthreads=8)
     assert np.all((ok == 0) | (np.abs(clear) < 1e-6))
+
+
+# ---- host-callback form: user FK / metric / validity, device for kNN + search ----------
+def _rot_metric_weights(ref, pose):
+    """weights[v, r] under the test metric: translation distance + 0.25 x Frobenius norm of the rotation
+    difference (same operation order as plugin_capi.cpp / ref_nnf_driver.cpp)."""
+    V, R = len(pose), len(ref)
+    w = np.empty((V, R))
+    rot = [0, 1, 2, 4, 5, 6, 8, 9, 10]
+    for r in range(R):
+        d = pose[:, [3, 7, 11]] - ref[r, [3, 7, 11]]
+        t = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+        f = np.zeros(V)
+        for c in rot:
+            e = ref[r, c] - pose[:, c]
+            f = f + e * e
+        w[:, r] = t + 0.25 * np.sqrt(f)
+    return w
+
+
+@pytest.mark.parametrize("name", ["defaults_s4", "w12m20_seed7", "w20m30"])
+def test_host_form_with_translation_weights_equals_device_form(P, O, synth, name):
+    """prgpu_nnf_create_graph + set_weights + set_edge_evaluator with the translation metric evaluated on the
+    HOST and the oracle's evaluateEdge as the validity callback must walk exactly the LazySP sequence of the
+    device form (same costs after every search, same path)."""
+    c = CASES[name]
+    tseed, pseed, W, M, k, D, ns, nb = [int(x) for x in c["params"]]
+    gw, ow = _worlds(P, O, synth, c)
+    dev = P.Nnf(gw, c["ref_sub"], c["ik_call_counts"], c["ik"], num_nn=k, discretization=D)
+    st, po = dev.vertices()
+    h = P.Nnf.host_form(7, c["ik_call_counts"], c["ik"], num_nn=k, discretization=D)
+    assert (h.n_vertices, h.n_edges, h.n_ik) == (dev.n_vertices, dev.n_edges, dev.n_ik)
+    assert np.array_equal(h.knn(), c["knn"]) and np.array_equal(h.states(), c["states"])
+    pose = np.array(po)
+    pose[0], pose[1] = c["ref_sub"][0], c["ref_sub"][-1]     # the dummies carry the end poses
+    ref = c["ref_sub"]
+    d = ref[None, :, [3, 7, 11]] - pose[:, None, [3, 7, 11]]
+    w = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2])
+    h.set_weights(w)
+    calls = []
+
+    def evaluate(a, b):
+        calls.append(len(a))
+        v, _, _ = ow.check_motion_batch(a, b, 0.05, mode=1, want_clearance=False)
+        return v
+    h.set_edge_evaluator(evaluate)
+    rd, rh = dev.solve(max_lazy_iters=4000), h.solve(max_lazy_iters=4000)
+    assert rd["solved"] == rh["solved"] == int(c["solved"])
+    assert rd["lazy_iters"] == rh["lazy_iters"]
+    assert np.allclose(rd["goal_cost_trace"], rh["goal_cost_trace"], rtol=1e-12, atol=0)
+    assert np.array_equal(rd["path"], rh["path"])
+    assert abs(rd["final_error"] - rh["final_error"]) <= 1e-12
+    assert sum(calls) == rh["n_evaluated"] or sum(calls) >= rh["n_evaluated"]
+
+
+def test_host_form_errors(P, synth):
+    h = P.Nnf.host_form(7, [2, 2], np.zeros((4, 7)), num_nn=2, discretization=1)
+    with pytest.raises(P.PrgpuError):
+        h.solve(max_lazy_iters=1)                       # no weights
+    with pytest.raises(P.PrgpuError):
+        h.set_weights(np.full((h.n_vertices, 2), -1.0))  # negative weights
+    h.set_weights(np.zeros((h.n_vertices, 2)))
+    with pytest.raises(P.PrgpuError):
+        h.solve(max_lazy_iters=1)                       # no evaluator
+    with pytest.raises(P.PrgpuError):
+        P.Nnf.host_form(9, [2, 2], np.zeros((4, 9)))     # dof out of range
+
+
+@pytest.mark.parametrize("name,with_world", [("defaults_s4", False), ("w12m20_seed7", True), ("w20m30", False)])
+def test_plugin_host_callbacks_rotation_metric_vs_compiled_reference(P, O, synth, name, with_world):
+    """NNFrechet::NNFrechet (drop-in name) with a task metric the device has no model of (rotation term): the
+    planner must take the host-callback form -- also when a world was given -- and reproduce the compiled
+    reference run with the same callbacks: IK budget, final g[goal], solved flag, a valid path."""
+    import plugin_lib as PL
+    if O.ref_nnf() is None:
+        pytest.skip("oracle/_ref/libref_frechet.so not built")
+    c = CASES[name]
+    tseed, pseed, W, M, k, D, ns, nb = [int(x) for x in c["params"]]
+    dh, link, xyzr = synth.default_arm()
+    sph, box = G.case_world_arrays(synth, c)
+    pw = PL.PluginWorld(dh, link, xyzr, sph, box)
+    ow = O.World(dh, link, xyzr, sph, box)
+    ref = O.ref_nnf_run(ow, c["ref_full"], W, M, k, D, c["ik"], seed=pseed, solve_seconds=300.0, metric=1)
+    g = pw.nnf_run_host(W, M, k, D, pseed, c["ref_full"], c["ik"], metric=1, with_world=with_world, solve_seconds=120.0)
+    assert g["host_form"] == 1
+    assert np.array_equal(g["layer_counts"], ref["ik_call_counts"])
+    solved = g["status"] == 6
+    assert int(solved) == int(ref["solved"])
+    assert _close(g["goal_cost"], ref["goal_cost"], 1e-12)
+    if solved:
+        # a real c0 -> c1 path of the reference's NN graph, collision-free under the specification
+        edges = set(map(tuple, ref["edges"].tolist()))
+        path = [int(v) for v in g["path"]]
+        assert (0, path[0]) in edges and (path[-1], 1) in edges
+        assert all((u, v) in edges for u, v in zip(path[:-1], path[1:]))
+        assert np.array_equal(g["path_states"], ref["states"][path])
+        if len(path) > 1:
+            v, _, _ = ow.check_motion_batch(ref["states"][path[:-1]], ref["states"][path[1:]], 0.05, mode=1,
+                                            want_clearance=False)
+            assert v.all()
+        # optimal under the rotation metric: the best coupling of the path costs the reference's g[goal]
+        pose = ref["pose"].copy()
+        w = _rot_metric_weights(ref["ref"], pose)
+        seq = [0] + path + [1]
+        f = w[seq].T
+        Rr, L = f.shape
+        B = np.full((Rr, L), np.inf)
+        B[0, 0] = f[0, 0]
+        for r in range(Rr):
+            for j in range(L):
+                if r == 0 and j == 0:
+                    continue
+                best = min(B[r - 1, j] if r else np.inf, B[r, j - 1] if j else np.inf,
+                           B[r - 1, j - 1] if r and j else np.inf)
+                B[r, j] = max(best, f[r, j])
+        assert _close(B[-1, -1], ref["goal_cost"], 1e-9)
+
+
+def test_plugin_translation_metric_without_world_takes_host_form(P, O, synth):
+    """No setWorld(): the user's FK / metric / validity checker are the only model -- the result must equal the
+    device form's (golden) result."""
+    import plugin_lib as PL
+    c = CASES["w20m30"]
+    tseed, pseed, W, M, k, D, ns, nb = [int(x) for x in c["params"]]
+    dh, link, xyzr = synth.default_arm()
+    sph, box = G.case_world_arrays(synth, c)
+    pw = PL.PluginWorld(dh, link, xyzr, sph, box)
+    ow = O.World(dh, link, xyzr, sph, box)
+    g = pw.nnf_run_host(W, M, k, D, pseed, c["ref_full"], c["ik"], metric=0, with_world=False, solve_seconds=120.0)
+    assert g["host_form"] == 1
+    assert int(g["status"] == 6) == int(c["solved"])
+    assert _close(g["goal_cost"], float(c["goal_cost"]), 1e-9)   # FK through the fp64 device kernel vs goldens
+    if g["status"] == 6:
+        G.check_solution_path(c, g["path"], ow)
