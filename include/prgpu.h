@@ -316,6 +316,19 @@ int prgpu_check_motion_batch_sharded_device(prgpu_world_t *w, prgpu_comm_t *c, c
 uint64_t prgpu_diag_launch_count(void);
 /* live micro-benchmark: issue peak of mma.sync.m16n8k8 TF32 (the instruction K1's scan uses), TFLOP/s */
 int prgpu_diag_mma_tf32_peak(int device, double *tflops);
+/* The numbers the exactness proofs of K1's filter path rest on, as the device computes them.  Runs the PRODUCTION
+ * scan kernel over the whole tree for nq queries with the caller's thresholds T (thresh: in = any float, out = T
+ * rounded up to a TF32 number, as the search does).  Per query: counts = nodes the scan reported (D < 0; only
+ * min(counts, cap) are stored), idx = their local indices, D = (|x|^2 - 2 q.x - T) from the tensor cores,
+ * key32 = (|x|^2 - 2 q.x) from the fp32 FMA chain of the re-cut, eps = (eps_tc, eps_32) as knn_select_kernel
+ * computes them.  tests/test_gpu_bounds.py checks |D - exact| <= eps_tc, |key32 - exact| <= eps_32 and that no node
+ * with exact key < T - eps_tc is missing. */
+int prgpu_diag_knn_scan(prgpu_knn_t *h, const double *queries, uint32_t nq, float *thresh, uint32_t cap, uint32_t *counts,
+                        uint32_t *idx /* nq x cap */, float *D /* nq x cap */, float *key32 /* nq x cap */,
+                        double *eps /* nq x 2 */);
+/* K2's filter: largest distance between a link-sphere centre from the production fp32 forward-kinematics chain and
+ * the fp64 chain of the specification, per state (max_err: n); *delta = the bound prgpu_world_create derived. */
+int prgpu_diag_fk_centre_error(prgpu_world_t *w, const double *states, uint64_t n, double *max_err, double *delta);
 
 #ifdef __cplusplus
 }

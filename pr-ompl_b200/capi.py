@@ -101,6 +101,8 @@ SIGNATURES = {
     "prgpu_nnf_knn_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "prgpu_nnf_get_edges": (C.c_int, [c_vp, c_vp, c_vp]),
     "prgpu_nnf_solve": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, C.c_uint32, c_vp]),
+    "prgpu_diag_knn_scan": (C.c_int, [c_vp, c_vp, C.c_uint32, c_vp, C.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "prgpu_diag_fk_centre_error": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp, C.POINTER(C.c_double)]),
     "prgpu_nnf_create_graph": (C.c_int, [C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.POINTER(c_vp)]),
     "prgpu_nnf_set_weights": (C.c_int, [c_vp, c_vp]),
     "prgpu_nnf_set_edge_evaluator": (C.c_int, [c_vp, c_vp, c_vp]),
@@ -184,6 +186,20 @@ class KnnIndex:
         n = C.c_uint64()
         _check(lib().prgpu_knn_size(self.h, C.byref(n)))
         return n.value
+
+    def diag_scan(self, queries, thresh, cap):
+        """prgpu_diag_knn_scan: the production scan's D, the fp32 re-cut keys and the error bounds."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)
+        nq = len(q)
+        t = np.ascontiguousarray(np.broadcast_to(thresh, (nq,)), dtype=np.float32).copy()
+        counts = np.zeros(nq, dtype=np.uint32)
+        idx = np.zeros((nq, cap), dtype=np.uint32)
+        D = np.zeros((nq, cap), dtype=np.float32)
+        k32 = np.zeros((nq, cap), dtype=np.float32)
+        eps = np.zeros((nq, 2))
+        _check(lib().prgpu_diag_knn_scan(self.h, _ptr(q), nq, _ptr(t), cap, _ptr(counts), _ptr(idx), _ptr(D),
+                                         _ptr(k32), _ptr(eps)))
+        return dict(thresh=t, counts=counts, idx=idx, D=D, key32=k32, eps_tc=eps[:, 0], eps_32=eps[:, 1])
 
     def set_search_mode(self, force_exact):
         """0 auto (k-d index, tensor-core filter or exact kernel, whichever is cheapest), 1 / True exact fp64 kernel only,
@@ -328,6 +344,14 @@ class World:
         ms = C.c_float()
         _check(lib().prgpu_world_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def diag_fk_centre_error(self, states):
+        """(max over link spheres of |fp32-chain centre - fp64-chain centre| per state, delta)"""
+        q = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, self.dof)
+        err = np.zeros(len(q))
+        delta = C.c_double()
+        _check(lib().prgpu_diag_fk_centre_error(self.h, _ptr(q), len(q), _ptr(err), C.byref(delta)))
+        return err, delta.value
 
     def check_motion_batch(self, a, b, resolution, mode=MODE_OMPL_DISCRETE, check_first=False):
         a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, self.dof)

@@ -743,14 +743,14 @@ int prgpu_world_create(int device, int dof, const double *dh, int ns, const int3
     if (ncell <= (1ull << 24) && out > 0.0) {
       rc = w->df.reserve(ncell * sizeof(float));
       if (rc == PRGPU_OK)
-        rc = dfield_build_launch(H.os_d, nos, H.ob_d, nob, n3, org, cell, slack, 1.0e3, w->df.as<float>(), w->stream);
+        rc = dfield_build_launch(H.os_d, nos, H.ob_d, nob, n3, org, cell, slack, 1.0e3, w->df.as<uint32_t>(), w->stream);
       if (rc == PRGPU_OK && cudaStreamSynchronize(w->stream) != cudaSuccess)
         rc = fail(PRGPU_ECUDA, "clearance field build failed");
       if (rc != PRGPU_OK) {
         prgpu_world_destroy(w);
         return rc;
       }
-      H.df = w->df.as<float>();
+      H.df = w->df.as<uint32_t>();
       for (int c = 0; c < 3; ++c) {
         H.df_n[c] = n3[c];
         H.df_org[c] = (float)org[c];
@@ -788,7 +788,8 @@ int prgpu_world_destroy(prgpu_world_t *w) {
   w->d_valid.release();
   w->d_pose.release();
   for (void *p : {(void *)w->cm_scratch.owed, (void *)w->cm_scratch.off, w->cm_scratch.tmp, (void *)w->cm_scratch.item_edge,
-                  (void *)w->cm_scratch.gaps, (void *)w->cm_scratch.queue, (void *)w->cm_scratch.queue_n})
+                  (void *)w->cm_scratch.gaps, (void *)w->cm_scratch.queue, (void *)w->cm_scratch.queue_n,
+                  (void *)w->cm_scratch.pair_ref, w->cm_scratch.pair_centre, (void *)w->cm_scratch.pair_n})
     if (p)
       cudaFree(p);
   w->timer.destroy();

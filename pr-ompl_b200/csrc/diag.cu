@@ -1,7 +1,7 @@
 // Measurement aids behind the C ABI (include/prgpu.h, prgpu_diag_*): the launch counter and the live
 // micro-benchmark of the warp-level TF32 MMA issue rate that K1's scan is measured against.
 #include <algorithm>
-#include "common.cuh"
+#include "capi_internal.cuh"
 
 namespace prgpu {
 unsigned long long g_launch_count = 0;
@@ -34,6 +34,72 @@ using namespace prgpu;
 
 extern "C" {
 uint64_t prgpu_diag_launch_count(void) { return g_launch_count; }
+
+int prgpu_diag_knn_scan(prgpu_knn_t *h, const double *queries, uint32_t nq, float *thresh, uint32_t cap, uint32_t *counts,
+                        uint32_t *idx, float *D, float *key32, double *eps) {
+  if (!h || !queries || !thresh || !counts || !idx || !D || !key32 || !eps || nq == 0 || cap == 0)
+    return fail(PRGPU_EINVAL, "diag_knn_scan: NULL argument");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  DevBuf dq, dt, dc, di, dk, d32, de;
+  auto done = [&](int rc) {
+    cudaStreamSynchronize(s);
+    for (DevBuf *b : {&dq, &dt, &dc, &di, &dk, &d32, &de})
+      b->release();
+    return rc;
+  };
+  const size_t cells = (size_t)nq * cap;
+  int rc;
+  if ((rc = dq.reserve((size_t)nq * h->dim * 8)) != PRGPU_OK || (rc = dt.reserve((size_t)nq * 4)) != PRGPU_OK ||
+      (rc = dc.reserve((size_t)nq * 4)) != PRGPU_OK || (rc = di.reserve(cells * 4)) != PRGPU_OK ||
+      (rc = dk.reserve(cells * 4)) != PRGPU_OK || (rc = d32.reserve(cells * 4)) != PRGPU_OK ||
+      (rc = de.reserve((size_t)nq * 16)) != PRGPU_OK)
+    return done(rc);
+  cudaMemcpyAsync(dq.p, queries, (size_t)nq * h->dim * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dt.p, thresh, (size_t)nq * 4, cudaMemcpyHostToDevice, s);
+  rc = knn_diag_scan(h->dim, h->view(), dq.as<double>(), nq, dt.as<float>(), cap, dc.as<uint32_t>(), di.as<uint32_t>(),
+                     dk.as<float>(), d32.as<float>(), de.as<double>(), s);
+  if (rc != PRGPU_OK)
+    return done(rc);
+  cudaMemcpyAsync(thresh, dt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(counts, dc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(idx, di.p, cells * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(D, dk.p, cells * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(key32, d32.p, cells * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(eps, de.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess)
+    return done(fail(PRGPU_ECUDA, std::string("diag_knn_scan: ") + cudaGetErrorString(e)));
+  return done(PRGPU_OK);
+}
+
+int prgpu_diag_fk_centre_error(prgpu_world_t *w, const double *states, uint64_t n, double *max_err, double *delta) {
+  if (!w || (n && (!states || !max_err)))
+    return fail(PRGPU_EINVAL, "diag_fk_centre_error: NULL argument");
+  if (delta)
+    *delta = (double)w->host.delta;
+  if (n == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(w->device));
+  DevBuf dq, de;
+  auto done = [&](int rc) {
+    cudaStreamSynchronize(w->stream);
+    dq.release();
+    de.release();
+    return rc;
+  };
+  int rc;
+  if ((rc = dq.reserve((size_t)n * w->host.dof * 8)) != PRGPU_OK || (rc = de.reserve((size_t)n * 8)) != PRGPU_OK)
+    return done(rc);
+  cudaMemcpyAsync(dq.p, states, (size_t)n * w->host.dof * 8, cudaMemcpyHostToDevice, w->stream);
+  if ((rc = diag_fk_centre_launch(w->host, w->dev, dq.as<double>(), n, de.as<double>(), w->stream)) != PRGPU_OK)
+    return done(rc);
+  cudaMemcpyAsync(max_err, de.p, (size_t)n * 8, cudaMemcpyDeviceToHost, w->stream);
+  cudaError_t e = cudaStreamSynchronize(w->stream);
+  if (e != cudaSuccess)
+    return done(fail(PRGPU_ECUDA, std::string("diag_fk_centre_error: ") + cudaGetErrorString(e)));
+  return done(PRGPU_OK);
+}
 
 int prgpu_diag_mma_tf32_peak(int device, double *tflops) {
   if (!tflops)

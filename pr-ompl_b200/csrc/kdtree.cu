@@ -32,7 +32,10 @@ namespace {
 #endif
 constexpr int KD_PPL_ = KD_PPL;       // leaf slots per lane
 constexpr int KD_LEAF = 32 * KD_PPL_; // slots per leaf
-constexpr int KD_WARPS = 8;           // queries per block
+#ifndef KD_WARPS_N
+#define KD_WARPS_N 8
+#endif
+constexpr int KD_WARPS = KD_WARPS_N;  // queries per block
 
 __device__ __forceinline__ uint32_t ord32(float f) { // order-preserving float -> uint
   const uint32_t u = __float_as_uint(f);

@@ -55,6 +55,12 @@ int knn_search_exact(int dim, const KnnTreeView &t, const double *queries_dev, u
 int knn_search(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev,
                uint32_t *idx_dev, double *dist_dev, KnnScratch &scratch, int sm_count, cudaStream_t stream,
                KernelTimer *timer = nullptr, int force_exact = 0);
+// measurement aid behind prgpu_diag_knn_scan: the production scan kernel over the whole tree with caller-given
+// thresholds (rounded up to TF32 numbers in place); every reported node's D, its fp32 re-cut key and the two
+// error bounds of the selection
+int knn_diag_scan(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, float *thresh_dev, uint32_t cap,
+                  uint32_t *counts_dev, uint32_t *cidx_dev, float *ckey_dev, float *key32_dev, double *eps_dev,
+                  cudaStream_t stream);
 // Deferred form for callers that enqueue more work behind the search (the sharded step): the filter path
 // leaves the unproven-query list on the device (scratch.flags[0] = count, [1+i] = query ids) instead of
 // synchronising; *pending says whether such a list exists.  knn_search_finish(nflag) then re-runs those

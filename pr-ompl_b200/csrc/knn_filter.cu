@@ -377,6 +377,31 @@ __global__ void knn_sample_threshold_kernel(uint32_t nq, int kp, uint32_t cap, u
 //      exact squared distance is >= T_q - eps_tc + |q|^2, which must lie strictly above the k-th selected.
 // Unproven queries, overflowed candidate buffers and over-long survivor lists are flagged for the exact
 // kernel.
+// the two error bounds the selection rests on (derivation: DESIGN.md §4 K1 step 3; pinned on the CPU by
+// tests/test_filter_bounds.py and on the device by prgpu_diag_knn_scan / tests/test_gpu_bounds.py)
+__device__ __forceinline__ void filter_error_bounds(double xmax2, double qn2, float T, double &eps_tc,
+                                                             double &eps32) {
+  const double xn = sqrt(xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
+  const double u24 = 5.9604644775390625e-08;
+  eps32 = 16.0 * u24 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
+  const double at = T < CUDART_INF_F ? fabs((double)T) : 0.0;
+  eps_tc = 1.01 * 0.001953125 * qn * xn + 3.814697265625e-06 * ((xn + qn) * (xn + qn) + at) + 1e-30;
+}
+// fp32 key |x|^2 - 2 q.x of node i by the FMA chain of the sample pass (q2[d] = fp32(-2 q_d))
+template <int DIM> __device__ __forceinline__ float key32_chain(const float *__restrict__ ptsf, uint32_t i, const float (&q2)[7]) {
+  const float4 *rec = reinterpret_cast<const float4 *>(ptsf + (size_t)i * 8);
+  const float4 a = rec[0], b = rec[1];
+  float x = b.w;
+  x = fmaf(q2[0], a.x, x);
+  if (DIM > 1) x = fmaf(q2[1], a.y, x);
+  if (DIM > 2) x = fmaf(q2[2], a.z, x);
+  if (DIM > 3) x = fmaf(q2[3], a.w, x);
+  if (DIM > 4) x = fmaf(q2[4], b.x, x);
+  if (DIM > 5) x = fmaf(q2[5], b.y, x);
+  if (DIM > 6) x = fmaf(q2[6], b.z, x);
+  return x;
+}
+
 constexpr int SEL_THREADS = 128;
 constexpr int SEL_MAX_L1 = 512;        // level-1 survivors
 constexpr int SEL_MAX_SURVIVORS = 64;  // level-2 survivors
@@ -418,11 +443,10 @@ knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
       qn2 += qx[d] * qx[d];
-    const double xn = sqrt(*xmax2) * (1.0 + 1e-12), qn = sqrt(qn2) * (1.0 + 1e-12);
-    const double u24 = 5.9604644775390625e-08;
-    s_eps32 = 16.0 * u24 * (xn + qn) * (xn + qn) * (1.0 + 1e-6) + 1e-30;
-    const double at = T < CUDART_INF_F ? fabs((double)T) : 0.0;
-    s_eps_tc = 1.01 * 0.001953125 * qn * xn + 3.814697265625e-06 * ((xn + qn) * (xn + qn) + at) + 1e-30;
+    double etc, e32;
+    filter_error_bounds(*xmax2, qn2, T, etc, e32);
+    s_eps_tc = etc;
+    s_eps32 = e32;
     s_qn2 = qn2;
     n_l1 = 0;
     n_sv = 0;
@@ -472,19 +496,8 @@ knn_select_kernel(const double *__restrict__ pts, const float *__restrict__ ptsf
 #pragma unroll
     for (int d = 0; d < 7; ++d)
       q2[d] = d < DIM ? (float)(-2.0 * qx[d < DIM ? d : 0]) : 0.f;
-    for (uint32_t c = tid; c < n1; c += SEL_THREADS) {
-      const float4 *rec = reinterpret_cast<const float4 *>(ptsf + (size_t)l1_i[c] * 8);
-      const float4 a = rec[0], b = rec[1];
-      float x = b.w;
-      x = fmaf(q2[0], a.x, x);
-      if (DIM > 1) x = fmaf(q2[1], a.y, x);
-      if (DIM > 2) x = fmaf(q2[2], a.z, x);
-      if (DIM > 3) x = fmaf(q2[3], a.w, x);
-      if (DIM > 4) x = fmaf(q2[4], b.x, x);
-      if (DIM > 5) x = fmaf(q2[5], b.y, x);
-      if (DIM > 6) x = fmaf(q2[6], b.z, x);
-      l1_k[c] = x;
-    }
+    for (uint32_t c = tid; c < n1; c += SEL_THREADS)
+      l1_k[c] = key32_chain<DIM>(ptsf, l1_i[c], q2);
   }
   if (tid == 0)
     s_kk = CUDART_INF_F;
@@ -758,7 +771,77 @@ int filter_path(const KnnTreeView &t, const double *queries, uint32_t nq, int k,
   return filter_fallback<DIM>(t, queries, nq, k, lo, idx_out, dist_out, sc, sm_count, stream, nflag);
 }
 
+// ---- measurement aid: the scan's own numbers (prgpu_diag_knn_scan) ----------------------------------------
+__global__ void diag_round_thresholds_kernel(float *thresh, uint32_t nq, uint32_t *counts) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq) {
+    thresh[q] = tf32_round_up(thresh[q]);
+    counts[q] = 0;
+  }
+}
+template <int DIM>
+__global__ void diag_keys_kernel(const float *__restrict__ ptsf, const double *__restrict__ xmax2,
+                                 const double *__restrict__ queries, const float *__restrict__ thresh, uint32_t nq,
+                                 uint32_t cap, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ cidx,
+                                 float *__restrict__ key32, double *__restrict__ eps) {
+  const uint32_t q = blockIdx.x;
+  float q2[7];
+  double qn2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < 7; ++d) {
+    const double x = d < DIM ? queries[(size_t)q * DIM + (d < DIM ? d : 0)] : 0.0;
+    q2[d] = d < DIM ? (float)(-2.0 * x) : 0.f;
+    qn2 += x * x;
+  }
+  const uint32_t cnt = min(counts[q], cap);
+  for (uint32_t c = threadIdx.x; c < cnt; c += blockDim.x)
+    key32[(size_t)q * cap + c] = key32_chain<DIM>(ptsf, cidx[(size_t)q * cap + c], q2);
+  if (threadIdx.x == 0) {
+    double etc, e32;
+    filter_error_bounds(*xmax2, qn2, thresh[q], etc, e32);
+    eps[2 * (size_t)q] = etc;
+    eps[2 * (size_t)q + 1] = e32;
+  }
+}
+template <int DIM>
+int diag_scan(const KnnTreeView &t, const double *queries, uint32_t nq, float *thresh, uint32_t cap, uint32_t *counts,
+              uint32_t *cidx, float *ckey, float *key32, double *eps, cudaStream_t stream) {
+  const uint32_t qblocks = (nq + CT_QPB - 1) / CT_QPB;
+  const uint32_t ntiles = (t.n + CT_TILE - 1) / CT_TILE;
+  diag_round_thresholds_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(thresh, nq, counts); PRGPU_COUNT_LAUNCH(1);
+  const size_t smem2 = (size_t)CT_STAGES * CT_TILE * 40 + 2 * CT_STAGES * sizeof(uint64_t);
+  auto coll = knn_collect_kernel<DIM>;
+  PRGPU_CUDA_TRY(cudaFuncSetAttribute(coll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  const uint32_t chunks = std::min<uint32_t>(ntiles, 64u);
+  const uint32_t tpc = (ntiles + chunks - 1) / chunks;
+  coll<<<dim3(qblocks, (ntiles + tpc - 1) / tpc), FT_THREADS, smem2, stream>>>(
+      t.ptsf + 8 * t.stride, t.ptsf + 16 * t.stride, t.n, queries, nq, nullptr, thresh, 1u, tpc, cap, counts, cidx, ckey); PRGPU_COUNT_LAUNCH(1);
+  diag_keys_kernel<DIM><<<nq, 128, 0, stream>>>(t.ptsf, t.xmax2, queries, thresh, nq, cap, counts, cidx, key32, eps); PRGPU_COUNT_LAUNCH(1);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
 } // namespace
+
+int knn_diag_scan(int dim, const KnnTreeView &t, const double *queries_dev, uint32_t nq, float *thresh_dev, uint32_t cap,
+                  uint32_t *counts_dev, uint32_t *cidx_dev, float *ckey_dev, float *key32_dev, double *eps_dev,
+                  cudaStream_t stream) {
+  if (!t.ptsf || dim > 7)
+    return fail(PRGPU_EINVAL, "diag_knn_scan: the tree has no TF32 mirror (dim <= 7 only)");
+  switch (dim) {
+#define PRGPU_DIM_CASE(D)                                                                          \
+  case D:                                                                                          \
+    return diag_scan<D>(t, queries_dev, nq, thresh_dev, cap, counts_dev, cidx_dev, ckey_dev, key32_dev, eps_dev, stream);
+    PRGPU_DIM_CASE(1)
+    PRGPU_DIM_CASE(2)
+    PRGPU_DIM_CASE(3)
+    PRGPU_DIM_CASE(4)
+    PRGPU_DIM_CASE(5)
+    PRGPU_DIM_CASE(6)
+    PRGPU_DIM_CASE(7)
+#undef PRGPU_DIM_CASE
+  }
+  return fail(PRGPU_ELIMIT, "diag_knn_scan: dim must be in [1,7]");
+}
 
 static bool filter_eligible(int dim, const KnnTreeView &t, uint32_t nq, int k, int force_exact) {
   return !force_exact && t.ptsf != nullptr && dim <= 7 && k >= 1 && k <= KNN_FILTER_MAX_K &&

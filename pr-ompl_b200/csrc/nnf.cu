@@ -340,6 +340,140 @@ __global__ void __launch_bounds__(BAND_THREADS) nnf_band_dp_kernel(const NnfBand
 // dependent vertices (one flag + one gather round trip per NN-graph level) instead of one grid- or
 // cluster-wide barrier per level, and every SM takes part.
 constexpr int FLOW_THREADS = 256;
+
+// One vertex's column of the banded table, by one warp (lanes = rows, 32 at a time).  Row recurrence
+// x_r = max(f_r, min(x_{r-1}, m_r)), m_r = min over the predecessors' cells (r, p) and (r-1, p), evaluated as a
+// shuffle scan of clamp compositions.  The records of up to 32 predecessors are fetched by different lanes and
+// handed round by shuffles, the cells of four predecessors are in flight at a time.  While gathering, every lane
+// also notes which predecessor cell the fixed-order walk of followBackpointers' restatement would take from its
+// row: the first cell with value <= f_r if there is one, else the first that attains m_r; composed with "stays on
+// the vertex while x_{r-1} <= max(f_r, m_r)" this gives the hop word of every cell (nnf.cuh).
+// COMPARE: returns whether any stored value changed (warp-uniform); else returns true.
+template <bool COMPARE>
+__device__ __forceinline__ bool band_column(const NnfBandDev &g, uint32_t s, const NnfVertexMeta &m, uint32_t lane) {
+  double px = 0.0, py = 0.0, pz = 0.0;
+  if (!g.ftab) {
+    px = g.pnn[3 * (size_t)s];
+    py = g.pnn[3 * (size_t)s + 1];
+    pz = g.pnn[3 * (size_t)s + 2];
+  }
+  double carry = NNF_INF;
+  unsigned long long carry_hop = NNF_HOP_NONE;
+  bool changed = false;
+  for (uint32_t c0 = 0; c0 < m.band_w; c0 += 32) {
+    const bool active = c0 + lane < m.band_w;
+    const uint32_t r = m.band_lo + c0 + lane;
+    double f = 0.0;
+    if (active) {
+      if (g.ftab) {
+        f = g.ftab[(size_t)s * g.R + r];
+      } else {
+        const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
+                     dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
+        f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      }
+    }
+    double mm = NNF_INF;
+    uint32_t amin = 0xFFFFFFFFu, fle = 0xFFFFFFFFu; // (predecessor index in the list << 1) | (row r-1 ? 1 : 0)
+    for (uint32_t e0 = m.pred_begin; e0 < m.pred_end; e0 += 32) {
+      const uint32_t ne = min(32u, m.pred_end - e0);
+      NnfEdgeRec mine;
+      mine.col_off = 0;
+      mine.band_lo = 0;
+      mine.band_w_blocked = 0x80000000u;
+      if (lane < ne)
+        mine = g.edge[e0 + lane];
+      for (uint32_t j0 = 0; j0 < ne; j0 += 4) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int src = (int)min(j0 + u, 31u);
+          const uint64_t co = __shfl_sync(0xffffffffu, mine.col_off, src);
+          const uint32_t bl = __shfl_sync(0xffffffffu, mine.band_lo, src);
+          uint32_t bw = __shfl_sync(0xffffffffu, mine.band_w_blocked, src);
+          if (j0 + u >= ne)
+            bw = 0x80000000u;
+          v[2 * u] = NNF_INF;
+          v[2 * u + 1] = NNF_INF;
+          if (active && !(bw & 0x80000000u)) {
+            const uint32_t i0 = r - bl;
+            if (i0 < bw)
+              v[2 * u] = __ldcg(g.Bc + co + i0);
+            const uint32_t i1 = i0 - 1u;
+            if (r > 0 && i1 < bw)
+              v[2 * u + 1] = __ldcg(g.Bc + co + i1);
+          }
+        }
+        const uint32_t code0 = (e0 - m.pred_begin + j0) << 1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (v[u] < mm) {
+            mm = v[u];
+            amin = code0 + (uint32_t)u;
+          }
+          if (fle == 0xFFFFFFFFu && v[u] <= f)
+            fle = code0 + (uint32_t)u;
+        }
+      }
+    }
+    const bool is_start = s == g.start_pos && r == 0;
+    Clamp gfn;
+    gfn.a = -NNF_INF;
+    gfn.b = NNF_INF;
+    if (active) {
+      gfn.a = f;
+      gfn.b = fmax(f, mm);
+      if (is_start)
+        gfn.a = gfn.b = 0.0;
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      Clamp lower;
+      lower.a = __shfl_up_sync(0xffffffffu, gfn.a, off);
+      lower.b = __shfl_up_sync(0xffffffffu, gfn.b, off);
+      if ((int)lane >= off)
+        gfn = compose(gfn, lower);
+    }
+    const double x = fmax(gfn.a, fmin(carry, gfn.b));
+    const uint32_t last = min(31u, m.band_w - c0 - 1u);
+    unsigned long long h = NNF_HOP_NONE;
+    if (g.hop) {
+      double xprev = __shfl_up_sync(0xffffffffu, x, 1);
+      if (lane == 0)
+        xprev = carry;
+      // the walk stays on the vertex: (r-1, s) explains the cell (inactive lanes inherit, they are never stored)
+      const bool stays = !active || (!is_start && xprev != NNF_INF && xprev <= fmax(f, mm));
+      unsigned long long own = NNF_HOP_NONE;
+      if (active && !stays) {
+        if (is_start) {
+          own = NNF_HOP_START;
+        } else if (x != NNF_INF) {
+          const uint32_t code = fle != 0xFFFFFFFFu ? fle : amin;
+          const uint32_t e = m.pred_begin + (code >> 1);
+          const NnfEdgeRec rec = g.edge[e];
+          const unsigned long long cell = rec.col_off + (r - rec.band_lo) - (code & 1u);
+          own = (cell << 28) | ((unsigned long long)g.pred_pos[e] << 1) | (code & 1u);
+        }
+      }
+      const unsigned nonstay = __ballot_sync(0xffffffffu, !stays) & ((2u << lane) - 1u);
+      const int src = nonstay ? 31 - __clz(nonstay) : 0;
+      h = __shfl_sync(0xffffffffu, own, src);
+      if (!nonstay)
+        h = carry_hop;
+      carry_hop = __shfl_sync(0xffffffffu, h, last);
+    }
+    if (active) {
+      if (COMPARE)
+        changed |= __ldcg(g.Bc + m.col_off + c0 + lane) != x;
+      __stcg(g.Bc + m.col_off + c0 + lane, x);
+      if (g.hop)
+        __stcg(g.hop + m.col_off + c0 + lane, h);
+    }
+    carry = __shfl_sync(0xffffffffu, x, last);
+  }
+  return COMPARE ? __any_sync(0xffffffffu, changed) : true;
+}
+
 __global__ void __launch_bounds__(FLOW_THREADS)
 nnf_flow_dp_kernel(const NnfBandDev g, uint32_t first_pos, uint32_t epoch, volatile uint32_t *done) {
   const uint32_t lane = threadIdx.x & 31;
@@ -365,85 +499,7 @@ nnf_flow_dp_kernel(const NnfBandDev g, uint32_t first_pos, uint32_t epoch, volat
       }
       __threadfence(); // acquire: the columns behind the flags
       __syncwarp();
-      double px = 0.0, py = 0.0, pz = 0.0;
-      if (!g.ftab) {
-        px = g.pnn[3 * (size_t)s];
-        py = g.pnn[3 * (size_t)s + 1];
-        pz = g.pnn[3 * (size_t)s + 2];
-      }
-      double carry = NNF_INF;
-      for (uint32_t c0 = 0; c0 < m.band_w; c0 += 32) {
-        const bool active = c0 + lane < m.band_w;
-        const uint32_t r = m.band_lo + c0 + lane;
-        Clamp gfn;
-        gfn.a = -NNF_INF;
-        gfn.b = NNF_INF;
-        // min over the predecessors' cells (r, p) and (r-1, p).  The records of up to 32 predecessors are
-        // fetched by different lanes and handed round by shuffles, and the cells of four predecessors are
-        // in flight at a time: a vertex costs a few memory round trips, not two per predecessor.
-        double mm = NNF_INF;
-        for (uint32_t e0 = m.pred_begin; e0 < m.pred_end; e0 += 32) {
-          const uint32_t ne = min(32u, m.pred_end - e0);
-          NnfEdgeRec mine;
-          mine.col_off = 0;
-          mine.band_lo = 0;
-          mine.band_w_blocked = 0x80000000u;
-          if (lane < ne)
-            mine = g.edge[e0 + lane];
-          for (uint32_t j0 = 0; j0 < ne; j0 += 4) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int src = (int)min(j0 + u, 31u);
-              const uint64_t co = __shfl_sync(0xffffffffu, mine.col_off, src);
-              const uint32_t bl = __shfl_sync(0xffffffffu, mine.band_lo, src);
-              uint32_t bw = __shfl_sync(0xffffffffu, mine.band_w_blocked, src);
-              if (j0 + u >= ne)
-                bw = 0x80000000u;
-              v[2 * u] = NNF_INF;
-              v[2 * u + 1] = NNF_INF;
-              if (active && !(bw & 0x80000000u)) {
-                const uint32_t i0 = r - bl;
-                if (i0 < bw)
-                  v[2 * u] = __ldcg(g.Bc + co + i0);
-                const uint32_t i1 = i0 - 1u;
-                if (r > 0 && i1 < bw)
-                  v[2 * u + 1] = __ldcg(g.Bc + co + i1);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              mm = fmin(mm, v[u]);
-          }
-        }
-        if (active) {
-          double f;
-          if (g.ftab) {
-            f = g.ftab[(size_t)s * g.R + r];
-          } else {
-            const double dx = __dsub_rn(g.pref[3 * (size_t)r], px), dy = __dsub_rn(g.pref[3 * (size_t)r + 1], py),
-                         dz = __dsub_rn(g.pref[3 * (size_t)r + 2], pz);
-            f = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-          }
-          gfn.a = f;
-          gfn.b = fmax(f, mm);
-          if (s == g.start_pos && r == 0)
-            gfn.a = gfn.b = 0.0;
-        }
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          Clamp lower;
-          lower.a = __shfl_up_sync(0xffffffffu, gfn.a, off);
-          lower.b = __shfl_up_sync(0xffffffffu, gfn.b, off);
-          if ((int)lane >= off)
-            gfn = compose(gfn, lower);
-        }
-        const double x = fmax(gfn.a, fmin(carry, gfn.b));
-        if (active)
-          __stcg(g.Bc + m.col_off + c0 + lane, x);
-        const uint32_t last = min(31u, m.band_w - c0 - 1u);
-        carry = __shfl_sync(0xffffffffu, x, last);
-      }
+      band_column<false>(g, s, m, lane);
       __threadfence(); // release: the column before the flag
     }
     __syncwarp();

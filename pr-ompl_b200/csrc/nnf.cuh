@@ -46,8 +46,52 @@ struct NnfBandDev {
   const double *pnn, *pref;
   const double *ftab;        // as NnfGraphDev::ftab
   double *Bc;
+  // hop[cell]: where the optimal path through this cell LEAVES the cell's vertex -- the predecessor cell on
+  // another vertex, found by the fixed order of followBackpointers' restatement ((r-1, s) first, then the
+  // predecessors in list order, (r, p) before (r-1, p)) and already composed over the rows the path stays on
+  // the vertex.  Walking goal -> start costs one dependent load per NN edge of the path.  NULL: not kept.
+  unsigned long long *hop;
   uint32_t start_pos, goal_pos;
 };
+// hop word: bits 63..28 predecessor cell (offset into Bc), bits 27..1 its sorted position, bit 0: the predecessor
+// cell's row is (leaving row - 1) instead of the leaving row
+constexpr unsigned long long NNF_HOP_START = ~0ull;       // the start cell (0, c0)
+constexpr unsigned long long NNF_HOP_NONE = ~0ull - 1ull; // unreachable cell
+constexpr uint32_t NNF_HOP_MAX_V = 1u << 27;
+
+// Device-resident LazySP loop (NNFrechet::solve, frechet/src/NNFrechet.cpp:106-152): one persistent block
+// chases the hops of the current optimum, evaluates the path's not-yet-known NN edges (evaluateEdge), does the
+// reference's bookkeeping in path order, knocks the first colliding edge out and repairs the bottleneck table
+// LOCALLY -- only vertices whose predecessors' columns changed are recomputed, level by level, which is what
+// LPAStar::updateVertex / computeShortestPath do with their priority queue (LPAStar.cpp:17-159).
+struct NnfLazyOut {
+  uint32_t status, iters, n_evaluated, n_collisions, path_len, epoch, repaired_vertices, pad;
+  double goal_cost, final_error;
+};
+enum : uint32_t { NNF_LAZY_RUNNING = 0, NNF_LAZY_SOLVED = 1, NNF_LAZY_NO_PATH = 2, NNF_LAZY_CONTINUE = 3,
+                  NNF_LAZY_NEED_REBUILD = 4, NNF_LAZY_ERROR = 5 };
+struct NnfLazyDev {
+  const uint32_t *succ_off, *succ_pos; // CSR of NN-graph successors by sorted position
+  const uint32_t *level;               // level of a sorted position
+  const uint32_t *vertex_of_pos;
+  const uint32_t *pred_eid;            // CSR slot -> NN edge id
+  NnfEdgeRec *edge_rw;                 // = NnfBandDev::edge, writable (blocked bit)
+  uint32_t *stamp, *worklist;          // V each
+  const double *states;                // V x dof by vertex id
+  int8_t *known;                       // per NN edge id: -1 unknown, 0 collides, 1 free
+  uint8_t *evaluated, *blocked;        // per NN edge id
+  uint32_t *path_pos, *path_slot;      // cap_hops each
+  unsigned long long *path_cell;       // cap_hops
+  uint32_t cap_hops;
+  uint32_t *out_path;                  // NN-graph vertex ids of the solution
+  double *trace;                       // goal cost of every search, or NULL
+  NnfLazyOut *out;
+  uint32_t max_iters, epoch;
+  double tau_ub, check_resolution;
+  int band_full, dof;
+};
+int nnf_lazysp_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const NnfBandDev &g, const NnfLazyDev &z,
+                      cudaStream_t stream);
 int nnf_rowmin_launch(int R, uint32_t V, const double *pnn, const double *pref, const double *ftab,
                       unsigned long long *rowmin_bits, cudaStream_t stream);
 int nnf_band_launch(int R, uint32_t V, const double *pnn, const double *pref, const double *ftab, double tau,

@@ -119,7 +119,9 @@ static __device__ __noinline__ bool round_valid(const DeviceWorld *wp, const Obs
   const bool pow2 = (S & (S - 1)) == 0;
   const int sh = 31 - __clz(S);
   const float dout = w.df_out;
-  const float *df = w.df;
+  const uint32_t *df = w.df;
+  const float two_delta = 2.0f * w.delta;
+  bool hit = false; // some sphere certainly penetrates an obstacle (the field's upper bound)
   constexpr int RV_U = 8; // field loads in flight per lane
   for (int base = 0; base < nitems; base += 32 * RV_U) {
     float dv[RV_U];
@@ -132,10 +134,15 @@ static __device__ __noinline__ bool round_valid(const DeviceWorld *wp, const Obs
         const float fx = (c[0] - dox) * dinv, fy = (c[1] - doy) * dinv, fz = (c[2] - doz) * dinv;
         const bool in = fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)dnx && fy < (float)dny && fz < (float)dnz;
         // (outside the field's box, or NaN: the margin)
-        const float d = in ? __ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx) : dout;
-        dv[u] = d - arm.sphere[pow2 ? (it & (S - 1)) : (it % S)].w;
+        const float2 d = in ? df_unpack(__ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx))
+                            : make_float2(dout, CUDART_INF_F);
+        const float rs = arm.sphere[pow2 ? (it & (S - 1)) : (it % S)].w;
+        dv[u] = d.x - rs;
+        hit |= d.y < rs - two_delta;
       }
     }
+    if (__any_sync(0xffffffffu, hit))
+      return false;
 #pragma unroll
     for (int u = 0; u < RV_U; ++u) {
       const int it = base + u * 32 + tid;

@@ -8,6 +8,7 @@
 // delta bounds the fp32 rounding of centres and arithmetic, so levels 1-2 never reject a colliding
 // pair; every "collision" verdict comes from level 3.
 #pragma once
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include "common.cuh"
 
@@ -42,7 +43,11 @@ struct DeviceWorld {
   // min_j(df - r_j) is a lower bound of the state's clearance: the states of an edge within that
   // distance (in workspace motion, bounded through rho[]) of a tested state are free without being
   // tested.  df == nullptr: no field.  Outside the field's box every obstacle is >= df_out away.
-  const float *df;
+  // Two-sided: a cell's 32-bit word packs two fp16 numbers (df_unpack): .x, the lower bound above (rounded down),
+  // and .y >= the distance from ANY point of the cell to the nearest obstacle surface plus the same slacks
+  // (rounded up) -- a link sphere whose true radius exceeds .y certainly penetrates an obstacle, so the state
+  // is invalid without walking a list or running the fp64 chain (the specification's verdict is clearance <= 0).
+  const uint32_t *df;
   int df_n[3];
   float df_org[3], df_inv, df_out;
   // rho[i]: upper bound, over all configurations and link spheres, of the distance between a sphere centre
@@ -459,6 +464,10 @@ struct FrameF32 {
   }
 };
 
+__device__ __forceinline__ float2 df_unpack(uint32_t word) {
+  return __half22float2(*reinterpret_cast<const __half2 *>(&word));
+}
+
 // Pass 1 (clearance field): fp32 FK frame by frame; the field loads of a link's spheres are issued in
 // groups of 4 and consumed only after the NEXT frame has been computed, so the L2 latency of the field
 // overlaps the sincos / frame product; no per-sphere branch.  Returns the mask of the sphere slots the
@@ -466,35 +475,54 @@ struct FrameF32 {
 // Requires w.df != nullptr.
 // `centres` (optional, 3 floats per sphere slot): receives every sphere centre, so that the second pass of the
 // same thread need not repeat the FK chain.
+// `hit_out` (optional): set to true when some sphere CERTAINLY collides (the field's upper bound lies below its
+// true radius): the state is invalid, whatever the returned mask says.
+// Only the centres of the spheres the field could NOT certify are stored (they are the ones a list walk needs);
+// ALL_CENTRES stores every one (measurement aid).
+template <bool ALL_CENTRES = false>
 __device__ __forceinline__ uint32_t grid_certify(const DeviceWorld &w, const ArmTableF32 &arm, const double *q,
-                                                 float *cmin_out, float *centres = nullptr) {
-  const float *df = w.df;
+                                                 float *cmin_out, float *centres = nullptr, bool *hit_out = nullptr) {
+  const uint32_t *df = w.df;
+  const float two_delta = 2.0f * w.delta;
+  float hmin = CUDART_INF_F; // min over spheres of (upper bound - true radius): < 0 -> certain collision
   const int dnx = w.df_n[0], dny = w.df_n[1], dnz = w.df_n[2];
   const float dox = w.df_org[0], doy = w.df_org[1], doz = w.df_org[2], dinv = w.df_inv, dout = w.df_out;
   float cmin = CUDART_INF_F;
   uint32_t unc = 0;
   float dv0 = CUDART_INF_F, dv1 = CUDART_INF_F, dv2 = CUDART_INF_F, dv3 = CUDART_INF_F; // field - radius, in flight
+  float3 cc[4];                                                                       // their centres
   int jb = 0;                                                                         // slot of dv0
   FrameF32 f;
   auto consume = [&]() {
     cmin = fminf(fminf(cmin, dv0), fminf(dv1, fminf(dv2, dv3)));
-    unc |= (dv0 > 0.f ? 0u : 1u << jb) | (dv1 > 0.f ? 0u : 2u << jb) | (dv2 > 0.f ? 0u : 4u << jb) |
-           (dv3 > 0.f ? 0u : 8u << jb);
+    const uint32_t u4 = (dv0 > 0.f ? 0u : 1u) | (dv1 > 0.f ? 0u : 2u) | (dv2 > 0.f ? 0u : 4u) | (dv3 > 0.f ? 0u : 8u);
+    unc |= u4 << jb;
+    if (!ALL_CENTRES && centres && u4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (u4 & (1u << k)) {
+          centres[3 * (jb + k)] = cc[k].x;
+          centres[3 * (jb + k) + 1] = cc[k].y;
+          centres[3 * (jb + k) + 2] = cc[k].z;
+        }
+    }
   };
-  auto lookup = [&](int j) -> float {
+  auto lookup = [&](int j, int k) -> float {
     const float4 sp = arm.sphere[j];
     float cx, cy, cz;
     f.centre(sp, cx, cy, cz);
-    if (centres) {
+    cc[k] = make_float3(cx, cy, cz);
+    if (ALL_CENTRES && centres) {
       centres[3 * j] = cx;
       centres[3 * j + 1] = cy;
       centres[3 * j + 2] = cz;
     }
     const float fx = (cx - dox) * dinv, fy = (cy - doy) * dinv, fz = (cz - doz) * dinv;
-    float dv = dout; // outside the field's box (or NaN)
+    float2 dv = make_float2(dout, CUDART_INF_F); // outside the field's box (or NaN)
     if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)dnx && fy < (float)dny && fz < (float)dnz)
-      dv = __ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx);
-    return dv - sp.w;
+      dv = df_unpack(__ldg(df + ((size_t)(int)fz * dny + (int)fy) * dnx + (int)fx));
+    hmin = fminf(hmin, dv.y - (sp.w - two_delta)); // sp.w = radius + delta
+    return dv.x - sp.w;
   };
   f.reset();
   for (int i = 0; i <= w.dof; ++i) {
@@ -505,15 +533,17 @@ __device__ __forceinline__ uint32_t grid_certify(const DeviceWorld &w, const Arm
     while (j < je) {
       consume(); // the previous group: its loads had a frame product (or a group) to land
       jb = j;
-      dv0 = lookup(j);
-      dv1 = j + 1 < je ? lookup(j + 1) : CUDART_INF_F;
-      dv2 = j + 2 < je ? lookup(j + 2) : CUDART_INF_F;
-      dv3 = j + 3 < je ? lookup(j + 3) : CUDART_INF_F;
+      dv0 = lookup(j, 0);
+      dv1 = j + 1 < je ? lookup(j + 1, 1) : CUDART_INF_F;
+      dv2 = j + 2 < je ? lookup(j + 2, 2) : CUDART_INF_F;
+      dv3 = j + 3 < je ? lookup(j + 3, 3) : CUDART_INF_F;
       j += 4;
     }
   }
   consume();
   *cmin_out = cmin < CUDART_INF_F ? cmin : 0.f;
+  if (hit_out)
+    *hit_out = hmin < 0.f;
   return unc;
 }
 
@@ -607,7 +637,10 @@ static __device__ __noinline__ bool state_valid_grid(const DeviceWorld *wp, cons
   if (!w.df)
     return grid_lists(w, *tp, q, 0xFFFFFFFFu);
   float cmin, centres[3 * WORLD_MAX_S];
-  const uint32_t unc = grid_certify(w, *tp->arm, q, &cmin, centres);
+  bool hit;
+  const uint32_t unc = grid_certify(w, *tp->arm, q, &cmin, centres, &hit);
+  if (hit)
+    return false;
   if (unc == 0) {
     if (clear)
       *clear = cmin;
