@@ -663,6 +663,59 @@ def measure_knn(env, args, want_cpu):
                                       "note": "tree replicated on every GPU, queries split, results all-gathered"}
         full.close()
 
+    # ---- BASELINE configs[4], measured instead of argued: the NN step of a lock-step planner whose TREE is
+    #      node-sharded.  One growTree = nearest(q_rand) over the tree + one appended node (RRTConnect.cpp:181,
+    #      :209).  Sharded: every rank scans its 1/G of the nodes, ONE all-gather of the per-shard best record,
+    #      merge; the new node goes to shard (i mod G).  Beside it: the same step on one GPU holding the whole
+    #      tree (what query-sharding does: each GPU plans its own queries on its own trees). ----
+    if world > 1 and not args.no_extra:
+        lockstep = {}
+        for n_tree, q_batch in ((100_000, 1), (10_000_000, 1), (10_000_000, 64)):
+            cloud = synth.cloud(21, n_tree + 512)
+            mine = torch.from_numpy(np.ascontiguousarray(cloud[:n_tree][rank::world])).to(dev)
+            shard = P.KnnIndex(7, device=env.local_rank, capacity=len(mine) + 1024)
+            shard.add_device(mine, len(mine), stream)
+            shard.set_index_base(0)   # (records carry shard-local indices here; the timing does not depend on them)
+            whole = P.KnnIndex(7, device=env.local_rank, capacity=n_tree + 1024)
+            whole.add_device(torch.from_numpy(cloud[:n_tree]).to(dev), n_tree, stream)
+            newn = torch.from_numpy(cloud[n_tree:n_tree + 512]).to(dev)
+            qb = torch.from_numpy(synth.cloud(22, 256 * q_batch)).to(dev)
+            oi = torch.empty((q_batch, 1), dtype=torch.int32, device=dev)
+            od = torch.empty((q_batch, 1), dtype=torch.float64, device=dev)
+            reps = 200
+
+            def grow_sharded():
+                for i in range(reps):
+                    shard.nearest_k_sharded_device(comm, qb[(i % 256) * q_batch:(i % 256 + 1) * q_batch], q_batch, 1,
+                                                   oi, od, stream=stream)
+                    if i % world == rank:
+                        shard.add_device(newn[i:i + 1], 1, stream)
+
+            def grow_single():
+                for i in range(reps):
+                    whole.nearest_k_device(qb[(i % 256) * q_batch:(i % 256 + 1) * q_batch], q_batch, 1, oi, od,
+                                           stream=stream)
+                    whole.add_device(newn[i:i + 1], 1, stream)
+            out = {}
+            for name, fn in (("node_sharded", grow_sharded), ("single_gpu_whole_tree", grow_single)):
+                fn()
+                torch.cuda.synchronize()
+                env.barrier()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                out[name + "_us_per_growTree_nn"] = env.max_over_ranks((time.perf_counter() - t0) / reps * 1e6)
+            lockstep[f"tree={n_tree},queries_per_step={q_batch}"] = out
+            shard.close()
+            whole.close()
+            del mine, newn, qb
+        lockstep["note"] = ("per growTree: nearest over the tree + one appended node; node_sharded = "
+                            "prgpu_knn_nearest_k_sharded_device (local scan of N/G nodes + one NCCL all-gather + merge) "
+                            "with the new node appended to shard i mod G; single_gpu_whole_tree = prgpu_knn_nearest_k_"
+                            "device on one GPU (query-sharded planning: no collective).  Planner trees of the 4096-query "
+                            "batch hold tens to hundreds of nodes: far left of the first row")
+        extra["configs4_lockstep_node_sharded_nn"] = lockstep
+
     # ---- the other shapes of the sweep (single GPU) ----
     if world == 1 and not args.no_extra:
         def time_knn(t_, nq, kk, reps=5):
@@ -913,6 +966,15 @@ def measure_nnf(env, args, want_cpu):
                 "h2d_bytes_per_step": int(ik.nbytes + ref.nbytes), "d2h_bytes_per_step": int(g.n_vertices * 19 * 8)},
         "gpu_launches_per_step": launches, "clocks": None, "extra": {},
     }
+    ls = g.loop_stats()
+    tot = float(sum(ls["phase_cycles"].values())) or 1.0
+    line["extra"]["lazysp_loop"] = {
+        "kernel_launches": ls["launches"], "columns_repaired": ls["repaired_vertices"],
+        "columns_repaired_per_iteration": ls["repaired_vertices"] / max(1, iters),
+        "nn_vertices": g.n_vertices, "wide_waves_handed_to_full_sweep": ls["wide_waves_handed_to_full_sweep"],
+        "phase_share_of_loop_kernel": {kname: c / tot for kname, c in ls["phase_cycles"].items()},
+        "note": "the LazySP loop runs in one persistent kernel (hop chase -> per-hop pass -> evaluateEdge -> "
+                "bookkeeping -> local repair of the bottleneck table); the host reads one record per launch"}
     g.close()
     gw.close()
     if want_cpu:

@@ -269,6 +269,19 @@ int prgpu_nnf_set_edge_evaluator(prgpu_nnf_t *h, prgpu_nnf_edge_eval_fn fn, void
  * level by level by one thread-block cluster.  All return identical costs and paths. */
 int prgpu_nnf_set_mode(prgpu_nnf_t *h, int mode);
 int prgpu_nnf_band_info(prgpu_nnf_t *h, double *tau, uint64_t *cells, uint32_t *rebuilds);
+/* With search kernel 0 and a device world the whole LazySP loop of solve() runs in ONE persistent kernel: it
+ * follows the optimum's hop words, evaluates the path's unknown NN edges, does the reference's bookkeeping in
+ * path order, knocks the first colliding edge out and repairs the table locally (only vertices whose
+ * predecessors' columns changed are recomputed -- what LPAStar::updateVertex / computeShortestPath do,
+ * frechet/src/LPAStar.cpp:17-159); the host reads one status record per call or band rebuild.  launches: kernel
+ * launches of that loop so far; repaired_vertices: columns recomputed by the local repairs; phase_cycles: SM
+ * cycles of the loop's five phases (the block's thread-0 clock).  A repair wave that outgrows one block (more than
+ * 2048 columns) is handed to the whole-GPU sweep from its current level, so an iteration never costs more than it
+ * did with the host-side loop.  (Environment
+ * PRGPU_NNF_HOST_LOOP=1 keeps the loop on the host, one full search per iteration: same results.) */
+int prgpu_nnf_loop_stats(prgpu_nnf_t *h, uint64_t *launches, uint64_t *repaired_vertices,
+                         uint64_t *phase_cycles /* 6, or NULL: SM cycles of hop chase, per-hop pass, edge evaluation,
+                                                  bookkeeping, repair; [5] = repair waves handed to the whole-GPU sweep */);
 /* duration of the latest search kernel (measurement aid, always on) */
 int prgpu_nnf_last_dp_ms(prgpu_nnf_t *h, float *ms);
 

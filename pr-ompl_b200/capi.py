@@ -108,6 +108,7 @@ SIGNATURES = {
     "prgpu_nnf_set_edge_evaluator": (C.c_int, [c_vp, c_vp, c_vp]),
     "prgpu_nnf_set_mode": (C.c_int, [c_vp, C.c_int]),
     "prgpu_nnf_band_info": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), c_u32p]),
+    "prgpu_nnf_loop_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_vp]),
     "prgpu_nnf_last_dp_ms": (C.c_int, [c_vp, C.POINTER(C.c_float)]),
 }
 
@@ -572,6 +573,14 @@ class Nnf:
         tau, cells, reb = C.c_double(), C.c_uint64(), C.c_uint32()
         _check(lib().prgpu_nnf_band_info(self.h, C.byref(tau), C.byref(cells), C.byref(reb)))
         return dict(tau=tau.value, cells=cells.value, rebuilds=reb.value)
+
+    def loop_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        cyc = np.zeros(6, dtype=np.uint64)
+        _check(lib().prgpu_nnf_loop_stats(self.h, C.byref(a), C.byref(b), _ptr(cyc)))
+        names = ("hop_chase", "per_hop_pass", "edge_evaluation", "bookkeeping", "repair")
+        return dict(launches=a.value, repaired_vertices=b.value, phase_cycles={n: int(c) for n, c in zip(names, cyc)},
+                    wide_waves_handed_to_full_sweep=int(cyc[5]))
 
     def last_dp_ms(self):
         ms = C.c_float()

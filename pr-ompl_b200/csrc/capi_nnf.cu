@@ -58,6 +58,15 @@ struct prgpu_nnf {
   uint32_t band_rebuilds = 0;
   uint32_t total_iters = 0, n_evaluated = 0, n_collisions = 0;
   uint64_t knn_filter_calls = 0, knn_fallback_queries = 0;
+  // device-resident LazySP loop (mode 0 with a device world): the per-edge LazySP state lives on the device
+  // while that loop runs; the host mirrors (known / evaluated / blocked) are refreshed on demand
+  DevBuf d_succ_off, d_succ_pos, d_vop, d_stamp, d_worklist, d_known, d_evaluated, d_hop, d_path_pos, d_path_slot,
+      d_path_cell, d_out_path, d_trace, d_lazy_out;
+  bool host_state_current = true, dev_state_current = false;
+  uint32_t lazy_epoch = 0;
+  uint64_t repaired_vertices = 0, lazy_launches = 0;
+  uint64_t lazy_cycles[5] = {0, 0, 0, 0, 0};
+  uint64_t lazy_bailouts = 0;
 };
 
 namespace {
@@ -110,6 +119,12 @@ int nnf_build_band(prgpu_nnf *h, cudaStream_t s) {
   if ((rc = h->d_Bc.reserve(std::max<size_t>((size_t)h->band_cells * 8, 16))) != PRGPU_OK)
     return rc;
   h->bg.Bc = h->d_Bc.as<double>();
+  h->bg.hop = nullptr;
+  if (h->band_cells < (1ull << 36) && h->V < NNF_HOP_MAX_V) {
+    if ((rc = h->d_hop.reserve(std::max<size_t>((size_t)h->band_cells * 8, 16))) != PRGPU_OK)
+      return rc;
+    h->bg.hop = h->d_hop.as<unsigned long long>();
+  }
   rc = nnf_band_pack_launch(V, h->E, h->d_band_lo.as<uint32_t>(), h->d_band_w.as<unsigned long long>(),
                             h->d_col_off.as<unsigned long long>(), h->g.pred_off, h->g.pred_pos, h->g.pred_eid,
                             h->g.blocked, h->d_meta.as<NnfVertexMeta>(), h->d_edge.as<NnfEdgeRec>(), s);
@@ -118,6 +133,33 @@ int nnf_build_band(prgpu_nnf *h, cudaStream_t s) {
   h->band_valid = true;
   h->dirty_level = 0;
   ++h->band_rebuilds;
+  return PRGPU_OK;
+}
+
+// per-edge LazySP state: host mirrors <-> device arrays of the device-resident loop
+int nnf_state_to_host(prgpu_nnf *h) {
+  if (h->host_state_current)
+    return PRGPU_OK;
+  cudaStream_t s = h->stream;
+  if (h->E) {
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(h->known.data(), h->d_known.p, h->E, cudaMemcpyDeviceToHost, s));
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(h->evaluated.data(), h->d_evaluated.p, h->E, cudaMemcpyDeviceToHost, s));
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(h->blocked.data(), h->d_blocked.p, h->E, cudaMemcpyDeviceToHost, s));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  h->host_state_current = true;
+  return PRGPU_OK;
+}
+int nnf_state_to_device(prgpu_nnf *h) {
+  if (h->dev_state_current)
+    return PRGPU_OK;
+  cudaStream_t s = h->stream;
+  if (h->E) { // (blocked edges are mirrored on the device by both loops as they happen)
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(h->d_known.p, h->known.data(), h->E, cudaMemcpyHostToDevice, s));
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(h->d_evaluated.p, h->evaluated.data(), h->E, cudaMemcpyHostToDevice, s));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  h->dev_state_current = true;
   return PRGPU_OK;
 }
 
@@ -164,6 +206,10 @@ int prgpu_nnf_destroy(prgpu_nnf_t *h) {
     return PRGPU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  for (DevBuf *b : {&h->d_succ_off, &h->d_succ_pos, &h->d_vop, &h->d_stamp, &h->d_worklist, &h->d_known, &h->d_evaluated,
+                    &h->d_hop, &h->d_path_pos, &h->d_path_slot, &h->d_path_cell, &h->d_out_path, &h->d_trace,
+                    &h->d_lazy_out})
+    b->release();
   for (DevBuf *b : {&h->d_ftab, &h->d_states, &h->d_pose, &h->d_lvl_start, &h->d_level, &h->d_pred_off, &h->d_pred_pos,
                     &h->d_pred_eid, &h->d_blocked, &h->d_pnn, &h->d_pref, &h->d_B, &h->d_path, &h->d_pn, &h->d_cost,
                     &h->d_band_lo, &h->d_band_w, &h->d_col_off, &h->d_meta, &h->d_edge, &h->d_Bc, &h->d_scan_tmp,
@@ -482,16 +528,36 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
   h->blocked.assign(E, 0);
   h->known.assign(E, -1);
   NNF_TRY(upload(h->d_blocked, h->blocked, s));
+  NNF_TRY(upload(h->d_vop, h->vertex_of_pos, s));
   if (w) {
-    DevBuf d_vop;
-    int rc = upload(d_vop, h->vertex_of_pos, s);
-    if (rc == PRGPU_OK)
-      rc = h->d_pnn.reserve((size_t)V * 3 * 8);
-    if (rc == PRGPU_OK)
-      rc = nnf_translations_launch(h->d_pose.as<double>(), d_vop.as<uint32_t>(), V, h->d_pnn.as<double>(), s);
-    cudaStreamSynchronize(s);
-    d_vop.release();
-    NNF_TRY(rc);
+    NNF_TRY(h->d_pnn.reserve((size_t)V * 3 * 8));
+    NNF_TRY(nnf_translations_launch(h->d_pose.as<double>(), h->d_vop.as<uint32_t>(), V, h->d_pnn.as<double>(), s));
+    // successors by sorted position + the work arrays of the device-resident LazySP loop
+    std::vector<uint32_t> succ_off(V + 1, 0), succ_pos(E);
+    for (uint32_t o = 0; o < E; ++o)
+      succ_off[pred_pos[o] + 1]++;
+    for (uint32_t p = 0; p < V; ++p)
+      succ_off[p + 1] += succ_off[p];
+    {
+      std::vector<uint32_t> cur(succ_off.begin(), succ_off.end() - 1);
+      for (uint32_t p = 0; p < V; ++p)
+        for (uint32_t o = pred_off_s[p]; o < pred_off_s[p + 1]; ++o)
+          succ_pos[cur[pred_pos[o]]++] = p;
+    }
+    NNF_TRY(upload(h->d_succ_off, succ_off, s));
+    NNF_TRY(upload(h->d_succ_pos, succ_pos, s));
+    NNF_TRY(h->d_stamp.reserve((size_t)V * 4));
+    NNF_CUDA(cudaMemsetAsync(h->d_stamp.p, 0, (size_t)V * 4, s));
+    NNF_TRY(h->d_worklist.reserve((size_t)V * 4));
+    NNF_TRY(h->d_known.reserve(std::max<size_t>(E, 16)));
+    NNF_TRY(h->d_evaluated.reserve(std::max<size_t>(E, 16)));
+    const uint32_t cap_hops = Lv + 8;
+    NNF_TRY(h->d_path_pos.reserve((size_t)cap_hops * 4));
+    NNF_TRY(h->d_path_slot.reserve((size_t)cap_hops * 4));
+    NNF_TRY(h->d_path_cell.reserve((size_t)cap_hops * 8));
+    NNF_TRY(h->d_out_path.reserve((size_t)cap_hops * 4));
+    NNF_TRY(h->d_lazy_out.reserve(sizeof(NnfLazyOut)));
+    NNF_CUDA(cudaStreamSynchronize(s));
   }
   if (w) {
     std::vector<double> pref((size_t)R * 3);
@@ -544,6 +610,7 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
   bg.pref = g.pref;
   bg.ftab = nullptr;
   bg.Bc = nullptr;
+  bg.hop = nullptr;
   bg.start_pos = g.start_pos;
   bg.goal_pos = g.goal_pos;
   *out = h;
@@ -648,6 +715,12 @@ int prgpu_nnf_knn_stats(prgpu_nnf_t *h, uint64_t *filter_calls, uint64_t *fallba
 int prgpu_nnf_get_edges(prgpu_nnf_t *h, uint32_t *edges, uint8_t *flags) {
   if (!h)
     return fail(PRGPU_EINVAL, "nnf_get_edges: NULL handle");
+  if (flags) {
+    PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+    int rc = nnf_state_to_host(h);
+    if (rc != PRGPU_OK)
+      return rc;
+  }
   for (uint32_t e = 0; e < h->E; ++e) {
     if (edges) {
       edges[2 * (size_t)e] = h->edges[e].first;
@@ -656,6 +729,21 @@ int prgpu_nnf_get_edges(prgpu_nnf_t *h, uint32_t *edges, uint8_t *flags) {
     if (flags)
       flags[e] = (uint8_t)((h->evaluated[e] ? 1 : 0) | (h->blocked[e] ? 2 : 0));
   }
+  return PRGPU_OK;
+}
+
+int prgpu_nnf_loop_stats(prgpu_nnf_t *h, uint64_t *launches, uint64_t *repaired_vertices, uint64_t *phase_cycles) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "nnf_loop_stats: NULL handle");
+  if (phase_cycles) {
+    for (int i = 0; i < 5; ++i)
+      phase_cycles[i] = h->lazy_cycles[i];
+    phase_cycles[5] = h->lazy_bailouts;
+  }
+  if (launches)
+    *launches = h->lazy_launches;
+  if (repaired_vertices)
+    *repaired_vertices = h->repaired_vertices;
   return PRGPU_OK;
 }
 
@@ -686,7 +774,109 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
   std::vector<uint32_t> finalPath;
   bool solutionFound = false;
   uint32_t iters = 0;
-  while (iters < max_lazy_iters) { // NNFrechet.cpp:106
+  static const bool host_loop_forced = getenv("PRGPU_NNF_HOST_LOOP") != nullptr;
+  const bool device_loop = h->mode == 0 && !h->eval_fn && h->world && !host_loop_forced && h->V < NNF_HOP_MAX_V &&
+                           h->d_stamp.p != nullptr;
+  if (device_loop) {
+    // ---- the whole loop on the device: full search only after a band (re)build, local repair otherwise ----
+    int rc = nnf_state_to_device(h);
+    if (rc != PRGPU_OK)
+      return rc;
+    h->host_state_current = false;
+    if (goal_cost_trace && (rc = h->d_trace.reserve(std::max<size_t>((size_t)max_lazy_iters * 8, 16))) != PRGPU_OK)
+      return rc;
+    while (true) {
+      if (!h->band_valid) {
+        if (h->tau_ub == 0.0 && (rc = nnf_initial_tau(h, s)) != PRGPU_OK)
+          return rc;
+        if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
+          return rc;
+      }
+      if (!h->bg.hop)
+        return fail(PRGPU_ELIMIT, "nnf_solve: band too large for the hop words");
+      if (h->dirty_level < h->Lv) {
+        rc = nnf_flow_dp_launch(h->bg, h->lvl_start_host[h->dirty_level], ++h->epoch, h->d_done.as<uint32_t>(),
+                                h->sm_count, s, &h->timer);
+        if (rc != PRGPU_OK)
+          return rc;
+        h->dirty_level = h->Lv;
+      }
+      NnfLazyDev z;
+      z.succ_off = h->d_succ_off.as<uint32_t>();
+      z.succ_pos = h->d_succ_pos.as<uint32_t>();
+      z.level = h->g.level;
+      z.vertex_of_pos = h->d_vop.as<uint32_t>();
+      z.pred_eid = h->g.pred_eid;
+      z.edge_rw = h->d_edge.as<NnfEdgeRec>();
+      z.stamp = h->d_stamp.as<uint32_t>();
+      z.worklist = h->d_worklist.as<uint32_t>();
+      z.states = h->d_states.as<double>();
+      z.known = h->d_known.as<int8_t>();
+      z.evaluated = h->d_evaluated.as<uint8_t>();
+      z.blocked = h->d_blocked.as<uint8_t>();
+      z.path_pos = h->d_path_pos.as<uint32_t>();
+      z.path_slot = h->d_path_slot.as<uint32_t>();
+      z.path_cell = h->d_path_cell.as<unsigned long long>();
+      z.cap_hops = h->Lv + 8;
+      z.out_path = h->d_out_path.as<uint32_t>();
+      z.trace = goal_cost_trace ? h->d_trace.as<double>() + iters : nullptr;
+      z.out = h->d_lazy_out.as<NnfLazyOut>();
+      z.max_iters = max_lazy_iters - iters;
+      z.epoch = h->lazy_epoch;
+      z.tau_ub = h->tau_ub;
+      z.check_resolution = h->params.check_resolution;
+      z.band_full = h->band_full ? 1 : 0;
+      z.dof = dof;
+      if ((rc = nnf_lazysp_launch(h->world->host, h->world->dev, h->bg, z, s)) != PRGPU_OK)
+        return rc;
+      ++h->lazy_launches;
+      NnfLazyOut o;
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(&o, h->d_lazy_out.p, sizeof(o), cudaMemcpyDeviceToHost, s));
+      PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+      iters += o.iters;
+      h->total_iters += o.iters;
+      h->n_evaluated += o.n_evaluated;
+      h->n_collisions += o.n_collisions;
+      h->lazy_epoch = o.epoch;
+      h->repaired_vertices += o.repaired_vertices;
+      for (int i = 0; i < 5; ++i)
+        h->lazy_cycles[i] += o.cycles[i];
+      if (o.iters)
+        res->goal_cost = o.goal_cost;
+      if (o.final_error >= 0.0) // a path was extracted in this launch
+        res->final_error = o.final_error;
+      if (o.status == NNF_LAZY_NEED_FLOW) { // a wide repair wave: whole-GPU sweep from its level, then back to the loop
+        h->dirty_level = std::min(h->dirty_level, o.pad);
+        ++h->lazy_bailouts;
+        continue;
+      }
+      if (o.status == NNF_LAZY_NEED_REBUILD) {
+        static const double headroom = getenv("PRGPU_NNF_TAU_HEADROOM") ? atof(getenv("PRGPU_NNF_TAU_HEADROOM")) : 1.03;
+        h->tau_ub = o.goal_cost < 1e300 ? o.goal_cost * headroom : h->tau_ub * 2.0;
+        if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
+          return rc;
+        continue;
+      }
+      if (o.status == NNF_LAZY_ERROR)
+        return fail(PRGPU_ECUDA, "nnf_solve: inconsistent bottleneck table while following the hops");
+      if (o.status == NNF_LAZY_SOLVED) {
+        solutionFound = true;
+        finalPath.resize(o.path_len);
+        if (o.path_len)
+          PRGPU_CUDA_TRY(cudaMemcpyAsync(finalPath.data(), h->d_out_path.p, (size_t)o.path_len * 4, cudaMemcpyDeviceToHost, s));
+      }
+      break; // solved, no path, or the iteration budget of this call is spent
+    }
+    if (goal_cost_trace && iters)
+      PRGPU_CUDA_TRY(cudaMemcpyAsync(goal_cost_trace, h->d_trace.p, (size_t)iters * 8, cudaMemcpyDeviceToHost, s));
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+  } else {
+    int rc0 = nnf_state_to_host(h);
+    if (rc0 != PRGPU_OK)
+      return rc0;
+    h->dev_state_current = false;
+  }
+  while (!device_loop && iters < max_lazy_iters) { // NNFrechet.cpp:106
     int rc;
     uint32_t np = 0;
     double goalCost = 0.0;

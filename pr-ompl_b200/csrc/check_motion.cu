@@ -22,6 +22,9 @@ namespace prgpu {
 namespace {
 
 constexpr int CM_THREADS = 128;
+#ifndef CM_MINB
+#define CM_MINB 8 // resident blocks per SM the two FK-heavy kernels of the pair-dealt pipeline are compiled for
+#endif
 
 template <int SP>
 __global__ void __launch_bounds__(CM_THREADS)
@@ -335,7 +338,7 @@ __device__ __forceinline__ bool cm_push_items(const CmItems &it, uint32_t ref, u
   return true;
 }
 
-__global__ void __launch_bounds__(CM_THREADS)
+__global__ void __launch_bounds__(CM_THREADS, CM_MINB)
 cm_sample2_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
                   uint32_t n, double resolution, int mode, int check_first, volatile uint8_t *valid,
                   uint32_t *__restrict__ owed, uint2 *__restrict__ gaps, CmItems items) {
@@ -463,7 +466,7 @@ cm_lists_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ f
 }
 
 // phase B against the clearance field only
-__global__ void __launch_bounds__(CM_THREADS)
+__global__ void __launch_bounds__(CM_THREADS, CM_MINB)
 cm_certify_b_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ from, const double *__restrict__ to,
                     uint32_t total, double resolution, int mode, int check_first, volatile uint8_t *valid,
                     const uint32_t *__restrict__ item_edge, const uint32_t *__restrict__ item_p, CmItems items) {

@@ -23,6 +23,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "kdtree.cuh"
 
 namespace prgpu {
@@ -366,6 +367,329 @@ kd_search_kernel(const KdNode *__restrict__ nodes, const double *__restrict__ le
   if (visited && lane == 0)
     atomicAdd(visited, nvis);
 }
+
+// ---- team search: the same traversal, with the warps of a block helping one another -----------------------
+// A query is a dependent chain (descend -> leaf -> pop), ~2 us per leaf for a lone warp, so the slowest query of
+// a batch bounds the kernel and a small batch cannot fill the machine.  Here a block of KD_WARPS warps owns QPB
+// queries (QPB <= KD_WARPS, chosen by the host from the batch size).  Every warp is a WORKER: it explores one
+// subtree of one query with a private register stack and a private sorted list, exactly as above.  A worker that
+// runs out of work raises its bit in `idle`; a busy worker that sees an idle bit hands over the BOTTOM entry of
+// its stack (the shallowest pending subtree) through the idle warp's mailbox.  The workers of a query share one
+// pruning bound (the smallest k-th distance any of them holds -- k real nodes, hence an upper bound of the true
+// k-th distance) and merge their lists into the query's list when their subtree is done; the last one writes the
+// result.  Same distances, same (distance, index) order, so the output is bit-identical to the single-warp search.
+struct KdSlot {                 // one query of the block
+  double qx[8];
+  double list_d[32];
+  uint32_t list_i[32];
+  unsigned long long bound;     // bits of the squared pruning bound (non-negative doubles order like their bits)
+  uint32_t lock, workers, qid, pad;
+};
+struct KdMail {
+  double rd;
+  uint32_t node, slot;
+  volatile uint32_t ready;
+  uint32_t pad;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(KD_WARPS * 32, KD_MINB)
+kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict__ leaf_pts,
+                      const uint32_t *__restrict__ leaf_idx, const float *__restrict__ root_cell, int levels,
+                      uint32_t index_base, const double *__restrict__ queries, uint32_t nq, int k, int qpb,
+                      uint32_t *__restrict__ idx_out, double *__restrict__ dist_out,
+                      unsigned long long *__restrict__ visited) {
+  __shared__ KdSlot slots[KD_WARPS];
+  __shared__ KdMail mail[KD_WARPS];
+  __shared__ uint32_t idle; // bit w: warp w waits for work
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t first_leaf = (1u << levels) - 1u;
+  const uint32_t ALL = (1u << KD_WARPS) - 1u;
+  // ---- set-up: slot w <- query blockIdx.x * qpb + w ----
+  if (w < qpb) {
+    const uint32_t q = blockIdx.x * (uint32_t)qpb + (uint32_t)w;
+    KdSlot &sl = slots[w];
+    if (lane < 8)
+      sl.qx[lane] = (q < nq && lane < DIM) ? queries[(size_t)q * DIM + lane] : 0.0;
+    sl.list_d[lane] = INFINITY;
+    sl.list_i[lane] = PRGPU_INVALID_INDEX;
+    if (lane == 0) {
+      sl.bound = (unsigned long long)__double_as_longlong((double)INFINITY);
+      sl.lock = 0;
+      sl.workers = q < nq ? 1u : 0u;
+      sl.qid = q;
+    }
+  }
+  if (lane == 0) {
+    mail[w].ready = 0;
+    if (w == 0)
+      idle = 0;
+  }
+  __syncthreads();
+  bool have = w < qpb && slots[w].workers != 0;
+  uint32_t slot = (uint32_t)w, node = 0;
+  double rd = 0.0;
+  if (have) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const double x = slots[w].qx[d];
+      const double o = fmax(0.0, fmax((double)root_cell[d] - x, x - (double)root_cell[8 + d]));
+      rd += o * o;
+    }
+  }
+  unsigned long long nvis = 0;
+  while (true) {
+    if (!have) {
+      // ---- idle: advertise, then wait for a hand-over or for everybody to be idle ----
+      if (lane == 0)
+        atomicOr(&idle, 1u << w);
+      bool got = false, quit = false;
+      while (!got && !quit) {
+        if (lane == 0) {
+          if (mail[w].ready) {
+            got = true;
+          } else if (*(volatile uint32_t *)&idle == ALL) {
+            quit = true;
+          } else {
+            __nanosleep(200);
+          }
+        }
+        got = __shfl_sync(0xFFFFFFFFu, (int)got, 0) != 0;
+        quit = __shfl_sync(0xFFFFFFFFu, (int)quit, 0) != 0;
+      }
+      if (quit)
+        break;
+      __threadfence_block();
+      slot = mail[w].slot;
+      node = mail[w].node;
+      rd = mail[w].rd;
+      __syncwarp();
+      if (lane == 0)
+        mail[w].ready = 0;
+      have = true;
+    }
+    // ---- one work unit: the subtree `node` (cell distance rd) of query slot `slot` ----
+    KdSlot &sl = slots[slot];
+    const double *xq = sl.qx;
+    double qx[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+      qx[d] = xq[d];
+    double best_d = INFINITY;
+    uint32_t best_i = PRGPU_INVALID_INDEX;
+    double r2loc = INFINITY; // from this worker's own list
+    uint32_t stk_node = 0;
+    double stk_rd = 0.0;
+    int sp = 0;
+    KdTreelet tl;
+    tl.delta = 0.0;
+    tl.left = true;
+    if (node < first_leaf)
+      tl = kd_load_treelet(nodes, node, first_leaf, lane, xq);
+    int tv = 0;
+    uint32_t to = 0;
+    bool alive = true;
+    while (alive) {
+      double r2hi = fmin(r2loc, __longlong_as_double((long long)*(volatile unsigned long long *)&sl.bound));
+      while (node < first_leaf) {
+        if (tv > 3) {
+          tl = kd_load_treelet(nodes, node, first_leaf, lane, xq);
+          tv = 0;
+          to = 0;
+        }
+        const int src = (1 << tv) - 1 + (int)to;
+        const bool left = __shfl_sync(0xFFFFFFFFu, (int)tl.left, src) != 0;
+        const double rd_far = rd + __shfl_sync(0xFFFFFFFFu, tl.delta, src);
+        if (rd_far * (1.0 - 1e-12) <= r2hi) {
+          const uint32_t far = 2 * node + (left ? 2u : 1u);
+          if (lane == sp) {
+            stk_node = far;
+            stk_rd = rd_far;
+          }
+          ++sp;
+          if (far >= first_leaf) {
+            const char *base = reinterpret_cast<const char *>(leaf_pts + (size_t)(far - first_leaf) * DIM * KD_LEAF);
+            if (lane * 128 < DIM * KD_LEAF * 8)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(base + lane * 128));
+          } else if (lane < 4) {
+            const uint64_t idx = (((uint64_t)far + 1) << lane) - 1;
+            if (idx < first_leaf)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + idx));
+          }
+        }
+        node = 2 * node + (left ? 1u : 2u);
+        ++tv;
+        to = 2 * to + (left ? 0u : 1u);
+      }
+      const uint32_t leaf = node - first_leaf;
+      const double *lp = leaf_pts + (size_t)leaf * DIM * KD_LEAF + lane;
+      double c0[KD_PPL_][DIM];
+      uint32_t my_i[KD_PPL_];
+#pragma unroll
+      for (int j = 0; j < KD_PPL_; ++j) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+          c0[j][d] = lp[d * KD_LEAF + j * 32];
+        my_i[j] = leaf_idx[(size_t)leaf * KD_LEAF + j * 32 + lane];
+      }
+      // ---- while the leaf loads are in flight: hand the bottom of the stack to an idle warp ----
+      if (sp >= 2 && *(volatile uint32_t *)&idle != 0) {
+        int target = -1;
+        if (lane == 0) {
+          const uint32_t m = *(volatile uint32_t *)&idle;
+          if (m) {
+            const int t = __ffs(m) - 1;
+            if (atomicAnd(&idle, ~(1u << t)) & (1u << t))
+              target = t;
+          }
+        }
+        target = __shfl_sync(0xFFFFFFFFu, target, 0);
+        if (target >= 0) {
+          const uint32_t dn = __shfl_sync(0xFFFFFFFFu, stk_node, 0);
+          const double dr = __shfl_sync(0xFFFFFFFFu, stk_rd, 0);
+          if (lane == 0) {
+            atomicAdd(&sl.workers, 1u);
+            mail[target].slot = slot;
+            mail[target].node = dn;
+            mail[target].rd = dr;
+            __threadfence_block();
+            mail[target].ready = 1;
+          }
+          stk_node = __shfl_down_sync(0xFFFFFFFFu, stk_node, 1);
+          stk_rd = __shfl_down_sync(0xFFFFFFFFu, stk_rd, 1);
+          --sp;
+        }
+      }
+      uint32_t nx_node = 0;
+      double nx_rd = 0.0;
+      KdTreelet nx_tl = tl;
+      if (sp > 0) {
+        nx_node = __shfl_sync(0xFFFFFFFFu, stk_node, sp - 1);
+        nx_rd = __shfl_sync(0xFFFFFFFFu, stk_rd, sp - 1);
+        if (nx_node < first_leaf)
+          nx_tl = kd_load_treelet(nodes, nx_node, first_leaf, lane, xq);
+      }
+      double s[KD_PPL_];
+#pragma unroll
+      for (int j = 0; j < KD_PPL_; ++j) {
+        double a = __dsub_rn(c0[j][0], qx[0]);
+        s[j] = __dmul_rn(a, a);
+#pragma unroll
+        for (int d = 1; d < DIM; ++d) {
+          a = __dsub_rn(c0[j][d], qx[d]);
+          s[j] = __dadd_rn(s[j], __dmul_rn(a, a));
+        }
+      }
+      nvis += 1;
+      bool improved = false;
+#pragma unroll
+      for (int j = 0; j < KD_PPL_; ++j) {
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, my_i[j] != PRGPU_INVALID_INDEX && s[j] <= r2hi);
+        while (cand) {
+          const int c = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const double cs = __shfl_sync(0xFFFFFFFFu, s[j], c);
+          const uint32_t ci = __shfl_sync(0xFFFFFFFFu, my_i[j], c);
+          if (cs > r2hi)
+            continue;
+          const double cd = __dsqrt_rn(cs);
+          const bool before = lane < k && (best_d < cd || (best_d == cd && best_i < ci));
+          const int pos = __popc(__ballot_sync(0xFFFFFFFFu, before));
+          if (pos >= k)
+            continue;
+          const double up_d = __shfl_up_sync(0xFFFFFFFFu, best_d, 1);
+          const uint32_t up_i = __shfl_up_sync(0xFFFFFFFFu, best_i, 1);
+          if (lane == pos) {
+            best_d = cd;
+            best_i = ci;
+          } else if (lane > pos && lane < k) {
+            best_d = up_d;
+            best_i = up_i;
+          }
+          const double r = __shfl_sync(0xFFFFFFFFu, best_d, k - 1);
+          if (r < INFINITY) {
+            r2loc = __dmul_ru(r, r) * (1.0 + 0x1p-50);
+            r2hi = fmin(r2hi, r2loc);
+            improved = true;
+          }
+        }
+      }
+      if (improved && lane == 0)
+        atomicMin(&sl.bound, (unsigned long long)__double_as_longlong(r2loc));
+      r2hi = fmin(r2hi, __longlong_as_double((long long)*(volatile unsigned long long *)&sl.bound));
+      alive = false;
+      bool first_pop = true;
+      while (sp > 0) {
+        --sp;
+        const uint32_t pn = first_pop ? nx_node : __shfl_sync(0xFFFFFFFFu, stk_node, sp);
+        const double prd = first_pop ? nx_rd : __shfl_sync(0xFFFFFFFFu, stk_rd, sp);
+        if (prd * (1.0 - 1e-12) <= r2hi) {
+          node = pn;
+          rd = prd;
+          if (pn < first_leaf)
+            tl = first_pop ? nx_tl : kd_load_treelet(nodes, pn, first_leaf, lane, xq);
+          tv = 0;
+          to = 0;
+          alive = true;
+          break;
+        }
+        first_pop = false;
+      }
+    }
+    // ---- the unit is done: merge this worker's list into the query's (under the slot lock) ----
+    if (lane == 0) {
+      while (atomicCAS(&sl.lock, 0u, 1u) != 0u)
+        __nanosleep(50);
+    }
+    __syncwarp();
+    __threadfence_block();
+    {
+      double md = sl.list_d[lane];
+      uint32_t mi = sl.list_i[lane];
+      const int mine = __popc(__ballot_sync(0xFFFFFFFFu, lane < k && best_i != PRGPU_INVALID_INDEX));
+      for (int c = 0; c < mine; ++c) { // ascending: once one entry does not enter, none of the rest does
+        const double cd = __shfl_sync(0xFFFFFFFFu, best_d, c);
+        const uint32_t ci = __shfl_sync(0xFFFFFFFFu, best_i, c);
+        const bool before = lane < k && (md < cd || (md == cd && mi < ci));
+        const int pos = __popc(__ballot_sync(0xFFFFFFFFu, before));
+        if (pos >= k)
+          break;
+        const double up_d = __shfl_up_sync(0xFFFFFFFFu, md, 1);
+        const uint32_t up_i = __shfl_up_sync(0xFFFFFFFFu, mi, 1);
+        if (lane == pos) {
+          md = cd;
+          mi = ci;
+        } else if (lane > pos && lane < k) {
+          md = up_d;
+          mi = up_i;
+        }
+      }
+      sl.list_d[lane] = md;
+      sl.list_i[lane] = mi;
+      const double r = __shfl_sync(0xFFFFFFFFu, md, k - 1);
+      uint32_t left = 0;
+      if (lane == 0) {
+        if (r < INFINITY)
+          atomicMin(&sl.bound, (unsigned long long)__double_as_longlong(__dmul_ru(r, r) * (1.0 + 0x1p-50)));
+        left = atomicSub(&sl.workers, 1u) - 1u;
+      }
+      left = __shfl_sync(0xFFFFFFFFu, left, 0);
+      if (left == 0 && lane < k) { // the query's last worker writes the result
+        const uint32_t q = sl.qid;
+        idx_out[(size_t)q * k + lane] = mi == PRGPU_INVALID_INDEX ? mi : mi + index_base;
+        if (dist_out)
+          dist_out[(size_t)q * k + lane] = md;
+      }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0)
+      atomicExch(&sl.lock, 0u);
+    have = false;
+  }
+  if (visited && lane == 0 && nvis)
+    atomicAdd(visited, nvis);
+}
 } // namespace
 
 void KdIndex::release() {
@@ -471,6 +795,44 @@ int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev,
     return fail(PRGPU_ELIMIT, "kd_search: k must be in [1,32]");
   if (nq == 0)
     return PRGPU_OK;
+  static const int team_env = getenv("PRGPU_KD_TEAM") ? atoi(getenv("PRGPU_KD_TEAM")) : -1;
+  if (team_env != 0 && KD_WARPS >= 2) {
+    // queries per block: all KD_WARPS warps own a query when the batch alone fills the machine; smaller batches
+    // get several warps per query from the start (PRGPU_KD_TEAM = queries per block, 0 = the single-warp kernel)
+    int qpb = KD_WARPS;
+    while (qpb > 1 && (uint64_t)nq * KD_WARPS < (uint64_t)qpb * 4096)
+      qpb >>= 1;
+    if (team_env > 0)
+      qpb = std::min(team_env, (int)KD_WARPS);
+    const unsigned tblocks = (nq + qpb - 1) / qpb;
+    if (timer)
+      timer->begin(stream);
+    switch (kd.dim) {
+#define KD_CASE(D)                                                                                 \
+  case D:                                                                                          \
+    kd_search_team_kernel<D><<<tblocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell, \
+                                                                   kd.levels, index_base, queries_dev, nq, k, qpb,     \
+                                                                   idx_dev, dist_dev,                                  \
+                                                                   kd.count_visits ? kd.visited : nullptr);            \
+    break;
+      KD_CASE(1)
+      KD_CASE(2)
+      KD_CASE(3)
+      KD_CASE(4)
+      KD_CASE(5)
+      KD_CASE(6)
+      KD_CASE(7)
+      KD_CASE(8)
+#undef KD_CASE
+    default:
+      return fail(PRGPU_ELIMIT, "kd_search: dim must be in [1,8]");
+    }
+    PRGPU_COUNT_LAUNCH(1);
+    if (timer)
+      timer->end(stream);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    return PRGPU_OK;
+  }
   const unsigned blocks = (nq + KD_WARPS - 1) / KD_WARPS;
   if (timer)
     timer->begin(stream);

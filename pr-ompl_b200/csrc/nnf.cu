@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 #include "nnf.cuh"
+#include "edge_plan.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -508,6 +509,322 @@ nnf_flow_dp_kernel(const NnfBandDev g, uint32_t first_pos, uint32_t epoch, volat
   }
 }
 
+// ---- device-resident LazySP loop (nnf.cuh: NnfLazyDev) -----------------------------------------------------
+constexpr int LAZY_THREADS = 512;
+constexpr uint32_t LAZY_WAVE_BUDGET = 2048; // columns one block repairs per knock-out before it hands the rest
+                                            // of the wave to the whole-GPU sweep (about the cost of that sweep)
+
+constexpr uint32_t LAZY_WL_CAP = 4096;   // dirty vertices of one wave kept in shared memory
+constexpr uint32_t LAZY_HASH = 8192;     // open-addressing set of the wave's vertices (de-duplication)
+constexpr uint32_t LAZY_DONE = 0xFFFFFFFFu;
+
+template <int SP>
+__global__ void __launch_bounds__(LAZY_THREADS)
+nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const NnfLazyDev z, uint32_t tables_bytes) {
+  const DeviceWorld &w = *wp;
+  extern __shared__ float4 s_obs[];
+  const ObstacleTables tabs = load_tables(w, s_obs);
+  // the repair wave's bookkeeping lives in shared memory: the level starts (level of a sorted position by binary
+  // search), the wave's dirty vertices with their levels, a hash set against duplicates, the current level's list
+  uint32_t *s_lvl_start = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(s_obs) + tables_bytes);
+  uint32_t *wl_pos = s_lvl_start + ((g.Lv + 1 + 3) & ~3u);
+  uint32_t *wl_level = wl_pos + LAZY_WL_CAP;
+  uint32_t *hset = wl_level + LAZY_WL_CAP;
+  uint32_t *cur = hset + LAZY_HASH;
+  __shared__ uint32_t s_status, s_n, s_level, s_target, s_wl_n, s_cur_n, s_next, s_overflow;
+  __shared__ unsigned long long s_err_bits;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t NW = LAZY_THREADS / 32;
+  for (uint32_t i = tid; i <= g.Lv; i += LAZY_THREADS)
+    s_lvl_start[i] = g.lvl_start[i];
+  __syncthreads();
+  auto level_of = [&](uint32_t pos) -> uint32_t { // largest L with lvl_start[L] <= pos
+    uint32_t lo = 0, hi = g.Lv;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_lvl_start[mid] <= pos)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    return lo;
+  };
+  auto push = [&](uint32_t pos) { // one thread: add a dirty vertex to the wave (once)
+    uint32_t hslot = (pos * 2654435761u) & (LAZY_HASH - 1u);
+    while (true) {
+      const uint32_t old = atomicCAS(hset + hslot, 0u, pos + 1u);
+      if (old == pos + 1u)
+        return; // already in the wave
+      if (old == 0u)
+        break;
+      hslot = (hslot + 1u) & (LAZY_HASH - 1u);
+    }
+    const uint32_t i = atomicAdd(&s_wl_n, 1u);
+    if (i >= LAZY_WL_CAP) {
+      s_overflow = 1;
+      return;
+    }
+    const uint32_t lv = level_of(pos);
+    wl_pos[i] = pos;
+    wl_level[i] = lv;
+    atomicMin(&s_next, lv);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.meta + pos)); // the warp that takes it starts with this record
+  };
+  const int dof = z.dof;
+  const uint32_t R = (uint32_t)g.R;
+  uint32_t iters = 0, epoch = z.epoch, n_eval = 0, n_coll = 0, repaired = 0; // thread 0's copies are the truth
+  double goal_cost = 0.0, final_error = -1.0; // final_error < 0: no path extracted by this launch
+  uint32_t path_len = 0;
+  unsigned long long cyc[5] = {0, 0, 0, 0, 0};
+  long long t_mark = clock64();
+  auto lap = [&](int phase) { // thread 0's phase clock
+    const long long now = clock64();
+    cyc[phase] += (unsigned long long)(now - t_mark);
+    t_mark = now;
+  };
+  while (true) {
+    // ---- search result: the goal's cost, then the hops of the optimum, goal -> start ----
+    if (tid == 0) {
+      uint32_t status = NNF_LAZY_RUNNING;
+      s_err_bits = 0ull;
+      if (iters >= z.max_iters) {
+        status = NNF_LAZY_CONTINUE;
+      } else {
+        const NnfVertexMeta mg = g.meta[g.goal_pos];
+        const uint32_t gi = (R - 1u) - mg.band_lo;
+        const double cost = gi < mg.band_w ? __ldcg(g.Bc + mg.col_off + gi) : NNF_INF;
+        if (!(cost <= z.tau_ub) && !z.band_full) {
+          goal_cost = cost; // the band may not contain the optimum: the host widens it (NNF_LAZY_NEED_REBUILD)
+          status = NNF_LAZY_NEED_REBUILD;
+        } else {
+          if (z.trace)
+            z.trace[iters] = cost;
+          ++iters;
+          goal_cost = cost;
+          if (cost == NNF_INF) {
+            status = NNF_LAZY_NO_PATH; // the search found no path (NNFrechet.cpp:112-113)
+          } else {
+            uint32_t n = 0, pos = g.goal_pos;
+            unsigned long long cell = mg.col_off + gi;
+            while (true) {
+              if (n >= z.cap_hops) {
+                status = NNF_LAZY_ERROR;
+                break;
+              }
+              z.path_pos[n] = pos;
+              z.path_cell[n] = cell;
+              ++n;
+              const unsigned long long h = __ldcg(g.hop + cell);
+              if (h == NNF_HOP_START)
+                break;
+              if (h == NNF_HOP_NONE) {
+                status = NNF_LAZY_ERROR;
+                break;
+              }
+              cell = h >> 28;
+              pos = (uint32_t)(h >> 1) & (NNF_HOP_MAX_V - 1u);
+            }
+            s_n = n;
+          }
+        }
+      }
+      s_status = status;
+      lap(0);
+    }
+    __syncthreads();
+    if (s_status != NNF_LAZY_RUNNING)
+      break;
+    const uint32_t n = s_n; // hop 0 = c1 (goal), hop n-1 = c0 (start)
+    // ---- per hop, a warp each: the NN edge it crossed, and max node weight over the rows it stayed (mFinalError
+    //      = max over the NON-dummy path nodes, NNFrechet.cpp:629-640) ----
+    for (uint32_t i = warp; i < n; i += NW) {
+      const uint32_t sp = z.path_pos[i];
+      const NnfVertexMeta m = g.meta[sp];
+      const unsigned long long cell = z.path_cell[i];
+      const uint32_t r_hi = m.band_lo + (uint32_t)(cell - m.col_off);
+      const unsigned long long h = g.hop[cell];
+      uint32_t r_lo = 0;
+      if (h != NNF_HOP_START) {
+        const uint32_t pp = (uint32_t)(h >> 1) & (NNF_HOP_MAX_V - 1u);
+        const NnfVertexMeta mp = g.meta[pp];
+        r_lo = mp.band_lo + (uint32_t)((h >> 28) - mp.col_off) + (uint32_t)(h & 1ull);
+        // CSR slot of the NN edge pp -> sp
+        uint32_t slot = 0xFFFFFFFFu;
+        for (uint32_t e = m.pred_begin + lane; e < m.pred_end; e += 32)
+          if (g.pred_pos[e] == pp)
+            slot = e;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+          slot = min(slot, __shfl_xor_sync(0xffffffffu, slot, off));
+        if (lane == 0)
+          z.path_slot[i] = slot;
+      }
+      if (sp != g.start_pos && sp != g.goal_pos) {
+        double fm = 0.0;
+        for (uint32_t r = r_lo + lane; r <= r_hi; r += 32)
+          fm = fmax(fm, node_weight(g.ftab, g.R, g.pref, g.pnn, r, sp));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+          fm = fmax(fm, __shfl_xor_sync(0xffffffffu, fm, off));
+        if (lane == 0)
+          atomicMax(&s_err_bits, (unsigned long long)__double_as_longlong(fm)); // non-negative doubles order like their bits
+      }
+    }
+    __syncthreads();
+    if (tid == 0)
+      lap(1);
+    // ---- evaluateEdge for the path's NN edges whose verdict is not known yet (a warp per edge) ----
+    // NN path, start -> goal: hops n-2 .. 1; the edge INTO hop i comes from hop i+1: edges i = n-3 .. 1
+    for (uint32_t i = 1 + warp; i + 2 < n; i += NW) {
+      const uint32_t eid = z.pred_eid[z.path_slot[i]];
+      if (z.known[eid] >= 0)
+        continue;
+      const uint32_t vu = z.vertex_of_pos[z.path_pos[i + 1]], vv = z.vertex_of_pos[z.path_pos[i]];
+      double a[WORLD_MAX_DOF], b[WORLD_MAX_DOF];
+#pragma unroll
+      for (int k = 0; k < WORLD_MAX_DOF; ++k) {
+        a[k] = k < dof ? z.states[(size_t)vu * dof + k] : 0.0;
+        b[k] = k < dof ? z.states[(size_t)vv * dof + k] : 0.0;
+      }
+      const EdgePlan pl = plan_edge(a, b, z.check_resolution, PRGPU_MODE_NNF_ALPHA, 0);
+      bool ok = true;
+      for (uint32_t p0 = 0; p0 < pl.np && ok; p0 += 32) {
+        bool good = true;
+        if (p0 + lane < pl.np) {
+          double q[WORLD_MAX_DOF];
+          edge_state(pl, a, b, PRGPU_MODE_NNF_ALPHA, p0 + lane, q);
+          good = state_valid_call<SP>(wp, &tabs, q);
+        }
+        ok = !__any_sync(0xffffffffu, !good);
+      }
+      if (lane == 0)
+        z.known[eid] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- the reference's bookkeeping, in path order (NNFrechet.cpp:120-151) ----
+    if (tid == 0) {
+      lap(2);
+      final_error = __longlong_as_double((long long)s_err_bits);
+      bool collision_free = true;
+      for (uint32_t i = n >= 3 ? n - 3 : 0; i >= 1 && n >= 3; --i) {
+        const uint32_t slot = z.path_slot[i], eid = z.pred_eid[slot];
+        if (!z.evaluated[eid]) {
+          z.evaluated[eid] = 1;
+          ++n_eval;
+          if (z.known[eid] == 0) { // markEdgeInCollision (:131-136, :685-702)
+            z.blocked[eid] = 1;
+            z.edge_rw[slot].band_w_blocked |= 0x80000000u;
+            ++n_coll;
+            collision_free = false;
+            s_target = z.path_pos[i];
+            break;
+          }
+        }
+      }
+      if (collision_free) {
+        path_len = n >= 2 ? n - 2 : 0;
+        for (uint32_t k = 0; k < path_len; ++k)
+          z.out_path[k] = z.vertex_of_pos[z.path_pos[n - 2 - k]];
+        s_status = NNF_LAZY_SOLVED;
+      } else {
+        // repair: the knocked-out edge's target is the first dirty vertex
+        ++epoch;
+        s_wl_n = 0;
+        s_overflow = 0;
+        s_next = LAZY_DONE;
+      }
+      lap(3);
+    }
+    __syncthreads();
+    if (s_status != NNF_LAZY_RUNNING)
+      break;
+    // ---- local repair, level by level: recompute the dirty vertices' columns; a changed column makes the
+    //      vertex's successors dirty (they sit at later levels).  Mostly a long, thin wave (one or two vertices
+    //      per level along the old optimum): a latency chain, so its bookkeeping stays in shared memory ----
+    for (uint32_t i = tid; i < LAZY_HASH; i += LAZY_THREADS)
+      hset[i] = 0;
+    __syncthreads();
+    if (tid == 0)
+      push(s_target);
+    __syncthreads();
+    uint32_t L = s_next, wave = 0;
+    bool bailed = false;
+    while (L != LAZY_DONE) {
+      __syncthreads(); // everybody has read L
+      // the entries of level L -> cur[]; the smallest later level -> s_next
+      if (tid == 0) {
+        s_cur_n = 0;
+        s_next = LAZY_DONE;
+      }
+      __syncthreads();
+      const uint32_t nwl = min(s_wl_n, LAZY_WL_CAP);
+      for (uint32_t i = tid; i < nwl; i += LAZY_THREADS) {
+        const uint32_t lv = wl_level[i];
+        if (lv == L) {
+          const uint32_t j = atomicAdd(&s_cur_n, 1u);
+          if (j < LAZY_WAVE_BUDGET)
+            cur[j] = wl_pos[i];
+          wl_level[i] = LAZY_DONE;
+        } else if (lv != LAZY_DONE) {
+          atomicMin(&s_next, lv);
+        }
+      }
+      __syncthreads();
+      const uint32_t cnt = s_cur_n;
+      wave += cnt;
+      if (wave > LAZY_WAVE_BUDGET || s_overflow) { // everything before level L is consistent; the host re-sweeps
+        bailed = true;                             // levels >= L with the whole GPU
+        break;
+      }
+      for (uint32_t i = warp; i < cnt; i += NW) {
+        const uint32_t sp = cur[i];
+        const NnfVertexMeta m = g.meta[sp];
+        const uint32_t so0 = z.succ_off[sp], so1 = z.succ_off[sp + 1]; // in flight while the column is computed
+        uint32_t first_succ = so0 + lane < so1 ? z.succ_pos[so0 + lane] : 0u;
+        if (m.band_w != 0 && band_column<true>(g, sp, m, lane))
+          for (uint32_t e = so0 + lane; e < so1; e += 32) {
+            push(e == so0 + lane ? first_succ : z.succ_pos[e]);
+          }
+      }
+      __syncthreads();
+      if (tid == 0)
+        repaired += cnt;
+      if (s_overflow) { // a successor did not fit: it sits at a level > L, re-sweep from L + 1
+        bailed = true;
+        ++L;
+        break;
+      }
+      L = s_next;
+    }
+    if (tid == 0)
+      lap(4);
+    if (bailed) {
+      if (tid == 0) {
+        s_status = NNF_LAZY_NEED_FLOW;
+        s_level = L;
+      }
+      __syncthreads();
+      break;
+    }
+  }
+  if (tid == 0) {
+    NnfLazyOut o;
+    for (int i = 0; i < 5; ++i)
+      o.cycles[i] = cyc[i];
+    o.status = s_status;
+    o.iters = iters;
+    o.n_evaluated = n_eval;
+    o.n_collisions = n_coll;
+    o.path_len = path_len;
+    o.epoch = epoch;
+    o.repaired_vertices = repaired;
+    o.pad = s_status == NNF_LAZY_NEED_FLOW ? s_level : 0;
+    o.goal_cost = goal_cost;
+    o.final_error = final_error;
+    *z.out = o;
+  }
+}
+
 __device__ __forceinline__ double band_get(const NnfBandDev &g, uint32_t r, uint32_t s) {
   const NnfVertexMeta m = g.meta[s];
   const uint32_t i = r - m.band_lo;
@@ -747,6 +1064,35 @@ int nnf_band_backtrack_launch(const NnfBandDev &g, uint32_t *out_path, uint32_t 
 int nnf_backtrack_launch(const NnfGraphDev &g, uint32_t *out_path, uint32_t cap_pairs, uint32_t *out_n,
                          double *out_cost, cudaStream_t stream) {
   nnf_backtrack_kernel<<<1, 32, 0, stream>>>(g, out_path, cap_pairs, out_n, out_cost); PRGPU_COUNT_LAUNCH(1);
+  PRGPU_CUDA_TRY(cudaGetLastError());
+  return PRGPU_OK;
+}
+
+int nnf_lazysp_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const NnfBandDev &g, const NnfLazyDev &z,
+                      cudaStream_t stream) {
+  const size_t tables = (obstacle_tables_bytes(w) + 15) & ~(size_t)15;
+  const size_t smem = tables + (((size_t)g.Lv + 1 + 3) & ~(size_t)3) * sizeof(uint32_t) +
+                      (2 * (size_t)LAZY_WL_CAP + LAZY_HASH + LAZY_WAVE_BUDGET) * sizeof(uint32_t);
+  if (smem > 200 * 1024)
+    return fail(PRGPU_ELIMIT, "nnf_lazysp: obstacle tables + level counters exceed shared memory");
+#define NNF_LAZY_CASE(SPV)                                                                         \
+  do {                                                                                             \
+    auto kern = nnf_lazysp_kernel<SPV>;                                                            \
+    PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<1, LAZY_THREADS, smem, stream>>>(w_dev, g, z, (uint32_t)tables);                        \
+  } while (0)
+  if (w.grid_n[0] > 0)
+    NNF_LAZY_CASE(0);
+  else if (w.S <= 8)
+    NNF_LAZY_CASE(8);
+  else if (w.S <= 16)
+    NNF_LAZY_CASE(16);
+  else if (w.S <= 24)
+    NNF_LAZY_CASE(24);
+  else
+    NNF_LAZY_CASE(32);
+#undef NNF_LAZY_CASE
+  PRGPU_COUNT_LAUNCH(1);
   PRGPU_CUDA_TRY(cudaGetLastError());
   return PRGPU_OK;
 }

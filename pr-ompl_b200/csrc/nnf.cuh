@@ -67,9 +67,12 @@ constexpr uint32_t NNF_HOP_MAX_V = 1u << 27;
 struct NnfLazyOut {
   uint32_t status, iters, n_evaluated, n_collisions, path_len, epoch, repaired_vertices, pad;
   double goal_cost, final_error;
+  unsigned long long cycles[5]; // SM cycles spent in: hop chase, per-hop pass, edge evaluation, bookkeeping, repair
 };
 enum : uint32_t { NNF_LAZY_RUNNING = 0, NNF_LAZY_SOLVED = 1, NNF_LAZY_NO_PATH = 2, NNF_LAZY_CONTINUE = 3,
-                  NNF_LAZY_NEED_REBUILD = 4, NNF_LAZY_ERROR = 5 };
+                  NNF_LAZY_NEED_REBUILD = 4, NNF_LAZY_ERROR = 5,
+                  NNF_LAZY_NEED_FLOW = 6 }; // the repair wave outgrew one block: the host re-sweeps from `epoch`'s
+                                            // level with the whole GPU (out.pad = that level) and relaunches
 struct NnfLazyDev {
   const uint32_t *succ_off, *succ_pos; // CSR of NN-graph successors by sorted position
   const uint32_t *level;               // level of a sorted position

@@ -294,3 +294,26 @@ def test_kd_index_degenerate_clouds(P, O):
         oi, od = O.knn(pts, q, 16, nthreads=8)
         assert np.array_equal(gi, oi) and np.array_equal(gd, od)
         tree.close()
+
+
+@pytest.mark.parametrize("nq", [1, 7, 300, 700, 1500, 3000, 5000])
+def test_kd_team_search_every_batch_size(P, O, nq):
+    """The team kernel gives a block's 8 warps 1, 2, 4 or 8 queries depending on the batch size, and idle warps take
+    subtrees over from busy ones; whatever the split, the answers are the brute-force answers (ties by index,
+    duplicates, clustered queries whose searches are unusually long)."""
+    rng = np.random.default_rng(100 + nq)
+    n = 1 << 18
+    pts = rng.uniform(-np.pi, np.pi, size=(n, 7))
+    pts[1000:3000] = pts[:2000]                                   # duplicates
+    pts[-20000:] = pts[-1] + 0.05 * rng.normal(size=(20000, 7))   # a dense blob: long searches for queries inside it
+    q = rng.uniform(-np.pi, np.pi, size=(nq, 7))
+    q[: max(1, nq // 5)] = pts[-1] + 0.05 * rng.normal(size=(max(1, nq // 5), 7))
+    tree = P.KnnIndex(7)
+    tree.add(pts)
+    tree.set_search_mode(3)
+    for k in (1, 16, 32):
+        gi, gd = tree.nearest_k(q, k)
+        oi, od = O.knn(pts, q, k, nthreads=8)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od), (nq, k)
+    assert tree.index_stats()["indexed_nodes"] == n
+    tree.close()
