@@ -316,6 +316,15 @@ int prgpu_knn_nearest_k_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const do
                                        uint32_t *idx_dev, double *dist_dev, void *stream);
 int prgpu_knn_nearest_k_sharded(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries, uint64_t nq, int k,
                                 uint32_t *idx, double *dist);
+/* The other partitioning (the tree fits one GPU and is held WHOLE by every rank; the QUERIES are split): this rank's
+ * nq_local queries are searched locally -- the k-d index makes that sub-linear -- and one all-gather hands every rank
+ * the answers of all ranks: idx_all / dist_all are [nranks][nq_local][k], rank-major.  Every rank passes the same
+ * nq_local.  Collective; asynchronous on `stream` unless the local search had to fall back (rare). */
+int prgpu_knn_nearest_k_query_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries_dev, uint64_t nq_local,
+                                             int k, uint32_t *idx_all_dev, double *dist_all_dev, void *stream);
+/* the same with host buffers (queries in, all ranks' answers out), synchronous */
+int prgpu_knn_nearest_k_query_sharded(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries, uint64_t nq_local, int k,
+                                      uint32_t *idx_all, double *dist_all);
 /* checkMotion over an edge batch replicated on every rank: rank r validates its slice, one all-gather of
  * 1 byte per edge; every rank receives all n verdicts.  Collective. */
 int prgpu_check_motion_batch_sharded_device(prgpu_world_t *w, prgpu_comm_t *c, const double *from_dev,

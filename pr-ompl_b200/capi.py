@@ -88,6 +88,8 @@ SIGNATURES = {
     "prgpu_comm_allgather": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, c_vp]),
     "prgpu_comm_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64)]),
     "prgpu_knn_nearest_k_sharded_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
+    "prgpu_knn_nearest_k_query_sharded_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
+    "prgpu_knn_nearest_k_query_sharded": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp]),
     "prgpu_knn_nearest_k_sharded": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp]),
     "prgpu_check_motion_batch_sharded_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_uint64, C.c_double, C.c_int,
                                                           C.c_int, c_vp, c_vp]),
@@ -256,6 +258,21 @@ class KnnIndex:
         """Collective: this handle holds one shard of the tree (set_index_base = first global index)."""
         _check(lib().prgpu_knn_nearest_k_sharded_device(self.h, comm.h, _ptr(q_dev), nq, k, _ptr(idx_dev),
                                                         _ptr(dist_dev), C.c_void_p(stream)))
+
+    def nearest_k_query_sharded_device(self, comm, q_dev, nq_local, k, idx_all_dev, dist_all_dev, stream=0):
+        """Collective: every rank holds the whole tree and searches its own nq_local queries; all ranks receive
+        all answers ([nranks][nq_local][k])."""
+        _check(lib().prgpu_knn_nearest_k_query_sharded_device(self.h, comm.h, _ptr(q_dev), nq_local, k,
+                                                              _ptr(idx_all_dev), _ptr(dist_all_dev), C.c_void_p(stream)))
+
+    def nearest_k_query_sharded(self, comm, queries, k):
+        queries = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)
+        nr = comm.nranks
+        idx = np.empty((nr, len(queries), k), dtype=np.uint32)
+        dist = np.empty((nr, len(queries), k), dtype=np.float64)
+        _check(lib().prgpu_knn_nearest_k_query_sharded(self.h, comm.h, _ptr(queries), len(queries), k, _ptr(idx),
+                                                       _ptr(dist)))
+        return idx, dist
 
     def nearest_k_sharded(self, comm, queries, k):
         queries = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)

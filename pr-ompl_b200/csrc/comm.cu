@@ -259,6 +259,66 @@ int prgpu_knn_nearest_k_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const do
   return step(true, c->flags_host[c->rank]);
 }
 
+int prgpu_knn_nearest_k_query_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries_dev, uint64_t nq_local,
+                                             int k, uint32_t *idx_all_dev, double *dist_all_dev, void *stream_) {
+  if (!h || !c || (nq_local && (!queries_dev || !idx_all_dev || !dist_all_dev)))
+    return fail(PRGPU_EINVAL, "knn_nearest_k_query_sharded: NULL argument");
+  if (c->device < 0 || c->device != h->device)
+    return fail(PRGPU_EINVAL, "knn_nearest_k_query_sharded: communicator and tree live on different devices");
+  if (k < 1 || k > PRGPU_MAX_K)
+    return fail(PRGPU_ELIMIT, "knn_nearest_k_query_sharded: k must be in [1,PRGPU_MAX_K]");
+  if (nq_local == 0)
+    return PRGPU_OK;
+  if (nq_local > 0x7FFFFFFFull)
+    return fail(PRGPU_ELIMIT, "knn_nearest_k_query_sharded: too many queries in one call");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t ent = (size_t)nq_local * k;
+  const size_t chunk = (ent * 12 + 15) / 16 * 16; // [dist f64 x ent | idx u32 x ent], 16-byte multiple
+  int rc;
+  if ((rc = c->send.reserve(chunk)) != PRGPU_OK || (rc = c->recv.reserve(chunk * c->nranks)) != PRGPU_OK)
+    return rc;
+  char *send = c->send.as<char>(), *recv = c->recv.as<char>();
+  // this rank's queries against the WHOLE tree it holds (index, filter or exact path: knn_dispatch decides)
+  if ((rc = knn_dispatch(h, queries_dev, (uint32_t)nq_local, k, nullptr, reinterpret_cast<uint32_t *>(send + ent * 8),
+                         reinterpret_cast<double *>(send), stream, nullptr)) != PRGPU_OK)
+    return rc;
+  if (c->nranks == 1) {
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(recv, send, chunk, cudaMemcpyDeviceToDevice, stream));
+  } else if ((rc = comm_allgather(c, send, recv, chunk, stream)) != PRGPU_OK)
+    return rc;
+  // records -> the two result tables, rank-major
+  PRGPU_CUDA_TRY(cudaMemcpy2DAsync(dist_all_dev, ent * 8, recv, chunk, ent * 8, c->nranks, cudaMemcpyDeviceToDevice, stream));
+  PRGPU_CUDA_TRY(cudaMemcpy2DAsync(idx_all_dev, ent * 4, recv + ent * 8, chunk, ent * 4, c->nranks,
+                                   cudaMemcpyDeviceToDevice, stream));
+  return PRGPU_OK;
+}
+
+int prgpu_knn_nearest_k_query_sharded(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries, uint64_t nq_local, int k,
+                                      uint32_t *idx_all, double *dist_all) {
+  if (!h || !c || (nq_local && (!queries || !idx_all)))
+    return fail(PRGPU_EINVAL, "knn_nearest_k_query_sharded: NULL argument");
+  if (nq_local == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  const size_t all = (size_t)nq_local * k * (size_t)c->nranks;
+  int rc;
+  if ((rc = h->d_q.reserve((size_t)nq_local * h->dim * sizeof(double))) != PRGPU_OK ||
+      (rc = h->d_idx.reserve(all * sizeof(uint32_t))) != PRGPU_OK || (rc = h->d_dist.reserve(all * sizeof(double))) != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(h->d_q.p, queries, (size_t)nq_local * h->dim * sizeof(double), cudaMemcpyHostToDevice,
+                                 h->stream));
+  rc = prgpu_knn_nearest_k_query_sharded_device(h, c, h->d_q.as<double>(), nq_local, k, h->d_idx.as<uint32_t>(),
+                                                h->d_dist.as<double>(), h->stream);
+  if (rc != PRGPU_OK)
+    return rc;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(idx_all, h->d_idx.p, all * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (dist_all)
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(dist_all, h->d_dist.p, all * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PRGPU_OK;
+}
+
 int prgpu_knn_nearest_k_sharded(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries, uint64_t nq, int k,
                                 uint32_t *idx, double *dist) {
   if (!h || !c || (nq && (!queries || !idx)))

@@ -533,7 +533,7 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
         my_i[j] = leaf_idx[(size_t)leaf * KD_LEAF + j * 32 + lane];
       }
       // ---- while the leaf loads are in flight: hand the bottom of the stack to an idle warp ----
-      if (sp >= 2 && *(volatile uint32_t *)&idle != 0) {
+      while (sp >= 2 && *(volatile uint32_t *)&idle != 0) { // (every idle warp gets one, while the stack lasts)
         int target = -1;
         if (lane == 0) {
           const uint32_t m = *(volatile uint32_t *)&idle;
@@ -558,6 +558,8 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
           stk_node = __shfl_down_sync(0xFFFFFFFFu, stk_node, 1);
           stk_rd = __shfl_down_sync(0xFFFFFFFFu, stk_rd, 1);
           --sp;
+        } else {
+          break; // another donor was faster
         }
       }
       uint32_t nx_node = 0;

@@ -7,7 +7,7 @@ tail -3 gpurun_out/${TAG}_bench${N}.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/${TAG}_bench${N}.json"))
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["extra"].get("sharded_c_abi"), d["extra"]["phase_breakdown"], d["extra"].get("query_sharded"))
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["extra"].get("query_sharded_c_abi"), d["extra"]["phase_breakdown"]); print(json.dumps(d["extra"].get("strong_scaling_one_batch"), indent=1)); print(json.dumps(d["extra"].get("configs4_lockstep_node_sharded_nn"), indent=1))
 for k in ("check_motion","rrtc"):
     b=d["extra"][k]; print(k, b.get("value"), b.get("e2e",{}).get("value"))
 PY

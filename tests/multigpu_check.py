@@ -57,6 +57,24 @@ def main():
             print(f"{name}: n={n} world={world} ok={ok} redo_steps={comm.redo_steps()} "
                   f"stats={tree.search_stats()}", flush=True)
         tree.close()
+    # the other partitioning: whole tree on every rank, queries split, every rank receives every answer
+    n, nq_local = 400_000, 300
+    pts = synth.cloud(30, n, dup_fraction=0.05)
+    tree = P.KnnIndex(7, device=local, capacity=n)
+    tree.add(pts)
+    q_all = synth.cloud(31, nq_local * world)
+    for mode in (0, 3):                           # auto, and the k-d index forced
+        tree.set_search_mode(mode)
+        for k in (1, 16):
+            hi, hd = tree.nearest_k_query_sharded(comm, q_all[rank * nq_local:(rank + 1) * nq_local], k)
+            oi, od = O.knn(pts, q_all, k, nthreads=8)
+            same = np.array_equal(hi.reshape(-1, k), oi) and np.array_equal(hd.reshape(-1, k), od)
+            if not same:
+                print(f"[rank {rank}] MISMATCH query-sharded mode={mode} k={k}", flush=True)
+            ok = ok and same
+    if rank == 0:
+        print(f"query-sharded: n={n} world={world} ok={ok} index={tree.index_stats()['indexed_nodes']}", flush=True)
+    tree.close()
     # edges: replicated batch, sliced validation, all-gather of the verdicts
     dh, link, xyzr = synth.default_arm()
     sph, box = synth.obstacles(3)
