@@ -80,6 +80,10 @@ int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64
  * synchronises the stream once per call (it reads the number of unproven queries).  force_exact != 0
  * disables the filter. */
 int prgpu_knn_set_search_mode(prgpu_knn_t *h, int force_exact);
+/* Builds the k-d index over the current nodes now (synchronous, ~4.4 ns per node).  Without this call the index
+ * is built automatically once the batched searches on an unchanged node set have cost as much extra as the build
+ * (see knn_dispatch in csrc/capi.cu); appends and clear() make it stale.  Results never depend on it. */
+int prgpu_knn_build_index(prgpu_knn_t *h);
 /* Sub-linear search.  Batched calls without `lo` (>= 16 queries, k <= 32) over >= 2^17 points are served by a
  * balanced k-d tree built on the device over the configuration buffer: same results bit for bit under the
  * (distance, index) order, ~1e-3 of the pairs.  The index is built at the second such call on an unchanged

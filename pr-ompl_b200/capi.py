@@ -51,6 +51,7 @@ SIGNATURES = {
     "prgpu_knn_nearest_k": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
     "prgpu_knn_nearest_k_device": (C.c_int, [c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "prgpu_knn_set_search_mode": (C.c_int, [c_vp, C.c_int]),
+    "prgpu_knn_build_index": (C.c_int, [c_vp]),
     "prgpu_knn_index_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float), c_u32p,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "prgpu_knn_search_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -189,6 +190,10 @@ class KnnIndex:
         n = C.c_uint64()
         _check(lib().prgpu_knn_size(self.h, C.byref(n)))
         return n.value
+
+    def build_index(self):
+        """k-d index over the current nodes, now (otherwise built once the brute-force searches have cost as much)."""
+        _check(lib().prgpu_knn_build_index(self.h))
 
     def diag_scan(self, queries, thresh, cap):
         """prgpu_diag_knn_scan: the production scan's D, the fp32 re-cut keys and the error bounds."""

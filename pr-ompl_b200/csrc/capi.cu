@@ -207,7 +207,7 @@ int prgpu_knn_clear(prgpu_knn_t *h) {
     return fail(PRGPU_EINVAL, "knn_clear: NULL handle");
   h->n = 0;
   h->kd_valid = false;
-  h->kd_pending = 0;
+  h->kd_regret_ms = 0.0;
   if (h->xmax2) {
     PRGPU_CUDA_TRY(cudaSetDevice(h->device));
     PRGPU_CUDA_TRY(cudaMemsetAsync(h->xmax2, 0, sizeof(double), h->stream));
@@ -264,7 +264,7 @@ int prgpu_knn_add_device(prgpu_knn_t *h, const double *pts_dev, uint64_t n, void
   h->n += n;
   if (n) {
     h->kd_valid = false;
-    h->kd_pending = 0;
+    h->kd_regret_ms = 0.0;
   }
   return PRGPU_OK;
 }
@@ -320,7 +320,7 @@ int prgpu_knn_add(prgpu_knn_t *h, const double *pts, uint64_t n) {
   }
   h->n += n;
   h->kd_valid = false;
-  h->kd_pending = 0;
+  h->kd_regret_ms = 0.0;
   PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PRGPU_OK;
 }
@@ -348,15 +348,32 @@ int prgpu_knn_get_points(prgpu_knn_t *h, uint64_t first, uint64_t n, double *pts
 } // extern "C"
 
 // Batched queries over a big, unchanged node set go through the k-d index (kdtree.cu): identical results,
-// ~1e-3 of the pairs.  The index is built at the SECOND eligible search on the same node set (a structure
-// that is refilled before every search never pays for a build); adds and clear() make it stale.
-// Measured on B200 (scripts/kdbench.py): an indexed search costs 0.3-0.8 ms whatever the batch (<= 4096
-// queries: one warp per query, latency-bound); the TF32 filter scan costs ~0.1 ms + n*nq / 1.05e10 ms, the
-// exact fp64 kernel (taken below 128 queries) ~ n*nq / 2.3e8 ms.
+// ~1e-3 of the pairs.  Building costs ~4.4 ns per node (44 ms for 1e7 nodes), so the index is built by the
+// "ski rental" rule: every eligible search that had to run without it adds its estimated extra cost to a regret
+// account, and the build happens when the account reaches the build cost (never more than twice the cost of the
+// best choice in hindsight; a structure that is refilled or appended to between searches never pays for a
+// build -- appends and clear() make the index stale and reset the account).  prgpu_knn_build_index() builds it
+// at once for callers that know the tree is final (a benchmark's set-up, a roadmap).
+// Measured on B200 (scripts/kdbench.py): an indexed search costs 0.2-0.6 ms for <= 4096 queries (latency-bound
+// team search); the TF32 filter scan ~0.1 ms + n*nq / 1.05e10 ms, the exact fp64 kernel (below 128 queries)
+// ~ n*nq / 2.3e8 ms.
 static const uint32_t KD_MIN_NODES = 1u << 17;
+static double brute_ms(uint64_t n, uint32_t nq) {
+  const double pairs = (double)n * nq;
+  return nq >= 128 ? 0.1 + pairs / 1.05e10 : pairs / 2.3e8;
+}
+static double indexed_ms(uint64_t n, uint32_t nq) { return 0.19 + nq * 7e-6 * std::max(1.0, std::log2((double)n / 1024.0)); }
 static bool kd_pays(uint64_t n, uint32_t nq) {
   const double pairs = (double)n * nq;
   return nq >= 128 ? pairs >= 4e9 : (nq >= 8 && pairs >= 1.5e8);
+}
+static int kd_build_now(prgpu_knn *h, cudaStream_t stream) {
+  // appends may still be in flight on the caller's stream(s)
+  PRGPU_CUDA_TRY(cudaDeviceSynchronize());
+  const int rc = kd_build(h->kd, h->dim, h->pts, h->stride, (uint32_t)h->n, stream);
+  if (rc == PRGPU_OK)
+    h->kd_valid = true;
+  return rc;
 }
 int knn_dispatch(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev, uint32_t *idx_dev,
                  double *dist_dev, cudaStream_t stream, bool *pending) {
@@ -365,14 +382,13 @@ int knn_dispatch(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, co
   const bool possible = !h->force_exact && !h->no_index && !lo_dev && k <= 32 && h->n >= 128;
   const bool eligible = possible && (h->force_index || (h->n >= KD_MIN_NODES && kd_pays(h->n, nq)));
   if (eligible) {
-    if (!h->kd_valid && (h->force_index || ++h->kd_pending >= 2)) {
-      // appends may still be in flight on the caller's stream(s)
-      PRGPU_CUDA_TRY(cudaDeviceSynchronize());
-      int rc = kd_build(h->kd, h->dim, h->pts, h->stride, (uint32_t)h->n, stream);
-      if (rc == PRGPU_OK)
-        h->kd_valid = true;
-      else if (rc != PRGPU_ENOMEM)
-        return rc; // out of memory: keep serving from the brute-force path
+    if (!h->kd_valid) {
+      h->kd_regret_ms += std::max(0.0, brute_ms(h->n, nq) - indexed_ms(h->n, nq));
+      if (h->force_index || h->kd_regret_ms >= 4.4e-6 * (double)h->n) {
+        const int rc = kd_build_now(h, stream);
+        if (rc != PRGPU_OK && rc != PRGPU_ENOMEM)
+          return rc; // out of memory: keep serving from the brute-force path
+      }
     }
     if (h->kd_valid) {
       ++h->kd_calls;
@@ -382,6 +398,20 @@ int knn_dispatch(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, co
   return knn_search_deferred(h->dim, h->view(), queries_dev, nq, k, lo_dev, idx_dev, dist_dev, h->scratch, h->sm_count,
                              stream, &h->timer, h->force_exact, pending);
 }
+
+extern "C" {
+
+int prgpu_knn_build_index(prgpu_knn_t *h) {
+  if (!h)
+    return fail(PRGPU_EINVAL, "knn_build_index: NULL handle");
+  if (h->kd_valid)
+    return PRGPU_OK;
+  if (h->n < 128 || h->dim > 8)
+    return fail(PRGPU_EINVAL, "knn_build_index: needs at least 128 nodes");
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  return kd_build_now(h, h->stream);
+}
+} // extern "C"
 
 extern "C" {
 

@@ -42,7 +42,8 @@ struct prgpu_knn {
   int force_index = 0;             // search mode 3: the k-d index whenever it can answer (tests)
   prgpu::KdIndex kd;               // sub-linear index over nodes [0, kd.n); stale when kd_valid is false
   bool kd_valid = false;
-  unsigned kd_pending = 0;         // eligible searches seen on the current node set without an index
+  double kd_regret_ms = 0.0;       // what the eligible searches on the current node set have cost beyond an indexed
+                                   // search so far (estimated); the index is built when this reaches its build cost
   unsigned long long kd_calls = 0;
   prgpu::KnnTreeView view() const {
     prgpu::KnnTreeView v;

@@ -5,7 +5,7 @@ P=prgpu_loader.load(); synth=P.synth
 dev=torch.device('cuda',0); stream=torch.cuda.current_stream().cuda_stream
 for N in (10_000_000, 1_250_000):
     pts=torch.from_numpy(synth.cloud(0,N)).to(dev)
-    tree=P.KnnIndex(7,capacity=N); tree.add_device(pts,N,stream)
+    tree=P.KnnIndex(7,capacity=N); tree.add_device(pts,N,stream); torch.cuda.synchronize(); tree.build_index()
     for Q,k in ((4096,16),(4096,1),(512,16),(64,16),(32768,16)):
         q=torch.from_numpy(synth.cloud(1,Q)).to(dev)
         i_=torch.empty((Q,k),dtype=torch.int32,device=dev); d_=torch.empty((Q,k),dtype=torch.float64,device=dev)

@@ -6,7 +6,7 @@ P = prgpu_loader.load(); synth = P.synth
 dev = torch.device('cuda', 0); stream = torch.cuda.current_stream().cuda_stream
 N, Q, k = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000, 4096, 16
 pts = torch.from_numpy(synth.cloud(0, N)).to(dev)
-tree = P.KnnIndex(7, capacity=N); tree.add_device(pts, N, stream)
+tree = P.KnnIndex(7, capacity=N); tree.add_device(pts, N, stream); torch.cuda.synchronize(); tree.build_index()
 q = torch.from_numpy(synth.cloud(1, Q)).to(dev)
 i_ = torch.empty((Q, k), dtype=torch.int32, device=dev); d_ = torch.empty((Q, k), dtype=torch.float64, device=dev)
 for _ in range(4):

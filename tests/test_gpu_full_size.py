@@ -8,8 +8,8 @@ pytestmark = pytest.mark.gpu
 
 
 def test_knn_sweep_full_size(P, O, synth):
-    """N=1e7, Q=4096, k=16 and k=1: the tensor-core filter path (mode 2) and the k-d index (mode 0, built at
-    the second batched search) equal the exact kernel (mode 1) on every query; a spread subset equals the CPU
+    """N=1e7, Q=4096, k=16 and k=1: the tensor-core filter path (mode 2) and the k-d index (mode 0 after
+    prgpu_knn_build_index) equal the exact kernel (mode 1) on every query; a spread subset equals the CPU
     oracle; rows are sorted; reported distances are the reference's distance of the reported nodes."""
     import torch
     n, nq = 10_000_000, 4096
@@ -27,7 +27,7 @@ def test_knn_sweep_full_size(P, O, synth):
         ei, ed = t.nearest_k(q, k)
         assert np.array_equal(fi, ei) and np.array_equal(fd, ed)
         t.set_search_mode(0)
-        t.nearest_k(q, k)
+        t.build_index()
         ii, id_ = t.nearest_k(q, k)
         ist = t.index_stats()
         assert ist["indexed_nodes"] == n and ist["index_calls"] >= 1

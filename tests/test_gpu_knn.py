@@ -317,3 +317,33 @@ def test_kd_team_search_every_batch_size(P, O, nq):
         assert np.array_equal(gi, oi) and np.array_equal(gd, od), (nq, k)
     assert tree.index_stats()["indexed_nodes"] == n
     tree.close()
+
+
+def test_kd_index_is_built_when_it_has_paid_for_itself(P, O, synth):
+    """Auto mode: the index is built once the brute-force searches on an unchanged node set have cost about as
+    much extra as the build (not at once: a structure that is refilled between searches must never pay for it);
+    an append resets the account; answers are the same before and after."""
+    n, nq, k = 4_000_000, 4096, 16
+    pts = synth.cloud(0, n)
+    q = synth.cloud(1, nq)
+    t = P.KnnIndex(7, capacity=n + 16)
+    t.add(pts)
+    first_i, first_d = t.nearest_k(q, k)
+    assert t.index_stats()["indexed_nodes"] == 0                # one search does not justify a build
+    built_at = None
+    for i in range(2, 60):
+        gi, gd = t.nearest_k(q, k)
+        assert np.array_equal(gi, first_i) and np.array_equal(gd, first_d)
+        if t.index_stats()["indexed_nodes"] and built_at is None:
+            built_at = i
+    assert built_at is not None and 4 <= built_at <= 40, built_at
+    t.add(synth.cloud(3, 1))                                    # stale: the account starts again
+    t.nearest_k(q, k)
+    t.nearest_k(q, k)
+    assert t.index_stats()["indexed_nodes"] == 0
+    t.build_index()                                             # the explicit call builds at once
+    assert t.index_stats()["indexed_nodes"] == n + 1
+    gi, gd = t.nearest_k(q[:300], k)
+    oi, od = O.knn(np.vstack([pts, synth.cloud(3, 1)]), q[:300], k, nthreads=8)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    t.close()
