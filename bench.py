@@ -604,14 +604,16 @@ def measure_knn(env, args, want_cpu):
 
     indexed = ist["indexed_nodes"] > 0
     if indexed:
-        summ = ncu_summary("kd_search_kernel")
-        roof = dict(hbm_block(kms), bound="hbm", kernel="kd_search_kernel", kernel_ms=kms,
+        summ = ncu_summary("kd_search_team_kernel")
+        roof = dict(hbm_block(kms), bound="hbm", kernel="kd_search_team_kernel", kernel_ms=kms,
                     traffic=None if not summ else summ.get("dram_bytes"),
                     issue_slots_busy_pct_ncu=None if not summ else summ.get("issue_slots_busy_pct"),
-                    binds="latency: one warp per query walks ~300 tree nodes and ~120 leaves of 64 nodes, a dependent "
-                          "chain; the algorithmic bytes are SURVEY §8(d)'s brute-force figure (the whole tree once), the "
-                          "search itself touches ~0.05 % of the tree per query but different leaves for different "
-                          "queries (ncu traffic above)",
+                    binds="latency: a query walks ~300 tree nodes and ~125 leaves of 64 slots, a dependent chain (the "
+                          "warps of a block take subtrees over from one another); the algorithmic bytes are SURVEY "
+                          "§8(d)'s brute-force figure (the whole tree once), the search touches ~0.08 % of the tree per "
+                          "query but different leaves for different queries: `traffic` (ncu, per launch) is 3.6x the "
+                          "algorithmic bytes and the kernel moves it at about half the HBM peak",
+                    traffic_gbs=None if not summ or not summ.get("dram_bytes") else summ["dram_bytes"] / (kms * 1e-3) / 1e9,
                     index={"build_ms": ist["build_ms"], "builds": ist["builds"],
                            "leaves_of_64_per_query": ist["leaves_visited"] / max(1, ist["index_calls"] * Q)})
     else:
@@ -825,13 +827,22 @@ def measure_check_motion(env, args, want_cpu):
                                                        n_local, 0.01, 0, 0, P.capi._ptr(e2e_valid)))
     e2e_s = env.timed_host(e2e_step)
     valid_fraction = float(valid.float().mean().item())
+    weak = None
+    if world > 1 and not args.no_extra:
+        # the same 1e6-edge batch on EVERY GPU (per-GPU work fixed): what splitting independent batches buys
+        aw, bw = torch.from_numpy(a_all).to(dev), torch.from_numpy(b_all).to(dev)
+        vw = torch.empty(E, dtype=torch.uint8, device=dev)
+        wms, _, _ = env.timed(lambda record=False: world_h.check_motion_batch_device(aw, bw, E, 0.01, vw, stream=stream),
+                              flush_l2=True)
+        weak = {"value": world * E / (wms * 1e-3), "unit": "edges/s", "ms_per_step": wms,
+                "note": f"weak scaling: {E} edges per GPU, {world * E} per step"}
+        del aw, bw, vw
     algo_bytes = n_local * (2 * 56 + 1)
-    kernels = ["cm_sample_kernel", "cm_resolve_kernel", "cm_phase_b_kernel"]
+    kernels = ["cm_sample2_kernel", "cm_lists_kernel<0>", "cm_certify_b_kernel", "cm_lists_kernel<1>"]
     issue = {kname: (ncu_summary(kname) or {}).get("issue_slots_busy_pct") for kname in kernels}
     lanes = {kname: (ncu_summary(kname) or {}).get("threads_per_inst") for kname in kernels}
     roof = {"bound": "hbm", "achieved": algo_bytes / (kms * 1e-3) / 1e9, "peak": env.hbm_peak, "unit": "GB/s",
-            "frac": algo_bytes / (kms * 1e-3) / 1e9 / env.hbm_peak, "traffic": ncu_traffic(kernels + [
-                "cm_gaps_kernel", "cm_expand_kernel"]),
+            "frac": algo_bytes / (kms * 1e-3) / 1e9 / env.hbm_peak, "traffic": ncu_traffic(kernels),
             "kernel": "+".join(kernels), "kernel_ms": kms, "peak_source": env.peak_src,
             "algorithmic_bytes_per_launch": algo_bytes,
             "binds": "issue / latency (fp32 FK chain + dependent L2 loads), not HBM: SURVEY §8(d) puts this kernel "
@@ -850,7 +861,7 @@ def measure_check_motion(env, args, want_cpu):
                    "valid_fraction": valid_fraction},
         "roofline": roof,
         "e2e": {"value": E / e2e_s, "unit": unit, "h2d_bytes_per_step": n_local * 112, "d2h_bytes_per_step": n_local},
-        "gpu_launches_per_step": launches, "clocks": clocks, "extra": {},
+        "gpu_launches_per_step": launches, "clocks": clocks, "extra": {} if weak is None else {"weak_scaling": weak},
     }
     if want_cpu:
         line["cpu_baseline"] = cpu_baseline(args, "check_motion", synth)
@@ -892,6 +903,17 @@ def measure_rrtc(env, args, want_cpu):
         rb.summary()
     e2e_s = env.timed_host(e2e_step)
     summ = rb.summary()
+    weak = None
+    if world > 1 and not args.no_extra:
+        # all 4096 queries on EVERY GPU (different sample streams per rank): the batch time is set by the queries
+        # that exhaust their budget, so planning more batches side by side is what more GPUs buy
+        sw, gw_ = torch.from_numpy(starts_all.copy()).to(dev), torch.from_numpy(goals_all.copy()).to(dev)
+        rbw = P.RrtcBatch(world_h, Bq, -np.pi, np.pi, extension_type="ext-con", seed=4 + 1000 * rank, query_id_base=0,
+                          max_iters=args.plan_iters, max_nodes=2048)
+        wms, _, _ = env.timed(lambda record=False: rbw.run_device(sw, gw_, stream), flush_l2=True)
+        weak = {"value": world * Bq / (wms * 1e-3), "unit": "plans/s", "ms_per_step": wms,
+                "note": f"weak scaling: {Bq} queries per GPU, {world * Bq} per step"}
+        rbw.close()
     nodes = int(summ["n_start"].sum() + summ["n_goal"].sum())
     algo_bytes = n_local * 112 + nodes * 60 + n_local * 16
     kernels = ["rrtc_batch_kernel", "rrtc_team_kernel"]
@@ -915,7 +937,7 @@ def measure_rrtc(env, args, want_cpu):
                    "mean_samples_per_plan": float(summ["iterations"].mean())},
         "roofline": roof,
         "e2e": {"value": Bq / e2e_s, "unit": unit, "h2d_bytes_per_step": n_local * 112, "d2h_bytes_per_step": n_local * 16},
-        "gpu_launches_per_step": launches, "clocks": clocks, "extra": {},
+        "gpu_launches_per_step": launches, "clocks": clocks, "extra": {} if weak is None else {"weak_scaling": weak},
     }
     rb.close()
     world_h.close()

@@ -364,7 +364,9 @@ __device__ __forceinline__ bool band_column(const NnfBandDev &g, uint32_t s, con
   for (uint32_t c0 = 0; c0 < m.band_w; c0 += 32) {
     const bool active = c0 + lane < m.band_w;
     const uint32_t r = m.band_lo + c0 + lane;
-    double f = 0.0;
+    double f = 0.0, old = 0.0;
+    if (COMPARE && active)
+      old = __ldcg(g.Bc + m.col_off + c0 + lane); // in flight under the gather (the repair wave is a latency chain)
     if (active) {
       if (g.ftab) {
         f = g.ftab[(size_t)s * g.R + r];
@@ -465,7 +467,7 @@ __device__ __forceinline__ bool band_column(const NnfBandDev &g, uint32_t s, con
     }
     if (active) {
       if (COMPARE)
-        changed |= __ldcg(g.Bc + m.col_off + c0 + lane) != x;
+        changed |= old != x;
       __stcg(g.Bc + m.col_off + c0 + lane, x);
       if (g.hop)
         __stcg(g.hop + m.col_off + c0 + lane, h);

@@ -9,5 +9,5 @@ import json
 d=json.load(open("gpurun_out/${TAG}_bench${N}.json"))
 print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["extra"].get("query_sharded_c_abi"), d["extra"]["phase_breakdown"]); print(json.dumps(d["extra"].get("strong_scaling_one_batch"), indent=1)); print(json.dumps(d["extra"].get("configs4_lockstep_node_sharded_nn"), indent=1))
 for k in ("check_motion","rrtc"):
-    b=d["extra"][k]; print(k, b.get("value"), b.get("e2e",{}).get("value"))
+    b=d["extra"][k]; print(k, b.get("value"), b.get("ms_per_step"), b.get("e2e",{}).get("value"), b.get("extra"))
 PY

@@ -5,7 +5,7 @@ import numpy as np, torch, prgpu_loader, bench
 P = prgpu_loader.load(); synth = P.synth
 dh, link, xyzr = synth.default_arm(); sph, box = synth.obstacles(3, n_spheres=16, n_boxes=16)
 gw = P.World(dh, link, xyzr, sph, box)
-ref, counts, ik = bench.nnf_problem(synth, dh, 200, 1024, 1)
+_, ref, counts, ik = bench.nnf_problem(synth, dh, 200, 1024, 1)
 g = P.Nnf(gw, ref, counts, ik, num_nn=5, discretization=1)
 r = g.solve(max_lazy_iters=int(sys.argv[1]))
 print("ok", r["lazy_iters"], g.last_dp_ms())
