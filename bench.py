@@ -966,12 +966,15 @@ def measure_nnf(env, args, want_cpu):
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
     # the first search sweeps the whole band (dirty level 0): the launch the roofline is quoted on
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
     t0 = time.perf_counter()
     r1 = g.solve(max_lazy_iters=1)
     first_search_ms = g.last_dp_ms()
     info = g.band_info()
     r = g.solve(max_lazy_iters=20000) if not r1["solved"] else r1
     solve_s = time.perf_counter() - t0
+    nnf_clocks = sampler.stop()
     launches = env.launches() - l0
     iters = int(r1["lazy_iters"] + (0 if r1["solved"] else r["lazy_iters"]))
     nE = g.n_edges
@@ -999,7 +1002,7 @@ def measure_nnf(env, args, want_cpu):
                              "only the levels at or after a knocked-out edge and are latency-bound on the level chain"},
         "e2e": {"value": 1.0 / (setup_s + solve_s), "unit": unit,
                 "h2d_bytes_per_step": int(ik.nbytes + ref.nbytes), "d2h_bytes_per_step": int(g.n_vertices * 19 * 8)},
-        "gpu_launches_per_step": launches, "clocks": None, "extra": {},
+        "gpu_launches_per_step": launches, "clocks": nnf_clocks, "extra": {},
     }
     ls = g.loop_stats()
     tot = float(sum(ls["phase_cycles"].values())) or 1.0
@@ -1007,6 +1010,7 @@ def measure_nnf(env, args, want_cpu):
         "kernel_launches": ls["launches"], "columns_repaired": ls["repaired_vertices"],
         "columns_repaired_per_iteration": ls["repaired_vertices"] / max(1, iters),
         "nn_vertices": g.n_vertices, "wide_waves_handed_to_full_sweep": ls["wide_waves_handed_to_full_sweep"],
+        "sm_clocks_during_solve": nnf_clocks,
         "phase_share_of_loop_kernel": {kname: c / tot for kname, c in ls["phase_cycles"].items()},
         "note": "the LazySP loop runs in one persistent kernel (hop chase -> per-hop pass -> evaluateEdge -> "
                 "bookkeeping -> local repair of the bottleneck table); the host reads one record per launch"}
@@ -1071,7 +1075,10 @@ def block(line):
     """A workload's line as a block of the headline line's `extra`."""
     keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "roofline", "e2e", "gpu_launches_per_step",
             "cpu_baseline")
-    return {k: line[k] for k in keep if k in line}
+    out = {k: line[k] for k in keep if k in line}
+    if line.get("extra"):
+        out["extra"] = line["extra"]
+    return out
 
 
 def run_ours(args, rank, local_rank, world):

@@ -363,9 +363,8 @@ static double brute_ms(uint64_t n, uint32_t nq) {
   return nq >= 128 ? 0.1 + pairs / 1.05e10 : pairs / 2.3e8;
 }
 static double indexed_ms(uint64_t n, uint32_t nq) { return 0.19 + nq * 7e-6 * std::max(1.0, std::log2((double)n / 1024.0)); }
-static bool kd_pays(uint64_t n, uint32_t nq) {
-  const double pairs = (double)n * nq;
-  return nq >= 128 ? pairs >= 4e9 : (nq >= 8 && pairs >= 1.5e8);
+static bool kd_pays(uint64_t n, uint32_t nq) { // the indexed search is expected to beat the brute-force one by > 10 %
+  return nq >= 8 && brute_ms(n, nq) > 1.1 * indexed_ms(n, nq);
 }
 static int kd_build_now(prgpu_knn *h, cudaStream_t stream) {
   // appends may still be in flight on the caller's stream(s)

@@ -60,7 +60,7 @@ struct prgpu_nnf {
   uint64_t knn_filter_calls = 0, knn_fallback_queries = 0;
   // device-resident LazySP loop (mode 0 with a device world): the per-edge LazySP state lives on the device
   // while that loop runs; the host mirrors (known / evaluated / blocked) are refreshed on demand
-  DevBuf d_succ_off, d_succ_pos, d_vop, d_stamp, d_worklist, d_known, d_evaluated, d_hop, d_path_pos, d_path_slot,
+  DevBuf d_succ_off, d_succ_pos, d_succ_pb, d_vop, d_stamp, d_worklist, d_known, d_evaluated, d_hop, d_path_pos, d_path_slot,
       d_path_cell, d_out_path, d_trace, d_lazy_out;
   bool host_state_current = true, dev_state_current = false;
   uint32_t lazy_epoch = 0;
@@ -206,7 +206,7 @@ int prgpu_nnf_destroy(prgpu_nnf_t *h) {
     return PRGPU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf *b : {&h->d_succ_off, &h->d_succ_pos, &h->d_vop, &h->d_stamp, &h->d_worklist, &h->d_known, &h->d_evaluated,
+  for (DevBuf *b : {&h->d_succ_off, &h->d_succ_pos, &h->d_succ_pb, &h->d_vop, &h->d_stamp, &h->d_worklist, &h->d_known, &h->d_evaluated,
                     &h->d_hop, &h->d_path_pos, &h->d_path_slot, &h->d_path_cell, &h->d_out_path, &h->d_trace,
                     &h->d_lazy_out})
     b->release();
@@ -533,7 +533,7 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
     NNF_TRY(h->d_pnn.reserve((size_t)V * 3 * 8));
     NNF_TRY(nnf_translations_launch(h->d_pose.as<double>(), h->d_vop.as<uint32_t>(), V, h->d_pnn.as<double>(), s));
     // successors by sorted position + the work arrays of the device-resident LazySP loop
-    std::vector<uint32_t> succ_off(V + 1, 0), succ_pos(E);
+    std::vector<uint32_t> succ_off(V + 1, 0), succ_pos(E), succ_pb(E);
     for (uint32_t o = 0; o < E; ++o)
       succ_off[pred_pos[o] + 1]++;
     for (uint32_t p = 0; p < V; ++p)
@@ -543,9 +543,12 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
       for (uint32_t p = 0; p < V; ++p)
         for (uint32_t o = pred_off_s[p]; o < pred_off_s[p + 1]; ++o)
           succ_pos[cur[pred_pos[o]]++] = p;
+      for (uint32_t e = 0; e < E; ++e)
+        succ_pb[e] = pred_off_s[succ_pos[e]];
     }
     NNF_TRY(upload(h->d_succ_off, succ_off, s));
     NNF_TRY(upload(h->d_succ_pos, succ_pos, s));
+    NNF_TRY(upload(h->d_succ_pb, succ_pb, s));
     NNF_TRY(h->d_stamp.reserve((size_t)V * 4));
     NNF_CUDA(cudaMemsetAsync(h->d_stamp.p, 0, (size_t)V * 4, s));
     NNF_TRY(h->d_worklist.reserve((size_t)V * 4));
@@ -804,6 +807,7 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
       NnfLazyDev z;
       z.succ_off = h->d_succ_off.as<uint32_t>();
       z.succ_pos = h->d_succ_pos.as<uint32_t>();
+      z.succ_pb = h->d_succ_pb.as<uint32_t>();
       z.level = h->g.level;
       z.vertex_of_pos = h->d_vop.as<uint32_t>();
       z.pred_eid = h->g.pred_eid;

@@ -377,6 +377,7 @@ __device__ __forceinline__ bool band_column(const NnfBandDev &g, uint32_t s, con
       }
     }
     double mm = NNF_INF;
+    uint32_t first_pp = 0; // lane j: sorted position of predecessor j (the first 32 of the list)
     uint32_t amin = 0xFFFFFFFFu, fle = 0xFFFFFFFFu; // (predecessor index in the list << 1) | (row r-1 ? 1 : 0)
     for (uint32_t e0 = m.pred_begin; e0 < m.pred_end; e0 += 32) {
       const uint32_t ne = min(32u, m.pred_end - e0);
@@ -384,8 +385,11 @@ __device__ __forceinline__ bool band_column(const NnfBandDev &g, uint32_t s, con
       mine.col_off = 0;
       mine.band_lo = 0;
       mine.band_w_blocked = 0x80000000u;
-      if (lane < ne)
+      if (lane < ne) {
         mine = g.edge[e0 + lane];
+        if (e0 == m.pred_begin)
+          first_pp = g.pred_pos[e0 + lane]; // for the hop word, fetched with the records instead of after the scan
+      }
       for (uint32_t j0 = 0; j0 < ne; j0 += 4) {
         double v[8];
 #pragma unroll
@@ -447,15 +451,21 @@ __device__ __forceinline__ bool band_column(const NnfBandDev &g, uint32_t s, con
       // the walk stays on the vertex: (r-1, s) explains the cell (inactive lanes inherit, they are never stored)
       const bool stays = !active || (!is_start && xprev != NNF_INF && xprev <= fmax(f, mm));
       unsigned long long own = NNF_HOP_NONE;
+      const bool need = active && !stays && !is_start && x != NNF_INF;
+      const uint32_t code = fle != 0xFFFFFFFFu ? fle : amin;
+      // the chosen predecessor's position: handed round from the lane that fetched it with the records
+      const uint32_t pj = need ? (code >> 1) : 0u;
+      uint32_t pp = __shfl_sync(0xffffffffu, first_pp, (int)(pj & 31u));
       if (active && !stays) {
         if (is_start) {
           own = NNF_HOP_START;
         } else if (x != NNF_INF) {
-          const uint32_t code = fle != 0xFFFFFFFFu ? fle : amin;
-          const uint32_t e = m.pred_begin + (code >> 1);
+          const uint32_t e = m.pred_begin + pj;
+          if (pj >= 32u)
+            pp = g.pred_pos[e];
           const NnfEdgeRec rec = g.edge[e];
           const unsigned long long cell = rec.col_off + (r - rec.band_lo) - (code & 1u);
-          own = (cell << 28) | ((unsigned long long)g.pred_pos[e] << 1) | (code & 1u);
+          own = (cell << 28) | ((unsigned long long)pp << 1) | (code & 1u);
         }
       }
       const unsigned nonstay = __ballot_sync(0xffffffffu, !stays) & ((2u << lane) - 1u);
@@ -533,7 +543,7 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
   uint32_t *wl_level = wl_pos + LAZY_WL_CAP;
   uint32_t *hset = wl_level + LAZY_WL_CAP;
   uint32_t *cur = hset + LAZY_HASH;
-  __shared__ uint32_t s_status, s_n, s_level, s_target, s_wl_n, s_cur_n, s_next, s_overflow;
+  __shared__ uint32_t s_status, s_n, s_level, s_target, s_wl_n, s_overflow, s_par, s_cur_n2[2], s_next2[2];
   __shared__ unsigned long long s_err_bits;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t NW = LAZY_THREADS / 32;
@@ -551,7 +561,7 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
     }
     return lo;
   };
-  auto push = [&](uint32_t pos) { // one thread: add a dirty vertex to the wave (once)
+  auto push = [&](uint32_t pos, uint32_t pb) { // one thread: add a dirty vertex to the wave (once)
     uint32_t hslot = (pos * 2654435761u) & (LAZY_HASH - 1u);
     while (true) {
       const uint32_t old = atomicCAS(hset + hslot, 0u, pos + 1u);
@@ -569,8 +579,13 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
     const uint32_t lv = level_of(pos);
     wl_pos[i] = pos;
     wl_level[i] = lv;
-    atomicMin(&s_next, lv);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.meta + pos)); // the warp that takes it starts with this record
+    atomicMin(&s_next2[s_par], lv);
+    // the warp that takes it starts with these: the vertex record, its first predecessor records, its position
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.meta + pos));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.edge + pb));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.edge + pb + 4));
+    if (g.pnn)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(g.pnn + 3 * (size_t)pos));
   };
   const int dof = z.dof;
   const uint32_t R = (uint32_t)g.R;
@@ -644,7 +659,7 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
       const NnfVertexMeta m = g.meta[sp];
       const unsigned long long cell = z.path_cell[i];
       const uint32_t r_hi = m.band_lo + (uint32_t)(cell - m.col_off);
-      const unsigned long long h = g.hop[cell];
+      const unsigned long long h = __ldcg(g.hop + cell); // (written with st.cg by the repair wave)
       uint32_t r_lo = 0;
       if (h != NNF_HOP_START) {
         const uint32_t pp = (uint32_t)(h >> 1) & (NNF_HOP_MAX_V - 1u);
@@ -733,7 +748,10 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
         ++epoch;
         s_wl_n = 0;
         s_overflow = 0;
-        s_next = LAZY_DONE;
+        s_par = 1; // the first push (the knocked-out edge's target) reports its level through pair 1 ...
+        s_cur_n2[0] = 0;
+        s_next2[0] = LAZY_DONE; // ... and the level loop starts on a fresh pair 0
+        s_next2[1] = LAZY_DONE;
       }
       lap(3);
     }
@@ -747,47 +765,55 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
       hset[i] = 0;
     __syncthreads();
     if (tid == 0)
-      push(s_target);
+      push(s_target, g.meta[s_target].pred_begin);
     __syncthreads();
-    uint32_t L = s_next, wave = 0;
+    auto process = [&](uint32_t sp) { // one warp: recompute a dirty vertex; a changed column dirties its successors
+      const NnfVertexMeta m = g.meta[sp];
+      const uint32_t so0 = z.succ_off[sp], so1 = z.succ_off[sp + 1]; // in flight while the column is computed
+      const uint32_t first_succ = so0 + lane < so1 ? z.succ_pos[so0 + lane] : 0u;
+      const uint32_t first_pb = so0 + lane < so1 ? z.succ_pb[so0 + lane] : 0u;
+      if (m.band_w != 0 && band_column<true>(g, sp, m, lane))
+        for (uint32_t e = so0 + lane; e < so1; e += 32) {
+          if (e == so0 + lane)
+            push(first_succ, first_pb);
+          else
+            push(z.succ_pos[e], z.succ_pb[e]);
+        }
+    };
+    // block-wide, level by level; two barriers per level (the per-level counters are double-buffered: the other
+    // parity's pair is reset while this level is processed).  One warp carrying a thin wave alone (no barriers at
+    // all) was tried and is slower (0.85 vs 0.59 ms per iteration): a column is a ~3 us dependent chain and the
+    // waves average 1.5 vertices per level, which the block overlaps.
+    uint32_t L = s_next2[1], wave = 0, par = 0;
     bool bailed = false;
     while (L != LAZY_DONE) {
-      __syncthreads(); // everybody has read L
-      // the entries of level L -> cur[]; the smallest later level -> s_next
-      if (tid == 0) {
-        s_cur_n = 0;
-        s_next = LAZY_DONE;
-      }
-      __syncthreads();
+      // the entries of level L -> cur[]; the smallest later level -> s_next2[par] (pushes below add to it)
       const uint32_t nwl = min(s_wl_n, LAZY_WL_CAP);
       for (uint32_t i = tid; i < nwl; i += LAZY_THREADS) {
         const uint32_t lv = wl_level[i];
         if (lv == L) {
-          const uint32_t j = atomicAdd(&s_cur_n, 1u);
+          const uint32_t j = atomicAdd(&s_cur_n2[par], 1u);
           if (j < LAZY_WAVE_BUDGET)
             cur[j] = wl_pos[i];
           wl_level[i] = LAZY_DONE;
         } else if (lv != LAZY_DONE) {
-          atomicMin(&s_next, lv);
+          atomicMin(&s_next2[par], lv);
         }
       }
       __syncthreads();
-      const uint32_t cnt = s_cur_n;
+      const uint32_t cnt = s_cur_n2[par];
+      if (tid == 0) { // the next level's pair
+        s_cur_n2[par ^ 1u] = 0;
+        s_next2[par ^ 1u] = LAZY_DONE;
+      }
+      s_par = par; // (every thread writes the same value; push() reads it)
       wave += cnt;
       if (wave > LAZY_WAVE_BUDGET || s_overflow) { // everything before level L is consistent; the host re-sweeps
         bailed = true;                             // levels >= L with the whole GPU
         break;
       }
-      for (uint32_t i = warp; i < cnt; i += NW) {
-        const uint32_t sp = cur[i];
-        const NnfVertexMeta m = g.meta[sp];
-        const uint32_t so0 = z.succ_off[sp], so1 = z.succ_off[sp + 1]; // in flight while the column is computed
-        uint32_t first_succ = so0 + lane < so1 ? z.succ_pos[so0 + lane] : 0u;
-        if (m.band_w != 0 && band_column<true>(g, sp, m, lane))
-          for (uint32_t e = so0 + lane; e < so1; e += 32) {
-            push(e == so0 + lane ? first_succ : z.succ_pos[e]);
-          }
-      }
+      for (uint32_t i = warp; i < cnt; i += NW)
+        process(cur[i]);
       __syncthreads();
       if (tid == 0)
         repaired += cnt;
@@ -796,7 +822,8 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
         ++L;
         break;
       }
-      L = s_next;
+      L = s_next2[par];
+      par ^= 1u;
     }
     if (tid == 0)
       lap(4);

@@ -75,6 +75,7 @@ enum : uint32_t { NNF_LAZY_RUNNING = 0, NNF_LAZY_SOLVED = 1, NNF_LAZY_NO_PATH = 
                                             // level with the whole GPU (out.pad = that level) and relaunches
 struct NnfLazyDev {
   const uint32_t *succ_off, *succ_pos; // CSR of NN-graph successors by sorted position
+  const uint32_t *succ_pb;             // per successor entry: first predecessor record of that successor (prefetch)
   const uint32_t *level;               // level of a sorted position
   const uint32_t *vertex_of_pos;
   const uint32_t *pred_eid;            // CSR slot -> NN edge id
