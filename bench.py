@@ -489,7 +489,10 @@ def measure_knn(env, args, want_cpu):
     dd = torch.empty((Q, k), dtype=torch.float64, device=dev)
     bufs = dict(idx=idx, dist=dd)
     comm = env.comm()
+    fused = False
     if world > 1:
+        # fused search + exchange: the search kernel writes result rows into every rank's window over NVLink
+        fused = comm.enable_peer_windows(12 * k * Q * world) and os.environ.get("PRGPU_BENCH_NO_FUSED") != "1"
         gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
         gd = torch.empty((world, Q, k), dtype=torch.float64, device=dev)
     tree.set_profiling(True)
@@ -537,7 +540,8 @@ def measure_knn(env, args, want_cpu):
         ci, cd = gi.clone(), gd.clone()
         local_search(q_dev, Q, k, idx, dd)
         torch.cuda.synchronize()
-        cross = {"own_slice_equals_local_search": bool(torch.equal(ci[rank], idx)) and bool(torch.equal(cd[rank], dd))}
+        cross = {"own_slice_equals_local_search": bool(torch.equal(ci[rank], idx)) and bool(torch.equal(cd[rank], dd)),
+                 "fused_steps": comm.fused_steps(), "exchange": "peer windows (fused)" if fused else "ncclAllGather"}
     # per-phase breakdown (untimed extra steps, events between the phases): what does not shrink with the shard
     for _ in range(5):
         traced_step()
@@ -775,8 +779,11 @@ def measure_knn(env, args, want_cpu):
             "workload": workload_string(args, "knn"),
             "parallelism": "single GPU" if world == 1 else f"{world} GPUs, each holding the whole tree and its own batch "
                            f"of {Q} queries ({world * Q} queries per step in total); one C-ABI call per step "
-                           f"(prgpu_knn_nearest_k_query_sharded_device): local indexed search + ONE NCCL all-gather of "
-                           f"the packed (distance, index) records, every rank ends with every answer",
+                           f"(prgpu_knn_nearest_k_query_sharded_device): " + (
+                               "the index search kernel writes every result row straight into every rank's window (NVLink "
+                               "peer stores from the kernel's epilogue) + one flag-exchange kernel: no collective call"
+                               if fused else "local indexed search + ONE NCCL all-gather of the packed (distance, index) "
+                               "records") + "; every rank ends with every answer",
             "l2": f"inputs larger than L2 ({n_local * 56 / 1e6:.0f} MB tree shard per GPU, fp64 SoA)",
             "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks; the tree is the "
                           "NearestNeighbors structure's state (as in the CPU reference arm), pinned host queries in / "

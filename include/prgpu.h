@@ -312,6 +312,16 @@ int prgpu_comm_size(const prgpu_comm_t *c);
 int prgpu_comm_allgather(prgpu_comm_t *c, const void *send, void *recv, uint64_t bytes_per_rank, void *stream);
 /* sharded steps that had to be repeated because some shard left queries unproven (see below) */
 int prgpu_comm_stats(const prgpu_comm_t *c, uint64_t *redo_steps);
+/* Symmetric windows for the FUSED search + exchange: every rank allocates a window of 2 x bytes (+ flags), the
+ * CUDA IPC handles travel over the communicator's own all-gather, and every rank maps every window (NVLink peer
+ * memory).  With windows enabled, prgpu_knn_nearest_k_query_sharded_device lets the index search kernel write
+ * each result row straight into every rank's window from its epilogue and exchanges arrival flags with one tiny
+ * kernel: no collective call, no staging copy.  Collective.  Returns PRGPU_ENODEV (on every rank) when peer
+ * memory cannot be mapped between these ranks: the all-gather path then stays in use.  bytes >= 12 * k * nq_local *
+ * nranks of the largest step. */
+int prgpu_comm_enable_peer_windows(prgpu_comm_t *c, uint64_t bytes);
+/* steps that took the fused form so far */
+int prgpu_comm_stats2(const prgpu_comm_t *c, uint64_t *fused_steps);
 /* nearestK over a tree whose nodes are sharded over the ranks (each rank's handle holds its shard, with
  * prgpu_knn_set_index_base = the shard's first global index; queries replicated): local search, ONE
  * all-gather of the per-shard (distance, index) records, ordered merge.  Every rank receives the global

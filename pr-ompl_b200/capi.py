@@ -87,6 +87,8 @@ SIGNATURES = {
     "prgpu_comm_rank": (C.c_int, [c_vp]),
     "prgpu_comm_size": (C.c_int, [c_vp]),
     "prgpu_comm_allgather": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, c_vp]),
+    "prgpu_comm_enable_peer_windows": (C.c_int, [c_vp, C.c_uint64]),
+    "prgpu_comm_stats2": (C.c_int, [c_vp, C.POINTER(C.c_uint64)]),
     "prgpu_comm_stats": (C.c_int, [c_vp, C.POINTER(C.c_uint64)]),
     "prgpu_knn_nearest_k_sharded_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
     "prgpu_knn_nearest_k_query_sharded_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
@@ -318,6 +320,15 @@ class Comm:
 
     def allgather(self, send, recv, bytes_per_rank, stream=0):
         _check(lib().prgpu_comm_allgather(self.h, _ptr(send), _ptr(recv), bytes_per_rank, C.c_void_p(stream)))
+
+    def enable_peer_windows(self, nbytes):
+        """Collective.  True if every rank mapped every window (the fused search + exchange is then used)."""
+        return lib().prgpu_comm_enable_peer_windows(self.h, int(nbytes)) == 0
+
+    def fused_steps(self):
+        v = C.c_uint64()
+        _check(lib().prgpu_comm_stats2(self.h, C.byref(v)))
+        return v.value
 
     def redo_steps(self):
         v = C.c_uint64()

@@ -374,6 +374,15 @@ static int kd_build_now(prgpu_knn *h, cudaStream_t stream) {
     h->kd_valid = true;
   return rc;
 }
+bool knn_index_ready(const prgpu_knn *h, uint32_t nq, int k) {
+  return h->kd_valid && !h->force_exact && !h->no_index && k <= 32 &&
+         (h->force_index || (h->n >= KD_MIN_NODES && kd_pays(h->n, nq)));
+}
+int knn_index_search(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, cudaStream_t stream,
+                     const prgpu::KdPeerOut *peers) {
+  ++h->kd_calls;
+  return kd_search(h->kd, h->index_base, queries_dev, nq, k, nullptr, nullptr, stream, &h->timer, peers);
+}
 int knn_dispatch(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev, uint32_t *idx_dev,
                  double *dist_dev, cudaStream_t stream, bool *pending) {
   if (pending)

@@ -78,6 +78,11 @@ struct prgpu_world {
 };
 
 
+// the k-d index as seen by the fused multi-GPU step (comm.cu): is it built and the right tool for this batch;
+// search with the result rows written into the peers' windows
+bool knn_index_ready(const prgpu_knn *h, uint32_t nq, int k);
+int knn_index_search(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, cudaStream_t stream,
+                     const prgpu::KdPeerOut *peers);
 // search dispatch shared by the single-GPU and the sharded entry points (capi.cu)
 int knn_dispatch(prgpu_knn *h, const double *queries_dev, uint32_t nq, int k, const uint32_t *lo_dev, uint32_t *idx_dev,
                  double *dist_dev, cudaStream_t stream, bool *pending);

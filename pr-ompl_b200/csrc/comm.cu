@@ -76,7 +76,33 @@ struct prgpu_comm {
   DevBuf send, recv;
   uint32_t *flags_host = nullptr; // pinned, nranks words
   uint64_t redo_steps = 0;
+  // symmetric windows (prgpu_comm_enable_peer_windows): every rank's window mapped into this process over
+  // CUDA IPC; two halves used alternately + one page of arrival flags
+  char *win = nullptr;                  // this rank's window
+  char *peer_win[KD_MAX_PEERS] = {};    // all ranks' windows as seen from here (own entry = win)
+  uint64_t win_half = 0;                // bytes per half
+  uint32_t win_epoch = 0;
+  uint64_t fused_steps = 0;
 };
+
+namespace {
+constexpr uint64_t WIN_FLAGS_BYTES = 4096;
+// arrival flags: rank r's word `me` of the half's flag row is set to `epoch` by rank `me` when its rows are in
+// r's window; then every rank waits for all words of its own row
+__global__ void comm_signal_wait_kernel(KdPeerOut po, unsigned long long flags_off, uint32_t epoch) {
+  const int r = threadIdx.x;
+  __threadfence_system();
+  if (r < po.nranks) {
+    volatile uint32_t *theirs = reinterpret_cast<volatile uint32_t *>(po.base[r] + flags_off);
+    theirs[po.rank] = epoch;
+    __threadfence_system();
+    volatile uint32_t *mine = reinterpret_cast<volatile uint32_t *>(po.base[po.rank] + flags_off);
+    while (mine[r] != epoch)
+      __nanosleep(100);
+  }
+  __threadfence_system();
+}
+} // namespace
 
 static int comm_allgather(prgpu_comm *c, const void *send, void *recv, uint64_t bytes, cudaStream_t stream) {
   if (c->custom) {
@@ -169,6 +195,11 @@ int prgpu_comm_destroy(prgpu_comm_t *c) {
     c->recv.release();
     if (c->flags_host)
       cudaFreeHost(c->flags_host);
+    for (int r = 0; r < c->nranks && r < KD_MAX_PEERS; ++r)
+      if (c->peer_win[r] && r != c->rank)
+        cudaIpcCloseMemHandle(c->peer_win[r]);
+    if (c->win)
+      cudaFree(c->win);
   }
   if (c->nccl)
     g_nccl.CommDestroy(c->nccl);
@@ -259,6 +290,89 @@ int prgpu_knn_nearest_k_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const do
   return step(true, c->flags_host[c->rank]);
 }
 
+int prgpu_comm_enable_peer_windows(prgpu_comm_t *c, uint64_t bytes) {
+  if (!c || bytes == 0)
+    return fail(PRGPU_EINVAL, "comm_enable_peer_windows: NULL / empty");
+  if (c->device < 0 || c->custom || c->nranks > KD_MAX_PEERS)
+    return fail(PRGPU_EINVAL, "comm_enable_peer_windows: needs an NCCL communicator on a device (<= 16 ranks)");
+  if (c->win)
+    return bytes <= c->win_half ? PRGPU_OK : fail(PRGPU_EINVAL, "comm_enable_peer_windows: already enabled, smaller");
+  PRGPU_CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t half = (bytes + 4095) / 4096 * 4096;
+  char *win = nullptr;
+  PRGPU_CUDA_TRY(cudaMalloc(&win, 2 * half + 2 * WIN_FLAGS_BYTES));
+  PRGPU_CUDA_TRY(cudaMemset(win, 0, 2 * half + 2 * WIN_FLAGS_BYTES));
+  // exchange the IPC handles through the communicator's own all-gather
+  cudaIpcMemHandle_t mine;
+  cudaError_t e = cudaIpcGetMemHandle(&mine, win);
+  int rc = e == cudaSuccess ? PRGPU_OK : fail(PRGPU_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  const size_t hb = 64;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle size");
+  std::vector<char> all(hb * c->nranks, 0);
+  if (rc == PRGPU_OK && ((rc = c->send.reserve(hb)) != PRGPU_OK || (rc = c->recv.reserve(hb * c->nranks)) != PRGPU_OK)) {
+  }
+  if (rc == PRGPU_OK) {
+    char tmp[64] = {0};
+    std::memcpy(tmp, &mine, sizeof(mine));
+    cudaMemcpy(c->send.p, tmp, hb, cudaMemcpyHostToDevice);
+    rc = comm_allgather(c, c->send.p, c->recv.p, hb, nullptr);
+    if (rc == PRGPU_OK && cudaDeviceSynchronize() != cudaSuccess)
+      rc = fail(PRGPU_ECUDA, "comm_enable_peer_windows: handle exchange failed");
+    if (rc == PRGPU_OK)
+      cudaMemcpy(all.data(), c->recv.p, hb * c->nranks, cudaMemcpyDeviceToHost);
+  }
+  // every rank must learn whether EVERY rank could map every window (else nobody uses them): count successes
+  int ok = rc == PRGPU_OK ? 1 : 0;
+  for (int r = 0; ok && r < c->nranks; ++r) {
+    if (r == c->rank) {
+      c->peer_win[r] = win;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, all.data() + hb * r, sizeof(hd));
+    void *p = nullptr;
+    e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      fail(PRGPU_ECUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      break;
+    }
+    c->peer_win[r] = static_cast<char *>(p);
+  }
+  char okb[64] = {0};
+  okb[0] = (char)ok;
+  std::vector<char> oks(hb * c->nranks, 0);
+  cudaMemcpy(c->send.p, okb, hb, cudaMemcpyHostToDevice);
+  if (comm_allgather(c, c->send.p, c->recv.p, hb, nullptr) == PRGPU_OK && cudaDeviceSynchronize() == cudaSuccess)
+    cudaMemcpy(oks.data(), c->recv.p, hb * c->nranks, cudaMemcpyDeviceToHost);
+  else
+    ok = 0;
+  for (int r = 0; r < c->nranks; ++r)
+    ok = ok && oks[hb * r] != 0;
+  if (!ok) {
+    for (int r = 0; r < c->nranks; ++r) {
+      if (c->peer_win[r] && r != c->rank)
+        cudaIpcCloseMemHandle(c->peer_win[r]);
+      c->peer_win[r] = nullptr;
+    }
+    cudaFree(win);
+    return fail(PRGPU_ENODEV, "comm_enable_peer_windows: peer memory is not available between these ranks "
+                              "(the all-gather path stays in use)");
+  }
+  c->win = win;
+  c->win_half = half;
+  return PRGPU_OK;
+}
+
+int prgpu_comm_stats2(const prgpu_comm_t *c, uint64_t *fused_steps) {
+  if (!c)
+    return fail(PRGPU_EINVAL, "comm_stats2: NULL handle");
+  if (fused_steps)
+    *fused_steps = c->fused_steps;
+  return PRGPU_OK;
+}
+
 int prgpu_knn_nearest_k_query_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const double *queries_dev, uint64_t nq_local,
                                              int k, uint32_t *idx_all_dev, double *dist_all_dev, void *stream_) {
   if (!h || !c || (nq_local && (!queries_dev || !idx_all_dev || !dist_all_dev)))
@@ -274,8 +388,35 @@ int prgpu_knn_nearest_k_query_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, co
   PRGPU_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t ent = (size_t)nq_local * k;
-  const size_t chunk = (ent * 12 + 15) / 16 * 16; // [dist f64 x ent | idx u32 x ent], 16-byte multiple
   int rc;
+  // ---- fused form: the index search writes every result row straight into every rank's window (NVLink peer
+  //      stores from the search kernel's epilogue); then one tiny kernel exchanges arrival flags; no collective
+  //      call and no staging copy on the path.  Taken when the windows are mapped and the index answers.
+  if (c->win && c->nranks > 1 && knn_index_ready(h, (uint32_t)nq_local, k) &&
+      (uint64_t)ent * 12 * c->nranks <= c->win_half) {
+    const uint32_t epoch = ++c->win_epoch;
+    const uint64_t half_off = (epoch & 1u) * c->win_half;
+    KdPeerOut po;
+    std::memset(&po, 0, sizeof(po));
+    for (int r = 0; r < c->nranks; ++r)
+      po.base[r] = c->peer_win[r] + half_off;
+    po.idx_off = (unsigned long long)ent * 8 * c->nranks;
+    po.nranks = c->nranks;
+    po.rank = c->rank;
+    if ((rc = knn_index_search(h, queries_dev, (uint32_t)nq_local, k, stream, &po)) != PRGPU_OK)
+      return rc;
+    KdPeerOut pf = po; // the flag rows sit behind the two halves
+    for (int r = 0; r < c->nranks; ++r)
+      pf.base[r] = c->peer_win[r];
+    comm_signal_wait_kernel<<<1, 32, 0, stream>>>(pf, 2 * c->win_half + (epoch & 1u) * WIN_FLAGS_BYTES, epoch); PRGPU_COUNT_LAUNCH(1);
+    PRGPU_CUDA_TRY(cudaGetLastError());
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(dist_all_dev, c->win + half_off, ent * 8 * c->nranks, cudaMemcpyDeviceToDevice, stream));
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(idx_all_dev, c->win + half_off + po.idx_off, ent * 4 * c->nranks,
+                                   cudaMemcpyDeviceToDevice, stream));
+    ++c->fused_steps;
+    return PRGPU_OK;
+  }
+  const size_t chunk = (ent * 12 + 15) / 16 * 16; // [dist f64 x ent | idx u32 x ent], 16-byte multiple
   if ((rc = c->send.reserve(chunk)) != PRGPU_OK || (rc = c->recv.reserve(chunk * c->nranks)) != PRGPU_OK)
     return rc;
   char *send = c->send.as<char>(), *recv = c->recv.as<char>();

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include "kdtree.cuh"
 
 namespace prgpu {
@@ -398,7 +399,7 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
                       const uint32_t *__restrict__ leaf_idx, const float *__restrict__ root_cell, int levels,
                       uint32_t index_base, const double *__restrict__ queries, uint32_t nq, int k, int qpb,
                       uint32_t *__restrict__ idx_out, double *__restrict__ dist_out,
-                      unsigned long long *__restrict__ visited) {
+                      unsigned long long *__restrict__ visited, const KdPeerOut po) {
   __shared__ KdSlot slots[KD_WARPS];
   __shared__ KdMail mail[KD_WARPS];
   __shared__ uint32_t idle; // bit w: warp w waits for work
@@ -678,9 +679,18 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
       left = __shfl_sync(0xFFFFFFFFu, left, 0);
       if (left == 0 && lane < k) { // the query's last worker writes the result
         const uint32_t q = sl.qid;
-        idx_out[(size_t)q * k + lane] = mi == PRGPU_INVALID_INDEX ? mi : mi + index_base;
-        if (dist_out)
-          dist_out[(size_t)q * k + lane] = md;
+        const uint32_t gi = mi == PRGPU_INVALID_INDEX ? mi : mi + index_base;
+        if (po.nranks > 0) { // fused exchange: the row goes into every rank's window (NVLink stores)
+          const size_t row = ((size_t)po.rank * nq + q) * k + lane;
+          for (int r = 0; r < po.nranks; ++r) {
+            reinterpret_cast<double *>(po.base[r])[row] = md;
+            reinterpret_cast<uint32_t *>(po.base[r] + po.idx_off)[row] = gi;
+          }
+        } else {
+          idx_out[(size_t)q * k + lane] = gi;
+          if (dist_out)
+            dist_out[(size_t)q * k + lane] = md;
+        }
       }
     }
     __threadfence_block();
@@ -792,12 +802,18 @@ int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint3
 }
 
 int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev, uint32_t nq, int k, uint32_t *idx_dev,
-              double *dist_dev, cudaStream_t stream, KernelTimer *timer) {
+              double *dist_dev, cudaStream_t stream, KernelTimer *timer, const KdPeerOut *peers) {
+  KdPeerOut po;
+  std::memset(&po, 0, sizeof(po));
+  if (peers)
+    po = *peers;
   if (k < 1 || k > 32)
     return fail(PRGPU_ELIMIT, "kd_search: k must be in [1,32]");
   if (nq == 0)
     return PRGPU_OK;
   static const int team_env = getenv("PRGPU_KD_TEAM") ? atoi(getenv("PRGPU_KD_TEAM")) : -1;
+  if (peers && (team_env == 0 || KD_WARPS < 2))
+    return fail(PRGPU_EINVAL, "kd_search: the fused exchange needs the team kernel");
   if (team_env != 0 && KD_WARPS >= 2) {
     // queries per block: all KD_WARPS warps own a query when the batch alone fills the machine; smaller batches
     // get several warps per query from the start (PRGPU_KD_TEAM = queries per block, 0 = the single-warp kernel)
@@ -815,7 +831,7 @@ int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev,
     kd_search_team_kernel<D><<<tblocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell, \
                                                                    kd.levels, index_base, queries_dev, nq, k, qpb,     \
                                                                    idx_dev, dist_dev,                                  \
-                                                                   kd.count_visits ? kd.visited : nullptr);            \
+                                                                   kd.count_visits ? kd.visited : nullptr, po);        \
     break;
       KD_CASE(1)
       KD_CASE(2)

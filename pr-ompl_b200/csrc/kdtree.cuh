@@ -23,9 +23,18 @@ struct KdIndex {
   unsigned builds = 0;
   void release();
 };
+// Fused search + exchange (multi-GPU, queries sharded): instead of idx_dev / dist_dev the team kernel's last
+// worker of a query writes the result row straight into EVERY rank's window -- peer memory mapped over
+// NVLink -- at row (rank * nq + q): no collective call, the transfer rides on the search.
+constexpr int KD_MAX_PEERS = 16;
+struct KdPeerOut {
+  char *base[KD_MAX_PEERS];   // every rank's window (this process's mapping), dist table at 0
+  unsigned long long idx_off; // byte offset of the index table inside a window
+  int nranks, rank;
+};
 // builds the index over nodes [0, n) of the fp64 SoA buffer; synchronises `stream`
 int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint32_t n, cudaStream_t stream);
 // exact k nearest of every query under (sqrt-distance, index); idx = local index + index_base
 int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev, uint32_t nq, int k, uint32_t *idx_dev,
-              double *dist_dev, cudaStream_t stream, KernelTimer *timer);
+              double *dist_dev, cudaStream_t stream, KernelTimer *timer, const KdPeerOut *peers = nullptr);
 } // namespace prgpu

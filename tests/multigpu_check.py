@@ -63,17 +63,24 @@ def main():
     tree = P.KnnIndex(7, device=local, capacity=n)
     tree.add(pts)
     q_all = synth.cloud(31, nq_local * world)
-    for mode in (0, 3):                           # auto, and the k-d index forced
-        tree.set_search_mode(mode)
-        for k in (1, 16):
-            hi, hd = tree.nearest_k_query_sharded(comm, q_all[rank * nq_local:(rank + 1) * nq_local], k)
-            oi, od = O.knn(pts, q_all, k, nthreads=8)
-            same = np.array_equal(hi.reshape(-1, k), oi) and np.array_equal(hd.reshape(-1, k), od)
-            if not same:
-                print(f"[rank {rank}] MISMATCH query-sharded mode={mode} k={k}", flush=True)
-            ok = ok and same
+    for windows in (False, True):                 # all-gather form, then the fused search + exchange over peer memory
+        if windows:
+            fused_ok = comm.enable_peer_windows(12 * 32 * nq_local * world)
+            if rank == 0:
+                print(f"peer windows: {'mapped' if fused_ok else 'NOT available (all-gather path stays)'}", flush=True)
+        for mode in (0, 3):                       # auto, and the k-d index forced
+            tree.set_search_mode(mode)
+            for k in (1, 16):
+                for rep in range(3):              # (both window halves, flag rows reused)
+                    hi, hd = tree.nearest_k_query_sharded(comm, q_all[rank * nq_local:(rank + 1) * nq_local], k)
+                oi, od = O.knn(pts, q_all, k, nthreads=8)
+                same = np.array_equal(hi.reshape(-1, k), oi) and np.array_equal(hd.reshape(-1, k), od)
+                if not same:
+                    print(f"[rank {rank}] MISMATCH query-sharded windows={windows} mode={mode} k={k}", flush=True)
+                ok = ok and same
     if rank == 0:
-        print(f"query-sharded: n={n} world={world} ok={ok} index={tree.index_stats()['indexed_nodes']}", flush=True)
+        print(f"query-sharded: n={n} world={world} ok={ok} index={tree.index_stats()['indexed_nodes']} "
+              f"fused_steps={comm.fused_steps()}", flush=True)
     tree.close()
     # edges: replicated batch, sliced validation, all-gather of the verdicts
     dh, link, xyzr = synth.default_arm()
