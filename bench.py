@@ -582,6 +582,7 @@ def measure_knn(env, args, want_cpu):
 
     e2e_s = env.timed_host(e2e_step)
     e2e_s2 = env.timed_host(lambda: e2e_step(reupload=True), K=max(3, env.K // 3))
+    tree.build_index()   # the refills left the index stale; everything below searches the final tree again
     h2d, d2h = Q * 56, world * Q * k * 12
     algo_bytes = n_local * 56 + Q * 56 + Q * k * 12
     tpeak, tsrc = tensor_peak()
