@@ -15,6 +15,7 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 #include <algorithm>
+#include <cstdlib>
 #include "check_motion.cuh"
 #include "edge_plan.cuh"
 
@@ -775,7 +776,10 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
         }
         if (!scratch->pair_n) // [0] phase A items, [1] phase B items, [2] owed states of the pass
           PRGPU_CUDA_TRY(cudaMalloc(&scratch->pair_n, 4 * sizeof(uint32_t)));
-        CmItems ia{scratch->pair_ref, reinterpret_cast<float4 *>(scratch->pair_centre), scratch->pair_n, (uint32_t)scratch->pair_cap};
+        // (PRGPU_CM_ITEM_CAP shrinks the table for tests of the in-kernel overflow path: results must not change)
+        const char *cap_env = getenv("PRGPU_CM_ITEM_CAP");
+        const size_t use_cap = cap_env ? std::min<size_t>(scratch->pair_cap, (size_t)atoll(cap_env)) : scratch->pair_cap;
+        CmItems ia{scratch->pair_ref, reinterpret_cast<float4 *>(scratch->pair_centre), scratch->pair_n, (uint32_t)use_cap};
         CmItems ib = ia;
         ib.count = scratch->pair_n + 1;
         PRGPU_CUDA_TRY(cudaFuncSetAttribute(cm_sample2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

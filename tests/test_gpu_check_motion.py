@@ -115,3 +115,17 @@ def test_field_and_grid_switches_do_not_change_verdicts(P, synth, world_arrays, 
             ref_v, ref_s = v, s
         else:
             assert np.array_equal(v, ref_v) and np.array_equal(s, ref_s), env
+
+
+def test_item_table_overflow_changes_nothing(P, synth, gpu_world, monkeypatch):
+    """Large batches deal the obstacle-list walks out as (state, sphere) items; when the item table is full a lane
+    walks its own lists on the spot.  With the table shrunk to almost nothing the verdicts must be the same."""
+    a, b = synth.edges(2, 60000)
+    ref = gpu_world.check_motion_batch(a, b, 0.01)
+    ref_nnf = gpu_world.check_motion_batch(a, b, 0.05, mode=P.MODE_NNF_ALPHA)
+    for cap in ("0", "7", "1000"):
+        monkeypatch.setenv("PRGPU_CM_ITEM_CAP", cap)
+        assert np.array_equal(gpu_world.check_motion_batch(a, b, 0.01), ref), cap
+        assert np.array_equal(gpu_world.check_motion_batch(a, b, 0.05, mode=P.MODE_NNF_ALPHA), ref_nnf), cap
+    monkeypatch.delenv("PRGPU_CM_ITEM_CAP")
+    assert np.array_equal(gpu_world.check_motion_batch(a, b, 0.01), ref)
