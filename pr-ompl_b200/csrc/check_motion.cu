@@ -300,6 +300,7 @@ cm_gaps_kernel(uint32_t n, int mode, const uint8_t *__restrict__ valid, uint32_t
 //   lists    : one thread per item walks the obstacle list of the centre's cell; phase A and phase B share it;
 //   certify_b: phase B's states against the clearance field only, uncertified spheres become items again.
 // If the item table is full the lane walks its own lists on the spot (correctness never depends on capacity).
+constexpr uint32_t CM_NO_ITEM = 0xFFFFFFFFu; // a reserved slot that was never filled (see cm_push_items)
 struct CmItems {
   uint32_t *ref;   // phase A: edge * 8 + slot; phase B: index of the owed state
   float4 *centre;  // x, y, z, sphere slot (as int bits)
@@ -326,8 +327,14 @@ __device__ __forceinline__ bool cm_push_items(const CmItems &it, uint32_t ref, u
   if (lane == 31)
     base = atomicAdd(it.count, total);
   base = __shfl_sync(0xffffffffu, base, 31);
-  if (base + total > it.cap)
-    return false; // (the counter keeps the overshoot; the lists kernel clamps it)
+  if (base + total > it.cap) {
+    // the counter keeps the overshoot and the lists kernel clamps it to the capacity: the slots this push had
+    // reserved below the capacity stay without an item, so they are marked (a stale item of an earlier call
+    // would otherwise be walked against this call's edges)
+    for (uint32_t o = base + (uint32_t)lane; o < it.cap; o += 32)
+      it.ref[o] = CM_NO_ITEM;
+    return false;
+  }
   uint32_t o = base + incl - mine;
   while (unc) {
     const int j = __ffs(unc) - 1;
@@ -445,6 +452,8 @@ cm_lists_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ f
   const uint32_t total = min(*items.count, items.cap);
   for (uint32_t g = blockIdx.x * CM_THREADS + threadIdx.x; g < total; g += gridDim.x * CM_THREADS) {
     const uint32_t ref = items.ref[g];
+    if (ref == CM_NO_ITEM)
+      continue;
     const uint32_t e = PHASE == 0 ? ref >> 3 : item_edge[ref];
     if (valid[e] == 0)
       continue;

@@ -405,7 +405,7 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
   __shared__ uint32_t idle; // bit w: warp w waits for work
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t first_leaf = (1u << levels) - 1u;
-  const uint32_t ALL = (1u << KD_WARPS) - 1u;
+  const uint32_t ALL = KD_WARPS >= 32 ? 0xFFFFFFFFu : (1u << (KD_WARPS & 31)) - 1u;
   // ---- set-up: slot w <- query blockIdx.x * qpb + w ----
   if (w < qpb) {
     const uint32_t q = blockIdx.x * (uint32_t)qpb + (uint32_t)w;
