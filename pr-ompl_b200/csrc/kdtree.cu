@@ -147,7 +147,7 @@ __global__ void kd_cut_kernel(const uint64_t *__restrict__ keys, uint32_t n, int
 }
 __global__ void kd_leaves_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, int dim, int levels,
                                  const uint32_t *__restrict__ perm, double *__restrict__ leaf_pts,
-                                 uint32_t *__restrict__ leaf_idx) {
+                                 float *__restrict__ leaf_f32, uint32_t *__restrict__ leaf_idx) {
   const uint32_t leaf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (leaf >= (1u << levels))
     return;
@@ -157,8 +157,11 @@ __global__ void kd_leaves_kernel(const double *__restrict__ pts, uint64_t stride
     const bool have = b + slot < e;
     const uint32_t src = have ? perm[b + slot] : 0u;
     leaf_idx[(size_t)leaf * KD_LEAF + slot] = have ? src : PRGPU_INVALID_INDEX;
-    for (int d = 0; d < dim; ++d)
-      leaf_pts[((size_t)leaf * dim + d) * KD_LEAF + slot] = have ? pts[(size_t)d * stride + src] : (double)INFINITY;
+    for (int d = 0; d < dim; ++d) {
+      const double x = have ? pts[(size_t)d * stride + src] : (double)INFINITY;
+      leaf_pts[((size_t)leaf * dim + d) * KD_LEAF + slot] = x;
+      leaf_f32[((size_t)leaf * dim + d) * KD_LEAF + slot] = __double2float_rn(x); // the filter's copy (see kd_T32)
+    }
   }
 }
 
@@ -185,9 +188,13 @@ __device__ __forceinline__ KdTreelet kd_load_treelet(const KdNode *__restrict__ 
       const double x = xq[nd.dim];
       t.left = x < (double)nd.cut;
       // distance to the far half-space (planes widened by one fp32 ulp, see kd_cut_kernel)
-      const double pd = t.left ? fmax(0.0, (double)nd.cut_lo - x) : fmax(0.0, x - (double)nd.cut_hi);
+      const double pp = (double)(t.left ? nd.cut_lo : nd.cut_hi) - x;
+      double pd = t.left ? pp : -pp;
+      pd = pd > 0.0 ? pd : 0.0;
       // term of this dimension already inside the cell distance: distance to the cell's own bounds
-      const double off = fmax(0.0, fmax((double)nd.lo - x, x - (double)nd.hi));
+      const double o1 = (double)nd.lo - x, o2 = x - (double)nd.hi;
+      double off = o1 > o2 ? o1 : o2;
+      off = off > 0.0 ? off : 0.0;
       t.delta = pd * pd - off * off;
     }
   }
@@ -384,8 +391,29 @@ struct KdSlot {                 // one query of the block
   double list_d[32];
   uint32_t list_i[32];
   unsigned long long bound;     // bits of the squared pruning bound (non-negative doubles order like their bits)
-  uint32_t lock, workers, qid, pad;
+  uint32_t lock, workers, qid;
+  uint32_t bound_t;             // bits of the fp32 leaf threshold that goes with `bound` (kd_T32)
+  double err;                   // E of kd_T32: what rounding the query and the nodes to fp32 can move a distance by
+  float qf[8];
 };
+
+// ---- the fp32 leaf filter ----------------------------------------------------------------------------------
+// A leaf is first evaluated on its fp32 copy: s32 = sum_d (x32_d - q32_d)^2 in fp32 (FMA chain).  With a_d = x_d -
+// q_d the exact differences and A = |a| the exact distance: x32_d = x_d (1 + al), q32_d = q_d (1 + be), the fp32
+// subtraction adds a relative 2^-24, so a32 = a + z with |z| <= 2^-24 A + (1 + 2^-24) 2^-24 (|x| + |q|) =: 2^-24 A + E,
+// and the FMA chain of 7 non-negative terms is within (1 + 2^-24)^8 of |a32|^2.  Hence
+//   A >= (sqrt(s32) (1 - 4.2 * 2^-24) - E) / (1 + 2^-24),
+// and a node with s32 > T32 := ((r (1 + 2^-21) + E)^2 (1 + 2^-19) + 1e-37, rounded UP to fp32, has A > r (1 + 2^-22):
+// its fp64 distance as the reference computes it (relative error < 2^-49) is strictly above r, the k-th best so far,
+// so it cannot enter the list whatever its index.  Everything else -- including NaN / inf from coordinates beyond
+// fp32, and every node while the list is not full (T32 = +inf) -- is evaluated again from the fp64 block in the
+// reference's own arithmetic.  The filter only rejects; the list never sees an fp32 number.
+// E takes |x| <= M, the largest norm inside the root cell; 1e-40 / 1e-37 cover fp32 underflow.
+__device__ __forceinline__ float kd_T32(double r, double E) {
+  double t = r * (1.0 + 0x1p-21) + E;
+  t = t * t * (1.0 + 0x1p-19) + 1e-37;
+  return __double2float_ru(t); // +inf beyond fp32: everything is a candidate
+}
 struct KdMail {
   double rd;
   uint32_t node, slot;
@@ -393,9 +421,10 @@ struct KdMail {
   uint32_t pad;
 };
 
-template <int DIM>
+template <int DIM, bool F32>
 __global__ void __launch_bounds__(KD_WARPS * 32, KD_MINB)
 kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict__ leaf_pts,
+                      const float *__restrict__ leaf_f32,
                       const uint32_t *__restrict__ leaf_idx, const float *__restrict__ root_cell, int levels,
                       uint32_t index_base, const double *__restrict__ queries, uint32_t nq, int k, int qpb,
                       uint32_t *__restrict__ idx_out, double *__restrict__ dist_out,
@@ -410,12 +439,27 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
   if (w < qpb) {
     const uint32_t q = blockIdx.x * (uint32_t)qpb + (uint32_t)w;
     KdSlot &sl = slots[w];
-    if (lane < 8)
-      sl.qx[lane] = (q < nq && lane < DIM) ? queries[(size_t)q * DIM + lane] : 0.0;
+    const double x = (q < nq && lane < DIM) ? queries[(size_t)q * DIM + lane] : 0.0;
+    if (lane < 8) {
+      sl.qx[lane] = x;
+      sl.qf[lane] = __double2float_rn(x);
+    }
     sl.list_d[lane] = INFINITY;
     sl.list_i[lane] = PRGPU_INVALID_INDEX;
+    // |q|^2 and M^2 (largest norm inside the root cell) for E
+    double q2 = x * x, m2 = 0.0;
+    if (lane < DIM) {
+      const double m = fmax(fabs((double)root_cell[lane]), fabs((double)root_cell[8 + lane]));
+      m2 = m * m;
+    }
+    for (int o = 16; o; o >>= 1) {
+      q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, o);
+      m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+    }
     if (lane == 0) {
       sl.bound = (unsigned long long)__double_as_longlong((double)INFINITY);
+      sl.bound_t = __float_as_uint(INFINITY);
+      sl.err = (__dsqrt_ru(q2) + __dsqrt_ru(m2)) * (1.0 + 0x1p-40) * (0x1p-24 * (1.0 + 0x1p-23)) + 1e-40;
       sl.lock = 0;
       sl.workers = q < nq ? 1u : 0u;
       sl.qid = q;
@@ -472,13 +516,20 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
     // ---- one work unit: the subtree `node` (cell distance rd) of query slot `slot` ----
     KdSlot &sl = slots[slot];
     const double *xq = sl.qx;
-    double qx[DIM];
+    double qx[F32 ? 1 : DIM]; // (the fp32 form reads the fp64 query from shared memory, for candidates only)
+    float qf[F32 ? DIM : 1];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d)
-      qx[d] = xq[d];
+    for (int d = 0; d < DIM; ++d) {
+      if (F32)
+        qf[d] = sl.qf[d];
+      else
+        qx[d] = xq[d];
+    }
+    const double err = sl.err;
     double best_d = INFINITY;
     uint32_t best_i = PRGPU_INVALID_INDEX;
     double r2loc = INFINITY; // from this worker's own list
+    float t32loc = INFINITY; // the fp32 leaf threshold that goes with r2loc
     uint32_t stk_node = 0;
     double stk_rd = 0.0;
     int sp = 0;
@@ -492,6 +543,7 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
     bool alive = true;
     while (alive) {
       double r2hi = fmin(r2loc, __longlong_as_double((long long)*(volatile unsigned long long *)&sl.bound));
+      float t32 = fminf(t32loc, __uint_as_float(*(volatile uint32_t *)&sl.bound_t));
       while (node < first_leaf) {
         if (tv > 3) {
           tl = kd_load_treelet(nodes, node, first_leaf, lane, xq);
@@ -524,14 +576,24 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
       }
       const uint32_t leaf = node - first_leaf;
       const double *lp = leaf_pts + (size_t)leaf * DIM * KD_LEAF + lane;
-      double c0[KD_PPL_][DIM];
+      double c0[F32 ? 1 : KD_PPL_][F32 ? 1 : DIM];
+      float f0[F32 ? KD_PPL_ : 1][F32 ? DIM : 1];
       uint32_t my_i[KD_PPL_];
+      if (F32) {
+        const float *fp = leaf_f32 + (size_t)leaf * DIM * KD_LEAF + lane;
 #pragma unroll
-      for (int j = 0; j < KD_PPL_; ++j) {
+        for (int j = 0; j < KD_PPL_; ++j)
 #pragma unroll
-        for (int d = 0; d < DIM; ++d)
-          c0[j][d] = lp[d * KD_LEAF + j * 32];
-        my_i[j] = leaf_idx[(size_t)leaf * KD_LEAF + j * 32 + lane];
+          for (int d = 0; d < DIM; ++d)
+            f0[j][d] = fp[d * KD_LEAF + j * 32];
+      } else {
+#pragma unroll
+        for (int j = 0; j < KD_PPL_; ++j) {
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            c0[j][d] = lp[d * KD_LEAF + j * 32];
+          my_i[j] = leaf_idx[(size_t)leaf * KD_LEAF + j * 32 + lane];
+        }
       }
       // ---- while the leaf loads are in flight: hand the bottom of the stack to an idle warp ----
       while (sp >= 2 && *(volatile uint32_t *)&idle != 0) { // (every idle warp gets one, while the stack lasts)
@@ -573,20 +635,54 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
           nx_tl = kd_load_treelet(nodes, nx_node, first_leaf, lane, xq);
       }
       double s[KD_PPL_];
+      unsigned pass[KD_PPL_]; // fp32 form: the slots the filter could not reject
+      if (F32) {
 #pragma unroll
-      for (int j = 0; j < KD_PPL_; ++j) {
-        double a = __dsub_rn(c0[j][0], qx[0]);
-        s[j] = __dmul_rn(a, a);
+        for (int j = 0; j < KD_PPL_; ++j) {
+          float a = f0[j][0] - qf[0];
+          float s32 = a * a;
 #pragma unroll
-        for (int d = 1; d < DIM; ++d) {
-          a = __dsub_rn(c0[j][d], qx[d]);
-          s[j] = __dadd_rn(s[j], __dmul_rn(a, a));
+          for (int d = 1; d < DIM; ++d) {
+            a = f0[j][d] - qf[d];
+            s32 = fmaf(a, a, s32);
+          }
+          pass[j] = __ballot_sync(0xFFFFFFFFu, !(s32 > t32)); // (NaN passes)
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < KD_PPL_; ++j) {
+          double a = __dsub_rn(c0[j][0], qx[0]);
+          s[j] = __dmul_rn(a, a);
+#pragma unroll
+          for (int d = 1; d < DIM; ++d) {
+            a = __dsub_rn(c0[j][d], qx[d]);
+            s[j] = __dadd_rn(s[j], __dmul_rn(a, a));
+          }
+          pass[j] = 0xFFFFFFFFu;
         }
       }
       nvis += 1;
       bool improved = false;
 #pragma unroll
       for (int j = 0; j < KD_PPL_; ++j) {
+        if (F32) {
+          if (pass[j] == 0)
+            continue;
+          // the candidates again, from the fp64 block, in the reference's arithmetic
+          s[j] = INFINITY;
+          my_i[j] = PRGPU_INVALID_INDEX;
+          if ((pass[j] >> lane) & 1u) {
+            my_i[j] = leaf_idx[(size_t)leaf * KD_LEAF + j * 32 + lane];
+            double a = __dsub_rn(lp[j * 32], xq[0]);
+            double acc = __dmul_rn(a, a);
+#pragma unroll
+            for (int d = 1; d < DIM; ++d) {
+              a = __dsub_rn(lp[d * KD_LEAF + j * 32], xq[d]);
+              acc = __dadd_rn(acc, __dmul_rn(a, a));
+            }
+            s[j] = acc;
+          }
+        }
         unsigned cand = __ballot_sync(0xFFFFFFFFu, my_i[j] != PRGPU_INVALID_INDEX && s[j] <= r2hi);
         while (cand) {
           const int c = __ffs(cand) - 1;
@@ -617,8 +713,17 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
           }
         }
       }
-      if (improved && lane == 0)
-        atomicMin(&sl.bound, (unsigned long long)__double_as_longlong(r2loc));
+      if (improved) {
+        if (F32) {
+          t32loc = kd_T32(__shfl_sync(0xFFFFFFFFu, best_d, k - 1), err);
+          t32 = fminf(t32, t32loc);
+        }
+        if (lane == 0) {
+          atomicMin(&sl.bound, (unsigned long long)__double_as_longlong(r2loc));
+          if (F32)
+            atomicMin(&sl.bound_t, __float_as_uint(t32loc));
+        }
+      }
       r2hi = fmin(r2hi, __longlong_as_double((long long)*(volatile unsigned long long *)&sl.bound));
       alive = false;
       bool first_pop = true;
@@ -672,8 +777,11 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
       const double r = __shfl_sync(0xFFFFFFFFu, md, k - 1);
       uint32_t left = 0;
       if (lane == 0) {
-        if (r < INFINITY)
+        if (r < INFINITY) {
           atomicMin(&sl.bound, (unsigned long long)__double_as_longlong(__dmul_ru(r, r) * (1.0 + 0x1p-50)));
+          if (F32)
+            atomicMin(&sl.bound_t, __float_as_uint(kd_T32(r, err)));
+        }
         left = atomicSub(&sl.workers, 1u) - 1u;
       }
       left = __shfl_sync(0xFFFFFFFFu, left, 0);
@@ -705,11 +813,12 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
 } // namespace
 
 void KdIndex::release() {
-  for (void *p : {(void *)nodes, (void *)leaf_pts, (void *)leaf_idx, (void *)visited, (void *)root_cell})
+  for (void *p : {(void *)nodes, (void *)leaf_pts, (void *)leaf_f32, (void *)leaf_idx, (void *)visited, (void *)root_cell})
     if (p)
       cudaFree(p);
   nodes = nullptr;
   leaf_pts = nullptr;
+  leaf_f32 = nullptr;
   leaf_idx = nullptr;
   visited = nullptr;
   root_cell = nullptr;
@@ -754,6 +863,7 @@ int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint3
   } while (0)
   KD_TRY(cudaMalloc(&kd.nodes, sizeof(KdNode) * (size_t)std::max<uint32_t>(nleaf - 1, 1)));
   KD_TRY(cudaMalloc(&kd.leaf_pts, sizeof(double) * (size_t)nleaf * dim * KD_LEAF));
+  KD_TRY(cudaMalloc(&kd.leaf_f32, sizeof(float) * (size_t)nleaf * dim * KD_LEAF));
   KD_TRY(cudaMalloc(&kd.leaf_idx, sizeof(uint32_t) * (size_t)nleaf * KD_LEAF));
   KD_TRY(cudaMalloc(&kd.visited, sizeof(unsigned long long)));
   KD_TRY(cudaMalloc(&kd.root_cell, sizeof(float) * 16));
@@ -785,7 +895,7 @@ int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint3
     std::swap(perm_a, perm_b);
     std::swap(cells_a, cells_b);
   }
-  kd_leaves_kernel<<<(nleaf + 7) / 8, 256, 0, stream>>>(pts_soa, stride, n, dim, L, perm_a, kd.leaf_pts, kd.leaf_idx); PRGPU_COUNT_LAUNCH(1);
+  kd_leaves_kernel<<<(nleaf + 7) / 8, 256, 0, stream>>>(pts_soa, stride, n, dim, L, perm_a, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx); PRGPU_COUNT_LAUNCH(1);
   KD_TRY(cudaGetLastError());
   cudaEventRecord(e1, stream);
   KD_TRY(cudaEventSynchronize(e1));
@@ -823,15 +933,22 @@ int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev,
     if (team_env > 0)
       qpb = std::min(team_env, (int)KD_WARPS);
     const unsigned tblocks = (nq + qpb - 1) / qpb;
+    // leaves filtered on their fp32 copy (default; PRGPU_KD_F32=0 evaluates every leaf from the fp64 block -- same
+    // results, kept for A/B tests)
+    const bool f32 = !(getenv("PRGPU_KD_F32") && atoi(getenv("PRGPU_KD_F32")) == 0);
     if (timer)
       timer->begin(stream);
     switch (kd.dim) {
 #define KD_CASE(D)                                                                                 \
   case D:                                                                                          \
-    kd_search_team_kernel<D><<<tblocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell, \
-                                                                   kd.levels, index_base, queries_dev, nq, k, qpb,     \
-                                                                   idx_dev, dist_dev,                                  \
-                                                                   kd.count_visits ? kd.visited : nullptr, po);        \
+    if (f32)                                                                                       \
+      kd_search_team_kernel<D, true><<<tblocks, KD_WARPS * 32, 0, stream>>>(                       \
+          kd.nodes, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx, kd.root_cell, kd.levels, index_base, queries_dev, nq, k, \
+          qpb, idx_dev, dist_dev, kd.count_visits ? kd.visited : nullptr, po);                     \
+    else                                                                                           \
+      kd_search_team_kernel<D, false><<<tblocks, KD_WARPS * 32, 0, stream>>>(                      \
+          kd.nodes, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx, kd.root_cell, kd.levels, index_base, queries_dev, nq, k, \
+          qpb, idx_dev, dist_dev, kd.count_visits ? kd.visited : nullptr, po);                     \
     break;
       KD_CASE(1)
       KD_CASE(2)

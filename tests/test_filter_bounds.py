@@ -71,3 +71,71 @@ def test_fp32_key_error_within_eps_32():
             key_real = (x * x).sum(1) - 2.0 * x @ qi
             err = np.abs(acc.astype(np.float64) - key_real)
             assert err.max() <= eps_32(qn, xn), (scale, offset, err.max(), eps_32(qn, xn))
+
+
+# ---- the fp32 leaf filter of the k-d index (csrc/kdtree.cu: kd_T32) ------------------------------------------
+def kd_err(qn, mn):
+    return (qn + mn) * (1.0 + 2.0 ** -40) * (2.0 ** -24 * (1.0 + 2.0 ** -23)) + 1e-40
+
+
+def kd_T32(r, E):
+    t = r * (1.0 + 2.0 ** -21) + E
+    t = t * t * (1.0 + 2.0 ** -19) + 1e-37
+    with np.errstate(over="ignore"):
+        f = np.float32(t)
+    if np.float64(f) < t:                                  # __double2float_ru
+        f = np.nextafter(f, np.float32(np.inf))
+    return f
+
+
+def fp32_chain(x32, q32):
+    """s32 of the leaf pass: a = x32 - q32 (fp32), s = fma(a, a, s) in dimension order."""
+    with np.errstate(over="ignore", invalid="ignore"):
+        a = (x32 - q32).astype(np.float32)
+        s = (a[:, 0].astype(np.float64) * a[:, 0]).astype(np.float32)
+        for d in range(1, x32.shape[1]):
+            s = (a[:, d].astype(np.float64) * a[:, d] + s.astype(np.float64)).astype(np.float32)
+    return s
+
+
+def test_kd_leaf_filter_never_rejects_a_node_within_the_bound():
+    """The filter rejects a node iff s32 > T32(r).  So every node whose fp64 distance (as the reference computes
+    it) is <= r must have s32 <= T32(r) -- for r the distance of the node itself (the tightest r it can meet)."""
+    rng = np.random.default_rng(7)
+    cases = [(1.0, 0.0), (1e-3, 0.0), (1e6, 0.0), (1e-6, 0.0), (1e-6, 250.0), (1e-9, -40.0), (1.0, 1e5),
+             (1e-30, 0.0), (1e-42, 0.0), (1e30, 0.0)]
+    for scale, offset in cases:
+        x = rng.uniform(-np.pi, np.pi, (30000, 7)) * scale + offset
+        q = rng.uniform(-np.pi, np.pi, (32, 7)) * scale + offset
+        q[:8] = x[:8]                                       # queries that are nodes
+        q[8:16] = x[8:16] + 1e-7 * scale                    # and almost nodes
+        mn = np.sqrt((np.abs(x).max(0) ** 2).sum())         # M: largest norm inside the bounding box
+        with np.errstate(over="ignore"):
+            x32 = x.astype(np.float32)
+        for qi in q:
+            E = kd_err(np.sqrt((qi * qi).sum()), mn)
+            with np.errstate(over="ignore"):
+                s32 = fp32_chain(x32, qi.astype(np.float32)[None, :])
+            a = x - qi
+            s = a[:, 0] * a[:, 0]
+            for d in range(1, 7):
+                s = s + a[:, d] * a[:, d]                   # the reference's order: sub, mul, add
+            dist = np.sqrt(s)
+            T = np.array([kd_T32(r, E) for r in dist[:2000]], dtype=np.float32)
+            assert np.all(~(s32[:2000] > T)), (scale, offset)
+            # and the bound is not vacuous: at the scale of the data it rejects what is 1e-3 farther
+            if offset == 0.0 and 1e-6 <= scale <= 1e6:
+                far = dist[:2000] * (1 - 1e-3)
+                Tf = np.array([kd_T32(r, E) for r in far], dtype=np.float32)
+                assert np.mean(s32[:2000] > Tf) > 0.95, (scale, offset)
+
+
+def test_kd_leaf_filter_out_of_range_coordinates_pass():
+    """Coordinates beyond fp32 become inf, differences inf or NaN: never rejected against an infinite threshold, and
+    NaN is never rejected at all (the kernel tests !(s32 > T32))."""
+    x32 = np.array([[np.inf, 0, 0, 0, 0, 0, 0], [np.inf, 0, 0, 0, 0, 0, 0]], dtype=np.float32)
+    q32 = np.array([[np.inf, 0, 0, 0, 0, 0, 0]], dtype=np.float32)
+    s = fp32_chain(x32, q32)
+    assert np.all(np.isnan(s)) and not np.any(s > np.float32(1.0))
+    assert kd_T32(1e30, 0.0) == np.float32(np.inf)          # a threshold beyond fp32 rejects nothing
+    assert not (np.float32(np.inf) > kd_T32(1e30, 0.0))

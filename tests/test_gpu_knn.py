@@ -347,3 +347,29 @@ def test_kd_index_is_built_when_it_has_paid_for_itself(P, O, synth):
     oi, od = O.knn(np.vstack([pts, synth.cloud(3, 1)]), q[:300], k, nthreads=8)
     assert np.array_equal(gi, oi) and np.array_equal(gd, od)
     t.close()
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1e-6, 250.0), (1e-9, -40.0), (1e6, 0.0), (1e-6, 0.0),
+                                          (1e-42, 0.0), (1e36, 0.0), (1e39, 0.0)])
+def test_kd_fp32_leaf_filter_changes_nothing(P, O, monkeypatch, scale, offset):
+    """The index searches read a leaf's fp32 copy first and evaluate only what that cannot reject from the fp64
+    block (csrc/kdtree.cu, kd_T32).  Families chosen against the fp32 step: spacings far below the fp32 resolution
+    at the data's offset (every node of a leaf collapses onto a few fp32 values), fp32-subnormal and beyond-fp32
+    coordinates, exact duplicates.  Results = the oracle's = the fp64-only form's (PRGPU_KD_F32=0), bit for bit."""
+    rng = np.random.default_rng(11)
+    n = 1 << 17
+    pts = rng.uniform(-np.pi, np.pi, size=(n, 7)) * scale + offset
+    pts[5000:6000] = pts[:1000]                                   # duplicates
+    q = rng.uniform(-np.pi, np.pi, size=(64, 7)) * scale + offset
+    q[:16] = pts[rng.integers(0, n, 16)]
+    tree = P.KnnIndex(7)
+    tree.add(pts)
+    tree.set_search_mode(3)
+    for k in (1, 16):
+        oi, od = O.knn(pts, q, k, nthreads=8)
+        for f32 in ("1", "0"):
+            monkeypatch.setenv("PRGPU_KD_F32", f32)
+            gi, gd = tree.nearest_k(q, k)
+            assert np.array_equal(gi, oi) and np.array_equal(gd, od), (k, f32)
+    assert tree.index_stats()["indexed_nodes"] == n
+    tree.close()
