@@ -90,7 +90,7 @@ int prgpu_knn_build_index(prgpu_knn_t *h);
  * point set (so a structure refilled before every search never builds one); add/clear make it stale.
  * prgpu_knn_set_search_mode(h, 2) keeps the brute-force paths only (mode 1: the exact fp64 kernel only;
  * mode 3: the index whenever it can answer -- no `lo`, k <= 32, >= 128 points -- built at once; mode 0: auto).
- * indexed_nodes: points covered by a valid index (0: none); leaves_visited: 32-point leaves evaluated by
+ * indexed_nodes: points covered by a valid index (0: none); leaves_visited: leaves (64 or 96 slots) evaluated by
  * all index searches so far (reading it synchronises the device).  Any pointer may be NULL. */
 int prgpu_knn_index_stats(prgpu_knn_t *h, uint64_t *indexed_nodes, float *build_ms, uint32_t *builds,
                           uint64_t *index_calls, uint64_t *leaves_visited);

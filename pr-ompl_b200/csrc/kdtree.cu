@@ -29,11 +29,10 @@
 
 namespace prgpu {
 namespace {
-#ifndef KD_PPL
-#define KD_PPL 2
-#endif
-constexpr int KD_PPL_ = KD_PPL;       // leaf slots per lane
-constexpr int KD_LEAF = 32 * KD_PPL_; // slots per leaf
+// Leaf capacity = 32 * PPL slots (PPL = slots per lane, a template parameter of the search kernels): kd_build takes
+// the PPL in {2, 3} that leaves the fewest empty slots for the node count at hand -- a balanced tree has 2^L leaves of
+// n / 2^L nodes, so one fixed capacity would leave up to half of every leaf (traffic and arithmetic) empty.
+constexpr int KD_PPL_MIN = 2, KD_PPL_MAX = 3;
 #ifndef KD_WARPS_N
 #define KD_WARPS_N 8
 #endif
@@ -145,14 +144,15 @@ __global__ void kd_cut_kernel(const uint64_t *__restrict__ keys, uint32_t n, int
   l[8 + nd.dim] = fminf(c[8 + nd.dim], nd.cut_hi);
   r[nd.dim] = fmaxf(c[nd.dim], nd.cut_lo);
 }
-__global__ void kd_leaves_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, int dim, int levels,
+__global__ void kd_leaves_kernel(const double *__restrict__ pts, uint64_t stride, uint32_t n, int dim, int levels, int ppl,
                                  const uint32_t *__restrict__ perm, double *__restrict__ leaf_pts,
                                  float *__restrict__ leaf_f32, uint32_t *__restrict__ leaf_idx) {
   const uint32_t leaf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (leaf >= (1u << levels))
     return;
+  const int KD_LEAF = 32 * ppl;
   const uint64_t b = kd_bound(leaf, n, levels), e = kd_bound((uint64_t)leaf + 1, n, levels);
-  for (int j = 0; j < KD_PPL_; ++j) {
+  for (int j = 0; j < ppl; ++j) {
     const uint32_t slot = j * 32 + lane;
     const bool have = b + slot < e;
     const uint32_t src = have ? perm[b + slot] : 0u;
@@ -204,13 +204,14 @@ __device__ __forceinline__ KdTreelet kd_load_treelet(const KdNode *__restrict__ 
 #ifndef KD_MINB
 #define KD_MINB 4
 #endif
-template <int DIM>
+template <int DIM, int KD_PPL_>
 __global__ void __launch_bounds__(KD_WARPS * 32, KD_MINB)
 kd_search_kernel(const KdNode *__restrict__ nodes, const double *__restrict__ leaf_pts,
                  const uint32_t *__restrict__ leaf_idx, const float *__restrict__ root_cell, int levels,
                  uint32_t index_base,
                  const double *__restrict__ queries, uint32_t nq, int k, uint32_t *__restrict__ idx_out,
                  double *__restrict__ dist_out, unsigned long long *__restrict__ visited) {
+  constexpr int KD_LEAF = 32 * KD_PPL_;
   __shared__ double sq[KD_WARPS][8];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q = blockIdx.x * KD_WARPS + w;
@@ -421,7 +422,7 @@ struct KdMail {
   uint32_t pad;
 };
 
-template <int DIM, bool F32>
+template <int DIM, bool F32, int KD_PPL_>
 __global__ void __launch_bounds__(KD_WARPS * 32, KD_MINB)
 kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict__ leaf_pts,
                       const float *__restrict__ leaf_f32,
@@ -429,6 +430,7 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
                       uint32_t index_base, const double *__restrict__ queries, uint32_t nq, int k, int qpb,
                       uint32_t *__restrict__ idx_out, double *__restrict__ dist_out,
                       unsigned long long *__restrict__ visited, const KdPeerOut po) {
+  constexpr int KD_LEAF = 32 * KD_PPL_;
   __shared__ KdSlot slots[KD_WARPS];
   __shared__ KdMail mail[KD_WARPS];
   __shared__ uint32_t idle; // bit w: warp w waits for work
@@ -560,9 +562,11 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
             stk_rd = rd_far;
           }
           ++sp;
-          if (far >= first_leaf) {
-            const char *base = reinterpret_cast<const char *>(leaf_pts + (size_t)(far - first_leaf) * DIM * KD_LEAF);
-            if (lane * 128 < DIM * KD_LEAF * 8)
+          if (far >= first_leaf) { // (the rows the pop will read first: the fp32 copy in the filtered form)
+            const size_t row0 = (size_t)(far - first_leaf) * DIM * KD_LEAF;
+            const char *base = F32 ? reinterpret_cast<const char *>(leaf_f32 + row0)
+                                   : reinterpret_cast<const char *>(leaf_pts + row0);
+            if (lane * 128 < DIM * KD_LEAF * (F32 ? 4 : 8))
               asm volatile("prefetch.global.L2 [%0];" ::"l"(base + lane * 128));
           } else if (lane < 4) {
             const uint64_t idx = (((uint64_t)far + 1) << lane) - 1;
@@ -828,11 +832,32 @@ void KdIndex::release() {
 
 int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint32_t n, cudaStream_t stream) {
   kd.release();
-  if (n < 2 * KD_LEAF)
+  if (n < 2 * 32 * KD_PPL_MIN)
     return fail(PRGPU_EINVAL, "kd_build: too few nodes");
-  int L = 0;
-  while ((((uint64_t)n + (1ull << L) - 1) >> L) > (uint64_t)KD_LEAF)
-    ++L;
+  // leaf capacity: the one that leaves the fewest empty slots (ties: the smaller leaf)
+  int L = 0, ppl = KD_PPL_MIN;
+  double best_fill = -1.0;
+  for (int c = KD_PPL_MIN; c <= KD_PPL_MAX && n >= 2u * 32u * (unsigned)c; ++c) {
+    int l = 0;
+    while ((((uint64_t)n + (1ull << l) - 1) >> l) > (uint64_t)(32 * c))
+      ++l;
+    const double fill = (double)n / ((double)(1ull << l) * 32.0 * c);
+    if (fill > best_fill + 1e-9) {
+      best_fill = fill;
+      L = l;
+      ppl = c;
+    }
+  }
+  if (getenv("PRGPU_KD_PPL")) { // (tests: force a capacity)
+    const int c = atoi(getenv("PRGPU_KD_PPL"));
+    if (c >= KD_PPL_MIN && c <= KD_PPL_MAX && n >= 2u * 32u * (unsigned)c) {
+      ppl = c;
+      L = 0;
+      while ((((uint64_t)n + (1ull << L) - 1) >> L) > (uint64_t)(32 * c))
+        ++L;
+    }
+  }
+  const int KD_LEAF = 32 * ppl;
   const uint32_t nleaf = 1u << L;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaEventCreate(&e0);
@@ -895,7 +920,7 @@ int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint3
     std::swap(perm_a, perm_b);
     std::swap(cells_a, cells_b);
   }
-  kd_leaves_kernel<<<(nleaf + 7) / 8, 256, 0, stream>>>(pts_soa, stride, n, dim, L, perm_a, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx); PRGPU_COUNT_LAUNCH(1);
+  kd_leaves_kernel<<<(nleaf + 7) / 8, 256, 0, stream>>>(pts_soa, stride, n, dim, L, ppl, perm_a, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx); PRGPU_COUNT_LAUNCH(1);
   KD_TRY(cudaGetLastError());
   cudaEventRecord(e1, stream);
   KD_TRY(cudaEventSynchronize(e1));
@@ -904,12 +929,87 @@ int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint3
   kd.build_ms = ms;
   kd.n = n;
   kd.levels = L;
+  kd.ppl = ppl;
   kd.dim = dim;
   ++kd.builds;
   cleanup();
   return PRGPU_OK;
 #undef KD_TRY
 }
+
+namespace {
+template <int D, bool F32, int PPL>
+void kd_launch_team_one(const KdIndex &kd, unsigned tblocks, uint32_t index_base, const double *queries_dev, uint32_t nq,
+                        int k, int qpb, uint32_t *idx_dev, double *dist_dev, const KdPeerOut &po, cudaStream_t stream) {
+  kd_search_team_kernel<D, F32, PPL><<<tblocks, KD_WARPS * 32, 0, stream>>>(
+      kd.nodes, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx, kd.root_cell, kd.levels, index_base, queries_dev, nq, k, qpb,
+      idx_dev, dist_dev, kd.count_visits ? kd.visited : nullptr, po);
+}
+template <int D>
+void kd_launch_team_dim(const KdIndex &kd, bool f32, unsigned tblocks, uint32_t index_base, const double *queries_dev,
+                        uint32_t nq, int k, int qpb, uint32_t *idx_dev, double *dist_dev, const KdPeerOut &po,
+                        cudaStream_t stream) {
+#define KD_GO(F, P) kd_launch_team_one<D, F, P>(kd, tblocks, index_base, queries_dev, nq, k, qpb, idx_dev, dist_dev, po, stream)
+  if (kd.ppl == 3) {
+    if (f32)
+      KD_GO(true, 3);
+    else
+      KD_GO(false, 3);
+  } else {
+    if (f32)
+      KD_GO(true, 2);
+    else
+      KD_GO(false, 2);
+  }
+#undef KD_GO
+}
+bool kd_launch_team(const KdIndex &kd, bool f32, unsigned tblocks, uint32_t index_base, const double *queries_dev,
+                    uint32_t nq, int k, int qpb, uint32_t *idx_dev, double *dist_dev, const KdPeerOut &po,
+                    cudaStream_t stream) {
+  switch (kd.dim) {
+#define KD_CASE(D)                                                                                                  \
+  case D:                                                                                                           \
+    kd_launch_team_dim<D>(kd, f32, tblocks, index_base, queries_dev, nq, k, qpb, idx_dev, dist_dev, po, stream);    \
+    return true;
+    KD_CASE(1)
+    KD_CASE(2)
+    KD_CASE(3)
+    KD_CASE(4)
+    KD_CASE(5)
+    KD_CASE(6)
+    KD_CASE(7)
+    KD_CASE(8)
+#undef KD_CASE
+  }
+  return false;
+}
+bool kd_launch_single(const KdIndex &kd, unsigned blocks, uint32_t index_base, const double *queries_dev, uint32_t nq,
+                      int k, uint32_t *idx_dev, double *dist_dev, cudaStream_t stream) {
+  switch (kd.dim) {
+#define KD_CASE(D)                                                                                                  \
+  case D:                                                                                                           \
+    if (kd.ppl == 3)                                                                                                \
+      kd_search_kernel<D, 3><<<blocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell, \
+                                                                   kd.levels, index_base, queries_dev, nq, k, idx_dev, \
+                                                                   dist_dev, kd.count_visits ? kd.visited : nullptr); \
+    else                                                                                                            \
+      kd_search_kernel<D, 2><<<blocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell, \
+                                                                   kd.levels, index_base, queries_dev, nq, k, idx_dev, \
+                                                                   dist_dev, kd.count_visits ? kd.visited : nullptr); \
+    return true;
+    KD_CASE(1)
+    KD_CASE(2)
+    KD_CASE(3)
+    KD_CASE(4)
+    KD_CASE(5)
+    KD_CASE(6)
+    KD_CASE(7)
+    KD_CASE(8)
+#undef KD_CASE
+  }
+  return false;
+}
+} // namespace
 
 int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev, uint32_t nq, int k, uint32_t *idx_dev,
               double *dist_dev, cudaStream_t stream, KernelTimer *timer, const KdPeerOut *peers) {
@@ -938,30 +1038,8 @@ int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev,
     const bool f32 = !(getenv("PRGPU_KD_F32") && atoi(getenv("PRGPU_KD_F32")) == 0);
     if (timer)
       timer->begin(stream);
-    switch (kd.dim) {
-#define KD_CASE(D)                                                                                 \
-  case D:                                                                                          \
-    if (f32)                                                                                       \
-      kd_search_team_kernel<D, true><<<tblocks, KD_WARPS * 32, 0, stream>>>(                       \
-          kd.nodes, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx, kd.root_cell, kd.levels, index_base, queries_dev, nq, k, \
-          qpb, idx_dev, dist_dev, kd.count_visits ? kd.visited : nullptr, po);                     \
-    else                                                                                           \
-      kd_search_team_kernel<D, false><<<tblocks, KD_WARPS * 32, 0, stream>>>(                      \
-          kd.nodes, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx, kd.root_cell, kd.levels, index_base, queries_dev, nq, k, \
-          qpb, idx_dev, dist_dev, kd.count_visits ? kd.visited : nullptr, po);                     \
-    break;
-      KD_CASE(1)
-      KD_CASE(2)
-      KD_CASE(3)
-      KD_CASE(4)
-      KD_CASE(5)
-      KD_CASE(6)
-      KD_CASE(7)
-      KD_CASE(8)
-#undef KD_CASE
-    default:
+    if (!kd_launch_team(kd, f32, tblocks, index_base, queries_dev, nq, k, qpb, idx_dev, dist_dev, po, stream))
       return fail(PRGPU_ELIMIT, "kd_search: dim must be in [1,8]");
-    }
     PRGPU_COUNT_LAUNCH(1);
     if (timer)
       timer->end(stream);
@@ -971,25 +1049,8 @@ int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev,
   const unsigned blocks = (nq + KD_WARPS - 1) / KD_WARPS;
   if (timer)
     timer->begin(stream);
-  switch (kd.dim) {
-#define KD_CASE(D)                                                                                 \
-  case D:                                                                                          \
-    kd_search_kernel<D><<<blocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell,   \
-                                                              kd.levels, index_base, queries_dev, nq, k, idx_dev, \
-                                                              dist_dev, kd.count_visits ? kd.visited : nullptr);  \
-    break;
-    KD_CASE(1)
-    KD_CASE(2)
-    KD_CASE(3)
-    KD_CASE(4)
-    KD_CASE(5)
-    KD_CASE(6)
-    KD_CASE(7)
-    KD_CASE(8)
-#undef KD_CASE
-  default:
+  if (!kd_launch_single(kd, blocks, index_base, queries_dev, nq, k, idx_dev, dist_dev, stream))
     return fail(PRGPU_ELIMIT, "kd_search: dim must be in [1,8]");
-  }
   PRGPU_COUNT_LAUNCH(1);
   if (timer)
     timer->end(stream);

@@ -12,13 +12,14 @@ struct __align__(32) KdNode {
 };
 struct KdIndex {
   KdNode *nodes = nullptr;      // 2^levels - 1 internal nodes, heap order (children of i: 2i+1, 2i+2)
-  double *leaf_pts = nullptr;   // [leaf][dim][32] fp64, +inf in unused slots
+  double *leaf_pts = nullptr;   // [leaf][dim][32 * ppl] fp64, +inf in unused slots
   float *leaf_f32 = nullptr;    // [leaf][dim][slots] the same coordinates rounded to fp32: what the searches read first
-  uint32_t *leaf_idx = nullptr; // [leaf][32] insertion index (local to the handle), PRGPU_INVALID_INDEX if unused
+  uint32_t *leaf_idx = nullptr; // [leaf][32 * ppl] insertion index (local to the handle), PRGPU_INVALID_INDEX if unused
   float *root_cell = nullptr;   // lo[8], hi[8] of the root cell
   unsigned long long *visited = nullptr; // leaves visited by the searches so far (when count_visits)
   uint32_t n = 0;               // nodes covered (0: no index)
   int levels = 0, dim = 0;
+  int ppl = 2;                  // leaf capacity = 32 * ppl slots (chosen by kd_build from the node count)
   bool count_visits = true;
   float build_ms = 0.f;
   unsigned builds = 0;

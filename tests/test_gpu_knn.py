@@ -362,14 +362,17 @@ def test_kd_fp32_leaf_filter_changes_nothing(P, O, monkeypatch, scale, offset):
     pts[5000:6000] = pts[:1000]                                   # duplicates
     q = rng.uniform(-np.pi, np.pi, size=(64, 7)) * scale + offset
     q[:16] = pts[rng.integers(0, n, 16)]
-    tree = P.KnnIndex(7)
-    tree.add(pts)
-    tree.set_search_mode(3)
-    for k in (1, 16):
-        oi, od = O.knn(pts, q, k, nthreads=8)
-        for f32 in ("1", "0"):
-            monkeypatch.setenv("PRGPU_KD_F32", f32)
-            gi, gd = tree.nearest_k(q, k)
-            assert np.array_equal(gi, oi) and np.array_equal(gd, od), (k, f32)
-    assert tree.index_stats()["indexed_nodes"] == n
-    tree.close()
+    oracle = {k: O.knn(pts, q, k, nthreads=8) for k in (1, 16)}
+    for ppl in ("2", "3"):                                         # leaf capacity 64 / 96 (kd_build picks by fill)
+        monkeypatch.setenv("PRGPU_KD_PPL", ppl)
+        tree = P.KnnIndex(7)
+        tree.add(pts)
+        tree.set_search_mode(3)
+        for k in (1, 16):
+            oi, od = oracle[k]
+            for f32 in ("1", "0"):
+                monkeypatch.setenv("PRGPU_KD_F32", f32)
+                gi, gd = tree.nearest_k(q, k)
+                assert np.array_equal(gi, oi) and np.array_equal(gd, od), (k, f32, ppl)
+        assert tree.index_stats()["indexed_nodes"] == n
+        tree.close()
