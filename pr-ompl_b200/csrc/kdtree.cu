@@ -426,7 +426,8 @@ template <int DIM, bool F32, int KD_PPL_>
 __global__ void __launch_bounds__(KD_WARPS * 32, KD_MINB)
 kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict__ leaf_pts,
                       const float *__restrict__ leaf_f32,
-                      const uint32_t *__restrict__ leaf_idx, const float *__restrict__ root_cell, int levels,
+                      const uint32_t *__restrict__ leaf_idx, const float *__restrict__ root_cell,
+                      const uint32_t first_leaf, // 2^levels - 1: heap index of the first leaf
                       uint32_t index_base, const double *__restrict__ queries, uint32_t nq, int k, int qpb,
                       uint32_t *__restrict__ idx_out, double *__restrict__ dist_out,
                       unsigned long long *__restrict__ visited, const KdPeerOut po) {
@@ -435,7 +436,6 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
   __shared__ KdMail mail[KD_WARPS];
   __shared__ uint32_t idle; // bit w: warp w waits for work
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t first_leaf = (1u << levels) - 1u;
   const uint32_t ALL = KD_WARPS >= 32 ? 0xFFFFFFFFu : (1u << (KD_WARPS & 31)) - 1u;
   // ---- set-up: slot w <- query blockIdx.x * qpb + w ----
   if (w < qpb) {
@@ -562,12 +562,14 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
             stk_rd = rd_far;
           }
           ++sp;
-          if (far >= first_leaf) { // (the rows the pop will read first: the fp32 copy in the filtered form)
-            const size_t row0 = (size_t)(far - first_leaf) * DIM * KD_LEAF;
-            const char *base = F32 ? reinterpret_cast<const char *>(leaf_f32 + row0)
-                                   : reinterpret_cast<const char *>(leaf_pts + row0);
-            if (lane * 128 < DIM * KD_LEAF * (F32 ? 4 : 8))
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(base + lane * 128));
+          if (far >= first_leaf) { // (the block the pop will read first -- the fp32 copy in the filtered form --
+                                   //  towards L2: one bulk prefetch for the whole contiguous block)
+            if (lane == 0) {
+              const size_t row0 = (size_t)(far - first_leaf) * DIM * KD_LEAF;
+              const char *base = F32 ? reinterpret_cast<const char *>(leaf_f32 + row0)
+                                     : reinterpret_cast<const char *>(leaf_pts + row0);
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(DIM * KD_LEAF * (F32 ? 4 : 8)));
+            }
           } else if (lane < 4) {
             const uint64_t idx = (((uint64_t)far + 1) << lane) - 1;
             if (idx < first_leaf)
@@ -814,6 +816,7 @@ kd_search_team_kernel(const KdNode *__restrict__ nodes, const double *__restrict
   if (visited && lane == 0 && nvis)
     atomicAdd(visited, nvis);
 }
+
 } // namespace
 
 void KdIndex::release() {
@@ -942,25 +945,26 @@ template <int D, bool F32, int PPL>
 void kd_launch_team_one(const KdIndex &kd, unsigned tblocks, uint32_t index_base, const double *queries_dev, uint32_t nq,
                         int k, int qpb, uint32_t *idx_dev, double *dist_dev, const KdPeerOut &po, cudaStream_t stream) {
   kd_search_team_kernel<D, F32, PPL><<<tblocks, KD_WARPS * 32, 0, stream>>>(
-      kd.nodes, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx, kd.root_cell, kd.levels, index_base, queries_dev, nq, k, qpb,
-      idx_dev, dist_dev, kd.count_visits ? kd.visited : nullptr, po);
+      kd.nodes, kd.leaf_pts, kd.leaf_f32, kd.leaf_idx, kd.root_cell, (1u << kd.levels) - 1u, index_base, queries_dev, nq, k,
+      qpb, idx_dev, dist_dev, kd.count_visits ? kd.visited : nullptr, po);
 }
 template <int D>
 void kd_launch_team_dim(const KdIndex &kd, bool f32, unsigned tblocks, uint32_t index_base, const double *queries_dev,
                         uint32_t nq, int k, int qpb, uint32_t *idx_dev, double *dist_dev, const KdPeerOut &po,
                         cudaStream_t stream) {
 #define KD_GO(F, P) kd_launch_team_one<D, F, P>(kd, tblocks, index_base, queries_dev, nq, k, qpb, idx_dev, dist_dev, po, stream)
-  if (kd.ppl == 3) {
-    if (f32)
-      KD_GO(true, 3);
-    else
-      KD_GO(false, 3);
-  } else {
-    if (f32)
-      KD_GO(true, 2);
-    else
-      KD_GO(false, 2);
+#define KD_GO2(P)                                                                                  \
+  case P:                                                                                          \
+    if (f32)                                                                                       \
+      KD_GO(true, P);                                                                              \
+    else                                                                                           \
+      KD_GO(false, P);                                                                             \
+    break;
+  switch (kd.ppl) {
+    KD_GO2(2)
+    KD_GO2(3)
   }
+#undef KD_GO2
 #undef KD_GO
 }
 bool kd_launch_team(const KdIndex &kd, bool f32, unsigned tblocks, uint32_t index_base, const double *queries_dev,
@@ -985,17 +989,18 @@ bool kd_launch_team(const KdIndex &kd, bool f32, unsigned tblocks, uint32_t inde
 }
 bool kd_launch_single(const KdIndex &kd, unsigned blocks, uint32_t index_base, const double *queries_dev, uint32_t nq,
                       int k, uint32_t *idx_dev, double *dist_dev, cudaStream_t stream) {
+#define KD_S(D, P)                                                                                                  \
+  case P:                                                                                                           \
+    kd_search_kernel<D, P><<<blocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell,   \
+                                                                 kd.levels, index_base, queries_dev, nq, k, idx_dev, \
+                                                                 dist_dev, kd.count_visits ? kd.visited : nullptr); \
+    break;
   switch (kd.dim) {
 #define KD_CASE(D)                                                                                                  \
   case D:                                                                                                           \
-    if (kd.ppl == 3)                                                                                                \
-      kd_search_kernel<D, 3><<<blocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell, \
-                                                                   kd.levels, index_base, queries_dev, nq, k, idx_dev, \
-                                                                   dist_dev, kd.count_visits ? kd.visited : nullptr); \
-    else                                                                                                            \
-      kd_search_kernel<D, 2><<<blocks, KD_WARPS * 32, 0, stream>>>(kd.nodes, kd.leaf_pts, kd.leaf_idx, kd.root_cell, \
-                                                                   kd.levels, index_base, queries_dev, nq, k, idx_dev, \
-                                                                   dist_dev, kd.count_visits ? kd.visited : nullptr); \
+    switch (kd.ppl) {                                                                                               \
+      KD_S(D, 2) KD_S(D, 3)                                                                                         \
+    }                                                                                                               \
     return true;
     KD_CASE(1)
     KD_CASE(2)
@@ -1027,9 +1032,15 @@ int kd_search(const KdIndex &kd, uint32_t index_base, const double *queries_dev,
   if (team_env != 0 && KD_WARPS >= 2) {
     // queries per block: all KD_WARPS warps own a query when the batch alone fills the machine; smaller batches
     // get several warps per query from the start (PRGPU_KD_TEAM = queries per block, 0 = the single-warp kernel)
-    int qpb = KD_WARPS;
-    while (qpb > 1 && (uint64_t)nq * KD_WARPS < (uint64_t)qpb * 4096)
-      qpb >>= 1;
+    // ... so that the blocks of the batch fill every block slot of the machine once: ceil(nq / slots)
+    static int slots = 0;
+    if (!slots) {
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      slots = std::max(1, sms) * KD_MINB;
+    }
+    int qpb = (int)std::min<uint64_t>(KD_WARPS, ((uint64_t)nq + slots - 1) / slots);
     if (team_env > 0)
       qpb = std::min(team_env, (int)KD_WARPS);
     const unsigned tblocks = (nq + qpb - 1) / qpb;

@@ -370,7 +370,7 @@ def test_kd_fp32_leaf_filter_changes_nothing(P, O, monkeypatch, scale, offset):
         tree.set_search_mode(3)
         for k in (1, 16):
             oi, od = oracle[k]
-            for f32 in ("1", "0"):
+            for f32 in ("1", "0"):                                 # filtered form (default), fp64-only form
                 monkeypatch.setenv("PRGPU_KD_F32", f32)
                 gi, gd = tree.nearest_k(q, k)
                 assert np.array_equal(gi, oi) and np.array_equal(gd, od), (k, f32, ppl)
