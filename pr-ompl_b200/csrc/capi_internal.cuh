@@ -21,6 +21,14 @@ struct DevBuf {
     bytes = need;
     return PRGPU_OK;
   }
+  // for tables that are rebuilt a little larger many times (the NNF band): grow geometrically, so that the number of
+  // cudaFree + cudaMalloc pairs of several hundred MB -- each a device-wide sync, at times hundreds of ms -- stays
+  // logarithmic
+  int reserve_grow(size_t need) {
+    if (need <= bytes)
+      return PRGPU_OK;
+    return reserve(need + need / 2 > 2 * bytes ? need + need / 2 : 2 * bytes);
+  }
   void release() {
     if (p)
       cudaFree(p);

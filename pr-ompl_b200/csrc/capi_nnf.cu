@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cfloat>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -116,12 +117,23 @@ int nnf_build_band(prgpu_nnf *h, cudaStream_t s) {
   PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
   h->band_cells = last_off + last_w;
   h->band_full = h->band_cells == (uint64_t)R * V;
-  if ((rc = h->d_Bc.reserve(std::max<size_t>((size_t)h->band_cells * 8, 16))) != PRGPU_OK)
+  // The band is rebuilt a little wider several times per solve (the goal cost creeps up with every knocked-out
+  // edge).  A cudaFree + cudaMalloc pair of several hundred MB is a device-wide sync that at times takes hundreds of
+  // ms, so the two cell tables are sized ONCE for the whole R x V table when that is a small part of the free memory
+  // (3.9 GB each at the benchmark size, of 180 GB), and grow geometrically otherwise.
+  size_t want = std::max<size_t>((size_t)h->band_cells * 8, 16);
+  if (want > h->d_Bc.bytes) {
+    size_t free_b = 0, total_b = 0;
+    const size_t full = (size_t)R * V * 8;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && full <= free_b / 8)
+      want = full;
+  }
+  if ((rc = h->d_Bc.reserve_grow(want)) != PRGPU_OK)
     return rc;
   h->bg.Bc = h->d_Bc.as<double>();
   h->bg.hop = nullptr;
   if (h->band_cells < (1ull << 36) && h->V < NNF_HOP_MAX_V) {
-    if ((rc = h->d_hop.reserve(std::max<size_t>((size_t)h->band_cells * 8, 16))) != PRGPU_OK)
+    if ((rc = h->d_hop.reserve_grow(std::max<size_t>(want, h->d_Bc.bytes))) != PRGPU_OK)
       return rc;
     h->bg.hop = h->d_hop.as<unsigned long long>();
   }
@@ -788,12 +800,27 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
     h->host_state_current = false;
     if (goal_cost_trace && (rc = h->d_trace.reserve(std::max<size_t>((size_t)max_lazy_iters * 8, 16))) != PRGPU_OK)
       return rc;
+    // PRGPU_NNF_TRACE=1: one line per launch on stderr (host clock; every step below ends in a stream sync)
+    static const bool trace = getenv("PRGPU_NNF_TRACE") != nullptr;
+    auto now_ms = []() {
+      return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    double t_prev = now_ms();
+    auto lapse = [&](const char *what, uint32_t a, uint32_t b) {
+      if (!trace)
+        return;
+      cudaStreamSynchronize(s);
+      const double t = now_ms();
+      fprintf(stderr, "[nnf] %-10s %9.3f ms  %u %u\n", what, t - t_prev, a, b);
+      t_prev = t;
+    };
     while (true) {
       if (!h->band_valid) {
         if (h->tau_ub == 0.0 && (rc = nnf_initial_tau(h, s)) != PRGPU_OK)
           return rc;
         if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
           return rc;
+        lapse("band", 0, 0);
       }
       if (!h->bg.hop)
         return fail(PRGPU_ELIMIT, "nnf_solve: band too large for the hop words");
@@ -802,6 +829,7 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
                                 h->sm_count, s, &h->timer);
         if (rc != PRGPU_OK)
           return rc;
+        lapse("sweep", h->dirty_level, h->Lv);
         h->dirty_level = h->Lv;
       }
       NnfLazyDev z;
@@ -837,6 +865,7 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
       NnfLazyOut o;
       PRGPU_CUDA_TRY(cudaMemcpyAsync(&o, h->d_lazy_out.p, sizeof(o), cudaMemcpyDeviceToHost, s));
       PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
+      lapse("lazy", o.iters, o.status);
       iters += o.iters;
       h->total_iters += o.iters;
       h->n_evaluated += o.n_evaluated;
@@ -855,10 +884,11 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
         continue;
       }
       if (o.status == NNF_LAZY_NEED_REBUILD) {
-        static const double headroom = getenv("PRGPU_NNF_TAU_HEADROOM") ? atof(getenv("PRGPU_NNF_TAU_HEADROOM")) : 1.03;
+        static const double headroom = getenv("PRGPU_NNF_TAU_HEADROOM") ? atof(getenv("PRGPU_NNF_TAU_HEADROOM")) : 1.15;
         h->tau_ub = o.goal_cost < 1e300 ? o.goal_cost * headroom : h->tau_ub * 2.0;
         if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
           return rc;
+        lapse("reband", 0, 0);
         continue;
       }
       if (o.status == NNF_LAZY_ERROR)
@@ -928,7 +958,7 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
         // a finite cost found inside the band is an upper bound of the optimum: use it directly
         // (with some headroom: the goal cost creeps up with every knocked-out edge, and a rebuild costs
         // about ten searches)
-        static const double headroom = getenv("PRGPU_NNF_TAU_HEADROOM") ? atof(getenv("PRGPU_NNF_TAU_HEADROOM")) : 1.03;
+        static const double headroom = getenv("PRGPU_NNF_TAU_HEADROOM") ? atof(getenv("PRGPU_NNF_TAU_HEADROOM")) : 1.15;
         h->tau_ub = goalCost < 1e300 ? goalCost * headroom : h->tau_ub * 2.0;
         if ((rc = nnf_build_band(h, s)) != PRGPU_OK)
           return rc;
