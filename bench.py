@@ -624,14 +624,16 @@ def measure_knn(env, args, want_cpu):
         roof = dict(hbm_block(kms), bound="hbm", kernel="kd_search_team_kernel", kernel_ms=kms,
                     traffic=None if not summ else summ.get("dram_bytes"),
                     issue_slots_busy_pct_ncu=None if not summ else summ.get("issue_slots_busy_pct"),
-                    binds="latency: a query walks ~300 tree nodes and ~125 leaves of 64 slots, a dependent chain (the "
-                          "warps of a block take subtrees over from one another); the algorithmic bytes are SURVEY "
-                          "§8(d)'s brute-force figure (the whole tree once), the search touches ~0.08 % of the tree per "
-                          "query but different leaves for different queries: `traffic` (ncu, per launch) is 3.6x the "
-                          "algorithmic bytes and the kernel moves it at about half the HBM peak",
+                    binds="issue slots + latency: a query walks ~250 tree nodes and ~90 leaves (96 slots each, read as "
+                          "their fp32 copy; ~7 % of the half-leaves hold a candidate and are read again in fp64), a "
+                          "dependent chain per query (the warps of a block take subtrees over from one another); ncu: "
+                          "issue slots 64 % busy, SMs active 76 % of the kernel (the slowest queries set its end). The "
+                          "algorithmic bytes are SURVEY §8(d)'s brute-force figure (the whole tree once); the search "
+                          "touches ~0.07 % of the tree per query but different leaves for different queries: `traffic` "
+                          "(ncu, per launch) is 1.7x the algorithmic bytes",
                     traffic_gbs=None if not summ or not summ.get("dram_bytes") else summ["dram_bytes"] / (kms * 1e-3) / 1e9,
                     index={"build_ms": ist["build_ms"], "builds": ist["builds"],
-                           "leaves_of_64_per_query": ist["leaves_visited"] / max(1, ist["index_calls"] * Q)})
+                           "leaves_per_query": ist["leaves_visited"] / max(1, ist["index_calls"] * Q)})
     else:
         roof = scan_roofline(kms)
     extra = {"phase_breakdown": breakdown, "search_path": "k-d index" if indexed else "brute-force scan"}

@@ -855,6 +855,8 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
       z.out = h->d_lazy_out.as<NnfLazyOut>();
       z.max_iters = max_lazy_iters - iters;
       z.epoch = h->lazy_epoch;
+      static const uint32_t wave_budget = getenv("PRGPU_NNF_WAVE_BUDGET") ? (uint32_t)atoi(getenv("PRGPU_NNF_WAVE_BUDGET")) : 2048u;
+      z.wave_budget = std::min<uint32_t>(wave_budget, 2048u); // (the kernel's level list holds 2048 columns)
       z.tau_ub = h->tau_ub;
       z.check_resolution = h->params.check_resolution;
       z.band_full = h->band_full ? 1 : 0;

@@ -808,7 +808,7 @@ nnf_lazysp_kernel(const DeviceWorld *__restrict__ wp, const NnfBandDev g, const 
       }
       s_par = par; // (every thread writes the same value; push() reads it)
       wave += cnt;
-      if (wave > LAZY_WAVE_BUDGET || s_overflow) { // everything before level L is consistent; the host re-sweeps
+      if (wave > z.wave_budget || s_overflow) { // everything before level L is consistent; the host re-sweeps
         bailed = true;                             // levels >= L with the whole GPU
         break;
       }

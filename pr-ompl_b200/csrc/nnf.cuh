@@ -91,6 +91,7 @@ struct NnfLazyDev {
   double *trace;                       // goal cost of every search, or NULL
   NnfLazyOut *out;
   uint32_t max_iters, epoch;
+  uint32_t wave_budget;                // columns one block repairs per knock-out before the whole-GPU sweep takes over
   double tau_ub, check_resolution;
   int band_full, dof;
 };
