@@ -1058,8 +1058,10 @@ def measure_nnf(env, args, want_cpu):
 
 def measure_dropin_a(env, args, want_cpu):
     """One planner instance at a time through the UNMODIFIED reference planner source over the GPU
-    NearestNeighbors / validators (oracle/_ref/libdropin_a.so): a launch + sync per growTree.  SURVEY §7.3
-    item 3: this path is latency-bound and loses to the CPU for small trees -- measured, not hidden."""
+    NearestNeighbors / validators (oracle/_ref/libdropin_a.so): a launch + sync per nearest / checkMotion / add.
+    SURVEY §7.3 item 3: this path is latency-bound -- one call is a few tens of microseconds whatever the GPU does
+    in it (arguments and results travel through a mapped host window, tiny launches read the world's tables in
+    place) -- and about breaks even with one CPU thread on the reference's small trees; measured, not hidden."""
     import plugin_lib
     np, synth = env.np, env.synth
     L = plugin_lib.dropin()

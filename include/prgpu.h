@@ -55,6 +55,12 @@ int prgpu_device_count(void); /* number of CUDA devices, 0 if none; never fails 
  * Distances are RealVectorStateSpace::distance bit for bit (sequential sum of squared
  * differences in double, no FMA, IEEE sqrt).
  * ---------------------------------------------------------------------------------- */
+/* One-at-a-time use (a host planner: add(1 node), nearest(1 query) per growTree): calls of <= 64 queries on trees of
+ * <= 65536 nodes and adds of <= 8 points pass their arguments and results through a window of mapped pinned host
+ * memory instead of copy calls.  A small prgpu_knn_add() returns once its append is QUEUED on the handle's stream:
+ * every later call on the handle is ordered behind it (the *_device entry points wait for it when given another
+ * stream), and an error of the append surfaces at the next synchronising call.  PRGPU_NO_HOST_WINDOW=1 keeps the
+ * copy path for every size. */
 typedef struct prgpu_knn prgpu_knn_t;
 int prgpu_knn_create(int device, int dim, uint64_t capacity_hint, prgpu_knn_t **out);
 int prgpu_knn_destroy(prgpu_knn_t *h);

@@ -68,6 +68,19 @@ int prgpu_device_count(void) {
 
 /* ---------------------------------------------- K1 ---------------------------------------------- */
 
+} // extern "C"
+int knn_settle(prgpu_knn *h) {
+  if (h->ring_used) {
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->ring_used = 0;
+  }
+  return PRGPU_OK;
+}
+static bool host_window_on() { // PRGPU_NO_HOST_WINDOW: tiny calls take the copy path too (A/B tests)
+  return getenv("PRGPU_NO_HOST_WINDOW") == nullptr;
+}
+extern "C" {
+
 // Grows the tree buffers.  Callers may append on their own stream (prgpu_knn_add_device), so nothing here
 // may be ordered only against h->stream: the first allocation zeroes xmax2 and waits for it; a regrow waits
 // for the whole device (pending appends into the old buffers, on whatever stream they were issued) before
@@ -195,6 +208,7 @@ int prgpu_knn_destroy(prgpu_knn_t *h) {
   h->d_lo.release();
   h->d_idx.release();
   h->d_dist.release();
+  h->win.release();
   h->timer.destroy();
   if (h->stream)
     cudaStreamDestroy(h->stream);
@@ -255,7 +269,10 @@ int prgpu_knn_add_device(prgpu_knn_t *h, const double *pts_dev, uint64_t n, void
   if (h->n + n >= 0xFFFFFFFFull)
     return fail(PRGPU_ELIMIT, "knn_add: more than 2^32-2 points");
   PRGPU_CUDA_TRY(cudaSetDevice(h->device));
-  int rc = knn_reserve(h, h->n + n);
+  int rc;
+  if ((cudaStream_t)stream != h->stream && (rc = knn_settle(h)) != PRGPU_OK)
+    return rc;
+  rc = knn_reserve(h, h->n + n);
   if (rc != PRGPU_OK)
     return rc;
   rc = knn_transpose_append(h->dim, pts_dev, n, h->pts, h->ptsf, h->xmax2, h->stride, h->n, (cudaStream_t)stream);
@@ -276,7 +293,19 @@ int prgpu_knn_add(prgpu_knn_t *h, const double *pts, uint64_t n) {
     return PRGPU_OK;
   PRGPU_CUDA_TRY(cudaSetDevice(h->device));
   const size_t bytes = (size_t)n * h->dim * sizeof(double);
-  int rc = h->stage.reserve(bytes);
+  int rc;
+  if (n <= 8 && host_window_on() && h->win.ensure(KNN_WIN_BYTES)) {
+    // a planner's add(): the points go into the window's ring and the append kernel reads them from there; no
+    // copy call and no synchronisation -- the next search is ordered behind it on the same stream.  A slot is
+    // reused only after a synchronisation of that stream (every host-buffer search is one).
+    if (h->ring_used + n > KNN_WIN_RING_SLOTS && (rc = knn_settle(h)) != PRGPU_OK)
+      return rc;
+    const size_t off = KNN_WIN_RING + (size_t)h->ring_used * 8 * sizeof(double);
+    std::memcpy(h->win.host + off, pts, bytes);
+    h->ring_used += (uint32_t)n;
+    return prgpu_knn_add_device(h, reinterpret_cast<const double *>(h->win.dev + off), n, h->stream);
+  }
+  rc = h->stage.reserve(bytes);
   if (rc != PRGPU_OK)
     return rc;
   const uint64_t CH = 1ull << 20; // nodes per pipeline stage
@@ -286,6 +315,7 @@ int prgpu_knn_add(prgpu_knn_t *h, const double *pts, uint64_t n) {
     if (rc != PRGPU_OK)
       return rc;
     PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->ring_used = 0;
     return PRGPU_OK;
   }
   // Bulk loads: the stages are copied on a second stream and transposed (fp64 SoA + the two mirrors) as
@@ -457,6 +487,11 @@ int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64
   if (nq > 0x7FFFFFFFull)
     return fail(PRGPU_ELIMIT, "knn_nearest_k: too many queries in one call");
   PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  if ((cudaStream_t)stream != h->stream) {
+    const int rs = knn_settle(h);
+    if (rs != PRGPU_OK)
+      return rs;
+  }
   double *dd = dist_dev;
   if (!dd) {
     int rc = h->d_dist.reserve((size_t)nq * k * sizeof(double));
@@ -477,6 +512,24 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
     return PRGPU_OK;
   PRGPU_CUDA_TRY(cudaSetDevice(h->device));
   int rc;
+  if (nq <= KNN_WIN_MAX_Q && h->n <= KNN_WIN_MAX_NODES && host_window_on() && h->win.ensure(KNN_WIN_BYTES)) {
+    // a planner's nearest(): query and result travel through the mapped window (see HostWindow)
+    std::memcpy(h->win.host + KNN_WIN_Q, queries, (size_t)nq * h->dim * sizeof(double));
+    if (lo)
+      std::memcpy(h->win.host + KNN_WIN_LO, lo, (size_t)nq * sizeof(uint32_t));
+    rc = knn_dispatch(h, reinterpret_cast<const double *>(h->win.dev + KNN_WIN_Q), (uint32_t)nq, k,
+                      lo ? reinterpret_cast<const uint32_t *>(h->win.dev + KNN_WIN_LO) : nullptr,
+                      reinterpret_cast<uint32_t *>(h->win.dev + KNN_WIN_IDX),
+                      reinterpret_cast<double *>(h->win.dev + KNN_WIN_DIST), h->stream, nullptr);
+    if (rc != PRGPU_OK)
+      return rc;
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->ring_used = 0;
+    std::memcpy(idx, h->win.host + KNN_WIN_IDX, (size_t)nq * k * sizeof(uint32_t));
+    if (dist)
+      std::memcpy(dist, h->win.host + KNN_WIN_DIST, (size_t)nq * k * sizeof(double));
+    return PRGPU_OK;
+  }
   if ((rc = h->d_q.reserve((size_t)nq * h->dim * sizeof(double))) != PRGPU_OK)
     return rc;
   if ((rc = h->d_idx.reserve((size_t)nq * k * sizeof(uint32_t))) != PRGPU_OK)
@@ -503,6 +556,7 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
     PRGPU_CUDA_TRY(cudaMemcpyAsync(dist, h->d_dist.p, (size_t)nq * k * sizeof(double),
                                    cudaMemcpyDeviceToHost, h->stream));
   PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->ring_used = 0;
   return PRGPU_OK;
 }
 
@@ -607,6 +661,25 @@ int prgpu_world_create(int device, int dof, const double *dh, int ns, const int3
   }
   const double bt = rmax + delta;
   H.box_thr2 = (float)(bt * bt * (1.0 + 1e-6));
+  { // the fp32 arm table of the filter kernels: spheres grouped by the frame they ride on (counting sort, stable)
+    ArmTableF32 &arm = H.arm_f32;
+    std::memset(&arm, 0, sizeof(arm));
+    for (int i = 0; i < WORLD_MAX_DOF; ++i)
+      for (int c = 0; c < 5; ++c)
+        arm.dh[i][c] = (float)H.dh[i][c];
+    int n = 0;
+    for (int i = 0; i <= H.dof; ++i) {
+      arm.link_first[i] = (uint8_t)n;
+      for (int sp = 0; sp < H.S; ++sp)
+        if (H.sphere_link[sp] == i) {
+          arm.sphere[n] = make_float4((float)H.sphere_local[sp][0], (float)H.sphere_local[sp][1],
+                                      (float)H.sphere_local[sp][2], H.sphere_r[sp]);
+          arm.sphere_id[n] = (uint8_t)sp;
+          ++n;
+        }
+    }
+    arm.link_first[H.dof + 1] = (uint8_t)n;
+  }
 
   // ---- broad phase: uniform grid over the inflated obstacle boxes --------------------------------
   std::vector<uint32_t> cell_start;
@@ -825,6 +898,7 @@ int prgpu_world_destroy(prgpu_world_t *w) {
   w->d_b.release();
   w->d_valid.release();
   w->d_pose.release();
+  w->win.release();
   for (void *p : {(void *)w->cm_scratch.owed, (void *)w->cm_scratch.off, w->cm_scratch.tmp, (void *)w->cm_scratch.item_edge,
                   (void *)w->cm_scratch.gaps, (void *)w->cm_scratch.queue, (void *)w->cm_scratch.queue_n,
                   (void *)w->cm_scratch.pair_ref, w->cm_scratch.pair_centre, (void *)w->cm_scratch.pair_n})
@@ -881,6 +955,19 @@ int prgpu_check_motion_batch(prgpu_world_t *w, const double *from, const double 
       (rc = w->d_valid.reserve(n)) != PRGPU_OK)
     return rc;
   const uint64_t CH = 1ull << 18; // edges per pipeline stage
+  if (n <= 32 && host_window_on() && w->win.ensure(8192)) {
+    // a planner's checkMotion(): the edge and the verdict travel through the mapped window (see HostWindow)
+    std::memcpy(w->win.host, from, bytes);
+    std::memcpy(w->win.host + 2048, to, bytes);
+    rc = check_motion_launch(w->host, w->dev, reinterpret_cast<const double *>(w->win.dev),
+                             reinterpret_cast<const double *>(w->win.dev + 2048), n, resolution, mode, check_first,
+                             w->win.dev + 4096, w->sm_count, w->stream, &w->timer, &w->cm_scratch);
+    if (rc != PRGPU_OK)
+      return rc;
+    PRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+    std::memcpy(valid, w->win.host + 4096, n);
+    return PRGPU_OK;
+  }
   if (n < 2 * CH) {
     PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_a.p, from, bytes, cudaMemcpyHostToDevice, w->stream));
     PRGPU_CUDA_TRY(cudaMemcpyAsync(w->d_b.p, to, bytes, cudaMemcpyHostToDevice, w->stream));

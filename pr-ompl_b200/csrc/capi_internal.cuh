@@ -37,6 +37,42 @@ struct DevBuf {
   }
   template <class T> T *as() { return static_cast<T *>(p); }
 };
+// A small window of mapped pinned host memory (zero copy).  A planner that drives the structures one call at a
+// time -- the reference's own RRTConnect over GpuNearestNeighbors / GpuMotionValidator: one nearest(), one
+// checkMotion(), one add() per growTree -- pays launch + copy latency, not bandwidth: three pageable cudaMemcpyAsync
+// calls cost more than the kernel between them.  Tiny calls therefore put their arguments into this window, the
+// kernels read them and write their results through the device alias of the same pages, and the one stream
+// synchronisation the call needs anyway makes the results visible.
+struct HostWindow {
+  unsigned char *host = nullptr, *dev = nullptr;
+  size_t bytes = 0;
+  bool failed = false; // mapped allocations refused once: stay on the copy path
+  bool ensure(size_t need) {
+    if (host && bytes >= need)
+      return true;
+    if (failed)
+      return false;
+    release();
+    void *p = nullptr, *d = nullptr;
+    if (cudaHostAlloc(&p, need, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (p)
+        cudaFreeHost(p);
+      failed = true;
+      return false;
+    }
+    host = static_cast<unsigned char *>(p);
+    dev = static_cast<unsigned char *>(d);
+    bytes = need;
+    return true;
+  }
+  void release() {
+    if (host)
+      cudaFreeHost(host);
+    host = dev = nullptr;
+    bytes = 0;
+  }
+};
 } // namespace prgpu
 
 struct prgpu_knn {
@@ -70,7 +106,15 @@ struct prgpu_knn {
   prgpu::DevBuf stage, d_q, d_lo, d_idx, d_dist;
   cudaStream_t copy_stream = nullptr;       // uploads of bulk prgpu_knn_add calls
   std::vector<cudaEvent_t> copy_events;
+  prgpu::HostWindow win;                    // tiny host-buffer calls (see HostWindow)
+  uint32_t ring_used = 0;                   // points of small prgpu_knn_add calls whose append has not been synchronised
 };
+// layout of prgpu_knn::win
+constexpr size_t KNN_WIN_Q = 0, KNN_WIN_LO = 4096, KNN_WIN_IDX = 8192, KNN_WIN_DIST = 16384, KNN_WIN_RING = 32768,
+                 KNN_WIN_BYTES = 65536;
+constexpr uint32_t KNN_WIN_MAX_Q = 64, KNN_WIN_RING_SLOTS = 512, KNN_WIN_MAX_NODES = 1u << 16;
+// appends of small host adds may still be in flight on h->stream: wait for them before another stream uses the tree
+int knn_settle(prgpu_knn *h);
 
 struct prgpu_world {
   int device = 0, sm_count = 0;
@@ -83,6 +127,7 @@ struct prgpu_world {
   prgpu::KernelTimer timer;
   cudaStream_t copy_stream = nullptr;       // uploads of the staged host-buffer checkMotion
   std::vector<cudaEvent_t> copy_events;
+  prgpu::HostWindow win;                    // tiny host-buffer calls (see HostWindow)
 };
 
 

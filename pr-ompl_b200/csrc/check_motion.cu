@@ -17,12 +17,32 @@
 #include <algorithm>
 #include <cstdlib>
 #include "check_motion.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 #include "edge_plan.cuh"
 
 namespace prgpu {
 namespace {
 
 constexpr int CM_THREADS = 128;
+
+// cudaFuncSetAttribute costs microseconds; a planner's single-edge call is a few of them long.  The opt-in is
+// remembered per kernel and device and raised only when a larger world asks for more.
+template <class K> cudaError_t set_smem_once(K kern, size_t smem) {
+  static std::map<std::pair<const void *, int>, size_t> have; // (kernels of one signature share this instantiation)
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &h = have[std::make_pair(reinterpret_cast<const void *>(kern), dev)];
+  if (smem <= h)
+    return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    h = smem;
+  return e;
+}
 #ifndef CM_MINB
 #define CM_MINB 8 // resident blocks per SM the two FK-heavy kernels of the pair-dealt pipeline are compiled for
 #endif
@@ -34,7 +54,7 @@ check_motion_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict
                     uint8_t *__restrict__ valid) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
-  const ObstacleTables tabs = load_tables(w, s_obs);
+  const ObstacleTables tabs = load_tables(w, s_obs, n > 64); // (a planner's single edge: tables read in place)
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -601,7 +621,7 @@ __global__ void __launch_bounds__(CM_THREADS)
 is_valid_kernel(const DeviceWorld *__restrict__ wp, const double *__restrict__ qs, uint64_t n, uint8_t *__restrict__ valid) {
   const DeviceWorld &w = *wp;
   extern __shared__ float4 s_obs[];
-  const ObstacleTables tabs = load_tables(w, s_obs);
+  const ObstacleTables tabs = load_tables(w, s_obs, n > 1024); // (a handful of states: tables read in place)
   __syncthreads();
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
@@ -895,7 +915,7 @@ int check_motion_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const do
     timer->begin(stream);
   PRGPU_SP_DISPATCH(w.S, {
     auto kern = check_motion_kernel<SP>;
-    PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PRGPU_CUDA_TRY(set_smem_once(kern, smem));
     kern<<<(unsigned)blocks, CM_THREADS, smem, stream>>>(w_dev, from_dev, to_dev, n, resolution, mode,
                                                          check_first, valid_dev); PRGPU_COUNT_LAUNCH(1);
   });
@@ -925,7 +945,7 @@ int is_valid_launch(const DeviceWorld &w, const DeviceWorld *w_dev, const double
     blocks = 148 * 8;
   PRGPU_SP_DISPATCH(w.S, {
     auto kern = is_valid_kernel<SP>;
-    PRGPU_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PRGPU_CUDA_TRY(set_smem_once(kern, smem));
     kern<<<(unsigned)blocks, CM_THREADS, smem, stream>>>(w_dev, q_dev, n, valid_dev); PRGPU_COUNT_LAUNCH(1);
   });
   PRGPU_CUDA_TRY(cudaGetLastError());

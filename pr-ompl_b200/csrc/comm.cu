@@ -238,6 +238,11 @@ int prgpu_knn_nearest_k_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, const do
     return PRGPU_OK;
   if (nq > 0x7FFFFFFFull)
     return fail(PRGPU_ELIMIT, "knn_nearest_k_sharded: too many queries in one call");
+  if ((cudaStream_t)stream_ != h->stream) { // small host adds may still be appending on the handle's stream
+    const int rs = knn_settle(h);
+    if (rs != PRGPU_OK)
+      return rs;
+  }
   PRGPU_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t ent = (size_t)nq * k;
@@ -389,6 +394,8 @@ int prgpu_knn_nearest_k_query_sharded_device(prgpu_knn_t *h, prgpu_comm_t *c, co
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t ent = (size_t)nq_local * k;
   int rc;
+  if (stream != h->stream && (rc = knn_settle(h)) != PRGPU_OK) // small host adds may still be appending
+    return rc;
   // ---- fused form: the index search writes every result row straight into every rank's window (NVLink peer
   //      stores from the search kernel's epilogue); then one tiny kernel exchanges arrival flags; no collective
   //      call and no staging copy on the path.  Taken when the windows are mapped and the index answers.

@@ -17,6 +17,12 @@ namespace prgpu {
 constexpr int WORLD_MAX_DOF = PRGPU_MAX_DIM;
 constexpr int WORLD_MAX_S = PRGPU_MAX_LINK_SPHERES;
 
+struct ArmTableF32 { // fp32 copy of the arm for the filter path (built once by prgpu_world_create; kernels copy it to shared memory)
+  float dh[WORLD_MAX_DOF][5];        // a, d, cos(alpha), sin(alpha), theta0
+  float4 sphere[WORLD_MAX_S];        // local x,y,z and radius + delta, ordered by link
+  uint8_t sphere_id[WORLD_MAX_S];    // original sphere index of slot j
+  uint8_t link_first[WORLD_MAX_DOF + 2]; // spheres of frame i are slots [link_first[i], link_first[i+1])
+};
 struct DeviceWorld {
   int dof, S, n_os, n_ob;
   double dh[WORLD_MAX_DOF][5];       // a, d, cos(alpha), sin(alpha), theta0
@@ -53,6 +59,7 @@ struct DeviceWorld {
   // rho[i]: upper bound, over all configurations and link spheres, of the distance between a sphere centre
   // and the axis of joint i -- a unit change of joint i moves no sphere centre by more than rho[i]
   float rho[WORLD_MAX_DOF];
+  ArmTableF32 arm_f32;               // the fp32 arm table the filter kernels keep in shared memory
 };
 constexpr int WORLD_GRID_MAX_CELLS = 8192;
 constexpr int WORLD_GRID_MAX_ITEMS = 32768;
@@ -367,12 +374,6 @@ __device__ __forceinline__ void load_obstacles(const DeviceWorld &w, float4 *s_o
 // delta bounds |fp32 distance - exact distance| of a (sphere, obstacle) pair.  Three outcomes per
 // candidate pair: farther than r+R+delta -> free; nearer than r+R-delta -> colliding (both certain in
 // fp32); in between -> the fp64 chain and the specification's formula decide.
-struct ArmTableF32 { // fp32 copy of the arm for the filter path (shared memory)
-  float dh[WORLD_MAX_DOF][5];        // a, d, cos(alpha), sin(alpha), theta0
-  float4 sphere[WORLD_MAX_S];        // local x,y,z and radius + delta, ordered by link
-  uint8_t sphere_id[WORLD_MAX_S];    // original sphere index of slot j
-  uint8_t link_first[WORLD_MAX_DOF + 2]; // spheres of frame i are slots [link_first[i], link_first[i+1])
-};
 struct ObstacleTables { // shared-memory views
   const float4 *os, *ob;
   const uint32_t *cell_start;
@@ -386,44 +387,44 @@ __host__ __device__ __forceinline__ size_t obstacle_tables_bytes(const DeviceWor
   return b;
 }
 // cooperative load of all tables; returns the views (call from every thread, then __syncthreads)
-__device__ __forceinline__ ObstacleTables load_tables(const DeviceWorld &w, float4 *smem) {
+// `stage` = false (tiny launches: a planner's single checkMotion / isValid): only the arm table goes to shared
+// memory, the obstacle tables and the grid are read where they lie -- copying up to 100 KB per block would cost
+// several times the few look-ups such a launch makes.
+__device__ __forceinline__ ObstacleTables load_tables(const DeviceWorld &w, float4 *smem, bool stage = true) {
   ObstacleTables t;
   float4 *s_os = smem, *s_ob = smem + w.n_os;
-  load_obstacles(w, s_os, s_ob);
-  t.os = s_os;
-  t.ob = s_ob;
+  t.os = w.os_f;
+  t.ob = w.ob_f;
+  if (stage) {
+    load_obstacles(w, s_os, s_ob);
+    t.os = s_os;
+    t.ob = s_ob;
+  }
   t.cell_start = nullptr;
   t.cell_item = nullptr;
   ArmTableF32 *arm = reinterpret_cast<ArmTableF32 *>(smem + w.n_os + 2 * w.n_ob);
   t.arm = arm;
-  if (threadIdx.x < WORLD_MAX_DOF)
-    for (int c = 0; c < 5; ++c)
-      arm->dh[threadIdx.x][c] = (float)w.dh[threadIdx.x][c];
-  if (threadIdx.x == 0) { // spheres grouped by the frame they ride on (counting sort, stable)
-    int n = 0;
-    for (int i = 0; i <= w.dof; ++i) {
-      arm->link_first[i] = (uint8_t)n;
-      for (int s = 0; s < w.S; ++s)
-        if (w.sphere_link[s] == i) {
-          arm->sphere[n] = make_float4((float)w.sphere_local[s][0], (float)w.sphere_local[s][1],
-                                       (float)w.sphere_local[s][2], w.sphere_r[s]);
-          arm->sphere_id[n] = (uint8_t)s;
-          ++n;
-        }
-    }
-    arm->link_first[w.dof + 1] = (uint8_t)n;
+  { // (spheres grouped by the frame they ride on: prepared by prgpu_world_create)
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&w.arm_f32);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(arm);
+    for (uint32_t i = threadIdx.x; i < sizeof(ArmTableF32) / 4; i += blockDim.x)
+      dst[i] = src[i];
   }
   if (w.grid_n[0] > 0) {
-    const uint32_t ncell = (uint32_t)(w.grid_n[0] * w.grid_n[1] * w.grid_n[2]);
-    uint32_t *cs = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(arm) +
-                                                ((sizeof(ArmTableF32) + 15) & ~(size_t)15));
-    uint16_t *ci = reinterpret_cast<uint16_t *>(cs + ncell + 1);
-    for (uint32_t i = threadIdx.x; i <= ncell; i += blockDim.x)
-      cs[i] = w.cell_start[i];
-    for (uint32_t i = threadIdx.x; i < w.grid_items; i += blockDim.x)
-      ci[i] = w.cell_item[i];
-    t.cell_start = cs;
-    t.cell_item = ci;
+    t.cell_start = w.cell_start;
+    t.cell_item = w.cell_item;
+    if (stage) {
+      const uint32_t ncell = (uint32_t)(w.grid_n[0] * w.grid_n[1] * w.grid_n[2]);
+      uint32_t *cs = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(arm) +
+                                                  ((sizeof(ArmTableF32) + 15) & ~(size_t)15));
+      uint16_t *ci = reinterpret_cast<uint16_t *>(cs + ncell + 1);
+      for (uint32_t i = threadIdx.x; i <= ncell; i += blockDim.x)
+        cs[i] = w.cell_start[i];
+      for (uint32_t i = threadIdx.x; i < w.grid_items; i += blockDim.x)
+        ci[i] = w.cell_item[i];
+      t.cell_start = cs;
+      t.cell_item = ci;
+    }
   }
   return t;
 }

@@ -129,3 +129,18 @@ def test_item_table_overflow_changes_nothing(P, synth, gpu_world, monkeypatch):
         assert np.array_equal(gpu_world.check_motion_batch(a, b, 0.05, mode=P.MODE_NNF_ALPHA), ref_nnf), cap
     monkeypatch.delenv("PRGPU_CM_ITEM_CAP")
     assert np.array_equal(gpu_world.check_motion_batch(a, b, 0.01), ref)
+
+
+@pytest.mark.parametrize("mode_name", ["MODE_OMPL_DISCRETE", "MODE_NNF_ALPHA"])
+def test_single_edge_calls_through_the_host_window(P, synth, gpu_world, monkeypatch, mode_name):
+    """A planner's checkMotion() is one edge per call: the edge and the verdict travel through a mapped host window.
+    One edge at a time, 7 at a time and the copy path (PRGPU_NO_HOST_WINDOW) all give the batch's verdicts."""
+    mode = getattr(P, mode_name)
+    a, b = synth.edges(91, 120, max_len=1.2)
+    ref = gpu_world.check_motion_batch(a, b, 0.02, mode=mode)       # 120 edges: the copy path
+    one = np.concatenate([gpu_world.check_motion_batch(a[i:i + 1], b[i:i + 1], 0.02, mode=mode) for i in range(120)])
+    seven = np.concatenate([gpu_world.check_motion_batch(a[i:i + 7], b[i:i + 7], 0.02, mode=mode) for i in range(0, 120, 7)])
+    assert np.array_equal(one, ref) and np.array_equal(seven, ref)
+    monkeypatch.setenv("PRGPU_NO_HOST_WINDOW", "1")
+    one = np.concatenate([gpu_world.check_motion_batch(a[i:i + 1], b[i:i + 1], 0.02, mode=mode) for i in range(120)])
+    assert np.array_equal(one, ref)

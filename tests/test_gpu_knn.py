@@ -376,3 +376,46 @@ def test_kd_fp32_leaf_filter_changes_nothing(P, O, monkeypatch, scale, offset):
                 assert np.array_equal(gi, oi) and np.array_equal(gd, od), (k, f32, ppl)
         assert tree.index_stats()["indexed_nodes"] == n
         tree.close()
+
+
+@pytest.mark.parametrize("window", [True, False])
+def test_small_calls_through_the_host_window(P, O, monkeypatch, window):
+    """A planner drives the structure one call at a time: add(1 node), nearest(1 query).  Those calls hand their
+    arguments to the kernels through a mapped host window (no copy calls; small adds are not synchronised -- the next
+    search is ordered behind them).  Same answers as the copy path (PRGPU_NO_HOST_WINDOW) and the oracle: 1300 adds
+    in a row (the window's ring of 512 slots wraps twice, the tree buffer regrows), then adds and searches interleaved."""
+    if not window:
+        monkeypatch.setenv("PRGPU_NO_HOST_WINDOW", "1")
+    rng = np.random.default_rng(77)
+    pts = rng.uniform(-np.pi, np.pi, size=(1500, 7))
+    pts[700:720] = pts[100:120]                                   # duplicates: ties by insertion index
+    q = rng.uniform(-np.pi, np.pi, size=(64, 7))
+    tree = P.KnnIndex(7)
+    for i in range(1300):
+        tree.add(pts[i:i + 1])
+    gi, gd = tree.nearest_k(q, 5)                                 # 64 queries: still a window call
+    oi, od = O.knn(pts[:1300], q, 5, nthreads=4)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    for i in range(1300, 1500):
+        tree.add(pts[i:i + 1])
+        if i % 3 == 0:
+            tree.add(pts[i:i + 1] + 1e-3)                         # an extra node now and then (both go to the oracle)
+        qq = q[i % 64:i % 64 + 1]
+        gi, gd = tree.nearest_k(qq, 3)
+        have = tree.points(0, tree.size())
+        oi, od = O.knn(have, qq, 3, nthreads=1)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od), i
+    # a foreign stream after small adds: the appends are waited for
+    import torch
+    tree.add(pts[:3] + 0.5)
+    have = np.vstack([have, pts[:3] + 0.5])
+    s = torch.cuda.Stream()
+    qd = torch.from_numpy(q).cuda()
+    i_ = torch.empty((64, 4), dtype=torch.int32, device="cuda")
+    d_ = torch.empty((64, 4), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    tree.nearest_k_device(qd, 64, 4, i_, d_, stream=s.cuda_stream)
+    s.synchronize()
+    oi, od = O.knn(have, q, 4, nthreads=4)
+    assert np.array_equal(i_.cpu().numpy().astype(np.uint32), oi) and np.array_equal(d_.cpu().numpy(), od)
+    tree.close()
