@@ -995,6 +995,7 @@ def measure_nnf(env, args, want_cpu):
     info = g.band_info()
     r = g.solve(max_lazy_iters=20000) if not r1["solved"] else r1
     solve_s = time.perf_counter() - t0
+    info_final = g.band_info()
     nnf_clocks = sampler.stop()
     launches = env.launches() - l0
     iters = int(r1["lazy_iters"] + (0 if r1["solved"] else r["lazy_iters"]))
@@ -1013,7 +1014,7 @@ def measure_nnf(env, args, want_cpu):
                    "lazy_iterations": iters, "ms_per_lazy_iteration": solve_s / max(1, iters) * 1e3,
                    "solved": int(r["solved"]), "final_frechet_error": r["final_error"],
                    "edges_evaluated": int(r["n_evaluated"]), "edges_in_collision": int(r["n_collisions"]),
-                   "band": info, "l2": "band table 8 B/cell larger than L2 on the first search"},
+                   "band": info, "band_at_the_end": info_final, "l2": "band table 8 B/cell larger than L2 on the first search"},
         "roofline": {"bound": "hbm", "achieved": algo / (first_search_ms * 1e-3) / 1e9, "peak": env.hbm_peak,
                      "unit": "GB/s", "frac": algo / (first_search_ms * 1e-3) / 1e9 / env.hbm_peak,
                      "traffic": None if not summ else summ.get("dram_bytes"), "kernel": "nnf_flow_dp_kernel",
