@@ -653,6 +653,34 @@ def measure_knn(env, args, want_cpu):
         step()
         step()
 
+    # ---- throughput with two batches in flight (one GPU): a 4096-query batch is one query per warp slot of the
+    #      machine, so the SMs idle for a quarter of the kernel while the heaviest queries are finished; a second
+    #      stream lets the next batch's blocks take the freed slots.  Not the headline (a step there is one batch at
+    #      a time); reported because a serving loop would issue batches this way ----
+    if indexed and world == 1 and not args.no_extra:
+        s2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        q2 = [q_dev, torch.from_numpy(synth.cloud(2, Q)).to(dev)]
+        o2 = [(torch.empty_like(idx), torch.empty_like(dd)) for _ in range(2)]
+        tree.set_profiling(False)
+        torch.cuda.synchronize()
+        for j in range(4):
+            tree.nearest_k_device(q2[j & 1], Q, k, o2[j & 1][0], o2[j & 1][1], stream=s2[j & 1].cuda_stream)
+        torch.cuda.synchronize()
+        nb = 2 * max(args.steps, 10)
+        t0 = time.perf_counter()
+        for j in range(nb):
+            tree.nearest_k_device(q2[j & 1], Q, k, o2[j & 1][0], o2[j & 1][1], stream=s2[j & 1].cuda_stream)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        local_search(q_dev, Q, k, idx, dd)
+        torch.cuda.synchronize()
+        extra["two_batches_in_flight"] = {
+            "queries_per_s": nb * Q / dt, "ms_per_batch": dt / nb * 1e3, "batches": nb,
+            "identical_to_one_at_a_time": bool(torch.equal(o2[0][0], idx)) and bool(torch.equal(o2[0][1], dd)),
+            "note": "batches issued alternately on two streams (host clock around the whole run, synchronised on "
+                    "both sides); every batch is a complete prgpu_knn_nearest_k_device call"}
+        tree.set_profiling(True)
+
     # ---- strong scaling of ONE configs[1] batch (Q queries in total), both partitionings ----
     if world > 1 and not args.no_extra:
         strong = {}
@@ -1023,7 +1051,9 @@ def measure_nnf(env, args, want_cpu):
                      "note": "the FIRST search of the solve (every band cell recomputed); later searches recompute "
                              "only the levels at or after a knocked-out edge and are latency-bound on the level chain"},
         "e2e": {"value": 1.0 / (setup_s + solve_s), "unit": unit,
-                "h2d_bytes_per_step": int(ik.nbytes + ref.nbytes), "d2h_bytes_per_step": int(g.n_vertices * 19 * 8)},
+                "h2d_bytes_per_step": int(ik.nbytes + ref.nbytes),
+                # the kNN table of the NN graph (host-side graph construction) + the path and one record per launch
+                "d2h_bytes_per_step": int(len(ik) * k * 4 + len(r.get("path", [])) * 4 + 96 * max(1, launches))},
         "gpu_launches_per_step": launches, "clocks": nnf_clocks, "extra": {},
     }
     ls = g.loop_stats()

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "capi_internal.cuh"
 #include "rrtc_batch.cuh"
@@ -52,6 +53,62 @@ int select_device(int device, int *sm_count) {
 } // namespace prgpu
 
 using namespace prgpu;
+
+// ---- DevBuf's allocator: the device's stream-ordered pool, kept warm (capi_internal.cuh) ----
+namespace {
+struct PoolState {
+  cudaStream_t stream = nullptr;
+  int state = 0; // 0: untried, 1: in use, -1: unavailable (plain cudaMalloc)
+};
+PoolState g_pool[64];
+std::mutex g_pool_mu;
+PoolState *pool_for_current_device() {
+  static const bool off = getenv("PRGPU_NO_POOL") != nullptr;
+  int dev = -1;
+  if (off || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+    return nullptr;
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  PoolState &ps = g_pool[dev];
+  if (ps.state == 0) {
+    ps.state = -1;
+    int supported = 0;
+    cudaMemPool_t pool = nullptr;
+    unsigned long long never = ~0ull;
+    if (cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && supported &&
+        cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never) == cudaSuccess &&
+        cudaStreamCreateWithFlags(&ps.stream, cudaStreamNonBlocking) == cudaSuccess)
+      ps.state = 1;
+    else
+      cudaGetLastError();
+  }
+  return ps.state == 1 ? &ps : nullptr;
+}
+} // namespace
+namespace prgpu {
+cudaError_t dev_alloc(void **p, size_t bytes) {
+  if (PoolState *ps = pool_for_current_device()) {
+    cudaError_t e = cudaMallocAsync(p, bytes, ps->stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(ps->stream); // usable on every stream from here on
+    if (e == cudaSuccess || e == cudaErrorMemoryAllocation)
+      return e;
+    cudaGetLastError();
+  }
+  return cudaMalloc(p, bytes);
+}
+void dev_free(void *p) {
+  if (!p)
+    return;
+  if (PoolState *ps = pool_for_current_device()) {
+    cudaDeviceSynchronize(); // cudaFree's semantics: nothing on the device still uses the block
+    if (cudaFreeAsync(p, ps->stream) == cudaSuccess)
+      return;
+    cudaGetLastError();
+  }
+  cudaFree(p);
+}
+} // namespace prgpu
 
 extern "C" {
 

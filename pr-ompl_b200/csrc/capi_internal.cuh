@@ -7,17 +7,25 @@
 
 namespace prgpu {
 // grow-only device buffer
+// Device memory of the handles' work buffers comes from the device's stream-ordered pool with the release threshold
+// raised to "never" (capi.cu): a planner object is created and destroyed per planning query, and cudaMalloc / cudaFree
+// of its ~30 buffers (up to GBs) cost 0.1 s per set-up at random; from the pool a re-created handle gets the previous
+// one's memory back.  The calls keep cudaMalloc / cudaFree semantics (the memory is usable on every stream when
+// dev_alloc returns; dev_free waits for the device first).  PRGPU_NO_POOL=1: plain cudaMalloc / cudaFree.
+cudaError_t dev_alloc(void **p, size_t bytes);
+void dev_free(void *p);
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
+  bool plain = false; // plain cudaMalloc memory (buffers handed to NCCL / other libraries)
   int reserve(size_t need) {
     if (need <= bytes)
       return PRGPU_OK;
     if (p)
-      cudaFree(p);
+      plain ? (void)cudaFree(p) : dev_free(p);
     p = nullptr;
     bytes = 0;
-    PRGPU_CUDA_TRY(cudaMalloc(&p, need));
+    PRGPU_CUDA_TRY(plain ? cudaMalloc(&p, need) : dev_alloc(&p, need));
     bytes = need;
     return PRGPU_OK;
   }
@@ -31,7 +39,7 @@ struct DevBuf {
   }
   void release() {
     if (p)
-      cudaFree(p);
+      plain ? (void)cudaFree(p) : dev_free(p);
     p = nullptr;
     bytes = 0;
   }

@@ -92,6 +92,23 @@ __global__ void nnf_block_edge_kernel(NnfEdgeRec *edge, uint32_t slot, uint8_t *
 }
 
 // (re)build the band for the current tau_ub: per-vertex row interval, column offsets, packed records
+// host copies of the vertex states (and, device form, FK poses), fetched on first use
+int nnf_fetch_vertices(prgpu_nnf *h) {
+  if (!h->states.empty() || h->V == 0)
+    return PRGPU_OK;
+  PRGPU_CUDA_TRY(cudaSetDevice(h->device));
+  std::vector<double> st((size_t)h->V * h->dof), po;
+  PRGPU_CUDA_TRY(cudaMemcpyAsync(st.data(), h->d_states.p, st.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (!h->host_form) {
+    po.resize((size_t)h->V * 12);
+    PRGPU_CUDA_TRY(cudaMemcpyAsync(po.data(), h->d_pose.p, po.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->states.swap(st);
+  h->pose.swap(po);
+  return PRGPU_OK;
+}
+
 int nnf_build_band(prgpu_nnf *h, cudaStream_t s) {
   const int R = h->R;
   const uint32_t V = h->V;
@@ -260,6 +277,16 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
     device = w->device;
   PRGPU_CUDA_TRY(cudaSetDevice(device));
   const int dof = w ? w->host.dof : dof_in, k = params->num_nn, D = params->discretization;
+  // PRGPU_NNF_TRACE=1: the set-up's phases on stderr (host clock)
+  const bool trace = getenv("PRGPU_NNF_TRACE") != nullptr;
+  double t_prev = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  auto lapse = [&](const char *what) {
+    if (!trace)
+      return;
+    const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    fprintf(stderr, "[nnf] setup %-12s %9.3f ms\n", what, t - t_prev);
+    t_prev = t;
+  };
 
   prgpu_nnf *h = new prgpu_nnf();
   h->world = w;
@@ -389,6 +416,7 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
     NNF_TRY(rc);
   }
 
+  lapse("knn");
   // ---- NN graph in creation order (:407-464) -----------------------------------------------------
   const uint32_t c0 = 0, c1 = 1;
   auto ikVertex = [](uint32_t i) { return 2 + i; };
@@ -397,6 +425,14 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
   for (uint32_t i = 0; i < ML; ++i)
     h->edges.emplace_back(ikVertex(M0 + i), c1); // :435
   std::vector<uint32_t> sub_src, sub_dst, sub_step, sub_layer;
+  {
+    const size_t n_sub = (size_t)nq * k * D;
+    h->edges.reserve((size_t)M0 + ML + n_sub + (size_t)nq * k);
+    sub_src.reserve(n_sub);
+    sub_dst.reserve(n_sub);
+    sub_step.reserve(n_sub);
+    sub_layer.reserve(n_sub);
+  }
   std::vector<uint32_t> layer_of_ik(N);
   {
     uint32_t i = 0;
@@ -436,6 +472,7 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
   h->V = V;
   h->E = E;
 
+  lapse("expand");
   // ---- vertex data on the device: states, FK poses ----------------------------------------------
   NNF_TRY(h->d_states.reserve((size_t)V * dof * 8));
   NNF_TRY(h->d_pose.reserve((size_t)V * 12 * 8));
@@ -467,13 +504,10 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
     d_step.release();
     NNF_TRY(rc);
   }
-  h->states.resize((size_t)V * dof);
-  NNF_CUDA(cudaMemcpyAsync(h->states.data(), h->d_states.p, (size_t)V * dof * 8, cudaMemcpyDeviceToHost, s));
-  if (w) {
-    h->pose.resize((size_t)V * 12);
-    NNF_CUDA(cudaMemcpyAsync(h->pose.data(), h->d_pose.p, (size_t)V * 12 * 8, cudaMemcpyDeviceToHost, s));
-  }
+  // (host copies of the vertex states / poses -- 185 MB at the benchmark size -- are fetched on first use:
+  //  prgpu_nnf_get_vertices and the host LazySP loop; the device-resident loop never needs them)
 
+  lapse("subsample");
   // ---- predecessors (by vertex, creation order), topological levels, level-sorted order ---------
   h->pred_off_v.assign(V + 1, 0);
   for (auto &e : h->edges)
@@ -531,6 +565,7 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
   h->slot_of_eid.assign(E, 0);
   for (uint32_t o = 0; o < E; ++o)
     h->slot_of_eid[pred_eid[o]] = o;
+  lapse("csr");
   NNF_TRY(upload(h->d_lvl_start, lvl_start, s));
   NNF_TRY(upload(h->d_level, level_s, s));
   NNF_TRY(upload(h->d_pred_off, pred_off_s, s));
@@ -596,6 +631,7 @@ int nnf_create_common(prgpu_world_t *w, int device, int dof_in, const prgpu_nnf_
   NNF_TRY(h->d_cost.reserve(16));
   NNF_TRY(h->timer.enable(true));
   NNF_CUDA(cudaStreamSynchronize(s));
+  lapse("uploads");
 
   NnfGraphDev &g = h->g;
   g.R = R;
@@ -707,6 +743,9 @@ int prgpu_nnf_get_knn(prgpu_nnf_t *h, uint32_t *knn) {
 int prgpu_nnf_get_vertices(prgpu_nnf_t *h, double *states, double *pose12) {
   if (!h)
     return fail(PRGPU_EINVAL, "nnf_get_vertices: NULL handle");
+  const int rcf = nnf_fetch_vertices(h);
+  if (rcf != PRGPU_OK)
+    return rcf;
   if (states)
     std::memcpy(states, h->states.data(), h->states.size() * 8);
   if (pose12) {
@@ -908,6 +947,8 @@ int prgpu_nnf_solve(prgpu_nnf_t *h, uint32_t max_lazy_iters, prgpu_nnf_result *r
     PRGPU_CUDA_TRY(cudaStreamSynchronize(s));
   } else {
     int rc0 = nnf_state_to_host(h);
+    if (rc0 == PRGPU_OK)
+      rc0 = nnf_fetch_vertices(h); // evaluateEdge batches and mFinalError of the host loop read the host copies
     if (rc0 != PRGPU_OK)
       return rc0;
     h->dev_state_current = false;

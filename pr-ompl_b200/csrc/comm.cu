@@ -73,7 +73,7 @@ struct prgpu_comm {
   ncclComm_t nccl = nullptr;
   prgpu_allgather_fn custom = nullptr;
   void *ctx = nullptr;
-  DevBuf send, recv;
+  DevBuf send, recv; // plain cudaMalloc memory (set at creation): these are handed to NCCL
   uint32_t *flags_host = nullptr; // pinned, nranks words
   uint64_t redo_steps = 0;
   // symmetric windows (prgpu_comm_enable_peer_windows): every rank's window mapped into this process over
@@ -141,6 +141,7 @@ int prgpu_comm_init(int device, int rank, int nranks, const void *id128, prgpu_c
   if ((rc = nccl_load()) != PRGPU_OK)
     return rc;
   prgpu_comm *c = new prgpu_comm();
+  c->send.plain = c->recv.plain = true;
   c->device = device;
   c->rank = rank;
   c->nranks = nranks;
@@ -172,6 +173,7 @@ int prgpu_comm_init_custom(int device, int rank, int nranks, prgpu_allgather_fn 
       return rc;
   }
   prgpu_comm *c = new prgpu_comm();
+  c->send.plain = c->recv.plain = true;
   c->device = device; // -1: host-only communicator (plumbing tests without a GPU); compute entry points refuse it
   c->rank = rank;
   c->nranks = nranks;
