@@ -79,6 +79,11 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
                         uint32_t *idx, double *dist);
 int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64_t nq, int k,
                                const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, void *stream);
+/* Batches in flight.  Searches served by the k-d index (below) use no per-handle scratch: device-buffer calls on
+ * one handle may be issued on several streams at once (different output buffers), and the next batch's blocks then
+ * take the SM slots the tail of the previous one leaves idle -- 1.5x the one-at-a-time throughput at 4096 queries
+ * over 1e7 nodes (bench.py: extra.two_batches_in_flight).  The brute-force paths share the handle's scratch:
+ * one call at a time there. */
 /* Search strategy.  By default batched calls (>= 128 queries, k <= 16, dim <= 7, >= 8192 points) use an
  * TF32 tensor-core filter scan followed by an fp32 re-cut and an exact fp64 re-rank of the few surviving
  * candidates, with a per-query proof that no discarded point can precede them; unproven queries are

@@ -419,3 +419,32 @@ def test_small_calls_through_the_host_window(P, O, monkeypatch, window):
     oi, od = O.knn(have, q, 4, nthreads=4)
     assert np.array_equal(i_.cpu().numpy().astype(np.uint32), oi) and np.array_equal(d_.cpu().numpy(), od)
     tree.close()
+
+
+def test_two_batches_in_flight_on_two_streams(P, O):
+    """Indexed searches use no per-handle scratch: two batches issued on two streams at once (include/prgpu.h,
+    "Batches in flight") give what each gives alone."""
+    import torch
+    rng = np.random.default_rng(5150)
+    n = 1 << 18
+    pts = rng.uniform(-np.pi, np.pi, size=(n, 7))
+    tree = P.KnnIndex(7)
+    tree.add(pts)
+    tree.set_search_mode(3)
+    qs = [rng.uniform(-np.pi, np.pi, size=(1500, 7)) for _ in range(2)]
+    want = [O.knn(pts, q, 16, nthreads=8) for q in qs]
+    tree.nearest_k(qs[0][:64], 16)                                # builds the index
+    assert tree.index_stats()["indexed_nodes"] == n
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    qd = [torch.from_numpy(q).cuda() for q in qs]
+    out = [(torch.empty((1500, 16), dtype=torch.int32, device="cuda"),
+            torch.empty((1500, 16), dtype=torch.float64, device="cuda")) for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(6):                                          # alternately, never waiting in between
+        j = rep & 1
+        tree.nearest_k_device(qd[j], 1500, 16, out[j][0], out[j][1], stream=streams[j].cuda_stream)
+    torch.cuda.synchronize()
+    for j in range(2):
+        assert np.array_equal(out[j][0].cpu().numpy().astype(np.uint32), want[j][0])
+        assert np.array_equal(out[j][1].cpu().numpy(), want[j][1])
+    tree.close()
