@@ -441,15 +441,16 @@ int prgpu_knn_get_points(prgpu_knn_t *h, uint64_t first, uint64_t n, double *pts
 // best choice in hindsight; a structure that is refilled or appended to between searches never pays for a
 // build -- appends and clear() make the index stale and reset the account).  prgpu_knn_build_index() builds it
 // at once for callers that know the tree is final (a benchmark's set-up, a roadmap).
-// Measured on B200 (scripts/kdbench.py): an indexed search costs 0.2-0.6 ms for <= 4096 queries (latency-bound
-// team search); the TF32 filter scan ~0.1 ms + n*nq / 1.05e10 ms, the exact fp64 kernel (below 128 queries)
+// Measured on B200 (scripts/kd_var.py, 1e7 nodes): an indexed search costs 0.20 / 0.37 / 2.08 ms for 512 / 4096 /
+// 32768 queries (team search with the fp32 leaf filter: 0.17 ms + 4.4 us * log2(n / 1024) per 1000 queries); the
+// TF32 filter scan ~0.1 ms + n*nq / 1.05e10 ms, the exact fp64 kernel (below 128 queries)
 // ~ n*nq / 2.3e8 ms.
 static const uint32_t KD_MIN_NODES = 1u << 17;
 static double brute_ms(uint64_t n, uint32_t nq) {
   const double pairs = (double)n * nq;
   return nq >= 128 ? 0.1 + pairs / 1.05e10 : pairs / 2.3e8;
 }
-static double indexed_ms(uint64_t n, uint32_t nq) { return 0.19 + nq * 7e-6 * std::max(1.0, std::log2((double)n / 1024.0)); }
+static double indexed_ms(uint64_t n, uint32_t nq) { return 0.17 + nq * 4.4e-6 * std::max(1.0, std::log2((double)n / 1024.0)); }
 static bool kd_pays(uint64_t n, uint32_t nq) { // the indexed search is expected to beat the brute-force one by > 10 %
   return nq >= 8 && brute_ms(n, nq) > 1.1 * indexed_ms(n, nq);
 }
