@@ -33,7 +33,10 @@
 namespace prgpu {
 namespace {
 
-constexpr int RB_WARPS = 8;            // queries in flight per block (first kernel) / team size (second)
+#ifndef RB_WARPS_N
+#define RB_WARPS_N 8
+#endif
+constexpr int RB_WARPS = RB_WARPS_N;   // queries in flight per block (first kernel) / team size (second)
 constexpr int RB_THREADS = RB_WARPS * 32;
 #ifndef RB_CUT
 #define RB_CUT 256                     // samples after which an unsolved query moves to the team kernel
