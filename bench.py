@@ -829,7 +829,9 @@ def measure_knn(env, args, want_cpu):
             "l2": f"inputs larger than L2 ({n_local * 56 / 1e6:.0f} MB tree shard per GPU, fp64 SoA)",
             "e2e_timing": "host clock around synchronous C-ABI calls, max over ranks; the tree is the "
                           "NearestNeighbors structure's state (as in the CPU reference arm), pinned host queries in / "
-                          "host results out every step; e2e.with_tree_reupload also refills the tree from host memory",
+                          "host results out every step (one GPU: the caller's result buffers are pinned, so the search kernel "
+                          "writes the d2h bytes into them itself as queries finish -- zero copy -- instead of two copies "
+                          "after the search); e2e.with_tree_reupload also refills the tree from host memory",
             "arithmetic": "TF32 tensor-core filter -> fp32 re-cut -> fp64 exact distances + proof; results "
                           "bit-identical to the fp64 reference",
             "filter_fallback_queries": stats["fallback_queries"],

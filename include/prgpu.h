@@ -77,6 +77,8 @@ int prgpu_knn_get_points(prgpu_knn_t *h, uint64_t first, uint64_t n, double *pts
  * dist: nq x k (+inf padded) or NULL. */
 int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int k, const uint32_t *lo,
                         uint32_t *idx, double *dist);
+/* (Host form: when idx / dist are pinned host memory and the k-d index serves the call, the search kernel writes the
+ * result rows straight into them -- the transfer rides under the search instead of following it as copies.) */
 int prgpu_knn_nearest_k_device(prgpu_knn_t *h, const double *queries_dev, uint64_t nq, int k,
                                const uint32_t *lo_dev, uint32_t *idx_dev, double *dist_dev, void *stream);
 /* Batches in flight.  Searches served by the k-d index (below) use no per-handle scratch: device-buffer calls on

@@ -596,6 +596,26 @@ int prgpu_knn_nearest_k(prgpu_knn_t *h, const double *queries, uint64_t nq, int 
     return rc;
   PRGPU_CUDA_TRY(cudaMemcpyAsync(h->d_q.p, queries, (size_t)nq * h->dim * sizeof(double),
                                  cudaMemcpyHostToDevice, h->stream));
+  if (!lo && host_window_on() && knn_index_ready(h, (uint32_t)nq, k)) {
+    // An indexed search writes a query's row once, when its last worker is done.  If the caller's result buffers
+    // are pinned host memory the kernel writes the rows there itself (zero copy): the transfer rides under the
+    // search instead of following it as two copies.
+    cudaPointerAttributes ai, ad;
+    std::memset(&ai, 0, sizeof(ai));
+    std::memset(&ad, 0, sizeof(ad));
+    const bool pin_i = cudaPointerGetAttributes(&ai, idx) == cudaSuccess && ai.type == cudaMemoryTypeHost && ai.devicePointer;
+    const bool pin_d = !dist || (cudaPointerGetAttributes(&ad, dist) == cudaSuccess && ad.type == cudaMemoryTypeHost && ad.devicePointer);
+    cudaGetLastError(); // (older drivers report unregistered memory as an error)
+    if (pin_i && pin_d) {
+      rc = knn_dispatch(h, h->d_q.as<double>(), (uint32_t)nq, k, nullptr, static_cast<uint32_t *>(ai.devicePointer),
+                        dist ? static_cast<double *>(ad.devicePointer) : h->d_dist.as<double>(), h->stream, nullptr);
+      if (rc != PRGPU_OK)
+        return rc;
+      PRGPU_CUDA_TRY(cudaStreamSynchronize(h->stream));
+      h->ring_used = 0;
+      return PRGPU_OK;
+    }
+  }
   const uint32_t *lo_dev = nullptr;
   if (lo) {
     if ((rc = h->d_lo.reserve((size_t)nq * sizeof(uint32_t))) != PRGPU_OK)

@@ -448,3 +448,30 @@ def test_two_batches_in_flight_on_two_streams(P, O):
         assert np.array_equal(out[j][0].cpu().numpy().astype(np.uint32), want[j][0])
         assert np.array_equal(out[j][1].cpu().numpy(), want[j][1])
     tree.close()
+
+
+def test_pinned_result_buffers_are_written_by_the_search_itself(P, O):
+    """prgpu_knn_nearest_k with PINNED host result buffers and an indexed search: the kernel writes the rows into
+    the caller's memory (zero copy).  Same rows as with pageable buffers (the copy path) and the oracle."""
+    import torch
+    rng = np.random.default_rng(99)
+    n, nq, k = 1 << 18, 1000, 16
+    pts = rng.uniform(-np.pi, np.pi, size=(n, 7))
+    q = rng.uniform(-np.pi, np.pi, size=(nq, 7))
+    tree = P.KnnIndex(7)
+    tree.add(pts)
+    tree.set_search_mode(3)
+    gi, gd = tree.nearest_k(q, k)                                 # numpy (pageable) buffers; builds the index
+    assert tree.index_stats()["indexed_nodes"] == n
+    oi, od = O.knn(pts, q, k, nthreads=8)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    qp = torch.from_numpy(q).pin_memory()
+    ip = torch.full((nq, k), -1, dtype=torch.int32).pin_memory()
+    dp = torch.full((nq, k), -1.0, dtype=torch.float64).pin_memory()
+    for with_dist in (True, False):
+        ip.fill_(-1)
+        P.capi._check(P.lib().prgpu_knn_nearest_k(tree.h, P.capi._ptr(qp), nq, k, None, P.capi._ptr(ip),
+                                                  P.capi._ptr(dp) if with_dist else None))
+        assert np.array_equal(ip.numpy().astype(np.uint32), oi)
+    assert np.array_equal(dp.numpy(), od)
+    tree.close()
