@@ -375,6 +375,9 @@ int prgpu_diag_mma_tf32_peak(int device, double *tflops);
 int prgpu_diag_knn_scan(prgpu_knn_t *h, const double *queries, uint32_t nq, float *thresh, uint32_t cap, uint32_t *counts,
                         uint32_t *idx /* nq x cap */, float *D /* nq x cap */, float *key32 /* nq x cap */,
                         double *eps /* nq x 2 */);
+/* K1's index: the leaf capacity (slots: 64 or 96) and depth (2^levels leaves) prgpu_knn_build_index takes for n
+ * nodes -- the capacity that leaves the fewest slots of the balanced tree's leaves empty.  Host arithmetic only. */
+int prgpu_diag_kd_leaf_capacity(uint64_t n, int *slots, int *levels);
 /* K2's filter: largest distance between a link-sphere centre from the production fp32 forward-kinematics chain and
  * the fp64 chain of the specification, per state (max_err: n); *delta = the bound prgpu_world_create derived. */
 int prgpu_diag_fk_centre_error(prgpu_world_t *w, const double *states, uint64_t n, double *max_err, double *delta);

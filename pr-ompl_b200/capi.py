@@ -108,6 +108,7 @@ SIGNATURES = {
     "prgpu_nnf_solve": (C.c_int, [c_vp, C.c_uint32, c_vp, c_vp, C.c_uint32, c_vp]),
     "prgpu_diag_knn_scan": (C.c_int, [c_vp, c_vp, C.c_uint32, c_vp, C.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "prgpu_diag_fk_centre_error": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp, C.POINTER(C.c_double)]),
+    "prgpu_diag_kd_leaf_capacity": (C.c_int, [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "prgpu_nnf_create_graph": (C.c_int, [C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.POINTER(c_vp)]),
     "prgpu_nnf_set_weights": (C.c_int, [c_vp, c_vp]),
     "prgpu_nnf_set_edge_evaluator": (C.c_int, [c_vp, c_vp, c_vp]),

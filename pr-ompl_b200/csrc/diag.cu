@@ -2,6 +2,7 @@
 // micro-benchmark of the warp-level TF32 MMA issue rate that K1's scan is measured against.
 #include <algorithm>
 #include "capi_internal.cuh"
+#include "kdtree.cuh"
 
 namespace prgpu {
 unsigned long long g_launch_count = 0;
@@ -33,6 +34,18 @@ __global__ void diag_mma_tf32_kernel(float *out, int iters) {
 using namespace prgpu;
 
 extern "C" {
+
+int prgpu_diag_kd_leaf_capacity(uint64_t n, int *slots, int *levels) {
+  if (!slots || !levels)
+    return prgpu::fail(PRGPU_EINVAL, "diag_kd_leaf_capacity: NULL argument");
+  if (n < 128 || n >= 0xFFFFFFFFull)
+    return prgpu::fail(PRGPU_EINVAL, "diag_kd_leaf_capacity: the index needs 128 .. 2^32-2 nodes");
+  int ppl = 0, L = 0;
+  prgpu::kd_leaf_capacity((uint32_t)n, &ppl, &L);
+  *slots = 32 * ppl;
+  *levels = L;
+  return PRGPU_OK;
+}
 uint64_t prgpu_diag_launch_count(void) { return g_launch_count; }
 
 int prgpu_diag_knn_scan(prgpu_knn_t *h, const double *queries, uint32_t nq, float *thresh, uint32_t cap, uint32_t *counts,

@@ -833,11 +833,9 @@ void KdIndex::release() {
   levels = 0;
 }
 
-int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint32_t n, cudaStream_t stream) {
-  kd.release();
-  if (n < 2 * 32 * KD_PPL_MIN)
-    return fail(PRGPU_EINVAL, "kd_build: too few nodes");
-  // leaf capacity: the one that leaves the fewest empty slots (ties: the smaller leaf)
+// leaf capacity (32 * ppl slots) and tree depth for n nodes: the capacity that leaves the fewest empty slots (ties: the
+// smaller leaf); PRGPU_KD_PPL forces one (tests)
+void kd_leaf_capacity(uint32_t n, int *ppl_out, int *levels_out) {
   int L = 0, ppl = KD_PPL_MIN;
   double best_fill = -1.0;
   for (int c = KD_PPL_MIN; c <= KD_PPL_MAX && n >= 2u * 32u * (unsigned)c; ++c) {
@@ -851,7 +849,7 @@ int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint3
       ppl = c;
     }
   }
-  if (getenv("PRGPU_KD_PPL")) { // (tests: force a capacity)
+  if (getenv("PRGPU_KD_PPL")) {
     const int c = atoi(getenv("PRGPU_KD_PPL"));
     if (c >= KD_PPL_MIN && c <= KD_PPL_MAX && n >= 2u * 32u * (unsigned)c) {
       ppl = c;
@@ -860,6 +858,16 @@ int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint3
         ++L;
     }
   }
+  *ppl_out = ppl;
+  *levels_out = L;
+}
+
+int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint32_t n, cudaStream_t stream) {
+  kd.release();
+  if (n < 2 * 32 * KD_PPL_MIN)
+    return fail(PRGPU_EINVAL, "kd_build: too few nodes");
+  int L = 0, ppl = KD_PPL_MIN;
+  kd_leaf_capacity(n, &ppl, &L);
   const int KD_LEAF = 32 * ppl;
   const uint32_t nleaf = 1u << L;
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -34,6 +34,8 @@ struct KdPeerOut {
   unsigned long long idx_off; // byte offset of the index table inside a window
   int nranks, rank;
 };
+// leaf capacity (32 * ppl slots) and depth kd_build takes for n nodes (n >= 128)
+void kd_leaf_capacity(uint32_t n, int *ppl, int *levels);
 // builds the index over nodes [0, n) of the fp64 SoA buffer; synchronises `stream`
 int kd_build(KdIndex &kd, int dim, const double *pts_soa, uint64_t stride, uint32_t n, cudaStream_t stream);
 // exact k nearest of every query under (sqrt-distance, index); idx = local index + index_base
